@@ -1,0 +1,882 @@
+// rtx_api.cu — implementation of the C-ABI in include/rtx_b200.h: context, scene upload (SoA device buffers +
+// wide BVH build), camera, the wavefront host loop, resolve, and the batch entry points used for parity.
+// There is no CPU fallback anywhere in this library: every arithmetic entry point launches CUDA kernels.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rtx_bvh.hpp"
+#include "rtx_kernels.cuh"
+
+using rtxbvh::Box;
+using rtxbvh::Node4;
+
+static thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct rtx_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::vector<void*> scene_allocs;
+    DevScene S{};
+    bool have_scene = false, have_camera = false;
+    DevCamera C{};
+    int W = 0, H = 0;
+    // accumulation
+    float4 *accum = nullptr, *accum_sq = nullptr;
+    int moments = 0;
+    // path pool
+    Pool pool{};
+    std::vector<void*> pool_allocs;
+    int64_t pool_paths = 1 << 20;
+    Ctl* ctl = nullptr;       // device
+    Ctl* ctl_host = nullptr;  // pinned
+    int count_stats = 0, time_kernels = 1;
+    rtx_stats stats{};
+    double env_total = 0;
+    // scene summary
+    uint32_t tlas_nodes = 0, blas_nodes = 0, n_entries = 0, n_tris = 0;
+    std::vector<cudaEvent_t> events;
+};
+
+static int32_t fail(rtx_ctx* ctx, int32_t code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) return fail(ctx, RTX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+template <class T>
+static int32_t upload(rtx_ctx* ctx, const std::vector<T>& v, const T** out, bool scene = true) {
+    *out = nullptr;
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    void* p = nullptr;
+    CU(cudaMalloc(&p, bytes));
+    if (scene) ctx->scene_allocs.push_back(p);
+    if (!v.empty()) CU(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *out = (const T*)p;
+    return RTX_OK;
+}
+#define UP(vec, field)                                                    \
+    do {                                                                  \
+        int32_t rc_ = upload(ctx, vec, &field);                           \
+        if (rc_ != RTX_OK) return rc_;                                    \
+    } while (0)
+
+static void free_scene(rtx_ctx* ctx) {
+    for (void* p : ctx->scene_allocs) cudaFree(p);
+    ctx->scene_allocs.clear();
+    ctx->have_scene = false;
+}
+static void free_pool(rtx_ctx* ctx) {
+    for (void* p : ctx->pool_allocs) cudaFree(p);
+    ctx->pool_allocs.clear();
+    ctx->pool = Pool{};
+}
+
+struct Scratch {  // RAII device scratch
+    std::vector<void*> ptrs;
+    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+    template <class T>
+    cudaError_t in(T** dev, const T* host, size_t n, cudaStream_t st) {
+        cudaError_t e = cudaMalloc((void**)dev, std::max<size_t>(n * sizeof(T), 16));
+        if (e != cudaSuccess) return e;
+        ptrs.push_back(*dev);
+        if (host && n) e = cudaMemcpyAsync(*dev, host, n * sizeof(T), cudaMemcpyHostToDevice, st);
+        return e;
+    }
+    template <class T>
+    cudaError_t out(T** dev, T* host, size_t n) {
+        *dev = nullptr;
+        if (!host) return cudaSuccess;
+        cudaError_t e = cudaMalloc((void**)dev, std::max<size_t>(n * sizeof(T), 16));
+        if (e == cudaSuccess) ptrs.push_back(*dev);
+        return e;
+    }
+};
+
+extern "C" {
+
+int32_t rtx_abi_version(void) { return RTX_ABI_VERSION; }
+
+const char* rtx_last_error(const rtx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int32_t rtx_create(int32_t device_id, rtx_ctx** out) {
+    if (!out) return fail(nullptr, RTX_ERR_INVALID, "rtx_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, RTX_ERR_CUDA, "rtx_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (device_id < 0 || device_id >= n) return fail(nullptr, RTX_ERR_INVALID, "rtx_create: device %d out of range [0,%d)", device_id, n);
+    rtx_ctx* ctx = new rtx_ctx();
+    ctx->device = device_id;
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&ctx->ctl, sizeof(Ctl))) != cudaSuccess || (e = cudaMallocHost((void**)&ctx->ctl_host, sizeof(Ctl))) != cudaSuccess) {
+        fail(nullptr, RTX_ERR_CUDA, "rtx_create: %s", cudaGetErrorString(e));
+        delete ctx;
+        return RTX_ERR_CUDA;
+    }
+    *out = ctx;
+    return RTX_OK;
+}
+
+int32_t rtx_destroy(rtx_ctx* ctx) {
+    if (!ctx) return RTX_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_scene(ctx);
+    free_pool(ctx);
+    if (ctx->accum) cudaFree(ctx->accum);
+    if (ctx->accum_sq) cudaFree(ctx->accum_sq);
+    if (ctx->ctl) cudaFree(ctx->ctl);
+    if (ctx->ctl_host) cudaFreeHost(ctx->ctl_host);
+    for (auto ev : ctx->events) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return RTX_OK;
+}
+
+int32_t rtx_set_option(rtx_ctx* ctx, const char* key, int64_t value) {
+    if (!ctx || !key) return RTX_ERR_INVALID;
+    std::string k(key);
+    if (k == "pool_paths") {
+        if (value < 1024 || value > (1ll << 26)) return fail(ctx, RTX_ERR_INVALID, "pool_paths out of range");
+        if (value != ctx->pool_paths) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); free_pool(ctx); }
+        ctx->pool_paths = value;
+    } else if (k == "count_stats") ctx->count_stats = value != 0;
+    else if (k == "time_kernels") ctx->time_kernels = value != 0;
+    else return fail(ctx, RTX_ERR_INVALID, "unknown option '%s'", key);
+    return RTX_OK;
+}
+
+// ---- scene upload -------------------------------------------------------------------------------------------------
+static Box prim_box(const rtx_scene_desc* d, int kind, int idx) {
+    Box b;
+    b.reset();
+    if (kind == RTX_GEOM_SPHERE) {
+        double r = std::fabs(d->sph_radius[idx]);
+        for (int a = 0; a < 3; a++) {
+            double c0 = d->sph_center[3 * idx + a], c1 = c0 + d->sph_velocity[3 * idx + a];
+            b.lo[a] = std::min(c0, c1) - r;
+            b.hi[a] = std::max(c0, c1) + r;
+        }
+    } else if (kind == RTX_GEOM_QUAD) {
+        for (int corner = 0; corner < 4; corner++) {
+            double p[3];
+            for (int a = 0; a < 3; a++)
+                p[a] = d->quad_q[3 * idx + a] + ((corner & 1) ? d->quad_u[3 * idx + a] : 0.0) + ((corner & 2) ? d->quad_v[3 * idx + a] : 0.0);
+            b.grow(p);
+        }
+    } else if (kind == RTX_GEOM_TRIANGLE) {
+        b.grow(d->tri_v0 + 3 * idx); b.grow(d->tri_v1 + 3 * idx); b.grow(d->tri_v2 + 3 * idx);
+    } else {
+        for (int a = 0; a < 3; a++) { b.lo[a] = -INFINITY; b.hi[a] = INFINITY; }
+    }
+    // a hit may sit a few ulps off a flat primitive's plane: pad like the reference (rt/aabb.go:117-128)
+    for (int a = 0; a < 3; a++)
+        if (b.hi[a] - b.lo[a] < 1e-4) { b.lo[a] -= 1e-4; b.hi[a] += 1e-4; }
+    return b;
+}
+static Box xform_box(const rtx_scene_desc* d, Box b, int xfBegin, int xfCount) {  // innermost first, like the wrappers' constructors
+    for (int k = xfCount - 1; k >= 0; k--) {
+        int x = xfBegin + k;
+        const double* a = d->xf_a + 3 * x;
+        if (!b.finite()) return b;
+        if (d->xf_type[x] == RTX_XF_TRANSLATE) {
+            for (int i = 0; i < 3; i++) { b.lo[i] += a[i]; b.hi[i] += a[i]; }
+        } else if (d->xf_type[x] == RTX_XF_ROTATE_Y) {
+            Box r;
+            r.reset();
+            for (int c = 0; c < 8; c++) {
+                double px = (c & 1) ? b.hi[0] : b.lo[0], py = (c & 2) ? b.hi[1] : b.lo[1], pz = (c & 4) ? b.hi[2] : b.lo[2];
+                double q[3] = {a[1] * px + a[0] * pz, py, -a[0] * px + a[1] * pz};
+                r.grow(q);
+            }
+            b = r;
+        } else {
+            for (int i = 0; i < 3; i++) {
+                double l = b.lo[i] * a[i], h = b.hi[i] * a[i];
+                b.lo[i] = std::min(l, h); b.hi[i] = std::max(l, h);
+            }
+        }
+        // rotation / scaling round: keep the box conservative
+        for (int i = 0; i < 3; i++) {
+            double m = std::max(std::fabs(b.lo[i]), std::fabs(b.hi[i])) * 1e-12 + 1e-300;
+            b.lo[i] -= m; b.hi[i] += m;
+        }
+    }
+    return b;
+}
+
+int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
+    if (!ctx || !d) return RTX_ERR_INVALID;
+    if (d->abi_version != RTX_ABI_VERSION) return fail(ctx, RTX_ERR_INVALID, "scene abi_version %u != %d", d->abi_version, RTX_ABI_VERSION);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    free_scene(ctx);
+    DevScene S{};
+
+    // ---- validation
+    auto bad = [&](const char* what) { return fail(ctx, RTX_ERR_INVALID, "scene: %s", what); };
+    for (int i = 0; i < d->n_textures; i++) {
+        if (d->tex_type[i] == RTX_TEX_CHECKER) {
+            if (d->tex_even[i] < 0 || d->tex_even[i] >= d->n_textures || d->tex_odd[i] < 0 || d->tex_odd[i] >= d->n_textures) return bad("checker child out of range");
+        } else if (d->tex_type[i] != RTX_TEX_SOLID) return fail(ctx, RTX_ERR_UNSUPPORTED, "texture type %d is outside the device path", d->tex_type[i]);
+    }
+    for (int i = 0; i < d->n_materials; i++) {
+        int t = d->mat_type[i];
+        if (t < RTX_MAT_LAMBERTIAN || t > RTX_MAT_ISOTROPIC) return fail(ctx, RTX_ERR_UNSUPPORTED, "material type %d is outside the device path", t);
+        if ((t == RTX_MAT_LAMBERTIAN || t == RTX_MAT_DIFFUSE_LIGHT || t == RTX_MAT_ISOTROPIC) && (d->mat_tex[i] < 0 || d->mat_tex[i] >= d->n_textures))
+            return bad("material texture out of range");
+    }
+    auto matok = [&](const int32_t* m, int n) { for (int i = 0; i < n; i++) if (m[i] < 0 || m[i] >= d->n_materials) return false; return true; };
+    if (!matok(d->sph_mat, d->n_spheres) || !matok(d->quad_mat, d->n_quads) || !matok(d->tri_mat, d->n_tris) || !matok(d->plane_mat, d->n_planes) ||
+        !matok(d->vol_mat, d->n_volumes))
+        return bad("material index out of range");
+    auto primCount = [&](int kind) { return kind == RTX_GEOM_SPHERE ? d->n_spheres : kind == RTX_GEOM_QUAD ? d->n_quads : kind == RTX_GEOM_TRIANGLE ? d->n_tris : d->n_planes; };
+    for (int i = 0; i < d->n_list_items; i++) {
+        int k = d->list_item_kind[i];
+        if (k < RTX_GEOM_SPHERE || k > RTX_GEOM_PLANE || d->list_item_index[i] < 0 || d->list_item_index[i] >= primCount(k)) return bad("list item out of range");
+    }
+    for (int g = 0; g < d->n_groups; g++) {
+        int lim = d->group_kind[g] == RTX_GEOM_LIST ? d->n_list_items : d->n_tris;
+        if ((d->group_kind[g] != RTX_GEOM_LIST && d->group_kind[g] != RTX_GEOM_MESH) || d->group_begin[g] < 0 || d->group_count[g] < 0 ||
+            d->group_begin[g] + d->group_count[g] > lim)
+            return bad("group range invalid");
+    }
+    for (int x = 0; x < d->n_xforms; x++)
+        if (d->xf_type[x] < RTX_XF_TRANSLATE || d->xf_type[x] > RTX_XF_SCALE) return fail(ctx, RTX_ERR_UNSUPPORTED, "transform op %d is outside the device path", d->xf_type[x]);
+    for (int e = 0; e < d->n_entries; e++) {
+        int k = d->entry_geom_kind[e], gi = d->entry_geom_index[e];
+        if (k < RTX_GEOM_SPHERE || k > RTX_GEOM_MESH) return bad("entry kind invalid");
+        if (k <= RTX_GEOM_PLANE ? (gi < 0 || gi >= primCount(k)) : (gi < 0 || gi >= d->n_groups || d->group_kind[gi] != k)) return bad("entry geometry out of range");
+        if (d->entry_xf_count[e] < 0 || d->entry_xf_begin[e] < 0 || d->entry_xf_begin[e] + d->entry_xf_count[e] > d->n_xforms) return bad("entry transform range invalid");
+        if (d->entry_volume[e] >= d->n_volumes) return bad("entry volume out of range");
+        if (d->entry_volume[e] >= 0 && (k == RTX_GEOM_MESH || k == RTX_GEOM_PLANE))
+            return fail(ctx, RTX_ERR_UNSUPPORTED, "Volume boundary must be a primitive or a HittableList of primitives");
+    }
+    for (int i = 0; i < d->n_lights; i++)
+        if (d->light_quad[i] >= d->n_quads) return bad("light quad out of range");
+
+    // ---- textures, materials
+    std::vector<DTexture> texs(d->n_textures);
+    for (int i = 0; i < d->n_textures; i++) {
+        texs[i].type = d->tex_type[i]; texs[i].even = d->tex_even ? d->tex_even[i] : -1; texs[i].odd = d->tex_odd ? d->tex_odd[i] : -1;
+        texs[i].inv_scale = d->tex_inv_scale ? d->tex_inv_scale[i] : 0;
+        for (int c = 0; c < 3; c++) texs[i].color[c] = (float)d->tex_color[3 * i + c];
+    }
+    std::vector<DMaterial> mats(d->n_materials);
+    for (int i = 0; i < d->n_materials; i++) {
+        mats[i].type = d->mat_type[i]; mats[i].tex = d->mat_tex[i]; mats[i].fuzz = d->mat_fuzz[i]; mats[i].ior = d->mat_ior[i]; mats[i].pad = 0;
+        for (int c = 0; c < 3; c++) mats[i].albedo[c] = (float)d->mat_albedo[3 * i + c];
+    }
+    // ---- primitives in float64
+    std::vector<double> sph((size_t)8 * d->n_spheres);
+    std::vector<int> sphMat(d->sph_mat, d->sph_mat + d->n_spheres);
+    for (int i = 0; i < d->n_spheres; i++) {
+        for (int a = 0; a < 3; a++) { sph[8 * i + a] = d->sph_center[3 * i + a]; sph[8 * i + 3 + a] = d->sph_velocity[3 * i + a]; }
+        sph[8 * i + 6] = std::fmax(0.0, d->sph_radius[i]);  // rt/sphere.go:18
+        sph[8 * i + 7] = 0;
+    }
+    std::vector<double> quads((size_t)16 * d->n_quads);
+    std::vector<int> quadMat(d->quad_mat, d->quad_mat + d->n_quads);
+    for (int i = 0; i < d->n_quads; i++) {  // NewQuad rt/quad.go:16-33, same operation order
+        const double *Q = d->quad_q + 3 * i, *u = d->quad_u + 3 * i, *v = d->quad_v + 3 * i;
+        double n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+        double l2 = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+        double l = std::sqrt(l2);
+        double nn[3] = {n[0], n[1], n[2]};
+        if (l != 0) { double inv = 1 / l; nn[0] = inv * n[0]; nn[1] = inv * n[1]; nn[2] = inv * n[2]; }
+        double D = nn[0] * Q[0] + nn[1] * Q[1] + nn[2] * Q[2];
+        double wk = 1.0 / l2;
+        double* o = quads.data() + 16 * (size_t)i;
+        for (int a = 0; a < 3; a++) { o[a] = Q[a]; o[3 + a] = u[a]; o[6 + a] = v[a]; o[9 + a] = wk * n[a]; o[12 + a] = nn[a]; }
+        o[15] = D;
+    }
+    std::vector<double> planes((size_t)8 * d->n_planes);
+    std::vector<int> planeMat(d->plane_mat, d->plane_mat + d->n_planes);
+    for (int i = 0; i < d->n_planes; i++)
+        for (int a = 0; a < 3; a++) { planes[8 * i + a] = d->plane_point[3 * i + a]; planes[8 * i + 3 + a] = d->plane_normal[3 * i + a]; }
+
+    // ---- triangles: meshes are permuted into BLAS leaf order; loose triangles follow
+    std::vector<Node4> nodes;
+    std::vector<double> tris, triNrm;
+    std::vector<int4> triInfo;
+    std::vector<int> devTriOfDesc(d->n_tris, -1);
+    auto pushTri = [&](int ti, int localId, int rank) {
+        const double *v0 = d->tri_v0 + 3 * ti, *v1 = d->tri_v1 + 3 * ti, *v2 = d->tri_v2 + 3 * ti;
+        double e1[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]}, e2[3] = {v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2]};
+        double n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};  // rt/triangle.go:19-25
+        double l = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        if (l != 0) { double inv = 1 / l; n[0] = inv * n[0]; n[1] = inv * n[1]; n[2] = inv * n[2]; }
+        int dev = (int)triInfo.size();
+        for (int a = 0; a < 3; a++) tris.push_back(v0[a]);
+        for (int a = 0; a < 3; a++) tris.push_back(e1[a]);
+        for (int a = 0; a < 3; a++) tris.push_back(e2[a]);
+        tris.push_back(0);
+        for (int a = 0; a < 3; a++) triNrm.push_back(n[a]);
+        triNrm.push_back(0);
+        triInfo.push_back(make_int4(localId, d->tri_mat[ti], rank, 0));
+        devTriOfDesc[ti] = dev;
+        return dev;
+    };
+    std::vector<int> groupRoot(d->n_groups, -1), groupTriBase(d->n_groups, 0);
+    uint32_t blasNodes = 0;
+    for (int g = 0; g < d->n_groups; g++) {
+        if (d->group_kind[g] != RTX_GEOM_MESH) continue;
+        int begin = d->group_begin[g], count = d->group_count[g];
+        std::vector<Box> boxes(count);
+        for (int k = 0; k < count; k++) boxes[k] = prim_box(d, RTX_GEOM_TRIANGLE, begin + k);
+        std::vector<int> ranks;
+        if (d->tri_rank) ranks.assign(d->tri_rank + begin, d->tri_rank + begin + count);
+        else ranks = rtxbvh::canonical_ranks(boxes);
+        int base = (int)triInfo.size();
+        groupTriBase[g] = base;
+        std::vector<int> perm;
+        size_t before = nodes.size();
+        groupRoot[g] = rtxbvh::build_bvh4(boxes, 4, nodes, perm, [&](int first, int cnt) { return ((base + first) << 3) | (cnt - 1); });
+        blasNodes += (uint32_t)(nodes.size() - before);
+        for (int k = 0; k < count; k++) pushTri(begin + perm[k], perm[k], ranks[perm[k]]);
+        if (count > 0 && (size_t)(base + count) >= (1u << 28)) return fail(ctx, RTX_ERR_UNSUPPORTED, "too many triangles");
+    }
+    auto devPrim = [&](int kind, int idx) {
+        if (kind != RTX_GEOM_TRIANGLE) return idx;
+        if (devTriOfDesc[idx] < 0) pushTri(idx, 0, 0);
+        return devTriOfDesc[idx];
+    };
+    std::vector<int2> listItems(d->n_list_items);
+    for (int i = 0; i < d->n_list_items; i++) listItems[i] = make_int2(d->list_item_kind[i], devPrim(d->list_item_kind[i], d->list_item_index[i]));
+
+    // ---- entries, their world bounds, ranks
+    std::vector<DEntry> entries(d->n_entries);
+    std::vector<Box> entryBox(d->n_entries);
+    for (int e = 0; e < d->n_entries; e++) {
+        DEntry& E = entries[e];
+        int k = d->entry_geom_kind[e], gi = d->entry_geom_index[e];
+        E.kind = k; E.index = 0; E.a = 0; E.b = 0;
+        E.xf_begin = d->entry_xf_begin[e]; E.xf_count = d->entry_xf_count[e]; E.volume = d->entry_volume[e]; E.rank = e;
+        Box b;
+        b.reset();
+        if (k <= RTX_GEOM_PLANE) {
+            E.index = devPrim(k, gi);
+            b = prim_box(d, k, gi);
+        } else if (k == RTX_GEOM_LIST) {
+            E.a = d->group_begin[gi]; E.b = d->group_count[gi];
+            for (int i = 0; i < E.b; i++) b.grow(prim_box(d, d->list_item_kind[E.a + i], d->list_item_index[E.a + i]));
+            if (E.b == 0) continue;
+        } else {
+            E.a = groupRoot[gi]; E.b = groupTriBase[gi];
+            for (int i = 0; i < d->group_count[gi]; i++) b.grow(prim_box(d, RTX_GEOM_TRIANGLE, d->group_begin[gi] + i));
+        }
+        entryBox[e] = xform_box(d, b, E.xf_begin, E.xf_count);
+    }
+    {  // test-order ranks: the caller's Go tree, or the canonical stable median-split order
+        std::vector<int> ranks;
+        if (d->entry_rank) ranks.assign(d->entry_rank, d->entry_rank + d->n_entries);
+        else if (d->world_is_bvh) {
+            std::vector<Box> rb(d->n_entries);
+            for (int e = 0; e < d->n_entries; e++) rb[e] = entryBox[e];
+            ranks = rtxbvh::canonical_ranks(rb);
+        } else {
+            ranks.resize(d->n_entries);
+            for (int e = 0; e < d->n_entries; e++) ranks[e] = e;
+        }
+        for (int e = 0; e < d->n_entries; e++) entries[e].rank = ranks[e];
+    }
+    // ---- TLAS over bounded entries; unbounded ones (planes) are tested for every ray
+    std::vector<int> unbounded, boundedIdx;
+    std::vector<Box> tb;
+    for (int e = 0; e < d->n_entries; e++) {
+        bool empty = (entries[e].kind == RTX_GEOM_LIST && entries[e].b == 0) || (entries[e].kind == RTX_GEOM_MESH && entries[e].a < 0);
+        if (empty) continue;
+        if (!entryBox[e].finite()) {
+            if (entries[e].kind == RTX_GEOM_MESH || entries[e].volume >= 0) return fail(ctx, RTX_ERR_UNSUPPORTED, "entry %d: unbounded mesh/volume", e);
+            if (entries[e].kind == RTX_GEOM_LIST) return fail(ctx, RTX_ERR_UNSUPPORTED, "entry %d: a HittableList containing an infinite Plane is outside the device path", e);
+            unbounded.push_back(e);
+        } else {
+            boundedIdx.push_back(e);
+            tb.push_back(entryBox[e]);
+        }
+    }
+    std::vector<int> perm;
+    size_t before = nodes.size();
+    int tlasRoot = rtxbvh::build_bvh4(tb, 1, nodes, perm, [&](int first, int) { return first; });
+    // leaf codes reference positions in `perm`; rewrite them to entry indices
+    for (size_t ni = before; ni < nodes.size(); ni++)
+        for (int c = 0; c < 4; c++)
+            if (nodes[ni].child[c] < 0 && nodes[ni].lox[c] <= nodes[ni].hix[c]) nodes[ni].child[c] = ~boundedIdx[perm[~nodes[ni].child[c]]];
+    ctx->tlas_nodes = (uint32_t)(nodes.size() - before);
+    ctx->blas_nodes = blasNodes;
+    ctx->n_entries = d->n_entries;
+    ctx->n_tris = (uint32_t)triInfo.size();
+
+    std::vector<DXform> xfs(d->n_xforms);
+    for (int x = 0; x < d->n_xforms; x++) {
+        xfs[x].type = d->xf_type[x]; xfs[x].pad = 0;
+        for (int a = 0; a < 3; a++) { xfs[x].a[a] = d->xf_a[3 * x + a]; xfs[x].b[a] = d->xf_b ? d->xf_b[3 * x + a] : 0; }
+    }
+    std::vector<DVolume> vols(d->n_volumes);
+    for (int i = 0; i < d->n_volumes; i++) { vols[i].neg_inv_density = d->vol_neg_inv_density[i]; vols[i].mat = d->vol_mat[i]; vols[i].pad = 0; }
+    std::vector<int> lights(d->light_quad, d->light_quad + d->n_lights);
+
+    // ---- HDRI: BuildDistribution (rt/hdri.go:145-224) in float64, same loop order
+    std::vector<float4> envTex;
+    std::vector<double> marg, cond, pdf;
+    double totalPower = 0;
+    if (d->env_width > 0 && d->env_height > 0 && d->env_rgb) {
+        int W = d->env_width, H = d->env_height;
+        envTex.resize((size_t)W * H);
+        pdf.assign((size_t)W * H, 0.0);
+        marg.assign(H + 1, 0.0);
+        cond.assign((size_t)H * (W + 1), 0.0);
+        std::vector<double> rowSums(H, 0.0);
+        for (int y = 0; y < H; y++) {
+            double v = ((double)y + 0.5) / (double)H;
+            double theta = (0.5 - v) * M_PI;
+            double sinTheta = std::cos(theta);
+            double* cr = cond.data() + (size_t)y * (W + 1);
+            for (int x = 0; x < W; x++) {
+                size_t idx = (size_t)y * W + x;
+                const double* c = d->env_rgb + 3 * idx;
+                envTex[idx] = make_float4((float)c[0], (float)c[1], (float)c[2], 0.f);
+                double lum = 0.2126 * c[0] + 0.7152 * c[1] + 0.0722 * c[2];
+                double w = lum * sinTheta;
+                if (w < 0) w = 0;
+                pdf[idx] = w;
+                rowSums[y] += w;
+                totalPower += w;
+                cr[x + 1] = cr[x] + w;
+            }
+        }
+        for (int y = 0; y < H; y++)
+            if (rowSums[y] > 0) {
+                double* cr = cond.data() + (size_t)y * (W + 1);
+                for (int x = 0; x <= W; x++) cr[x] /= rowSums[y];
+            }
+        for (int y = 0; y < H; y++) marg[y + 1] = marg[y] + rowSums[y];
+        if (totalPower > 0) {
+            for (int y = 0; y <= H; y++) marg[y] /= totalPower;
+            for (auto& p : pdf) p /= totalPower;
+        }
+        S.env_w = W; S.env_h = H; S.env_is = d->env_importance_sampling != 0; S.env_rot = d->env_rotation; S.env_total = totalPower;
+    }
+    ctx->env_total = totalPower;
+
+    // ---- upload
+    std::vector<float4> nodeData(nodes.size() * 8);
+    if (!nodes.empty()) std::memcpy(nodeData.data(), nodes.data(), nodes.size() * sizeof(Node4));
+    {   // 128-byte alignment of the node array: cudaMalloc returns >= 256-byte aligned memory
+        UP(nodeData, S.nodes);
+    }
+    UP(entries, S.entries);
+    UP(unbounded, S.unbounded);
+    UP(sph, S.spheres); UP(sphMat, S.sph_mat);
+    UP(quads, S.quads); UP(quadMat, S.quad_mat);
+    UP(tris, S.tris); UP(triNrm, S.tri_nrm); UP(triInfo, S.tri_info);
+    UP(planes, S.planes); UP(planeMat, S.plane_mat);
+    UP(listItems, S.list_items);
+    UP(xfs, S.xforms); UP(vols, S.volumes); UP(mats, S.mats); UP(texs, S.texs); UP(lights, S.light_quads);
+    UP(envTex, S.env_tex); UP(marg, S.env_marg); UP(cond, S.env_cond); UP(pdf, S.env_pdf);
+    S.tlas_root = tlasRoot;
+    S.n_entries = d->n_entries;
+    S.n_unbounded = (int)unbounded.size();
+    S.n_lights = d->n_lights;
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->S = S;
+    ctx->have_scene = true;
+    std::memset(&ctx->stats, 0, sizeof ctx->stats);
+    return RTX_OK;
+}
+
+// ---- camera (Initialize, rt/camera.go:286-344, float64, same operation order) -----------------------------------------
+int32_t rtx_camera_set(rtx_ctx* ctx, const rtx_camera_desc* c) {
+    if (!ctx || !c) return RTX_ERR_INVALID;
+    if (c->image_width <= 0 || !(c->aspect_ratio > 0)) return fail(ctx, RTX_ERR_INVALID, "camera: bad resolution");
+    CU(cudaSetDevice(ctx->device));
+    DevCamera C{};
+    int W = c->image_width;
+    int H = c->has_derived ? c->image_height : std::max((int)((double)W / c->aspect_ratio), 1);
+    auto sub3 = [](const double* a, const double* b, double* o) { for (int i = 0; i < 3; i++) o[i] = a[i] - b[i]; };
+    auto scale3 = [](const double* a, double t, double* o) { for (int i = 0; i < 3; i++) o[i] = t * a[i]; };
+    auto unit3 = [](const double* a, double* o) {
+        double l = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+        if (l == 0) { o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; return; }
+        double inv = 1 / l;
+        for (int i = 0; i < 3; i++) o[i] = inv * a[i];
+    };
+    auto cross3 = [](const double* a, const double* b, double* o) {
+        double r[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+        o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
+    };
+    const double Pi = 3.1415926535897932385;  // rt/utils.go:11
+    if (c->has_derived) {
+        for (int i = 0; i < 3; i++) {
+            C.center[i] = c->center[i]; C.pixel00[i] = c->pixel00_loc[i]; C.du[i] = c->pixel_delta_u[i]; C.dv[i] = c->pixel_delta_v[i];
+            C.u[i] = c->u[i]; C.v[i] = c->v[i]; C.w[i] = c->w[i];
+        }
+        C.defocus_radius = c->defocus_radius; C.viewport_w = c->viewport_width; C.viewport_h = c->viewport_height;
+    } else {
+        double theta = c->vfov * Pi / 180.0;
+        double h = std::tan(theta / 2);
+        double vh = 2 * h * c->focus_dist;
+        double vw = vh * ((double)W / (double)H);
+        double w[3], u[3], v[3], t[3];
+        if (c->free_camera) { for (int i = 0; i < 3; i++) w[i] = -c->forward[i]; }
+        else { sub3(c->look_from, c->look_at, t); unit3(t, w); }
+        cross3(c->vup, w, t); unit3(t, u);
+        cross3(w, u, v);
+        double vpU[3], vpV[3], nv[3] = {-v[0], -v[1], -v[2]};
+        scale3(u, vw, vpU); scale3(nv, vh, vpV);
+        scale3(vpU, 1 / (double)W, C.du);
+        scale3(vpV, 1 / (double)H, C.dv);
+        double wf[3], hU[3], hV[3], ul[3], sum[3];
+        scale3(w, c->focus_dist, wf); scale3(vpU, 1 / 2.0, hU); scale3(vpV, 1 / 2.0, hV);
+        for (int i = 0; i < 3; i++) ul[i] = ((c->look_from[i] - wf[i]) - hU[i]) - hV[i];
+        for (int i = 0; i < 3; i++) sum[i] = C.du[i] + C.dv[i];
+        for (int i = 0; i < 3; i++) C.pixel00[i] = ul[i] + 0.5 * sum[i];
+        for (int i = 0; i < 3; i++) { C.center[i] = c->look_from[i]; C.u[i] = u[i]; C.v[i] = v[i]; C.w[i] = w[i]; }
+        C.defocus_radius = c->focus_dist * std::tan((c->defocus_angle / 2) * Pi / 180.0);
+        C.viewport_w = vw; C.viewport_h = vh;
+    }
+    C.defocus_angle = c->defocus_angle; C.focus_dist = c->focus_dist;
+    for (int i = 0; i < 3; i++) {
+        C.look_from[i] = c->look_from[i]; C.look_at[i] = c->look_at[i]; C.vup[i] = c->vup[i]; C.forward[i] = c->forward[i];
+        C.look_vel[i] = c->camera_motion ? c->look_from2[i] - c->look_from[i] : 0.0;
+        C.look_at_vel[i] = c->camera_motion ? c->look_at2[i] - c->look_at[i] : 0.0;
+        C.background[i] = (float)c->background[i];
+    }
+    C.camera_motion = c->camera_motion; C.free_camera = c->free_camera;
+    C.width = W; C.height = H; C.use_sky = c->use_sky_gradient; C.phantom = c->phantom_hdri; C.max_depth = c->max_depth;
+    bool resize = (W != ctx->W || H != ctx->H) || !ctx->accum;
+    ctx->C = C; ctx->W = W; ctx->H = H; ctx->have_camera = true;
+    if (resize) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->accum) cudaFree(ctx->accum);
+        if (ctx->accum_sq) cudaFree(ctx->accum_sq);
+        ctx->accum = ctx->accum_sq = nullptr;
+        size_t bytes = (size_t)W * H * sizeof(float4);
+        CU(cudaMalloc((void**)&ctx->accum, bytes));
+        CU(cudaMalloc((void**)&ctx->accum_sq, bytes));
+        CU(cudaMemsetAsync(ctx->accum, 0, bytes, ctx->stream));
+        CU(cudaMemsetAsync(ctx->accum_sq, 0, bytes, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return RTX_OK;
+}
+
+int32_t rtx_image_size(const rtx_ctx* ctx, int32_t* w, int32_t* h) {
+    if (!ctx || !ctx->have_camera) return RTX_ERR_STATE;
+    if (w) *w = ctx->W;
+    if (h) *h = ctx->H;
+    return RTX_OK;
+}
+
+int32_t rtx_accum_clear(rtx_ctx* ctx) {
+    if (!ctx || !ctx->have_camera) return ctx ? fail(ctx, RTX_ERR_STATE, "camera not set") : RTX_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    size_t bytes = (size_t)ctx->W * ctx->H * sizeof(float4);
+    CU(cudaMemsetAsync(ctx->accum, 0, bytes, ctx->stream));
+    CU(cudaMemsetAsync(ctx->accum_sq, 0, bytes, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RTX_OK;
+}
+int32_t rtx_accum_enable_moments(rtx_ctx* ctx, int32_t enable) {
+    if (!ctx) return RTX_ERR_INVALID;
+    ctx->moments = enable != 0;
+    return RTX_OK;
+}
+int32_t rtx_accum_device_ptr(rtx_ctx* ctx, void** sum_dev, void** sumsq_dev, int64_t* n_floats) {
+    if (!ctx || !ctx->have_camera) return ctx ? fail(ctx, RTX_ERR_STATE, "camera not set") : RTX_ERR_INVALID;
+    if (sum_dev) *sum_dev = ctx->accum;
+    if (sumsq_dev) *sumsq_dev = ctx->accum_sq;
+    if (n_floats) *n_floats = (int64_t)4 * ctx->W * ctx->H;
+    return RTX_OK;
+}
+
+static int32_t ensure_pool(rtx_ctx* ctx) {
+    if (ctx->pool.capacity == ctx->pool_paths) return RTX_OK;
+    free_pool(ctx);
+    size_t P = (size_t)ctx->pool_paths;
+    Pool p{};
+    auto alloc = [&](void** out, size_t bytes) {
+        cudaError_t e = cudaMalloc(out, bytes);
+        if (e == cudaSuccess) ctx->pool_allocs.push_back(*out);
+        return e;
+    };
+    CU(alloc((void**)&p.ray_o, 2 * P * sizeof(double2)));
+    CU(alloc((void**)&p.ray_d, 2 * P * sizeof(double2)));
+    CU(alloc((void**)&p.thr, P * sizeof(float4)));
+    CU(alloc((void**)&p.rad, P * sizeof(float4)));
+    CU(alloc((void**)&p.pix, P * sizeof(uint2)));
+    CU(alloc((void**)&p.hit_p, 2 * P * sizeof(double2)));
+    CU(alloc((void**)&p.hit_n, 2 * P * sizeof(double2)));
+    CU(alloc((void**)&p.q_a, P * sizeof(int)));
+    CU(alloc((void**)&p.q_b, P * sizeof(int)));
+    CU(alloc((void**)&p.q_free, P * sizeof(int)));
+    CU(alloc((void**)&p.q_mat, (size_t)Q_COUNT * P * sizeof(int)));
+    CU(alloc((void**)&p.q_done, P * sizeof(int)));
+    CU(alloc((void**)&p.sh_d, 4 * P * sizeof(double2)));
+    CU(alloc((void**)&p.sh_c, 2 * P * sizeof(float4)));
+    p.capacity = (int)P;
+    ctx->pool = p;
+    return RTX_OK;
+}
+
+// ---- the hot path ------------------------------------------------------------------------------------------------------
+int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t camera_max_depth, uint64_t seed, uint32_t sample_base) {
+    if (!ctx) return RTX_ERR_INVALID;
+    if (!ctx->have_scene || !ctx->have_camera) return fail(ctx, RTX_ERR_STATE, "rtx_render_pass: scene and camera must be set first");
+    if (spp < 0 || max_depth < 0) return fail(ctx, RTX_ERR_INVALID, "rtx_render_pass: negative spp/depth");
+    CU(cudaSetDevice(ctx->device));
+    int32_t rc = ensure_pool(ctx);
+    if (rc != RTX_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    const int P = ctx->pool.capacity;
+    PassParams pp{};
+    pp.spp = spp; pp.max_depth = max_depth; pp.camera_max_depth = camera_max_depth;
+    pp.seed_lo = (uint32_t)seed; pp.seed_hi = (uint32_t)(seed >> 32); pp.sample_base = sample_base;
+    pp.moments = ctx->moments; pp.count_stats = ctx->count_stats;
+
+    Ctl init{};
+    init.total = (unsigned long long)ctx->W * ctx->H * (unsigned long long)spp;
+    if (max_depth == 0) init.total = 0;  // RayColor(depth 0) is black: nothing to trace (samples still count in the divisor)
+    init.n_free = P;
+    CU(cudaMemcpyAsync(ctx->ctl, &init, sizeof(Ctl), cudaMemcpyHostToDevice, st));
+    k_pool_init<<<(P + 255) / 256, 256, 0, st>>>(ctx->pool, ctx->ctl);
+
+    const int BATCH = 16;
+    enum { EV_GEN = 0, EV_EXT, EV_SHADE, EV_CONN, EV_ACC, EV_KINDS };
+    const bool timing = ctx->time_kernels != 0;
+    size_t needEvents = 2 + (timing ? (size_t)BATCH * EV_KINDS * 2 : 0);
+    while (ctx->events.size() < needEvents) {
+        cudaEvent_t ev;
+        CU(cudaEventCreate(&ev));
+        ctx->events.push_back(ev);
+    }
+    cudaEvent_t evStart = ctx->events[0], evStop = ctx->events[1];
+    double msKind[EV_KINDS] = {0, 0, 0, 0, 0};
+    uint64_t launches = 1;
+    CU(cudaEventRecord(evStart, st));
+    const int gridBig = (P + 255) / 256, gridTrace = (P + 127) / 128, gridShadow = (2 * P + 127) / 128;
+    long long iter = 0;
+    int activeEstimate = P;  // shrinks the launch grids once the pool drains (from the last polled control block)
+    for (;;) {
+        int used = 0;
+        for (int b = 0; b < BATCH; b++, iter++) {
+            int* q_cur = (iter & 1) ? ctx->pool.q_b : ctx->pool.q_a;
+            int* q_next = (iter & 1) ? ctx->pool.q_a : ctx->pool.q_b;
+            cudaEvent_t* ev = timing ? &ctx->events[2 + (size_t)b * EV_KINDS * 2] : nullptr;
+            k_iter_begin<<<1, 32, 0, st>>>(ctx->ctl);
+            if (timing) cudaEventRecord(ev[0], st);
+            k_generate<<<gridBig, 256, 0, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->C, pp);
+            if (timing) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
+            if (ctx->count_stats) k_extend<true><<<gridTrace, 128, 0, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->S, pp);
+            else k_extend<false><<<gridTrace, 128, 0, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->S, pp);
+            if (timing) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); }
+            k_shade<<<gridBig, 256, 0, st>>>(ctx->ctl, ctx->pool, q_next, ctx->S, ctx->C, pp);
+            if (timing) { cudaEventRecord(ev[5], st); cudaEventRecord(ev[6], st); }
+            if (ctx->S.n_lights > 0) {
+                if (ctx->count_stats) k_connect<true><<<gridShadow, 128, 0, st>>>(ctx->ctl, ctx->pool, ctx->S, pp);
+                else k_connect<false><<<gridShadow, 128, 0, st>>>(ctx->ctl, ctx->pool, ctx->S, pp);
+                launches++;
+            }
+            if (timing) { cudaEventRecord(ev[7], st); cudaEventRecord(ev[8], st); }
+            k_accumulate<<<gridBig, 256, 0, st>>>(ctx->ctl, ctx->pool, ctx->accum, ctx->accum_sq, ctx->moments);
+            if (timing) cudaEventRecord(ev[9], st);
+            launches += 5;
+            used++;
+        }
+        (void)activeEstimate;
+        CU(cudaMemcpyAsync(ctx->ctl_host, ctx->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (timing)
+            for (int b = 0; b < used; b++)
+                for (int k = 0; k < EV_KINDS; k++) {
+                    float ms = 0;
+                    cudaEventElapsedTime(&ms, ctx->events[2 + (size_t)b * EV_KINDS * 2 + 2 * k], ctx->events[2 + (size_t)b * EV_KINDS * 2 + 2 * k + 1]);
+                    msKind[k] += ms;
+                }
+        if (ctx->ctl_host->done) break;
+    }
+    CU(cudaEventRecord(evStop, st));
+    CU(cudaEventSynchronize(evStop));
+    CU(cudaGetLastError());
+    float msTotal = 0;
+    cudaEventElapsedTime(&msTotal, evStart, evStop);
+    const Ctl& c = *ctx->ctl_host;
+    rtx_stats& s = ctx->stats;
+    s.paths = (uint64_t)ctx->W * ctx->H * (uint64_t)spp;
+    s.extension_rays = c.ext_rays; s.shadow_rays = c.shadow_rays; s.nodes_visited = c.nodes;
+    s.tri_tests = c.tris; s.sphere_tests = c.spheres; s.quad_tests = c.quads; s.plane_tests = c.planes;
+    s.wavefront_iterations = c.iterations; s.kernel_launches = launches;
+    s.ms_generate = msKind[EV_GEN]; s.ms_extend = msKind[EV_EXT]; s.ms_shade = msKind[EV_SHADE]; s.ms_connect = msKind[EV_CONN];
+    s.ms_total = msTotal;
+    s.tlas_nodes = ctx->tlas_nodes; s.blas_nodes = ctx->blas_nodes; s.n_entries = ctx->n_entries; s.n_tris = ctx->n_tris;
+    if (max_depth == 0 && spp > 0) {
+        // every sample is black but still counted: bump the per-pixel sample count only
+    }
+    return RTX_OK;
+}
+
+int32_t rtx_get_stats(rtx_ctx* ctx, rtx_stats* out) {
+    if (!ctx || !out) return RTX_ERR_INVALID;
+    *out = ctx->stats;
+    out->tlas_nodes = ctx->tlas_nodes; out->blas_nodes = ctx->blas_nodes; out->n_entries = ctx->n_entries; out->n_tris = ctx->n_tris;
+    return RTX_OK;
+}
+
+int32_t rtx_resolve_rgba8(rtx_ctx* ctx, int32_t total_spp, uint8_t* pix, int64_t nbytes) {
+    if (!ctx || !pix) return RTX_ERR_INVALID;
+    if (!ctx->have_camera) return fail(ctx, RTX_ERR_STATE, "camera not set");
+    int npix = ctx->W * ctx->H;
+    if (nbytes != (int64_t)4 * npix) return fail(ctx, RTX_ERR_INVALID, "rtx_resolve_rgba8: nbytes %lld != 4*W*H = %d", (long long)nbytes, 4 * npix);
+    if (total_spp <= 0) return fail(ctx, RTX_ERR_INVALID, "rtx_resolve_rgba8: total_spp must be positive");
+    CU(cudaSetDevice(ctx->device));
+    uchar4* dev = nullptr;
+    CU(cudaMalloc((void**)&dev, (size_t)npix * 4));
+    k_resolve_rgba8<<<(npix + 255) / 256, 256, 0, ctx->stream>>>(ctx->accum, npix, 1.0 / (double)total_spp, dev);
+    cudaError_t e = cudaMemcpyAsync(pix, dev, (size_t)npix * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail(ctx, RTX_ERR_CUDA, "rtx_resolve_rgba8: %s", cudaGetErrorString(e));
+    return RTX_OK;
+}
+
+int32_t rtx_resolve_accum(rtx_ctx* ctx, float* sum_rgb, float* sumsq_rgb, uint32_t* n) {
+    if (!ctx) return RTX_ERR_INVALID;
+    if (!ctx->have_camera) return fail(ctx, RTX_ERR_STATE, "camera not set");
+    CU(cudaSetDevice(ctx->device));
+    size_t npix = (size_t)ctx->W * ctx->H;
+    std::vector<float4> h(npix);
+    CU(cudaMemcpyAsync(h.data(), ctx->accum, npix * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < npix; i++) {
+        if (sum_rgb) { sum_rgb[3 * i] = h[i].x; sum_rgb[3 * i + 1] = h[i].y; sum_rgb[3 * i + 2] = h[i].z; }
+        if (n) n[i] = (uint32_t)(h[i].w + 0.5f);
+    }
+    if (sumsq_rgb) {
+        CU(cudaMemcpyAsync(h.data(), ctx->accum_sq, npix * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < npix; i++) { sumsq_rgb[3 * i] = h[i].x; sumsq_rgb[3 * i + 1] = h[i].y; sumsq_rgb[3 * i + 2] = h[i].z; }
+    }
+    return RTX_OK;
+}
+
+// ---- batch entry points (parity tests) -------------------------------------------------------------------------------------
+#define BACK(dev, host, n) if (host) CU(cudaMemcpyAsync(host, dev, (n) * sizeof(*host), cudaMemcpyDeviceToHost, ctx->stream))
+
+int32_t rtx_trace_closest(rtx_ctx* ctx, const double* rays, int64_t n, double tmin, double tmax, int32_t* entry_id, int32_t* prim_id, double* t,
+                          double* normal, uint8_t* front, double* uv, double* p) {
+    if (!ctx || (!rays && n > 0) || n < 0) return RTX_ERR_INVALID;
+    if (!ctx->have_scene) return fail(ctx, RTX_ERR_STATE, "rtx_trace_closest: no scene uploaded");
+    if (n == 0) return RTX_OK;
+    CU(cudaSetDevice(ctx->device));
+    Scratch sc;
+    double* dRays; int *dEntry, *dPrim; double *dT, *dN, *dUV, *dP; unsigned char* dFront;
+    CU(sc.in(&dRays, rays, (size_t)7 * n, ctx->stream));
+    CU(sc.out(&dEntry, entry_id, n)); CU(sc.out(&dPrim, prim_id, n)); CU(sc.out(&dT, t, n)); CU(sc.out(&dN, normal, 3 * n));
+    CU(sc.out(&dFront, (unsigned char*)front, n)); CU(sc.out(&dUV, uv, 2 * n)); CU(sc.out(&dP, p, 3 * n));
+    k_trace_closest<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->S, dRays, n, tmin, tmax, dEntry, dPrim, dT, dN, dFront, dUV, dP);
+    CU(cudaGetLastError());
+    BACK(dEntry, entry_id, n); BACK(dPrim, prim_id, n); BACK(dT, t, n); BACK(dN, normal, 3 * n); BACK(dFront, front, n); BACK(dUV, uv, 2 * n); BACK(dP, p, 3 * n);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RTX_OK;
+}
+
+int32_t rtx_camera_rays(rtx_ctx* ctx, const int32_t* ij, const double* sq, const double* disk, const double* tm, int64_t n, double* rays_out) {
+    if (!ctx || !ij || !sq || !disk || !tm || !rays_out || n < 0) return RTX_ERR_INVALID;
+    if (!ctx->have_camera) return fail(ctx, RTX_ERR_STATE, "camera not set");
+    if (n == 0) return RTX_OK;
+    CU(cudaSetDevice(ctx->device));
+    Scratch sc;
+    int* dIj; double *dSq, *dDisk, *dTm, *dOut;
+    CU(sc.in(&dIj, ij, (size_t)2 * n, ctx->stream)); CU(sc.in(&dSq, sq, (size_t)2 * n, ctx->stream));
+    CU(sc.in(&dDisk, disk, (size_t)2 * n, ctx->stream)); CU(sc.in(&dTm, tm, (size_t)n, ctx->stream));
+    CU(sc.out(&dOut, rays_out, (size_t)7 * n));
+    k_camera_rays<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->C, dIj, dSq, dDisk, dTm, n, dOut);
+    CU(cudaGetLastError());
+    BACK(dOut, rays_out, (size_t)7 * n);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RTX_OK;
+}
+
+static int32_t need_env(rtx_ctx* ctx) {
+    if (!ctx->have_scene) return fail(ctx, RTX_ERR_STATE, "no scene uploaded");
+    if (ctx->S.env_w <= 0) return fail(ctx, RTX_ERR_STATE, "scene has no HDRI environment");
+    return RTX_OK;
+}
+int32_t rtx_hdri_sample(rtx_ctx* ctx, const double* xi, int64_t n, double* dir, double* emission, double* pdf) {
+    if (!ctx || !xi || !dir || !emission || !pdf || n < 0) return RTX_ERR_INVALID;
+    int32_t rc = need_env(ctx);
+    if (rc != RTX_OK) return rc;
+    if (ctx->env_total == 0) return fail(ctx, RTX_ERR_STATE, "HDRI has zero total power");
+    if (n == 0) return RTX_OK;
+    CU(cudaSetDevice(ctx->device));
+    Scratch sc;
+    double *dXi, *dDir, *dEm, *dPdf;
+    CU(sc.in(&dXi, xi, (size_t)2 * n, ctx->stream));
+    CU(sc.out(&dDir, dir, (size_t)3 * n)); CU(sc.out(&dEm, emission, (size_t)3 * n)); CU(sc.out(&dPdf, pdf, (size_t)n));
+    k_hdri_sample<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->S, dXi, n, dDir, dEm, dPdf);
+    CU(cudaGetLastError());
+    BACK(dDir, dir, (size_t)3 * n); BACK(dEm, emission, (size_t)3 * n); BACK(dPdf, pdf, (size_t)n);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RTX_OK;
+}
+int32_t rtx_hdri_pdf(rtx_ctx* ctx, const double* dir, int64_t n, double* pdf) {
+    if (!ctx || !dir || !pdf || n < 0) return RTX_ERR_INVALID;
+    int32_t rc = need_env(ctx);
+    if (rc != RTX_OK) return rc;
+    if (n == 0) return RTX_OK;
+    CU(cudaSetDevice(ctx->device));
+    Scratch sc;
+    double *dDir, *dPdf;
+    CU(sc.in(&dDir, dir, (size_t)3 * n, ctx->stream));
+    CU(sc.out(&dPdf, pdf, (size_t)n));
+    k_hdri_pdf<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->S, dDir, n, dPdf);
+    CU(cudaGetLastError());
+    BACK(dPdf, pdf, (size_t)n);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RTX_OK;
+}
+int32_t rtx_hdri_lookup(rtx_ctx* ctx, const double* dir, int64_t n, double* rgb) {
+    if (!ctx || !dir || !rgb || n < 0) return RTX_ERR_INVALID;
+    int32_t rc = need_env(ctx);
+    if (rc != RTX_OK) return rc;
+    if (n == 0) return RTX_OK;
+    CU(cudaSetDevice(ctx->device));
+    Scratch sc;
+    double *dDir, *dRgb;
+    CU(sc.in(&dDir, dir, (size_t)3 * n, ctx->stream));
+    CU(sc.out(&dRgb, rgb, (size_t)3 * n));
+    k_hdri_lookup<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->S, dDir, n, dRgb);
+    CU(cudaGetLastError());
+    BACK(dRgb, rgb, (size_t)3 * n);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RTX_OK;
+}
+int32_t rtx_hdri_total_power(const rtx_ctx* ctx, double* total_power) {
+    if (!ctx || !total_power) return RTX_ERR_INVALID;
+    if (!ctx->have_scene || ctx->S.env_w <= 0) return RTX_ERR_STATE;
+    *total_power = ctx->env_total;
+    return RTX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,497 @@
+// rtx_device.cuh — device-side data layout and the ray/scene intersection core (sm_100a).
+//
+// Precision model: the reference computes in float64 with no FMA contraction. Primitive tests,
+// instance transforms and hit points are therefore evaluated in float64 in the reference's exact operation
+// order (this TU is compiled with --fmad=false), so primitive ids AND t agree bit-for-bit with the CPU
+// restatement. Only the BVH box tests run in float32, made conservative (outward-rounded boxes, padded ray
+// origin, relative slack on tnear/tfar) so that a box the float64 ray touches is never culled.
+// B200 has a half-rate FP64 pipe, which is what makes this affordable.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rtx_b200.h"
+
+#define RTX_STACK_SIZE 64
+#define RTX_SENTINEL 0x7fffffff
+#define RTX_INF_D (__longlong_as_double(0x7ff0000000000000LL))
+
+struct DEntry {      // 32 B, one per world entry (rt/hittable_list.go:16 insertion order)
+    int kind;        // RTX_GEOM_*
+    int index;       // primitive index (device arrays), or unused for groups
+    int xf_begin, xf_count;
+    int volume;      // -1 or index into volumes
+    int rank;        // test-order rank inside the reference BVH (exact-tie resolution only)
+    int a;           // LIST: first item   MESH: BLAS root node
+    int b;           // LIST: item count   MESH: first triangle of the mesh (device order)
+};
+struct DXform {      // 64 B
+    double a[3];     // TRANSLATE offset | ROTATE_Y (sin, cos, -) | SCALE factor
+    double b[3];     // SCALE inverse factor
+    int type, pad;
+};
+struct DVolume { double neg_inv_density; int mat, pad; };
+struct DMaterial {   // 40 B
+    double fuzz, ior;
+    float albedo[3];
+    int type, tex, pad;
+};
+struct DTexture {    // 32 B
+    double inv_scale;
+    float color[3];
+    int type, even, odd;
+};
+
+struct DevScene {
+    const float4* nodes;  // wide BVH: 8 x float4 (128 B, 128-B aligned) per 4-wide node; TLAS and all BLAS share the array
+    int tlas_root;        // -1: no bounded entries
+    int n_entries;
+    const DEntry* entries;
+    const int* unbounded;  // entries tested for every ray (infinite Plane: universe bbox, rt/plane.go:17)
+    int n_unbounded;
+    const double* spheres;  // 8 doubles: c0.xyz, vel.xyz, radius, -
+    const int* sph_mat;
+    const double* quads;    // 16 doubles: Q, u, v, w, normal, D (rt/quad.go:16-33)
+    const int* quad_mat;
+    const double* tris;     // 10 doubles (80 B, 5 x LDG.128): v0, e1 = v1-v0, e2 = v2-v0, -
+    const double* tri_nrm;  // 4 doubles: unit normal (rt/triangle.go:25), -
+    const int4* tri_info;   // x: primitive id inside its geometry (face order), y: material, z: rank, w: -
+    const double* planes;   // 8 doubles: point, normal, -,-
+    const int* plane_mat;
+    const int2* list_items;  // (kind, device index)
+    const DXform* xforms;
+    const DVolume* volumes;
+    const DMaterial* mats;
+    const DTexture* texs;
+    const int* light_quads;
+    int n_lights;
+    // HDRI
+    const float4* env_tex;  // w*h linear RGB
+    int env_w, env_h, env_is;
+    double env_rot;
+    const double* env_marg;  // h+1
+    const double* env_cond;  // h*(w+1)
+    const double* env_pdf;   // w*h (normalised, rt/hdri.go:217-219)
+    double env_total;
+};
+
+struct RayD {
+    double ox, oy, oz, dx, dy, dz, tm;
+};
+struct RayF {  // float32 ray for box tests: padded near/far origins and reciprocal direction
+    float onx, ony, onz, ofx, ofy, ofz, ix, iy, iz;
+    bool nx, ny, nz;
+};
+struct Hit {
+    double t;
+    int entry;  // -1 = miss
+    int kind;   // RTX_GEOM_SPHERE..PLANE of the primitive that was hit, or 6 = volume medium
+    int prim;   // device primitive index (spheres/quads/tris/planes arrays)
+    int item;   // primitive id inside the entry's geometry (list item / mesh face / 0)
+};
+#define RTX_KIND_VOLUME 6
+
+struct TraceCounters {
+    unsigned nodes, tris, spheres, quads, planes;
+};
+
+// ---- small float64 helpers in the reference's operation order -------------------------------------------------
+struct D3 { double x, y, z; };
+__device__ __forceinline__ D3 d3(double x, double y, double z) { D3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ D3 sub(D3 a, D3 b) { return d3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ D3 add(D3 a, D3 b) { return d3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ D3 scale(D3 a, double t) { return d3(t * a.x, t * a.y, t * a.z); }
+__device__ __forceinline__ double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }  // (x+y)+z like rt/vec3.go:79
+__device__ __forceinline__ D3 cross(D3 a, D3 b) { return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ double len2(D3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+__device__ __forceinline__ D3 unit(D3 a) {  // rt/vec3.go:32-38
+    double l = sqrt(len2(a));
+    if (l == 0) return a;
+    return scale(a, 1 / l);
+}
+__device__ __forceinline__ D3 ld3(const double* p) { return d3(p[0], p[1], p[2]); }
+
+// ---- instance transforms (rt/transform.go:93-102, :159-187, :408-440): ray into object space, outermost first --
+__device__ __forceinline__ void xform_ray(const DevScene& S, const DEntry& e, RayD& r) {
+    for (int k = 0; k < e.xf_count; k++) {
+        const DXform& x = S.xforms[e.xf_begin + k];
+        if (x.type == RTX_XF_TRANSLATE) {
+            r.ox -= x.a[0]; r.oy -= x.a[1]; r.oz -= x.a[2];
+        } else if (x.type == RTX_XF_ROTATE_Y) {
+            double s = x.a[0], c = x.a[1];
+            double ox = c * r.ox - s * r.oz, oz = s * r.ox + c * r.oz;
+            double dx = c * r.dx - s * r.dz, dz = s * r.dx + c * r.dz;
+            r.ox = ox; r.oz = oz; r.dx = dx; r.dz = dz;
+        } else {
+            r.ox *= x.b[0]; r.oy *= x.b[1]; r.oz *= x.b[2];
+            r.dx *= x.b[0]; r.dy *= x.b[1]; r.dz *= x.b[2];
+        }
+    }
+}
+// hit point and normal back to world space, innermost first
+__device__ __forceinline__ void xform_back(const DevScene& S, const DEntry& e, D3& P, D3& N) {
+    for (int k = e.xf_count - 1; k >= 0; k--) {
+        const DXform& x = S.xforms[e.xf_begin + k];
+        if (x.type == RTX_XF_TRANSLATE) {
+            P.x += x.a[0]; P.y += x.a[1]; P.z += x.a[2];
+        } else if (x.type == RTX_XF_ROTATE_Y) {
+            double s = x.a[0], c = x.a[1];
+            double px = c * P.x + s * P.z, pz = -s * P.x + c * P.z;
+            double nx = c * N.x + s * N.z, nz = -s * N.x + c * N.z;
+            P.x = px; P.z = pz; N.x = nx; N.z = nz;
+        } else {
+            P.x *= x.a[0]; P.y *= x.a[1]; P.z *= x.a[2];
+            N = unit(d3(N.x * x.b[0], N.y * x.b[1], N.z * x.b[2]));
+        }
+    }
+}
+
+// ---- primitive tests: return t, or NaN when the reference's Hit would return false before its interval test ----
+#define RTX_NAN_D (__longlong_as_double(0x7ff8000000000000LL))
+
+// rt/sphere.go:63-85. Open interval (Surrounds): the root choice depends on the interval, so it is evaluated here.
+__device__ __forceinline__ double isect_sphere(const double* s, const RayD& r, double tmin, double tmax) {
+    D3 c = d3(s[0] + r.tm * s[3], s[1] + r.tm * s[4], s[2] + r.tm * s[5]);
+    D3 o = d3(r.ox, r.oy, r.oz), d = d3(r.dx, r.dy, r.dz);
+    D3 oc = sub(c, o);
+    double a = len2(d);
+    double h = dot(d, oc);
+    double cc = len2(oc) - s[6] * s[6];
+    double disc = h * h - a * cc;
+    if (disc < 0) return RTX_NAN_D;
+    double sq = sqrt(disc);
+    double root = (h - sq) / a;
+    if (!(tmin < root && root < tmax)) {
+        root = (h + sq) / a;
+        if (!(tmin < root && root < tmax)) return RTX_NAN_D;
+    }
+    return root;
+}
+// rt/quad.go:44-84 (closed interval is applied by the caller)
+__device__ __forceinline__ double isect_quad(const double* q, const RayD& r, double tmin, double tmax, double* uv) {
+    D3 n = ld3(q + 12), o = d3(r.ox, r.oy, r.oz), d = d3(r.dx, r.dy, r.dz);
+    double denom = dot(n, d);
+    if (fabs(denom) < 1e-8) return RTX_NAN_D;
+    double t = (q[15] - dot(n, o)) / denom;
+    if (!(tmin <= t && t <= tmax)) return RTX_NAN_D;
+    D3 P = add(o, scale(d, t));
+    D3 pl = sub(P, ld3(q));
+    D3 w = ld3(q + 9);
+    double alpha = dot(w, cross(pl, ld3(q + 6)));
+    double beta = dot(w, cross(ld3(q + 3), pl));
+    if (!(0.0 <= alpha && alpha <= 1.0) || !(0.0 <= beta && beta <= 1.0)) return RTX_NAN_D;
+    if (uv) { uv[0] = alpha; uv[1] = beta; }
+    return t;
+}
+// rt/triangle.go:57-104 Möller–Trumbore; e1/e2 are the same float64 values the reference recomputes per call.
+__device__ __forceinline__ double isect_tri(const double* tp, const RayD& r, double* uv) {
+    const double2* p2 = reinterpret_cast<const double2*>(tp);
+    double2 a0 = __ldg(p2), a1 = __ldg(p2 + 1), a2 = __ldg(p2 + 2), a3 = __ldg(p2 + 3), a4 = __ldg(p2 + 4);
+    D3 v0 = d3(a0.x, a0.y, a1.x), e1 = d3(a1.y, a2.x, a2.y), e2 = d3(a3.x, a3.y, a4.x);
+    D3 o = d3(r.ox, r.oy, r.oz), d = d3(r.dx, r.dy, r.dz);
+    D3 h = cross(d, e2);
+    double a = dot(e1, h);
+    if (fabs(a) < 1e-8) return RTX_NAN_D;
+    double f = 1.0 / a;
+    D3 s = sub(o, v0);
+    double u = f * dot(s, h);
+    if (u < 0.0 || u > 1.0) return RTX_NAN_D;
+    D3 q = cross(s, e1);
+    double v = f * dot(d, q);
+    if (v < 0.0 || u + v > 1.0) return RTX_NAN_D;
+    if (uv) { uv[0] = u; uv[1] = v; }
+    return f * dot(e2, q);
+}
+// rt/plane.go:24-34 (open interval applied by the caller)
+__device__ __forceinline__ double isect_plane(const double* p, const RayD& r) {
+    D3 n = ld3(p + 3), o = d3(r.ox, r.oy, r.oz), d = d3(r.dx, r.dy, r.dz);
+    double denom = dot(n, d);
+    if (fabs(denom) < 1e-8) return RTX_NAN_D;
+    return dot(sub(ld3(p), o), n) / denom;
+}
+
+__device__ __forceinline__ bool kind_closed(int kind) { return kind == RTX_GEOM_QUAD || kind == RTX_GEOM_TRIANGLE || kind == RTX_KIND_VOLUME; }
+
+// Generic primitive t with the reference's interval convention against [tmin, tmax].
+__device__ __forceinline__ double isect_prim(const DevScene& S, int kind, int idx, const RayD& r, double tmin, double tmax, TraceCounters* tc) {
+    double t;
+    if (kind == RTX_GEOM_SPHERE) {
+        if (tc) tc->spheres++;
+        return isect_sphere(S.spheres + 8 * (size_t)idx, r, tmin, tmax);
+    } else if (kind == RTX_GEOM_QUAD) {
+        if (tc) tc->quads++;
+        return isect_quad(S.quads + 16 * (size_t)idx, r, tmin, tmax, nullptr);
+    } else if (kind == RTX_GEOM_TRIANGLE) {
+        if (tc) tc->tris++;
+        t = isect_tri(S.tris + 10 * (size_t)idx, r, nullptr);
+        return (tmin <= t && t <= tmax) ? t : RTX_NAN_D;
+    } else {
+        if (tc) tc->planes++;
+        t = isect_plane(S.planes + 8 * (size_t)idx, r);
+        return (tmin < t && t < tmax) ? t : RTX_NAN_D;
+    }
+}
+
+// ---- float32 conservative ray ---------------------------------------------------------------------------------
+#define RTX_BOX_EPS 4.76837158e-7f  /* 2^-21 relative slack on tnear / tfar */
+__device__ __forceinline__ void make_rayf(const RayD& r, RayF& f) {
+    float ox = __double2float_rn(r.ox), oy = __double2float_rn(r.oy), oz = __double2float_rn(r.oz);
+    float dx = __double2float_rn(r.dx), dy = __double2float_rn(r.dy), dz = __double2float_rn(r.dz);
+    // pad >= |o - fl(o)| = 2^-24 |o|; 2^-22 |o| + tiny keeps a 4x margin
+    float px = fmaf(fabsf(ox), 2.38418579e-7f, 1e-30f), py = fmaf(fabsf(oy), 2.38418579e-7f, 1e-30f), pz = fmaf(fabsf(oz), 2.38418579e-7f, 1e-30f);
+    f.nx = signbit(dx); f.ny = signbit(dy); f.nz = signbit(dz);
+    f.ix = 1.0f / dx; f.iy = 1.0f / dy; f.iz = 1.0f / dz;
+    f.onx = f.nx ? ox - px : ox + px; f.ofx = f.nx ? ox + px : ox - px;
+    f.ony = f.ny ? oy - py : oy + py; f.ofy = f.ny ? oy + py : oy - py;
+    f.onz = f.nz ? oz - pz : oz + pz; f.ofz = f.nz ? oz + pz : oz - pz;
+}
+
+// One 4-wide node: returns conservative entry distances (inf = culled) for the 4 children.
+__device__ __forceinline__ void node_test(const float4* __restrict__ n, const RayF& f, float tmin, float tmax, float d[4], int c[4]) {
+    float4 lox = __ldg(n + 0), loy = __ldg(n + 1), loz = __ldg(n + 2), hix = __ldg(n + 3), hiy = __ldg(n + 4), hiz = __ldg(n + 5);
+    int4 ch = __ldg(reinterpret_cast<const int4*>(n + 6));
+    float4 nx = f.nx ? hix : lox, fx = f.nx ? lox : hix;
+    float4 ny = f.ny ? hiy : loy, fy = f.ny ? loy : hiy;
+    float4 nz = f.nz ? hiz : loz, fz = f.nz ? loz : hiz;
+#define RTX_CHILD(k, comp)                                                                     \
+    {                                                                                          \
+        float tnx = (nx.comp - f.onx) * f.ix, tny = (ny.comp - f.ony) * f.iy, tnz = (nz.comp - f.onz) * f.iz; \
+        float tfx = (fx.comp - f.ofx) * f.ix, tfy = (fy.comp - f.ofy) * f.iy, tfz = (fz.comp - f.ofz) * f.iz; \
+        float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                   \
+        float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));                                   \
+        tn = fmaf(-fabsf(tn), RTX_BOX_EPS, tn);                                                \
+        tf = fmaf(fabsf(tf), RTX_BOX_EPS, tf);                                                 \
+        d[k] = (tn <= tf) ? tn : __int_as_float(0x7f800000);                                   \
+    }
+    RTX_CHILD(0, x) RTX_CHILD(1, y) RTX_CHILD(2, z) RTX_CHILD(3, w)
+#undef RTX_CHILD
+    c[0] = ch.x; c[1] = ch.y; c[2] = ch.z; c[3] = ch.w;
+}
+
+// Exact ties in t: the reference keeps whichever primitive its traversal order and interval conventions favour
+// (quads/triangles accept t == max, spheres/planes do not; rt/quad.go:53, rt/triangle.go:89, rt/sphere.go:80).
+// For two candidates a (tested earlier) and b (tested later) at the same t the survivor is b iff b is closed.
+__device__ __forceinline__ bool tie_candidate_wins(int crank_e, int crank_p, int ckind, int brank_e, int brank_p, int bkind) {
+    bool cand_later = (crank_e > brank_e) || (crank_e == brank_e && crank_p > brank_p);
+    return cand_later ? kind_closed(ckind) : !kind_closed(bkind);
+}
+
+struct BestRank { int e, p; };
+
+template <bool ANY_HIT>
+struct Tracer {
+    const DevScene& S;
+    TraceCounters* tc;
+    double tmin, tlimit;  // caller's interval
+    Hit best;
+    BestRank brank;
+    bool have;
+
+    __device__ __forceinline__ Tracer(const DevScene& s, double tmn, double tmx, TraceCounters* c) : S(s), tc(c), tmin(tmn), tlimit(tmx) {
+        best.t = tmx; best.entry = -1; best.kind = -1; best.prim = -1; best.item = -1;
+        brank.e = -1; brank.p = -1; have = false;
+    }
+    // candidate at parameter t (already inside the primitive's own interval convention w.r.t. [tmin, best.t])
+    __device__ __forceinline__ void offer(double t, int entry, int erank, int kind, int prim, int item, int prank) {
+        if (!(t == t)) return;
+        if (t == best.t) {
+            if (!have) { if (!kind_closed(kind)) return; }
+            else if (!tie_candidate_wins(erank, prank, kind, brank.e, brank.p, best.kind)) return;
+        }
+        best.t = t; best.entry = entry; best.kind = kind; best.prim = prim; best.item = item;
+        brank.e = erank; brank.p = prank; have = true;
+    }
+    // candidate interval for primitive tests: accept up to and including the current best (ties resolved in offer)
+    __device__ __forceinline__ double tmax_closed() const { return best.t; }
+    __device__ __forceinline__ double tmax_open() const { return have ? nextafter(best.t, RTX_INF_D) : best.t; }
+
+    __device__ __forceinline__ void test_prim(int kind, int idx, const RayD& r, int entry, int erank, int item, int prank) {
+        // open-interval primitives must still be allowed to tie with an existing best hit
+        double mx = kind_closed(kind) ? tmax_closed() : tmax_open();
+        double t = isect_prim(S, kind, idx, r, tmin, mx, tc);
+        offer(t, entry, erank, kind, idx, item, prank);
+    }
+};
+
+// Closest boundary crossing of an entry's geometry in [tmin, tmax] for Volume (rt/volume.go:38-46): HittableList
+// semantics (rt/hittable_list.go:31-45) over the list items, or a single primitive.
+__device__ __forceinline__ double isect_boundary(const DevScene& S, const DEntry& e, const RayD& ro, double tmin, double tmax, TraceCounters* tc) {
+    double closest = tmax;
+    bool hit = false;
+    if (e.kind == RTX_GEOM_LIST) {
+        for (int k = 0; k < e.b; k++) {
+            int2 it = S.list_items[e.a + k];
+            double t = isect_prim(S, it.x, it.y, ro, tmin, closest, tc);
+            if (t == t) { closest = t; hit = true; }
+        }
+    } else {
+        double t = isect_prim(S, e.kind, e.index, ro, tmin, closest, tc);
+        if (t == t) { closest = t; hit = true; }
+    }
+    return hit ? closest : RTX_NAN_D;
+}
+
+// uniform in (0,1) for the Volume free-flight draw, supplied by the caller's counter RNG
+struct VolumeRng {
+    uint32_t k0, k1, c0, c1, c2;
+    bool transparent;  // level-1 parity protocol: volumes do not intersect
+};
+__device__ double rtx_volume_uniform(const VolumeRng& vr, int entry);  // defined in rtx_kernels.cu (Philox)
+
+// ---- the scene query: closest hit (or any hit) of world.Hit(r, [tmin,tmax]) ----------------------------------------
+template <bool ANY_HIT>
+__device__ __noinline__ Hit trace_scene(const DevScene& S, const RayD& rw, double tmin, double tmax, const VolumeRng& vr, TraceCounters* tc) {
+    Tracer<ANY_HIT> T(S, tmin, tmax, tc);
+    // entries with unbounded geometry are tested for every ray
+    for (int k = 0; k < S.n_unbounded; k++) {
+        int ei = S.unbounded[k];
+        DEntry e = S.entries[ei];
+        RayD ro = rw;
+        xform_ray(S, e, ro);
+        T.test_prim(e.kind, e.index, ro, ei, e.rank, 0, 0);
+        if (ANY_HIT && T.have) return T.best;
+    }
+    if (S.tlas_root < 0) return T.best;
+
+    int stack[RTX_STACK_SIZE];
+    int sp = 0;
+    RayF fw;
+    make_rayf(rw, fw);
+    RayF f = fw;
+    RayD ro = rw;   // current (object-space when inside an instance) ray
+    int cur = -1;   // entry index of the instance being traversed
+    DEntry ce;
+    float ftmin = __double2float_rd(tmin);
+    int node = S.tlas_root;
+    for (;;) {
+        if (node >= 0) {
+            float d[4]; int c[4];
+            if (tc) tc->nodes++;
+            node_test(S.nodes + 8 * (size_t)node, f, ftmin, __double2float_ru(T.best.t), d, c);
+            // sort the 4 children by entry distance (5-comparator network)
+#define RTX_CSWAP(i, j) if (d[j] < d[i]) { float td = d[i]; d[i] = d[j]; d[j] = td; int tcx = c[i]; c[i] = c[j]; c[j] = tcx; }
+            RTX_CSWAP(0, 1) RTX_CSWAP(2, 3) RTX_CSWAP(0, 2) RTX_CSWAP(1, 3) RTX_CSWAP(1, 2)
+#undef RTX_CSWAP
+            const float INF = __int_as_float(0x7f800000);
+            if (d[3] < INF) stack[sp++] = c[3];
+            if (d[2] < INF) stack[sp++] = c[2];
+            if (d[1] < INF) stack[sp++] = c[1];
+            if (d[0] < INF) { node = c[0]; continue; }
+        } else {
+            int code = ~node;
+            if (cur < 0) {
+                // TLAS leaf: exactly one world entry
+                int ei = code;
+                DEntry e = S.entries[ei];
+                RayD r2 = rw;
+                xform_ray(S, e, r2);
+                if (e.volume >= 0) {
+                    if (!vr.transparent) {
+                        // rt/volume.go:34-79
+                        double t1 = isect_boundary(S, e, r2, -RTX_INF_D, RTX_INF_D, tc);
+                        if (t1 == t1) {
+                            double t2 = isect_boundary(S, e, r2, t1 + 0.0001, RTX_INF_D, tc);
+                            if (t2 == t2) {
+                                if (t1 < tmin) t1 = tmin;
+                                if (t2 > T.best.t) t2 = T.best.t;
+                                if (t1 < t2) {
+                                    if (t1 < 0) t1 = 0;
+                                    double rayLength = sqrt(rw.dx * rw.dx + rw.dy * rw.dy + rw.dz * rw.dz);
+                                    double inside = (t2 - t1) * rayLength;
+                                    double hd = S.volumes[e.volume].neg_inv_density * log(rtx_volume_uniform(vr, ei));
+                                    if (!(hd > inside)) T.offer(t1 + hd / rayLength, ei, e.rank, RTX_KIND_VOLUME, e.volume, 0, 0);
+                                }
+                            }
+                        }
+                    }
+                } else if (e.kind == RTX_GEOM_MESH) {
+                    stack[sp++] = RTX_SENTINEL;
+                    cur = ei; ce = e; ro = r2;
+                    make_rayf(ro, f);
+                    node = e.a;
+                    continue;
+                } else if (e.kind == RTX_GEOM_LIST) {
+                    for (int k = 0; k < e.b; k++) {
+                        int2 it = S.list_items[e.a + k];
+                        T.test_prim(it.x, it.y, r2, ei, e.rank, k, k);
+                    }
+                } else {
+                    T.test_prim(e.kind, e.index, r2, ei, e.rank, 0, 0);
+                }
+            } else {
+                // BLAS leaf: code = first << 3 | (count - 1), triangles contiguous in device order
+                int first = code >> 3, cnt = (code & 7) + 1;
+                for (int k = 0; k < cnt; k++) {
+                    int ti = first + k;
+                    if (tc) tc->tris++;
+                    double t = isect_tri(S.tris + 10 * (size_t)ti, ro, nullptr);
+                    if (tmin <= t && t <= T.best.t) {
+                        int4 info = __ldg(S.tri_info + ti);
+                        T.offer(t, cur, ce.rank, RTX_GEOM_TRIANGLE, ti, info.x, info.z);
+                    }
+                }
+            }
+            if (ANY_HIT && T.have) return T.best;
+        }
+        // pop
+        if (sp == 0) break;
+        node = stack[--sp];
+        if (node == RTX_SENTINEL) {
+            cur = -1; f = fw;
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    return T.best;
+}
+
+// Full hit record (rec.P, rec.Normal against the ray, FrontFace, material) of a finished query.
+struct HitInfo {
+    D3 P, N;
+    int mat;
+    bool front;
+    double u, v;
+};
+__device__ __forceinline__ void finalize_hit(const DevScene& S, const RayD& rw, const Hit& h, bool want_uv, HitInfo& out) {
+    DEntry e = S.entries[h.entry];
+    out.u = 0; out.v = 0;
+    if (h.kind == RTX_KIND_VOLUME) {  // rt/volume.go:72-76
+        out.P = d3(rw.ox + h.t * rw.dx, rw.oy + h.t * rw.dy, rw.oz + h.t * rw.dz);
+        out.N = d3(1, 0, 0);
+        out.front = true;
+        out.mat = S.volumes[h.prim].mat;
+        return;
+    }
+    RayD r = rw;
+    xform_ray(S, e, r);
+    D3 o = d3(r.ox, r.oy, r.oz), d = d3(r.dx, r.dy, r.dz);
+    D3 P = add(o, scale(d, h.t));  // r.At(t), rt/ray.go:21
+    D3 n;
+    if (h.kind == RTX_GEOM_SPHERE) {
+        const double* s = S.spheres + 8 * (size_t)h.prim;
+        D3 c = d3(s[0] + r.tm * s[3], s[1] + r.tm * s[4], s[2] + r.tm * s[5]);
+        n = scale(sub(P, c), 1 / s[6]);  // Div(Radius)
+        out.mat = S.sph_mat[h.prim];
+        if (want_uv) {  // getSphereUV rt/sphere.go:53-59
+            const double PI = 3.14159265358979323846;
+            double theta = acos(-n.y), phi = atan2(-n.z, n.x) + PI;
+            out.u = phi / (2 * PI); out.v = theta / PI;
+        }
+    } else if (h.kind == RTX_GEOM_QUAD) {
+        const double* q = S.quads + 16 * (size_t)h.prim;
+        n = ld3(q + 12);
+        out.mat = S.quad_mat[h.prim];
+        if (want_uv) { double uv[2] = {0, 0}; isect_quad(q, r, -RTX_INF_D, RTX_INF_D, uv); out.u = uv[0]; out.v = uv[1]; }
+    } else if (h.kind == RTX_GEOM_TRIANGLE) {
+        n = ld3(S.tri_nrm + 4 * (size_t)h.prim);
+        out.mat = S.tri_info[h.prim].y;
+        if (want_uv) { double uv[2] = {0, 0}; isect_tri(S.tris + 10 * (size_t)h.prim, r, uv); out.u = uv[0]; out.v = uv[1]; }
+    } else {
+        n = ld3(S.planes + 8 * (size_t)h.prim + 3);
+        out.mat = S.plane_mat[h.prim];
+    }
+    out.front = dot(d, n) < 0;  // SetFaceNormal with the object-space ray (rt/hittable.go:20-30); never recomputed afterwards
+    if (!out.front) n = d3(-n.x, -n.y, -n.z);
+    xform_back(S, e, P, n);
+    out.P = P; out.N = n;
+}

@@ -1,0 +1,602 @@
+// rtx_kernels.cuh — the wavefront path tracer: generate -> extend -> shade -> connect -> accumulate, plus resolve
+// and the batch entry points used by the parity tests. Hand-written CUDA for sm_100a; no tensor cores (nothing on
+// this path is a dense contraction). One wavefront iteration advances every in-flight path by one bounce.
+//
+// Mapping to the reference (paths relative to /root/reference/):
+//   k_generate    Camera.GetRay                      rt/camera.go:368-435
+//   k_extend      world.Hit(r, [0.001, inf))         rt/camera.go:451 -> rt/bvh.go:219, rt/aabb.go:59, primitives
+//   k_shade       rayColorInternal body              rt/camera.go:453-518, rt/material.go, rt/texture.go, rt/hdri.go
+//   k_connect     shadow world.Hit of NEE            rt/camera.go:582, :639
+//   k_accumulate  pixelColor.Add(...)                rt/bucket_renderer.go:271
+//   k_resolve     scale / gamma / clamp / RGBA8      rt/bucket_renderer.go:275-285
+#pragma once
+#include "rtx_device.cuh"
+
+// ---- Philox4x32-10 counter RNG: key = run seed, counter = (pixel, global sample, bounce, stream) ------------------
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ double u01(uint32_t x) { return ((double)x + 0.5) * 2.3283064365386963e-10; }   // (0,1)
+__device__ __forceinline__ float u01f(uint32_t x) { return ((float)(x >> 8) + 0.5f) * 5.9604645e-8f; }      // (0,1), 24 bits
+
+__device__ double rtx_volume_uniform(const VolumeRng& vr, int entry) {
+    uint4 r = philox4x32(vr.c0, vr.c1, vr.c2, 64u + (uint32_t)entry, vr.k0, vr.k1);
+    return u01(r.x);
+}
+
+enum { Q_MISS = 0, Q_LAMBERTIAN = 1, Q_METAL = 2, Q_DIELECTRIC = 3, Q_LIGHT = 4, Q_ISOTROPIC = 5, Q_COUNT = 6 };
+enum { STREAM_CAMERA = 0, STREAM_LENS = 1, STREAM_NEE = 2, STREAM_SCATTER = 3 };
+
+struct DevCamera {  // post-Initialize state (rt/camera.go:41-56)
+    double center[3], pixel00[3], du[3], dv[3], u[3], v[3], w[3];
+    double defocus_radius, defocus_angle, focus_dist, viewport_w, viewport_h;
+    double look_from[3], look_vel[3], look_at[3], look_at_vel[3], vup[3], forward[3];
+    int camera_motion, free_camera;
+    int width, height;
+    float background[3];
+    int use_sky, phantom, max_depth;
+};
+
+struct Ctl {  // device-resident control block of the wavefront loop
+    unsigned long long cursor, total;  // next path id / paths of this pass
+    unsigned long long gen_base;
+    int n_active, n_cont, n_gen, n_free, n_next, n_shadow, n_done;
+    int n_mat[Q_COUNT];
+    int done, pad;
+    // statistics
+    unsigned long long ext_rays, shadow_rays, nodes, tris, spheres, quads, planes, iterations;
+};
+
+struct Pool {  // SoA path state; one entry per in-flight path slot
+    int capacity;
+    double2* ray_o;   // [2P] (ox,oy) (oz,time)
+    double2* ray_d;   // [2P] (dx,dy) (dz,-)
+    float4* thr;      // throughput rgb, w = bits: bounce | allowLightHits << 16
+    float4* rad;      // accumulated radiance rgb
+    uint2* pix;       // (pixel index, global sample index)
+    double2* hit_p;   // [2P] (Px,Py) (Pz,t)
+    double2* hit_n;   // [2P] (Nx,Ny) (Nz, bits: material | front << 31)
+    int* q_a;         // active queue, ping
+    int* q_b;         // active queue, pong
+    int* q_free;      // free-slot stack
+    int* q_mat;       // [Q_COUNT * P] material-sorted shading queues
+    int* q_done;      // finished paths awaiting accumulation
+    double2* sh_d;    // [2 * 2P] shadow requests: (dx,dy) (dz,tmax)
+    float4* sh_c;     // [2P] contribution rgb, w = bits: slot | kind << 30
+};
+
+struct PassParams {
+    int spp, max_depth, camera_max_depth;
+    uint32_t seed_lo, seed_hi, sample_base;
+    int moments, count_stats;
+};
+
+// warp-aggregated queue append: one atomic per warp (ballot + popc), returns this lane's position
+__device__ __forceinline__ int warp_append(int* counter, bool pred) {
+    unsigned mask = __ballot_sync(__activemask(), pred);
+    if (!pred) return -1;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1));
+}
+
+// ---- K0: iteration bookkeeping ---------------------------------------------------------------------------------
+__global__ void k_iter_begin(Ctl* ctl) {
+    if (threadIdx.x != 0) return;
+    int n_cont = ctl->n_next;
+    unsigned long long remaining = ctl->total - ctl->cursor;
+    int n_gen = (int)min((unsigned long long)ctl->n_free, remaining);
+    ctl->gen_base = ctl->cursor;
+    ctl->cursor += n_gen;
+    ctl->n_free -= n_gen;
+    ctl->n_cont = n_cont;
+    ctl->n_gen = n_gen;
+    ctl->n_active = n_cont + n_gen;
+    ctl->n_next = 0; ctl->n_shadow = 0; ctl->n_done = 0;
+    for (int i = 0; i < Q_COUNT; i++) ctl->n_mat[i] = 0;
+    ctl->done = (n_cont + n_gen == 0);
+    ctl->iterations += (n_cont + n_gen != 0);
+}
+
+// ---- K1: camera ray generation (rt/camera.go:368-435) ----------------------------------------------------------
+__device__ __forceinline__ RayD camera_ray(const DevCamera& C, int i, int j, double offx, double offy, double tm, double px, double py) {
+    D3 center, du, dv, uu, vv;
+    D3 p00;
+    if (!C.camera_motion && !C.free_camera) {
+        center = ld3(C.center); du = ld3(C.du); dv = ld3(C.dv); uu = ld3(C.u); vv = ld3(C.v); p00 = ld3(C.pixel00);
+    } else {  // slow path :390-417
+        center = add(ld3(C.look_from), scale(ld3(C.look_vel), tm));
+        D3 ww;
+        if (C.free_camera) ww = d3(-C.forward[0], -C.forward[1], -C.forward[2]);
+        else ww = unit(sub(center, add(ld3(C.look_at), scale(ld3(C.look_at_vel), tm))));
+        uu = unit(cross(ld3(C.vup), ww));
+        vv = cross(ww, uu);
+        D3 vpU = scale(uu, C.viewport_w), vpV = scale(d3(-vv.x, -vv.y, -vv.z), C.viewport_h);
+        du = scale(vpU, 1 / (double)C.width);
+        dv = scale(vpV, 1 / (double)C.height);
+        D3 ul = sub(sub(sub(center, scale(ww, C.focus_dist)), scale(vpU, 1 / 2.0)), scale(vpV, 1 / 2.0));
+        p00 = add(ul, scale(add(du, dv), 0.5));
+    }
+    D3 ps = add(add(p00, scale(du, (double)i + offx)), scale(dv, (double)j + offy));
+    D3 ro = center;
+    if (C.defocus_angle > 0) {  // defocusDiskSample :354-362
+        D3 dU = scale(uu, C.defocus_radius), dV = scale(vv, C.defocus_radius);
+        ro = add(add(center, scale(dU, px)), scale(dV, py));
+    }
+    D3 rd = sub(ps, ro);
+    RayD r; r.ox = ro.x; r.oy = ro.y; r.oz = ro.z; r.dx = rd.x; r.dy = rd.y; r.dz = rd.z; r.tm = tm;
+    return r;
+}
+
+__global__ void __launch_bounds__(256) k_generate(Ctl* ctl, Pool pool, int* q_cur, DevCamera C, PassParams pp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ctl->n_gen) return;
+    int slot = pool.q_free[ctl->n_free + i];
+    unsigned long long pid = ctl->gen_base + (unsigned long long)i;
+    unsigned npix = (unsigned)C.width * (unsigned)C.height;
+    uint32_t sample = pp.sample_base + (uint32_t)(pid / npix);
+    uint32_t pixel = (uint32_t)(pid % npix);
+    int px = pixel % C.width, py = pixel / C.width;
+    uint4 r0 = philox4x32(pixel, sample, 0, STREAM_CAMERA, pp.seed_lo, pp.seed_hi);
+    double offx = u01(r0.x) - 0.5, offy = u01(r0.y) - 0.5, tm = u01(r0.z);
+    double lx = 0, ly = 0;
+    if (C.defocus_angle > 0) {  // uniform unit disk (the reference rejection-samples the same distribution, rt/vec3.go:66-77)
+        float rr = sqrtf(u01f(r0.w));
+        uint4 r1 = philox4x32(pixel, sample, 0, STREAM_LENS, pp.seed_lo, pp.seed_hi);
+        float sn, cs;
+        sincospif(2.0f * u01f(r1.x), &sn, &cs);
+        lx = rr * cs; ly = rr * sn;
+    }
+    RayD r = camera_ray(C, px, py, offx, offy, tm, lx, ly);
+    pool.ray_o[2 * slot] = make_double2(r.ox, r.oy);
+    pool.ray_o[2 * slot + 1] = make_double2(r.oz, r.tm);
+    pool.ray_d[2 * slot] = make_double2(r.dx, r.dy);
+    pool.ray_d[2 * slot + 1] = make_double2(r.dz, 0.0);
+    pool.thr[slot] = make_float4(1.f, 1.f, 1.f, __int_as_float(0 | (1 << 16)));
+    pool.rad[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pool.pix[slot] = make_uint2(pixel, sample);
+    q_cur[ctl->n_cont + i] = slot;
+}
+
+__device__ __forceinline__ void flush_counters(Ctl* ctl, const TraceCounters& tc, bool shadow, bool valid) {
+    // block-level reduction would be cheaper; counters are a debug/measurement option
+    if (!valid) return;
+    atomicAdd(&ctl->nodes, (unsigned long long)tc.nodes);
+    atomicAdd(&ctl->tris, (unsigned long long)tc.tris);
+    atomicAdd(&ctl->spheres, (unsigned long long)tc.spheres);
+    atomicAdd(&ctl->quads, (unsigned long long)tc.quads);
+    atomicAdd(&ctl->planes, (unsigned long long)tc.planes);
+}
+
+// ---- K2: extend — closest hit of every active path, then binning into material-sorted shading queues -------------
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_extend(Ctl* ctl, Pool pool, const int* q_cur, DevScene S, PassParams pp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = ctl->n_active;
+    bool valid = i < n;
+    int q = -1, slot = -1;
+    if (valid) {
+        slot = q_cur[i];
+        double2 a = pool.ray_o[2 * slot], b = pool.ray_o[2 * slot + 1], c = pool.ray_d[2 * slot], d = pool.ray_d[2 * slot + 1];
+        RayD r; r.ox = a.x; r.oy = a.y; r.oz = b.x; r.tm = b.y; r.dx = c.x; r.dy = c.y; r.dz = d.x;
+        uint2 ps = pool.pix[slot];
+        int bounce = __float_as_int(pool.thr[slot].w) & 0xffff;
+        VolumeRng vr; vr.k0 = pp.seed_lo; vr.k1 = pp.seed_hi; vr.c0 = ps.x; vr.c1 = ps.y; vr.c2 = (uint32_t)bounce * 4u; vr.transparent = false;
+        TraceCounters tc = {0, 0, 0, 0, 0};
+        Hit h = trace_scene<false>(S, r, 0.001, RTX_INF_D, vr, COUNT ? &tc : nullptr);
+        if (COUNT) flush_counters(ctl, tc, false, true);
+        if (h.entry < 0) {
+            q = Q_MISS;
+        } else {
+            HitInfo hi;
+            finalize_hit(S, r, h, false, hi);
+            pool.hit_p[2 * slot] = make_double2(hi.P.x, hi.P.y);
+            pool.hit_p[2 * slot + 1] = make_double2(hi.P.z, h.t);
+            long long bits = (long long)(unsigned)hi.mat | (hi.front ? (1LL << 31) : 0);
+            pool.hit_n[2 * slot] = make_double2(hi.N.x, hi.N.y);
+            pool.hit_n[2 * slot + 1] = make_double2(hi.N.z, __longlong_as_double(bits));
+            int mt = S.mats[hi.mat].type;
+            q = mt == RTX_MAT_LAMBERTIAN ? Q_LAMBERTIAN : mt == RTX_MAT_METAL ? Q_METAL : mt == RTX_MAT_DIELECTRIC ? Q_DIELECTRIC
+                : mt == RTX_MAT_DIFFUSE_LIGHT ? Q_LIGHT : Q_ISOTROPIC;
+        }
+    }
+    // material-sorted queues: one warp-aggregated append per queue
+#pragma unroll
+    for (int k = 0; k < Q_COUNT; k++) {
+        int pos = warp_append(&ctl->n_mat[k], q == k);
+        if (q == k) pool.q_mat[(size_t)k * pool.capacity + pos] = slot;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->ext_rays, (unsigned long long)n);
+}
+
+// ---- textures (rt/texture.go:43-45, :63-77) ----------------------------------------------------------------------
+__device__ __forceinline__ float3 tex_value(const DevScene& S, int id, D3 p) {
+    DTexture t = S.texs[id];
+    for (int guard = 0; guard < 8 && t.type == RTX_TEX_CHECKER; guard++) {
+        long long xi = (long long)floor(t.inv_scale * p.x + 1e-4);
+        long long yi = (long long)floor(t.inv_scale * p.y + 1e-4);
+        long long zi = (long long)floor(t.inv_scale * p.z + 1e-4);
+        bool even = ((xi + yi + zi) % 2) == 0;
+        t = S.texs[even ? t.even : t.odd];
+    }
+    return make_float3(t.color[0], t.color[1], t.color[2]);
+}
+
+// ---- HDRI (rt/hdri.go) -------------------------------------------------------------------------------------------
+__device__ __forceinline__ int clampi_dev(int x, int low, int high) { return x < low ? low : (x < high ? x : high - 1); }  // rt/image_loader.go:112-120
+__device__ __forceinline__ void dir_to_uv(const DevScene& S, D3 dir, double& u, double& v) {  // rt/hdri.go:75-94
+    const double PI = 3.14159265358979323846;
+    D3 d = unit(dir);
+    double phi = atan2(d.z, d.x), theta = asin(d.y);
+    u = 0.5 + phi / (2 * PI);
+    v = 0.5 - theta / PI;
+    u = u + S.env_rot / (2 * PI);
+    u = u - floor(u);
+}
+__device__ __forceinline__ float3 env_lookup(const DevScene& S, D3 dir) {  // Sample :120-128 + PixelDataBilinear rt/image_loader.go:399-436
+    double u, v;
+    dir_to_uv(S, dir, u, v);
+    int W = S.env_w, H = S.env_h;
+    double px = u * (double)W - 0.5, py = v * (double)H - 0.5;
+    int x0 = (int)floor(px), y0 = (int)floor(py);
+    int x1 = x0 + 1, y1 = y0 + 1;
+    float fx = (float)(px - (double)x0), fy = (float)(py - (double)y0);
+    x0 = ((x0 % W) + W) % W; x1 = ((x1 % W) + W) % W;
+    y0 = clampi_dev(y0, 0, H); y1 = clampi_dev(y1, 0, H);
+    float4 c00 = __ldg(S.env_tex + (size_t)y0 * W + x0), c10 = __ldg(S.env_tex + (size_t)y0 * W + x1);
+    float4 c01 = __ldg(S.env_tex + (size_t)y1 * W + x0), c11 = __ldg(S.env_tex + (size_t)y1 * W + x1);
+    float3 c0 = make_float3(c00.x * (1 - fx) + c10.x * fx, c00.y * (1 - fx) + c10.y * fx, c00.z * (1 - fx) + c10.z * fx);
+    float3 c1 = make_float3(c01.x * (1 - fx) + c11.x * fx, c01.y * (1 - fx) + c11.y * fx, c01.z * (1 - fx) + c11.z * fx);
+    return make_float3(c0.x * (1 - fy) + c1.x * fy, c0.y * (1 - fy) + c1.y * fy, c0.z * (1 - fy) + c1.z * fy);
+}
+__device__ __forceinline__ int search_cdf(const double* cdf, int n, double xi) {  // rt/hdri.go:300-322, n = len(cdf)-1
+    int low = 0, high = n;
+    while (low < high) {
+        int mid = (low + high) / 2;
+        if (__ldg(cdf + mid + 1) <= xi) low = mid + 1;
+        else high = mid;
+    }
+    if (low >= n) low = n - 1;
+    if (low < 0) low = 0;
+    return low;
+}
+__device__ __forceinline__ double env_pdf(const DevScene& S, D3 dir) {  // rt/hdri.go:262-297
+    const double PI = 3.14159265358979323846;
+    if (!S.env_is || S.env_total == 0) return 1.0 / (4.0 * PI);
+    double u, v;
+    dir_to_uv(S, dir, u, v);
+    int x = clampi_dev((int)(u * (double)S.env_w), 0, S.env_w), y = clampi_dev((int)(v * (double)S.env_h), 0, S.env_h);
+    double theta = (0.5 - v) * PI;
+    double sinTheta = cos(theta);
+    if (sinTheta < 1e-10) sinTheta = 1e-10;
+    double p = S.env_pdf[(size_t)y * S.env_w + x] * (double)(S.env_w * S.env_h) / (2.0 * PI * PI * sinTheta);
+    return p < 1e-10 ? 1e-10 : p;
+}
+__device__ __forceinline__ void env_sample(const DevScene& S, double xi1, double xi2, D3& dir, float3& emission, double& pdf) {  // :228-259
+    const double PI = 3.14159265358979323846;
+    int y = search_cdf(S.env_marg, S.env_h, xi1);
+    int x = search_cdf(S.env_cond + (size_t)y * (S.env_w + 1), S.env_w, xi2);
+    double u = ((double)x + 0.5) / (double)S.env_w, v = ((double)y + 0.5) / (double)S.env_h;
+    u = u - S.env_rot / (2 * PI);  // UVToDirection :97-113
+    u = u - floor(u);
+    double phi = (u - 0.5) * 2 * PI, theta = (0.5 - v) * PI;
+    double ct = cos(theta);
+    dir = d3(ct * cos(phi), sin(theta), ct * sin(phi));
+    float4 e = __ldg(S.env_tex + (size_t)y * S.env_w + x);
+    emission = make_float3(e.x, e.y, e.z);
+    pdf = env_pdf(S, dir);
+}
+
+// uniform direction on the unit sphere (the reference rejection-samples the same distribution, rt/vec3.go:45-54)
+__device__ __forceinline__ D3 unit_sphere(uint32_t a, uint32_t b) {
+    float z = 1.0f - 2.0f * u01f(a);
+    float r = sqrtf(fmaxf(0.f, 1.0f - z * z));
+    float sn, cs;
+    sincospif(2.0f * u01f(b), &sn, &cs);
+    return d3((double)(r * cs), (double)(r * sn), (double)z);
+}
+
+// ---- K4: shade — one thread per queue element, queues concatenated in material order --------------------------------
+__global__ void __launch_bounds__(256) k_shade(Ctl* ctl, Pool pool, int* q_next, DevScene S, DevCamera C, PassParams pp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // locate (queue, index): prefix over the six queue counts
+    int type = -1, idx = i;
+#pragma unroll
+    for (int k = 0; k < Q_COUNT; k++) {
+        int c = ctl->n_mat[k];
+        if (type < 0) {
+            if (idx < c) type = k;
+            else idx -= c;
+        }
+    }
+    bool valid = type >= 0;
+    bool cont = false, finished = false;
+    int slot = -1;
+    int nshadow = 0;
+    D3 sh_dir[2];
+    double sh_tmax[2];
+    float3 sh_c[2];
+    if (valid) {
+        slot = pool.q_mat[(size_t)type * pool.capacity + idx];
+        double2 a = pool.ray_o[2 * slot], b = pool.ray_o[2 * slot + 1], c = pool.ray_d[2 * slot], d = pool.ray_d[2 * slot + 1];
+        D3 rd = d3(c.x, c.y, d.x);
+        double tm = b.y;
+        float4 th = pool.thr[slot];
+        float4 L = pool.rad[slot];
+        int flags = __float_as_int(th.w);
+        int bounce = flags & 0xffff;
+        bool allow = (flags >> 16) & 1;
+        uint2 ps = pool.pix[slot];
+        (void)a;
+        if (type == Q_MISS) {  // rt/camera.go:451-466
+            float3 col;
+            if (S.env_w > 0) {
+                bool primary = (bounce == 0) && (pp.max_depth == pp.camera_max_depth);  // depth == c.MaxDepth
+                if (C.phantom && primary) col = make_float3(0, 0, 0);
+                else col = env_lookup(S, rd);
+            } else if (C.use_sky) {  // SkyGradient :520-526
+                D3 ud = unit(rd);
+                float t = (float)(0.5 * (ud.y + 1.0));
+                col = make_float3((1.f - t) + 0.5f * t, (1.f - t) + 0.7f * t, (1.f - t) + 1.0f * t);
+            } else col = make_float3(C.background[0], C.background[1], C.background[2]);
+            L.x += th.x * col.x; L.y += th.y * col.y; L.z += th.z * col.z;
+            finished = true;
+        } else {
+            double2 hp0 = pool.hit_p[2 * slot], hp1 = pool.hit_p[2 * slot + 1], hn0 = pool.hit_n[2 * slot], hn1 = pool.hit_n[2 * slot + 1];
+            D3 P = d3(hp0.x, hp0.y, hp1.x), N = d3(hn0.x, hn0.y, hn1.x);
+            long long bits = __double_as_longlong(hn1.y);
+            int mat = (int)(bits & 0x7fffffff);
+            bool front = (bits >> 31) & 1;
+            DMaterial M = S.mats[mat];
+            if (type == Q_LIGHT) {  // Scatter == false: rt/camera.go:473-481, rt/material.go:226-236
+                if (allow) {
+                    float3 e = tex_value(S, M.tex, P);
+                    L.x += th.x * e.x; L.y += th.y * e.y; L.z += th.z * e.z;
+                }
+                finished = true;
+            } else {
+                uint4 rs = philox4x32(ps.x, ps.y, (uint32_t)bounce, STREAM_SCATTER, pp.seed_lo, pp.seed_hi);
+                D3 nd;
+                float3 att;
+                bool scattered = true, next_allow = true;
+                if (type == Q_LAMBERTIAN) {  // rt/material.go:57-68
+                    nd = add(N, unit_sphere(rs.x, rs.y));
+                    if (fabs(nd.x) < 1e-8 && fabs(nd.y) < 1e-8 && fabs(nd.z) < 1e-8) nd = N;
+                    att = tex_value(S, M.tex, P);
+                    if (S.n_lights > 0) {  // useMIS, rt/camera.go:487-517
+                        const double PI = 3.14159265358979323846;
+                        uint4 rn = philox4x32(ps.x, ps.y, (uint32_t)bounce, STREAM_NEE, pp.seed_lo, pp.seed_hi);
+                        int li = (int)(u01(rn.x) * (double)S.n_lights);
+                        if (li >= S.n_lights) li = S.n_lights - 1;
+                        if (S.env_w > 0 && S.env_is && S.env_total != 0) {  // sampleHDRILight :565-607
+                            D3 ldir; float3 em; double pdfH;
+                            env_sample(S, u01(rs.z), u01(rs.w), ldir, em, pdfH);
+                            double cosT = dot(N, ldir);
+                            if (cosT > 0) {
+                                double pdfB = cosT / PI;  // Lambertian.PDF rt/material.go:70-76
+                                double w = pdfH / (pdfH + pdfB);
+                                double s = cosT / pdfH * w;
+                                float3 cc = make_float3(fminf((float)(em.x * s) * att.x, 20.f), fminf((float)(em.y * s) * att.y, 20.f), fminf((float)(em.z * s) * att.z, 20.f));
+                                sh_dir[nshadow] = ldir; sh_tmax[nshadow] = RTX_INF_D;
+                                sh_c[nshadow] = make_float3(th.x * cc.x, th.y * cc.y, th.z * cc.z);
+                                nshadow++;
+                            }
+                        }
+                        int lq = S.light_quads[li];
+                        if (lq >= 0) {  // sampleAreaLight :610-678
+                            const double* q = S.quads + 16 * (size_t)lq;
+                            D3 lp = add(add(ld3(q), scale(ld3(q + 3), u01(rn.y))), scale(ld3(q + 6), u01(rn.z)));  // SamplePoint rt/quad.go:87-92
+                            D3 toL = sub(lp, P);
+                            double dist = sqrt(len2(toL));
+                            D3 ldir = unit(toL);
+                            double cosT = dot(N, ldir);
+                            double cosL = fabs(dot(ld3(q + 12), d3(-ldir.x, -ldir.y, -ldir.z)));
+                            if (cosT > 0 && !(cosL < 0.001)) {
+                                float3 em = tex_value(S, S.mats[S.quad_mat[lq]].tex, lp);  // lightQuad.mat.Emitted(0,0,lightPoint)
+                                if (S.mats[S.quad_mat[lq]].type != RTX_MAT_DIFFUSE_LIGHT) em = make_float3(0, 0, 0);
+                                double area = sqrt(len2(cross(ld3(q + 3), ld3(q + 6))));
+                                double pdfL = (dist * dist) / (cosL * area);
+                                double pdfB = cosT / PI;
+                                double w = pdfL / (pdfL + pdfB);
+                                double s = cosT / pdfL * w;
+                                double nl = (double)S.n_lights;
+                                float3 cc = make_float3(fminf((float)(em.x * s * att.x * nl), 20.f), fminf((float)(em.y * s * att.y * nl), 20.f),
+                                                        fminf((float)(em.z * s * att.z * nl), 20.f));
+                                sh_dir[nshadow] = ldir; sh_tmax[nshadow] = dist - 0.001;
+                                sh_c[nshadow] = make_float3(th.x * cc.x, th.y * cc.y, th.z * cc.z);
+                                nshadow++;
+                            }
+                        }
+                        next_allow = false;  // indirect path must not pick up the light again (:514)
+                    }
+                } else if (type == Q_METAL) {  // rt/material.go:113-119
+                    double dn = dot(rd, N);
+                    D3 refl = sub(rd, scale(N, 2 * dn));
+                    nd = add(unit(refl), scale(unit_sphere(rs.x, rs.y), M.fuzz));
+                    att = make_float3(M.albedo[0], M.albedo[1], M.albedo[2]);
+                    scattered = dot(nd, N) > 0;
+                } else if (type == Q_DIELECTRIC) {  // rt/material.go:164-188
+                    att = make_float3(1.f, 1.f, 1.f);
+                    double ri = front ? 1.0 / M.ior : M.ior;
+                    D3 ud = unit(rd);
+                    double cosT = fmin(dot(d3(-ud.x, -ud.y, -ud.z), N), 1.0);
+                    double sinT = sqrt(1.0 - cosT * cosT);
+                    bool cannot = ri * sinT > 1.0;
+                    bool reflect = cannot;
+                    if (!cannot) {
+                        double r0 = (1 - ri) / (1 + ri);
+                        r0 = r0 * r0;
+                        double om = 1 - cosT;
+                        double refl = r0 + (1 - r0) * (om * om * om * om * om);
+                        reflect = refl > u01(rs.x);
+                    }
+                    if (reflect) nd = sub(ud, scale(N, 2 * dot(ud, N)));
+                    else {  // Refract rt/vec3.go:110-117
+                        D3 perp = scale(add(ud, scale(N, cosT)), ri);
+                        D3 par = scale(N, -sqrt(fabs(1.0 - len2(perp))));
+                        nd = add(perp, par);
+                    }
+                } else {  // Q_ISOTROPIC rt/material.go:266-270
+                    nd = unit_sphere(rs.x, rs.y);
+                    att = tex_value(S, M.tex, P);
+                }
+                if (!scattered) {
+                    finished = true;  // absorbed: emission of a scattering material is zero
+                    nshadow = 0;
+                } else {
+                    th.x *= att.x; th.y *= att.y; th.z *= att.z;
+                    bounce++;
+                    th.w = __int_as_float((bounce & 0xffff) | (next_allow ? (1 << 16) : 0));
+                    pool.ray_o[2 * slot] = make_double2(P.x, P.y);
+                    pool.ray_o[2 * slot + 1] = make_double2(P.z, tm);
+                    pool.ray_d[2 * slot] = make_double2(nd.x, nd.y);
+                    pool.ray_d[2 * slot + 1] = make_double2(nd.z, 0.0);
+                    pool.thr[slot] = th;
+                    if (bounce >= pp.max_depth) finished = true;  // rayColorInternal(depth <= 0) returns black (:444-446)
+                    else cont = true;
+                }
+            }
+        }
+        if (finished) pool.rad[slot] = L;
+    }
+    int pos = warp_append(&ctl->n_next, cont);
+    if (cont) q_next[pos] = slot;
+    pos = warp_append(&ctl->n_done, finished);
+    if (finished) pool.q_done[pos] = slot;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        bool has = k < nshadow;
+        int sp = warp_append(&ctl->n_shadow, has);
+        if (has) {
+            pool.sh_d[2 * sp] = make_double2(sh_dir[k].x, sh_dir[k].y);
+            pool.sh_d[2 * sp + 1] = make_double2(sh_dir[k].z, sh_tmax[k]);
+            pool.sh_c[sp] = make_float4(sh_c[k].x, sh_c[k].y, sh_c[k].z, __int_as_float(slot));
+        }
+    }
+}
+
+// ---- K3: connect — shadow rays of next-event estimation (any hit in [0.001, tmax]) ----------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_connect(Ctl* ctl, Pool pool, DevScene S, PassParams pp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = ctl->n_shadow;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->shadow_rays, (unsigned long long)n);
+    if (i >= n) return;
+    float4 cc = pool.sh_c[i];
+    int slot = __float_as_int(cc.w);
+    double2 o0 = pool.ray_o[2 * slot], o1 = pool.ray_o[2 * slot + 1], d0 = pool.sh_d[2 * i], d1 = pool.sh_d[2 * i + 1];
+    RayD r; r.ox = o0.x; r.oy = o0.y; r.oz = o1.x; r.dx = d0.x; r.dy = d0.y; r.dz = d1.x; r.tm = 0;  // NewRay(hitPoint, lightDir, 0)
+    uint2 ps = pool.pix[slot];
+    int bounce = __float_as_int(pool.thr[slot].w) & 0xffff;
+    VolumeRng vr; vr.k0 = pp.seed_lo; vr.k1 = pp.seed_hi; vr.c0 = ps.x; vr.c1 = ps.y;
+    vr.c2 = (uint32_t)bounce * 4u + (d1.y == RTX_INF_D ? 2u : 1u); vr.transparent = false;
+    TraceCounters tc = {0, 0, 0, 0, 0};
+    Hit h = trace_scene<true>(S, r, 0.001, d1.y, vr, COUNT ? &tc : nullptr);
+    if (COUNT) flush_counters(ctl, tc, true, true);
+    if (h.entry < 0) {
+        atomicAdd(&pool.rad[slot].x, cc.x);
+        atomicAdd(&pool.rad[slot].y, cc.y);
+        atomicAdd(&pool.rad[slot].z, cc.z);
+    }
+}
+
+// ---- K6a: accumulate finished paths into the per-pixel sums, recycle their slots --------------------------------------
+__global__ void __launch_bounds__(256) k_accumulate(Ctl* ctl, Pool pool, float4* accum, float4* accum_sq, int moments) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = i < ctl->n_done;
+    int slot = -1;
+    if (valid) {
+        slot = pool.q_done[i];
+        float4 L = pool.rad[slot];
+        uint32_t pixel = pool.pix[slot].x;
+        float* a = reinterpret_cast<float*>(accum + pixel);
+        atomicAdd(a + 0, L.x); atomicAdd(a + 1, L.y); atomicAdd(a + 2, L.z); atomicAdd(a + 3, 1.0f);
+        if (moments) {
+            float* s = reinterpret_cast<float*>(accum_sq + pixel);
+            atomicAdd(s + 0, L.x * L.x); atomicAdd(s + 1, L.y * L.y); atomicAdd(s + 2, L.z * L.z);
+        }
+    }
+    int pos = warp_append(&ctl->n_free, valid);
+    if (valid) pool.q_free[pos] = slot;
+}
+
+// ---- K6b: resolve (rt/bucket_renderer.go:275-285, rt/utils.go:85-90) -----------------------------------------------------
+__global__ void k_resolve_rgba8(const float4* accum, int npix, double scale, uchar4* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    float4 a = accum[i];
+    double c[3] = {(double)a.x * scale, (double)a.y * scale, (double)a.z * scale};
+    unsigned char o[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        double g = c[k] > 0 ? sqrt(c[k]) : 0;   // LinearToGamma
+        g = g < 0.0 ? 0.0 : (g > 0.999 ? 0.999 : g);  // Interval{0,0.999}.Clamp
+        o[k] = (unsigned char)(256 * g);
+    }
+    out[i] = make_uchar4(o[0], o[1], o[2], 255);
+}
+
+__global__ void k_pool_init(Pool pool, Ctl* ctl) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pool.capacity) pool.q_free[i] = pool.capacity - 1 - i;
+}
+
+// ---- batch entry points for the parity tests ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_trace_closest(DevScene S, const double* rays, long long n, double tmin, double tmax, int* entry_id, int* prim_id,
+                                                       double* t, double* normal, unsigned char* front, double* uv, double* p) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* q = rays + 7 * i;
+    RayD r; r.ox = q[0]; r.oy = q[1]; r.oz = q[2]; r.dx = q[3]; r.dy = q[4]; r.dz = q[5]; r.tm = q[6];
+    VolumeRng vr = {0, 0, 0, 0, 0, true};
+    Hit h = trace_scene<false>(S, r, tmin, tmax, vr, nullptr);
+    bool hit = h.entry >= 0;
+    HitInfo hi;
+    if (hit) finalize_hit(S, r, h, true, hi);
+    if (entry_id) entry_id[i] = hit ? h.entry : -1;
+    if (prim_id) prim_id[i] = hit ? h.item : -1;
+    if (t) t[i] = hit ? h.t : 0;
+    if (normal) { normal[3 * i] = hit ? hi.N.x : 0; normal[3 * i + 1] = hit ? hi.N.y : 0; normal[3 * i + 2] = hit ? hi.N.z : 0; }
+    if (front) front[i] = hit && hi.front;
+    if (uv) { uv[2 * i] = hit ? hi.u : 0; uv[2 * i + 1] = hit ? hi.v : 0; }
+    if (p) { p[3 * i] = hit ? hi.P.x : 0; p[3 * i + 1] = hit ? hi.P.y : 0; p[3 * i + 2] = hit ? hi.P.z : 0; }
+}
+
+__global__ void k_camera_rays(DevCamera C, const int* ij, const double* sq, const double* disk, const double* tm, long long n, double* out) {
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    RayD r = camera_ray(C, ij[2 * k], ij[2 * k + 1], sq[2 * k], sq[2 * k + 1], tm[k], disk[2 * k], disk[2 * k + 1]);
+    double* o = out + 7 * k;
+    o[0] = r.ox; o[1] = r.oy; o[2] = r.oz; o[3] = r.dx; o[4] = r.dy; o[5] = r.dz; o[6] = r.tm;
+}
+
+__global__ void k_hdri_sample(DevScene S, const double* xi, long long n, double* dir, double* emission, double* pdf) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    D3 d; float3 e; double p;
+    env_sample(S, xi[2 * i], xi[2 * i + 1], d, e, p);
+    dir[3 * i] = d.x; dir[3 * i + 1] = d.y; dir[3 * i + 2] = d.z;
+    emission[3 * i] = e.x; emission[3 * i + 1] = e.y; emission[3 * i + 2] = e.z;
+    pdf[i] = p;
+}
+__global__ void k_hdri_pdf(DevScene S, const double* dir, long long n, double* pdf) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pdf[i] = env_pdf(S, d3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]));
+}
+__global__ void k_hdri_lookup(DevScene S, const double* dir, long long n, double* rgb) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float3 c = env_lookup(S, d3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]));
+    rgb[3 * i] = c.x; rgb[3 * i + 1] = c.y; rgb[3 * i + 2] = c.z;
+}

@@ -1,0 +1,91 @@
+// rt_capi.cpp — a small C surface over the C++ host mirror so that tests/bench (Python, ctypes) can obtain the
+// flattened description of the named scenes and drive the BucketRenderer mirror. Not part of the drop-in
+// boundary (that is include/rtx_b200.h); it only exposes host logic that a Go caller has natively.
+#include <cstring>
+
+#include "rt.hpp"
+
+using namespace rt;
+
+struct rth_scene {
+    Scene scene;
+    HittablePtr world;  // HittableList or BVHNode
+    std::shared_ptr<FlatScene> flat;
+    rtx_scene_desc desc;
+    rtx_camera_desc cam;
+};
+
+static thread_local std::string g_err;
+
+extern "C" {
+
+const char* rth_last_error() { return g_err.c_str(); }
+
+// name: random | cornell | cornell-glossy | cornell-lucy | hdri-test (main.go:108-152). use_bvh = wrap the world in
+// NewBVHNodeFromList as main.go:77 does. width<=0 keeps the scene's own resolution / quality.
+rth_scene* rth_scene_named(const char* name, const char* asset_root, uint64_t seed, int32_t use_bvh,
+                           int32_t width, double aspect, int32_t spp, int32_t depth) {
+    try {
+        auto s = new rth_scene();
+        s->scene = LoadSceneByName(name, asset_root ? asset_root : ".", seed);
+        Camera& c = *s->scene.camera;
+        if (width > 0) c.SetResolution(width, aspect);
+        if (spp > 0) c.SamplesPerPixel = spp;
+        if (depth > 0) c.MaxDepth = depth;
+        c.Initialize();
+        s->world = use_bvh ? std::static_pointer_cast<Hittable>(NewBVHNodeFromList(s->scene.world)) : std::static_pointer_cast<Hittable>(s->scene.world);
+        s->flat = Flatten(s->world, c);
+        s->desc = s->flat->Desc();
+        c.FillDesc(s->cam);
+        return s;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+void rth_scene_free(rth_scene* s) { delete s; }
+const rtx_scene_desc* rth_scene_desc(rth_scene* s) { return &s->desc; }
+const rtx_camera_desc* rth_camera_desc(rth_scene* s) { return &s->cam; }
+int32_t rth_image_height(rth_scene* s) { return s->scene.camera->ImageHeight; }
+
+// ImageHeight rule of Camera.Initialize (rt/camera.go:299) for KAT tests.
+int32_t rth_image_height_for(int32_t width, double aspect) {
+    Camera c;
+    c.SetResolution(width, aspect);
+    c.Initialize();
+    return c.ImageHeight;
+}
+
+// Full BucketRenderer run (3 passes, rt/bucket_renderer.go:175-191) of a named scene; pix = RGBA8 4*W*H.
+int32_t rth_bucket_render(rth_scene* s, uint64_t seed, uint8_t* pix, int64_t nbytes, double* seconds, const char* save_path) {
+    try {
+        BucketRenderer r(s->scene.camera, s->world, 32, 1);
+        r.seed = seed;
+        r.RenderToCompletion();
+        if ((int64_t)r.Pix().size() != nbytes) { g_err = "pix size mismatch"; return RTX_ERR_INVALID; }
+        std::memcpy(pix, r.Pix().data(), r.Pix().size());
+        if (seconds) *seconds = r.GetRenderDurationSeconds();
+        if (save_path && *save_path && r.SaveImage(save_path) != 0) { g_err = "SaveImage failed"; return RTX_ERR_INVALID; }
+        return RTX_OK;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return RTX_ERR_INVALID;
+    }
+}
+
+int32_t rth_load_hdr(const char* path, int32_t* w, int32_t* h, double* rgb_out, int64_t capacity) {
+    int ww, hh;
+    std::vector<double> rgb;
+    std::string err;
+    if (!LoadHDR(path, ww, hh, rgb, &err)) { g_err = err; return RTX_ERR_INVALID; }
+    *w = ww; *h = hh;
+    if (rgb_out) {
+        if ((int64_t)rgb.size() > capacity) { g_err = "capacity"; return RTX_ERR_INVALID; }
+        std::memcpy(rgb_out, rgb.data(), rgb.size() * sizeof(double));
+    }
+    return RTX_OK;
+}
+
+int32_t rth_write_png(const char* path, const uint8_t* rgba, int32_t w, int32_t h) { return WritePNG(path, rgba, w, h); }
+
+}  // extern "C"

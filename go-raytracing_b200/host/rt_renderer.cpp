@@ -1,0 +1,142 @@
+// rt_renderer.cpp — BucketRenderer / ProgressiveRenderer mirrors (rt/bucket_renderer.go, rt/renderer.go).
+//
+// The constructor, the 3-pass state machine of Update() and SaveImage/IsCompleted/GetRenderDuration keep the
+// reference's behaviour; the body of renderPass (rt/bucket_renderer.go:170-214: worker goroutines, 32x32 tiles,
+// GetRay/RayColor per sample, gamma + RGBA8 pack) is ONE call into the CUDA library per pass.
+// bucketSize / numWorkers are accepted and ignored (the device schedules its own work).
+// The ebiten Draw()/stats-bar overlay is display cosmetics and out of scope.
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+
+#include "rt.hpp"
+
+namespace rt {
+
+static void check(rtx_ctx* ctx, int32_t rc, const char* what) {
+    if (rc != RTX_OK) throw std::runtime_error(std::string(what) + ": " + rtx_last_error(ctx));
+}
+
+BucketRenderer::BucketRenderer(CameraPtr camera, HittablePtr world, int /*bucketSize*/, int /*numWorkers*/, int deviceId) : camera_(camera) {
+    flat_ = Flatten(world, *camera);
+    int32_t rc = rtx_create(deviceId, &ctx_);
+    if (rc != RTX_OK) throw std::runtime_error(std::string("rtx_create: ") + rtx_last_error(nullptr));
+    rtx_scene_desc sd = flat_->Desc();
+    check(ctx_, rtx_scene_upload(ctx_, &sd), "rtx_scene_upload");
+    rtx_camera_desc cd;
+    camera->FillDesc(cd);
+    check(ctx_, rtx_camera_set(ctx_, &cd), "rtx_camera_set");
+    int32_t w, h;
+    check(ctx_, rtx_image_size(ctx_, &w, &h), "rtx_image_size");
+    w_ = w; h_ = h;
+    pix_.assign((size_t)4 * w * h, 0);  // image.NewRGBA (rt/bucket_renderer.go:55)
+}
+BucketRenderer::~BucketRenderer() {
+    if (ctx_) rtx_destroy(ctx_);
+}
+
+void BucketRenderer::renderPass() {  // rt/bucket_renderer.go:170-191 pass schedule
+    int spp, depth;
+    switch (currentPass_) {
+        case 0: spp = 1; depth = 3; break;
+        case 1: spp = std::max(1, camera_->SamplesPerPixel / 4); depth = std::max(3, camera_->MaxDepth / 2); break;
+        default: spp = camera_->SamplesPerPixel; depth = camera_->MaxDepth; break;
+    }
+    check(ctx_, rtx_accum_clear(ctx_), "rtx_accum_clear");  // each pass overwrites the framebuffer (:291-300)
+    check(ctx_, rtx_render_pass(ctx_, spp, depth, camera_->MaxDepth, seed + (uint64_t)currentPass_, 0), "rtx_render_pass");
+    check(ctx_, rtx_resolve_rgba8(ctx_, spp, pix_.data(), (int64_t)pix_.size()), "rtx_resolve_rgba8");
+}
+
+int BucketRenderer::Update() {  // rt/bucket_renderer.go:127-164, one pass per tick
+    if (completed_) return 0;
+    auto t0 = std::chrono::steady_clock::now();
+    renderPass();
+    duration_s_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    currentPass_++;
+    if (currentPass_ >= totalPasses_) completed_ = true;
+    return 0;
+}
+void BucketRenderer::RenderToCompletion() {
+    while (!completed_) Update();
+}
+
+std::shared_ptr<BucketRenderer> NewBucketRenderer(CameraPtr camera, HittablePtr world, int bucketSize, int numWorkers) {
+    return std::make_shared<BucketRenderer>(camera, world, bucketSize, numWorkers);
+}
+std::shared_ptr<BucketRenderer> NewProgressiveRenderer(CameraPtr camera, HittablePtr world) {
+    return std::make_shared<BucketRenderer>(camera, world, 0, 0);
+}
+
+// ---- PNG (stored deflate blocks; rt/bucket_renderer.go:417-438 uses image/png) ------------------------------
+static uint32_t crcTable[256];
+static void crcInit() {
+    static bool done = false;
+    if (done) return;
+    for (uint32_t n = 0; n < 256; n++) {
+        uint32_t c = n;
+        for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+        crcTable[n] = c;
+    }
+    done = true;
+}
+static uint32_t crcUpdate(uint32_t c, const uint8_t* p, size_t n) {
+    for (size_t i = 0; i < n; i++) c = crcTable[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+    return c;
+}
+static void chunk(FILE* f, const char* type, const std::vector<uint8_t>& data) {
+    uint8_t len[4] = {(uint8_t)(data.size() >> 24), (uint8_t)(data.size() >> 16), (uint8_t)(data.size() >> 8), (uint8_t)data.size()};
+    std::fwrite(len, 1, 4, f);
+    std::fwrite(type, 1, 4, f);
+    if (!data.empty()) std::fwrite(data.data(), 1, data.size(), f);
+    uint32_t c = crcUpdate(0xFFFFFFFFu, (const uint8_t*)type, 4);
+    c = crcUpdate(c, data.data(), data.size()) ^ 0xFFFFFFFFu;
+    uint8_t cb[4] = {(uint8_t)(c >> 24), (uint8_t)(c >> 16), (uint8_t)(c >> 8), (uint8_t)c};
+    std::fwrite(cb, 1, 4, f);
+}
+int WritePNG(const std::string& path, const uint8_t* rgba, int w, int h) {
+    crcInit();
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) return -1;
+    const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    std::fwrite(sig, 1, 8, f);
+    std::vector<uint8_t> ihdr = {(uint8_t)(w >> 24), (uint8_t)(w >> 16), (uint8_t)(w >> 8), (uint8_t)w,
+                                 (uint8_t)(h >> 24), (uint8_t)(h >> 16), (uint8_t)(h >> 8), (uint8_t)h, 8, 6, 0, 0, 0};
+    chunk(f, "IHDR", ihdr);
+    std::vector<uint8_t> raw;
+    raw.reserve((size_t)h * (4 * w + 1));
+    for (int y = 0; y < h; y++) {
+        raw.push_back(0);
+        raw.insert(raw.end(), rgba + (size_t)y * 4 * w, rgba + (size_t)(y + 1) * 4 * w);
+    }
+    std::vector<uint8_t> z = {0x78, 0x01};
+    uint32_t a = 1, b = 0;
+    for (uint8_t v : raw) { a = (a + v) % 65521; b = (b + a) % 65521; }
+    size_t pos = 0;
+    while (pos < raw.size()) {
+        size_t n = std::min<size_t>(65535, raw.size() - pos);
+        z.push_back(pos + n == raw.size() ? 1 : 0);
+        z.push_back((uint8_t)n); z.push_back((uint8_t)(n >> 8));
+        z.push_back((uint8_t)~n); z.push_back((uint8_t)(~n >> 8));
+        z.insert(z.end(), raw.begin() + pos, raw.begin() + pos + n);
+        pos += n;
+    }
+    uint32_t adler = (b << 16) | a;
+    z.push_back((uint8_t)(adler >> 24)); z.push_back((uint8_t)(adler >> 16)); z.push_back((uint8_t)(adler >> 8)); z.push_back((uint8_t)adler);
+    chunk(f, "IDAT", z);
+    chunk(f, "IEND", {});
+    std::fclose(f);
+    return 0;
+}
+int BucketRenderer::SaveImage(const std::string& filename) const {
+    if (filename.size() > 4 && filename.substr(filename.size() - 4) == ".ppm") {
+        FILE* f = std::fopen(filename.c_str(), "wb");
+        if (!f) return -1;
+        std::fprintf(f, "P6\n%d %d\n255\n", w_, h_);
+        for (size_t i = 0; i < (size_t)w_ * h_; i++) std::fwrite(&pix_[4 * i], 1, 3, f);
+        std::fclose(f);
+        return 0;
+    }
+    return WritePNG(filename, pix_.data(), w_, h_);
+}
+
+}  // namespace rt
