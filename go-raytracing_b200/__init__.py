@@ -88,7 +88,7 @@ ABI_SYMBOLS = [
     "rtx_create", "rtx_destroy", "rtx_last_error", "rtx_abi_version", "rtx_scene_upload", "rtx_camera_set", "rtx_image_size",
     "rtx_render_pass", "rtx_accum_clear", "rtx_accum_enable_moments", "rtx_accum_device_ptr", "rtx_resolve_rgba8", "rtx_resolve_accum",
     "rtx_trace_closest", "rtx_camera_rays", "rtx_hdri_sample", "rtx_hdri_pdf", "rtx_hdri_lookup", "rtx_hdri_total_power",
-    "rtx_get_stats", "rtx_set_option",
+    "rtx_get_stats", "rtx_set_option", "rtx_set_stream",
 ]
 
 _lib_cache = None
@@ -128,6 +128,7 @@ def lib() -> C.CDLL:
         L.rtx_hdri_total_power.argtypes = [C.c_void_p, _pd]
         L.rtx_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.rtx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+        L.rtx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         _lib_cache = L
     return _lib_cache
 
@@ -473,6 +474,10 @@ class Context:
 
     def set_option(self, key: str, value: int):
         self._check(self._L.rtx_set_option(self._h, key.encode(), int(value)), f"rtx_set_option({key})")
+
+    def set_stream(self, cuda_stream: int):
+        """Run on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream); 0/None = own stream."""
+        self._check(self._L.rtx_set_stream(self._h, C.c_void_p(cuda_stream or None)), "rtx_set_stream")
 
     def upload(self, desc_ptr):
         self._check(self._L.rtx_scene_upload(self._h, desc_ptr), "rtx_scene_upload")

@@ -23,7 +23,8 @@ struct DevBuf {
 
 struct rtx_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // stream in use
+    cudaStream_t own_stream = nullptr;  // created by rtx_create
     std::string err;
     std::vector<void*> scene_allocs;
     DevScene S{};
@@ -134,7 +135,16 @@ int32_t rtx_create(int32_t device_id, rtx_ctx** out) {
         delete ctx;
         return RTX_ERR_CUDA;
     }
+    ctx->own_stream = ctx->stream;
     *out = ctx;
+    return RTX_OK;
+}
+
+int32_t rtx_set_stream(rtx_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return RTX_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return RTX_OK;
 }
 
@@ -149,7 +159,7 @@ int32_t rtx_destroy(rtx_ctx* ctx) {
     if (ctx->ctl) cudaFree(ctx->ctl);
     if (ctx->ctl_host) cudaFreeHost(ctx->ctl_host);
     for (auto ev : ctx->events) cudaEventDestroy(ev);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return RTX_OK;
 }
@@ -161,7 +171,7 @@ int32_t rtx_set_option(rtx_ctx* ctx, const char* key, int64_t value) {
         if (value < 1024 || value > (1ll << 26)) return fail(ctx, RTX_ERR_INVALID, "pool_paths out of range");
         if (value != ctx->pool_paths) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); free_pool(ctx); }
         ctx->pool_paths = value;
-    } else if (k == "count_stats") ctx->count_stats = value != 0;
+    } else if (k == "count_stats") ctx->count_stats = (int)value;  // bit 0: extend kernel, bit 1: connect kernel
     else if (k == "time_kernels") ctx->time_kernels = value != 0;
     else return fail(ctx, RTX_ERR_INVALID, "unknown option '%s'", key);
     return RTX_OK;
@@ -499,6 +509,7 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     S.n_entries = d->n_entries;
     S.n_unbounded = (int)unbounded.size();
     S.n_lights = d->n_lights;
+    S.vol_draws = d->world_is_bvh ? 2 : 1;
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->S = S;
     ctx->have_scene = true;
@@ -688,13 +699,13 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
             if (timing) cudaEventRecord(ev[0], st);
             k_generate<<<gridBig, 256, 0, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->C, pp);
             if (timing) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
-            if (ctx->count_stats) k_extend<true><<<gridTrace, 128, 0, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->S, pp);
+            if (ctx->count_stats & 1) k_extend<true><<<gridTrace, 128, 0, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->S, pp);
             else k_extend<false><<<gridTrace, 128, 0, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->S, pp);
             if (timing) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); }
             k_shade<<<gridBig, 256, 0, st>>>(ctx->ctl, ctx->pool, q_next, ctx->S, ctx->C, pp);
             if (timing) { cudaEventRecord(ev[5], st); cudaEventRecord(ev[6], st); }
             if (ctx->S.n_lights > 0) {
-                if (ctx->count_stats) k_connect<true><<<gridShadow, 128, 0, st>>>(ctx->ctl, ctx->pool, ctx->S, pp);
+                if (ctx->count_stats & 2) k_connect<true><<<gridShadow, 128, 0, st>>>(ctx->ctl, ctx->pool, ctx->S, pp);
                 else k_connect<false><<<gridShadow, 128, 0, st>>>(ctx->ctl, ctx->pool, ctx->S, pp);
                 launches++;
             }

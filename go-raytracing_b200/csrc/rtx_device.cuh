@@ -73,6 +73,11 @@ struct DevScene {
     const double* env_cond;  // h*(w+1)
     const double* env_pdf;   // w*h (normalised, rt/hdri.go:217-219)
     double env_total;
+    // The reference stores every BVH leaf as BOTH children of its node (rt/bvh.go:141), so BVHNode.Hit runs each leaf
+    // twice (rt/bvh.go:228-236). Deterministic primitives are unaffected, but Volume.Hit draws a fresh random number
+    // per call (rt/volume.go:66): under NewBVHNodeFromList a volume gets two independent free-flight samples per
+    // query and the nearer one wins, i.e. the medium is effectively twice as dense. 2 when world_is_bvh, else 1.
+    int vol_draws;
 };
 
 struct RayD {
@@ -336,7 +341,7 @@ struct VolumeRng {
     uint32_t k0, k1, c0, c1, c2;
     bool transparent;  // level-1 parity protocol: volumes do not intersect
 };
-__device__ double rtx_volume_uniform(const VolumeRng& vr, int entry);  // defined in rtx_kernels.cu (Philox)
+__device__ double2 rtx_volume_uniform(const VolumeRng& vr, int entry);  // two uniforms, defined in rtx_kernels.cuh (Philox)
 
 // ---- the scene query: closest hit (or any hit) of world.Hit(r, [tmin,tmax]) ----------------------------------------
 template <bool ANY_HIT>
@@ -398,7 +403,10 @@ __device__ __noinline__ Hit trace_scene(const DevScene& S, const RayD& rw, doubl
                                     if (t1 < 0) t1 = 0;
                                     double rayLength = sqrt(rw.dx * rw.dx + rw.dy * rw.dy + rw.dz * rw.dz);
                                     double inside = (t2 - t1) * rayLength;
-                                    double hd = S.volumes[e.volume].neg_inv_density * log(rtx_volume_uniform(vr, ei));
+                                    double2 uu = rtx_volume_uniform(vr, ei);
+                                    double nid = S.volumes[e.volume].neg_inv_density;
+                                    double hd = nid * log(uu.x);
+                                    if (S.vol_draws > 1) hd = fmin(hd, nid * log(uu.y));  // leaf visited twice, see DevScene::vol_draws
                                     if (!(hd > inside)) T.offer(t1 + hd / rayLength, ei, e.rank, RTX_KIND_VOLUME, e.volume, 0, 0);
                                 }
                             }

@@ -26,9 +26,9 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c
 __device__ __forceinline__ double u01(uint32_t x) { return ((double)x + 0.5) * 2.3283064365386963e-10; }   // (0,1)
 __device__ __forceinline__ float u01f(uint32_t x) { return ((float)(x >> 8) + 0.5f) * 5.9604645e-8f; }      // (0,1), 24 bits
 
-__device__ double rtx_volume_uniform(const VolumeRng& vr, int entry) {
+__device__ double2 rtx_volume_uniform(const VolumeRng& vr, int entry) {
     uint4 r = philox4x32(vr.c0, vr.c1, vr.c2, 64u + (uint32_t)entry, vr.k0, vr.k1);
-    return u01(r.x);
+    return make_double2(u01(r.x), u01(r.y));
 }
 
 enum { Q_MISS = 0, Q_LAMBERTIAN = 1, Q_METAL = 2, Q_DIELECTRIC = 3, Q_LIGHT = 4, Q_ISOTROPIC = 5, Q_COUNT = 6 };

@@ -249,8 +249,14 @@ int32_t rtx_hdri_pdf(rtx_ctx* ctx, const double* dir, int64_t n, double* pdf);
 int32_t rtx_hdri_lookup(rtx_ctx* ctx, const double* dir, int64_t n, double* rgb); /* Environment.Sample, rt/hdri.go:120 */
 int32_t rtx_hdri_total_power(const rtx_ctx* ctx, double* total_power);            /* rt/hdri.go:325 */
 
+/* Run all subsequent work of this context on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL restores
+ * the context's own stream). Lets the caller order the library's kernels with its own (e.g. the NCCL reduce of the
+ * accumulation buffers issued by torch.distributed) and time them with events on that stream. */
+int32_t rtx_set_stream(rtx_ctx* ctx, void* cuda_stream);
+
 int32_t rtx_get_stats(rtx_ctx* ctx, rtx_stats* out);
-/* Tunables: "pool_paths" (in-flight path slots), "count_stats" (0/1 per-ray counters). Returns RTX_ERR_INVALID for unknown keys. */
+/* Tunables: "pool_paths" (in-flight path slots), "count_stats" (per-ray traversal counters: bit 0 extension rays, bit 1 shadow
+ * rays), "time_kernels" (CUDA-event time per kernel kind, default 1). Returns RTX_ERR_INVALID for unknown keys. */
 int32_t rtx_set_option(rtx_ctx* ctx, const char* key, int64_t value);
 
 #ifdef __cplusplus

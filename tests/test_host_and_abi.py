@@ -1,0 +1,106 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/rtx_b200.h declares, it refuses
+to run without a device (no fallback), and the C++ host mirror of the Go rt API builds / flattens the configured
+scenes the way the reference's scene functions describe them (rt/scenes.go)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_header_symbols_exported(grt):
+    header = open(os.path.join(ROOT, "include", "rtx_b200.h")).read()
+    declared = set(re.findall(r"\b(rtx_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(grt.ABI_SYMBOLS), declared ^ set(grt.ABI_SYMBOLS)
+    L = grt.lib()
+    for s in declared:
+        assert hasattr(L, s), s
+    assert L.rtx_abi_version() == grt.RTX_ABI_VERSION
+
+
+def test_struct_layout_matches_header(grt):
+    # sizes follow from the field lists in include/rtx_b200.h (LP64): catches a drifting ctypes mirror
+    assert C.sizeof(grt.CameraDesc) == 8 + 4 * 3 + 4 + 8 + 9 * 8 + 16 + 48 + 8 + 48 + 8 + 8 + 7 * 24 + 24
+    assert C.sizeof(grt.Stats) == 10 * 8 + 5 * 8 + 4 * 4
+
+
+def test_no_cpu_fallback(grt):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(grt.RtxError) as e:
+        grt.Context(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_scene_shapes(grt):
+    # object counts of the scene functions (rt/scenes.go)
+    c = grt.config_scene("cornell")
+    d = c.desc
+    assert (c.width, c.height) == (400, 225)
+    assert d.n_entries == 9 and d.n_quads == 6 + 3 * 6 and d.n_groups == 3 and d.n_volumes == 1 and d.n_lights == 1
+    kinds = [d.entry_geom_kind[i] for i in range(9)]
+    assert kinds == [grt.GEOM_QUAD] * 6 + [grt.GEOM_LIST] * 3
+    # boxes: Translate outermost, then RotateY (scale 1 is skipped, rt/transform.go:27)
+    assert [d.entry_xf_count[i] for i in range(9)] == [0] * 6 + [2, 2, 0]
+    xb = d.entry_xf_begin[6]
+    assert d.xf_type[xb] == grt.XF_TRANSLATE and d.xf_type[xb + 1] == grt.XF_ROTATE_Y
+    assert (d.xf_a[3 * xb], d.xf_a[3 * xb + 1], d.xf_a[3 * xb + 2]) == (265.0, 0.0, 295.0)
+    assert d.entry_volume[8] == 0 and d.vol_neg_inv_density[0] == -1.0 / 0.001
+    assert d.light_quad[0] == 0 and d.world_is_bvh == 1
+    assert (c.cam.samples_per_pixel, c.cam.max_depth, c.cam.vfov) == (10, 10, 40.0)
+
+    g = grt.config_scene("cornell-glossy")
+    assert g.desc.n_entries == 10 and g.desc.n_spheres == 4 and g.desc.n_quads == 6 and (g.width, g.height) == (600, 337)
+    assert g.desc.light_quad[0] == 5  # the light is the 6th quad added (rt/scenes.go:674-680)
+
+    r = grt.config_scene("random")
+    assert r.desc.n_planes == 1 and r.desc.n_spheres == r.desc.n_entries - 1 and 330 < r.desc.n_spheres < 380
+    assert r.cam.defocus_angle == 0.6 and r.cam.use_sky_gradient == 1 and r.desc.n_lights == 0
+    # seeded: same seed -> identical geometry, different seed -> different
+    r2 = grt.config_scene("random")
+    n = 3 * r.desc.n_spheres
+    assert np.array_equal(np.ctypeslib.as_array(r.desc.sph_center, (n,)), np.ctypeslib.as_array(r2.desc.sph_center, (n,)))
+    r3 = grt.config_scene("random", seed=7)
+    assert r3.desc.n_spheres != r.desc.n_spheres or not np.array_equal(np.ctypeslib.as_array(r.desc.sph_center, (n,)),
+                                                                    np.ctypeslib.as_array(r3.desc.sph_center, (n,)))
+
+    h = grt.config_scene("hdri-test", width=800)
+    assert h.desc.n_spheres == 5 and h.desc.n_planes == 1 and h.desc.n_lights == 0      # no AddLight => no NEE
+    assert h.desc.env_width == 1024 and h.desc.env_height == 512 and h.cam.phantom_hdri == 1
+    assert (h.width, h.height) == (800, 450)
+
+
+def test_lucy_instances(grt):
+    s = grt.config_scene("cornell-lucy", width=120, spp=1)
+    d = s.desc
+    assert d.n_entries == 16 and d.n_groups == 1 and d.group_kind[0] == grt.GEOM_MESH
+    assert d.group_count[0] == d.n_tris and d.n_tris > 250000
+    inst = [i for i in range(16) if d.entry_geom_kind[i] == grt.GEOM_MESH]
+    assert len(inst) == 10 and all(d.entry_geom_index[i] == 0 for i in inst)            # one mesh shared by ten instances
+    # Scale -> RotateY -> Translate, RotateY skipped when the angle is 0 (rt/transform.go:24-46, rt/scenes.go:776-790)
+    assert [d.entry_xf_count[i] for i in inst] == [3, 3, 3, 3, 2, 3, 3, 3, 2, 3]
+    xb = d.entry_xf_begin[inst[0]]
+    assert [d.xf_type[xb + k] for k in range(3)] == [grt.XF_TRANSLATE, grt.XF_ROTATE_Y, grt.XF_SCALE]
+    assert d.xf_a[3 * (xb + 2)] == 0.15 and d.xf_b[3 * (xb + 2)] == 1.0 / 0.15
+    # tri_rank is a permutation (DFS leaf order of the reference-order mesh BVH)
+    ranks = np.ctypeslib.as_array(d.tri_rank, (d.n_tris,))
+    assert np.array_equal(np.sort(ranks), np.arange(d.n_tris))
+
+
+def test_unsupported_objects_are_flatten_errors(grt):
+    H = grt.host()
+    assert H.rth_scene_named(b"earth", b".", 1, 1, 0, 1.0, 0, 0) is None
+    assert b"unknown scene" in H.rth_last_error()
+
+
+def test_png_writer(grt, tmp_path):
+    from PIL import Image
+    img = (np.arange(4 * 5 * 7, dtype=np.uint32).reshape(5, 7, 4) * 9 % 256).astype(np.uint8)
+    img[..., 3] = 255
+    p = str(tmp_path / "t.png")
+    assert grt.host().rth_write_png(p.encode(), img.ctypes.data, 7, 5) == 0
+    assert np.array_equal(np.asarray(Image.open(p)), img)

@@ -1,0 +1,393 @@
+"""GPU parity tests (run on the B200): the CUDA path, called through the C-ABI of include/rtx_b200.h, against the
+CPU oracle on the same inputs.
+
+Level 1 (north star): for identical input rays, hit / miss, (entry, primitive) ids and front_face must match
+bit-exactly; t, normals and hit points within 1e-5 relative. The device evaluates primitives in float64 in the
+reference's operation order, so the tests actually demand |dt| <= 1e-12 relative.
+Level 2: RNG streams differ, so images are compared statistically on per-pixel mean / variance of linear radiance.
+Tolerances are written next to each assertion."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REL_T = 1e-5      # north-star tolerance on t / normals
+TIGHT = 1e-12     # what the float64 device path actually achieves
+
+
+# ------------------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------------------
+def camera_batch(w, h, n, rng, centres=False):
+    if centres:
+        jj, ii = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+        ij = np.stack([ii.ravel(), jj.ravel()], axis=1).astype(np.int32)
+        n = len(ij)
+        return ij, np.zeros((n, 2)), np.zeros((n, 2)), np.full(n, 0.5)
+    ij = np.stack([rng.integers(0, w, n), rng.integers(0, h, n)], axis=1).astype(np.int32)
+    r, a = np.sqrt(rng.random(n)), rng.random(n) * 2 * np.pi
+    return ij, rng.random((n, 2)) - 0.5, np.stack([r * np.cos(a), r * np.sin(a)], axis=1), rng.random(n)
+
+
+def assert_level1(hg, ho, what=""):
+    assert np.array_equal(hg["entry"], ho["entry"]), f"{what}: entry ids differ at {np.flatnonzero(hg['entry'] != ho['entry'])[:8]}"
+    assert np.array_equal(hg["prim"], ho["prim"]), f"{what}: primitive ids differ at {np.flatnonzero(hg['prim'] != ho['prim'])[:8]}"
+    hit = ho["entry"] >= 0
+    assert np.array_equal(hg["front"][hit], ho["front"][hit]), f"{what}: front_face differs"
+    t_o, t_g = ho["t"][hit], hg["t"][hit]
+    assert np.all(np.abs(t_g - t_o) <= REL_T * np.abs(t_o)), f"{what}: t outside 1e-5 relative"
+    assert np.all(np.abs(t_g - t_o) <= TIGHT * np.maximum(np.abs(t_o), 1e-300)), f"{what}: t not bit-close: {np.abs(t_g - t_o).max()}"
+    assert np.all(np.abs(hg["normal"][hit] - ho["normal"][hit]) <= TIGHT), f"{what}: normals differ"
+    scale = np.maximum(np.abs(ho["p"][hit]).max(axis=1, keepdims=True), 1.0)
+    assert np.all(np.abs(hg["p"][hit] - ho["p"][hit]) <= TIGHT * scale), f"{what}: hit points differ"
+
+
+def secondary_rays(ho, rng, n):
+    hit = np.flatnonzero(ho["entry"] >= 0)[:n]
+    P, N = ho["p"][hit], ho["normal"][hit]
+    u = rng.standard_normal(P.shape)
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    scatter = np.concatenate([P, N + u, rng.random((len(P), 1))], axis=1)         # Lambertian: origin on the surface, |d| in (0,2)
+    shadow = np.concatenate([P, u * np.sign((u * N).sum(axis=1, keepdims=True)), np.zeros((len(P), 1))], axis=1)  # unit dir, time 0
+    return scatter, shadow
+
+
+CONFIG_SMALL = {"cornell": 160, "cornell-glossy": 160, "random": 200, "hdri-test": 240}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# level 1
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["cornell", "cornell-glossy", "random", "hdri-test"])
+def test_level1_configured_scenes(grt, orc, ctx, name):
+    rng = np.random.default_rng(1)
+    sc = grt.config_scene(name, width=CONFIG_SMALL[name])
+    ctx.load(sc)
+    o = orc.OracleScene(sc.desc_ptr, sc.cam_ptr)
+    # ray generation (device GetRay) is bit-exact
+    for centres in (True, False):
+        ij, sq, disk, tm = camera_batch(sc.width, sc.height, 100000, rng, centres)
+        rg, ro = ctx.camera_rays(ij, sq, disk, tm), o.camera_rays(ij, sq, disk, tm)
+        assert np.array_equal(rg, ro), f"{name}: camera rays differ (max {np.abs(rg - ro).max()})"
+        hg, ho = ctx.trace_closest(ro), o.trace_closest(ro)
+        assert_level1(hg, ho, f"{name} primary centres={centres}")
+    scatter, shadow = secondary_rays(ho, rng, 60000)
+    assert_level1(ctx.trace_closest(scatter), o.trace_closest(scatter), f"{name} scatter")
+    hg, ho2 = ctx.trace_closest(shadow, 0.001, 300.0), o.trace_closest(shadow, 0.001, 300.0)
+    assert_level1(hg, ho2, f"{name} shadow")
+
+
+def test_level1_lucy_instances(grt, orc, ctx):
+    """10 instances (Scale -> RotateY -> Translate) of one 280K-triangle mesh: two-level traversal."""
+    rng = np.random.default_rng(2)
+    sc = grt.config_scene("cornell-lucy", width=320, spp=1)
+    ctx.load(sc)
+    st = ctx.stats()
+    assert st["n_tris"] >= 280000 and st["blas_nodes"] > 10000
+    o = orc.OracleScene(sc.desc_ptr, sc.cam_ptr)
+    ij, sq, disk, tm = camera_batch(sc.width, sc.height, 150000, rng)
+    ro = o.camera_rays(ij, sq, disk, tm)
+    assert np.array_equal(ctx.camera_rays(ij, sq, disk, tm), ro)
+    hg, ho = ctx.trace_closest(ro), o.trace_closest(ro)
+    assert_level1(hg, ho, "lucy primary")
+    assert (ho["entry"] >= 6).mean() > 0.2  # a good share of rays lands on the statues
+    scatter, shadow = secondary_rays(ho, rng, 100000)
+    assert_level1(ctx.trace_closest(scatter), o.trace_closest(scatter), "lucy scatter")
+    assert_level1(ctx.trace_closest(shadow, 0.001, 500.0), o.trace_closest(shadow, 0.001, 500.0), "lucy shadow")
+
+
+def _soup_scene(grt, rng, world_is_bvh=True, n_tri=3000, dup=True):
+    b = grt.SceneBuilder(world_is_bvh=world_is_bvh)
+    m = b.material("lambertian", (0.5, 0.5, 0.5))
+    v0 = rng.random((n_tri, 3)) * 10 - 5
+    v1 = v0 + rng.standard_normal((n_tri, 3)) * 0.4
+    v2 = v0 + rng.standard_normal((n_tri, 3)) * 0.4
+    g = b.mesh_group(v0, v1, v2, m)
+    b.entry(grt.GEOM_MESH, g)
+    b.entry(grt.GEOM_MESH, g, xforms=[("translate", (3.0, 1.0, -2.0)), ("rotate_y", 33.0), ("scale", (0.5, 1.25, 2.0))])
+    b.entry(grt.GEOM_MESH, g, xforms=[("scale", (-1.0, 1.0, 1.0))])  # mirrored instance (negative scale)
+    for k in range(40):
+        c = rng.random(3) * 10 - 5
+        b.entry(grt.GEOM_SPHERE, b.sphere(c, 0.1 + rng.random() * 0.6, m, center2=c + rng.standard_normal(3) * 0.5 if k % 2 else None))
+    for k in range(20):
+        q = b.quadp(rng.random(3) * 10 - 5, rng.standard_normal(3), rng.standard_normal(3), m)
+        b.entry(grt.GEOM_QUAD, q, xforms=[("rotate_y", float(rng.random() * 360))] if k % 3 == 0 else [])
+    b.entry(grt.GEOM_LIST, b.box_group((-1, -1, -1), (1, 2, 1), m), xforms=[("translate", (0, 0, 4)), ("rotate_y", -18.0)])
+    b.entry(grt.GEOM_TRIANGLE, b.triangle((-6, -6, 6), (6, -6, 6), (0, 6, 6), m))
+    b.entry(grt.GEOM_PLANE, b.planep((0, -5.5, 0), (0.1, 1, 0.05), m))
+    if dup:  # exact duplicates -> exact ties in t; the reference's interval conventions decide who wins
+        c = (1.5, 0.5, 0.25)
+        s1 = b.sphere(c, 0.9, m)
+        b.entry(grt.GEOM_SPHERE, s1)
+        b.entry(grt.GEOM_SPHERE, b.sphere(c, 0.9, m))
+        for _ in range(3):
+            b.entry(grt.GEOM_QUAD, b.quadp((-4, -4, -3), (8, 0, 0), (0, 8, 0), m))
+        for _ in range(2):
+            b.entry(grt.GEOM_TRIANGLE, b.triangle((-6, -6, 6), (6, -6, 6), (0, 6, 6), m))
+    return b.build()
+
+
+@pytest.mark.parametrize("world_is_bvh", [True, False])
+def test_level1_soup_instances_ties(grt, orc, ctx, world_is_bvh):
+    rng = np.random.default_rng(3)
+    built = _soup_scene(grt, rng, world_is_bvh)
+    cam = grt.make_camera(64, 1.0, 1, 5, 60, (0, 0, -14), (0, 0, 0))
+    ctx.load((built, cam))
+    o = orc.OracleScene(built.desc_ptr, grt.C.pointer(cam))
+    n = 300000
+    org = rng.standard_normal((n, 3)) * 6
+    tgt = rng.random((n, 3)) * 10 - 5
+    rays = np.concatenate([org, (tgt - org) * (0.2 + rng.random((n, 1)) * 2), rng.random((n, 1))], axis=1)
+    hg, ho = ctx.trace_closest(rays), o.trace_closest(rays)
+    assert_level1(hg, ho, f"soup bvh={world_is_bvh}")
+    assert (ho["entry"] >= 0).mean() > 0.5
+    # rays aimed at the duplicated primitives (ties)
+    n2 = 50000
+    org = np.array([0.0, 0.0, -12.0]) + rng.standard_normal((n2, 3)) * 0.5
+    tgt = np.stack([rng.random(n2) * 8 - 4, rng.random(n2) * 8 - 4, np.full(n2, -3.0)], axis=1)
+    rays2 = np.concatenate([org, tgt - org, np.zeros((n2, 1))], axis=1)
+    assert_level1(ctx.trace_closest(rays2), o.trace_closest(rays2), "ties")
+    # bounded intervals, including tmax exactly on a hit (closed for quads/triangles, open for spheres/planes)
+    t_exact = ho["t"][ho["entry"] >= 0][:20000]
+    sub = rays[ho["entry"] >= 0][:20000]
+    for k in range(0, len(sub), 5000):
+        tm = float(t_exact[k])
+        assert_level1(ctx.trace_closest(sub[k:k + 5000], 0.001, tm), o.trace_closest(sub[k:k + 5000], 0.001, tm), "tmax on a hit")
+        assert_level1(ctx.trace_closest(sub[k:k + 5000], tm, 1e9), o.trace_closest(sub[k:k + 5000], tm, 1e9), "tmin on a hit")
+
+
+def test_level1_degenerate_inputs(grt, orc, ctx):
+    # empty world, single primitive, axis-aligned rays with zero direction components, zero-length batch
+    cam = grt.make_camera(16, 1.0, 1, 5, 40, (0, 0, -5), (0, 0, 0))
+    empty = grt.SceneBuilder().build()
+    ctx.load((empty, cam))
+    rays = np.array([[0, 0, -5, 0, 0, 1, 0.0], [0, 0, -5, 1, 0, 0, 0.5]])
+    h = ctx.trace_closest(rays)
+    assert np.all(h["entry"] == -1) and np.all(h["prim"] == -1)
+    assert len(ctx.trace_closest(np.zeros((0, 7)))["t"]) == 0
+    b = grt.SceneBuilder()
+    m = b.material("lambertian", (0.5, 0.5, 0.5))
+    b.entry(grt.GEOM_LIST, b.box_group((-1, -1, -1), (1, 1, 1), m))
+    b.entry(grt.GEOM_SPHERE, b.sphere((0, 3, 0), 1.0, m))
+    built = b.build()
+    ctx.load((built, cam))
+    o = orc.OracleScene(built.desc_ptr, grt.C.pointer(cam))
+    axis = []
+    for x in np.linspace(-1.5, 1.5, 13):
+        for y in np.linspace(-1.5, 4.5, 13):
+            axis.append([x, y, -5, 0, 0, 1, 0])        # d.x = d.y = 0: 1/0 = inf in the slab test
+            axis.append([-5, y, x, 2, 0, 0, 0])
+            axis.append([x, 9, y / 3, 0, -3, 0, 0])
+    axis = np.array(axis, dtype=np.float64)
+    assert_level1(ctx.trace_closest(axis), o.trace_closest(axis), "axis-aligned")
+    # box-face tie: rays through an edge shared by two box quads
+    edge = np.array([[1.0, 0.3, -5, 0, 0, 1, 0], [0.2, 1.0, -5, 0, 0, 1, 0], [1.0, 1.0, -5, 0, 0, 1, 0]])
+    assert_level1(ctx.trace_closest(edge), o.trace_closest(edge), "box edges")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# HDRI importance sampling (rt/hdri.go:228-297)
+# ------------------------------------------------------------------------------------------------------------
+def test_hdri_sampling_matches_oracle(grt, orc, ctx):
+    sc = grt.config_scene("hdri-test", width=64, spp=1)
+    ctx.load(sc)
+    o = orc.OracleScene(sc.desc_ptr, sc.cam_ptr)
+    assert ctx.hdri_total_power() == o.hdri_total_power()  # same float64 loop order (rt/hdri.go:145-224)
+    rng = np.random.default_rng(4)
+    xi = rng.random((200000, 2))
+    xi[:6] = [[0, 0], [1 - 1e-16, 1 - 1e-16], [0, 1 - 1e-16], [0.5, 0.5], [1e-300, 0.999999], [0.25, 0]]
+    dg, eg, pg = ctx.hdri_sample(xi)
+    do, eo, po = o.hdri_sample(xi)
+    assert np.allclose(dg, do, rtol=0, atol=1e-14)
+    assert np.allclose(eg, eo, rtol=1e-6, atol=0)       # device texels are float32
+    assert np.allclose(pg, po, rtol=1e-12, atol=0)
+    dirs = rng.standard_normal((100000, 3))
+    dirs[:3] = [[0, 1, 0], [0, -1, 0], [1, 0, 0]]
+    assert np.allclose(ctx.hdri_pdf(dirs), o.hdri_pdf(dirs), rtol=1e-12)
+    assert np.allclose(ctx.hdri_lookup(dirs), o.hdri_lookup(dirs), rtol=2e-5, atol=1e-6)  # float32 bilinear weights
+    # chi-square style check: sampled pixel frequencies follow the luminance * cos(elevation) weights
+    W, H = sc.desc.env_width, sc.desc.env_height
+    u = 0.5 + np.arctan2(dg[:, 2], dg[:, 0]) / (2 * np.pi)
+    v = 0.5 - np.arcsin(np.clip(dg[:, 1], -1, 1)) / np.pi
+    rows = np.clip((v * H).astype(int), 0, H - 1) // 32
+    cols = np.clip((u * W).astype(int), 0, W - 1) // 64
+    counts = np.zeros((H // 32, W // 64))
+    np.add.at(counts, (rows, cols), 1)
+    rgb = np.ctypeslib.as_array(sc.desc.env_rgb, (H, W, 3))
+    lum = 0.2126 * rgb[..., 0] + 0.7152 * rgb[..., 1] + 0.0722 * rgb[..., 2]
+    wgt = lum * np.cos((0.5 - (np.arange(H) + 0.5) / H) * np.pi)[:, None]
+    expect = wgt.reshape(H // 32, 32, W // 64, 64).sum(axis=(1, 3))
+    expect = expect / expect.sum() * len(xi)
+    chi2 = ((counts - expect) ** 2 / expect).sum()
+    dof = counts.size - 1
+    assert chi2 < dof + 6 * np.sqrt(2 * dof), (chi2, dof)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# level 2: statistical image parity
+# ------------------------------------------------------------------------------------------------------------
+def z_scores(sg, qg, ng, so, qo, no):
+    mg, mo = sg / ng, so / no
+    vg = np.maximum(qg / ng - mg * mg, 0) * ng / max(ng - 1, 1)
+    vo = np.maximum(qo / no - mo * mo, 0) * no / max(no - 1, 1)
+    se = np.sqrt(vg / ng + vo / no)
+    return mg, mo, se
+
+
+def check_statistical(ctx, o, spp_g, spp_o, depth, cam_depth=None, seed=5, frac_limit=0.02, rel_mean=0.02):
+    ctx.clear()
+    ctx.enable_moments(True)
+    ctx.render_pass(spp_g, depth, camera_max_depth=cam_depth, seed=seed)
+    sg, qg, cnt = ctx.resolve_accum(moments=True)
+    assert np.all(cnt == spp_g)
+    r = o.render(spp_o, depth, seed=seed + 1, threads=0)
+    mg, mo, se = z_scores(sg.astype(np.float64), qg.astype(np.float64), spp_g, r["sum"], r["sumsq"], spp_o)
+    live = se > 1e-9
+    # pixels with no variance in either render (black background, saturated emitters) must agree outright
+    assert np.allclose(mg[~live], mo[~live], rtol=1e-4, atol=1e-5)
+    z = (mg[live] - mo[live]) / se[live]
+    frac = np.mean(np.abs(z) > 3)
+    assert frac < frac_limit, f"fraction of |z|>3 = {frac:.4f} (Gaussian 0.0027)"
+    assert abs(np.mean(z)) < 0.05, f"mean z = {np.mean(z):.4f}: coherent bias"
+    # image-level: global mean and 8x8 block means
+    gm, om = mg.mean(axis=(0, 1)), mo.mean(axis=(0, 1))
+    assert np.all(np.abs(gm - om) <= rel_mean * np.maximum(om, 1e-3)), (gm, om)
+    H, W, _ = mg.shape
+    bh, bw = H // 8 * 8, W // 8 * 8
+    blk = lambda a: a[:bh, :bw].reshape(bh // 8, 8, bw // 8, 8, 3).mean(axis=(1, 3))
+    bse = np.sqrt(blk(se ** 2) / 64)
+    bz = (blk(mg) - blk(mo)) / np.maximum(bse, 1e-9)
+    assert np.mean(np.abs(bz[bse > 1e-9]) > 4) < 0.01, "block-averaged bias"
+    # RMSE net of the noise both renders carry, relative to the mean level (north star: < 1 %)
+    noise = np.mean(se[live] ** 2)
+    rmse = np.sqrt(max(0.0, np.mean((mg - mo) ** 2) - noise * live.mean())) / max(mo.mean(), 1e-6)
+    assert rmse < 0.01 + 0.3 * np.sqrt(noise) / max(mo.mean(), 1e-6), f"excess RMSE {rmse:.4f}"
+    return mg, mo
+
+
+@pytest.mark.parametrize("name,width,spp,depth", [("cornell", 96, 128, 10), ("cornell-glossy", 96, 128, 5), ("random", 120, 96, 50),
+                                                 ("hdri-test", 128, 96, 20)])
+def test_level2_configured_scenes(grt, orc, ctx, name, width, spp, depth):
+    sc = grt.config_scene(name, width=width, spp=spp, depth=depth)
+    ctx.load(sc)
+    o = orc.OracleScene(sc.desc_ptr, sc.cam_ptr)
+    check_statistical(ctx, o, spp, spp, depth)
+
+
+def test_level2_reduced_depth_pass_sees_the_sky(grt, orc, ctx):
+    # passes 0/1 of the BucketRenderer run below Camera.MaxDepth, so the phantom-HDRI test `depth == c.MaxDepth`
+    # (rt/camera.go:456) is false and primary rays DO see the environment
+    sc = grt.config_scene("hdri-test", width=96, spp=32, depth=20)
+    ctx.load(sc)
+    o = orc.OracleScene(sc.desc_ptr, sc.cam_ptr)
+    mg, mo = check_statistical(ctx, o, 64, 64, 10, cam_depth=20)
+    assert mg[:8].mean() > 0.1  # sky rows are lit
+    ctx.clear()
+    ctx.render_pass(8, 20, camera_max_depth=20, seed=2)
+    s, _, _ = ctx.resolve_accum()
+    assert s[:8].max() == 0.0   # final pass: phantom background is black
+
+
+def test_level2_lucy(grt, orc, ctx):
+    sc = grt.config_scene("cornell-lucy", width=96, spp=32, depth=12)
+    ctx.load(sc)
+    o = orc.OracleScene(sc.desc_ptr, sc.cam_ptr)
+    check_statistical(ctx, o, 48, 48, 12, frac_limit=0.025)
+
+
+def test_level2_hdri_nee_with_area_light(grt, orc, ctx):
+    """A registered quad light AND an environment: exercises sampleHDRILight + sampleAreaLight together
+    (rt/camera.go:538-678), which none of the shipped scenes does."""
+    from conftest import SYN_HDR
+    _, _, _, rgb = orc.load_hdr(SYN_HDR, want_pixels=True)
+    b = grt.SceneBuilder()
+    ground = b.material("lambertian", b.checker(0.5, (0.2, 0.3, 0.1), (0.9, 0.9, 0.9)))
+    red = b.material("lambertian", (0.65, 0.05, 0.05))
+    glass = b.material("dielectric", 1.5)
+    metal = b.material("metal", (0.8, 0.6, 0.2), 0.3)
+    lm = b.material("light", (8, 7, 6))
+    b.entry(grt.GEOM_PLANE, b.planep((0, 0, 0), (0, 1, 0), ground))
+    b.entry(grt.GEOM_SPHERE, b.sphere((0, 1, 0), 1.0, red))
+    b.entry(grt.GEOM_SPHERE, b.sphere((-2.2, 0.8, 0.5), 0.8, glass))
+    b.entry(grt.GEOM_SPHERE, b.sphere((2.2, 0.8, 0.5), 0.8, metal))
+    lq = b.quadp((-1, 3.5, -1), (2, 0, 0), (0, 0, 2), lm)
+    b.entry(grt.GEOM_QUAD, lq)
+    b.light(lq)
+    b.environment(rgb, rotation_rad=0.7, importance_sampling=True)
+    built = b.build()
+    cam = grt.make_camera(96, 16.0 / 9.0, 64, 8, 40, (0, 2.5, 8), (0, 1, 0))
+    ctx.load((built, cam))
+    o = orc.OracleScene(built.desc_ptr, grt.C.pointer(cam))
+    check_statistical(ctx, o, 128, 128, 8, frac_limit=0.03)
+    assert ctx.stats()["shadow_rays"] > 0
+
+
+# ------------------------------------------------------------------------------------------------------------
+# size-independent properties, resolve, API behaviour
+# ------------------------------------------------------------------------------------------------------------
+def test_sample_slices_add_up_and_are_deterministic(grt, ctx):
+    """Sample slicing is how the path shards across GPUs: samples [0,16) must equal [0,8) + [8,16) (same Philox
+    counters) up to float32 summation order, and a pass is reproducible for a seed."""
+    sc = grt.config_scene("cornell-glossy", width=120, spp=16, depth=5)
+    ctx.load(sc)
+    ctx.clear(); ctx.render_pass(16, 5, seed=9)
+    full, _, n = ctx.resolve_accum()
+    ctx.clear(); ctx.render_pass(8, 5, seed=9, sample_base=0); ctx.render_pass(8, 5, seed=9, sample_base=8)
+    parts, _, n2 = ctx.resolve_accum()
+    assert np.all(n == 16) and np.all(n2 == 16)
+    assert np.allclose(full, parts, rtol=2e-5, atol=1e-5)
+    ctx.clear(); ctx.render_pass(16, 5, seed=9)
+    again, _, _ = ctx.resolve_accum()
+    assert np.allclose(full, again, rtol=2e-5, atol=1e-5)
+    ctx.clear(); ctx.render_pass(16, 5, seed=10)
+    other, _, _ = ctx.resolve_accum()
+    assert not np.allclose(full, other, rtol=1e-3, atol=1e-4)
+    # a small pool forces many regeneration rounds; the image must not depend on the pool size
+    c2 = grt.Context(0)
+    c2.set_option("pool_paths", 4096)
+    c2.load(sc)
+    c2.render_pass(16, 5, seed=9)
+    small, _, n3 = c2.resolve_accum()
+    c2.close()
+    assert np.all(n3 == 16) and np.allclose(full, small, rtol=2e-5, atol=1e-5)
+
+
+def test_resolve_matches_reference_pack(grt, orc, ctx):
+    sc = grt.config_scene("random", width=160, spp=8, depth=8)
+    ctx.load(sc)
+    ctx.clear(); ctx.render_pass(8, 8, seed=3)
+    s, _, _ = ctx.resolve_accum()
+    pix = ctx.resolve_rgba8(8)
+    ref = orc.resolve_rgba8(s.astype(np.float64), 8)   # scale, sqrt gamma, clamp 0.999, uint8(256 x), A = 255
+    assert pix.shape == (sc.height, sc.width, 4) and np.array_equal(pix, ref)
+    assert np.all(pix[..., 3] == 255)
+
+
+def test_depth_zero_and_errors(grt, ctx):
+    sc = grt.config_scene("cornell-glossy", width=64, spp=2, depth=5)
+    ctx.load(sc)
+    ctx.clear(); ctx.render_pass(4, 0, seed=1)             # RayColor(depth 0) is black (rt/camera.go:444-446)
+    s, _, _ = ctx.resolve_accum()
+    assert s.max() == 0.0
+    fresh = grt.Context(0)
+    with pytest.raises(grt.RtxError):
+        fresh.render_pass(1, 1)                              # no scene / camera: RTX_ERR_STATE
+    bad = grt.SceneBuilder()
+    bad.entry(grt.GEOM_SPHERE, 5)                            # dangling primitive index
+    with pytest.raises(grt.RtxError):
+        fresh.upload(bad.build().desc_ptr)
+    fresh.close()
+    with pytest.raises(grt.RtxError):
+        ctx.resolve_rgba8(0)
+
+
+def test_bucket_renderer_mirror(grt, orc):
+    """NewBucketRenderer(...).Update() state machine: three passes, the framebuffer holds the last one."""
+    sc = grt.config_scene("cornell-glossy", width=96, spp=32, depth=5)
+    pix, seconds = sc.bucket_render(seed=4)
+    assert pix.shape == (sc.height, sc.width, 4) and np.all(pix[..., 3] == 255) and seconds > 0
+    o = orc.OracleScene(sc.desc_ptr, sc.cam_ptr)
+    r = o.render(32, 5, seed=8, threads=0, moments=False)
+    ref = orc.resolve_rgba8(r["sum"], 32).astype(np.float64)
+    a = pix[..., :3].astype(np.float64)
+    assert abs(a.mean() - ref[..., :3].mean()) < 4.0         # 8-bit gamma-encoded levels
