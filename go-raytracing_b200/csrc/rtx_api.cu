@@ -40,7 +40,7 @@ struct rtx_ctx {
     int64_t pool_paths = 1 << 20;
     Ctl* ctl = nullptr;       // device
     Ctl* ctl_host = nullptr;  // pinned
-    int count_stats = 0, time_kernels = 1;
+    int count_stats = 0, time_kernels = 1, blas_leaf = 4;
     rtx_stats stats{};
     double env_total = 0;
     // scene summary
@@ -173,6 +173,10 @@ int32_t rtx_set_option(rtx_ctx* ctx, const char* key, int64_t value) {
         ctx->pool_paths = value;
     } else if (k == "count_stats") ctx->count_stats = (int)value;  // bit 0: extend kernel, bit 1: connect kernel
     else if (k == "time_kernels") ctx->time_kernels = value != 0;
+    else if (k == "blas_leaf") {  // triangles per BLAS leaf (1..8); takes effect at the next rtx_scene_upload
+        if (value < 1 || value > 8) return fail(ctx, RTX_ERR_INVALID, "blas_leaf must be in 1..8");
+        ctx->blas_leaf = (int)value;
+    }
     else return fail(ctx, RTX_ERR_INVALID, "unknown option '%s'", key);
     return RTX_OK;
 }
@@ -350,6 +354,7 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     };
     std::vector<int> groupRoot(d->n_groups, -1), groupTriBase(d->n_groups, 0);
     uint32_t blasNodes = 0;
+    int maxBlasDepth = 0, tlasDepth = 0;
     for (int g = 0; g < d->n_groups; g++) {
         if (d->group_kind[g] != RTX_GEOM_MESH) continue;
         int begin = d->group_begin[g], count = d->group_count[g];
@@ -362,7 +367,9 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
         groupTriBase[g] = base;
         std::vector<int> perm;
         size_t before = nodes.size();
-        groupRoot[g] = rtxbvh::build_bvh4(boxes, 4, nodes, perm, [&](int first, int cnt) { return ((base + first) << 3) | (cnt - 1); });
+        int depth = 0;
+        groupRoot[g] = rtxbvh::build_bvh4(boxes, ctx->blas_leaf, nodes, perm, [&](int first, int cnt) { return ((base + first) << 3) | (cnt - 1); }, &depth);
+        maxBlasDepth = std::max(maxBlasDepth, depth);
         blasNodes += (uint32_t)(nodes.size() - before);
         for (int k = 0; k < count; k++) pushTri(begin + perm[k], perm[k], ranks[perm[k]]);
         if (count > 0 && (size_t)(base + count) >= (1u << 28)) return fail(ctx, RTX_ERR_UNSUPPORTED, "too many triangles");
@@ -428,7 +435,11 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     }
     std::vector<int> perm;
     size_t before = nodes.size();
-    int tlasRoot = rtxbvh::build_bvh4(tb, 1, nodes, perm, [&](int first, int) { return first; });
+    int tlasRoot = rtxbvh::build_bvh4(tb, 1, nodes, perm, [&](int first, int) { return first; }, &tlasDepth);
+    // worst-case traversal stack: up to 3 deferred children per level on both levels + the instance marker
+    if (3 * (tlasDepth + maxBlasDepth) + 2 > RTX_STACK_SIZE)
+        return fail(ctx, RTX_ERR_UNSUPPORTED, "BVH too deep for the device traversal stack (TLAS depth %d, BLAS depth %d, stack %d)", tlasDepth,
+                    maxBlasDepth, RTX_STACK_SIZE);
     // leaf codes reference positions in `perm`; rewrite them to entry indices
     for (size_t ni = before; ni < nodes.size(); ni++)
         for (int c = 0; c < 4; c++)

@@ -128,19 +128,21 @@ struct Builder {
 //   leafCode(first, count) -> non-negative int; the node stores ~code. Appends nodes to `out` (global indices).
 // Returns the root node index (global) or -1 for an empty input. `perm` receives the primitive permutation.
 template <class LeafCode>
-int build_bvh4(const std::vector<Box>& boxes, int maxLeaf, std::vector<Node4>& out, std::vector<int>& perm, LeafCode leafCode) {
+int build_bvh4(const std::vector<Box>& boxes, int maxLeaf, std::vector<Node4>& out, std::vector<int>& perm, LeafCode leafCode, int* maxDepth = nullptr) {
+    if (maxDepth) *maxDepth = 0;
     if (boxes.empty()) { perm.clear(); return -1; }
     Builder B(boxes, maxLeaf);
     int root2 = B.build(0, (int)boxes.size());
     perm = B.idx;
-    struct Work { int n2; int outIndex; };
+    struct Work { int n2; int outIndex; int depth; };
     int rootOut = (int)out.size();
     out.emplace_back();
     std::vector<Work> stack;
-    stack.push_back({root2, rootOut});
+    stack.push_back({root2, rootOut, 1});
     while (!stack.empty()) {
         Work w = stack.back();
         stack.pop_back();
+        if (maxDepth && w.depth > *maxDepth) *maxDepth = w.depth;
         int kids[4];
         int nk = 0;
         const auto& n = B.n2[w.n2];
@@ -171,7 +173,7 @@ int build_bvh4(const std::vector<Box>& boxes, int maxLeaf, std::vector<Node4>& o
                     int oi = (int)out.size();
                     out.emplace_back();
                     node.child[i] = oi;
-                    stack.push_back({kids[i], oi});
+                    stack.push_back({kids[i], oi, w.depth + 1});
                 }
             } else {
                 float inf = std::numeric_limits<float>::infinity();

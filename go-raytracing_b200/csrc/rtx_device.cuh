@@ -12,7 +12,7 @@
 
 #include "../../include/rtx_b200.h"
 
-#define RTX_STACK_SIZE 64
+#define RTX_STACK_SIZE 48   /* checked against the built hierarchy at upload (rtx_api.cu) */
 #define RTX_SENTINEL 0x7fffffff
 #define RTX_INF_D (__longlong_as_double(0x7ff0000000000000LL))
 
@@ -344,8 +344,20 @@ struct VolumeRng {
 __device__ double2 rtx_volume_uniform(const VolumeRng& vr, int entry);  // two uniforms, defined in rtx_kernels.cuh (Philox)
 
 // ---- the scene query: closest hit (or any hit) of world.Hit(r, [tmin,tmax]) ----------------------------------------
+// Two-level, stack-based traversal of the 4-wide BVH in "while-while" form: an inner loop descends through internal
+// nodes only (all lanes of a warp run the same box-test code), leaves / instance entries are handled between inner
+// loops. The traversal stack lives in shared memory, one column per thread (bank-conflict free), so that stack
+// traffic does not compete with node and triangle fetches for L1. Every kernel that calls this runs 128-thread blocks.
+#define RTX_TRACE_THREADS 128
+#define RTX_DONE (int)0x80000001   /* negative, never a valid leaf code */
+#undef RTX_SENTINEL
+#define RTX_SENTINEL (int)0x80000000
+
 template <bool ANY_HIT>
 __device__ __noinline__ Hit trace_scene(const DevScene& S, const RayD& rw, double tmin, double tmax, const VolumeRng& vr, TraceCounters* tc) {
+    __shared__ int s_stack[RTX_STACK_SIZE][RTX_TRACE_THREADS];
+    int* stack = &s_stack[0][threadIdx.x];
+#define STK(i) stack[(i) * RTX_TRACE_THREADS]
     Tracer<ANY_HIT> T(S, tmin, tmax, tc);
     // entries with unbounded geometry are tested for every ray
     for (int k = 0; k < S.n_unbounded; k++) {
@@ -358,98 +370,97 @@ __device__ __noinline__ Hit trace_scene(const DevScene& S, const RayD& rw, doubl
     }
     if (S.tlas_root < 0) return T.best;
 
-    int stack[RTX_STACK_SIZE];
     int sp = 0;
-    RayF fw;
-    make_rayf(rw, fw);
-    RayF f = fw;
+    RayF f;
+    make_rayf(rw, f);
     RayD ro = rw;   // current (object-space when inside an instance) ray
     int cur = -1;   // entry index of the instance being traversed
-    DEntry ce;
-    float ftmin = __double2float_rd(tmin);
+    int crank = 0;
+    const float ftmin = __double2float_rd(tmin);
+    const float INF = __int_as_float(0x7f800000);
     int node = S.tlas_root;
     for (;;) {
-        if (node >= 0) {
+        // ---- inner loop: internal nodes only
+        while (node >= 0) {
             float d[4]; int c[4];
             if (tc) tc->nodes++;
             node_test(S.nodes + 8 * (size_t)node, f, ftmin, __double2float_ru(T.best.t), d, c);
-            // sort the 4 children by entry distance (5-comparator network)
 #define RTX_CSWAP(i, j) if (d[j] < d[i]) { float td = d[i]; d[i] = d[j]; d[j] = td; int tcx = c[i]; c[i] = c[j]; c[j] = tcx; }
             RTX_CSWAP(0, 1) RTX_CSWAP(2, 3) RTX_CSWAP(0, 2) RTX_CSWAP(1, 3) RTX_CSWAP(1, 2)
 #undef RTX_CSWAP
-            const float INF = __int_as_float(0x7f800000);
-            if (d[3] < INF) stack[sp++] = c[3];
-            if (d[2] < INF) stack[sp++] = c[2];
-            if (d[1] < INF) stack[sp++] = c[1];
-            if (d[0] < INF) { node = c[0]; continue; }
-        } else {
+            if (d[3] < INF) { STK(sp) = c[3]; sp++; }
+            if (d[2] < INF) { STK(sp) = c[2]; sp++; }
+            if (d[1] < INF) { STK(sp) = c[1]; sp++; }
+            if (d[0] < INF) node = c[0];
+            else if (sp > 0) { sp--; node = STK(sp); }
+            else node = RTX_DONE;
+        }
+        if (node == RTX_DONE) break;
+        // ---- a leaf, or the marker that ends an instance
+        if (node == RTX_SENTINEL) {
+            cur = -1; ro = rw;
+            make_rayf(rw, f);
+        } else if (cur >= 0) {
+            // BLAS leaf: code = first << 3 | (count - 1), triangles contiguous in device order
             int code = ~node;
-            if (cur < 0) {
-                // TLAS leaf: exactly one world entry
-                int ei = code;
-                DEntry e = S.entries[ei];
-                RayD r2 = rw;
-                xform_ray(S, e, r2);
-                if (e.volume >= 0) {
-                    if (!vr.transparent) {
-                        // rt/volume.go:34-79
-                        double t1 = isect_boundary(S, e, r2, -RTX_INF_D, RTX_INF_D, tc);
-                        if (t1 == t1) {
-                            double t2 = isect_boundary(S, e, r2, t1 + 0.0001, RTX_INF_D, tc);
-                            if (t2 == t2) {
-                                if (t1 < tmin) t1 = tmin;
-                                if (t2 > T.best.t) t2 = T.best.t;
-                                if (t1 < t2) {
-                                    if (t1 < 0) t1 = 0;
-                                    double rayLength = sqrt(rw.dx * rw.dx + rw.dy * rw.dy + rw.dz * rw.dz);
-                                    double inside = (t2 - t1) * rayLength;
-                                    double2 uu = rtx_volume_uniform(vr, ei);
-                                    double nid = S.volumes[e.volume].neg_inv_density;
-                                    double hd = nid * log(uu.x);
-                                    if (S.vol_draws > 1) hd = fmin(hd, nid * log(uu.y));  // leaf visited twice, see DevScene::vol_draws
-                                    if (!(hd > inside)) T.offer(t1 + hd / rayLength, ei, e.rank, RTX_KIND_VOLUME, e.volume, 0, 0);
-                                }
+            int first = code >> 3, cnt = (code & 7) + 1;
+            for (int k = 0; k < cnt; k++) {
+                int ti = first + k;
+                if (tc) tc->tris++;
+                double t = isect_tri(S.tris + 10 * (size_t)ti, ro, nullptr);
+                if (tmin <= t && t <= T.best.t) {
+                    int4 info = __ldg(S.tri_info + ti);
+                    T.offer(t, cur, crank, RTX_GEOM_TRIANGLE, ti, info.x, info.z);
+                }
+            }
+        } else {
+            // TLAS leaf: exactly one world entry
+            int ei = ~node;
+            DEntry e = S.entries[ei];
+            RayD r2 = rw;
+            xform_ray(S, e, r2);
+            if (e.volume >= 0) {
+                if (!vr.transparent) {
+                    // rt/volume.go:34-79
+                    double t1 = isect_boundary(S, e, r2, -RTX_INF_D, RTX_INF_D, tc);
+                    if (t1 == t1) {
+                        double t2 = isect_boundary(S, e, r2, t1 + 0.0001, RTX_INF_D, tc);
+                        if (t2 == t2) {
+                            if (t1 < tmin) t1 = tmin;
+                            if (t2 > T.best.t) t2 = T.best.t;
+                            if (t1 < t2) {
+                                if (t1 < 0) t1 = 0;
+                                double rayLength = sqrt(rw.dx * rw.dx + rw.dy * rw.dy + rw.dz * rw.dz);
+                                double inside = (t2 - t1) * rayLength;
+                                double2 uu = rtx_volume_uniform(vr, ei);
+                                double nid = S.volumes[e.volume].neg_inv_density;
+                                double hd = nid * log(uu.x);
+                                if (S.vol_draws > 1) hd = fmin(hd, nid * log(uu.y));  // leaf visited twice, see DevScene::vol_draws
+                                if (!(hd > inside)) T.offer(t1 + hd / rayLength, ei, e.rank, RTX_KIND_VOLUME, e.volume, 0, 0);
                             }
                         }
                     }
-                } else if (e.kind == RTX_GEOM_MESH) {
-                    stack[sp++] = RTX_SENTINEL;
-                    cur = ei; ce = e; ro = r2;
-                    make_rayf(ro, f);
-                    node = e.a;
-                    continue;
-                } else if (e.kind == RTX_GEOM_LIST) {
-                    for (int k = 0; k < e.b; k++) {
-                        int2 it = S.list_items[e.a + k];
-                        T.test_prim(it.x, it.y, r2, ei, e.rank, k, k);
-                    }
-                } else {
-                    T.test_prim(e.kind, e.index, r2, ei, e.rank, 0, 0);
+                }
+            } else if (e.kind == RTX_GEOM_MESH) {
+                STK(sp) = RTX_SENTINEL; sp++;
+                cur = ei; crank = e.rank; ro = r2;
+                make_rayf(ro, f);
+                node = e.a;
+                continue;
+            } else if (e.kind == RTX_GEOM_LIST) {
+                for (int k = 0; k < e.b; k++) {
+                    int2 it = S.list_items[e.a + k];
+                    T.test_prim(it.x, it.y, r2, ei, e.rank, k, k);
                 }
             } else {
-                // BLAS leaf: code = first << 3 | (count - 1), triangles contiguous in device order
-                int first = code >> 3, cnt = (code & 7) + 1;
-                for (int k = 0; k < cnt; k++) {
-                    int ti = first + k;
-                    if (tc) tc->tris++;
-                    double t = isect_tri(S.tris + 10 * (size_t)ti, ro, nullptr);
-                    if (tmin <= t && t <= T.best.t) {
-                        int4 info = __ldg(S.tri_info + ti);
-                        T.offer(t, cur, ce.rank, RTX_GEOM_TRIANGLE, ti, info.x, info.z);
-                    }
-                }
+                T.test_prim(e.kind, e.index, r2, ei, e.rank, 0, 0);
             }
-            if (ANY_HIT && T.have) return T.best;
         }
-        // pop
-        if (sp == 0) break;
-        node = stack[--sp];
-        if (node == RTX_SENTINEL) {
-            cur = -1; f = fw;
-            if (sp == 0) break;
-            node = stack[--sp];
-        }
+        if (ANY_HIT && T.have) return T.best;
+        if (sp > 0) { sp--; node = STK(sp); }
+        else break;
     }
+#undef STK
     return T.best;
 }
 

@@ -28,6 +28,10 @@ def camera_batch(sc, n, rng):
 def main():
     names = sys.argv[1:] or ["cornell", "cornell-glossy", "random", "hdri-test", "cornell-lucy"]
     ctx = grt.Context(0)
+    for kv in os.environ.get("RTX_OPTS", "").split(","):  # e.g. RTX_OPTS=blas_leaf=2,pool_paths=2097152
+        if "=" in kv:
+            k, v = kv.split("=")
+            ctx.set_option(k, int(v))
     rng = np.random.default_rng(0)
     for name in names:
         w = 1200 if name == "cornell-lucy" else 400
