@@ -242,8 +242,10 @@ def check_statistical(ctx, o, spp_g, spp_o, depth, cam_depth=None, seed=5, frac_
     assert np.all(cnt == spp_g)
     r = o.render(spp_o, depth, seed=seed + 1, threads=0)
     mg, mo, se = z_scores(sg.astype(np.float64), qg.astype(np.float64), spp_g, r["sum"], r["sumsq"], spp_o)
-    live = se > 1e-9
-    # pixels with no variance in either render (black background, saturated emitters) must agree outright
+    # Pixels with (numerically) no variance in either render — black background, saturated emitters, the constant blue
+    # channel of the sky gradient — must agree outright. The device accumulates float32 sums, so a channel that is
+    # exactly constant in the float64 oracle still shows a ~1e-7 relative spread there: it is not a live pixel.
+    live = se > 1e-5 * np.maximum(1.0, np.abs(mo))
     assert np.allclose(mg[~live], mo[~live], rtol=1e-4, atol=1e-5)
     z = (mg[live] - mo[live]) / se[live]
     frac = np.mean(np.abs(z) > 3)
