@@ -46,6 +46,8 @@ struct rtx_ctx {
     // scene summary
     uint32_t tlas_nodes = 0, blas_nodes = 0, n_entries = 0, n_tris = 0;
     std::vector<cudaEvent_t> events;
+    int num_sms = 0;
+    int* batch_cursor = nullptr;  // job cursor of k_trace_closest
 };
 
 static int32_t fail(rtx_ctx* ctx, int32_t code, const char* fmt, ...) {
@@ -136,6 +138,12 @@ int32_t rtx_create(int32_t device_id, rtx_ctx** out) {
         return RTX_ERR_CUDA;
     }
     ctx->own_stream = ctx->stream;
+    cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device_id);
+    if (ctx->num_sms <= 0 || cudaMalloc((void**)&ctx->batch_cursor, sizeof(int)) != cudaSuccess) {
+        fail(nullptr, RTX_ERR_CUDA, "rtx_create: device query / allocation failed");
+        rtx_destroy(ctx);
+        return RTX_ERR_CUDA;
+    }
     *out = ctx;
     return RTX_OK;
 }
@@ -157,6 +165,7 @@ int32_t rtx_destroy(rtx_ctx* ctx) {
     if (ctx->accum) cudaFree(ctx->accum);
     if (ctx->accum_sq) cudaFree(ctx->accum_sq);
     if (ctx->ctl) cudaFree(ctx->ctl);
+    if (ctx->batch_cursor) cudaFree(ctx->batch_cursor);
     if (ctx->ctl_host) cudaFreeHost(ctx->ctl_host);
     for (auto ev : ctx->events) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -697,7 +706,8 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
     double msKind[EV_KINDS] = {0, 0, 0, 0, 0};
     uint64_t launches = 1;
     CU(cudaEventRecord(evStart, st));
-    const int gridBig = (P + 255) / 256, gridTrace = (P + 127) / 128, gridShadow = (2 * P + 127) / 128;
+    // the trace kernels are persistent: one resident wave of warps pulls rays from a device-side cursor
+    const int gridBig = (P + 255) / 256, gridTrace = ctx->num_sms * RTX_TRACE_BLOCKS, gridShadow = gridTrace;
     long long iter = 0;
     int activeEstimate = P;  // shrinks the launch grids once the pool drains (from the last polled control block)
     for (;;) {
@@ -710,14 +720,14 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
             if (timing) cudaEventRecord(ev[0], st);
             k_generate<<<gridBig, 256, 0, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->C, pp);
             if (timing) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
-            if (ctx->count_stats & 1) k_extend<true><<<gridTrace, 128, 0, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->S, pp);
-            else k_extend<false><<<gridTrace, 128, 0, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->S, pp);
+            if (ctx->count_stats & 1) k_extend<true><<<gridTrace, RTX_TRACE_THREADS, 0, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->S, pp);
+            else k_extend<false><<<gridTrace, RTX_TRACE_THREADS, 0, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->S, pp);
             if (timing) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); }
             k_shade<<<gridBig, 256, 0, st>>>(ctx->ctl, ctx->pool, q_next, ctx->S, ctx->C, pp);
             if (timing) { cudaEventRecord(ev[5], st); cudaEventRecord(ev[6], st); }
             if (ctx->S.n_lights > 0) {
-                if (ctx->count_stats & 2) k_connect<true><<<gridShadow, 128, 0, st>>>(ctx->ctl, ctx->pool, ctx->S, pp);
-                else k_connect<false><<<gridShadow, 128, 0, st>>>(ctx->ctl, ctx->pool, ctx->S, pp);
+                if (ctx->count_stats & 2) k_connect<true><<<gridShadow, RTX_TRACE_THREADS, 0, st>>>(ctx->ctl, ctx->pool, ctx->S, pp);
+                else k_connect<false><<<gridShadow, RTX_TRACE_THREADS, 0, st>>>(ctx->ctl, ctx->pool, ctx->S, pp);
                 launches++;
             }
             if (timing) { cudaEventRecord(ev[7], st); cudaEventRecord(ev[8], st); }
@@ -816,7 +826,10 @@ int32_t rtx_trace_closest(rtx_ctx* ctx, const double* rays, int64_t n, double tm
     CU(sc.in(&dRays, rays, (size_t)7 * n, ctx->stream));
     CU(sc.out(&dEntry, entry_id, n)); CU(sc.out(&dPrim, prim_id, n)); CU(sc.out(&dT, t, n)); CU(sc.out(&dN, normal, 3 * n));
     CU(sc.out(&dFront, (unsigned char*)front, n)); CU(sc.out(&dUV, uv, 2 * n)); CU(sc.out(&dP, p, 3 * n));
-    k_trace_closest<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->S, dRays, n, tmin, tmax, dEntry, dPrim, dT, dN, dFront, dUV, dP);
+    if (n > (int64_t)1 << 30) return fail(ctx, RTX_ERR_INVALID, "rtx_trace_closest: at most 2^30 rays per call");
+    CU(cudaMemsetAsync(ctx->batch_cursor, 0, sizeof(int), ctx->stream));
+    k_trace_closest<<<ctx->num_sms * RTX_TRACE_BLOCKS, RTX_TRACE_THREADS, 0, ctx->stream>>>(ctx->S, dRays, (int)n, tmin, tmax, ctx->batch_cursor, dEntry, dPrim, dT, dN,
+                                                                                            dFront, dUV, dP);
     CU(cudaGetLastError());
     BACK(dEntry, entry_id, n); BACK(dPrim, prim_id, n); BACK(dT, t, n); BACK(dN, normal, 3 * n); BACK(dFront, front, n); BACK(dUV, uv, 2 * n); BACK(dP, p, 3 * n);
     CU(cudaStreamSynchronize(ctx->stream));

@@ -30,7 +30,7 @@ struct Box {
 };
 
 struct Node4 {  // 128 bytes; matches the 8 x float4 the device loads
-    float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
+    float lox[4], hix[4], loy[4], hiy[4], loz[4], hiz[4];  // {lo,hi} pairs per axis: the device picks near/far by a 16-byte offset
     int32_t child[4];  // >= 0 internal node index (global); < 0 leaf code (~child); empty: box inverted
     int32_t pad[4];
 };

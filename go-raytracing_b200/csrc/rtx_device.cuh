@@ -13,7 +13,6 @@
 #include "../../include/rtx_b200.h"
 
 #define RTX_STACK_SIZE 48   /* checked against the built hierarchy at upload (rtx_api.cu) */
-#define RTX_SENTINEL 0x7fffffff
 #define RTX_INF_D (__longlong_as_double(0x7ff0000000000000LL))
 
 struct DEntry {      // 32 B, one per world entry (rt/hittable_list.go:16 insertion order)
@@ -83,9 +82,11 @@ struct DevScene {
 struct RayD {
     double ox, oy, oz, dx, dy, dz, tm;
 };
-struct RayF {  // float32 ray for box tests: padded near/far origins and reciprocal direction
-    float onx, ony, onz, ofx, ofy, ofz, ix, iy, iz;
-    bool nx, ny, nz;
+struct RayF {  // float32 ray for the box tests: t_plane = fma(plane, i, c), with c padded so that t_near only errs low, t_far high
+    float ix, iy, iz;     // 1 / d
+    float cnx, cny, cnz;  // -(o * i) - E   (near planes)
+    float cfx, cfy, cfz;  // -(o * i) + E   (far planes),  E = 2^-21 |o * i|
+    int offx, offy, offz; // byte offset of the NEAR plane inside a node's {lo,hi} float4 pair: 0, or 16 when d < 0
 };
 struct Hit {
     double t;
@@ -238,35 +239,39 @@ __device__ __forceinline__ double isect_prim(const DevScene& S, int kind, int id
 }
 
 // ---- float32 conservative ray ---------------------------------------------------------------------------------
-#define RTX_BOX_EPS 4.76837158e-7f  /* 2^-21 relative slack on tnear / tfar */
+// Exact slab parameter: t = (p - o) / d with the float64 ray. Computed: fma(p, i~, c) with i~ = fl(1 / fl(d)) (relative
+// error <= 2^-23) and c = -fl(fl(o) * i~) -/+ E. Then |computed - t| <= 2^-21 |t| + 2^-22 |o / d|, so with
+// E = 2^-21 |o * i| and the 2^-21 relative slack applied to tnear / tfar in node_test, a box the float64 ray touches
+// is never culled. A zero direction component gives i = +-inf and NaN slab values, which fmaxf / fminf ignore (that axis
+// then never culls).
+#define RTX_BOX_EPS 4.76837158e-7f  /* 2^-21 */
 __device__ __forceinline__ void make_rayf(const RayD& r, RayF& f) {
-    float ox = __double2float_rn(r.ox), oy = __double2float_rn(r.oy), oz = __double2float_rn(r.oz);
-    float dx = __double2float_rn(r.dx), dy = __double2float_rn(r.dy), dz = __double2float_rn(r.dz);
-    // pad >= |o - fl(o)| = 2^-24 |o|; 2^-22 |o| + tiny keeps a 4x margin
-    float px = fmaf(fabsf(ox), 2.38418579e-7f, 1e-30f), py = fmaf(fabsf(oy), 2.38418579e-7f, 1e-30f), pz = fmaf(fabsf(oz), 2.38418579e-7f, 1e-30f);
-    f.nx = signbit(dx); f.ny = signbit(dy); f.nz = signbit(dz);
+    const float ox = __double2float_rn(r.ox), oy = __double2float_rn(r.oy), oz = __double2float_rn(r.oz);
+    const float dx = __double2float_rn(r.dx), dy = __double2float_rn(r.dy), dz = __double2float_rn(r.dz);
     f.ix = 1.0f / dx; f.iy = 1.0f / dy; f.iz = 1.0f / dz;
-    f.onx = f.nx ? ox - px : ox + px; f.ofx = f.nx ? ox + px : ox - px;
-    f.ony = f.ny ? oy - py : oy + py; f.ofy = f.ny ? oy + py : oy - py;
-    f.onz = f.nz ? oz - pz : oz + pz; f.ofz = f.nz ? oz + pz : oz - pz;
+    const float px = ox * f.ix, py = oy * f.iy, pz = oz * f.iz;
+    const float ex = fmaf(fabsf(px), RTX_BOX_EPS, 1e-30f), ey = fmaf(fabsf(py), RTX_BOX_EPS, 1e-30f), ez = fmaf(fabsf(pz), RTX_BOX_EPS, 1e-30f);
+    f.cnx = -px - ex; f.cfx = -px + ex;
+    f.cny = -py - ey; f.cfy = -py + ey;
+    f.cnz = -pz - ez; f.cfz = -pz + ez;
+    f.offx = signbit(dx) ? 16 : 0; f.offy = signbit(dy) ? 16 : 0; f.offz = signbit(dz) ? 16 : 0;
 }
 
-// One 4-wide node: returns conservative entry distances (inf = culled) for the 4 children.
-__device__ __forceinline__ void node_test(const float4* __restrict__ n, const RayF& f, float tmin, float tmax, float d[4], int c[4]) {
-    float4 lox = __ldg(n + 0), loy = __ldg(n + 1), loz = __ldg(n + 2), hix = __ldg(n + 3), hiy = __ldg(n + 4), hiz = __ldg(n + 5);
-    int4 ch = __ldg(reinterpret_cast<const int4*>(n + 6));
-    float4 nx = f.nx ? hix : lox, fx = f.nx ? lox : hix;
-    float4 ny = f.ny ? hiy : loy, fy = f.ny ? loy : hiy;
-    float4 nz = f.nz ? hiz : loz, fz = f.nz ? loz : hiz;
-#define RTX_CHILD(k, comp)                                                                     \
-    {                                                                                          \
-        float tnx = (nx.comp - f.onx) * f.ix, tny = (ny.comp - f.ony) * f.iy, tnz = (nz.comp - f.onz) * f.iz; \
-        float tfx = (fx.comp - f.ofx) * f.ix, tfy = (fy.comp - f.ofy) * f.iy, tfz = (fz.comp - f.ofz) * f.iz; \
-        float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                   \
-        float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));                                   \
-        tn = fmaf(-fabsf(tn), RTX_BOX_EPS, tn);                                                \
-        tf = fmaf(fabsf(tf), RTX_BOX_EPS, tf);                                                 \
-        d[k] = (tn <= tf) ? tn : __int_as_float(0x7f800000);                                   \
+// One 4-wide node (128 B: {lox,hix,loy,hiy,loz,hiz} float4 pairs, child int4, pad): conservative entry distances
+// (inf = culled) of the 4 children. The near / far planes are picked by address (per-ray byte offsets), not by selects.
+__device__ __forceinline__ void node_test(const float4* __restrict__ nodes, int node, const RayF& f, float tmin, float tmax, float d[4], int c[4]) {
+    const char* nb = reinterpret_cast<const char*>(nodes) + (size_t)node * 128;
+    const float4 nx = __ldg(reinterpret_cast<const float4*>(nb + f.offx)), fx = __ldg(reinterpret_cast<const float4*>(nb + 16 - f.offx));
+    const float4 ny = __ldg(reinterpret_cast<const float4*>(nb + 32 + f.offy)), fy = __ldg(reinterpret_cast<const float4*>(nb + 48 - f.offy));
+    const float4 nz = __ldg(reinterpret_cast<const float4*>(nb + 64 + f.offz)), fz = __ldg(reinterpret_cast<const float4*>(nb + 80 - f.offz));
+    const int4 ch = __ldg(reinterpret_cast<const int4*>(nb + 96));
+#define RTX_CHILD(k, comp)                                                                                   \
+    {                                                                                                        \
+        float tn = fmaxf(fmaxf(fmaf(nx.comp, f.ix, f.cnx), fmaf(ny.comp, f.iy, f.cny)), fmaxf(fmaf(nz.comp, f.iz, f.cnz), tmin)); \
+        float tf = fminf(fminf(fmaf(fx.comp, f.ix, f.cfx), fmaf(fy.comp, f.iy, f.cfy)), fminf(fmaf(fz.comp, f.iz, f.cfz), tmax)); \
+        tn = fmaf(-fabsf(tn), RTX_BOX_EPS, tn);                                                              \
+        tf = fmaf(fabsf(tf), RTX_BOX_EPS, tf);                                                               \
+        d[k] = (tn <= tf) ? tn : __int_as_float(0x7f800000);                                                 \
     }
     RTX_CHILD(0, x) RTX_CHILD(1, y) RTX_CHILD(2, z) RTX_CHILD(3, w)
 #undef RTX_CHILD
@@ -279,189 +284,6 @@ __device__ __forceinline__ void node_test(const float4* __restrict__ n, const Ra
 __device__ __forceinline__ bool tie_candidate_wins(int crank_e, int crank_p, int ckind, int brank_e, int brank_p, int bkind) {
     bool cand_later = (crank_e > brank_e) || (crank_e == brank_e && crank_p > brank_p);
     return cand_later ? kind_closed(ckind) : !kind_closed(bkind);
-}
-
-struct BestRank { int e, p; };
-
-template <bool ANY_HIT>
-struct Tracer {
-    const DevScene& S;
-    TraceCounters* tc;
-    double tmin, tlimit;  // caller's interval
-    Hit best;
-    BestRank brank;
-    bool have;
-
-    __device__ __forceinline__ Tracer(const DevScene& s, double tmn, double tmx, TraceCounters* c) : S(s), tc(c), tmin(tmn), tlimit(tmx) {
-        best.t = tmx; best.entry = -1; best.kind = -1; best.prim = -1; best.item = -1;
-        brank.e = -1; brank.p = -1; have = false;
-    }
-    // candidate at parameter t (already inside the primitive's own interval convention w.r.t. [tmin, best.t])
-    __device__ __forceinline__ void offer(double t, int entry, int erank, int kind, int prim, int item, int prank) {
-        if (!(t == t)) return;
-        if (t == best.t) {
-            if (!have) { if (!kind_closed(kind)) return; }
-            else if (!tie_candidate_wins(erank, prank, kind, brank.e, brank.p, best.kind)) return;
-        }
-        best.t = t; best.entry = entry; best.kind = kind; best.prim = prim; best.item = item;
-        brank.e = erank; brank.p = prank; have = true;
-    }
-    // candidate interval for primitive tests: accept up to and including the current best (ties resolved in offer)
-    __device__ __forceinline__ double tmax_closed() const { return best.t; }
-    __device__ __forceinline__ double tmax_open() const { return have ? nextafter(best.t, RTX_INF_D) : best.t; }
-
-    __device__ __forceinline__ void test_prim(int kind, int idx, const RayD& r, int entry, int erank, int item, int prank) {
-        // open-interval primitives must still be allowed to tie with an existing best hit
-        double mx = kind_closed(kind) ? tmax_closed() : tmax_open();
-        double t = isect_prim(S, kind, idx, r, tmin, mx, tc);
-        offer(t, entry, erank, kind, idx, item, prank);
-    }
-};
-
-// Closest boundary crossing of an entry's geometry in [tmin, tmax] for Volume (rt/volume.go:38-46): HittableList
-// semantics (rt/hittable_list.go:31-45) over the list items, or a single primitive.
-__device__ __forceinline__ double isect_boundary(const DevScene& S, const DEntry& e, const RayD& ro, double tmin, double tmax, TraceCounters* tc) {
-    double closest = tmax;
-    bool hit = false;
-    if (e.kind == RTX_GEOM_LIST) {
-        for (int k = 0; k < e.b; k++) {
-            int2 it = S.list_items[e.a + k];
-            double t = isect_prim(S, it.x, it.y, ro, tmin, closest, tc);
-            if (t == t) { closest = t; hit = true; }
-        }
-    } else {
-        double t = isect_prim(S, e.kind, e.index, ro, tmin, closest, tc);
-        if (t == t) { closest = t; hit = true; }
-    }
-    return hit ? closest : RTX_NAN_D;
-}
-
-// uniform in (0,1) for the Volume free-flight draw, supplied by the caller's counter RNG
-struct VolumeRng {
-    uint32_t k0, k1, c0, c1, c2;
-    bool transparent;  // level-1 parity protocol: volumes do not intersect
-};
-__device__ double2 rtx_volume_uniform(const VolumeRng& vr, int entry);  // two uniforms, defined in rtx_kernels.cuh (Philox)
-
-// ---- the scene query: closest hit (or any hit) of world.Hit(r, [tmin,tmax]) ----------------------------------------
-// Two-level, stack-based traversal of the 4-wide BVH in "while-while" form: an inner loop descends through internal
-// nodes only (all lanes of a warp run the same box-test code), leaves / instance entries are handled between inner
-// loops. The traversal stack lives in shared memory, one column per thread (bank-conflict free), so that stack
-// traffic does not compete with node and triangle fetches for L1. Every kernel that calls this runs 128-thread blocks.
-#define RTX_TRACE_THREADS 128
-#define RTX_DONE (int)0x80000001   /* negative, never a valid leaf code */
-#undef RTX_SENTINEL
-#define RTX_SENTINEL (int)0x80000000
-
-template <bool ANY_HIT>
-__device__ __noinline__ Hit trace_scene(const DevScene& S, const RayD& rw, double tmin, double tmax, const VolumeRng& vr, TraceCounters* tc) {
-    __shared__ int s_stack[RTX_STACK_SIZE][RTX_TRACE_THREADS];
-    int* stack = &s_stack[0][threadIdx.x];
-#define STK(i) stack[(i) * RTX_TRACE_THREADS]
-    Tracer<ANY_HIT> T(S, tmin, tmax, tc);
-    // entries with unbounded geometry are tested for every ray
-    for (int k = 0; k < S.n_unbounded; k++) {
-        int ei = S.unbounded[k];
-        DEntry e = S.entries[ei];
-        RayD ro = rw;
-        xform_ray(S, e, ro);
-        T.test_prim(e.kind, e.index, ro, ei, e.rank, 0, 0);
-        if (ANY_HIT && T.have) return T.best;
-    }
-    if (S.tlas_root < 0) return T.best;
-
-    int sp = 0;
-    RayF f;
-    make_rayf(rw, f);
-    RayD ro = rw;   // current (object-space when inside an instance) ray
-    int cur = -1;   // entry index of the instance being traversed
-    int crank = 0;
-    const float ftmin = __double2float_rd(tmin);
-    const float INF = __int_as_float(0x7f800000);
-    int node = S.tlas_root;
-    for (;;) {
-        // ---- inner loop: internal nodes only
-        while (node >= 0) {
-            float d[4]; int c[4];
-            if (tc) tc->nodes++;
-            node_test(S.nodes + 8 * (size_t)node, f, ftmin, __double2float_ru(T.best.t), d, c);
-#define RTX_CSWAP(i, j) if (d[j] < d[i]) { float td = d[i]; d[i] = d[j]; d[j] = td; int tcx = c[i]; c[i] = c[j]; c[j] = tcx; }
-            RTX_CSWAP(0, 1) RTX_CSWAP(2, 3) RTX_CSWAP(0, 2) RTX_CSWAP(1, 3) RTX_CSWAP(1, 2)
-#undef RTX_CSWAP
-            if (d[3] < INF) { STK(sp) = c[3]; sp++; }
-            if (d[2] < INF) { STK(sp) = c[2]; sp++; }
-            if (d[1] < INF) { STK(sp) = c[1]; sp++; }
-            if (d[0] < INF) node = c[0];
-            else if (sp > 0) { sp--; node = STK(sp); }
-            else node = RTX_DONE;
-        }
-        if (node == RTX_DONE) break;
-        // ---- a leaf, or the marker that ends an instance
-        if (node == RTX_SENTINEL) {
-            cur = -1; ro = rw;
-            make_rayf(rw, f);
-        } else if (cur >= 0) {
-            // BLAS leaf: code = first << 3 | (count - 1), triangles contiguous in device order
-            int code = ~node;
-            int first = code >> 3, cnt = (code & 7) + 1;
-            for (int k = 0; k < cnt; k++) {
-                int ti = first + k;
-                if (tc) tc->tris++;
-                double t = isect_tri(S.tris + 10 * (size_t)ti, ro, nullptr);
-                if (tmin <= t && t <= T.best.t) {
-                    int4 info = __ldg(S.tri_info + ti);
-                    T.offer(t, cur, crank, RTX_GEOM_TRIANGLE, ti, info.x, info.z);
-                }
-            }
-        } else {
-            // TLAS leaf: exactly one world entry
-            int ei = ~node;
-            DEntry e = S.entries[ei];
-            RayD r2 = rw;
-            xform_ray(S, e, r2);
-            if (e.volume >= 0) {
-                if (!vr.transparent) {
-                    // rt/volume.go:34-79
-                    double t1 = isect_boundary(S, e, r2, -RTX_INF_D, RTX_INF_D, tc);
-                    if (t1 == t1) {
-                        double t2 = isect_boundary(S, e, r2, t1 + 0.0001, RTX_INF_D, tc);
-                        if (t2 == t2) {
-                            if (t1 < tmin) t1 = tmin;
-                            if (t2 > T.best.t) t2 = T.best.t;
-                            if (t1 < t2) {
-                                if (t1 < 0) t1 = 0;
-                                double rayLength = sqrt(rw.dx * rw.dx + rw.dy * rw.dy + rw.dz * rw.dz);
-                                double inside = (t2 - t1) * rayLength;
-                                double2 uu = rtx_volume_uniform(vr, ei);
-                                double nid = S.volumes[e.volume].neg_inv_density;
-                                double hd = nid * log(uu.x);
-                                if (S.vol_draws > 1) hd = fmin(hd, nid * log(uu.y));  // leaf visited twice, see DevScene::vol_draws
-                                if (!(hd > inside)) T.offer(t1 + hd / rayLength, ei, e.rank, RTX_KIND_VOLUME, e.volume, 0, 0);
-                            }
-                        }
-                    }
-                }
-            } else if (e.kind == RTX_GEOM_MESH) {
-                STK(sp) = RTX_SENTINEL; sp++;
-                cur = ei; crank = e.rank; ro = r2;
-                make_rayf(ro, f);
-                node = e.a;
-                continue;
-            } else if (e.kind == RTX_GEOM_LIST) {
-                for (int k = 0; k < e.b; k++) {
-                    int2 it = S.list_items[e.a + k];
-                    T.test_prim(it.x, it.y, r2, ei, e.rank, k, k);
-                }
-            } else {
-                T.test_prim(e.kind, e.index, r2, ei, e.rank, 0, 0);
-            }
-        }
-        if (ANY_HIT && T.have) return T.best;
-        if (sp > 0) { sp--; node = STK(sp); }
-        else break;
-    }
-#undef STK
-    return T.best;
 }
 
 // Full hit record (rec.P, rec.Normal against the ray, FrontFace, material) of a finished query.

@@ -10,7 +10,7 @@
 //   k_accumulate  pixelColor.Add(...)                rt/bucket_renderer.go:271
 //   k_resolve     scale / gamma / clamp / RGBA8      rt/bucket_renderer.go:275-285
 #pragma once
-#include "rtx_device.cuh"
+#include "rtx_trace.cuh"
 
 // ---- Philox4x32-10 counter RNG: key = run seed, counter = (pixel, global sample, bounce, stream) ------------------
 __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
@@ -50,6 +50,7 @@ struct Ctl {  // device-resident control block of the wavefront loop
     int n_active, n_cont, n_gen, n_free, n_next, n_shadow, n_done;
     int n_mat[Q_COUNT];
     int done, pad;
+    int cur_extend, cur_connect;  // job cursors of the persistent trace kernels
     // statistics
     unsigned long long ext_rays, shadow_rays, nodes, tris, spheres, quads, planes, iterations;
 };
@@ -103,6 +104,7 @@ __global__ void k_iter_begin(Ctl* ctl) {
     ctl->n_gen = n_gen;
     ctl->n_active = n_cont + n_gen;
     ctl->n_next = 0; ctl->n_shadow = 0; ctl->n_done = 0;
+    ctl->cur_extend = 0; ctl->cur_connect = 0;
     for (int i = 0; i < Q_COUNT; i++) ctl->n_mat[i] = 0;
     ctl->done = (n_cont + n_gen == 0);
     ctl->iterations += (n_cont + n_gen != 0);
@@ -168,9 +170,8 @@ __global__ void __launch_bounds__(256) k_generate(Ctl* ctl, Pool pool, int* q_cu
     q_cur[ctl->n_cont + i] = slot;
 }
 
-__device__ __forceinline__ void flush_counters(Ctl* ctl, const TraceCounters& tc, bool shadow, bool valid) {
-    // block-level reduction would be cheaper; counters are a debug/measurement option
-    if (!valid) return;
+__device__ __forceinline__ void flush_counters(Ctl* ctl, const TraceCounters& tc) {
+    // one set of atomics per lane per launch of a persistent kernel; counters are a measurement option
     atomicAdd(&ctl->nodes, (unsigned long long)tc.nodes);
     atomicAdd(&ctl->tris, (unsigned long long)tc.tris);
     atomicAdd(&ctl->spheres, (unsigned long long)tc.spheres);
@@ -178,44 +179,64 @@ __device__ __forceinline__ void flush_counters(Ctl* ctl, const TraceCounters& tc
     atomicAdd(&ctl->planes, (unsigned long long)tc.planes);
 }
 
+__device__ __forceinline__ Hit best_to_hit(const Best& b) {
+    Hit h; h.t = b.t; h.entry = b.entry; h.kind = b.kind; h.prim = b.prim; h.item = b.item;
+    return h;
+}
+
 // ---- K2: extend — closest hit of every active path, then binning into material-sorted shading queues -------------
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_extend(Ctl* ctl, Pool pool, const int* q_cur, DevScene S, PassParams pp) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int n = ctl->n_active;
-    bool valid = i < n;
-    int q = -1, slot = -1;
-    if (valid) {
-        slot = q_cur[i];
-        double2 a = pool.ray_o[2 * slot], b = pool.ray_o[2 * slot + 1], c = pool.ray_d[2 * slot], d = pool.ray_d[2 * slot + 1];
-        RayD r; r.ox = a.x; r.oy = a.y; r.oz = b.x; r.tm = b.y; r.dx = c.x; r.dy = c.y; r.dz = d.x;
-        uint2 ps = pool.pix[slot];
-        int bounce = __float_as_int(pool.thr[slot].w) & 0xffff;
-        VolumeRng vr; vr.k0 = pp.seed_lo; vr.k1 = pp.seed_hi; vr.c0 = ps.x; vr.c1 = ps.y; vr.c2 = (uint32_t)bounce * 4u; vr.transparent = false;
-        TraceCounters tc = {0, 0, 0, 0, 0};
-        Hit h = trace_scene<false>(S, r, 0.001, RTX_INF_D, vr, COUNT ? &tc : nullptr);
-        if (COUNT) flush_counters(ctl, tc, false, true);
-        if (h.entry < 0) {
-            q = Q_MISS;
-        } else {
-            HitInfo hi;
-            finalize_hit(S, r, h, false, hi);
-            pool.hit_p[2 * slot] = make_double2(hi.P.x, hi.P.y);
-            pool.hit_p[2 * slot + 1] = make_double2(hi.P.z, h.t);
-            long long bits = (long long)(unsigned)hi.mat | (hi.front ? (1LL << 31) : 0);
-            pool.hit_n[2 * slot] = make_double2(hi.N.x, hi.N.y);
-            pool.hit_n[2 * slot + 1] = make_double2(hi.N.z, __longlong_as_double(bits));
-            int mt = S.mats[hi.mat].type;
-            q = mt == RTX_MAT_LAMBERTIAN ? Q_LAMBERTIAN : mt == RTX_MAT_METAL ? Q_METAL : mt == RTX_MAT_DIELECTRIC ? Q_DIELECTRIC
-                : mt == RTX_MAT_DIFFUSE_LIGHT ? Q_LIGHT : Q_ISOTROPIC;
+struct ExtendPolicy {
+    static constexpr bool ANY_HIT = false;
+    Ctl* ctl; Pool pool; const int* q_cur; const DevScene* S; uint32_t seed_lo, seed_hi;
+    __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:451
+    __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
+        const int slot = q_cur[job];
+        const double2 a = pool.ray_o[2 * slot], b = pool.ray_o[2 * slot + 1], c = pool.ray_d[2 * slot], d = pool.ray_d[2 * slot + 1];
+        r.ox = a.x; r.oy = a.y; r.oz = b.x; r.tm = b.y; r.dx = c.x; r.dy = c.y; r.dz = d.x;
+        tmax = RTX_INF_D;
+    }
+    __device__ __forceinline__ VolumeRng volume_rng(int job) const {
+        const int slot = q_cur[job];
+        const uint2 ps = pool.pix[slot];
+        const int bounce = __float_as_int(pool.thr[slot].w) & 0xffff;
+        VolumeRng vr; vr.k0 = seed_lo; vr.k1 = seed_hi; vr.c0 = ps.x; vr.c1 = ps.y; vr.c2 = (uint32_t)bounce * 4u; vr.transparent = false;
+        return vr;
+    }
+    __device__ __forceinline__ void retire(int job, bool valid, const RayD& r, const Best& b) const {
+        int q = -1, slot = -1;
+        if (valid) {
+            slot = q_cur[job];
+            if (b.entry < 0) {
+                q = Q_MISS;
+            } else {
+                HitInfo hi;
+                finalize_hit(*S, r, best_to_hit(b), false, hi);
+                pool.hit_p[2 * slot] = make_double2(hi.P.x, hi.P.y);
+                pool.hit_p[2 * slot + 1] = make_double2(hi.P.z, b.t);
+                const long long bits = (long long)(unsigned)hi.mat | (hi.front ? (1LL << 31) : 0);
+                pool.hit_n[2 * slot] = make_double2(hi.N.x, hi.N.y);
+                pool.hit_n[2 * slot + 1] = make_double2(hi.N.z, __longlong_as_double(bits));
+                const int mt = S->mats[hi.mat].type;
+                q = mt == RTX_MAT_LAMBERTIAN ? Q_LAMBERTIAN : mt == RTX_MAT_METAL ? Q_METAL : mt == RTX_MAT_DIELECTRIC ? Q_DIELECTRIC
+                    : mt == RTX_MAT_DIFFUSE_LIGHT ? Q_LIGHT : Q_ISOTROPIC;
+            }
+        }
+        // material-sorted queues: one warp-aggregated append per queue
+#pragma unroll
+        for (int k = 0; k < Q_COUNT; k++) {
+            const int pos = warp_append(&ctl->n_mat[k], q == k);
+            if (q == k) pool.q_mat[(size_t)k * pool.capacity + pos] = slot;
         }
     }
-    // material-sorted queues: one warp-aggregated append per queue
-#pragma unroll
-    for (int k = 0; k < Q_COUNT; k++) {
-        int pos = warp_append(&ctl->n_mat[k], q == k);
-        if (q == k) pool.q_mat[(size_t)k * pool.capacity + pos] = slot;
-    }
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_extend(Ctl* ctl, Pool pool, const int* q_cur, DevScene S, PassParams pp) {
+    ExtendPolicy P{ctl, pool, q_cur, &S, pp.seed_lo, pp.seed_hi};
+    TraceCounters tc = {0, 0, 0, 0, 0};
+    const int n = ctl->n_active;
+    trace_persistent<ExtendPolicy, COUNT>(S, P, &ctl->cur_extend, n, tc);
+    if (COUNT) flush_counters(ctl, tc);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->ext_rays, (unsigned long long)n);
 }
 
@@ -486,28 +507,45 @@ __global__ void __launch_bounds__(256) k_shade(Ctl* ctl, Pool pool, int* q_next,
 }
 
 // ---- K3: connect — shadow rays of next-event estimation (any hit in [0.001, tmax]) ----------------------------------
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_connect(Ctl* ctl, Pool pool, DevScene S, PassParams pp) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int n = ctl->n_shadow;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->shadow_rays, (unsigned long long)n);
-    if (i >= n) return;
-    float4 cc = pool.sh_c[i];
-    int slot = __float_as_int(cc.w);
-    double2 o0 = pool.ray_o[2 * slot], o1 = pool.ray_o[2 * slot + 1], d0 = pool.sh_d[2 * i], d1 = pool.sh_d[2 * i + 1];
-    RayD r; r.ox = o0.x; r.oy = o0.y; r.oz = o1.x; r.dx = d0.x; r.dy = d0.y; r.dz = d1.x; r.tm = 0;  // NewRay(hitPoint, lightDir, 0)
-    uint2 ps = pool.pix[slot];
-    int bounce = __float_as_int(pool.thr[slot].w) & 0xffff;
-    VolumeRng vr; vr.k0 = pp.seed_lo; vr.k1 = pp.seed_hi; vr.c0 = ps.x; vr.c1 = ps.y;
-    vr.c2 = (uint32_t)bounce * 4u + (d1.y == RTX_INF_D ? 2u : 1u); vr.transparent = false;
-    TraceCounters tc = {0, 0, 0, 0, 0};
-    Hit h = trace_scene<true>(S, r, 0.001, d1.y, vr, COUNT ? &tc : nullptr);
-    if (COUNT) flush_counters(ctl, tc, true, true);
-    if (h.entry < 0) {
-        atomicAdd(&pool.rad[slot].x, cc.x);
-        atomicAdd(&pool.rad[slot].y, cc.y);
-        atomicAdd(&pool.rad[slot].z, cc.z);
+struct ConnectPolicy {
+    static constexpr bool ANY_HIT = true;
+    Pool pool; uint32_t seed_lo, seed_hi;
+    __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:579, :636
+    __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
+        const int slot = __float_as_int(pool.sh_c[job].w);
+        const double2 o0 = pool.ray_o[2 * slot], o1 = pool.ray_o[2 * slot + 1], d0 = pool.sh_d[2 * job], d1 = pool.sh_d[2 * job + 1];
+        r.ox = o0.x; r.oy = o0.y; r.oz = o1.x; r.dx = d0.x; r.dy = d0.y; r.dz = d1.x; r.tm = 0;  // NewRay(hitPoint, lightDir, 0)
+        tmax = d1.y;
     }
+    __device__ __forceinline__ VolumeRng volume_rng(int job) const {
+        const int slot = __float_as_int(pool.sh_c[job].w);
+        const uint2 ps = pool.pix[slot];
+        // shade already advanced the bounce counter of the path: the shadow ray belongs to the bounce before it
+        const int bounce = (__float_as_int(pool.thr[slot].w) & 0xffff) - 1;
+        const double tmax = pool.sh_d[2 * job + 1].y;
+        VolumeRng vr; vr.k0 = seed_lo; vr.k1 = seed_hi; vr.c0 = ps.x; vr.c1 = ps.y;
+        vr.c2 = (uint32_t)bounce * 4u + (tmax == RTX_INF_D ? 2u : 1u); vr.transparent = false;
+        return vr;
+    }
+    __device__ __forceinline__ void retire(int job, bool valid, const RayD&, const Best& b) const {
+        if (valid && b.entry < 0) {
+            const float4 cc = pool.sh_c[job];
+            const int slot = __float_as_int(cc.w);
+            atomicAdd(&pool.rad[slot].x, cc.x);
+            atomicAdd(&pool.rad[slot].y, cc.y);
+            atomicAdd(&pool.rad[slot].z, cc.z);
+        }
+    }
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_connect(Ctl* ctl, Pool pool, DevScene S, PassParams pp) {
+    ConnectPolicy P{pool, pp.seed_lo, pp.seed_hi};
+    TraceCounters tc = {0, 0, 0, 0, 0};
+    const int n = ctl->n_shadow;
+    trace_persistent<ConnectPolicy, COUNT>(S, P, &ctl->cur_connect, n, tc);
+    if (COUNT) flush_counters(ctl, tc);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->shadow_rays, (unsigned long long)n);
 }
 
 // ---- K6a: accumulate finished paths into the per-pixel sums, recycle their slots --------------------------------------
@@ -552,24 +590,38 @@ __global__ void k_pool_init(Pool pool, Ctl* ctl) {
 }
 
 // ---- batch entry points for the parity tests ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_trace_closest(DevScene S, const double* rays, long long n, double tmin, double tmax, int* entry_id, int* prim_id,
-                                                       double* t, double* normal, unsigned char* front, double* uv, double* p) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double* q = rays + 7 * i;
-    RayD r; r.ox = q[0]; r.oy = q[1]; r.oz = q[2]; r.dx = q[3]; r.dy = q[4]; r.dz = q[5]; r.tm = q[6];
-    VolumeRng vr = {0, 0, 0, 0, 0, true};
-    Hit h = trace_scene<false>(S, r, tmin, tmax, vr, nullptr);
-    bool hit = h.entry >= 0;
-    HitInfo hi;
-    if (hit) finalize_hit(S, r, h, true, hi);
-    if (entry_id) entry_id[i] = hit ? h.entry : -1;
-    if (prim_id) prim_id[i] = hit ? h.item : -1;
-    if (t) t[i] = hit ? h.t : 0;
-    if (normal) { normal[3 * i] = hit ? hi.N.x : 0; normal[3 * i + 1] = hit ? hi.N.y : 0; normal[3 * i + 2] = hit ? hi.N.z : 0; }
-    if (front) front[i] = hit && hi.front;
-    if (uv) { uv[2 * i] = hit ? hi.u : 0; uv[2 * i + 1] = hit ? hi.v : 0; }
-    if (p) { p[3 * i] = hit ? hi.P.x : 0; p[3 * i + 1] = hit ? hi.P.y : 0; p[3 * i + 2] = hit ? hi.P.z : 0; }
+struct BatchPolicy {
+    static constexpr bool ANY_HIT = false;
+    const DevScene* S; const double* rays; double t0, t1;
+    int* entry_id; int* prim_id; double* t; double* normal; unsigned char* front; double* uv; double* p;
+    __device__ __forceinline__ double tmin() const { return t0; }
+    __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
+        const double* q = rays + 7 * (size_t)job;
+        r.ox = q[0]; r.oy = q[1]; r.oz = q[2]; r.dx = q[3]; r.dy = q[4]; r.dz = q[5]; r.tm = q[6];
+        tmax = t1;
+    }
+    __device__ __forceinline__ VolumeRng volume_rng(int) const { VolumeRng vr = {0, 0, 0, 0, 0, true}; return vr; }
+    __device__ __forceinline__ void retire(int job, bool valid, const RayD& r, const Best& b) const {
+        if (!valid) return;
+        const size_t i = (size_t)job;
+        const bool hit = b.entry >= 0;
+        HitInfo hi;
+        if (hit) finalize_hit(*S, r, best_to_hit(b), true, hi);
+        if (entry_id) entry_id[i] = hit ? b.entry : -1;
+        if (prim_id) prim_id[i] = hit ? b.item : -1;
+        if (t) t[i] = hit ? b.t : 0;
+        if (normal) { normal[3 * i] = hit ? hi.N.x : 0; normal[3 * i + 1] = hit ? hi.N.y : 0; normal[3 * i + 2] = hit ? hi.N.z : 0; }
+        if (front) front[i] = hit && hi.front;
+        if (uv) { uv[2 * i] = hit ? hi.u : 0; uv[2 * i + 1] = hit ? hi.v : 0; }
+        if (p) { p[3 * i] = hit ? hi.P.x : 0; p[3 * i + 1] = hit ? hi.P.y : 0; p[3 * i + 2] = hit ? hi.P.z : 0; }
+    }
+};
+
+__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_trace_closest(DevScene S, const double* rays, int n, double tmin, double tmax, int* cursor,
+        int* entry_id, int* prim_id, double* t, double* normal, unsigned char* front, double* uv, double* p) {
+    BatchPolicy P{&S, rays, tmin, tmax, entry_id, prim_id, t, normal, front, uv, p};
+    TraceCounters tc = {0, 0, 0, 0, 0};
+    trace_persistent<BatchPolicy, false>(S, P, cursor, n, tc);
 }
 
 __global__ void k_camera_rays(DevCamera C, const int* ij, const double* sq, const double* disk, const double* tm, long long n, double* out) {
