@@ -19,7 +19,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "csrc", "librtx_b200.so")
+LIB_PATH = os.environ.get("RTX_B200_LIB") or os.path.join(_HERE, "csrc", "librtx_b200.so")  # env override: A/B builds of the same library
 HOST_LIB_PATH = os.path.join(_HERE, "csrc", "librt_host.so")
 
 RTX_ABI_VERSION = 1

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -414,6 +415,26 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
         }
         entryBox[e] = xform_box(d, b, E.xf_begin, E.xf_count);
     }
+    // canonical [Translate][RotateY][Scale] chains (outermost first) get a one-load record, see xform_ray
+    std::vector<double> xfCanon((size_t)8 * std::max(d->n_entries, 1), 0.0);
+    for (int e = 0; e < d->n_entries; e++) {
+        double* q = xfCanon.data() + 8 * (size_t)e;
+        q[0] = q[1] = q[2] = 0; q[3] = 0; q[4] = 1; q[5] = q[6] = q[7] = 1;
+        int n = entries[e].xf_count, stage = 0;
+        bool canon = n > 0 && n <= 3;
+        for (int k = 0; k < n && canon; k++) {
+            int x = entries[e].xf_begin + k, t = d->xf_type[x];
+            int want = t == RTX_XF_TRANSLATE ? 0 : t == RTX_XF_ROTATE_Y ? 1 : 2;
+            if (want < stage) { canon = false; break; }
+            stage = want + 1;
+            if (t == RTX_XF_TRANSLATE) { q[0] = d->xf_a[3 * x]; q[1] = d->xf_a[3 * x + 1]; q[2] = d->xf_a[3 * x + 2]; }
+            else if (t == RTX_XF_ROTATE_Y) { q[3] = d->xf_a[3 * x]; q[4] = d->xf_a[3 * x + 1]; }
+            else if (d->xf_b) { q[5] = d->xf_b[3 * x]; q[6] = d->xf_b[3 * x + 1]; q[7] = d->xf_b[3 * x + 2]; }
+            else canon = false;
+        }
+        if (n > 0xffff) return fail(ctx, RTX_ERR_UNSUPPORTED, "entry %d: transform chain too long", e);
+        if (canon) entries[e].xf_count |= RTX_XF_CANON;
+    }
     {  // test-order ranks: the caller's Go tree, or the canonical stable median-split order
         std::vector<int> ranks;
         if (d->entry_rank) ranks.assign(d->entry_rank, d->entry_rank + d->n_entries);
@@ -523,7 +544,7 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     UP(tris, S.tris); UP(triNrm, S.tri_nrm); UP(triInfo, S.tri_info);
     UP(planes, S.planes); UP(planeMat, S.plane_mat);
     UP(listItems, S.list_items);
-    UP(xfs, S.xforms); UP(vols, S.volumes); UP(mats, S.mats); UP(texs, S.texs); UP(lights, S.light_quads);
+    UP(xfs, S.xforms); UP(xfCanon, S.xf_canon); UP(vols, S.volumes); UP(mats, S.mats); UP(texs, S.texs); UP(lights, S.light_quads);
     UP(envTex, S.env_tex); UP(marg, S.env_marg); UP(cond, S.env_cond); UP(pdf, S.env_pdf);
     S.tlas_root = tlasRoot;
     S.n_entries = d->n_entries;
@@ -746,6 +767,9 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
                     cudaEventElapsedTime(&ms, ctx->events[2 + (size_t)b * EV_KINDS * 2 + 2 * k], ctx->events[2 + (size_t)b * EV_KINDS * 2 + 2 * k + 1]);
                     msKind[k] += ms;
                 }
+        if (getenv("RTX_DEBUG_BATCH"))
+            fprintf(stderr, "[rtx] iter %lld: ms gen/ext/shade/conn/acc %.2f/%.2f/%.2f/%.2f/%.2f active %d next %d shadow %d cursor %llu\n", iter, msKind[0], msKind[1],
+                    msKind[2], msKind[3], msKind[4], ctx->ctl_host->n_active, ctx->ctl_host->n_next, ctx->ctl_host->n_shadow, ctx->ctl_host->cursor);
         if (ctx->ctl_host->done) break;
     }
     CU(cudaEventRecord(evStop, st));

@@ -18,7 +18,7 @@
 struct DEntry {      // 32 B, one per world entry (rt/hittable_list.go:16 insertion order)
     int kind;        // RTX_GEOM_*
     int index;       // primitive index (device arrays), or unused for groups
-    int xf_begin, xf_count;
+    int xf_begin, xf_count;  // xf_count bit 16 (RTX_XF_CANON): the chain is [Translate][RotateY][Scale] and S.xf_canon holds it
     int volume;      // -1 or index into volumes
     int rank;        // test-order rank inside the reference BVH (exact-tie resolution only)
     int a;           // LIST: first item   MESH: BLAS root node
@@ -59,6 +59,7 @@ struct DevScene {
     const int* plane_mat;
     const int2* list_items;  // (kind, device index)
     const DXform* xforms;
+    const double* xf_canon;  // 8 doubles per entry: offset xyz, sin, cos, inverse scale xyz (identity values where an op is absent)
     const DVolume* volumes;
     const DMaterial* mats;
     const DTexture* texs;
@@ -118,8 +119,11 @@ __device__ __forceinline__ D3 unit(D3 a) {  // rt/vec3.go:32-38
 __device__ __forceinline__ D3 ld3(const double* p) { return d3(p[0], p[1], p[2]); }
 
 // ---- instance transforms (rt/transform.go:93-102, :159-187, :408-440): ray into object space, outermost first --
-__device__ __forceinline__ void xform_ray(const DevScene& S, const DEntry& e, RayD& r) {
-    for (int k = 0; k < e.xf_count; k++) {
+#define RTX_XF_CANON 0x10000
+#define RTX_XF_COUNT(e) ((e).xf_count & 0xffff)
+__device__ __forceinline__ void xform_ray_chain(const DevScene& S, const DEntry& e, RayD& r) {
+    const int n = RTX_XF_COUNT(e);
+    for (int k = 0; k < n; k++) {
         const DXform& x = S.xforms[e.xf_begin + k];
         if (x.type == RTX_XF_TRANSLATE) {
             r.ox -= x.a[0]; r.oy -= x.a[1]; r.oz -= x.a[2];
@@ -134,9 +138,28 @@ __device__ __forceinline__ void xform_ray(const DevScene& S, const DEntry& e, Ra
         }
     }
 }
+// The wrappers the shipped scenes build (Transform.Apply, rt/transform.go:24-46; Translate(RotateY(box)), rt/scenes.go:520-538)
+// are always Translate outside RotateY outside Scale. For those, one 64-byte record replaces the op loop; absent ops hold
+// identity values, for which the float64 arithmetic below is exact (x - 0, 1 * x - 0 * z, x * 1), so the result is
+// bit-identical to applying only the ops that are present.
+__device__ __forceinline__ void xform_ray(const DevScene& S, int ei, const DEntry& e, RayD& r) {
+    if (e.xf_count == 0) return;
+    if (e.xf_count & RTX_XF_CANON) {
+        const double2* q = reinterpret_cast<const double2*>(S.xf_canon + 8 * (size_t)ei);
+        const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);  // (offx,offy) (offz,sin) (cos,invx) (invy,invz)
+        const double tx = r.ox - a.x, ty = r.oy - a.y, tz = r.oz - b.x;
+        const double sn = b.y, cs = c.x;
+        const double ox = cs * tx - sn * tz, oz = sn * tx + cs * tz;
+        const double dx = cs * r.dx - sn * r.dz, dz = sn * r.dx + cs * r.dz;
+        r.ox = ox * c.y; r.oy = ty * d.x; r.oz = oz * d.y;
+        r.dx = dx * c.y; r.dy = r.dy * d.x; r.dz = dz * d.y;
+        return;
+    }
+    xform_ray_chain(S, e, r);
+}
 // hit point and normal back to world space, innermost first
 __device__ __forceinline__ void xform_back(const DevScene& S, const DEntry& e, D3& P, D3& N) {
-    for (int k = e.xf_count - 1; k >= 0; k--) {
+    for (int k = RTX_XF_COUNT(e) - 1; k >= 0; k--) {
         const DXform& x = S.xforms[e.xf_begin + k];
         if (x.type == RTX_XF_TRANSLATE) {
             P.x += x.a[0]; P.y += x.a[1]; P.z += x.a[2];
@@ -218,37 +241,45 @@ __device__ __forceinline__ double isect_plane(const double* p, const RayD& r) {
 
 __device__ __forceinline__ bool kind_closed(int kind) { return kind == RTX_GEOM_QUAD || kind == RTX_GEOM_TRIANGLE || kind == RTX_KIND_VOLUME; }
 
-// Generic primitive t with the reference's interval convention against [tmin, tmax].
-__device__ __forceinline__ double isect_prim(const DevScene& S, int kind, int idx, const RayD& r, double tmin, double tmax, TraceCounters* tc) {
+// Generic primitive t with the reference's interval convention against [tmin, tmax]. Out of line (one copy of the
+// four float64 tests in each kernel keeps the trace loop inside the instruction cache); everything travels in registers.
+__device__ __noinline__ double isect_prim_ool(int kind, const double* p, double ox, double oy, double oz, double dx, double dy, double dz, double tm,
+                                              double tmin, double tmax) {
+    RayD r; r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz; r.tm = tm;
     double t;
-    if (kind == RTX_GEOM_SPHERE) {
-        if (tc) tc->spheres++;
-        return isect_sphere(S.spheres + 8 * (size_t)idx, r, tmin, tmax);
-    } else if (kind == RTX_GEOM_QUAD) {
-        if (tc) tc->quads++;
-        return isect_quad(S.quads + 16 * (size_t)idx, r, tmin, tmax, nullptr);
-    } else if (kind == RTX_GEOM_TRIANGLE) {
-        if (tc) tc->tris++;
-        t = isect_tri(S.tris + 10 * (size_t)idx, r, nullptr);
+    if (kind == RTX_GEOM_SPHERE) return isect_sphere(p, r, tmin, tmax);
+    if (kind == RTX_GEOM_QUAD) return isect_quad(p, r, tmin, tmax, nullptr);
+    if (kind == RTX_GEOM_TRIANGLE) {
+        t = isect_tri(p, r, nullptr);
         return (tmin <= t && t <= tmax) ? t : RTX_NAN_D;
-    } else {
-        if (tc) tc->planes++;
-        t = isect_plane(S.planes + 8 * (size_t)idx, r);
-        return (tmin < t && t < tmax) ? t : RTX_NAN_D;
     }
+    t = isect_plane(p, r);
+    return (tmin < t && t < tmax) ? t : RTX_NAN_D;
+}
+__device__ __forceinline__ double isect_prim(const DevScene& S, int kind, int idx, const RayD& r, double tmin, double tmax, TraceCounters* tc) {
+    const double* p;
+    if (kind == RTX_GEOM_SPHERE) { if (tc) tc->spheres++; p = S.spheres + 8 * (size_t)idx; }
+    else if (kind == RTX_GEOM_QUAD) { if (tc) tc->quads++; p = S.quads + 16 * (size_t)idx; }
+    else if (kind == RTX_GEOM_TRIANGLE) { if (tc) tc->tris++; p = S.tris + 10 * (size_t)idx; }
+    else { if (tc) tc->planes++; p = S.planes + 8 * (size_t)idx; }
+    return isect_prim_ool(kind, p, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tm, tmin, tmax);
 }
 
 // ---- float32 conservative ray ---------------------------------------------------------------------------------
 // Exact slab parameter: t = (p - o) / d with the float64 ray. Computed: fma(p, i~, c) with i~ = fl(1 / fl(d)) (relative
 // error <= 2^-23) and c = -fl(fl(o) * i~) -/+ E. Then |computed - t| <= 2^-21 |t| + 2^-22 |o / d|, so with
 // E = 2^-21 |o * i| and the 2^-21 relative slack applied to tnear / tfar in node_test, a box the float64 ray touches
-// is never culled. A zero direction component gives i = +-inf and NaN slab values, which fmaxf / fminf ignore (that axis
-// then never culls).
+// is never culled. |i| is clamped to 1e30 (a zero direction component would give inf and NaN slab values that never
+// cull: an axis-parallel ray would then walk every node its other axes reach). With the clamp, (p - o) * 1e30 keeps the
+// sign of the exact slab parameter and dwarfs every finite t, so such rays cull exactly like the reference's 1/0 = inf.
 #define RTX_BOX_EPS 4.76837158e-7f  /* 2^-21 */
 __device__ __forceinline__ void make_rayf(const RayD& r, RayF& f) {
     const float ox = __double2float_rn(r.ox), oy = __double2float_rn(r.oy), oz = __double2float_rn(r.oz);
     const float dx = __double2float_rn(r.dx), dy = __double2float_rn(r.dy), dz = __double2float_rn(r.dz);
     f.ix = 1.0f / dx; f.iy = 1.0f / dy; f.iz = 1.0f / dz;
+    if (!(fabsf(f.ix) <= 1e30f)) f.ix = copysignf(1e30f, dx);
+    if (!(fabsf(f.iy) <= 1e30f)) f.iy = copysignf(1e30f, dy);
+    if (!(fabsf(f.iz) <= 1e30f)) f.iz = copysignf(1e30f, dz);
     const float px = ox * f.ix, py = oy * f.iy, pz = oz * f.iz;
     const float ex = fmaf(fabsf(px), RTX_BOX_EPS, 1e-30f), ey = fmaf(fabsf(py), RTX_BOX_EPS, 1e-30f), ez = fmaf(fabsf(pz), RTX_BOX_EPS, 1e-30f);
     f.cnx = -px - ex; f.cfx = -px + ex;
@@ -304,7 +335,7 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const RayD& rw, 
         return;
     }
     RayD r = rw;
-    xform_ray(S, e, r);
+    xform_ray(S, h.entry, e, r);
     D3 o = d3(r.ox, r.oy, r.oz), d = d3(r.dx, r.dy, r.dz);
     D3 P = add(o, scale(d, h.t));  // r.At(t), rt/ray.go:21
     D3 n;
@@ -333,6 +364,6 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const RayD& rw, 
     }
     out.front = dot(d, n) < 0;  // SetFaceNormal with the object-space ray (rt/hittable.go:20-30); never recomputed afterwards
     if (!out.front) n = d3(-n.x, -n.y, -n.z);
-    xform_back(S, e, P, n);
+    if (e.xf_count) xform_back(S, e, P, n);
     out.P = P; out.N = n;
 }

@@ -24,7 +24,7 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c
     return make_uint4(c0, c1, c2, c3);
 }
 __device__ __forceinline__ double u01(uint32_t x) { return ((double)x + 0.5) * 2.3283064365386963e-10; }   // (0,1)
-__device__ __forceinline__ float u01f(uint32_t x) { return ((float)(x >> 8) + 0.5f) * 5.9604645e-8f; }      // (0,1), 24 bits
+__device__ __forceinline__ float u01f(uint32_t x) { return ((float)(x >> 9) + 0.5f) * 1.1920929e-7f; }      // [2^-24, 1 - 2^-24]: k + 0.5 is exact for k < 2^23
 
 __device__ double2 rtx_volume_uniform(const VolumeRng& vr, int entry) {
     uint4 r = philox4x32(vr.c0, vr.c1, vr.c2, 64u + (uint32_t)entry, vr.k0, vr.k1);

@@ -20,7 +20,10 @@
 #include "rtx_device.cuh"
 
 #define RTX_TRACE_THREADS 128
-#define RTX_TRACE_BLOCKS 4   /* resident blocks per SM the trace kernels are compiled for (register cap 65536 / (128 * 4) = 128) */
+#ifndef RTX_TRACE_BLOCKS
+#define RTX_TRACE_BLOCKS 4
+#endif
+/* resident blocks per SM the trace kernels are compiled for (register cap 65536 / (128 * 4) = 128) */
 #define RTX_ST_SENTINEL ((int)0x80000000)  /* stack marker: instance finished, back to the TLAS */
 #define RTX_ST_DONE ((int)0x80000001)
 #define RTX_ST_IDLE ((int)0x80000002)
@@ -105,11 +108,23 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
     RayF f;
     Best B;
     bool exhausted = false;
+    int round = 0;
     r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = r.tm = 0;
     f.ix = f.iy = f.iz = f.cnx = f.cny = f.cnz = f.cfx = f.cfy = f.cfz = 0; f.offx = f.offy = f.offz = 0;
     B.reset(0);
 
+#ifdef RTX_DEBUG_LONGRAY
+    int dbg_rounds = 0;
+#endif
     for (;;) {
+#ifdef RTX_DEBUG_LONGRAY
+        if (node != RTX_ST_IDLE && node != RTX_ST_DONE && ++dbg_rounds == 20000) {
+            double tm_; RayD w; P.load(job, w, tm_);
+            printf("[longray] job %d node %d sp %d cur %d world o=(%.17g %.17g %.17g) d=(%.17g %.17g %.17g) tm %.17g | cur o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g) best %.9g ft %g | f.i=(%g %g %g) cn=(%g %g %g) cf=(%g %g %g)\n",
+                   job, node, sp, cur, w.ox, w.oy, w.oz, w.dx, w.dy, w.dz, w.tm, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, B.t, B.ft, f.ix, f.iy, f.iz, f.cnx, f.cny, f.cnz, f.cfx, f.cfy, f.cfz);
+        }
+        if (node == RTX_ST_IDLE || node == RTX_ST_DONE) dbg_rounds = 0;
+#endif
         const bool leaf = node < 0 && node > RTX_ST_IDLE;
         const bool sN = node >= 0;
         const bool sT = leaf && cur >= 0;
@@ -117,7 +132,11 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
         const bool sR = node == RTX_ST_DONE || (node == RTX_ST_IDLE && !exhausted);
         const unsigned mN = __ballot_sync(FULL, sN), mT = __ballot_sync(FULL, sT), mE = __ballot_sync(FULL, sE), mR = __ballot_sync(FULL, sR);
         if ((mN | mT | mE | mR) == 0) break;
-        const int cN = __popc(mN), cT = __popc(mT), cE = __popc(mE), cR = __popc(mR);
+        // the phase with the most waiting lanes wins; equal counts are broken by a rotating priority, so that a lane
+        // can never be starved by a long-running neighbour that keeps re-entering a "higher" phase
+        round++;
+        const int cN = (__popc(mN) << 2) | (round & 3), cT = (__popc(mT) << 2) | ((round + 1) & 3), cE = (__popc(mE) << 2) | ((round + 2) & 3),
+                  cR = (__popc(mR) << 2) | ((round + 3) & 3);
 
         if (cN >= cT && cN >= cE && cN >= cR) {
             // ---- NODE: one 4-wide node per lane -------------------------------------------------------------------
@@ -162,7 +181,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                     const int ei = ~node;
                     const DEntry e = S.entries[ei];
                     RayD r2 = r;
-                    xform_ray(S, e, r2);
+                    xform_ray(S, ei, e, r2);
                     bool descend = false;
                     if (e.volume >= 0) {
                         const VolumeRng vr = P.volume_rng(job);
@@ -235,7 +254,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                         const int ei = S.unbounded[k];
                         const DEntry e = S.entries[ei];
                         RayD ro = r;
-                        xform_ray(S, e, ro);
+                        xform_ray(S, ei, e, ro);
                         B.test_prim(S, e.kind, e.index, ro, tmin, ei, e.rank, 0, 0, tcp);
                     }
                     if ((Policy::ANY_HIT && B.have) || S.tlas_root < 0) node = RTX_ST_DONE;

@@ -127,6 +127,29 @@ def _soup_scene(grt, rng, world_is_bvh=True, n_tri=3000, dup=True):
     return b.build()
 
 
+def test_level1_axis_parallel_rays_cull(grt, orc, ctx):
+    """Directions with one or two exactly-zero components (wall normal + an axis-aligned scatter direction: d = (0,0,-2))
+    must give the reference's hits AND must still be culled by the float32 box test on the degenerate axes: a ray whose
+    zero axes never cull walks a whole 280K-triangle instance (seconds per ray instead of microseconds)."""
+    import time
+    sc = grt.config_scene("cornell-lucy", width=64, spp=1, depth=4)
+    ctx.load(sc)
+    o = orc.OracleScene(sc.desc_ptr, sc.cam_ptr)
+    rng = np.random.default_rng(21)
+    n = 60000
+    org = np.stack([rng.random(n) * 555, rng.random(n) * 555, np.full(n, 555.0)], axis=1)
+    rays = np.concatenate([org, np.tile([0.0, 0.0, -2.0], (n, 1)), rng.random((n, 1))], axis=1)
+    rays[::3, 3:6] = [-0.0, 0.0, -2.0]
+    rays[1::3, 3:6] = [0.0, 0.3, -1.0]
+    rays[1::3, 0:3] = org[1::3] * [1, 0.2, 1]
+    t0 = time.time()
+    hg = ctx.trace_closest(rays)
+    dt = time.time() - t0
+    assert_level1(hg, o.trace_closest(rays), "axis-parallel")
+    assert (hg["entry"] >= 6).mean() > 0.1   # a fair share goes through the statues
+    assert dt < 5.0, f"{n} axis-parallel rays took {dt:.1f} s: degenerate axes are not culling"
+
+
 @pytest.mark.parametrize("world_is_bvh", [True, False])
 def test_level1_soup_instances_ties(grt, orc, ctx, world_is_bvh):
     rng = np.random.default_rng(3)

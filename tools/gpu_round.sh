@@ -1,5 +1,3 @@
 #!/bin/bash
-set -x
-mkdir -p gpurun_out
-timeout 600 python tools/gpu_check.py > gpurun_out/check.log 2>&1; tail -30 gpurun_out/check.log
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/pytest_gpu.log; cat gpurun_out/pytest_gpu.log
+for s in 16 64; do python tools/gpu_perf.py cornell-lucy $s 2>&1 | tail -1; done
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
