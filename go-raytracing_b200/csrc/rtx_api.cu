@@ -49,6 +49,8 @@ struct rtx_ctx {
     std::vector<cudaEvent_t> events;
     int num_sms = 0;
     int* batch_cursor = nullptr;  // job cursor of k_trace_closest
+    int* trace_spill = nullptr;   // global overflow columns of the trace kernels' shared-memory stacks
+    int trace_grid = 0;           // persistent grid: SMs x resident blocks
 };
 
 static int32_t fail(rtx_ctx* ctx, int32_t code, const char* fmt, ...) {
@@ -145,6 +147,28 @@ int32_t rtx_create(int32_t device_id, rtx_ctx** out) {
         rtx_destroy(ctx);
         return RTX_ERR_CUDA;
     }
+    {   // persistent trace kernels: opt in to the large dynamic shared-memory pool, size the grid to one resident wave
+        const int smem = (int)RTX_TRACE_SMEM_BYTES;
+        int occ = 0, minOcc = 1 << 30;
+        const void* kernels[5] = {(const void*)k_extend<false>, (const void*)k_extend<true>, (const void*)k_connect<false>, (const void*)k_connect<true>,
+                                  (const void*)k_trace_closest};
+        for (const void* k : kernels) {
+            if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
+                (e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, RTX_TRACE_THREADS, smem)) != cudaSuccess || occ < 1) {
+                fail(nullptr, RTX_ERR_CUDA, "rtx_create: trace kernel setup failed (%s, occupancy %d)", cudaGetErrorString(e), occ);
+                rtx_destroy(ctx);
+                return RTX_ERR_CUDA;
+            }
+            minOcc = std::min(minOcc, occ);
+        }
+        ctx->trace_grid = ctx->num_sms * minOcc;
+        size_t spillInts = (size_t)ctx->trace_grid * RTX_TRACE_K * RTX_TRACE_THREADS * (RTX_STACK_SIZE - RTX_SMEM_STACK);
+        if ((e = cudaMalloc((void**)&ctx->trace_spill, spillInts * sizeof(int))) != cudaSuccess) {
+            fail(nullptr, RTX_ERR_CUDA, "rtx_create: %s", cudaGetErrorString(e));
+            rtx_destroy(ctx);
+            return RTX_ERR_CUDA;
+        }
+    }
     *out = ctx;
     return RTX_OK;
 }
@@ -167,6 +191,7 @@ int32_t rtx_destroy(rtx_ctx* ctx) {
     if (ctx->accum_sq) cudaFree(ctx->accum_sq);
     if (ctx->ctl) cudaFree(ctx->ctl);
     if (ctx->batch_cursor) cudaFree(ctx->batch_cursor);
+    if (ctx->trace_spill) cudaFree(ctx->trace_spill);
     if (ctx->ctl_host) cudaFreeHost(ctx->ctl_host);
     for (auto ev : ctx->events) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -728,7 +753,7 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
     uint64_t launches = 1;
     CU(cudaEventRecord(evStart, st));
     // the trace kernels are persistent: one resident wave of warps pulls rays from a device-side cursor
-    const int gridBig = (P + 255) / 256, gridTrace = ctx->num_sms * RTX_TRACE_BLOCKS, gridShadow = gridTrace;
+    const int gridBig = (P + 255) / 256, gridTrace = ctx->trace_grid, gridShadow = gridTrace;
     long long iter = 0;
     int activeEstimate = P;  // shrinks the launch grids once the pool drains (from the last polled control block)
     for (;;) {
@@ -741,14 +766,14 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
             if (timing) cudaEventRecord(ev[0], st);
             k_generate<<<gridBig, 256, 0, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->C, pp);
             if (timing) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
-            if (ctx->count_stats & 1) k_extend<true><<<gridTrace, RTX_TRACE_THREADS, 0, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->S, pp);
-            else k_extend<false><<<gridTrace, RTX_TRACE_THREADS, 0, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->S, pp);
+            if (ctx->count_stats & 1) k_extend<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->S, pp, ctx->trace_spill);
+            else k_extend<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->S, pp, ctx->trace_spill);
             if (timing) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); }
             k_shade<<<gridBig, 256, 0, st>>>(ctx->ctl, ctx->pool, q_next, ctx->S, ctx->C, pp);
             if (timing) { cudaEventRecord(ev[5], st); cudaEventRecord(ev[6], st); }
             if (ctx->S.n_lights > 0) {
-                if (ctx->count_stats & 2) k_connect<true><<<gridShadow, RTX_TRACE_THREADS, 0, st>>>(ctx->ctl, ctx->pool, ctx->S, pp);
-                else k_connect<false><<<gridShadow, RTX_TRACE_THREADS, 0, st>>>(ctx->ctl, ctx->pool, ctx->S, pp);
+                if (ctx->count_stats & 2) k_connect<true><<<gridShadow, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, ctx->pool, ctx->S, pp, ctx->trace_spill);
+                else k_connect<false><<<gridShadow, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, ctx->pool, ctx->S, pp, ctx->trace_spill);
                 launches++;
             }
             if (timing) { cudaEventRecord(ev[7], st); cudaEventRecord(ev[8], st); }
@@ -852,8 +877,8 @@ int32_t rtx_trace_closest(rtx_ctx* ctx, const double* rays, int64_t n, double tm
     CU(sc.out(&dFront, (unsigned char*)front, n)); CU(sc.out(&dUV, uv, 2 * n)); CU(sc.out(&dP, p, 3 * n));
     if (n > (int64_t)1 << 30) return fail(ctx, RTX_ERR_INVALID, "rtx_trace_closest: at most 2^30 rays per call");
     CU(cudaMemsetAsync(ctx->batch_cursor, 0, sizeof(int), ctx->stream));
-    k_trace_closest<<<ctx->num_sms * RTX_TRACE_BLOCKS, RTX_TRACE_THREADS, 0, ctx->stream>>>(ctx->S, dRays, (int)n, tmin, tmax, ctx->batch_cursor, dEntry, dPrim, dT, dN,
-                                                                                            dFront, dUV, dP);
+    k_trace_closest<<<ctx->trace_grid, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, ctx->stream>>>(ctx->S, dRays, (int)n, tmin, tmax, ctx->batch_cursor, ctx->trace_spill,
+                                                                                               dEntry, dPrim, dT, dN, dFront, dUV, dP);
     CU(cudaGetLastError());
     BACK(dEntry, entry_id, n); BACK(dPrim, prim_id, n); BACK(dT, t, n); BACK(dN, normal, 3 * n); BACK(dFront, front, n); BACK(dUV, uv, 2 * n); BACK(dP, p, 3 * n);
     CU(cudaStreamSynchronize(ctx->stream));

@@ -20,10 +20,12 @@
 #include "rtx_device.cuh"
 
 #define RTX_TRACE_THREADS 128
-#ifndef RTX_TRACE_BLOCKS
-#define RTX_TRACE_BLOCKS 4
+#ifndef RTX_TRACE_K
+#define RTX_TRACE_K 2        /* ray slots per lane (shared-memory ray pool, see trace_persistent) */
 #endif
-/* resident blocks per SM the trace kernels are compiled for (register cap 65536 / (128 * 4) = 128) */
+#ifndef RTX_TRACE_BLOCKS
+#define RTX_TRACE_BLOCKS 4   /* resident blocks per SM the trace kernels are compiled for (caps registers at 65536 / (128 * blocks)) */
+#endif
 #define RTX_ST_SENTINEL ((int)0x80000000)  /* stack marker: instance finished, back to the TLAS */
 #define RTX_ST_DONE ((int)0x80000001)
 #define RTX_ST_IDLE ((int)0x80000002)
@@ -90,180 +92,305 @@ struct Best {
 //   void   load(int job, RayD& r, double& tmax) const;      world-space ray of job `job` (called again when an instance ends)
 //   VolumeRng volume_rng(int job) const;
 //   void   retire(int job, bool valid, const RayD& r, const Best& b);   warp-collective: every lane calls it, `valid` lanes own a finished query
-template <class Policy, bool COUNT>
-__device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, int* cursor, int njobs, TraceCounters& tc) {
-    __shared__ int s_stack[RTX_STACK_SIZE * RTX_TRACE_THREADS];
-    int* const stack = s_stack + threadIdx.x;
-#define STK(i) stack[(i) * RTX_TRACE_THREADS]
-#define POP() do { if (sp > 0) { sp--; node = STK(sp); } else node = RTX_ST_DONE; } while (0)
+//
+// Ray pool. Every lane owns K ray slots whose whole state lives in shared memory (slot = k * 128 + thread: each field
+// is an array over slots, so a warp touching "its" slots of one k is bank-conflict free). Registers only hold a ray while
+// one phase runs on it. With K > 1 a warp schedules 32 K rays onto 32 lanes: the phase that wins the vote finds a
+// ready ray in far more lanes than with one ray per lane. The first RTX_SMEM_STACK stack entries of a slot are in shared
+// memory, deeper ones spill to a global scratch column (rare: the stack seldom exceeds a dozen entries).
+#define RTX_SMEM_STACK 16
+#define RTX_PH_N 0
+#define RTX_PH_T 1
+#define RTX_PH_E 2
+#define RTX_PH_R 3
+#define RTX_PH_NONE 4   /* parked: idle slot after the job queue ran dry */
+#define RTX_SLOT_WORDS (9 + 1 + 1 + 4 + 14 + 2 + 6 + RTX_SMEM_STACK)   /* 32-bit words of shared memory per ray slot */
+
+template <int K>
+struct TracePool {
+    static constexpr int NS = K * RTX_TRACE_THREADS;
+    float* f;      // [9][NS]  ix iy iz cnx cny cnz cfx cfy cfz
+    int* off;      // [NS]     offx | offy << 8 | offz << 16
+    float* ft;     // [NS]
+    int *node, *sp, *cur, *job;
+    double* r;     // [7][NS]  current-space ray ox oy oz dx dy dz, and the ray time
+    double* bt;    // [NS]
+    int *be, *bk, *bp, *bi, *bre, *brp;  // best: entry, kind | have << 8, prim, item, rank_e, rank_p
+    int* stack;    // [RTX_SMEM_STACK][NS]
+    __device__ __forceinline__ explicit TracePool(unsigned char* base) {
+        double* d = reinterpret_cast<double*>(base);
+        r = d; d += 7 * NS;
+        bt = d; d += NS;
+        float* w = reinterpret_cast<float*>(d);
+        f = w; w += 9 * NS;
+        ft = w; w += NS;
+        int* q = reinterpret_cast<int*>(w);
+        off = q; q += NS; node = q; q += NS; sp = q; q += NS; cur = q; q += NS; job = q; q += NS;
+        be = q; q += NS; bk = q; q += NS; bp = q; q += NS; bi = q; q += NS; bre = q; q += NS; brp = q; q += NS;
+        stack = q;
+    }
+    __device__ __forceinline__ void load_rayf(int s, RayF& x) const {
+        x.ix = f[s]; x.iy = f[NS + s]; x.iz = f[2 * NS + s]; x.cnx = f[3 * NS + s]; x.cny = f[4 * NS + s]; x.cnz = f[5 * NS + s];
+        x.cfx = f[6 * NS + s]; x.cfy = f[7 * NS + s]; x.cfz = f[8 * NS + s];
+        const int o = off[s];
+        x.offx = o & 0xff; x.offy = (o >> 8) & 0xff; x.offz = (o >> 16) & 0xff;
+    }
+    __device__ __forceinline__ void store_rayf(int s, const RayF& x) const {
+        f[s] = x.ix; f[NS + s] = x.iy; f[2 * NS + s] = x.iz; f[3 * NS + s] = x.cnx; f[4 * NS + s] = x.cny; f[5 * NS + s] = x.cnz;
+        f[6 * NS + s] = x.cfx; f[7 * NS + s] = x.cfy; f[8 * NS + s] = x.cfz;
+        off[s] = x.offx | (x.offy << 8) | (x.offz << 16);
+    }
+    __device__ __forceinline__ void load_ray(int s, RayD& x) const {
+        x.ox = r[s]; x.oy = r[NS + s]; x.oz = r[2 * NS + s]; x.dx = r[3 * NS + s]; x.dy = r[4 * NS + s]; x.dz = r[5 * NS + s]; x.tm = r[6 * NS + s];
+    }
+    __device__ __forceinline__ void store_ray(int s, const RayD& x, bool with_time) const {
+        r[s] = x.ox; r[NS + s] = x.oy; r[2 * NS + s] = x.oz; r[3 * NS + s] = x.dx; r[4 * NS + s] = x.dy; r[5 * NS + s] = x.dz;
+        if (with_time) r[6 * NS + s] = x.tm;
+    }
+    __device__ __forceinline__ void load_best(int s, Best& b) const {
+        b.t = bt[s]; b.ft = ft[s]; b.entry = be[s];
+        const int kh = bk[s];
+        b.kind = (int)(signed char)(kh & 0xff); b.have = (kh >> 8) & 1;
+        b.prim = bp[s]; b.item = bi[s]; b.rank_e = bre[s]; b.rank_p = brp[s];
+    }
+    __device__ __forceinline__ void store_best(int s, const Best& b) const {
+        bt[s] = b.t; ft[s] = b.ft; be[s] = b.entry; bk[s] = (b.kind & 0xff) | (b.have ? 0x100 : 0);
+        bp[s] = b.prim; bi[s] = b.item; bre[s] = b.rank_e; brp[s] = b.rank_p;
+    }
+};
+
+template <class Policy, bool COUNT, int K>
+__device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, int* cursor, int njobs, TraceCounters& tc, int* spill, unsigned char* smem) {
+    typedef TracePool<K> Pool_;
+    constexpr int NS = Pool_::NS;
+    const Pool_ T(smem);
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const double tmin = P.tmin();
     const float ftmin = __double2float_rd(tmin);
     const float INF = __int_as_float(0x7f800000);
     TraceCounters* const tcp = COUNT ? &tc : nullptr;
+    const size_t spill_stride = (size_t)gridDim.x * NS;
+    int* const spill_col = spill + (size_t)blockIdx.x * NS;
 
-    int node = RTX_ST_IDLE, sp = 0, cur = -1, job = -1;
-    RayD r;
-    RayF f;
-    Best B;
+    // packed per-lane summary of my K slots: 4 bits each = phase (0..4) | in_instance << 3
+    unsigned stbits = 0;
+#pragma unroll
+    for (int k = 0; k < K; k++) stbits |= (unsigned)RTX_PH_R << (4 * k);
+    for (int k = 0; k < K; k++) T.node[k * RTX_TRACE_THREADS + threadIdx.x] = RTX_ST_IDLE;
     bool exhausted = false;
     int round = 0;
-    r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = r.tm = 0;
-    f.ix = f.iy = f.iz = f.cnx = f.cny = f.cnz = f.cfx = f.cfy = f.cfz = 0; f.offx = f.offy = f.offz = 0;
-    B.reset(0);
 
-#ifdef RTX_DEBUG_LONGRAY
-    int dbg_rounds = 0;
-#endif
+#define RTX_PUSH(v) do { if (sp < RTX_SMEM_STACK) T.stack[sp * NS + s] = (v); else spill_col[(size_t)(sp - RTX_SMEM_STACK) * spill_stride + s] = (v); sp++; } while (0)
+#define RTX_POP() do { if (sp > 0) { sp--; node = sp < RTX_SMEM_STACK ? T.stack[sp * NS + s] : spill_col[(size_t)(sp - RTX_SMEM_STACK) * spill_stride + s]; } \
+                       else node = RTX_ST_DONE; } while (0)
+#define RTX_CLASSIFY(nd, inst) ((nd) >= 0 ? RTX_PH_N : (nd) == RTX_ST_DONE ? RTX_PH_R : (nd) == RTX_ST_SENTINEL ? RTX_PH_E : (inst) ? RTX_PH_T : RTX_PH_E)
+
     for (;;) {
-#ifdef RTX_DEBUG_LONGRAY
-        if (node != RTX_ST_IDLE && node != RTX_ST_DONE && ++dbg_rounds == 20000) {
-            double tm_; RayD w; P.load(job, w, tm_);
-            printf("[longray] job %d node %d sp %d cur %d world o=(%.17g %.17g %.17g) d=(%.17g %.17g %.17g) tm %.17g | cur o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g) best %.9g ft %g | f.i=(%g %g %g) cn=(%g %g %g) cf=(%g %g %g)\n",
-                   job, node, sp, cur, w.ox, w.oy, w.oz, w.dx, w.dy, w.dz, w.tm, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, B.t, B.ft, f.ix, f.iy, f.iz, f.cnx, f.cny, f.cnz, f.cfx, f.cfy, f.cfz);
+        // ---- vote: one REDUX over packed per-phase lane counts ---------------------------------------------------------
+        unsigned present = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const unsigned ph = (stbits >> (4 * k)) & 7u;
+            present |= ph < 4u ? 1u << (ph * 8u) : 0u;   // parked slots do not vote
         }
-        if (node == RTX_ST_IDLE || node == RTX_ST_DONE) dbg_rounds = 0;
-#endif
-        const bool leaf = node < 0 && node > RTX_ST_IDLE;
-        const bool sN = node >= 0;
-        const bool sT = leaf && cur >= 0;
-        const bool sE = (leaf && cur < 0) || node == RTX_ST_SENTINEL;
-        const bool sR = node == RTX_ST_DONE || (node == RTX_ST_IDLE && !exhausted);
-        const unsigned mN = __ballot_sync(FULL, sN), mT = __ballot_sync(FULL, sT), mE = __ballot_sync(FULL, sE), mR = __ballot_sync(FULL, sR);
-        if ((mN | mT | mE | mR) == 0) break;
-        // the phase with the most waiting lanes wins; equal counts are broken by a rotating priority, so that a lane
-        // can never be starved by a long-running neighbour that keeps re-entering a "higher" phase
+        const unsigned c = __reduce_add_sync(FULL, present);
+        if (c == 0) break;
+        // the phase with the most ready lanes wins; equal counts are broken by a rotating priority, so that a ray can
+        // never be starved by a long-running neighbour that keeps re-entering a "higher" phase
         round++;
-        const int cN = (__popc(mN) << 2) | (round & 3), cT = (__popc(mT) << 2) | ((round + 1) & 3), cE = (__popc(mE) << 2) | ((round + 2) & 3),
-                  cR = (__popc(mR) << 2) | ((round + 3) & 3);
+        const int cN = ((c & 0xff) << 2) | (round & 3), cT = (((c >> 8) & 0xff) << 2) | ((round + 1) & 3),
+                  cE = (((c >> 16) & 0xff) << 2) | ((round + 2) & 3), cR = (((c >> 24) & 0xff) << 2) | ((round + 3) & 3);
+        const int phase = (cN >= cT && cN >= cE && cN >= cR) ? RTX_PH_N : (cT >= cE && cT >= cR) ? RTX_PH_T : (cE >= cR) ? RTX_PH_E : RTX_PH_R;
+        // my first slot waiting for this phase
+        int k = -1;
+#pragma unroll
+        for (int j = K - 1; j >= 0; j--) if ((int)((stbits >> (4 * j)) & 7u) == phase) k = j;
+        const bool mine = k >= 0;
+        const int s = (mine ? k : 0) * RTX_TRACE_THREADS + (int)threadIdx.x;
+        const bool inst = mine && ((stbits >> (4 * k + 3)) & 1u);
+        int newst = -1;  // phase | in_instance << 3 of slot k after this round
 
-        if (cN >= cT && cN >= cE && cN >= cR) {
-            // ---- NODE: one 4-wide node per lane -------------------------------------------------------------------
-            if (sN) {
-                float d[4]; int c[4];
+        if (phase == RTX_PH_N) {
+            // ---- NODE: one 4-wide node per lane -----------------------------------------------------------------------
+            if (mine) {
+                int node = T.node[s], sp = T.sp[s];
+                RayF f;
+                T.load_rayf(s, f);
+                float d[4]; int ch[4];
                 if (COUNT) tc.nodes++;
-                node_test(S.nodes, node, f, ftmin, B.ft, d, c);
-#define RTX_CSWAP(i, j) if (d[j] < d[i]) { float td = d[i]; d[i] = d[j]; d[j] = td; int tcx = c[i]; c[i] = c[j]; c[j] = tcx; }
+                node_test(S.nodes, node, f, ftmin, T.ft[s], d, ch);
+#define RTX_CSWAP(i, j) if (d[j] < d[i]) { float td = d[i]; d[i] = d[j]; d[j] = td; int tcx = ch[i]; ch[i] = ch[j]; ch[j] = tcx; }
                 RTX_CSWAP(0, 1) RTX_CSWAP(2, 3) RTX_CSWAP(0, 2) RTX_CSWAP(1, 3) RTX_CSWAP(1, 2)
 #undef RTX_CSWAP
-                if (d[3] < INF) { STK(sp) = c[3]; sp++; }
-                if (d[2] < INF) { STK(sp) = c[2]; sp++; }
-                if (d[1] < INF) { STK(sp) = c[1]; sp++; }
-                if (d[0] < INF) node = c[0];
-                else POP();
+                if (d[3] < INF) RTX_PUSH(ch[3]);
+                if (d[2] < INF) RTX_PUSH(ch[2]);
+                if (d[1] < INF) RTX_PUSH(ch[1]);
+                if (d[0] < INF) node = ch[0];
+                else RTX_POP();
+                T.node[s] = node; T.sp[s] = sp;
+                newst = RTX_CLASSIFY(node, inst) | (inst ? 8 : 0);
             }
-        } else if (cT >= cE && cT >= cR) {
-            // ---- TRI: one triangle of the pending BLAS leaf per lane ---------------------------------------------
-            if (sT) {
+        } else if (phase == RTX_PH_T) {
+            // ---- TRI: one triangle of the pending BLAS leaf per lane ------------------------------------------------
+            if (mine) {
+                int node = T.node[s];
                 const int code = ~node;
                 const int ti = code >> 3, rem = code & 7;
+                RayD r;
+                T.load_ray(s, r);
                 if (COUNT) tc.tris++;
                 const double t = isect_tri(S.tris + 10 * (size_t)ti, r, nullptr);
-                if (tmin <= t && t <= B.t) {
+                bool have = false;
+                if (tmin <= t && t <= T.bt[s]) {
                     const int4 info = __ldg(S.tri_info + ti);
+                    Best B;
+                    T.load_best(s, B);
+                    const int cur = T.cur[s];
                     B.offer(t, cur, S.entries[cur].rank, RTX_GEOM_TRIANGLE, ti, info.x, info.z);
+                    T.store_best(s, B);
+                    have = B.have;
                 }
-                if (Policy::ANY_HIT && B.have) node = RTX_ST_DONE;
-                else if (rem == 0) POP();
+                if (Policy::ANY_HIT && have) node = RTX_ST_DONE;
+                else if (rem == 0) { int sp = T.sp[s]; RTX_POP(); T.sp[s] = sp; }
                 else node = ~(((ti + 1) << 3) | (rem - 1));
+                T.node[s] = node;
+                newst = RTX_CLASSIFY(node, true) | 8;
             }
-        } else if (cE >= cR) {
-            // ---- ENTRY: a world entry (TLAS leaf), or the end of an instance -------------------------------------
-            if (sE) {
+        } else if (phase == RTX_PH_E) {
+            // ---- ENTRY: a world entry (TLAS leaf), or the end of an instance -----------------------------------------
+            if (mine) {
+                int node = T.node[s], sp = T.sp[s];
+                const int job = T.job[s];
+                bool in_inst = false;
                 if (node == RTX_ST_SENTINEL) {
+                    RayD r; RayF f;
                     double tmax_unused;
-                    cur = -1;
                     P.load(job, r, tmax_unused);
                     make_rayf(r, f);
-                    POP();
+                    T.store_ray(s, r, false); T.store_rayf(s, f);
+                    T.cur[s] = -1;
+                    RTX_POP();
                 } else {
                     const int ei = ~node;
                     const DEntry e = S.entries[ei];
-                    RayD r2 = r;
+                    RayD r, r2;
+                    T.load_ray(s, r);
+                    r2 = r;
                     xform_ray(S, ei, e, r2);
-                    bool descend = false;
-                    if (e.volume >= 0) {
-                        const VolumeRng vr = P.volume_rng(job);
-                        if (!vr.transparent) {
-                            // rt/volume.go:34-79
-                            double t1 = isect_boundary(S, e, r2, -RTX_INF_D, RTX_INF_D, tcp);
-                            if (t1 == t1) {
-                                double t2 = isect_boundary(S, e, r2, t1 + 0.0001, RTX_INF_D, tcp);
-                                if (t2 == t2) {
-                                    if (t1 < tmin) t1 = tmin;
-                                    if (t2 > B.t) t2 = B.t;
-                                    if (t1 < t2) {
-                                        if (t1 < 0) t1 = 0;
-                                        const double rayLength = sqrt(r.dx * r.dx + r.dy * r.dy + r.dz * r.dz);
-                                        const double inside = (t2 - t1) * rayLength;
-                                        const double2 uu = rtx_volume_uniform(vr, ei);
-                                        const double nid = S.volumes[e.volume].neg_inv_density;
-                                        double hd = nid * log(uu.x);
-                                        if (S.vol_draws > 1) hd = fmin(hd, nid * log(uu.y));  // leaf visited twice, see DevScene::vol_draws
-                                        if (!(hd > inside)) B.offer(t1 + hd / rayLength, ei, e.rank, RTX_KIND_VOLUME, e.volume, 0, 0);
+                    if (e.volume < 0 && e.kind == RTX_GEOM_MESH) {
+                        RayF f;
+                        RTX_PUSH(RTX_ST_SENTINEL);
+                        make_rayf(r2, f);
+                        T.store_ray(s, r2, false); T.store_rayf(s, f);
+                        T.cur[s] = ei;
+                        node = e.a;
+                        in_inst = true;
+                    } else {
+                        Best B;
+                        T.load_best(s, B);
+                        if (e.volume >= 0) {
+                            const VolumeRng vr = P.volume_rng(job);
+                            if (!vr.transparent) {
+                                // rt/volume.go:34-79
+                                double t1 = isect_boundary(S, e, r2, -RTX_INF_D, RTX_INF_D, tcp);
+                                if (t1 == t1) {
+                                    double t2 = isect_boundary(S, e, r2, t1 + 0.0001, RTX_INF_D, tcp);
+                                    if (t2 == t2) {
+                                        if (t1 < tmin) t1 = tmin;
+                                        if (t2 > B.t) t2 = B.t;
+                                        if (t1 < t2) {
+                                            if (t1 < 0) t1 = 0;
+                                            const double rayLength = sqrt(r.dx * r.dx + r.dy * r.dy + r.dz * r.dz);
+                                            const double inside = (t2 - t1) * rayLength;
+                                            const double2 uu = rtx_volume_uniform(vr, ei);
+                                            const double nid = S.volumes[e.volume].neg_inv_density;
+                                            double hd = nid * log(uu.x);
+                                            if (S.vol_draws > 1) hd = fmin(hd, nid * log(uu.y));  // leaf visited twice, see DevScene::vol_draws
+                                            if (!(hd > inside)) B.offer(t1 + hd / rayLength, ei, e.rank, RTX_KIND_VOLUME, e.volume, 0, 0);
+                                        }
                                     }
                                 }
                             }
+                        } else if (e.kind == RTX_GEOM_LIST) {
+                            for (int q = 0; q < e.b; q++) {
+                                const int2 it = S.list_items[e.a + q];
+                                B.test_prim(S, it.x, it.y, r2, tmin, ei, e.rank, q, q, tcp);
+                            }
+                        } else {
+                            B.test_prim(S, e.kind, e.index, r2, tmin, ei, e.rank, 0, 0, tcp);
                         }
-                    } else if (e.kind == RTX_GEOM_MESH) {
-                        STK(sp) = RTX_ST_SENTINEL; sp++;
-                        cur = ei; r = r2;
-                        make_rayf(r, f);
-                        node = e.a;
-                        descend = true;
-                    } else if (e.kind == RTX_GEOM_LIST) {
-                        for (int k = 0; k < e.b; k++) {
-                            const int2 it = S.list_items[e.a + k];
-                            B.test_prim(S, it.x, it.y, r2, tmin, ei, e.rank, k, k, tcp);
-                        }
-                    } else {
-                        B.test_prim(S, e.kind, e.index, r2, tmin, ei, e.rank, 0, 0, tcp);
-                    }
-                    if (!descend) {
+                        T.store_best(s, B);
                         if (Policy::ANY_HIT && B.have) node = RTX_ST_DONE;
-                        else POP();
+                        else RTX_POP();
                     }
                 }
+                T.node[s] = node; T.sp[s] = sp;
+                newst = RTX_CLASSIFY(node, in_inst) | (in_inst ? 8 : 0);
             }
         } else {
-            // ---- RETIRE + REFILL (warp-collective) ----------------------------------------------------------------
-            const bool fin = node == RTX_ST_DONE;
+            // ---- RETIRE + REFILL (warp-collective; one slot per lane per round) ---------------------------------------
+            const bool fin = mine && T.node[s] == RTX_ST_DONE;
             {
-                RayD rw = r;
-                double tmax_unused;
-                if (fin && cur >= 0) P.load(job, rw, tmax_unused);  // an any-hit query may end inside an instance
+                RayD rw;
+                Best B;
+                int job = -1;
+                B.reset(0);
+                rw.ox = rw.oy = rw.oz = rw.dx = rw.dy = rw.dz = rw.tm = 0;
+                if (fin) {
+                    job = T.job[s];
+                    T.load_best(s, B);
+                    double tmax_unused;
+                    if (T.cur[s] >= 0) P.load(job, rw, tmax_unused);  // an any-hit query may end inside an instance
+                    else T.load_ray(s, rw);
+                }
                 P.retire(job, fin, rw, B);
             }
-            if (fin) node = RTX_ST_IDLE;
+            if (mine) {
+                T.node[s] = RTX_ST_IDLE;
+                newst = RTX_PH_NONE;
+            }
             if (!exhausted) {
-                const unsigned want = __ballot_sync(FULL, node == RTX_ST_IDLE);
+                const unsigned want = __ballot_sync(FULL, mine);
                 const int cnt = __popc(want);
                 int base = 0;
                 if (lane == 0) base = atomicAdd(cursor, cnt);
                 base = __shfl_sync(FULL, base, 0);
                 const int my = base + __popc(want & ((1u << lane) - 1u));
-                if (node == RTX_ST_IDLE && my < njobs) {
+                if (mine && my < njobs) {
+                    RayD r; RayF f; Best B;
                     double tmax;
-                    job = my;
-                    P.load(job, r, tmax);
+                    P.load(my, r, tmax);
                     B.reset(tmax);
-                    cur = -1; sp = 0;
                     // entries with unbounded geometry (infinite Plane, rt/plane.go:17) are tested for every ray
-                    for (int k = 0; k < S.n_unbounded; k++) {
-                        const int ei = S.unbounded[k];
+                    for (int q = 0; q < S.n_unbounded; q++) {
+                        const int ei = S.unbounded[q];
                         const DEntry e = S.entries[ei];
                         RayD ro = r;
                         xform_ray(S, ei, e, ro);
                         B.test_prim(S, e.kind, e.index, ro, tmin, ei, e.rank, 0, 0, tcp);
                     }
+                    int node;
                     if ((Policy::ANY_HIT && B.have) || S.tlas_root < 0) node = RTX_ST_DONE;
-                    else { node = S.tlas_root; make_rayf(r, f); }
+                    else { node = S.tlas_root; make_rayf(r, f); T.store_rayf(s, f); }
+                    T.store_ray(s, r, true); T.store_best(s, B);
+                    T.node[s] = node; T.sp[s] = 0; T.cur[s] = -1; T.job[s] = my;
+                    newst = RTX_CLASSIFY(node, false);
                 }
                 if (base + cnt >= njobs) exhausted = true;
             }
+            // once the queue is dry, idle slots leave the vote; until then they keep asking for a refill
+            if (mine && newst == RTX_PH_NONE && !exhausted) newst = RTX_PH_R;
+            if (exhausted) {
+#pragma unroll
+                for (int j = 0; j < K; j++)
+                    if (j != k && (int)((stbits >> (4 * j)) & 7u) == RTX_PH_R && T.node[j * RTX_TRACE_THREADS + threadIdx.x] == RTX_ST_IDLE)
+                        stbits = (stbits & ~(0xfu << (4 * j))) | ((unsigned)RTX_PH_NONE << (4 * j));
+            }
         }
+        if (newst >= 0) stbits = (stbits & ~(0xfu << (4 * k))) | ((unsigned)newst << (4 * k));
     }
-#undef POP
-#undef STK
+#undef RTX_PUSH
+#undef RTX_POP
+#undef RTX_CLASSIFY
 }
