@@ -234,7 +234,7 @@ struct ExtendPolicy {
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_extend(Ctl* ctl, Pool pool, const int* q_cur, DevScene S, PassParams pp, int* spill) {
+__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_extend(Ctl* ctl, Pool pool, const int* q_cur, const __grid_constant__ DevScene S, PassParams pp, int* spill) {
     ExtendPolicy P{ctl, pool, q_cur, &S, pp.seed_lo, pp.seed_hi};
     TraceCounters tc = {0, 0, 0, 0, 0};
     const int n = ctl->n_active;
@@ -542,7 +542,7 @@ struct ConnectPolicy {
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_connect(Ctl* ctl, Pool pool, DevScene S, PassParams pp, int* spill) {
+__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_connect(Ctl* ctl, Pool pool, const __grid_constant__ DevScene S, PassParams pp, int* spill) {
     ConnectPolicy P{pool, pp.seed_lo, pp.seed_hi};
     TraceCounters tc = {0, 0, 0, 0, 0};
     const int n = ctl->n_shadow;
@@ -620,7 +620,7 @@ struct BatchPolicy {
     }
 };
 
-__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_trace_closest(DevScene S, const double* rays, int n, double tmin, double tmax, int* cursor, int* spill,
+__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_trace_closest(const __grid_constant__ DevScene S, const double* rays, int n, double tmin, double tmax, int* cursor, int* spill,
         int* entry_id, int* prim_id, double* t, double* normal, unsigned char* front, double* uv, double* p) {
     BatchPolicy P{&S, rays, tmin, tmax, entry_id, prim_id, t, normal, front, uv, p};
     TraceCounters tc = {0, 0, 0, 0, 0};
