@@ -261,7 +261,15 @@ def main():
             peak = 6650.0
         achieved = bytes_ray * my_ext_rays / max(my_ms_extend, 1e-9) / 1e6  # GB/s
         n_launch = sum(s["wavefront_iterations"] for s in stats if "wavefront_iterations" in s)
-        roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        traffic = None   # dram bytes of one k_extend launch from the committed ncu --set full capture, scaled to this run's average launch
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k_extend_traffic.json")))
+            traffic = tj["dram_bytes_per_ray"] * my_ext_rays / max(n_launch_pre := sum(s["wavefront_iterations"] for s in stats if "wavefront_iterations" in s), 1)
+        except Exception:
+            traffic = None
+        roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_note": "per launch, bytes; ncu dram__bytes_read+write per ray (profiles/r01_k_extend_traffic.json) x rays per launch of this run",
+                    "algorithmic_bytes_per_launch": bytes_ray * my_ext_rays / max(sum(s["wavefront_iterations"] for s in stats if "wavefront_iterations" in s), 1),
                     "peak_source": which, "bytes_per_ray": bytes_ray, "per_ray": per_ray, "launches": n_launch,
                     "avg_launch_ms": my_ms_extend / max(n_launch, 1), "kernel_share_of_step": my_ms_extend / max(sum(s["ms_total"] for s in stats), 1e-9),
                     "note": "algorithmic bytes = wide-BVH nodes + primitives fetched per extension ray (instrumented pass) + per-ray wavefront state; "

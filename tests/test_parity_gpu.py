@@ -275,8 +275,11 @@ def check_statistical(ctx, o, spp_g, spp_o, depth, cam_depth=None, seed=5, frac_
     assert frac < frac_limit, f"fraction of |z|>3 = {frac:.4f} (Gaussian 0.0027)"
     assert abs(np.mean(z)) < 0.05, f"mean z = {np.mean(z):.4f}: coherent bias"
     # image-level: global mean and 8x8 block means
+    # (the global mean of a heavy-tailed image is itself noisy: its standard error comes from the per-pixel ones; a fixed
+    # 2 % band alone fails about one Cornell render in eight at 128 spp with identical estimators)
     gm, om = mg.mean(axis=(0, 1)), mo.mean(axis=(0, 1))
-    assert np.all(np.abs(gm - om) <= rel_mean * np.maximum(om, 1e-3)), (gm, om)
+    gse = np.sqrt((se ** 2).sum(axis=(0, 1))) / (mg.shape[0] * mg.shape[1])
+    assert np.all(np.abs(gm - om) <= 4.0 * gse + 0.25 * rel_mean * np.maximum(om, 1e-3)), (gm, om, gse)
     H, W, _ = mg.shape
     bh, bw = H // 8 * 8, W // 8 * 8
     blk = lambda a: a[:bh, :bw].reshape(bh // 8, 8, bw // 8, 8, 3).mean(axis=(1, 3))
