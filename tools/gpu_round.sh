@@ -1,5 +1,3 @@
 #!/bin/bash
-mkdir -p gpurun_out
-nvidia-smi -L
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -5 gpurun_out/bench_n2.err; cat gpurun_out/bench_n2.json
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 1 --cpu-spp 1 | tail -1 | cut -c1-300
+for p in 1048576 4194304 8388608; do RTX_OPTS=pool_paths=$p timeout 300 python tools/gpu_perf.py cornell-lucy 64 2>&1 | tail -1; done
+timeout 300 python tools/gpu_check.py cornell 2>&1 | grep -E "trace|render|radiance"
