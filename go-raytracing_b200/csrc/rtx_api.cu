@@ -51,6 +51,10 @@ struct rtx_ctx {
     int* batch_cursor = nullptr;  // job cursor of k_trace_closest
     int* trace_spill = nullptr;   // global overflow columns of the trace kernels' shared-memory stacks
     int trace_grid = 0;           // persistent grid: SMs x resident blocks
+    void* geom_arena = nullptr;   // nodes + triangles + spheres + quads in one allocation: the L2 persisting window
+    size_t geom_bytes = 0;
+    int l2_persist = 0;  // measured on cornell-lucy: 1061 -> 1073 Mrays/s only, so off by default (it changes a process-wide device limit)
+    cudaStream_t window_stream = nullptr; bool window_set = false;
 };
 
 static int32_t fail(rtx_ctx* ctx, int32_t code, const char* fmt, ...) {
@@ -208,6 +212,7 @@ int32_t rtx_set_option(rtx_ctx* ctx, const char* key, int64_t value) {
         ctx->pool_paths = value;
     } else if (k == "count_stats") ctx->count_stats = (int)value;  // bit 0: extend kernel, bit 1: connect kernel
     else if (k == "time_kernels") ctx->time_kernels = value != 0;
+    else if (k == "l2_persist") { ctx->l2_persist = value != 0; ctx->window_set = false; }  // L2 persisting window over the scene geometry (default off)
     else if (k == "blas_leaf") {  // triangles per BLAS leaf (1..8); takes effect at the next rtx_scene_upload
         if (value < 1 || value > 8) return fail(ctx, RTX_ERR_INVALID, "blas_leaf must be in 1..8");
         ctx->blas_leaf = (int)value;
@@ -559,14 +564,33 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     // ---- upload
     std::vector<float4> nodeData(nodes.size() * 8);
     if (!nodes.empty()) std::memcpy(nodeData.data(), nodes.data(), nodes.size() * sizeof(Node4));
-    {   // 128-byte alignment of the node array: cudaMalloc returns >= 256-byte aligned memory
-        UP(nodeData, S.nodes);
+    {   // The geometry every ray fetches (nodes, triangles, spheres, quads) goes into ONE allocation so that a single L2
+        // access-policy window can keep it resident against the path pool streaming through the same cache (see render).
+        auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t bNodes = pad(nodeData.size() * sizeof(float4)), bTris = pad(tris.size() * sizeof(double)), bSph = pad(sph.size() * sizeof(double)),
+                     bQuads = pad(quads.size() * sizeof(double));
+        const size_t total = std::max<size_t>(bNodes + bTris + bSph + bQuads, 256);
+        char* base = nullptr;
+        CU(cudaMalloc((void**)&base, total));
+        ctx->scene_allocs.push_back(base);
+        ctx->geom_arena = base; ctx->geom_bytes = total; ctx->window_set = false;
+        auto put = [&](const void* src, size_t bytes, size_t off) {
+            return bytes ? cudaMemcpyAsync(base + off, src, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
+        };
+        CU(put(nodeData.data(), nodeData.size() * sizeof(float4), 0));
+        CU(put(tris.data(), tris.size() * sizeof(double), bNodes));
+        CU(put(sph.data(), sph.size() * sizeof(double), bNodes + bTris));
+        CU(put(quads.data(), quads.size() * sizeof(double), bNodes + bTris + bSph));
+        S.nodes = (const float4*)base;
+        S.tris = (const double*)(base + bNodes);
+        S.spheres = (const double*)(base + bNodes + bTris);
+        S.quads = (const double*)(base + bNodes + bTris + bSph);
     }
     UP(entries, S.entries);
     UP(unbounded, S.unbounded);
-    UP(sph, S.spheres); UP(sphMat, S.sph_mat);
-    UP(quads, S.quads); UP(quadMat, S.quad_mat);
-    UP(tris, S.tris); UP(triNrm, S.tri_nrm); UP(triInfo, S.tri_info);
+    UP(sphMat, S.sph_mat);
+    UP(quadMat, S.quad_mat);
+    UP(triNrm, S.tri_nrm); UP(triInfo, S.tri_info);
     UP(planes, S.planes); UP(planeMat, S.plane_mat);
     UP(listItems, S.list_items);
     UP(xfs, S.xforms); UP(xfCanon, S.xf_canon); UP(vols, S.volumes); UP(mats, S.mats); UP(texs, S.texs); UP(lights, S.light_quads);
@@ -726,6 +750,24 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
     int32_t rc = ensure_pool(ctx);
     if (rc != RTX_OK) return rc;
     cudaStream_t st = ctx->stream;
+    if (ctx->l2_persist && (!ctx->window_set || ctx->window_stream != st) && ctx->geom_bytes > 0) {
+        // Keep the scene geometry resident in L2: a persisting access-policy window over the geometry arena on the render
+        // stream. Without it the path pool (hundreds of MB per bounce) evicts nodes and triangles (ncu: lts hit rate 68 %).
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+            size_t want = std::min<size_t>(ctx->geom_bytes, (size_t)prop.persistingL2CacheMaxSize);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            cudaStreamAttrValue attr{};
+            attr.accessPolicyWindow.base_ptr = ctx->geom_arena;
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>(ctx->geom_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+        }
+        cudaGetLastError();  // the window is an optimisation: never fail the pass over it
+        ctx->window_set = true; ctx->window_stream = st;
+    }
     const int P = ctx->pool.capacity;
     PassParams pp{};
     pp.spp = spp; pp.max_depth = max_depth; pp.camera_max_depth = camera_max_depth;
