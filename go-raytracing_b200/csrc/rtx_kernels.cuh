@@ -185,7 +185,7 @@ __device__ __forceinline__ Hit best_to_hit(const Best& b) {
 }
 
 extern __shared__ __align__(16) unsigned char rtx_smem[];  // the trace kernels' ray pool (TracePool)
-#define RTX_TRACE_SMEM_BYTES ((size_t)RTX_TRACE_K * RTX_TRACE_THREADS * RTX_SLOT_WORDS * 4)
+#define RTX_TRACE_SMEM_BYTES ((size_t)RTX_TRACE_K * RTX_TRACE_THREADS * RTX_SLOT_WORDS * 4 + RTX_POOL_EXTRA_BYTES)
 
 // ---- K2: extend — closest hit of every active path, then binning into material-sorted shading queues -------------
 struct ExtendPolicy {

@@ -99,12 +99,17 @@ struct Best {
 // ready ray in far more lanes than with one ray per lane. The first RTX_SMEM_STACK stack entries of a slot are in shared
 // memory, deeper ones spill to a global scratch column (rare: the stack seldom exceeds a dozen entries).
 #define RTX_SMEM_STACK 16
+#ifndef RTX_N_STEPS
+#define RTX_N_STEPS 1
+#endif
 #define RTX_PH_N 0
 #define RTX_PH_T 1
 #define RTX_PH_E 2
 #define RTX_PH_R 3
 #define RTX_PH_NONE 4   /* parked: idle slot after the job queue ran dry */
 #define RTX_SLOT_WORDS (9 + 1 + 1 + 4 + 14 + 2 + 6 + RTX_SMEM_STACK)   /* 32-bit words of shared memory per ray slot */
+#define RTX_POOL_EXTRA_BYTES 256                                        /* column states + flags */
+#define RTX_PH_BUSY 5   /* claimed by a warp for the current round */
 
 template <int K>
 struct TracePool {
@@ -117,6 +122,8 @@ struct TracePool {
     double* bt;    // [NS]
     int *be, *bk, *bp, *bi, *bre, *brp;  // best: entry, kind | have << 8, prim, item, rank_e, rank_p
     int* stack;    // [RTX_SMEM_STACK][NS]
+    unsigned* col; // [32]  packed phase nibbles of the NS/32 slots of each bank column (block-shared scheduling state)
+    int* flags;    // [32]  flags[0]: job queue ran dry
     __device__ __forceinline__ explicit TracePool(unsigned char* base) {
         double* d = reinterpret_cast<double*>(base);
         r = d; d += 7 * NS;
@@ -127,7 +134,9 @@ struct TracePool {
         int* q = reinterpret_cast<int*>(w);
         off = q; q += NS; node = q; q += NS; sp = q; q += NS; cur = q; q += NS; job = q; q += NS;
         be = q; q += NS; bk = q; q += NS; bp = q; q += NS; bi = q; q += NS; bre = q; q += NS; brp = q; q += NS;
-        stack = q;
+        stack = q; q += RTX_SMEM_STACK * NS;
+        col = reinterpret_cast<unsigned*>(q); q += 32;
+        flags = q;
     }
     __device__ __forceinline__ void load_rayf(int s, RayF& x) const {
         x.ix = f[s]; x.iy = f[NS + s]; x.iz = f[2 * NS + s]; x.cnx = f[3 * NS + s]; x.cny = f[4 * NS + s]; x.cnz = f[5 * NS + s];
@@ -229,73 +238,107 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
     const size_t spill_stride = (size_t)gridDim.x * NS;
     int* const spill_col = spill + (size_t)blockIdx.x * NS;
 
-    // packed per-lane summary of my K slots: 4 bits each = phase (0..4) | in_instance << 3
-    unsigned stbits = 0;
-#pragma unroll
-    for (int k = 0; k < K; k++) stbits |= (unsigned)RTX_PH_R << (4 * k);
+    // Block-shared scheduling. A slot's phase is a nibble of its bank column's state word (column = slot % 32, NS / 32
+    // slots per column). Lane l of ANY warp of the block may run a phase on any slot of column l — shared-memory accesses stay
+    // conflict-free — and claims it with a compare-and-swap (phase -> BUSY). So each lane chooses among 4K candidates
+    // instead of its own K, and the four warps of a block usually run different phases at the same time.
+    constexpr int NCOL = NS / 32;
+    static_assert(NCOL <= 8, "one 32-bit state word per column holds at most 8 slots");
+    constexpr unsigned ALL_PARKED = 0x44444444u;
+    const unsigned warp = threadIdx.x >> 5;
+    volatile unsigned* const colstate = T.col;
+    volatile int* const dry = T.flags;
+    if (threadIdx.x < 32) {
+        unsigned w0 = ALL_PARKED;
+        for (int j = 0; j < NCOL; j++) w0 = (w0 & ~(0xfu << (4 * j))) | ((unsigned)RTX_PH_R << (4 * j));
+        T.col[threadIdx.x] = w0;
+        T.flags[threadIdx.x] = 0;
+    }
     for (int k = 0; k < K; k++) T.node[k * RTX_TRACE_THREADS + threadIdx.x] = RTX_ST_IDLE;
-    bool exhausted = false;
-    int round = 0;
+    __syncthreads();
+    unsigned round = warp;
 
 #define RTX_PUSH(v) do { if (sp < RTX_SMEM_STACK) T.stack[sp * NS + s] = (v); else spill_col[(size_t)(sp - RTX_SMEM_STACK) * spill_stride + s] = (v); sp++; } while (0)
 #define RTX_POP() do { if (sp > 0) { sp--; node = sp < RTX_SMEM_STACK ? T.stack[sp * NS + s] : spill_col[(size_t)(sp - RTX_SMEM_STACK) * spill_stride + s]; } \
                        else node = RTX_ST_DONE; } while (0)
 #define RTX_CLASSIFY(nd, inst) ((nd) >= 0 ? RTX_PH_N : (nd) == RTX_ST_DONE ? RTX_PH_R : (nd) == RTX_ST_SENTINEL ? RTX_PH_E : (inst) ? RTX_PH_T : RTX_PH_E)
 
+#define RTX_HASZERO_NIB(x) ((((x) - 0x11111111u) & ~(x)) & 0x88888888u)   /* lowest set bit marks the lowest zero nibble exactly */
     for (;;) {
-        // ---- vote: one REDUX over packed per-phase lane counts ---------------------------------------------------------
+        // ---- vote: one REDUX over packed per-phase counts of lanes whose column holds a ready slot ------------------------
+        unsigned w = colstate[lane];
         unsigned present = 0;
 #pragma unroll
-        for (int k = 0; k < K; k++) {
-            const unsigned ph = (stbits >> (4 * k)) & 7u;
-            present |= ph < 4u ? 1u << (ph * 8u) : 0u;   // parked slots do not vote
-        }
+        for (unsigned X = 0; X < 4; X++) present |= RTX_HASZERO_NIB(w ^ (X * 0x11111111u)) ? (1u << (8 * X)) : 0u;
         const unsigned c = __reduce_add_sync(FULL, present);
-        if (c == 0) break;
-        // the phase with the most ready lanes wins; equal counts are broken by a rotating priority, so that a ray can
-        // never be starved by a long-running neighbour that keeps re-entering a "higher" phase
+        if (c == 0) {
+            if (__all_sync(FULL, w == ALL_PARKED)) break;   // every slot of the block is parked: queue dry, all rays retired
+            __nanosleep(100);                                // other warps hold the remaining slots (BUSY): wait for them
+            continue;
+        }
+        // the phase with the most ready lanes wins; equal counts are broken by a priority that rotates with the round and
+        // differs between the warps of a block, so they spread over the phases and no ray starves
         round++;
         const int cN = ((c & 0xff) << 2) | (round & 3), cT = (((c >> 8) & 0xff) << 2) | ((round + 1) & 3),
                   cE = (((c >> 16) & 0xff) << 2) | ((round + 2) & 3), cR = (((c >> 24) & 0xff) << 2) | ((round + 3) & 3);
         const int phase = (cN >= cT && cN >= cE && cN >= cR) ? RTX_PH_N : (cT >= cE && cT >= cR) ? RTX_PH_T : (cE >= cR) ? RTX_PH_E : RTX_PH_R;
-        // my first slot waiting for this phase
-        int k = -1;
-#pragma unroll
-        for (int j = K - 1; j >= 0; j--) if ((int)((stbits >> (4 * j)) & 7u) == phase) k = j;
-        const bool mine = k >= 0;
-        const int s = (mine ? k : 0) * RTX_TRACE_THREADS + (int)threadIdx.x;
-        const bool inst = mine && ((stbits >> (4 * k + 3)) & 1u);
-        int newst = -1;  // phase | in_instance << 3 of slot k after this round
+        // claim one ready slot of my column (search start rotates so that no slot index is favoured)
+        int j = -1;
+        {
+            const unsigned rot = (round % NCOL) * 4u;
+            const unsigned pat = (unsigned)phase * 0x11111111u;
+            for (;;) {
+                const unsigned wr = __funnelshift_r(w, w, rot);
+                const unsigned hz = RTX_HASZERO_NIB(wr ^ pat);
+                if (!hz) break;
+                const int jj = (int)((((unsigned)(__ffs(hz) - 1) >> 2) + (rot >> 2)) & 7u);
+                const unsigned neww = w ^ ((unsigned)(phase ^ RTX_PH_BUSY) << (4 * jj));
+                const unsigned old = atomicCAS(const_cast<unsigned*>(colstate) + lane, w, neww);
+                if (old == w) { j = jj; break; }
+                w = old;
+            }
+        }
+        const bool mine = j >= 0;
+        const int s = (int)lane + 32 * (mine ? j : 0);
+        if (mine) __threadfence_block();   // see the slot as its previous owner left it
+        int newst = -1;  // phase of the claimed slot after this round
 
         if (phase == RTX_PH_N) {
             // ---- NODE: one 4-wide node per lane -----------------------------------------------------------------------
             if (mine) {
                 int node = T.node[s], sp = T.sp[s];
+                const bool inst = T.cur[s] >= 0;
                 RayF f;
                 T.load_rayf(s, f);
-                float d[4]; int ch[4];
-                if (COUNT) tc.nodes++;
-                node_test(S.nodes, node, f, ftmin, T.ft[s], d, ch);
+                const float ftmax = T.ft[s];
+                // up to RTX_N_STEPS levels per round: every extra level saves a vote and a state round trip, at the price of
+                // idle lanes once their next node is a leaf
+#pragma unroll 1
+                for (int step = 0; step < RTX_N_STEPS && node >= 0; step++) {
+                    float d[4]; int ch[4];
+                    if (COUNT) tc.nodes++;
+                    node_test(S.nodes, node, f, ftmin, ftmax, d, ch);
 #define RTX_CSWAP(i, j) if (d[j] < d[i]) { float td = d[i]; d[i] = d[j]; d[j] = td; int tcx = ch[i]; ch[i] = ch[j]; ch[j] = tcx; }
-                RTX_CSWAP(0, 1) RTX_CSWAP(2, 3) RTX_CSWAP(0, 2) RTX_CSWAP(1, 3) RTX_CSWAP(1, 2)
+                    RTX_CSWAP(0, 1) RTX_CSWAP(2, 3) RTX_CSWAP(0, 2) RTX_CSWAP(1, 3) RTX_CSWAP(1, 2)
 #undef RTX_CSWAP
-                if (sp + 3 <= RTX_SMEM_STACK) {
-                    int* const st = T.stack + s;
-                    if (d[3] < INF) { st[sp * NS] = ch[3]; sp++; }
-                    if (d[2] < INF) { st[sp * NS] = ch[2]; sp++; }
-                    if (d[1] < INF) { st[sp * NS] = ch[1]; sp++; }
-                    if (d[0] < INF) node = ch[0];
-                    else if (sp > 0) { sp--; node = st[sp * NS]; }
-                    else node = RTX_ST_DONE;
-                } else {
-                    if (d[3] < INF) RTX_PUSH(ch[3]);
-                    if (d[2] < INF) RTX_PUSH(ch[2]);
-                    if (d[1] < INF) RTX_PUSH(ch[1]);
-                    if (d[0] < INF) node = ch[0];
-                    else RTX_POP();
+                    if (sp + 3 <= RTX_SMEM_STACK) {
+                        int* const st = T.stack + s;
+                        if (d[3] < INF) { st[sp * NS] = ch[3]; sp++; }
+                        if (d[2] < INF) { st[sp * NS] = ch[2]; sp++; }
+                        if (d[1] < INF) { st[sp * NS] = ch[1]; sp++; }
+                        if (d[0] < INF) node = ch[0];
+                        else if (sp > 0) { sp--; node = st[sp * NS]; }
+                        else node = RTX_ST_DONE;
+                    } else {
+                        if (d[3] < INF) RTX_PUSH(ch[3]);
+                        if (d[2] < INF) RTX_PUSH(ch[2]);
+                        if (d[1] < INF) RTX_PUSH(ch[1]);
+                        if (d[0] < INF) node = ch[0];
+                        else RTX_POP();
+                    }
                 }
                 T.node[s] = node; T.sp[s] = sp;
-                newst = RTX_CLASSIFY(node, inst) | (inst ? 8 : 0);
+                newst = RTX_CLASSIFY(node, inst);
             }
         } else if (phase == RTX_PH_T) {
             // ---- TRI: one triangle of the pending BLAS leaf per lane ------------------------------------------------
@@ -321,7 +364,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                 else if (rem == 0) { int sp = T.sp[s]; RTX_POP(); T.sp[s] = sp; }
                 else node = ~(((ti + 1) << 3) | (rem - 1));
                 T.node[s] = node;
-                newst = RTX_CLASSIFY(node, true) | 8;
+                newst = RTX_CLASSIFY(node, true);
             }
         } else if (phase == RTX_PH_E) {
             // ---- ENTRY: a world entry (TLAS leaf), or the end of an instance -----------------------------------------
@@ -359,7 +402,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                     }
                 }
                 T.node[s] = node; T.sp[s] = sp;
-                newst = RTX_CLASSIFY(node, in_inst) | (in_inst ? 8 : 0);
+                newst = RTX_CLASSIFY(node, in_inst);
             }
         } else {
             // ---- RETIRE + REFILL (warp-collective; one slot per lane per round) ---------------------------------------
@@ -383,6 +426,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                 T.node[s] = RTX_ST_IDLE;
                 newst = RTX_PH_NONE;
             }
+            bool exhausted = __any_sync(FULL, dry[0] != 0);
             if (!exhausted) {
                 const unsigned want = __ballot_sync(FULL, mine);
                 const int cnt = __popc(want);
@@ -410,19 +454,20 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                     T.node[s] = node; T.sp[s] = 0; T.cur[s] = -1; T.job[s] = my;
                     newst = RTX_CLASSIFY(node, false);
                 }
-                if (base + cnt >= njobs) exhausted = true;
+                if (base + cnt >= njobs) {
+                    exhausted = true;
+                    if (lane == 0) dry[0] = 1;
+                }
             }
-            // once the queue is dry, idle slots leave the vote; until then they keep asking for a refill
+            // once the queue is dry, idle slots are parked for good; until then they keep asking for a refill
             if (mine && newst == RTX_PH_NONE && !exhausted) newst = RTX_PH_R;
-            if (exhausted) {
-#pragma unroll
-                for (int j = 0; j < K; j++)
-                    if (j != k && (int)((stbits >> (4 * j)) & 7u) == RTX_PH_R && T.node[j * RTX_TRACE_THREADS + threadIdx.x] == RTX_ST_IDLE)
-                        stbits = (stbits & ~(0xfu << (4 * j))) | ((unsigned)RTX_PH_NONE << (4 * j));
-            }
         }
-        if (newst >= 0) stbits = (stbits & ~(0xfu << (4 * k))) | ((unsigned)newst << (4 * k));
+        if (mine) {   // publish: slot state first, then its phase nibble (BUSY -> newst)
+            __threadfence_block();
+            atomicXor(const_cast<unsigned*>(colstate) + lane, (unsigned)(RTX_PH_BUSY ^ newst) << (4 * j));
+        }
     }
+#undef RTX_HASZERO_NIB
 #undef RTX_PUSH
 #undef RTX_POP
 #undef RTX_CLASSIFY
