@@ -100,7 +100,10 @@ struct Best {
 // memory, deeper ones spill to a global scratch column (rare: the stack seldom exceeds a dozen entries).
 #define RTX_SMEM_STACK 16
 #ifndef RTX_N_STEPS
-#define RTX_N_STEPS 1
+#define RTX_N_STEPS 3   /* node levels per NODE round (A/B on cornell-lucy: 1: 1041, 2: 1062, 3: 1090, 4: 1080 Mrays/s) */
+#endif
+#ifndef RTX_T_STEPS
+#define RTX_T_STEPS 4   /* triangles per TRI round (1: 1282, 2: 1303-1332, 4: 1373 Mrays/s) */
 #endif
 #define RTX_PH_N 0
 #define RTX_PH_T 1
@@ -344,25 +347,31 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
             // ---- TRI: one triangle of the pending BLAS leaf per lane ------------------------------------------------
             if (mine) {
                 int node = T.node[s];
-                const int code = ~node;
-                const int ti = code >> 3, rem = code & 7;
                 RayD r;
                 T.load_ray(s, r);
-                if (COUNT) tc.tris++;
-                const double t = isect_tri(S.tris + 10 * (size_t)ti, r, nullptr);
-                bool have = false;
-                if (tmin <= t && t <= T.bt[s]) {
-                    const int4 info = __ldg(S.tri_info + ti);
-                    Best B;
-                    T.load_best(s, B);
-                    const int cur = T.cur[s];
-                    B.offer(t, cur, S.entries[cur].rank, RTX_GEOM_TRIANGLE, ti, info.x, info.z);
-                    T.store_best(s, B);
-                    have = B.have;
+                double bt = T.bt[s];
+                // up to RTX_T_STEPS triangles of the leaf per round (the ray is loaded once); lanes with shorter leaves idle
+#pragma unroll 1
+                for (int step = 0; step < RTX_T_STEPS; step++) {
+                    const int code = ~node;
+                    const int ti = code >> 3, rem = code & 7;
+                    if (COUNT) tc.tris++;
+                    const double t = isect_tri(S.tris + 10 * (size_t)ti, r, nullptr);
+                    bool have = false;
+                    if (tmin <= t && t <= bt) {
+                        const int4 info = __ldg(S.tri_info + ti);
+                        Best B;
+                        T.load_best(s, B);
+                        const int cur = T.cur[s];
+                        B.offer(t, cur, S.entries[cur].rank, RTX_GEOM_TRIANGLE, ti, info.x, info.z);
+                        T.store_best(s, B);
+                        have = B.have;
+                        bt = B.t;
+                    }
+                    if (Policy::ANY_HIT && have) { node = RTX_ST_DONE; break; }
+                    if (rem == 0) { int sp = T.sp[s]; RTX_POP(); T.sp[s] = sp; break; }
+                    node = ~(((ti + 1) << 3) | (rem - 1));
                 }
-                if (Policy::ANY_HIT && have) node = RTX_ST_DONE;
-                else if (rem == 0) { int sp = T.sp[s]; RTX_POP(); T.sp[s] = sp; }
-                else node = ~(((ti + 1) << 3) | (rem - 1));
                 T.node[s] = node;
                 newst = RTX_CLASSIFY(node, true);
             }

@@ -286,10 +286,14 @@ def check_statistical(ctx, o, spp_g, spp_o, depth, cam_depth=None, seed=5, frac_
     bse = np.sqrt(blk(se ** 2) / 64)
     bz = (blk(mg) - blk(mo)) / np.maximum(bse, 1e-9)
     assert np.mean(np.abs(bz[bse > 1e-9]) > 4) < 0.01, "block-averaged bias"
-    # RMSE net of the noise both renders carry, relative to the mean level (north star: < 1 %)
+    # RMSE net of the noise both renders carry, relative to the mean level (north star: < 1 %). At these sample counts the
+    # noise itself is tens of percent of the mean and heavy-tailed (glossy fireflies), so the raw difference
+    # mean((mg-mo)^2) - noise is dominated by the error of the noise estimate (it failed one oracle draw in six with
+    # identical estimators). The same statement in noise units is robust: the mean squared z-score is 1 when the two
+    # renders share an expectation, 1 + (bias / se)^2 when they do not.
     noise = np.mean(se[live] ** 2)
-    rmse = np.sqrt(max(0.0, np.mean((mg - mo) ** 2) - noise * live.mean())) / max(mo.mean(), 1e-6)
-    assert rmse < 0.01 + 0.3 * np.sqrt(noise) / max(mo.mean(), 1e-6), f"excess RMSE {rmse:.4f}"
+    z2 = np.mean(np.clip(z, -6.0, 6.0) ** 2)
+    assert z2 < 1.25, f"mean z^2 = {z2:.3f}: excess RMSE {np.sqrt(max(0.0, z2 - 1.0) * noise) / max(mo.mean(), 1e-6):.4f} of the mean level"
     return mg, mo
 
 

@@ -1,3 +1,2 @@
 #!/bin/bash
-timeout 120 python tools/gpu_check.py cornell-lucy cornell 2>&1 | grep -E "trace|render|secondary|Error|error" 
-timeout 120 python tools/gpu_perf.py cornell-lucy 64 2>&1 | tail -1
+for i in 1 2 3 4 5 6; do timeout 300 python -m pytest tests/test_parity_gpu.py -m gpu -x -q -k "cornell-glossy-96" 2>&1 | grep -E "^E   .*(assert|Error)|passed|failed" | head -4; done
