@@ -156,7 +156,11 @@ int32_t rtx_create(int32_t device_id, rtx_ctx** out) {
         int occ = 0, minOcc = 1 << 30;
         const void* kernels[5] = {(const void*)k_extend<false>, (const void*)k_extend<true>, (const void*)k_connect<false>, (const void*)k_connect<true>,
                                   (const void*)k_trace_closest};
+        // developer knob: shared-memory carve-out in KB (the rest of the 256 KB array is L1); fewer resident blocks, more L1
+        const char* carveEnv = getenv("RTX_TRACE_CARVEOUT_KB");
+        const int carveKB = carveEnv ? atoi(carveEnv) : 0;
         for (const void* k : kernels) {
+            if (carveKB > 0) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(100, carveKB * 100 / 228));
             if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
                 (e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, RTX_TRACE_THREADS, smem)) != cudaSuccess || occ < 1) {
                 fail(nullptr, RTX_ERR_CUDA, "rtx_create: trace kernel setup failed (%s, occupancy %d)", cudaGetErrorString(e), occ);
@@ -165,8 +169,10 @@ int32_t rtx_create(int32_t device_id, rtx_ctx** out) {
             }
             minOcc = std::min(minOcc, occ);
         }
+        if (carveKB > 0) minOcc = std::max(1, std::min(minOcc, (int)((size_t)carveKB * 1024 / (smem + 1024))));
         ctx->trace_grid = ctx->num_sms * minOcc;
-        size_t spillInts = (size_t)ctx->trace_grid * RTX_TRACE_K * RTX_TRACE_THREADS * (RTX_STACK_SIZE - RTX_SMEM_STACK);
+        if (getenv("RTX_DEBUG_BATCH")) fprintf(stderr, "[rtx] trace kernels: %d blocks/SM, %d B dynamic smem per block, grid %d\n", minOcc, smem, ctx->trace_grid);
+        size_t spillInts = (size_t)ctx->trace_grid * RTX_TRACE_SLOTS * (RTX_STACK_SIZE - RTX_SMEM_STACK);
         if ((e = cudaMalloc((void**)&ctx->trace_spill, spillInts * sizeof(int))) != cudaSuccess) {
             fail(nullptr, RTX_ERR_CUDA, "rtx_create: %s", cudaGetErrorString(e));
             rtx_destroy(ctx);

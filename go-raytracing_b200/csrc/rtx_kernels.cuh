@@ -185,7 +185,7 @@ __device__ __forceinline__ Hit best_to_hit(const Best& b) {
 }
 
 extern __shared__ __align__(16) unsigned char rtx_smem[];  // the trace kernels' ray pool (TracePool)
-#define RTX_TRACE_SMEM_BYTES ((size_t)RTX_TRACE_K * RTX_TRACE_THREADS * RTX_SLOT_WORDS * 4 + RTX_POOL_EXTRA_BYTES)
+#define RTX_TRACE_SMEM_BYTES ((size_t)RTX_TRACE_SLOTS * RTX_SLOT_WORDS * 4 + RTX_POOL_EXTRA_BYTES)
 
 // ---- K2: extend — closest hit of every active path, then binning into material-sorted shading queues -------------
 struct ExtendPolicy {
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_extend(
     ExtendPolicy P{ctl, pool, q_cur, &S, pp.seed_lo, pp.seed_hi};
     TraceCounters tc = {0, 0, 0, 0, 0};
     const int n = ctl->n_active;
-    trace_persistent<ExtendPolicy, COUNT, RTX_TRACE_K>(S, P, &ctl->cur_extend, n, tc, spill, rtx_smem);
+    trace_persistent<ExtendPolicy, COUNT, RTX_TRACE_SLOTS>(S, P, &ctl->cur_extend, n, tc, spill, rtx_smem);
     if (COUNT) flush_counters(ctl, tc);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->ext_rays, (unsigned long long)n);
 }
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_connect
     ConnectPolicy P{pool, pp.seed_lo, pp.seed_hi};
     TraceCounters tc = {0, 0, 0, 0, 0};
     const int n = ctl->n_shadow;
-    trace_persistent<ConnectPolicy, COUNT, RTX_TRACE_K>(S, P, &ctl->cur_connect, n, tc, spill, rtx_smem);
+    trace_persistent<ConnectPolicy, COUNT, RTX_TRACE_SLOTS>(S, P, &ctl->cur_connect, n, tc, spill, rtx_smem);
     if (COUNT) flush_counters(ctl, tc);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->shadow_rays, (unsigned long long)n);
 }
@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_trace_c
         int* entry_id, int* prim_id, double* t, double* normal, unsigned char* front, double* uv, double* p) {
     BatchPolicy P{&S, rays, tmin, tmax, entry_id, prim_id, t, normal, front, uv, p};
     TraceCounters tc = {0, 0, 0, 0, 0};
-    trace_persistent<BatchPolicy, false, RTX_TRACE_K>(S, P, cursor, n, tc, spill, rtx_smem);
+    trace_persistent<BatchPolicy, false, RTX_TRACE_SLOTS>(S, P, cursor, n, tc, spill, rtx_smem);
 }
 
 __global__ void k_camera_rays(DevCamera C, const int* ij, const double* sq, const double* disk, const double* tm, long long n, double* out) {

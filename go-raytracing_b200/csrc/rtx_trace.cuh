@@ -20,8 +20,8 @@
 #include "rtx_device.cuh"
 
 #define RTX_TRACE_THREADS 128
-#ifndef RTX_TRACE_K
-#define RTX_TRACE_K 2        /* ray slots per lane (shared-memory ray pool, see trace_persistent) */
+#ifndef RTX_TRACE_SLOTS
+#define RTX_TRACE_SLOTS 224   /* ray slots per 128-thread block (shared-memory ray pool, see trace_persistent); multiple of 32, <= 256 (A/B on cornell-lucy: 256: 1370, 224: 1401 Mrays/s: a little more L1) */
 #endif
 #ifndef RTX_TRACE_BLOCKS
 #define RTX_TRACE_BLOCKS 4   /* resident blocks per SM the trace kernels are compiled for (caps registers at 65536 / (128 * blocks)) */
@@ -114,9 +114,10 @@ struct Best {
 #define RTX_POOL_EXTRA_BYTES 256                                        /* column states + flags */
 #define RTX_PH_BUSY 5   /* claimed by a warp for the current round */
 
-template <int K>
+template <int NSLOTS>
 struct TracePool {
-    static constexpr int NS = K * RTX_TRACE_THREADS;
+    static constexpr int NS = NSLOTS;
+    static_assert(NSLOTS % 32 == 0 && NSLOTS <= 256, "slots per block: a multiple of 32, at most 8 per bank column");
     float* f;      // [9][NS]  ix iy iz cnx cny cnz cfx cfy cfz
     int* off;      // [NS]     offx | offy << 8 | offz << 16
     float* ft;     // [NS]
@@ -175,7 +176,7 @@ struct TracePool {
 // `s`: the rare, bulky part of the ENTRY phase (float64 sphere / quad / plane tests, the
 // Volume free-flight with its log). Measured both ways on B200: inlined 1039 Mrays/s, out of line (-DRTX_ENTRY_OOL) 958 on
 // cornell-lucy. State travels through the shared-memory pool; Sp points at the kernel's __grid_constant__ parameter.
-template <int K>
+template <int NSLOTS>
 #ifndef RTX_ENTRY_OOL
 __device__ __forceinline__
 #else
@@ -184,7 +185,7 @@ __device__ __noinline__
 bool entry_other(const DevScene* Sp, unsigned char* smem, int s, int ei, double tmin, uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
                  uint32_t c2, bool transparent, TraceCounters* tcp) {
     const DevScene& S = *Sp;
-    const TracePool<K> T(smem);
+    const TracePool<NSLOTS> T(smem);
     const DEntry e = S.entries[ei];
     RayD r, r2;
     T.load_ray(s, r);
@@ -227,9 +228,9 @@ bool entry_other(const DevScene* Sp, unsigned char* smem, int s, int ei, double 
     return B.have;
 }
 
-template <class Policy, bool COUNT, int K>
+template <class Policy, bool COUNT, int NSLOTS>
 __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, int* cursor, int njobs, TraceCounters& tc, int* spill, unsigned char* smem) {
-    typedef TracePool<K> Pool_;
+    typedef TracePool<NSLOTS> Pool_;
     constexpr int NS = Pool_::NS;
     const Pool_ T(smem);
     const unsigned FULL = 0xffffffffu;
@@ -257,7 +258,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
         T.col[threadIdx.x] = w0;
         T.flags[threadIdx.x] = 0;
     }
-    for (int k = 0; k < K; k++) T.node[k * RTX_TRACE_THREADS + threadIdx.x] = RTX_ST_IDLE;
+    for (int i = threadIdx.x; i < NS; i += RTX_TRACE_THREADS) T.node[i] = RTX_ST_IDLE;
     __syncthreads();
     unsigned round = warp;
 
@@ -405,7 +406,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                     } else {
                         VolumeRng vr = {0, 0, 0, 0, 0, true};
                         if (e.volume >= 0) vr = P.volume_rng(job);
-                        const bool have = entry_other<K>(&S, smem, s, ei, tmin, vr.k0, vr.k1, vr.c0, vr.c1, vr.c2, vr.transparent, tcp);
+                        const bool have = entry_other<NSLOTS>(&S, smem, s, ei, tmin, vr.k0, vr.k1, vr.c0, vr.c1, vr.c2, vr.transparent, tcp);
                         if (Policy::ANY_HIT && have) node = RTX_ST_DONE;
                         else RTX_POP();
                     }
