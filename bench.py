@@ -186,12 +186,18 @@ def main():
 
     def step(i, e2e=False):
         """One pass. Returns this rank's stats dict."""
+        t_load = 0.0
         if e2e:
-            ctx.load(sc)                         # host -> device: flattened scene + camera, BVH build included
+            t0 = time.perf_counter()
+            ctx.load(sc)                         # host -> device: flattened scene + camera; mesh BVHs are built on the device
+            t_load = (time.perf_counter() - t0) * 1e3
+            up = ctx.stats()
         ctx.clear()
         if count > 0:
             ctx.render_pass(count, depth, camera_max_depth=depth, seed=args.seed + i, sample_base=base)
         st = ctx.stats() if count > 0 else {"kernel_launches": 0, "extension_rays": 0, "shadow_rays": 0, "ms_extend": 0.0, "ms_total": 0.0}
+        if e2e:
+            st = dict(st, load_ms=t_load, ms_bvh_build=up["ms_bvh_build"], ms_scene_upload=up["ms_scene_upload"], bvh_on_device=up["bvh_on_device"])
         mg.reduce_sum(acc, dst=0)                # the single collective of the path (NCCL over NVLink)
         if rank == 0:
             nonlocal pix
@@ -235,11 +241,16 @@ def main():
     e2e = None
     if not args.no_e2e:
         step(-100, True)
-        e_ms, _, _ = timed(max(1, min(args.steps, 2)), 1000, True)
+        e_ms, _, e_stats = timed(max(1, min(args.steps, 2)), 1000, True)
         e_steps = max(1, min(args.steps, 2))
         e2e = {"value": npix * spp * e_steps / (e_ms / 1e3) / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": desc_bytes(sc) + grt.C.sizeof(grt.CameraDesc),
                "d2h_bytes_per_step": 4 * npix, "ms_per_step": e_ms / e_steps,
-               "what": "rtx_scene_upload + rtx_camera_set (host SoA arrays -> HBM, wide-BVH build) + rtx_render_pass + reduce + rtx_resolve_rgba8 (RGBA8 -> host)"}
+               "breakdown_ms": {"scene_load_wall": sum(x.get("load_ms", 0.0) for x in e_stats) / e_steps,
+                                "rtx_scene_upload": sum(x.get("ms_scene_upload", 0.0) for x in e_stats) / e_steps,
+                                "device_bvh_build": sum(x.get("ms_bvh_build", 0.0) for x in e_stats) / e_steps,
+                                "render_pass_device": sum(x.get("ms_total", 0.0) for x in e_stats) / e_steps,
+                                "bvh_on_device": int(e_stats[0].get("bvh_on_device", 0))},
+               "what": "rtx_scene_upload + rtx_camera_set (host SoA arrays -> HBM, device BVH build) + rtx_render_pass + reduce + rtx_resolve_rgba8 (RGBA8 -> host)"}
 
     # roofline of the dominant kernel (k_extend): instrumented pass on rank 0's slice, not timed
     roofline = None

@@ -77,6 +77,7 @@ class Stats(C.Structure):
         ("wavefront_iterations", C.c_uint64), ("kernel_launches", C.c_uint64),
         ("ms_generate", C.c_double), ("ms_extend", C.c_double), ("ms_shade", C.c_double), ("ms_connect", C.c_double), ("ms_total", C.c_double),
         ("tlas_nodes", C.c_uint32), ("blas_nodes", C.c_uint32), ("n_entries", C.c_uint32), ("n_tris", C.c_uint32),
+        ("blas_depth", C.c_uint32), ("bvh_on_device", C.c_uint32), ("ms_bvh_build", C.c_double), ("ms_scene_upload", C.c_double),
     ]
 
     def as_dict(self):

@@ -1,6 +1,7 @@
 // rtx_api.cu — implementation of the C-ABI in include/rtx_b200.h: context, scene upload (SoA device buffers +
 // wide BVH build), camera, the wavefront host loop, resolve, and the batch entry points used for parity.
 // There is no CPU fallback anywhere in this library: every arithmetic entry point launches CUDA kernels.
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -11,6 +12,7 @@
 
 #include "rtx_bvh.hpp"
 #include "rtx_kernels.cuh"
+#include "rtx_bvh_gpu.cuh"
 
 using rtxbvh::Box;
 using rtxbvh::Node4;
@@ -42,6 +44,9 @@ struct rtx_ctx {
     Ctl* ctl = nullptr;       // device
     Ctl* ctl_host = nullptr;  // pinned
     int count_stats = 0, time_kernels = 1, blas_leaf = 4;
+    int bvh_device = 1;   // mesh BLAS construction on the device (rtx_bvh_gpu.cuh); 0 = host builder (rtx_bvh.hpp), kept for A/B
+    double ms_upload_blas = 0, ms_upload_total = 0;
+    int blas_depth = 0, built_on_device = 0;
     rtx_stats stats{};
     double env_total = 0;
     // scene summary
@@ -219,6 +224,7 @@ int32_t rtx_set_option(rtx_ctx* ctx, const char* key, int64_t value) {
     } else if (k == "count_stats") ctx->count_stats = (int)value;  // bit 0: extend kernel, bit 1: connect kernel
     else if (k == "time_kernels") ctx->time_kernels = value != 0;
     else if (k == "l2_persist") { ctx->l2_persist = value != 0; ctx->window_set = false; }  // L2 persisting window over the scene geometry (default off)
+    else if (k == "bvh_device") ctx->bvh_device = value != 0;  // takes effect at the next rtx_scene_upload
     else if (k == "blas_leaf") {  // triangles per BLAS leaf (1..8); takes effect at the next rtx_scene_upload
         if (value < 1 || value > 8) return fail(ctx, RTX_ERR_INVALID, "blas_leaf must be in 1..8");
         ctx->blas_leaf = (int)value;
@@ -289,6 +295,7 @@ static Box xform_box(const rtx_scene_desc* d, Box b, int xfBegin, int xfCount) {
 int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     if (!ctx || !d) return RTX_ERR_INVALID;
     if (d->abi_version != RTX_ABI_VERSION) return fail(ctx, RTX_ERR_INVALID, "scene abi_version %u != %d", d->abi_version, RTX_ABI_VERSION);
+    const auto tUpload0 = std::chrono::steady_clock::now();
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     free_scene(ctx);
@@ -376,18 +383,27 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     for (int i = 0; i < d->n_planes; i++)
         for (int a = 0; a < 3; a++) { planes[8 * i + a] = d->plane_point[3 * i + a]; planes[8 * i + 3 + a] = d->plane_normal[3 * i + a]; }
 
-    // ---- triangles: meshes are permuted into BLAS leaf order; loose triangles follow
-    std::vector<Node4> nodes;
-    std::vector<double> tris, triNrm;
+    // ---- triangles: meshes are permuted into BLAS leaf order; loose triangles (world entries / Box-list items) follow
+    std::vector<Node4> nodes;                       // host-built nodes: every BLAS with the host builder, and always the TLAS
+    std::vector<double> tris, triNrm;               // host-built triangle records: meshes (host builder only), then loose ones
     std::vector<int4> triInfo;
-    std::vector<int> devTriOfDesc(d->n_tris, -1);
+    int meshTotal = 0;
+    for (int g = 0; g < d->n_groups; g++)
+        if (d->group_kind[g] == RTX_GEOM_MESH) meshTotal += d->group_count[g];
+    if ((size_t)meshTotal + (size_t)d->n_tris >= (1u << 28)) return fail(ctx, RTX_ERR_UNSUPPORTED, "too many triangles");
+    std::vector<int> looseOfDesc(d->n_tris, -1), looseList;
+    auto noteLoose = [&](int kind, int idx) {
+        if (kind == RTX_GEOM_TRIANGLE && looseOfDesc[idx] < 0) { looseOfDesc[idx] = meshTotal + (int)looseList.size(); looseList.push_back(idx); }
+    };
+    for (int i = 0; i < d->n_list_items; i++) noteLoose(d->list_item_kind[i], d->list_item_index[i]);
+    for (int e = 0; e < d->n_entries; e++) noteLoose(d->entry_geom_kind[e], d->entry_geom_index[e]);
+    const int totalTris = meshTotal + (int)looseList.size();
     auto pushTri = [&](int ti, int localId, int rank) {
         const double *v0 = d->tri_v0 + 3 * ti, *v1 = d->tri_v1 + 3 * ti, *v2 = d->tri_v2 + 3 * ti;
         double e1[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]}, e2[3] = {v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2]};
         double n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};  // rt/triangle.go:19-25
         double l = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
         if (l != 0) { double inv = 1 / l; n[0] = inv * n[0]; n[1] = inv * n[1]; n[2] = inv * n[2]; }
-        int dev = (int)triInfo.size();
         for (int a = 0; a < 3; a++) tris.push_back(v0[a]);
         for (int a = 0; a < 3; a++) tris.push_back(e1[a]);
         for (int a = 0; a < 3; a++) tris.push_back(e2[a]);
@@ -395,36 +411,94 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
         for (int a = 0; a < 3; a++) triNrm.push_back(n[a]);
         triNrm.push_back(0);
         triInfo.push_back(make_int4(localId, d->tri_mat[ti], rank, 0));
-        devTriOfDesc[ti] = dev;
-        return dev;
     };
     std::vector<int> groupRoot(d->n_groups, -1), groupTriBase(d->n_groups, 0);
+    std::vector<Box> groupBox(d->n_groups);
+    for (auto& gb : groupBox) gb.reset();
     uint32_t blasNodes = 0;
     int maxBlasDepth = 0, tlasDepth = 0;
-    for (int g = 0; g < d->n_groups; g++) {
-        if (d->group_kind[g] != RTX_GEOM_MESH) continue;
-        int begin = d->group_begin[g], count = d->group_count[g];
-        std::vector<Box> boxes(count);
-        for (int k = 0; k < count; k++) boxes[k] = prim_box(d, RTX_GEOM_TRIANGLE, begin + k);
-        std::vector<int> ranks;
-        if (d->tri_rank) ranks.assign(d->tri_rank + begin, d->tri_rank + begin + count);
-        else ranks = rtxbvh::canonical_ranks(boxes);
-        int base = (int)triInfo.size();
-        groupTriBase[g] = base;
-        std::vector<int> perm;
-        size_t before = nodes.size();
-        int depth = 0;
-        groupRoot[g] = rtxbvh::build_bvh4(boxes, ctx->blas_leaf, nodes, perm, [&](int first, int cnt) { return ((base + first) << 3) | (cnt - 1); }, &depth);
-        maxBlasDepth = std::max(maxBlasDepth, depth);
-        blasNodes += (uint32_t)(nodes.size() - before);
-        for (int k = 0; k < count; k++) pushTri(begin + perm[k], perm[k], ranks[perm[k]]);
-        if (count > 0 && (size_t)(base + count) >= (1u << 28)) return fail(ctx, RTX_ERR_UNSUPPORTED, "too many triangles");
+    const bool deviceBuild = ctx->bvh_device != 0 && meshTotal > 0;
+    // device-built pieces (deviceBuild only): one node buffer per mesh, triangle records for all meshes
+    struct DevBlas { Node4* nodes; int n; };
+    std::vector<DevBlas> devBlas;
+    Scratch buildScratch;   // freed when the upload returns
+    double *dMeshTris = nullptr, *dTriNrm = nullptr;
+    int4* dTriInfo = nullptr;
+    cudaEvent_t evB0 = nullptr, evB1 = nullptr;
+    if (deviceBuild) {
+        // the flattened triangle arrays go to the device as they are; bounds, hierarchy and leaf-ordered records are built there
+        double *dV0, *dV1, *dV2; int *dMat, *dRank;
+        CU(buildScratch.in(&dV0, d->tri_v0, (size_t)3 * d->n_tris, ctx->stream));
+        CU(buildScratch.in(&dV1, d->tri_v1, (size_t)3 * d->n_tris, ctx->stream));
+        CU(buildScratch.in(&dV2, d->tri_v2, (size_t)3 * d->n_tris, ctx->stream));
+        CU(buildScratch.in(&dMat, d->tri_mat, (size_t)d->n_tris, ctx->stream));
+        std::vector<int> rankAll;
+        if (!d->tri_rank) {   // no ranks from the caller's Go tree: canonical ones (host restatement of rt/bvh.go's order; exact-tie resolution only)
+            rankAll.assign(d->n_tris, 0);
+            for (int g = 0; g < d->n_groups; g++) {
+                if (d->group_kind[g] != RTX_GEOM_MESH) continue;
+                const int begin = d->group_begin[g], count = d->group_count[g];
+                std::vector<Box> boxes(count);
+                for (int k = 0; k < count; k++) boxes[k] = prim_box(d, RTX_GEOM_TRIANGLE, begin + k);
+                std::vector<int> r = rtxbvh::canonical_ranks(boxes);
+                for (int k = 0; k < count; k++) rankAll[begin + k] = r[k];
+            }
+        }
+        CU(buildScratch.in(&dRank, d->tri_rank ? d->tri_rank : rankAll.data(), (size_t)d->n_tris, ctx->stream));
+        CU(cudaMalloc((void**)&dMeshTris, std::max<size_t>((size_t)10 * meshTotal * sizeof(double), 16)));
+        buildScratch.ptrs.push_back(dMeshTris);
+        CU(cudaMalloc((void**)&dTriNrm, std::max<size_t>((size_t)4 * totalTris * sizeof(double), 16)));
+        ctx->scene_allocs.push_back(dTriNrm);
+        CU(cudaMalloc((void**)&dTriInfo, std::max<size_t>((size_t)totalTris * sizeof(int4), 16)));
+        ctx->scene_allocs.push_back(dTriInfo);
+        CU(cudaEventCreate(&evB0)); CU(cudaEventCreate(&evB1));
+        CU(cudaEventRecord(evB0, ctx->stream));
+        int base = 0;
+        for (int g = 0; g < d->n_groups; g++) {
+            if (d->group_kind[g] != RTX_GEOM_MESH) continue;
+            const int begin = d->group_begin[g], count = d->group_count[g];
+            groupTriBase[g] = base;
+            if (count == 0) continue;
+            Node4* dn = nullptr;
+            CU(cudaMalloc((void**)&dn, ((size_t)count + 1) * sizeof(Node4)));
+            buildScratch.ptrs.push_back(dn);
+            rtxgpu::BlasResult br;
+            const char* what = "";
+            cudaError_t be = rtxgpu::build_blas(dV0 + 3 * (size_t)begin, dV1 + 3 * (size_t)begin, dV2 + 3 * (size_t)begin, dMat + begin, dRank + begin, count, ctx->blas_leaf,
+                                                (int)blasNodes, base, dn, dMeshTris + 10 * (size_t)base, dTriNrm + 4 * (size_t)base, dTriInfo + base, ctx->stream, &br, &what);
+            if (be != cudaSuccess) return fail(ctx, RTX_ERR_CUDA, "device BVH build of mesh group %d failed: %s (%s)", g, what, cudaGetErrorString(be));
+            groupRoot[g] = (int)blasNodes;   // local node 0 of this mesh
+            devBlas.push_back({dn, br.n_nodes});
+            blasNodes += (uint32_t)br.n_nodes;
+            maxBlasDepth = std::max(maxBlasDepth, br.depth);
+            for (int a = 0; a < 3; a++) { groupBox[g].lo[a] = br.lo[a]; groupBox[g].hi[a] = br.hi[a]; }
+            base += count;
+        }
+        CU(cudaEventRecord(evB1, ctx->stream));
+        nodes.resize(blasNodes);   // placeholders: the host-built TLAS below gets global node indices
+    } else {
+        for (int g = 0; g < d->n_groups; g++) {
+            if (d->group_kind[g] != RTX_GEOM_MESH) continue;
+            int begin = d->group_begin[g], count = d->group_count[g];
+            std::vector<Box> boxes(count);
+            for (int k = 0; k < count; k++) { boxes[k] = prim_box(d, RTX_GEOM_TRIANGLE, begin + k); groupBox[g].grow(boxes[k]); }
+            std::vector<int> ranks;
+            if (d->tri_rank) ranks.assign(d->tri_rank + begin, d->tri_rank + begin + count);
+            else ranks = rtxbvh::canonical_ranks(boxes);
+            int base = (int)triInfo.size();
+            groupTriBase[g] = base;
+            std::vector<int> perm;
+            size_t before = nodes.size();
+            int depth = 0;
+            groupRoot[g] = rtxbvh::build_bvh4(boxes, ctx->blas_leaf, nodes, perm, [&](int first, int cnt) { return ((base + first) << 3) | (cnt - 1); }, &depth);
+            maxBlasDepth = std::max(maxBlasDepth, depth);
+            blasNodes += (uint32_t)(nodes.size() - before);
+            for (int k = 0; k < count; k++) pushTri(begin + perm[k], perm[k], ranks[perm[k]]);
+        }
     }
-    auto devPrim = [&](int kind, int idx) {
-        if (kind != RTX_GEOM_TRIANGLE) return idx;
-        if (devTriOfDesc[idx] < 0) pushTri(idx, 0, 0);
-        return devTriOfDesc[idx];
-    };
+    const size_t hostMeshTris = triInfo.size();   // 0 with the device builder
+    for (int ti : looseList) pushTri(ti, 0, 0);
+    auto devPrim = [&](int kind, int idx) { return kind == RTX_GEOM_TRIANGLE ? looseOfDesc[idx] : idx; };
     std::vector<int2> listItems(d->n_list_items);
     for (int i = 0; i < d->n_list_items; i++) listItems[i] = make_int2(d->list_item_kind[i], devPrim(d->list_item_kind[i], d->list_item_index[i]));
 
@@ -447,7 +521,7 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
             if (E.b == 0) continue;
         } else {
             E.a = groupRoot[gi]; E.b = groupTriBase[gi];
-            for (int i = 0; i < d->group_count[gi]; i++) b.grow(prim_box(d, RTX_GEOM_TRIANGLE, d->group_begin[gi] + i));
+            b = groupBox[gi];   // union of the padded float64 triangle boxes (host loop or device reduction: same values)
         }
         entryBox[e] = xform_box(d, b, E.xf_begin, E.xf_count);
     }
@@ -513,7 +587,7 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     ctx->tlas_nodes = (uint32_t)(nodes.size() - before);
     ctx->blas_nodes = blasNodes;
     ctx->n_entries = d->n_entries;
-    ctx->n_tris = (uint32_t)triInfo.size();
+    ctx->n_tris = (uint32_t)totalTris;
 
     std::vector<DXform> xfs(d->n_xforms);
     for (int x = 0; x < d->n_xforms; x++) {
@@ -568,12 +642,10 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     ctx->env_total = totalPower;
 
     // ---- upload
-    std::vector<float4> nodeData(nodes.size() * 8);
-    if (!nodes.empty()) std::memcpy(nodeData.data(), nodes.data(), nodes.size() * sizeof(Node4));
     {   // The geometry every ray fetches (nodes, triangles, spheres, quads) goes into ONE allocation so that a single L2
         // access-policy window can keep it resident against the path pool streaming through the same cache (see render).
         auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
-        const size_t bNodes = pad(nodeData.size() * sizeof(float4)), bTris = pad(tris.size() * sizeof(double)), bSph = pad(sph.size() * sizeof(double)),
+        const size_t bNodes = pad(nodes.size() * sizeof(Node4)), bTris = pad((size_t)totalTris * 10 * sizeof(double)), bSph = pad(sph.size() * sizeof(double)),
                      bQuads = pad(quads.size() * sizeof(double));
         const size_t total = std::max<size_t>(bNodes + bTris + bSph + bQuads, 256);
         char* base = nullptr;
@@ -583,20 +655,35 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
         auto put = [&](const void* src, size_t bytes, size_t off) {
             return bytes ? cudaMemcpyAsync(base + off, src, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
         };
-        CU(put(nodeData.data(), nodeData.size() * sizeof(float4), 0));
-        CU(put(tris.data(), tris.size() * sizeof(double), bNodes));
+        if (deviceBuild) {   // device-built BLAS nodes and mesh triangles move device-to-device; the host adds the TLAS and the loose triangles
+            size_t off = 0;
+            for (const DevBlas& db : devBlas) {
+                CU(cudaMemcpyAsync(base + off, db.nodes, (size_t)db.n * sizeof(Node4), cudaMemcpyDeviceToDevice, ctx->stream));
+                off += (size_t)db.n * sizeof(Node4);
+            }
+            CU(put(nodes.data() + blasNodes, (nodes.size() - blasNodes) * sizeof(Node4), off));
+            CU(cudaMemcpyAsync(base + bNodes, dMeshTris, (size_t)meshTotal * 10 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            CU(put(tris.data(), tris.size() * sizeof(double), bNodes + (size_t)meshTotal * 10 * sizeof(double)));
+            if (!triNrm.empty()) CU(cudaMemcpyAsync(dTriNrm + 4 * (size_t)meshTotal, triNrm.data(), triNrm.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            if (!triInfo.empty()) CU(cudaMemcpyAsync(dTriInfo + meshTotal, triInfo.data(), triInfo.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+            S.tri_nrm = dTriNrm; S.tri_info = dTriInfo;
+        } else {
+            CU(put(nodes.data(), nodes.size() * sizeof(Node4), 0));
+            CU(put(tris.data(), tris.size() * sizeof(double), bNodes));
+            UP(triNrm, S.tri_nrm); UP(triInfo, S.tri_info);
+        }
         CU(put(sph.data(), sph.size() * sizeof(double), bNodes + bTris));
         CU(put(quads.data(), quads.size() * sizeof(double), bNodes + bTris + bSph));
         S.nodes = (const float4*)base;
         S.tris = (const double*)(base + bNodes);
         S.spheres = (const double*)(base + bNodes + bTris);
         S.quads = (const double*)(base + bNodes + bTris + bSph);
+        (void)hostMeshTris;
     }
     UP(entries, S.entries);
     UP(unbounded, S.unbounded);
     UP(sphMat, S.sph_mat);
     UP(quadMat, S.quad_mat);
-    UP(triNrm, S.tri_nrm); UP(triInfo, S.tri_info);
     UP(planes, S.planes); UP(planeMat, S.plane_mat);
     UP(listItems, S.list_items);
     UP(xfs, S.xforms); UP(xfCanon, S.xf_canon); UP(vols, S.volumes); UP(mats, S.mats); UP(texs, S.texs); UP(lights, S.light_quads);
@@ -607,8 +694,20 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     S.n_lights = d->n_lights;
     S.vol_draws = d->world_is_bvh ? 2 : 1;
     CU(cudaStreamSynchronize(ctx->stream));
+    ctx->ms_upload_blas = 0;
+    if (evB0) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, evB0, evB1);
+        ctx->ms_upload_blas = ms;
+        cudaEventDestroy(evB0); cudaEventDestroy(evB1);
+    }
+    if (getenv("RTX_DEBUG_BATCH"))
+        fprintf(stderr, "[rtx] scene upload: %d mesh triangles, %u BLAS nodes (depth %d, %s build %.2f ms), %u TLAS nodes\n", meshTotal, blasNodes, maxBlasDepth,
+                deviceBuild ? "device" : "host", ctx->ms_upload_blas, ctx->tlas_nodes);
     ctx->S = S;
     ctx->have_scene = true;
+    ctx->blas_depth = maxBlasDepth; ctx->built_on_device = deviceBuild ? 1 : 0;
+    ctx->ms_upload_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tUpload0).count();
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
     return RTX_OK;
 }
@@ -869,6 +968,8 @@ int32_t rtx_get_stats(rtx_ctx* ctx, rtx_stats* out) {
     if (!ctx || !out) return RTX_ERR_INVALID;
     *out = ctx->stats;
     out->tlas_nodes = ctx->tlas_nodes; out->blas_nodes = ctx->blas_nodes; out->n_entries = ctx->n_entries; out->n_tris = ctx->n_tris;
+    out->blas_depth = (uint32_t)ctx->blas_depth; out->bvh_on_device = (uint32_t)ctx->built_on_device;
+    out->ms_bvh_build = ctx->ms_upload_blas; out->ms_scene_upload = ctx->ms_upload_total;
     return RTX_OK;
 }
 

@@ -186,6 +186,11 @@ typedef struct rtx_stats {
     double ms_generate, ms_extend, ms_shade, ms_connect, ms_total; /* CUDA-event times, last pass */
     /* scene structure */
     uint32_t tlas_nodes, blas_nodes, n_entries, n_tris;
+    /* last rtx_scene_upload: where the mesh hierarchies were built and how long it took (CUDA events / host clock) */
+    uint32_t blas_depth;       /* deepest mesh hierarchy, in 4-wide levels                                   */
+    uint32_t bvh_on_device;    /* 1: built by the device builder (replaces NewBVHNodeFromList, rt/bvh.go:64) */
+    double ms_bvh_build;       /* device time of all mesh builds (0 with the host builder)                   */
+    double ms_scene_upload;    /* host wall time of the whole rtx_scene_upload call                          */
 } rtx_stats;
 
 typedef struct rtx_ctx rtx_ctx;

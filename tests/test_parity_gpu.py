@@ -127,6 +127,65 @@ def _soup_scene(grt, rng, world_is_bvh=True, n_tri=3000, dup=True):
     return b.build()
 
 
+def test_device_bvh_build(grt, orc, ctx):
+    """The mesh hierarchies are built on the device (rtx_bvh_gpu.cuh). Closest hits must not depend on the hierarchy: the
+    device-built and the host-built BVH give bit-identical hit records, the build is reproducible, and degenerate meshes
+    (1 / 2 / 5 triangles, 200 coincident triangles -> split-by-position fallback, zero-area triangles) agree with the oracle."""
+    rng = np.random.default_rng(11)
+    sc = grt.config_scene("cornell-lucy", width=200, spp=1)
+    o = orc.OracleScene(sc.desc_ptr, sc.cam_ptr)
+    ij, sq, disk, tm = camera_batch(sc.width, sc.height, 60000, rng)
+    rays = o.camera_rays(ij, sq, disk, tm)
+    res, nodes = {}, {}
+    try:
+        for mode in (0, 1, 1):
+            ctx.set_option("bvh_device", mode)
+            ctx.load(sc)
+            st = ctx.stats()
+            assert st["bvh_on_device"] == mode and st["blas_depth"] > 3 and st["n_tris"] >= 280000
+            if mode:
+                assert st["ms_bvh_build"] > 0
+                assert nodes.setdefault(1, st["blas_nodes"]) == st["blas_nodes"], "device build is not reproducible"
+            h = ctx.trace_closest(rays)
+            if mode in res:
+                for k in ("entry", "prim", "t", "normal", "p", "front"):
+                    assert np.array_equal(h[k], res[mode][k]), f"two device builds disagree on {k}"
+            res[mode] = h
+        for k in ("entry", "prim", "t", "normal", "p", "front"):
+            assert np.array_equal(res[0][k], res[1][k]), f"host-built and device-built BVH disagree on {k}"
+    finally:
+        ctx.set_option("bvh_device", 1)
+    # small and degenerate meshes
+    b = grt.SceneBuilder(world_is_bvh=True)
+    m = b.material("lambertian", (0.5, 0.5, 0.5))
+    x = 0.0
+    for n_tri in (1, 2, 5, 33):
+        v0 = rng.random((n_tri, 3)) * 2 - 1 + np.array([x, 0, 0])
+        g = b.mesh_group(v0, v0 + rng.standard_normal((n_tri, 3)) * 0.7, v0 + rng.standard_normal((n_tri, 3)) * 0.7, m)
+        b.entry(grt.GEOM_MESH, g)
+        x += 3.0
+    same = np.tile(np.array([[x, -1.0, 0.0]]), (200, 1))           # 200 coincident triangles: every centroid in one bin
+    b.entry(grt.GEOM_MESH, b.mesh_group(same, same + np.array([2.0, 0, 0]), same + np.array([0, 2.0, 0.5]), m))
+    x += 3.0
+    v0 = rng.random((40, 3)) * 2 - 1 + np.array([x, 0, 0])
+    v1 = v0 + rng.standard_normal((40, 3)) * 0.7
+    v2 = v0 + rng.standard_normal((40, 3)) * 0.7
+    v2[::4] = v1[::4]                                              # zero-area triangles (never hit: |a| < 1e-8)
+    v1[1::8] = v0[1::8]
+    b.entry(grt.GEOM_MESH, b.mesh_group(v0, v1, v2, m), xforms=[("rotate_y", 20.0)])
+    built = b.build()
+    cam = grt.make_camera(64, 1.0, 1, 5, 60, (x / 2, 0, -14), (x / 2, 0, 0))
+    ctx.load((built, cam))
+    o2 = orc.OracleScene(built.desc_ptr, grt.C.pointer(cam))
+    n = 120000
+    org = np.stack([rng.random(n) * (x + 4) - 2, rng.standard_normal(n) * 2, np.full(n, -10.0)], axis=1)
+    tgt = np.stack([rng.random(n) * (x + 4) - 2, rng.random(n) * 3 - 1.5, rng.random(n) * 2 - 1], axis=1)
+    r2 = np.concatenate([org, tgt - org, np.zeros((n, 1))], axis=1)
+    ho = o2.trace_closest(r2)
+    assert_level1(ctx.trace_closest(r2), ho, "small / degenerate meshes, device build")
+    assert (ho["entry"] >= 0).mean() > 0.02
+
+
 def test_level1_axis_parallel_rays_cull(grt, orc, ctx):
     """Directions with one or two exactly-zero components (wall normal + an axis-aligned scatter direction: d = (0,0,-2))
     must give the reference's hits AND must still be culled by the float32 box test on the degenerate axes: a ray whose

@@ -1,5 +1,20 @@
 #!/bin/bash
-for v in default s192b5 s160b6 s224b4 s128b7; do
-  if [ $v = default ]; then unset RTX_B200_LIB; else export RTX_B200_LIB=$PWD/go-raytracing_b200/csrc/variants/librtx_$v.so; fi
-  timeout 300 python tools/gpu_perf.py cornell-lucy 64 2>&1 | tail -1
-done
+# One GPU-box round: parity tests, smoke, both bench arms, then the ncu launch list and one full capture of k_extend.
+# Usage (under gpurun): bash tools/gpu_round.sh <tag>     outputs land in gpurun_out/<tag>_*
+tag=${1:-rNN}
+out=gpurun_out
+mkdir -p $out
+python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $out/${tag}_pytest_gpu.log
+tail -3 $out/${tag}_pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $out/${tag}_smoke.log
+python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"; cat $out/${tag}_bench.json
+python bench.py --impl reference --steps 1 --warmup 1 > $out/${tag}_bench_ref.json 2>> $out/${tag}_bench.err; cat $out/${tag}_bench_ref.json
+if [ "$2" != "noncu" ]; then
+python bench.py --spp 4 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $out/${tag}_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $out/${tag}_launches.csv \
+    python bench.py --spp 4 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $out/${tag}_ncu_l.log 2>&1
+python tools/gpu_perf.py cornell-lucy 24 > $out/${tag}_plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_extend -s 40 -c 1 -f -o $out/${tag}_prof_extend \
+    python tools/gpu_perf.py cornell-lucy 24 > $out/${tag}_ncu.log 2>&1
+tail -2 $out/${tag}_ncu.log
+fi
