@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=20261018)
+    ap.add_argument("--bvh-host", action="store_true", help="build mesh hierarchies with the host builder (A/B against the device builder)")
+    ap.add_argument("--no-clock-sampler", action="store_true")
     return ap.parse_args()
 
 
@@ -168,6 +170,9 @@ def main():
     base, count = mg.slice_samples(spp, rank, world)
 
     ctx = grt.Context(local)
+    if args.bvh_host:
+        ctx.set_option("bvh_device", 0)
+    trace = os.environ.get("BENCH_TRACE") == "1"
     if args.pool:
         ctx.set_option("pool_paths", args.pool)
     stream = torch.cuda.Stream()             # a real (non-default) stream shared by torch, NCCL ordering and the library
@@ -192,9 +197,12 @@ def main():
             ctx.load(sc)                         # host -> device: flattened scene + camera; mesh BVHs are built on the device
             t_load = (time.perf_counter() - t0) * 1e3
             up = ctx.stats()
+        tt = [time.perf_counter()]
         ctx.clear()
+        tt.append(time.perf_counter())
         if count > 0:
             ctx.render_pass(count, depth, camera_max_depth=depth, seed=args.seed + i, sample_base=base)
+        tt.append(time.perf_counter())
         st = ctx.stats() if count > 0 else {"kernel_launches": 0, "extension_rays": 0, "shadow_rays": 0, "ms_extend": 0.0, "ms_total": 0.0}
         if e2e:
             st = dict(st, load_ms=t_load, ms_bvh_build=up["ms_bvh_build"], ms_scene_upload=up["ms_scene_upload"], bvh_on_device=up["bvh_on_device"])
@@ -202,6 +210,10 @@ def main():
         if rank == 0:
             nonlocal pix
             pix = ctx.resolve_rgba8(spp, pix)    # divide by the TOTAL spp, gamma, clamp, pack; device -> host
+        tt.append(time.perf_counter())
+        if trace:
+            print(f"[bench rank {rank}] step {i}: load {t_load:.1f} clear {(tt[1]-tt[0])*1e3:.1f} render {(tt[2]-tt[1])*1e3:.1f} (device {st['ms_total']:.1f}) "
+                  f"reduce+resolve {(tt[3]-tt[2])*1e3:.1f} ms", file=sys.stderr, flush=True)
         return st
 
     def timed(n_steps, first, e2e):
@@ -225,7 +237,7 @@ def main():
     for i in range(args.warmup):
         step(-1 - i)
     clocks = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not args.no_clock_sampler:
         clocks.start()
     dev_ms, wall, stats = timed(args.steps, 0, False)
     clk = clocks.stop() if rank == 0 else None

@@ -24,8 +24,27 @@ struct DevBuf {
     size_t bytes = 0;
 };
 
+struct Slab {   // grow-only device allocation, bump-allocated afresh by every use: hot calls never cudaMalloc / cudaFree
+    char* base = nullptr;
+    size_t cap = 0, off = 0;
+    cudaError_t reserve(size_t bytes) {
+        off = 0;
+        if (bytes <= cap) return cudaSuccess;
+        if (base) cudaFree(base);
+        base = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMalloc((void**)&base, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    char* take(size_t bytes) { char* p = base + off; off += (bytes + 255) & ~(size_t)255; return off <= cap ? p : nullptr; }
+    void release() { if (base) cudaFree(base); base = nullptr; cap = off = 0; }
+};
+
 struct rtx_ctx {
     int device = 0;
+    Slab scene_slab, work_slab;   // the uploaded scene / working memory of rtx_scene_upload (device BVH build)
+    uchar4* rgba_dev = nullptr;   // resolve target, sized with the accumulation buffer
     cudaStream_t stream = nullptr;      // stream in use
     cudaStream_t own_stream = nullptr;  // created by rtx_create
     std::string err;
@@ -95,7 +114,7 @@ static int32_t upload(rtx_ctx* ctx, const std::vector<T>& v, const T** out, bool
         if (rc_ != RTX_OK) return rc_;                                    \
     } while (0)
 
-static void free_scene(rtx_ctx* ctx) {
+static void free_scene(rtx_ctx* ctx) {   // the slabs are kept for the next upload (grow-only); rtx_destroy releases them
     for (void* p : ctx->scene_allocs) cudaFree(p);
     ctx->scene_allocs.clear();
     ctx->have_scene = false;
@@ -202,6 +221,8 @@ int32_t rtx_destroy(rtx_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     free_scene(ctx);
     free_pool(ctx);
+    ctx->scene_slab.release(); ctx->work_slab.release();
+    if (ctx->rgba_dev) cudaFree(ctx->rgba_dev);
     if (ctx->accum) cudaFree(ctx->accum);
     if (ctx->accum_sq) cudaFree(ctx->accum_sq);
     if (ctx->ctl) cudaFree(ctx->ctl);
@@ -385,7 +406,7 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
 
     // ---- triangles: meshes are permuted into BLAS leaf order; loose triangles (world entries / Box-list items) follow
     std::vector<Node4> nodes;                       // host-built nodes: every BLAS with the host builder, and always the TLAS
-    std::vector<double> tris, triNrm;               // host-built triangle records: meshes (host builder only), then loose ones
+    std::vector<double> tris;                       // host-built triangle records: meshes (host builder only), then loose ones
     std::vector<int4> triInfo;
     int meshTotal = 0;
     for (int g = 0; g < d->n_groups; g++)
@@ -407,9 +428,7 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
         for (int a = 0; a < 3; a++) tris.push_back(v0[a]);
         for (int a = 0; a < 3; a++) tris.push_back(e1[a]);
         for (int a = 0; a < 3; a++) tris.push_back(e2[a]);
-        tris.push_back(0);
-        for (int a = 0; a < 3; a++) triNrm.push_back(n[a]);
-        triNrm.push_back(0);
+        for (int a = 0; a < 3; a++) tris.push_back(n[a]);
         triInfo.push_back(make_int4(localId, d->tri_mat[ti], rank, 0));
     };
     std::vector<int> groupRoot(d->n_groups, -1), groupTriBase(d->n_groups, 0);
@@ -421,17 +440,32 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     // device-built pieces (deviceBuild only): one node buffer per mesh, triangle records for all meshes
     struct DevBlas { Node4* nodes; int n; };
     std::vector<DevBlas> devBlas;
-    Scratch buildScratch;   // freed when the upload returns
-    double *dMeshTris = nullptr, *dTriNrm = nullptr;
-    int4* dTriInfo = nullptr;
+    double* dMeshTris = nullptr;
+    int4* dTriInfo = nullptr;   // mesh triangles only (work slab); copied into the scene slab at the end
     cudaEvent_t evB0 = nullptr, evB1 = nullptr;
     if (deviceBuild) {
-        // the flattened triangle arrays go to the device as they are; bounds, hierarchy and leaf-ordered records are built there
-        double *dV0, *dV1, *dV2; int *dMat, *dRank;
-        CU(buildScratch.in(&dV0, d->tri_v0, (size_t)3 * d->n_tris, ctx->stream));
-        CU(buildScratch.in(&dV1, d->tri_v1, (size_t)3 * d->n_tris, ctx->stream));
-        CU(buildScratch.in(&dV2, d->tri_v2, (size_t)3 * d->n_tris, ctx->stream));
-        CU(buildScratch.in(&dMat, d->tri_mat, (size_t)d->n_tris, ctx->stream));
+        // The flattened triangle arrays go to the device as they are; bounds, hierarchy and leaf-ordered records are built there.
+        // All working memory is carved from one grow-only slab: repeated uploads never touch cudaMalloc / cudaFree.
+        auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t nT = (size_t)d->n_tris;
+        size_t buildBytes = 0, nodeBytes = 0;
+        for (int g = 0; g < d->n_groups; g++) {
+            if (d->group_kind[g] != RTX_GEOM_MESH || d->group_count[g] == 0) continue;
+            size_t sb = 0;
+            const char* w = "";
+            rtxgpu::build_blas(nullptr, nullptr, nullptr, nullptr, nullptr, d->group_count[g], ctx->blas_leaf, 0, 0, nullptr, nullptr, nullptr, ctx->stream, nullptr, &w, nullptr, &sb);
+            buildBytes = std::max(buildBytes, sb);
+            nodeBytes += pad(((size_t)d->group_count[g] + 1) * sizeof(Node4));
+        }
+        const size_t workTotal = 3 * pad(3 * nT * sizeof(double)) + 2 * pad(nT * sizeof(int)) + pad((size_t)RTX_TRI_D * meshTotal * sizeof(double)) +
+                                 pad((size_t)meshTotal * sizeof(int4)) + nodeBytes + pad(buildBytes) + 4096;
+        CU(ctx->work_slab.reserve(workTotal));
+        Slab& W = ctx->work_slab;
+        double *dV0 = (double*)W.take(3 * nT * sizeof(double)), *dV1 = (double*)W.take(3 * nT * sizeof(double)), *dV2 = (double*)W.take(3 * nT * sizeof(double));
+        int *dMat = (int*)W.take(nT * sizeof(int)), *dRank = (int*)W.take(nT * sizeof(int));
+        dMeshTris = (double*)W.take((size_t)RTX_TRI_D * meshTotal * sizeof(double));
+        dTriInfo = (int4*)W.take((size_t)meshTotal * sizeof(int4));
+        char* buildScratch = W.take(buildBytes);
         std::vector<int> rankAll;
         if (!d->tri_rank) {   // no ranks from the caller's Go tree: canonical ones (host restatement of rt/bvh.go's order; exact-tie resolution only)
             rankAll.assign(d->n_tris, 0);
@@ -444,14 +478,18 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
                 for (int k = 0; k < count; k++) rankAll[begin + k] = r[k];
             }
         }
-        CU(buildScratch.in(&dRank, d->tri_rank ? d->tri_rank : rankAll.data(), (size_t)d->n_tris, ctx->stream));
-        CU(cudaMalloc((void**)&dMeshTris, std::max<size_t>((size_t)10 * meshTotal * sizeof(double), 16)));
-        buildScratch.ptrs.push_back(dMeshTris);
-        CU(cudaMalloc((void**)&dTriNrm, std::max<size_t>((size_t)4 * totalTris * sizeof(double), 16)));
-        ctx->scene_allocs.push_back(dTriNrm);
-        CU(cudaMalloc((void**)&dTriInfo, std::max<size_t>((size_t)totalTris * sizeof(int4), 16)));
-        ctx->scene_allocs.push_back(dTriInfo);
-        CU(cudaEventCreate(&evB0)); CU(cudaEventCreate(&evB1));
+        CU(cudaMemcpyAsync(dV0, d->tri_v0, 3 * nT * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(dV1, d->tri_v1, 3 * nT * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(dV2, d->tri_v2, 3 * nT * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(dMat, d->tri_mat, nT * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(dRank, d->tri_rank ? d->tri_rank : rankAll.data(), nT * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));   // rankAll is a local
+        while (ctx->events.size() < 4) {
+            cudaEvent_t ev;
+            CU(cudaEventCreate(&ev));
+            ctx->events.push_back(ev);
+        }
+        evB0 = ctx->events[2]; evB1 = ctx->events[3];
         CU(cudaEventRecord(evB0, ctx->stream));
         int base = 0;
         for (int g = 0; g < d->n_groups; g++) {
@@ -459,13 +497,13 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
             const int begin = d->group_begin[g], count = d->group_count[g];
             groupTriBase[g] = base;
             if (count == 0) continue;
-            Node4* dn = nullptr;
-            CU(cudaMalloc((void**)&dn, ((size_t)count + 1) * sizeof(Node4)));
-            buildScratch.ptrs.push_back(dn);
+            Node4* dn = (Node4*)W.take(((size_t)count + 1) * sizeof(Node4));
+            if (!dn || !buildScratch) return fail(ctx, RTX_ERR_CUDA, "device BVH build: work slab exhausted");
             rtxgpu::BlasResult br;
             const char* what = "";
+            size_t sb = buildBytes;
             cudaError_t be = rtxgpu::build_blas(dV0 + 3 * (size_t)begin, dV1 + 3 * (size_t)begin, dV2 + 3 * (size_t)begin, dMat + begin, dRank + begin, count, ctx->blas_leaf,
-                                                (int)blasNodes, base, dn, dMeshTris + 10 * (size_t)base, dTriNrm + 4 * (size_t)base, dTriInfo + base, ctx->stream, &br, &what);
+                                                (int)blasNodes, base, dn, dMeshTris + RTX_TRI_D * (size_t)base, dTriInfo + base, ctx->stream, &br, &what, buildScratch, &sb);
             if (be != cudaSuccess) return fail(ctx, RTX_ERR_CUDA, "device BVH build of mesh group %d failed: %s (%s)", g, what, cudaGetErrorString(be));
             groupRoot[g] = (int)blasNodes;   // local node 0 of this mesh
             devBlas.push_back({dn, br.n_nodes});
@@ -642,52 +680,61 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     ctx->env_total = totalPower;
 
     // ---- upload
-    {   // The geometry every ray fetches (nodes, triangles, spheres, quads) goes into ONE allocation so that a single L2
-        // access-policy window can keep it resident against the path pool streaming through the same cache (see render).
+    {   // Everything the kernels read lives in ONE grow-only slab. The geometry every ray fetches (nodes, triangles, spheres,
+        // quads) comes first and contiguous, so that a single L2 access-policy window can cover it (see rtx_render_pass).
         auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
-        const size_t bNodes = pad(nodes.size() * sizeof(Node4)), bTris = pad((size_t)totalTris * 10 * sizeof(double)), bSph = pad(sph.size() * sizeof(double)),
-                     bQuads = pad(quads.size() * sizeof(double));
-        const size_t total = std::max<size_t>(bNodes + bTris + bSph + bQuads, 256);
-        char* base = nullptr;
-        CU(cudaMalloc((void**)&base, total));
-        ctx->scene_allocs.push_back(base);
-        ctx->geom_arena = base; ctx->geom_bytes = total; ctx->window_set = false;
-        auto put = [&](const void* src, size_t bytes, size_t off) {
-            return bytes ? cudaMemcpyAsync(base + off, src, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
+        struct Item { const void* src; size_t bytes; const void** field; };
+        std::vector<Item> items;
+        auto want = [&](const void* src, size_t bytes, const void** field) { items.push_back({src, bytes, field}); };
+#define WANT(vec, field) want((vec).data(), (vec).size() * sizeof((vec)[0]), (const void**)&(field))
+        const size_t bNodes = pad(nodes.size() * sizeof(Node4)), bTris = pad((size_t)totalTris * RTX_TRI_D * sizeof(double)), bSph = pad(sph.size() * sizeof(double)),
+                     bQuads = pad(quads.size() * sizeof(double)), bInfo = pad((size_t)totalTris * sizeof(int4));
+        const size_t geom = std::max<size_t>(bNodes + bTris + bSph + bQuads, 256);
+        WANT(entries, S.entries); WANT(unbounded, S.unbounded); WANT(sphMat, S.sph_mat); WANT(quadMat, S.quad_mat); WANT(planes, S.planes); WANT(planeMat, S.plane_mat);
+        WANT(listItems, S.list_items); WANT(xfs, S.xforms); WANT(xfCanon, S.xf_canon); WANT(vols, S.volumes); WANT(mats, S.mats); WANT(texs, S.texs);
+        WANT(lights, S.light_quads); WANT(envTex, S.env_tex); WANT(marg, S.env_marg); WANT(cond, S.env_cond); WANT(pdf, S.env_pdf);
+#undef WANT
+        size_t total = geom + bInfo;
+        for (const Item& it : items) total += pad(std::max<size_t>(it.bytes, 16));
+        CU(ctx->scene_slab.reserve(total));
+        Slab& L = ctx->scene_slab;
+        char* base = L.take(geom);
+        ctx->geom_arena = base; ctx->geom_bytes = geom; ctx->window_set = false;
+        auto put = [&](const void* src, size_t bytes, char* dst) {
+            return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
         };
+        int4* infoDev = (int4*)L.take(bInfo);
         if (deviceBuild) {   // device-built BLAS nodes and mesh triangles move device-to-device; the host adds the TLAS and the loose triangles
             size_t off = 0;
             for (const DevBlas& db : devBlas) {
                 CU(cudaMemcpyAsync(base + off, db.nodes, (size_t)db.n * sizeof(Node4), cudaMemcpyDeviceToDevice, ctx->stream));
                 off += (size_t)db.n * sizeof(Node4);
             }
-            CU(put(nodes.data() + blasNodes, (nodes.size() - blasNodes) * sizeof(Node4), off));
-            CU(cudaMemcpyAsync(base + bNodes, dMeshTris, (size_t)meshTotal * 10 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-            CU(put(tris.data(), tris.size() * sizeof(double), bNodes + (size_t)meshTotal * 10 * sizeof(double)));
-            if (!triNrm.empty()) CU(cudaMemcpyAsync(dTriNrm + 4 * (size_t)meshTotal, triNrm.data(), triNrm.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-            if (!triInfo.empty()) CU(cudaMemcpyAsync(dTriInfo + meshTotal, triInfo.data(), triInfo.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
-            S.tri_nrm = dTriNrm; S.tri_info = dTriInfo;
+            CU(put(nodes.data() + blasNodes, (nodes.size() - blasNodes) * sizeof(Node4), base + off));
+            CU(cudaMemcpyAsync(base + bNodes, dMeshTris, (size_t)meshTotal * RTX_TRI_D * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            CU(put(tris.data(), tris.size() * sizeof(double), base + bNodes + (size_t)meshTotal * RTX_TRI_D * sizeof(double)));
+            CU(cudaMemcpyAsync(infoDev, dTriInfo, (size_t)meshTotal * sizeof(int4), cudaMemcpyDeviceToDevice, ctx->stream));
+            CU(put(triInfo.data(), triInfo.size() * sizeof(int4), (char*)(infoDev + meshTotal)));
         } else {
-            CU(put(nodes.data(), nodes.size() * sizeof(Node4), 0));
-            CU(put(tris.data(), tris.size() * sizeof(double), bNodes));
-            UP(triNrm, S.tri_nrm); UP(triInfo, S.tri_info);
+            CU(put(nodes.data(), nodes.size() * sizeof(Node4), base));
+            CU(put(tris.data(), tris.size() * sizeof(double), base + bNodes));
+            CU(put(triInfo.data(), triInfo.size() * sizeof(int4), (char*)infoDev));
         }
-        CU(put(sph.data(), sph.size() * sizeof(double), bNodes + bTris));
-        CU(put(quads.data(), quads.size() * sizeof(double), bNodes + bTris + bSph));
+        CU(put(sph.data(), sph.size() * sizeof(double), base + bNodes + bTris));
+        CU(put(quads.data(), quads.size() * sizeof(double), base + bNodes + bTris + bSph));
         S.nodes = (const float4*)base;
         S.tris = (const double*)(base + bNodes);
         S.spheres = (const double*)(base + bNodes + bTris);
         S.quads = (const double*)(base + bNodes + bTris + bSph);
+        S.tri_info = infoDev;
+        for (const Item& it : items) {
+            char* dst = L.take(std::max<size_t>(it.bytes, 16));
+            if (!dst) return fail(ctx, RTX_ERR_CUDA, "scene slab exhausted");
+            CU(put(it.src, it.bytes, dst));
+            *it.field = dst;
+        }
         (void)hostMeshTris;
     }
-    UP(entries, S.entries);
-    UP(unbounded, S.unbounded);
-    UP(sphMat, S.sph_mat);
-    UP(quadMat, S.quad_mat);
-    UP(planes, S.planes); UP(planeMat, S.plane_mat);
-    UP(listItems, S.list_items);
-    UP(xfs, S.xforms); UP(xfCanon, S.xf_canon); UP(vols, S.volumes); UP(mats, S.mats); UP(texs, S.texs); UP(lights, S.light_quads);
-    UP(envTex, S.env_tex); UP(marg, S.env_marg); UP(cond, S.env_cond); UP(pdf, S.env_pdf);
     S.tlas_root = tlasRoot;
     S.n_entries = d->n_entries;
     S.n_unbounded = (int)unbounded.size();
@@ -699,7 +746,6 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
         float ms = 0;
         cudaEventElapsedTime(&ms, evB0, evB1);
         ctx->ms_upload_blas = ms;
-        cudaEventDestroy(evB0); cudaEventDestroy(evB1);
     }
     if (getenv("RTX_DEBUG_BATCH"))
         fprintf(stderr, "[rtx] scene upload: %d mesh triangles, %u BLAS nodes (depth %d, %s build %.2f ms), %u TLAS nodes\n", meshTotal, blasNodes, maxBlasDepth,
@@ -777,7 +823,9 @@ int32_t rtx_camera_set(rtx_ctx* ctx, const rtx_camera_desc* c) {
         CU(cudaStreamSynchronize(ctx->stream));
         if (ctx->accum) cudaFree(ctx->accum);
         if (ctx->accum_sq) cudaFree(ctx->accum_sq);
-        ctx->accum = ctx->accum_sq = nullptr;
+        if (ctx->rgba_dev) cudaFree(ctx->rgba_dev);
+        ctx->accum = ctx->accum_sq = nullptr; ctx->rgba_dev = nullptr;
+        CU(cudaMalloc((void**)&ctx->rgba_dev, (size_t)W * H * sizeof(uchar4)));
         size_t bytes = (size_t)W * H * sizeof(float4);
         CU(cudaMalloc((void**)&ctx->accum, bytes));
         CU(cudaMalloc((void**)&ctx->accum_sq, bytes));
@@ -980,12 +1028,10 @@ int32_t rtx_resolve_rgba8(rtx_ctx* ctx, int32_t total_spp, uint8_t* pix, int64_t
     if (nbytes != (int64_t)4 * npix) return fail(ctx, RTX_ERR_INVALID, "rtx_resolve_rgba8: nbytes %lld != 4*W*H = %d", (long long)nbytes, 4 * npix);
     if (total_spp <= 0) return fail(ctx, RTX_ERR_INVALID, "rtx_resolve_rgba8: total_spp must be positive");
     CU(cudaSetDevice(ctx->device));
-    uchar4* dev = nullptr;
-    CU(cudaMalloc((void**)&dev, (size_t)npix * 4));
+    uchar4* dev = ctx->rgba_dev;   // sized by rtx_camera_set: no allocation on the per-pass path
     k_resolve_rgba8<<<(npix + 255) / 256, 256, 0, ctx->stream>>>(ctx->accum, npix, 1.0 / (double)total_spp, dev);
     cudaError_t e = cudaMemcpyAsync(pix, dev, (size_t)npix * 4, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(dev);
     if (e != cudaSuccess) return fail(ctx, RTX_ERR_CUDA, "rtx_resolve_rgba8: %s", cudaGetErrorString(e));
     return RTX_OK;
 }

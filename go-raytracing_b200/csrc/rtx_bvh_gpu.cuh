@@ -12,7 +12,7 @@
 //                     k_split    one thread per node sweeps the bins, picks (axis, plane), creates the two children
 //                     k_flags + exclusive scan + k_scatter    stable partition of every node's triangle range
 //   per wide level    k_collapse_count + exclusive scan + k_collapse_emit    binary tree -> Node4 records, breadth-first numbering
-//   k_tri_emit        triangle records (v0, e1, e2 / unit normal / info) in leaf order, float64, reference operation order
+//   k_tri_emit        triangle records (v0, e1, e2, unit normal / info) in leaf order, float64, reference operation order
 //
 // Determinism: bins are filled with min / max / integer-add atomics (order-independent), partitions and wide-node
 // numbering use exclusive scans, so the tree TOPOLOGY, the leaf contents and the node layout are reproducible; only the
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(128) k_collapse_emit(BNodes N, const int* item
 
 // ---- triangle records in leaf order (rt/triangle.go:17-25: e1, e2, unit normal; same float64 operation order as the host path) ----
 __global__ void __launch_bounds__(256) k_tri_emit(const double* v0, const double* v1, const double* v2, const int* mat, const int* rank, const int* idx, int n,
-                                                 double* tris, double* nrm, int4* info) {
+                                                 double* tris, int4* info) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const int s = idx[p];
@@ -377,10 +377,9 @@ __global__ void __launch_bounds__(256) k_tri_emit(const double* v0, const double
     double nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
     const double l = sqrt(nx * nx + ny * ny + nz * nz);
     if (l != 0) { const double inv = 1 / l; nx = inv * nx; ny = inv * ny; nz = inv * nz; }
-    double2* t = reinterpret_cast<double2*>(tris + 10 * (size_t)p);
-    t[0] = make_double2(a0, a1); t[1] = make_double2(a2, e1x); t[2] = make_double2(e1y, e1z); t[3] = make_double2(e2x, e2y); t[4] = make_double2(e2z, 0.0);
-    double2* q = reinterpret_cast<double2*>(nrm + 4 * (size_t)p);
-    q[0] = make_double2(nx, ny); q[1] = make_double2(nz, 0.0);
+    double2* t = reinterpret_cast<double2*>(tris + 12 * (size_t)p);   // RTX_TRI_D doubles: v0, e1, e2, n
+    t[0] = make_double2(a0, a1); t[1] = make_double2(a2, e1x); t[2] = make_double2(e1y, e1z); t[3] = make_double2(e2x, e2y); t[4] = make_double2(e2z, nx);
+    t[5] = make_double2(ny, nz);
     info[p] = make_int4(s, mat[s], rank[s], 0);
 }
 
@@ -392,13 +391,14 @@ struct BlasResult {
 };
 
 // Builds the BLAS of one mesh. Device inputs: v0/v1/v2 [3n] float64, mat/rank [n]. Device outputs: nodes_out [>= n] Node4 (local
-// index 0 = root), tris/nrm/info for the n triangles in leaf order (written at the pointers given: the caller passes
+// index 0 = root), tris/info for the n triangles in leaf order (written at the pointers given: the caller passes
 // base + tri_base offsets). Leaf codes carry tri_base, internal links node_base. Returns cudaSuccess or the failing call's error.
+// The working memory comes from the caller (no cudaMalloc / cudaFree here: they serialise against the whole driver): call once
+// with scratch == nullptr to get the size in *scratch_bytes, then with a buffer of at least that size.
 static inline cudaError_t build_blas(const double* v0, const double* v1, const double* v2, const int* mat, const int* rank, int n, int maxLeaf, int node_base,
-                                     int tri_base, rtxbvh::Node4* nodes_out, double* tris, double* nrm, int4* info, cudaStream_t st, BlasResult* res,
-                                     const char** what) {
-#define RTX_G(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { *what = #call; cudaFree(scratch); return e_; } } while (0)
-    char* scratch = nullptr;
+                                     int tri_base, rtxbvh::Node4* nodes_out, double* tris, int4* info, cudaStream_t st, BlasResult* res,
+                                     const char** what, char* scratch, size_t* scratch_bytes) {
+#define RTX_G(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { *what = #call; return e_; } } while (0)
     *what = "";
     const size_t N2 = (size_t)2 * n + 2;                               // binary nodes
     const int maxActive = n / (maxLeaf + 1) + 2;                       // nodes of one level that still split
@@ -413,7 +413,8 @@ static inline cudaError_t build_blas(const double* v0, const double* v1, const d
     const size_t oItA = carve((size_t)n * sizeof(int)), oItB = carve((size_t)n * sizeof(int)), oIoA = carve((size_t)n * sizeof(int)), oIoB = carve((size_t)n * sizeof(int));
     const size_t oKids = carve((size_t)n * sizeof(int4)), oCnt = carve((size_t)(n + 1) * sizeof(int)), oCoff = carve((size_t)(n + 1) * sizeof(int));
     const size_t oCtr = carve(sizeof(Ctr));
-    RTX_G(cudaMalloc((void**)&scratch, off));
+    if (!scratch) { *scratch_bytes = off; return cudaSuccess; }   // sizing call
+    if (*scratch_bytes < off) { *what = "build scratch too small"; return cudaErrorInvalidValue; }
     float4* b0[2] = {(float4*)(scratch + oB0a), (float4*)(scratch + oB0b)};
     float2* b1[2] = {(float2*)(scratch + oB1a), (float2*)(scratch + oB1b)};
     int* idx[2] = {(int*)(scratch + oIdxA), (int*)(scratch + oIdxB)};
@@ -438,9 +439,9 @@ static inline cudaError_t build_blas(const double* v0, const double* v1, const d
     for (int a = 0; a < 3; a++) { res->lo[a] = o2d_bits(h.mesh_lo[a]); res->hi[a] = o2d_bits(h.mesh_hi[a]); }
     int cur = 0, lb = 0, le = 1, levels = 0;
     while (h.active > 0) {
-        if (++levels > 128) { *what = "binary BVH deeper than 128 levels"; cudaFree(scratch); return cudaErrorUnknown; }
+        if (++levels > 128) { *what = "binary BVH deeper than 128 levels"; return cudaErrorUnknown; }
         const int nlev = le - lb;
-        if (nlev > maxActive * 2 + 2) { *what = "level wider than the bin scratch"; cudaFree(scratch); return cudaErrorUnknown; }
+        if (nlev > maxActive * 2 + 2) { *what = "level wider than the bin scratch"; return cudaErrorUnknown; }
         // bins are indexed by (node - lb); only splitting nodes use theirs
         const size_t words = (size_t)nlev * NODE_BIN_WORDS;
         k_bins_clear<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(bins, nlev);
@@ -474,10 +475,9 @@ static inline cudaError_t build_blas(const double* v0, const double* v1, const d
         it ^= 1;
     }
     res->n_nodes = total; res->depth = depth;
-    k_tri_emit<<<gridN, 256, 0, st>>>(v0, v1, v2, mat, rank, idx[cur], n, tris, nrm, info);
+    k_tri_emit<<<gridN, 256, 0, st>>>(v0, v1, v2, mat, rank, idx[cur], n, tris, info);
     RTX_G(cudaGetLastError());
     RTX_G(cudaStreamSynchronize(st));
-    cudaFree(scratch);
     return cudaSuccess;
 #undef RTX_G
 }

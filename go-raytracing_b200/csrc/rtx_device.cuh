@@ -13,6 +13,33 @@
 #include "../../include/rtx_b200.h"
 
 #define RTX_STACK_SIZE 48   /* checked against the built hierarchy at upload (rtx_api.cu) */
+#define RTX_TRI_D 12        /* doubles per triangle record */
+
+// ---- 256-bit global loads / stores (sm_100: LDG.E.256 / STG.E.256) --------------------------------------------------------
+// Every lane of a trace warp fetches from a different 128-byte line, and the L1 accepts one line per cycle per SM whatever
+// the access width: the cost of fetching a node or a primitive is its NUMBER OF LOAD INSTRUCTIONS. Blackwell's 32-byte
+// per-lane accesses halve it (node: 4 instead of 7, triangle: 3 instead of 5, ray: 2 instead of 4). Pointers must be 32-byte aligned.
+struct F8 { float4 a, b; };
+struct D4 { double x, y, z, w; };
+__device__ __forceinline__ F8 ldg256f(const void* p) {   // read-only data (scene)
+    F8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ D4 ldg256d(const void* p) {   // read-only data (scene)
+    D4 r;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ D4 ld256d(const void* p) {    // data other kernels of the pass write (path pool)
+    D4 r;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st256d(void* p, double x, double y, double z, double w) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x), "d"(y), "d"(z), "d"(w) : "memory");
+}
 #define RTX_INF_D (__longlong_as_double(0x7ff0000000000000LL))
 
 struct DEntry {      // 32 B, one per world entry (rt/hittable_list.go:16 insertion order)
@@ -52,8 +79,7 @@ struct DevScene {
     const int* sph_mat;
     const double* quads;    // 16 doubles: Q, u, v, w, normal, D (rt/quad.go:16-33)
     const int* quad_mat;
-    const double* tris;     // 10 doubles (80 B, 5 x LDG.128): v0, e1 = v1-v0, e2 = v2-v0, -
-    const double* tri_nrm;  // 4 doubles: unit normal (rt/triangle.go:25), -
+    const double* tris;     // 12 doubles (96 B, 3 x LDG.256): v0, e1 = v1-v0, e2 = v2-v0, unit normal (rt/triangle.go:19-25)
     const int4* tri_info;   // x: primitive id inside its geometry (face order), y: material, z: rank, w: -
     const double* planes;   // 8 doubles: point, normal, -,-
     const int* plane_mat;
@@ -145,14 +171,13 @@ __device__ __forceinline__ void xform_ray_chain(const DevScene& S, const DEntry&
 __device__ __forceinline__ void xform_ray(const DevScene& S, int ei, const DEntry& e, RayD& r) {
     if (e.xf_count == 0) return;
     if (e.xf_count & RTX_XF_CANON) {
-        const double2* q = reinterpret_cast<const double2*>(S.xf_canon + 8 * (size_t)ei);
-        const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);  // (offx,offy) (offz,sin) (cos,invx) (invy,invz)
-        const double tx = r.ox - a.x, ty = r.oy - a.y, tz = r.oz - b.x;
-        const double sn = b.y, cs = c.x;
+        const D4 a = ldg256d(S.xf_canon + 8 * (size_t)ei), b = ldg256d(S.xf_canon + 8 * (size_t)ei + 4);  // (offx,offy,offz,sin) (cos,invx,invy,invz)
+        const double tx = r.ox - a.x, ty = r.oy - a.y, tz = r.oz - a.z;
+        const double sn = a.w, cs = b.x;
         const double ox = cs * tx - sn * tz, oz = sn * tx + cs * tz;
         const double dx = cs * r.dx - sn * r.dz, dz = sn * r.dx + cs * r.dz;
-        r.ox = ox * c.y; r.oy = ty * d.x; r.oz = oz * d.y;
-        r.dx = dx * c.y; r.dy = r.dy * d.x; r.dz = dz * d.y;
+        r.ox = ox * b.y; r.oy = ty * b.z; r.oz = oz * b.w;
+        r.dx = dx * b.y; r.dy = r.dy * b.z; r.dz = dz * b.w;
         return;
     }
     xform_ray_chain(S, e, r);
@@ -198,25 +223,26 @@ __device__ __forceinline__ double isect_sphere(const double* s, const RayD& r, d
 }
 // rt/quad.go:44-84 (closed interval is applied by the caller)
 __device__ __forceinline__ double isect_quad(const double* q, const RayD& r, double tmin, double tmax, double* uv) {
-    D3 n = ld3(q + 12), o = d3(r.ox, r.oy, r.oz), d = d3(r.dx, r.dy, r.dz);
+    const D4 q3 = ldg256d(q + 12);   // normal, D
+    D3 n = d3(q3.x, q3.y, q3.z), o = d3(r.ox, r.oy, r.oz), d = d3(r.dx, r.dy, r.dz);
     double denom = dot(n, d);
     if (fabs(denom) < 1e-8) return RTX_NAN_D;
-    double t = (q[15] - dot(n, o)) / denom;
+    double t = (q3.w - dot(n, o)) / denom;
     if (!(tmin <= t && t <= tmax)) return RTX_NAN_D;
+    const D4 q0 = ldg256d(q), q1 = ldg256d(q + 4), q2 = ldg256d(q + 8);   // Q u | u v | v w
     D3 P = add(o, scale(d, t));
-    D3 pl = sub(P, ld3(q));
-    D3 w = ld3(q + 9);
-    double alpha = dot(w, cross(pl, ld3(q + 6)));
-    double beta = dot(w, cross(ld3(q + 3), pl));
+    D3 pl = sub(P, d3(q0.x, q0.y, q0.z));
+    D3 w = d3(q2.y, q2.z, q2.w);
+    double alpha = dot(w, cross(pl, d3(q1.z, q1.w, q2.x)));
+    double beta = dot(w, cross(d3(q0.w, q1.x, q1.y), pl));
     if (!(0.0 <= alpha && alpha <= 1.0) || !(0.0 <= beta && beta <= 1.0)) return RTX_NAN_D;
     if (uv) { uv[0] = alpha; uv[1] = beta; }
     return t;
 }
 // rt/triangle.go:57-104 Möller–Trumbore; e1/e2 are the same float64 values the reference recomputes per call.
 __device__ __forceinline__ double isect_tri(const double* tp, const RayD& r, double* uv) {
-    const double2* p2 = reinterpret_cast<const double2*>(tp);
-    double2 a0 = __ldg(p2), a1 = __ldg(p2 + 1), a2 = __ldg(p2 + 2), a3 = __ldg(p2 + 3), a4 = __ldg(p2 + 4);
-    D3 v0 = d3(a0.x, a0.y, a1.x), e1 = d3(a1.y, a2.x, a2.y), e2 = d3(a3.x, a3.y, a4.x);
+    const D4 a0 = ldg256d(tp), a1 = ldg256d(tp + 4), a2 = ldg256d(tp + 8);   // v0 e1.x | e1.yz e2.xy | e2.z n
+    D3 v0 = d3(a0.x, a0.y, a0.z), e1 = d3(a0.w, a1.x, a1.y), e2 = d3(a1.z, a1.w, a2.x);
     D3 o = d3(r.ox, r.oy, r.oz), d = d3(r.dx, r.dy, r.dz);
     D3 h = cross(d, e2);
     double a = dot(e1, h);
@@ -260,7 +286,7 @@ __device__ __forceinline__ double isect_prim(const DevScene& S, int kind, int id
     const double* p;
     if (kind == RTX_GEOM_SPHERE) { if (tc) tc->spheres++; p = S.spheres + 8 * (size_t)idx; }
     else if (kind == RTX_GEOM_QUAD) { if (tc) tc->quads++; p = S.quads + 16 * (size_t)idx; }
-    else if (kind == RTX_GEOM_TRIANGLE) { if (tc) tc->tris++; p = S.tris + 10 * (size_t)idx; }
+    else if (kind == RTX_GEOM_TRIANGLE) { if (tc) tc->tris++; p = S.tris + RTX_TRI_D * (size_t)idx; }
     else { if (tc) tc->planes++; p = S.planes + 8 * (size_t)idx; }
     return isect_prim_ool(kind, p, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tm, tmin, tmax);
 }
@@ -289,13 +315,18 @@ __device__ __forceinline__ void make_rayf(const RayD& r, RayF& f) {
 }
 
 // One 4-wide node (128 B: {lox,hix,loy,hiy,loz,hiz} float4 pairs, child int4, pad): conservative entry distances
-// (inf = culled) of the 4 children. The near / far planes are picked by address (per-ray byte offsets), not by selects.
+// (inf = culled) of the 4 children. Three 256-bit loads bring the {lo, hi} pairs, one 128-bit load the child links.
 __device__ __forceinline__ void node_test(const float4* __restrict__ nodes, int node, const RayF& f, float tmin, float tmax, float d[4], int c[4]) {
     const char* nb = reinterpret_cast<const char*>(nodes) + (size_t)node * 128;
-    const float4 nx = __ldg(reinterpret_cast<const float4*>(nb + f.offx)), fx = __ldg(reinterpret_cast<const float4*>(nb + 16 - f.offx));
-    const float4 ny = __ldg(reinterpret_cast<const float4*>(nb + 32 + f.offy)), fy = __ldg(reinterpret_cast<const float4*>(nb + 48 - f.offy));
-    const float4 nz = __ldg(reinterpret_cast<const float4*>(nb + 64 + f.offz)), fz = __ldg(reinterpret_cast<const float4*>(nb + 80 - f.offz));
-    const int4 ch = __ldg(reinterpret_cast<const int4*>(nb + 96));
+    const F8 X = ldg256f(nb), Y = ldg256f(nb + 32), Z = ldg256f(nb + 64);   // {lo, hi} of the four children, per axis
+    int4 ch;
+    asm("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(ch.x), "=r"(ch.y), "=r"(ch.z), "=r"(ch.w) : "l"(nb + 96));
+    const bool sx = f.offx != 0, sy = f.offy != 0, sz = f.offz != 0;   // direction negative: the near plane is hi
+#define RTX_SEL4(s, a, b) make_float4(s ? a.x : b.x, s ? a.y : b.y, s ? a.z : b.z, s ? a.w : b.w)
+    const float4 nx = RTX_SEL4(sx, X.b, X.a), fx = RTX_SEL4(sx, X.a, X.b);
+    const float4 ny = RTX_SEL4(sy, Y.b, Y.a), fy = RTX_SEL4(sy, Y.a, Y.b);
+    const float4 nz = RTX_SEL4(sz, Z.b, Z.a), fz = RTX_SEL4(sz, Z.a, Z.b);
+#undef RTX_SEL4
 #define RTX_CHILD(k, comp)                                                                                   \
     {                                                                                                        \
         float tn = fmaxf(fmaxf(fmaf(nx.comp, f.ix, f.cnx), fmaf(ny.comp, f.iy, f.cny)), fmaxf(fmaf(nz.comp, f.iz, f.cnz), tmin)); \
@@ -355,9 +386,9 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const RayD& rw, 
         out.mat = S.quad_mat[h.prim];
         if (want_uv) { double uv[2] = {0, 0}; isect_quad(q, r, -RTX_INF_D, RTX_INF_D, uv); out.u = uv[0]; out.v = uv[1]; }
     } else if (h.kind == RTX_GEOM_TRIANGLE) {
-        n = ld3(S.tri_nrm + 4 * (size_t)h.prim);
+        { const D4 tn = ldg256d(S.tris + RTX_TRI_D * (size_t)h.prim + 8); n = d3(tn.y, tn.z, tn.w); }
         out.mat = S.tri_info[h.prim].y;
-        if (want_uv) { double uv[2] = {0, 0}; isect_tri(S.tris + 10 * (size_t)h.prim, r, uv); out.u = uv[0]; out.v = uv[1]; }
+        if (want_uv) { double uv[2] = {0, 0}; isect_tri(S.tris + RTX_TRI_D * (size_t)h.prim, r, uv); out.u = uv[0]; out.v = uv[1]; }
     } else {
         n = ld3(S.planes + 8 * (size_t)h.prim + 3);
         out.mat = S.plane_mat[h.prim];

@@ -194,8 +194,8 @@ struct ExtendPolicy {
     __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:451
     __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
         const int slot = q_cur[job];
-        const double2 a = pool.ray_o[2 * slot], b = pool.ray_o[2 * slot + 1], c = pool.ray_d[2 * slot], d = pool.ray_d[2 * slot + 1];
-        r.ox = a.x; r.oy = a.y; r.oz = b.x; r.tm = b.y; r.dx = c.x; r.dy = c.y; r.dz = d.x;
+        const D4 a = ld256d(pool.ray_o + 2 * slot), c = ld256d(pool.ray_d + 2 * slot);
+        r.ox = a.x; r.oy = a.y; r.oz = a.z; r.tm = a.w; r.dx = c.x; r.dy = c.y; r.dz = c.z;
         tmax = RTX_INF_D;
     }
     __device__ __forceinline__ VolumeRng volume_rng(int job) const {
@@ -214,11 +214,9 @@ struct ExtendPolicy {
             } else {
                 HitInfo hi;
                 finalize_hit(*S, r, best_to_hit(b), false, hi);
-                pool.hit_p[2 * slot] = make_double2(hi.P.x, hi.P.y);
-                pool.hit_p[2 * slot + 1] = make_double2(hi.P.z, b.t);
                 const long long bits = (long long)(unsigned)hi.mat | (hi.front ? (1LL << 31) : 0);
-                pool.hit_n[2 * slot] = make_double2(hi.N.x, hi.N.y);
-                pool.hit_n[2 * slot + 1] = make_double2(hi.N.z, __longlong_as_double(bits));
+                st256d(pool.hit_p + 2 * slot, hi.P.x, hi.P.y, hi.P.z, b.t);
+                st256d(pool.hit_n + 2 * slot, hi.N.x, hi.N.y, hi.N.z, __longlong_as_double(bits));
                 const int mt = S->mats[hi.mat].type;
                 q = mt == RTX_MAT_LAMBERTIAN ? Q_LAMBERTIAN : mt == RTX_MAT_METAL ? Q_METAL : mt == RTX_MAT_DIELECTRIC ? Q_DIELECTRIC
                     : mt == RTX_MAT_DIFFUSE_LIGHT ? Q_LIGHT : Q_ISOTROPIC;
@@ -516,9 +514,9 @@ struct ConnectPolicy {
     __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:579, :636
     __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
         const int slot = __float_as_int(pool.sh_c[job].w);
-        const double2 o0 = pool.ray_o[2 * slot], o1 = pool.ray_o[2 * slot + 1], d0 = pool.sh_d[2 * job], d1 = pool.sh_d[2 * job + 1];
-        r.ox = o0.x; r.oy = o0.y; r.oz = o1.x; r.dx = d0.x; r.dy = d0.y; r.dz = d1.x; r.tm = 0;  // NewRay(hitPoint, lightDir, 0)
-        tmax = d1.y;
+        const D4 o0 = ld256d(pool.ray_o + 2 * slot), d0 = ld256d(pool.sh_d + 2 * job);
+        r.ox = o0.x; r.oy = o0.y; r.oz = o0.z; r.dx = d0.x; r.dy = d0.y; r.dz = d0.z; r.tm = 0;  // NewRay(hitPoint, lightDir, 0)
+        tmax = d0.w;
     }
     __device__ __forceinline__ VolumeRng volume_rng(int job) const {
         const int slot = __float_as_int(pool.sh_c[job].w);

@@ -105,6 +105,9 @@ struct Best {
 #ifndef RTX_T_STEPS
 #define RTX_T_STEPS 4   /* triangles per TRI round (1: 1282, 2: 1303-1332, 4: 1373 Mrays/s) */
 #endif
+#ifndef RTX_PARTNERS
+#define RTX_PARTNERS 0   /* partner columns a lane may claim from when its own column has no ready slot of the voted phase (0..3) */
+#endif
 #define RTX_PH_N 0
 #define RTX_PH_T 1
 #define RTX_PH_E 2
@@ -286,24 +289,35 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
         const int cN = ((c & 0xff) << 2) | (round & 3), cT = (((c >> 8) & 0xff) << 2) | ((round + 1) & 3),
                   cE = (((c >> 16) & 0xff) << 2) | ((round + 2) & 3), cR = (((c >> 24) & 0xff) << 2) | ((round + 3) & 3);
         const int phase = (cN >= cT && cN >= cE && cN >= cR) ? RTX_PH_N : (cT >= cE && cT >= cR) ? RTX_PH_T : (cE >= cR) ? RTX_PH_E : RTX_PH_R;
-        // claim one ready slot of my column (search start rotates so that no slot index is favoured)
+        // claim one ready slot of my column (search start rotates so that no slot index is favoured); a lane whose own column
+        // has none tries its RTX_PARTNERS partner columns (lane ^ 16, ^ 8, ^ 24): at worst a 2-way bank conflict with the
+        // partner lane, against an idle lane for the whole round
         int j = -1;
+        unsigned col = lane;
         {
             const unsigned rot = (round % NCOL) * 4u;
             const unsigned pat = (unsigned)phase * 0x11111111u;
-            for (;;) {
-                const unsigned wr = __funnelshift_r(w, w, rot);
-                const unsigned hz = RTX_HASZERO_NIB(wr ^ pat);
-                if (!hz) break;
-                const int jj = (int)((((unsigned)(__ffs(hz) - 1) >> 2) + (rot >> 2)) & 7u);
-                const unsigned neww = w ^ ((unsigned)(phase ^ RTX_PH_BUSY) << (4 * jj));
-                const unsigned old = atomicCAS(const_cast<unsigned*>(colstate) + lane, w, neww);
-                if (old == w) { j = jj; break; }
-                w = old;
+#pragma unroll
+            for (int attempt = 0; attempt <= RTX_PARTNERS; attempt++) {
+                if (attempt > 0) {
+                    if (j >= 0) break;
+                    col = lane ^ (attempt == 1 ? 16u : attempt == 2 ? 8u : 24u);
+                    w = colstate[col];
+                }
+                for (;;) {
+                    const unsigned wr = __funnelshift_r(w, w, rot);
+                    const unsigned hz = RTX_HASZERO_NIB(wr ^ pat);
+                    if (!hz) break;
+                    const int jj = (int)((((unsigned)(__ffs(hz) - 1) >> 2) + (rot >> 2)) & 7u);
+                    const unsigned neww = w ^ ((unsigned)(phase ^ RTX_PH_BUSY) << (4 * jj));
+                    const unsigned old = atomicCAS(const_cast<unsigned*>(colstate) + col, w, neww);
+                    if (old == w) { j = jj; break; }
+                    w = old;
+                }
             }
         }
         const bool mine = j >= 0;
-        const int s = (int)lane + 32 * (mine ? j : 0);
+        const int s = (int)col + 32 * (mine ? j : 0);
         if (mine) __threadfence_block();   // see the slot as its previous owner left it
         int newst = -1;  // phase of the claimed slot after this round
 
@@ -357,7 +371,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                     const int code = ~node;
                     const int ti = code >> 3, rem = code & 7;
                     if (COUNT) tc.tris++;
-                    const double t = isect_tri(S.tris + 10 * (size_t)ti, r, nullptr);
+                    const double t = isect_tri(S.tris + RTX_TRI_D * (size_t)ti, r, nullptr);
                     bool have = false;
                     if (tmin <= t && t <= bt) {
                         const int4 info = __ldg(S.tri_info + ti);
@@ -474,7 +488,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
         }
         if (mine) {   // publish: slot state first, then its phase nibble (BUSY -> newst)
             __threadfence_block();
-            atomicXor(const_cast<unsigned*>(colstate) + lane, (unsigned)(RTX_PH_BUSY ^ newst) << (4 * j));
+            atomicXor(const_cast<unsigned*>(colstate) + col, (unsigned)(RTX_PH_BUSY ^ newst) << (4 * j));
         }
     }
 #undef RTX_HASZERO_NIB
