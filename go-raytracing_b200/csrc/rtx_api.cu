@@ -948,7 +948,7 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
     uint64_t launches = 1;
     CU(cudaEventRecord(evStart, st));
     // the trace kernels are persistent: one resident wave of warps pulls rays from a device-side cursor
-    const int gridBig = (P + 255) / 256, gridTrace = ctx->trace_grid, gridShadow = gridTrace;
+    const int gridBig = std::min((P + 255) / 256, ctx->num_sms * 8), gridTrace = ctx->trace_grid, gridShadow = gridTrace;
     long long iter = 0;
     int activeEstimate = P;  // shrinks the launch grids once the pool drains (from the last polled control block)
     for (;;) {

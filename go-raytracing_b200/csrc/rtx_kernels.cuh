@@ -140,9 +140,12 @@ __device__ __forceinline__ RayD camera_ray(const DevCamera& C, int i, int j, dou
     return r;
 }
 
+// The stream kernels (generate / shade / accumulate) run on a fixed grid (a few blocks per SM) and stride over the work the
+// device-side control block announces: the host never learns the queue lengths, and a launch sized for the whole pool
+// (16 K blocks) costs ~70 us of block scheduling even when a handful of paths are left.
 __global__ void __launch_bounds__(256) k_generate(Ctl* ctl, Pool pool, int* q_cur, DevCamera C, PassParams pp) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ctl->n_gen) return;
+  const int n_gen = ctl->n_gen;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_gen; i += gridDim.x * blockDim.x) {
     int slot = pool.q_free[ctl->n_free + i];
     unsigned long long pid = ctl->gen_base + (unsigned long long)i;
     unsigned npix = (unsigned)C.width * (unsigned)C.height;
@@ -168,6 +171,7 @@ __global__ void __launch_bounds__(256) k_generate(Ctl* ctl, Pool pool, int* q_cu
     pool.rad[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
     pool.pix[slot] = make_uint2(pixel, sample);
     q_cur[ctl->n_cont + i] = slot;
+  }
 }
 
 __device__ __forceinline__ void flush_counters(Ctl* ctl, const TraceCounters& tc) {
@@ -330,7 +334,8 @@ __device__ __forceinline__ D3 unit_sphere(uint32_t a, uint32_t b) {
 
 // ---- K4: shade — one thread per queue element, queues concatenated in material order --------------------------------
 __global__ void __launch_bounds__(256) k_shade(Ctl* ctl, Pool pool, int* q_next, DevScene S, DevCamera C, PassParams pp) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_rounded = (ctl->n_active + 31) & ~31;   // whole warps stay together for the queue appends
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rounded; i += gridDim.x * blockDim.x) {
     // locate (queue, index): prefix over the six queue counts
     int type = -1, idx = i;
 #pragma unroll
@@ -505,6 +510,7 @@ __global__ void __launch_bounds__(256) k_shade(Ctl* ctl, Pool pool, int* q_next,
             pool.sh_c[sp] = make_float4(sh_c[k].x, sh_c[k].y, sh_c[k].z, __int_as_float(slot));
         }
     }
+  }
 }
 
 // ---- K3: connect — shadow rays of next-event estimation (any hit in [0.001, tmax]) ----------------------------------
@@ -551,8 +557,9 @@ __global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_connect
 
 // ---- K6a: accumulate finished paths into the per-pixel sums, recycle their slots --------------------------------------
 __global__ void __launch_bounds__(256) k_accumulate(Ctl* ctl, Pool pool, float4* accum, float4* accum_sq, int moments) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = i < ctl->n_done;
+  const int n_done = ctl->n_done, n_rounded = (n_done + 31) & ~31;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rounded; i += gridDim.x * blockDim.x) {
+    bool valid = i < n_done;
     int slot = -1;
     if (valid) {
         slot = pool.q_done[i];
@@ -567,6 +574,7 @@ __global__ void __launch_bounds__(256) k_accumulate(Ctl* ctl, Pool pool, float4*
     }
     int pos = warp_append(&ctl->n_free, valid);
     if (valid) pool.q_free[pos] = slot;
+  }
 }
 
 // ---- K6b: resolve (rt/bucket_renderer.go:275-285, rt/utils.go:85-90) -----------------------------------------------------
