@@ -63,6 +63,7 @@ struct rtx_ctx {
     Ctl* ctl = nullptr;       // device
     Ctl* ctl_host = nullptr;  // pinned
     int count_stats = 0, time_kernels = 1, blas_leaf = 4;
+    int pool_records = 1;   // path state as 256-byte records (1) or one array per field (0)
     int bvh_device = 1;   // mesh BLAS construction on the device (rtx_bvh_gpu.cuh); 0 = host builder (rtx_bvh.hpp), kept for A/B
     double ms_upload_blas = 0, ms_upload_total = 0;
     int blas_depth = 0, built_on_device = 0;
@@ -245,6 +246,10 @@ int32_t rtx_set_option(rtx_ctx* ctx, const char* key, int64_t value) {
     } else if (k == "count_stats") ctx->count_stats = (int)value;  // bit 0: extend kernel, bit 1: connect kernel
     else if (k == "time_kernels") ctx->time_kernels = value != 0;
     else if (k == "l2_persist") { ctx->l2_persist = value != 0; ctx->window_set = false; }  // L2 persisting window over the scene geometry (default off)
+    else if (k == "pool_records") {
+        if ((value != 0) != (ctx->pool_records != 0)) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); free_pool(ctx); }
+        ctx->pool_records = value != 0;
+    }
     else if (k == "bvh_device") ctx->bvh_device = value != 0;  // takes effect at the next rtx_scene_upload
     else if (k == "blas_leaf") {  // triangles per BLAS leaf (1..8); takes effect at the next rtx_scene_upload
         if (value < 1 || value > 8) return fail(ctx, RTX_ERR_INVALID, "blas_leaf must be in 1..8");
@@ -875,13 +880,21 @@ static int32_t ensure_pool(rtx_ctx* ctx) {
         if (e == cudaSuccess) ctx->pool_allocs.push_back(*out);
         return e;
     };
-    CU(alloc((void**)&p.ray_o, 2 * P * sizeof(double2)));
-    CU(alloc((void**)&p.ray_d, 2 * P * sizeof(double2)));
-    CU(alloc((void**)&p.thr, P * sizeof(float4)));
-    CU(alloc((void**)&p.rad, P * sizeof(float4)));
-    CU(alloc((void**)&p.pix, P * sizeof(uint2)));
-    CU(alloc((void**)&p.hit_p, 2 * P * sizeof(double2)));
-    CU(alloc((void**)&p.hit_n, 2 * P * sizeof(double2)));
+    if (ctx->pool_records) {   // one 256-byte record per path: [ray_o 32][ray_d 32][thr 16][rad 16][pix 8][-][hit_p 32][hit_n 32][-]
+        char* rec = nullptr;
+        CU(alloc((void**)&rec, P * 256));
+        p.ray_o = rec; p.ray_d = rec + 32; p.thr = rec + 64; p.rad = rec + 80; p.pix = rec + 96; p.hit_p = rec + 128; p.hit_n = rec + 160;
+        p.st_ray = p.st_thr = p.st_pix = p.st_hit = 256;
+    } else {
+        CU(alloc((void**)&p.ray_o, P * 32));
+        CU(alloc((void**)&p.ray_d, P * 32));
+        CU(alloc((void**)&p.thr, P * sizeof(float4)));
+        CU(alloc((void**)&p.rad, P * sizeof(float4)));
+        CU(alloc((void**)&p.pix, P * sizeof(uint2)));
+        CU(alloc((void**)&p.hit_p, P * 32));
+        CU(alloc((void**)&p.hit_n, P * 32));
+        p.st_ray = 32; p.st_thr = 16; p.st_pix = 8; p.st_hit = 32;
+    }
     CU(alloc((void**)&p.q_a, P * sizeof(int)));
     CU(alloc((void**)&p.q_b, P * sizeof(int)));
     CU(alloc((void**)&p.q_free, P * sizeof(int)));

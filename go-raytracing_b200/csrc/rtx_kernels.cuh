@@ -55,15 +55,28 @@ struct Ctl {  // device-resident control block of the wavefront loop
     unsigned long long ext_rays, shadow_rays, nodes, tris, spheres, quads, planes, iterations;
 };
 
-struct Pool {  // SoA path state; one entry per in-flight path slot
+// Path state, one entry per in-flight path slot. Slots are recycled in arbitrary order, so every access is a gather: the
+// fields of a path are therefore kept TOGETHER in one 256-byte record (two adjacent 128-byte lines: ray + throughput +
+// radiance + pixel in the first, the hit record in the second) instead of seven parallel arrays, which turns seven DRAM
+// rows per path into one. Each field is addressed as base + slot * stride, so the array-per-field layout is the same code
+// with other strides (rtx_set_option "pool_records" = 0, kept for A/B).
+struct Pool {
     int capacity;
-    double2* ray_o;   // [2P] (ox,oy) (oz,time)
-    double2* ray_d;   // [2P] (dx,dy) (dz,-)
-    float4* thr;      // throughput rgb, w = bits: bounce | allowLightHits << 16
-    float4* rad;      // accumulated radiance rgb
-    uint2* pix;       // (pixel index, global sample index)
-    double2* hit_p;   // [2P] (Px,Py) (Pz,t)
-    double2* hit_n;   // [2P] (Nx,Ny) (Nz, bits: material | front << 31)
+    char* ray_o;      // 4 doubles: ox, oy, oz, time
+    char* ray_d;      // 4 doubles: dx, dy, dz, -
+    char* thr;        // float4: throughput rgb, w = bits: bounce | allowLightHits << 16
+    char* rad;        // float4: accumulated radiance rgb
+    char* pix;        // uint2: (pixel index, global sample index)
+    char* hit_p;      // 4 doubles: Px, Py, Pz, t
+    char* hit_n;      // 4 doubles: Nx, Ny, Nz, bits: material | front << 31
+    int st_ray, st_thr, st_pix, st_hit;   // strides in bytes (records: all 256)
+    __device__ __forceinline__ double* f_ray_o(int slot) const { return reinterpret_cast<double*>(ray_o + (size_t)slot * st_ray); }
+    __device__ __forceinline__ double* f_ray_d(int slot) const { return reinterpret_cast<double*>(ray_d + (size_t)slot * st_ray); }
+    __device__ __forceinline__ float4* f_thr(int slot) const { return reinterpret_cast<float4*>(thr + (size_t)slot * st_thr); }
+    __device__ __forceinline__ float4* f_rad(int slot) const { return reinterpret_cast<float4*>(rad + (size_t)slot * st_thr); }
+    __device__ __forceinline__ uint2* f_pix(int slot) const { return reinterpret_cast<uint2*>(pix + (size_t)slot * st_pix); }
+    __device__ __forceinline__ double* f_hit_p(int slot) const { return reinterpret_cast<double*>(hit_p + (size_t)slot * st_hit); }
+    __device__ __forceinline__ double* f_hit_n(int slot) const { return reinterpret_cast<double*>(hit_n + (size_t)slot * st_hit); }
     int* q_a;         // active queue, ping
     int* q_b;         // active queue, pong
     int* q_free;      // free-slot stack
@@ -163,13 +176,11 @@ __global__ void __launch_bounds__(256) k_generate(Ctl* ctl, Pool pool, int* q_cu
         lx = rr * cs; ly = rr * sn;
     }
     RayD r = camera_ray(C, px, py, offx, offy, tm, lx, ly);
-    pool.ray_o[2 * slot] = make_double2(r.ox, r.oy);
-    pool.ray_o[2 * slot + 1] = make_double2(r.oz, r.tm);
-    pool.ray_d[2 * slot] = make_double2(r.dx, r.dy);
-    pool.ray_d[2 * slot + 1] = make_double2(r.dz, 0.0);
-    pool.thr[slot] = make_float4(1.f, 1.f, 1.f, __int_as_float(0 | (1 << 16)));
-    pool.rad[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-    pool.pix[slot] = make_uint2(pixel, sample);
+    st256d(pool.f_ray_o(slot), r.ox, r.oy, r.oz, r.tm);
+    st256d(pool.f_ray_d(slot), r.dx, r.dy, r.dz, 0.0);
+    *pool.f_thr(slot) = make_float4(1.f, 1.f, 1.f, __int_as_float(0 | (1 << 16)));
+    *pool.f_rad(slot) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *pool.f_pix(slot) = make_uint2(pixel, sample);
     q_cur[ctl->n_cont + i] = slot;
   }
 }
@@ -198,14 +209,14 @@ struct ExtendPolicy {
     __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:451
     __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
         const int slot = q_cur[job];
-        const D4 a = ld256d(pool.ray_o + 2 * slot), c = ld256d(pool.ray_d + 2 * slot);
+        const D4 a = ld256d(pool.f_ray_o(slot)), c = ld256d(pool.f_ray_d(slot));
         r.ox = a.x; r.oy = a.y; r.oz = a.z; r.tm = a.w; r.dx = c.x; r.dy = c.y; r.dz = c.z;
         tmax = RTX_INF_D;
     }
     __device__ __forceinline__ VolumeRng volume_rng(int job) const {
         const int slot = q_cur[job];
-        const uint2 ps = pool.pix[slot];
-        const int bounce = __float_as_int(pool.thr[slot].w) & 0xffff;
+        const uint2 ps = *pool.f_pix(slot);
+        const int bounce = __float_as_int(pool.f_thr(slot)->w) & 0xffff;
         VolumeRng vr; vr.k0 = seed_lo; vr.k1 = seed_hi; vr.c0 = ps.x; vr.c1 = ps.y; vr.c2 = (uint32_t)bounce * 4u; vr.transparent = false;
         return vr;
     }
@@ -219,8 +230,8 @@ struct ExtendPolicy {
                 HitInfo hi;
                 finalize_hit(*S, r, best_to_hit(b), false, hi);
                 const long long bits = (long long)(unsigned)hi.mat | (hi.front ? (1LL << 31) : 0);
-                st256d(pool.hit_p + 2 * slot, hi.P.x, hi.P.y, hi.P.z, b.t);
-                st256d(pool.hit_n + 2 * slot, hi.N.x, hi.N.y, hi.N.z, __longlong_as_double(bits));
+                st256d(pool.f_hit_p(slot), hi.P.x, hi.P.y, hi.P.z, b.t);
+                st256d(pool.f_hit_n(slot), hi.N.x, hi.N.y, hi.N.z, __longlong_as_double(bits));
                 const int mt = S->mats[hi.mat].type;
                 q = mt == RTX_MAT_LAMBERTIAN ? Q_LAMBERTIAN : mt == RTX_MAT_METAL ? Q_METAL : mt == RTX_MAT_DIELECTRIC ? Q_DIELECTRIC
                     : mt == RTX_MAT_DIFFUSE_LIGHT ? Q_LIGHT : Q_ISOTROPIC;
@@ -349,22 +360,22 @@ __global__ void __launch_bounds__(256) k_shade(Ctl* ctl, Pool pool, int* q_next,
     bool valid = type >= 0;
     bool cont = false, finished = false;
     int slot = -1;
-    int nshadow = 0;
-    D3 sh_dir[2];
-    double sh_tmax[2];
-    float3 sh_c[2];
+    // up to two shadow requests per Lambertian hit, in fixed registers (no dynamically indexed arrays: those live in local memory)
+    bool has_env = false, has_area = false;
+    D3 env_dir = d3(0, 0, 0), area_dir = d3(0, 0, 0);
+    double area_tmax = 0;
+    float3 env_c = make_float3(0, 0, 0), area_c = make_float3(0, 0, 0);
     if (valid) {
         slot = pool.q_mat[(size_t)type * pool.capacity + idx];
-        double2 a = pool.ray_o[2 * slot], b = pool.ray_o[2 * slot + 1], c = pool.ray_d[2 * slot], d = pool.ray_d[2 * slot + 1];
-        D3 rd = d3(c.x, c.y, d.x);
-        double tm = b.y;
-        float4 th = pool.thr[slot];
-        float4 L = pool.rad[slot];
+        const D4 ro4 = ld256d(pool.f_ray_o(slot)), rd4 = ld256d(pool.f_ray_d(slot));
+        D3 rd = d3(rd4.x, rd4.y, rd4.z);
+        double tm = ro4.w;
+        float4 th = *pool.f_thr(slot);
+        float4 L = *pool.f_rad(slot);
         int flags = __float_as_int(th.w);
         int bounce = flags & 0xffff;
         bool allow = (flags >> 16) & 1;
-        uint2 ps = pool.pix[slot];
-        (void)a;
+        uint2 ps = *pool.f_pix(slot);
         if (type == Q_MISS) {  // rt/camera.go:451-466
             float3 col;
             if (S.env_w > 0) {
@@ -379,9 +390,9 @@ __global__ void __launch_bounds__(256) k_shade(Ctl* ctl, Pool pool, int* q_next,
             L.x += th.x * col.x; L.y += th.y * col.y; L.z += th.z * col.z;
             finished = true;
         } else {
-            double2 hp0 = pool.hit_p[2 * slot], hp1 = pool.hit_p[2 * slot + 1], hn0 = pool.hit_n[2 * slot], hn1 = pool.hit_n[2 * slot + 1];
-            D3 P = d3(hp0.x, hp0.y, hp1.x), N = d3(hn0.x, hn0.y, hn1.x);
-            long long bits = __double_as_longlong(hn1.y);
+            const D4 hp = ld256d(pool.f_hit_p(slot)), hn = ld256d(pool.f_hit_n(slot));
+            D3 P = d3(hp.x, hp.y, hp.z), N = d3(hn.x, hn.y, hn.z);
+            long long bits = __double_as_longlong(hn.w);
             int mat = (int)(bits & 0x7fffffff);
             bool front = (bits >> 31) & 1;
             DMaterial M = S.mats[mat];
@@ -414,9 +425,9 @@ __global__ void __launch_bounds__(256) k_shade(Ctl* ctl, Pool pool, int* q_next,
                                 double w = pdfH / (pdfH + pdfB);
                                 double s = cosT / pdfH * w;
                                 float3 cc = make_float3(fminf((float)(em.x * s) * att.x, 20.f), fminf((float)(em.y * s) * att.y, 20.f), fminf((float)(em.z * s) * att.z, 20.f));
-                                sh_dir[nshadow] = ldir; sh_tmax[nshadow] = RTX_INF_D;
-                                sh_c[nshadow] = make_float3(th.x * cc.x, th.y * cc.y, th.z * cc.z);
-                                nshadow++;
+                                env_dir = ldir;
+                                env_c = make_float3(th.x * cc.x, th.y * cc.y, th.z * cc.z);
+                                has_env = true;
                             }
                         }
                         int lq = S.light_quads[li];
@@ -439,9 +450,9 @@ __global__ void __launch_bounds__(256) k_shade(Ctl* ctl, Pool pool, int* q_next,
                                 double nl = (double)S.n_lights;
                                 float3 cc = make_float3(fminf((float)(em.x * s * att.x * nl), 20.f), fminf((float)(em.y * s * att.y * nl), 20.f),
                                                         fminf((float)(em.z * s * att.z * nl), 20.f));
-                                sh_dir[nshadow] = ldir; sh_tmax[nshadow] = dist - 0.001;
-                                sh_c[nshadow] = make_float3(th.x * cc.x, th.y * cc.y, th.z * cc.z);
-                                nshadow++;
+                                area_dir = ldir; area_tmax = dist - 0.001;
+                                area_c = make_float3(th.x * cc.x, th.y * cc.y, th.z * cc.z);
+                                has_area = true;
                             }
                         }
                         next_allow = false;  // indirect path must not pick up the light again (:514)
@@ -479,35 +490,35 @@ __global__ void __launch_bounds__(256) k_shade(Ctl* ctl, Pool pool, int* q_next,
                 }
                 if (!scattered) {
                     finished = true;  // absorbed: emission of a scattering material is zero
-                    nshadow = 0;
+                    has_env = has_area = false;
                 } else {
                     th.x *= att.x; th.y *= att.y; th.z *= att.z;
                     bounce++;
                     th.w = __int_as_float((bounce & 0xffff) | (next_allow ? (1 << 16) : 0));
-                    pool.ray_o[2 * slot] = make_double2(P.x, P.y);
-                    pool.ray_o[2 * slot + 1] = make_double2(P.z, tm);
-                    pool.ray_d[2 * slot] = make_double2(nd.x, nd.y);
-                    pool.ray_d[2 * slot + 1] = make_double2(nd.z, 0.0);
-                    pool.thr[slot] = th;
+                    st256d(pool.f_ray_o(slot), P.x, P.y, P.z, tm);
+                    st256d(pool.f_ray_d(slot), nd.x, nd.y, nd.z, 0.0);
+                    *pool.f_thr(slot) = th;
                     if (bounce >= pp.max_depth) finished = true;  // rayColorInternal(depth <= 0) returns black (:444-446)
                     else cont = true;
                 }
             }
         }
-        if (finished) pool.rad[slot] = L;
+        if (finished) *pool.f_rad(slot) = L;
     }
     int pos = warp_append(&ctl->n_next, cont);
     if (cont) q_next[pos] = slot;
     pos = warp_append(&ctl->n_done, finished);
     if (finished) pool.q_done[pos] = slot;
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        bool has = k < nshadow;
-        int sp = warp_append(&ctl->n_shadow, has);
-        if (has) {
-            pool.sh_d[2 * sp] = make_double2(sh_dir[k].x, sh_dir[k].y);
-            pool.sh_d[2 * sp + 1] = make_double2(sh_dir[k].z, sh_tmax[k]);
-            pool.sh_c[sp] = make_float4(sh_c[k].x, sh_c[k].y, sh_c[k].z, __int_as_float(slot));
+    {
+        int sp = warp_append(&ctl->n_shadow, has_env);
+        if (has_env) {
+            st256d(pool.sh_d + 2 * sp, env_dir.x, env_dir.y, env_dir.z, RTX_INF_D);
+            pool.sh_c[sp] = make_float4(env_c.x, env_c.y, env_c.z, __int_as_float(slot));
+        }
+        sp = warp_append(&ctl->n_shadow, has_area);
+        if (has_area) {
+            st256d(pool.sh_d + 2 * sp, area_dir.x, area_dir.y, area_dir.z, area_tmax);
+            pool.sh_c[sp] = make_float4(area_c.x, area_c.y, area_c.z, __int_as_float(slot));
         }
     }
   }
@@ -520,15 +531,15 @@ struct ConnectPolicy {
     __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:579, :636
     __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
         const int slot = __float_as_int(pool.sh_c[job].w);
-        const D4 o0 = ld256d(pool.ray_o + 2 * slot), d0 = ld256d(pool.sh_d + 2 * job);
+        const D4 o0 = ld256d(pool.f_ray_o(slot)), d0 = ld256d(pool.sh_d + 2 * job);
         r.ox = o0.x; r.oy = o0.y; r.oz = o0.z; r.dx = d0.x; r.dy = d0.y; r.dz = d0.z; r.tm = 0;  // NewRay(hitPoint, lightDir, 0)
         tmax = d0.w;
     }
     __device__ __forceinline__ VolumeRng volume_rng(int job) const {
         const int slot = __float_as_int(pool.sh_c[job].w);
-        const uint2 ps = pool.pix[slot];
+        const uint2 ps = *pool.f_pix(slot);
         // shade already advanced the bounce counter of the path: the shadow ray belongs to the bounce before it
-        const int bounce = (__float_as_int(pool.thr[slot].w) & 0xffff) - 1;
+        const int bounce = (__float_as_int(pool.f_thr(slot)->w) & 0xffff) - 1;
         const double tmax = pool.sh_d[2 * job + 1].y;
         VolumeRng vr; vr.k0 = seed_lo; vr.k1 = seed_hi; vr.c0 = ps.x; vr.c1 = ps.y;
         vr.c2 = (uint32_t)bounce * 4u + (tmax == RTX_INF_D ? 2u : 1u); vr.transparent = false;
@@ -538,9 +549,10 @@ struct ConnectPolicy {
         if (valid && b.entry < 0) {
             const float4 cc = pool.sh_c[job];
             const int slot = __float_as_int(cc.w);
-            atomicAdd(&pool.rad[slot].x, cc.x);
-            atomicAdd(&pool.rad[slot].y, cc.y);
-            atomicAdd(&pool.rad[slot].z, cc.z);
+            float* L = reinterpret_cast<float*>(pool.f_rad(slot));
+            atomicAdd(L + 0, cc.x);
+            atomicAdd(L + 1, cc.y);
+            atomicAdd(L + 2, cc.z);
         }
     }
 };
@@ -563,8 +575,8 @@ __global__ void __launch_bounds__(256) k_accumulate(Ctl* ctl, Pool pool, float4*
     int slot = -1;
     if (valid) {
         slot = pool.q_done[i];
-        float4 L = pool.rad[slot];
-        uint32_t pixel = pool.pix[slot].x;
+        float4 L = *pool.f_rad(slot);
+        uint32_t pixel = pool.f_pix(slot)->x;
         float* a = reinterpret_cast<float*>(accum + pixel);
         atomicAdd(a + 0, L.x); atomicAdd(a + 1, L.y); atomicAdd(a + 2, L.z); atomicAdd(a + 3, 1.0f);
         if (moments) {

@@ -98,7 +98,9 @@ struct Best {
 // one phase runs on it. With K > 1 a warp schedules 32 K rays onto 32 lanes: the phase that wins the vote finds a
 // ready ray in far more lanes than with one ray per lane. The first RTX_SMEM_STACK stack entries of a slot are in shared
 // memory, deeper ones spill to a global scratch column (rare: the stack seldom exceeds a dozen entries).
+#ifndef RTX_SMEM_STACK
 #define RTX_SMEM_STACK 16
+#endif
 #ifndef RTX_N_STEPS
 #define RTX_N_STEPS 3   /* node levels per NODE round (A/B on cornell-lucy: 1: 1041, 2: 1062, 3: 1090, 4: 1080 Mrays/s) */
 #endif
@@ -107,6 +109,12 @@ struct Best {
 #endif
 #ifndef RTX_PARTNERS
 #define RTX_PARTNERS 0   /* partner columns a lane may claim from when its own column has no ready slot of the voted phase (0..3) */
+#endif
+#ifndef RTX_SKIP_LAST_SENTINEL
+#define RTX_SKIP_LAST_SENTINEL 1
+#endif
+#ifndef RTX_N_FAST
+#define RTX_N_FAST 0   /* lanes with a NODE-ready slot from which the NODE phase is taken without a vote (0 = always vote) */
 #endif
 #define RTX_PH_N 0
 #define RTX_PH_T 1
@@ -274,21 +282,30 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
     for (;;) {
         // ---- vote: one REDUX over packed per-phase counts of lanes whose column holds a ready slot ------------------------
         unsigned w = colstate[lane];
-        unsigned present = 0;
+        int phase;
+        // fast path: when at least RTX_N_FAST lanes have a NODE-ready slot the NODE phase runs without a full vote (one ballot
+        // instead of four zero-nibble tests, a REDUX and the arg-max). The rarer phases then wait until NODE runs short of
+        // lanes, which also lets them collect more lanes per round.
+        if (RTX_N_FAST > 0 && __popc(__ballot_sync(FULL, RTX_HASZERO_NIB(w) != 0u)) >= RTX_N_FAST) {
+            phase = RTX_PH_N;
+            round++;
+        } else {
+            unsigned present = 0;
 #pragma unroll
-        for (unsigned X = 0; X < 4; X++) present |= RTX_HASZERO_NIB(w ^ (X * 0x11111111u)) ? (1u << (8 * X)) : 0u;
-        const unsigned c = __reduce_add_sync(FULL, present);
-        if (c == 0) {
-            if (__all_sync(FULL, w == ALL_PARKED)) break;   // every slot of the block is parked: queue dry, all rays retired
-            __nanosleep(100);                                // other warps hold the remaining slots (BUSY): wait for them
-            continue;
+            for (unsigned X = 0; X < 4; X++) present |= RTX_HASZERO_NIB(w ^ (X * 0x11111111u)) ? (1u << (8 * X)) : 0u;
+            const unsigned c = __reduce_add_sync(FULL, present);
+            if (c == 0) {
+                if (__all_sync(FULL, w == ALL_PARKED)) break;   // every slot of the block is parked: queue dry, all rays retired
+                __nanosleep(100);                                // other warps hold the remaining slots (BUSY): wait for them
+                continue;
+            }
+            // the phase with the most ready lanes wins; equal counts are broken by a priority that rotates with the round and
+            // differs between the warps of a block, so they spread over the phases and no ray starves
+            round++;
+            const int cN = ((c & 0xff) << 2) | (round & 3), cT = (((c >> 8) & 0xff) << 2) | ((round + 1) & 3),
+                      cE = (((c >> 16) & 0xff) << 2) | ((round + 2) & 3), cR = (((c >> 24) & 0xff) << 2) | ((round + 3) & 3);
+            phase = (cN >= cT && cN >= cE && cN >= cR) ? RTX_PH_N : (cT >= cE && cT >= cR) ? RTX_PH_T : (cE >= cR) ? RTX_PH_E : RTX_PH_R;
         }
-        // the phase with the most ready lanes wins; equal counts are broken by a priority that rotates with the round and
-        // differs between the warps of a block, so they spread over the phases and no ray starves
-        round++;
-        const int cN = ((c & 0xff) << 2) | (round & 3), cT = (((c >> 8) & 0xff) << 2) | ((round + 1) & 3),
-                  cE = (((c >> 16) & 0xff) << 2) | ((round + 2) & 3), cR = (((c >> 24) & 0xff) << 2) | ((round + 3) & 3);
-        const int phase = (cN >= cT && cN >= cE && cN >= cR) ? RTX_PH_N : (cT >= cE && cT >= cR) ? RTX_PH_T : (cE >= cR) ? RTX_PH_E : RTX_PH_R;
         // claim one ready slot of my column (search start rotates so that no slot index is favoured); a lane whose own column
         // has none tries its RTX_PARTNERS partner columns (lane ^ 16, ^ 8, ^ 24): at worst a 2-way bank conflict with the
         // partner lane, against an idle lane for the whole round
@@ -411,7 +428,8 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                         RayD r2; RayF f;
                         T.load_ray(s, r2);
                         xform_ray(S, ei, e, r2);
-                        RTX_PUSH(RTX_ST_SENTINEL);
+                        // nothing left in the TLAS: the query ends inside the instance (retire re-reads the world ray), no way back needed
+                        if (RTX_SKIP_LAST_SENTINEL == 0 || sp > 0) RTX_PUSH(RTX_ST_SENTINEL);
                         make_rayf(r2, f);
                         T.store_ray(s, r2, false); T.store_rayf(s, f);
                         T.cur[s] = ei;
