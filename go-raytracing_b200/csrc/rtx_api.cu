@@ -63,7 +63,7 @@ struct rtx_ctx {
     Ctl* ctl = nullptr;       // device
     Ctl* ctl_host = nullptr;  // pinned
     int count_stats = 0, time_kernels = 1, blas_leaf = 4;
-    int pool_records = 1;   // path state as 256-byte records (1) or one array per field (0)
+    float4* per_sample = nullptr; size_t per_sample_cap = 0;   // moments mode: per-sample radiance sums of the running pass (grow-only)
     int bvh_device = 1;   // mesh BLAS construction on the device (rtx_bvh_gpu.cuh); 0 = host builder (rtx_bvh.hpp), kept for A/B
     double ms_upload_blas = 0, ms_upload_total = 0;
     int blas_depth = 0, built_on_device = 0;
@@ -224,6 +224,7 @@ int32_t rtx_destroy(rtx_ctx* ctx) {
     free_pool(ctx);
     ctx->scene_slab.release(); ctx->work_slab.release();
     if (ctx->rgba_dev) cudaFree(ctx->rgba_dev);
+    if (ctx->per_sample) cudaFree(ctx->per_sample);
     if (ctx->accum) cudaFree(ctx->accum);
     if (ctx->accum_sq) cudaFree(ctx->accum_sq);
     if (ctx->ctl) cudaFree(ctx->ctl);
@@ -246,10 +247,6 @@ int32_t rtx_set_option(rtx_ctx* ctx, const char* key, int64_t value) {
     } else if (k == "count_stats") ctx->count_stats = (int)value;  // bit 0: extend kernel, bit 1: connect kernel
     else if (k == "time_kernels") ctx->time_kernels = value != 0;
     else if (k == "l2_persist") { ctx->l2_persist = value != 0; ctx->window_set = false; }  // L2 persisting window over the scene geometry (default off)
-    else if (k == "pool_records") {
-        if ((value != 0) != (ctx->pool_records != 0)) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); free_pool(ctx); }
-        ctx->pool_records = value != 0;
-    }
     else if (k == "bvh_device") ctx->bvh_device = value != 0;  // takes effect at the next rtx_scene_upload
     else if (k == "blas_leaf") {  // triangles per BLAS leaf (1..8); takes effect at the next rtx_scene_upload
         if (value < 1 || value > 8) return fail(ctx, RTX_ERR_INVALID, "blas_leaf must be in 1..8");
@@ -880,28 +877,11 @@ static int32_t ensure_pool(rtx_ctx* ctx) {
         if (e == cudaSuccess) ctx->pool_allocs.push_back(*out);
         return e;
     };
-    if (ctx->pool_records) {   // one 256-byte record per path: [ray_o 32][ray_d 32][thr 16][rad 16][pix 8][-][hit_p 32][hit_n 32][-]
-        char* rec = nullptr;
-        CU(alloc((void**)&rec, P * 256));
-        p.ray_o = rec; p.ray_d = rec + 32; p.thr = rec + 64; p.rad = rec + 80; p.pix = rec + 96; p.hit_p = rec + 128; p.hit_n = rec + 160;
-        p.st_ray = p.st_thr = p.st_pix = p.st_hit = 256;
-    } else {
-        CU(alloc((void**)&p.ray_o, P * 32));
-        CU(alloc((void**)&p.ray_d, P * 32));
-        CU(alloc((void**)&p.thr, P * sizeof(float4)));
-        CU(alloc((void**)&p.rad, P * sizeof(float4)));
-        CU(alloc((void**)&p.pix, P * sizeof(uint2)));
-        CU(alloc((void**)&p.hit_p, P * 32));
-        CU(alloc((void**)&p.hit_n, P * 32));
-        p.st_ray = 32; p.st_thr = 16; p.st_pix = 8; p.st_hit = 32;
-    }
-    CU(alloc((void**)&p.q_a, P * sizeof(int)));
-    CU(alloc((void**)&p.q_b, P * sizeof(int)));
-    CU(alloc((void**)&p.q_free, P * sizeof(int)));
+    CU(alloc((void**)&p.rec[0], P * RTX_REC_BYTES));
+    CU(alloc((void**)&p.rec[1], P * RTX_REC_BYTES));
+    CU(alloc((void**)&p.hit, P * RTX_HIT_BYTES));
     CU(alloc((void**)&p.q_mat, (size_t)Q_COUNT * P * sizeof(int)));
-    CU(alloc((void**)&p.q_done, P * sizeof(int)));
-    CU(alloc((void**)&p.sh_d, 4 * P * sizeof(double2)));
-    CU(alloc((void**)&p.sh_c, 2 * P * sizeof(float4)));
+    CU(alloc((void**)&p.shadow, 2 * P * RTX_SHADOW_BYTES));
     p.capacity = (int)P;
     ctx->pool = p;
     return RTX_OK;
@@ -940,70 +920,85 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
     pp.seed_lo = (uint32_t)seed; pp.seed_hi = (uint32_t)(seed >> 32); pp.sample_base = sample_base;
     pp.moments = ctx->moments; pp.count_stats = ctx->count_stats;
 
+    const unsigned long long npix = (unsigned long long)ctx->W * ctx->H;
     Ctl init{};
-    init.total = (unsigned long long)ctx->W * ctx->H * (unsigned long long)spp;
-    if (max_depth == 0) init.total = 0;  // RayColor(depth 0) is black: nothing to trace (samples still count in the divisor)
-    init.n_free = P;
+    init.total = npix * (unsigned long long)spp;
+    if (max_depth == 0) init.total = 0;  // RayColor(depth 0) is black: nothing to trace (the samples still count in the divisor)
     CU(cudaMemcpyAsync(ctx->ctl, &init, sizeof(Ctl), cudaMemcpyHostToDevice, st));
-    k_pool_init<<<(P + 255) / 256, 256, 0, st>>>(ctx->pool, ctx->ctl);
+    Pool pool = ctx->pool;
+    pool.moments = ctx->moments; pool.npix = (uint32_t)npix; pool.sample_base = sample_base;
+    pool.target = reinterpret_cast<float*>(ctx->accum);
+    if (ctx->moments && spp > 0) {   // per-sample sums (squared and folded by k_pass_finish): tests only, bounded
+        const unsigned long long need = npix * (unsigned long long)spp;
+        if (need > (1ull << 28)) return fail(ctx, RTX_ERR_UNSUPPORTED, "moments are limited to 2^28 samples per pass (requested %llu)", need);
+        if (need > ctx->per_sample_cap) {
+            CU(cudaStreamSynchronize(st));
+            if (ctx->per_sample) cudaFree(ctx->per_sample);
+            ctx->per_sample = nullptr; ctx->per_sample_cap = 0;
+            CU(cudaMalloc((void**)&ctx->per_sample, need * sizeof(float4)));
+            ctx->per_sample_cap = need;
+        }
+        CU(cudaMemsetAsync(ctx->per_sample, 0, need * sizeof(float4), st));
+        pool.target = reinterpret_cast<float*>(ctx->per_sample);
+    }
 
     const int BATCH = 16;
-    enum { EV_GEN = 0, EV_EXT, EV_SHADE, EV_CONN, EV_ACC, EV_KINDS };
+    enum { EV_GEN = 0, EV_EXT, EV_SHADE, EV_CONN, EV_KINDS };
     const bool timing = ctx->time_kernels != 0;
-    size_t needEvents = 2 + (timing ? (size_t)BATCH * EV_KINDS * 2 : 0);
+    size_t needEvents = 4 + (timing ? (size_t)BATCH * EV_KINDS * 2 : 0);
     while (ctx->events.size() < needEvents) {
         cudaEvent_t ev;
         CU(cudaEventCreate(&ev));
         ctx->events.push_back(ev);
     }
     cudaEvent_t evStart = ctx->events[0], evStop = ctx->events[1];
-    double msKind[EV_KINDS] = {0, 0, 0, 0, 0};
-    uint64_t launches = 1;
+    double msKind[EV_KINDS] = {0, 0, 0, 0};
+    uint64_t launches = 0;
     CU(cudaEventRecord(evStart, st));
-    // the trace kernels are persistent: one resident wave of warps pulls rays from a device-side cursor
-    const int gridBig = std::min((P + 255) / 256, ctx->num_sms * 8), gridTrace = ctx->trace_grid, gridShadow = gridTrace;
+    // fixed grids: the stream kernels stride over device-side counts, the trace kernels are persistent (one resident wave of
+    // warps pulls rays from a device-side cursor); the host only polls the control block every BATCH iterations
+    const int gridStream = std::min((P + 255) / 256, ctx->num_sms * 8), gridTrace = ctx->trace_grid;
     long long iter = 0;
-    int activeEstimate = P;  // shrinks the launch grids once the pool drains (from the last polled control block)
     for (;;) {
         int used = 0;
         for (int b = 0; b < BATCH; b++, iter++) {
-            int* q_cur = (iter & 1) ? ctx->pool.q_b : ctx->pool.q_a;
-            int* q_next = (iter & 1) ? ctx->pool.q_a : ctx->pool.q_b;
-            cudaEvent_t* ev = timing ? &ctx->events[2 + (size_t)b * EV_KINDS * 2] : nullptr;
-            k_iter_begin<<<1, 32, 0, st>>>(ctx->ctl);
+            const int cur = (int)(iter & 1);   // rec[cur]: this iteration's paths; rec[cur ^ 1]: where k_shade writes the survivors
+            cudaEvent_t* ev = timing ? &ctx->events[4 + (size_t)b * EV_KINDS * 2] : nullptr;
+            k_iter_begin<<<1, 32, 0, st>>>(ctx->ctl, P);
             if (timing) cudaEventRecord(ev[0], st);
-            k_generate<<<gridBig, 256, 0, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->C, pp);
+            k_generate<<<gridStream, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->C, pp);
             if (timing) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
-            if (ctx->count_stats & 1) k_extend<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->S, pp, ctx->trace_spill);
-            else k_extend<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, ctx->pool, q_cur, ctx->S, pp, ctx->trace_spill);
+            if (ctx->count_stats & 1) k_extend<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
+            else k_extend<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
             if (timing) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); }
-            k_shade<<<gridBig, 256, 0, st>>>(ctx->ctl, ctx->pool, q_next, ctx->S, ctx->C, pp);
+            k_shade<<<gridStream, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, ctx->C, pp);
             if (timing) { cudaEventRecord(ev[5], st); cudaEventRecord(ev[6], st); }
             if (ctx->S.n_lights > 0) {
-                if (ctx->count_stats & 2) k_connect<true><<<gridShadow, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, ctx->pool, ctx->S, pp, ctx->trace_spill);
-                else k_connect<false><<<gridShadow, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, ctx->pool, ctx->S, pp, ctx->trace_spill);
+                if (ctx->count_stats & 2) k_connect<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, ctx->S, pp, ctx->trace_spill);
+                else k_connect<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, ctx->S, pp, ctx->trace_spill);
                 launches++;
             }
-            if (timing) { cudaEventRecord(ev[7], st); cudaEventRecord(ev[8], st); }
-            k_accumulate<<<gridBig, 256, 0, st>>>(ctx->ctl, ctx->pool, ctx->accum, ctx->accum_sq, ctx->moments);
-            if (timing) cudaEventRecord(ev[9], st);
-            launches += 5;
+            if (timing) cudaEventRecord(ev[7], st);
+            launches += 4;
             used++;
         }
-        (void)activeEstimate;
         CU(cudaMemcpyAsync(ctx->ctl_host, ctx->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (timing)
             for (int b = 0; b < used; b++)
                 for (int k = 0; k < EV_KINDS; k++) {
                     float ms = 0;
-                    cudaEventElapsedTime(&ms, ctx->events[2 + (size_t)b * EV_KINDS * 2 + 2 * k], ctx->events[2 + (size_t)b * EV_KINDS * 2 + 2 * k + 1]);
+                    cudaEventElapsedTime(&ms, ctx->events[4 + (size_t)b * EV_KINDS * 2 + 2 * k], ctx->events[4 + (size_t)b * EV_KINDS * 2 + 2 * k + 1]);
                     msKind[k] += ms;
                 }
         if (getenv("RTX_DEBUG_BATCH"))
-            fprintf(stderr, "[rtx] iter %lld: ms gen/ext/shade/conn/acc %.2f/%.2f/%.2f/%.2f/%.2f active %d next %d shadow %d cursor %llu\n", iter, msKind[0], msKind[1],
-                    msKind[2], msKind[3], msKind[4], ctx->ctl_host->n_active, ctx->ctl_host->n_next, ctx->ctl_host->n_shadow, ctx->ctl_host->cursor);
+            fprintf(stderr, "[rtx] iter %lld: ms gen/ext/shade/conn %.2f/%.2f/%.2f/%.2f active %d next %d shadow %d cursor %llu\n", iter, msKind[0], msKind[1],
+                    msKind[2], msKind[3], ctx->ctl_host->n_active, ctx->ctl_host->n_next, ctx->ctl_host->n_shadow, ctx->ctl_host->cursor);
         if (ctx->ctl_host->done) break;
+    }
+    if (spp > 0) {
+        k_pass_finish<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(ctx->accum, ctx->accum_sq, ctx->per_sample, (int)npix, spp, ctx->moments);
+        launches++;
     }
     CU(cudaEventRecord(evStop, st));
     CU(cudaEventSynchronize(evStop));
@@ -1019,9 +1014,6 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
     s.ms_generate = msKind[EV_GEN]; s.ms_extend = msKind[EV_EXT]; s.ms_shade = msKind[EV_SHADE]; s.ms_connect = msKind[EV_CONN];
     s.ms_total = msTotal;
     s.tlas_nodes = ctx->tlas_nodes; s.blas_nodes = ctx->blas_nodes; s.n_entries = ctx->n_entries; s.n_tris = ctx->n_tris;
-    if (max_depth == 0 && spp > 0) {
-        // every sample is black but still counted: bump the per-pixel sample count only
-    }
     return RTX_OK;
 }
 

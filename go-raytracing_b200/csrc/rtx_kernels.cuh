@@ -47,7 +47,7 @@ struct DevCamera {  // post-Initialize state (rt/camera.go:41-56)
 struct Ctl {  // device-resident control block of the wavefront loop
     unsigned long long cursor, total;  // next path id / paths of this pass
     unsigned long long gen_base;
-    int n_active, n_cont, n_gen, n_free, n_next, n_shadow, n_done;
+    int n_active, n_cont, n_gen, n_next, n_shadow;
     int n_mat[Q_COUNT];
     int done, pad;
     int cur_extend, cur_connect;  // job cursors of the persistent trace kernels
@@ -55,35 +55,35 @@ struct Ctl {  // device-resident control block of the wavefront loop
     unsigned long long ext_rays, shadow_rays, nodes, tris, spheres, quads, planes, iterations;
 };
 
-// Path state, one entry per in-flight path slot. Slots are recycled in arbitrary order, so every access is a gather: the
-// fields of a path are therefore kept TOGETHER in one 256-byte record (two adjacent 128-byte lines: ray + throughput +
-// radiance + pixel in the first, the hit record in the second) instead of seven parallel arrays, which turns seven DRAM
-// rows per path into one. Each field is addressed as base + slot * stride, so the array-per-field layout is the same code
-// with other strides (rtx_set_option "pool_records" = 0, kept for A/B).
+// Path state: a STREAM, not a slot pool. The in-flight paths of one wavefront iteration are the records [0, n_active) of
+// rec[cur]: the survivors of the previous iteration (written by k_shade in the order it appended them) followed by the
+// paths k_generate starts. Ray i of k_extend is record i, its hit lands in hit[i], the material queues hold such indices,
+// and k_shade writes the next ray of a surviving path to the next free record of rec[cur ^ 1]. So every kernel reads and
+// writes path state front to back (k_shade's reads follow the material queues, i.e. k_extend's retire order: a window of a
+// few MB that stays in L2); there is no free list, no slot recycling and no gather over a GB-sized pool.
+// Radiance never travels with the path: every contribution (environment / emission at the end of a path, next-event
+// estimation when its shadow ray arrives unoccluded) is added where it arises, with float atomics, to the pixel's sum —
+// or, when per-sample moments are requested (parity tests), to a per-sample sum that a final pass squares and folds in.
+#define RTX_REC_BYTES 128      /* [ox oy oz time][dx dy dz (pixel | sample << 32)][throughput rgb, bounce | allowLightHits << 16][-] */
+#define RTX_HIT_BYTES 64       /* [Px Py Pz t][Nx Ny Nz (material | front << 31)] */
+#define RTX_SHADOW_BYTES 96    /* [ox oy oz tmax][dx dy dz (pixel | sample << 32)][contribution rgb, bounce][-] */
 struct Pool {
     int capacity;
-    char* ray_o;      // 4 doubles: ox, oy, oz, time
-    char* ray_d;      // 4 doubles: dx, dy, dz, -
-    char* thr;        // float4: throughput rgb, w = bits: bounce | allowLightHits << 16
-    char* rad;        // float4: accumulated radiance rgb
-    char* pix;        // uint2: (pixel index, global sample index)
-    char* hit_p;      // 4 doubles: Px, Py, Pz, t
-    char* hit_n;      // 4 doubles: Nx, Ny, Nz, bits: material | front << 31
-    int st_ray, st_thr, st_pix, st_hit;   // strides in bytes (records: all 256)
-    __device__ __forceinline__ double* f_ray_o(int slot) const { return reinterpret_cast<double*>(ray_o + (size_t)slot * st_ray); }
-    __device__ __forceinline__ double* f_ray_d(int slot) const { return reinterpret_cast<double*>(ray_d + (size_t)slot * st_ray); }
-    __device__ __forceinline__ float4* f_thr(int slot) const { return reinterpret_cast<float4*>(thr + (size_t)slot * st_thr); }
-    __device__ __forceinline__ float4* f_rad(int slot) const { return reinterpret_cast<float4*>(rad + (size_t)slot * st_thr); }
-    __device__ __forceinline__ uint2* f_pix(int slot) const { return reinterpret_cast<uint2*>(pix + (size_t)slot * st_pix); }
-    __device__ __forceinline__ double* f_hit_p(int slot) const { return reinterpret_cast<double*>(hit_p + (size_t)slot * st_hit); }
-    __device__ __forceinline__ double* f_hit_n(int slot) const { return reinterpret_cast<double*>(hit_n + (size_t)slot * st_hit); }
-    int* q_a;         // active queue, ping
-    int* q_b;         // active queue, pong
-    int* q_free;      // free-slot stack
-    int* q_mat;       // [Q_COUNT * P] material-sorted shading queues
-    int* q_done;      // finished paths awaiting accumulation
-    double2* sh_d;    // [2 * 2P] shadow requests: (dx,dy) (dz,tmax)
-    float4* sh_c;     // [2P] contribution rgb, w = bits: slot | kind << 30
+    char* rec[2];     // path records, ping-pong
+    char* hit;        // hit record of job i of the current iteration
+    int* q_mat;       // [Q_COUNT * P] material-sorted shading queues (job indices)
+    char* shadow;     // [2P] shadow requests of the current iteration, self-contained
+    float* target;    // where radiance goes: float4 per pixel (accumulation buffer) or, with moments, float4 per sample of this pass
+    int moments;
+    uint32_t npix, sample_base;
+    __device__ __forceinline__ float* contribution_target(uint32_t pixel, uint32_t sample) const {
+        return target + 4 * (moments ? (size_t)(sample - sample_base) * npix + pixel : (size_t)pixel);
+    }
+    __device__ __forceinline__ void contribute(uint32_t pixel, uint32_t sample, float r, float g, float b) const {
+        if (r == 0.f && g == 0.f && b == 0.f) return;
+        float* t = contribution_target(pixel, sample);
+        atomicAdd(t + 0, r); atomicAdd(t + 1, g); atomicAdd(t + 2, b);
+    }
 };
 
 struct PassParams {
@@ -105,18 +105,17 @@ __device__ __forceinline__ int warp_append(int* counter, bool pred) {
 }
 
 // ---- K0: iteration bookkeeping ---------------------------------------------------------------------------------
-__global__ void k_iter_begin(Ctl* ctl) {
+__global__ void k_iter_begin(Ctl* ctl, int capacity) {
     if (threadIdx.x != 0) return;
-    int n_cont = ctl->n_next;
+    int n_cont = ctl->n_next;   // survivors: records [0, n_cont) of the buffer k_shade just wrote
     unsigned long long remaining = ctl->total - ctl->cursor;
-    int n_gen = (int)min((unsigned long long)ctl->n_free, remaining);
+    int n_gen = (int)min((unsigned long long)(capacity - n_cont), remaining);
     ctl->gen_base = ctl->cursor;
     ctl->cursor += n_gen;
-    ctl->n_free -= n_gen;
     ctl->n_cont = n_cont;
     ctl->n_gen = n_gen;
     ctl->n_active = n_cont + n_gen;
-    ctl->n_next = 0; ctl->n_shadow = 0; ctl->n_done = 0;
+    ctl->n_next = 0; ctl->n_shadow = 0;
     ctl->cur_extend = 0; ctl->cur_connect = 0;
     for (int i = 0; i < Q_COUNT; i++) ctl->n_mat[i] = 0;
     ctl->done = (n_cont + n_gen == 0);
@@ -156,10 +155,9 @@ __device__ __forceinline__ RayD camera_ray(const DevCamera& C, int i, int j, dou
 // The stream kernels (generate / shade / accumulate) run on a fixed grid (a few blocks per SM) and stride over the work the
 // device-side control block announces: the host never learns the queue lengths, and a launch sized for the whole pool
 // (16 K blocks) costs ~70 us of block scheduling even when a handful of paths are left.
-__global__ void __launch_bounds__(256) k_generate(Ctl* ctl, Pool pool, int* q_cur, DevCamera C, PassParams pp) {
-  const int n_gen = ctl->n_gen;
+__global__ void __launch_bounds__(256) k_generate(Ctl* ctl, Pool pool, int cur, DevCamera C, PassParams pp) {
+  const int n_gen = ctl->n_gen, n_cont = ctl->n_cont;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_gen; i += gridDim.x * blockDim.x) {
-    int slot = pool.q_free[ctl->n_free + i];
     unsigned long long pid = ctl->gen_base + (unsigned long long)i;
     unsigned npix = (unsigned)C.width * (unsigned)C.height;
     uint32_t sample = pp.sample_base + (uint32_t)(pid / npix);
@@ -176,12 +174,10 @@ __global__ void __launch_bounds__(256) k_generate(Ctl* ctl, Pool pool, int* q_cu
         lx = rr * cs; ly = rr * sn;
     }
     RayD r = camera_ray(C, px, py, offx, offy, tm, lx, ly);
-    st256d(pool.f_ray_o(slot), r.ox, r.oy, r.oz, r.tm);
-    st256d(pool.f_ray_d(slot), r.dx, r.dy, r.dz, 0.0);
-    *pool.f_thr(slot) = make_float4(1.f, 1.f, 1.f, __int_as_float(0 | (1 << 16)));
-    *pool.f_rad(slot) = make_float4(0.f, 0.f, 0.f, 0.f);
-    *pool.f_pix(slot) = make_uint2(pixel, sample);
-    q_cur[ctl->n_cont + i] = slot;
+    char* rec = pool.rec[cur] + (size_t)(n_cont + i) * RTX_REC_BYTES;   // appended behind the survivors
+    st256d(rec, r.ox, r.oy, r.oz, r.tm);
+    st256d(rec + 32, r.dx, r.dy, r.dz, __longlong_as_double((long long)(((unsigned long long)sample << 32) | pixel)));
+    *reinterpret_cast<float4*>(rec + 64) = make_float4(1.f, 1.f, 1.f, __int_as_float(0 | (1 << 16)));
   }
 }
 
@@ -205,33 +201,33 @@ extern __shared__ __align__(16) unsigned char rtx_smem[];  // the trace kernels'
 // ---- K2: extend — closest hit of every active path, then binning into material-sorted shading queues -------------
 struct ExtendPolicy {
     static constexpr bool ANY_HIT = false;
-    Ctl* ctl; Pool pool; const int* q_cur; const DevScene* S; uint32_t seed_lo, seed_hi;
+    Ctl* ctl; Pool pool; const char* rec; const DevScene* S; uint32_t seed_lo, seed_hi;
     __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:451
     __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
-        const int slot = q_cur[job];
-        const D4 a = ld256d(pool.f_ray_o(slot)), c = ld256d(pool.f_ray_d(slot));
+        const char* q = rec + (size_t)job * RTX_REC_BYTES;
+        const D4 a = ld256d(q), c = ld256d(q + 32);
         r.ox = a.x; r.oy = a.y; r.oz = a.z; r.tm = a.w; r.dx = c.x; r.dy = c.y; r.dz = c.z;
         tmax = RTX_INF_D;
     }
     __device__ __forceinline__ VolumeRng volume_rng(int job) const {
-        const int slot = q_cur[job];
-        const uint2 ps = *pool.f_pix(slot);
-        const int bounce = __float_as_int(pool.f_thr(slot)->w) & 0xffff;
-        VolumeRng vr; vr.k0 = seed_lo; vr.k1 = seed_hi; vr.c0 = ps.x; vr.c1 = ps.y; vr.c2 = (uint32_t)bounce * 4u; vr.transparent = false;
+        const char* q = rec + (size_t)job * RTX_REC_BYTES;
+        const unsigned long long ps = (unsigned long long)__double_as_longlong(ld256d(q + 32).w);
+        const int bounce = __float_as_int(reinterpret_cast<const float4*>(q + 64)->w) & 0xffff;
+        VolumeRng vr; vr.k0 = seed_lo; vr.k1 = seed_hi; vr.c0 = (uint32_t)ps; vr.c1 = (uint32_t)(ps >> 32); vr.c2 = (uint32_t)bounce * 4u; vr.transparent = false;
         return vr;
     }
     __device__ __forceinline__ void retire(int job, bool valid, const RayD& r, const Best& b) const {
-        int q = -1, slot = -1;
+        int q = -1;
         if (valid) {
-            slot = q_cur[job];
             if (b.entry < 0) {
                 q = Q_MISS;
             } else {
                 HitInfo hi;
                 finalize_hit(*S, r, best_to_hit(b), false, hi);
                 const long long bits = (long long)(unsigned)hi.mat | (hi.front ? (1LL << 31) : 0);
-                st256d(pool.f_hit_p(slot), hi.P.x, hi.P.y, hi.P.z, b.t);
-                st256d(pool.f_hit_n(slot), hi.N.x, hi.N.y, hi.N.z, __longlong_as_double(bits));
+                char* h = pool.hit + (size_t)job * RTX_HIT_BYTES;
+                st256d(h, hi.P.x, hi.P.y, hi.P.z, b.t);
+                st256d(h + 32, hi.N.x, hi.N.y, hi.N.z, __longlong_as_double(bits));
                 const int mt = S->mats[hi.mat].type;
                 q = mt == RTX_MAT_LAMBERTIAN ? Q_LAMBERTIAN : mt == RTX_MAT_METAL ? Q_METAL : mt == RTX_MAT_DIELECTRIC ? Q_DIELECTRIC
                     : mt == RTX_MAT_DIFFUSE_LIGHT ? Q_LIGHT : Q_ISOTROPIC;
@@ -241,14 +237,14 @@ struct ExtendPolicy {
 #pragma unroll
         for (int k = 0; k < Q_COUNT; k++) {
             const int pos = warp_append(&ctl->n_mat[k], q == k);
-            if (q == k) pool.q_mat[(size_t)k * pool.capacity + pos] = slot;
+            if (q == k) pool.q_mat[(size_t)k * pool.capacity + pos] = job;
         }
     }
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_extend(Ctl* ctl, Pool pool, const int* q_cur, const __grid_constant__ DevScene S, PassParams pp, int* spill) {
-    ExtendPolicy P{ctl, pool, q_cur, &S, pp.seed_lo, pp.seed_hi};
+__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_extend(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, PassParams pp, int* spill) {
+    ExtendPolicy P{ctl, pool, pool.rec[cur], &S, pp.seed_lo, pp.seed_hi};
     TraceCounters tc = {0, 0, 0, 0, 0};
     const int n = ctl->n_active;
     trace_persistent<ExtendPolicy, COUNT, RTX_TRACE_SLOTS>(S, P, &ctl->cur_extend, n, tc, spill, rtx_smem);
@@ -344,7 +340,7 @@ __device__ __forceinline__ D3 unit_sphere(uint32_t a, uint32_t b) {
 }
 
 // ---- K4: shade — one thread per queue element, queues concatenated in material order --------------------------------
-__global__ void __launch_bounds__(256) k_shade(Ctl* ctl, Pool pool, int* q_next, DevScene S, DevCamera C, PassParams pp) {
+__global__ void __launch_bounds__(256) k_shade(Ctl* ctl, Pool pool, int cur, DevScene S, DevCamera C, PassParams pp) {
   const int n_rounded = (ctl->n_active + 31) & ~31;   // whole warps stay together for the queue appends
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rounded; i += gridDim.x * blockDim.x) {
     // locate (queue, index): prefix over the six queue counts
@@ -358,24 +354,30 @@ __global__ void __launch_bounds__(256) k_shade(Ctl* ctl, Pool pool, int* q_next,
         }
     }
     bool valid = type >= 0;
-    bool cont = false, finished = false;
-    int slot = -1;
+    bool cont = false;
+    // the path's next record (written only if it survives) and, for the shadow requests, its identity and hit point
+    D3 P = d3(0, 0, 0), nd = d3(0, 0, 0);
+    double tm = 0, pixbits = 0;
+    float4 th = make_float4(0, 0, 0, 0);
+    int bounce0 = 0;
     // up to two shadow requests per Lambertian hit, in fixed registers (no dynamically indexed arrays: those live in local memory)
     bool has_env = false, has_area = false;
     D3 env_dir = d3(0, 0, 0), area_dir = d3(0, 0, 0);
     double area_tmax = 0;
     float3 env_c = make_float3(0, 0, 0), area_c = make_float3(0, 0, 0);
     if (valid) {
-        slot = pool.q_mat[(size_t)type * pool.capacity + idx];
-        const D4 ro4 = ld256d(pool.f_ray_o(slot)), rd4 = ld256d(pool.f_ray_d(slot));
+        const int job = pool.q_mat[(size_t)type * pool.capacity + idx];
+        const char* rec = pool.rec[cur] + (size_t)job * RTX_REC_BYTES;
+        const D4 ro4 = ld256d(rec), rd4 = ld256d(rec + 32);
         D3 rd = d3(rd4.x, rd4.y, rd4.z);
-        double tm = ro4.w;
-        float4 th = *pool.f_thr(slot);
-        float4 L = *pool.f_rad(slot);
+        tm = ro4.w; pixbits = rd4.w;
+        th = *reinterpret_cast<const float4*>(rec + 64);
         int flags = __float_as_int(th.w);
         int bounce = flags & 0xffff;
+        bounce0 = bounce;
         bool allow = (flags >> 16) & 1;
-        uint2 ps = *pool.f_pix(slot);
+        const unsigned long long psb = (unsigned long long)__double_as_longlong(pixbits);
+        uint2 ps = make_uint2((uint32_t)psb, (uint32_t)(psb >> 32));
         if (type == Q_MISS) {  // rt/camera.go:451-466
             float3 col;
             if (S.env_w > 0) {
@@ -387,11 +389,12 @@ __global__ void __launch_bounds__(256) k_shade(Ctl* ctl, Pool pool, int* q_next,
                 float t = (float)(0.5 * (ud.y + 1.0));
                 col = make_float3((1.f - t) + 0.5f * t, (1.f - t) + 0.7f * t, (1.f - t) + 1.0f * t);
             } else col = make_float3(C.background[0], C.background[1], C.background[2]);
-            L.x += th.x * col.x; L.y += th.y * col.y; L.z += th.z * col.z;
-            finished = true;
+            pool.contribute(ps.x, ps.y, th.x * col.x, th.y * col.y, th.z * col.z);
         } else {
-            const D4 hp = ld256d(pool.f_hit_p(slot)), hn = ld256d(pool.f_hit_n(slot));
-            D3 P = d3(hp.x, hp.y, hp.z), N = d3(hn.x, hn.y, hn.z);
+            const char* hrec = pool.hit + (size_t)job * RTX_HIT_BYTES;
+            const D4 hp = ld256d(hrec), hn = ld256d(hrec + 32);
+            P = d3(hp.x, hp.y, hp.z);
+            D3 N = d3(hn.x, hn.y, hn.z);
             long long bits = __double_as_longlong(hn.w);
             int mat = (int)(bits & 0x7fffffff);
             bool front = (bits >> 31) & 1;
@@ -399,12 +402,10 @@ __global__ void __launch_bounds__(256) k_shade(Ctl* ctl, Pool pool, int* q_next,
             if (type == Q_LIGHT) {  // Scatter == false: rt/camera.go:473-481, rt/material.go:226-236
                 if (allow) {
                     float3 e = tex_value(S, M.tex, P);
-                    L.x += th.x * e.x; L.y += th.y * e.y; L.z += th.z * e.z;
+                    pool.contribute(ps.x, ps.y, th.x * e.x, th.y * e.y, th.z * e.z);
                 }
-                finished = true;
             } else {
                 uint4 rs = philox4x32(ps.x, ps.y, (uint32_t)bounce, STREAM_SCATTER, pp.seed_lo, pp.seed_hi);
-                D3 nd;
                 float3 att;
                 bool scattered = true, next_allow = true;
                 if (type == Q_LAMBERTIAN) {  // rt/material.go:57-68
@@ -489,36 +490,38 @@ __global__ void __launch_bounds__(256) k_shade(Ctl* ctl, Pool pool, int* q_next,
                     att = tex_value(S, M.tex, P);
                 }
                 if (!scattered) {
-                    finished = true;  // absorbed: emission of a scattering material is zero
-                    has_env = has_area = false;
+                    has_env = has_area = false;  // absorbed: emission of a scattering material is zero
                 } else {
                     th.x *= att.x; th.y *= att.y; th.z *= att.z;
                     bounce++;
                     th.w = __int_as_float((bounce & 0xffff) | (next_allow ? (1 << 16) : 0));
-                    st256d(pool.f_ray_o(slot), P.x, P.y, P.z, tm);
-                    st256d(pool.f_ray_d(slot), nd.x, nd.y, nd.z, 0.0);
-                    *pool.f_thr(slot) = th;
-                    if (bounce >= pp.max_depth) finished = true;  // rayColorInternal(depth <= 0) returns black (:444-446)
-                    else cont = true;
+                    cont = bounce < pp.max_depth;  // rayColorInternal(depth <= 0) returns black (:444-446)
                 }
             }
         }
-        if (finished) *pool.f_rad(slot) = L;
     }
-    int pos = warp_append(&ctl->n_next, cont);
-    if (cont) q_next[pos] = slot;
-    pos = warp_append(&ctl->n_done, finished);
-    if (finished) pool.q_done[pos] = slot;
-    {
+    // survivors: the next ray goes to the next free record of the other buffer, in the order the warps arrive
+    const int pos = warp_append(&ctl->n_next, cont);
+    if (cont) {
+        char* out = pool.rec[cur ^ 1] + (size_t)pos * RTX_REC_BYTES;
+        st256d(out, P.x, P.y, P.z, tm);
+        st256d(out + 32, nd.x, nd.y, nd.z, pixbits);
+        *reinterpret_cast<float4*>(out + 64) = th;
+    }
+    {   // shadow requests carry everything k_connect needs (origin = the hit point, where the contribution goes)
         int sp = warp_append(&ctl->n_shadow, has_env);
         if (has_env) {
-            st256d(pool.sh_d + 2 * sp, env_dir.x, env_dir.y, env_dir.z, RTX_INF_D);
-            pool.sh_c[sp] = make_float4(env_c.x, env_c.y, env_c.z, __int_as_float(slot));
+            char* q = pool.shadow + (size_t)sp * RTX_SHADOW_BYTES;
+            st256d(q, P.x, P.y, P.z, RTX_INF_D);
+            st256d(q + 32, env_dir.x, env_dir.y, env_dir.z, pixbits);
+            *reinterpret_cast<float4*>(q + 64) = make_float4(env_c.x, env_c.y, env_c.z, __int_as_float(bounce0));
         }
         sp = warp_append(&ctl->n_shadow, has_area);
         if (has_area) {
-            st256d(pool.sh_d + 2 * sp, area_dir.x, area_dir.y, area_dir.z, area_tmax);
-            pool.sh_c[sp] = make_float4(area_c.x, area_c.y, area_c.z, __int_as_float(slot));
+            char* q = pool.shadow + (size_t)sp * RTX_SHADOW_BYTES;
+            st256d(q, P.x, P.y, P.z, area_tmax);
+            st256d(q + 32, area_dir.x, area_dir.y, area_dir.z, pixbits);
+            *reinterpret_cast<float4*>(q + 64) = make_float4(area_c.x, area_c.y, area_c.z, __int_as_float(bounce0));
         }
     }
   }
@@ -530,29 +533,26 @@ struct ConnectPolicy {
     Pool pool; uint32_t seed_lo, seed_hi;
     __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:579, :636
     __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
-        const int slot = __float_as_int(pool.sh_c[job].w);
-        const D4 o0 = ld256d(pool.f_ray_o(slot)), d0 = ld256d(pool.sh_d + 2 * job);
+        const char* q = pool.shadow + (size_t)job * RTX_SHADOW_BYTES;
+        const D4 o0 = ld256d(q), d0 = ld256d(q + 32);
         r.ox = o0.x; r.oy = o0.y; r.oz = o0.z; r.dx = d0.x; r.dy = d0.y; r.dz = d0.z; r.tm = 0;  // NewRay(hitPoint, lightDir, 0)
-        tmax = d0.w;
+        tmax = o0.w;
     }
     __device__ __forceinline__ VolumeRng volume_rng(int job) const {
-        const int slot = __float_as_int(pool.sh_c[job].w);
-        const uint2 ps = *pool.f_pix(slot);
-        // shade already advanced the bounce counter of the path: the shadow ray belongs to the bounce before it
-        const int bounce = (__float_as_int(pool.f_thr(slot)->w) & 0xffff) - 1;
-        const double tmax = pool.sh_d[2 * job + 1].y;
-        VolumeRng vr; vr.k0 = seed_lo; vr.k1 = seed_hi; vr.c0 = ps.x; vr.c1 = ps.y;
+        const char* q = pool.shadow + (size_t)job * RTX_SHADOW_BYTES;
+        const unsigned long long ps = (unsigned long long)__double_as_longlong(ld256d(q + 32).w);
+        const int bounce = __float_as_int(reinterpret_cast<const float4*>(q + 64)->w);   // the bounce whose hit issued the request
+        const double tmax = ld256d(q).w;
+        VolumeRng vr; vr.k0 = seed_lo; vr.k1 = seed_hi; vr.c0 = (uint32_t)ps; vr.c1 = (uint32_t)(ps >> 32);
         vr.c2 = (uint32_t)bounce * 4u + (tmax == RTX_INF_D ? 2u : 1u); vr.transparent = false;
         return vr;
     }
     __device__ __forceinline__ void retire(int job, bool valid, const RayD&, const Best& b) const {
-        if (valid && b.entry < 0) {
-            const float4 cc = pool.sh_c[job];
-            const int slot = __float_as_int(cc.w);
-            float* L = reinterpret_cast<float*>(pool.f_rad(slot));
-            atomicAdd(L + 0, cc.x);
-            atomicAdd(L + 1, cc.y);
-            atomicAdd(L + 2, cc.z);
+        if (valid && b.entry < 0) {   // unoccluded: the contribution shade prepared arrives
+            const char* q = pool.shadow + (size_t)job * RTX_SHADOW_BYTES;
+            const unsigned long long ps = (unsigned long long)__double_as_longlong(ld256d(q + 32).w);
+            const float4 cc = *reinterpret_cast<const float4*>(q + 64);
+            pool.contribute((uint32_t)ps, (uint32_t)(ps >> 32), cc.x, cc.y, cc.z);
         }
     }
 };
@@ -567,26 +567,22 @@ __global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_connect
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->shadow_rays, (unsigned long long)n);
 }
 
-// ---- K6a: accumulate finished paths into the per-pixel sums, recycle their slots --------------------------------------
-__global__ void __launch_bounds__(256) k_accumulate(Ctl* ctl, Pool pool, float4* accum, float4* accum_sq, int moments) {
-  const int n_done = ctl->n_done, n_rounded = (n_done + 31) & ~31;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rounded; i += gridDim.x * blockDim.x) {
-    bool valid = i < n_done;
-    int slot = -1;
-    if (valid) {
-        slot = pool.q_done[i];
-        float4 L = *pool.f_rad(slot);
-        uint32_t pixel = pool.f_pix(slot)->x;
-        float* a = reinterpret_cast<float*>(accum + pixel);
-        atomicAdd(a + 0, L.x); atomicAdd(a + 1, L.y); atomicAdd(a + 2, L.z); atomicAdd(a + 3, 1.0f);
-        if (moments) {
-            float* s = reinterpret_cast<float*>(accum_sq + pixel);
-            atomicAdd(s + 0, L.x * L.x); atomicAdd(s + 1, L.y * L.y); atomicAdd(s + 2, L.z * L.z);
+// ---- K6a: end of a pass — every pixel received `spp` samples; with moments, fold the per-sample sums into sum and sum of squares ----
+__global__ void __launch_bounds__(256) k_pass_finish(float4* accum, float4* accum_sq, const float4* per_sample, int npix, int spp, int moments) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    float4 a = accum[i];
+    if (moments) {
+        float4 q = accum_sq[i];
+        for (int s = 0; s < spp; s++) {
+            const float4 L = per_sample[(size_t)s * npix + i];
+            a.x += L.x; a.y += L.y; a.z += L.z;
+            q.x += L.x * L.x; q.y += L.y * L.y; q.z += L.z * L.z;
         }
+        accum_sq[i] = q;
     }
-    int pos = warp_append(&ctl->n_free, valid);
-    if (valid) pool.q_free[pos] = slot;
-  }
+    a.w += (float)spp;
+    accum[i] = a;
 }
 
 // ---- K6b: resolve (rt/bucket_renderer.go:275-285, rt/utils.go:85-90) -----------------------------------------------------
@@ -603,11 +599,6 @@ __global__ void k_resolve_rgba8(const float4* accum, int npix, double scale, uch
         o[k] = (unsigned char)(256 * g);
     }
     out[i] = make_uchar4(o[0], o[1], o[2], 255);
-}
-
-__global__ void k_pool_init(Pool pool, Ctl* ctl) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < pool.capacity) pool.q_free[i] = pool.capacity - 1 - i;
 }
 
 // ---- batch entry points for the parity tests ----------------------------------------------------------------------------
