@@ -28,8 +28,9 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
         sys.path.insert(0, p)
 
 # algorithmic bytes per unit of work of the extend kernel
-NODE_BYTES, TRI_BYTES, SPHERE_BYTES, QUAD_BYTES, PLANE_BYTES = 128, 80, 64, 128, 64
-RAY_STATE_BYTES = 64 + 64 + 8 + 16 + 8   # ray in, hit record out, two queue slots, throughput flags, (pixel,sample)
+NODE_BYTES, TRI_BYTES, SPHERE_BYTES, QUAD_BYTES, PLANE_BYTES = 128, 96, 64, 128, 64
+RAY_STATE_BYTES = 64 + 64 + 4 + 28      # ray in (64 of the 96-byte path record), hit record out, queue slot; 160 B as in SURVEY 8d
+REC_BYTES, HIT_BYTES, SHADOW_BYTES = 96, 64, 96   # used bytes of a path record / hit record / shadow request (csrc/rtx_kernels.cuh)
 
 
 def parse():
@@ -245,6 +246,7 @@ def main():
     # whole-job ray / launch counts (sum over ranks)
     tot = torch.tensor([sum(s["extension_rays"] for s in stats), sum(s["shadow_rays"] for s in stats), sum(s["kernel_launches"] for s in stats),
                         sum(s["ms_extend"] for s in stats), sum(s["ms_total"] for s in stats)], dtype=torch.float64, device="cuda")
+    my_ms_shade, my_ms_gen, my_sh_rays = sum(s["ms_shade"] for s in stats), sum(s["ms_generate"] for s in stats), sum(s["shadow_rays"] for s in stats)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     ext_rays, sh_rays, launches, ms_extend_sum, ms_total_sum = [float(x) for x in tot.tolist()]
@@ -287,7 +289,7 @@ def main():
         traffic = None   # dram bytes of one k_extend launch from the committed ncu --set full capture, scaled to this run's average launch
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k_extend_traffic.json")))
-            traffic = tj["dram_bytes_per_ray"] * my_ext_rays / max(n_launch_pre := sum(s["wavefront_iterations"] for s in stats if "wavefront_iterations" in s), 1)
+            traffic = tj["dram_bytes_per_ray"] * my_ext_rays / max(n_launch, 1)
         except Exception:
             traffic = None
         roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -297,6 +299,21 @@ def main():
                     "avg_launch_ms": my_ms_extend / max(n_launch, 1), "kernel_share_of_step": my_ms_extend / max(sum(s["ms_total"] for s in stats), 1e-9),
                     "note": "algorithmic bytes = wide-BVH nodes + primitives fetched per extension ray (instrumented pass) + per-ray wavefront state; "
                             "the scene fits in the 126 MB L2, so node/primitive fetches are served by L2, not HBM"}
+
+    # the stream kernels (HBM-bound): algorithmic bytes of this rank's slice / their CUDA-event time
+    roofline_stream = None
+    if roofline is not None:
+        my_paths = npix * count * args.steps
+        shade_bytes = my_ext_rays * (4 + REC_BYTES + HIT_BYTES) + max(my_ext_rays - my_paths, 0) * REC_BYTES + my_sh_rays * SHADOW_BYTES
+        gen_bytes = my_paths * REC_BYTES
+        pk = roofline["peak"]
+        roofline_stream = [
+            {"kernel": "k_shade", "bound": "hbm", "achieved": shade_bytes / max(my_ms_shade, 1e-9) / 1e6, "unit": "GB/s", "peak": pk,
+             "frac": shade_bytes / max(my_ms_shade, 1e-9) / 1e6 / pk, "share_of_step": my_ms_shade / max(sum(s["ms_total"] for s in stats), 1e-9),
+             "bytes": "per ray: queue slot 4 + path record 96 + hit record 64 read; per surviving path 96 written; per shadow request 96 written"},
+            {"kernel": "k_generate", "bound": "hbm", "achieved": gen_bytes / max(my_ms_gen, 1e-9) / 1e6, "unit": "GB/s", "peak": pk,
+             "frac": gen_bytes / max(my_ms_gen, 1e-9) / 1e6 / pk, "share_of_step": my_ms_gen / max(sum(s["ms_total"] for s in stats), 1e-9),
+             "bytes": "per path: 96-byte record written"}]
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -322,7 +339,7 @@ def main():
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": cfg(sc), "mrays_per_s": (ext_rays + sh_rays) / sec / 1e6, "rays_per_path": (ext_rays + sh_rays) / max(npix * spp * args.steps, 1),
             "wall_ms_per_step": wall * 1e3 / args.steps, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches) + args.steps,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "roofline_stream": roofline_stream, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     barrier()

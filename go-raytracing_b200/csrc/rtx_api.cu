@@ -59,7 +59,7 @@ struct rtx_ctx {
     // path pool
     Pool pool{};
     std::vector<void*> pool_allocs;
-    int64_t pool_paths = 1 << 22;  // in-flight path slots: persistent trace launches have a fixed tail, so few big launches beat many small ones (1 Mi: 123, 4 Mi: 137 Mpaths/s)
+    int64_t pool_paths = 1 << 23;  // in-flight paths per iteration: persistent trace launches have a fixed tail, so few big launches beat many small ones (cornell-lucy, 64 spp: 2 Mi 187, 4 Mi 198, 8 Mi 204 Mpaths/s)
     Ctl* ctl = nullptr;       // device
     Ctl* ctl_host = nullptr;  // pinned
     int count_stats = 0, time_kernels = 1, blas_leaf = 4;

@@ -14,7 +14,11 @@ python bench.py --spp 4 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $out/$
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --spp 4 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $out/${tag}_ncu_l.log 2>&1
 python tools/gpu_perf.py cornell-lucy 24 > $out/${tag}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_extend -s 40 -c 1 -f -o $out/${tag}_prof_extend \
+ncu --set full --clock-control none --import-source on -k regex:k_extend -s 10 -c 1 -f -o $out/${tag}_prof_extend \
     python tools/gpu_perf.py cornell-lucy 24 > $out/${tag}_ncu.log 2>&1
 tail -2 $out/${tag}_ncu.log
 fi
+# per-scene throughput table (short passes) and pool-size A/B
+for s in cornell random cornell-glossy cornell-lucy hdri-test; do python tools/gpu_perf.py $s 64 2>&1 | tail -1; done > $out/${tag}_scenes.log
+for pp in 2097152 8388608; do RTX_OPTS=pool_paths=$pp python tools/gpu_perf.py cornell-lucy 64 2>&1 | tail -1; RTX_OPTS=pool_paths=$pp python tools/gpu_perf.py hdri-test 32 2>&1 | tail -1; done >> $out/${tag}_scenes.log
+cat $out/${tag}_scenes.log
