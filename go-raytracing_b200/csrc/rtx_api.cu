@@ -64,6 +64,7 @@ struct rtx_ctx {
     Ctl* ctl_host = nullptr;  // pinned
     int count_stats = 0, time_kernels = 1, blas_leaf = 4;
     float4* per_sample = nullptr; size_t per_sample_cap = 0;   // moments mode: per-sample radiance sums of the running pass (grow-only)
+    int pixel_major = 1;  // path order of k_generate: all samples of a pixel consecutively (1) or sample-major (0)
     int bvh_device = 1;   // mesh BLAS construction on the device (rtx_bvh_gpu.cuh); 0 = host builder (rtx_bvh.hpp), kept for A/B
     double ms_upload_blas = 0, ms_upload_total = 0;
     int blas_depth = 0, built_on_device = 0;
@@ -247,6 +248,7 @@ int32_t rtx_set_option(rtx_ctx* ctx, const char* key, int64_t value) {
     } else if (k == "count_stats") ctx->count_stats = (int)value;  // bit 0: extend kernel, bit 1: connect kernel
     else if (k == "time_kernels") ctx->time_kernels = value != 0;
     else if (k == "l2_persist") { ctx->l2_persist = value != 0; ctx->window_set = false; }  // L2 persisting window over the scene geometry (default off)
+    else if (k == "pixel_major") ctx->pixel_major = value != 0;
     else if (k == "bvh_device") ctx->bvh_device = value != 0;  // takes effect at the next rtx_scene_upload
     else if (k == "blas_leaf") {  // triangles per BLAS leaf (1..8); takes effect at the next rtx_scene_upload
         if (value < 1 || value > 8) return fail(ctx, RTX_ERR_INVALID, "blas_leaf must be in 1..8");
@@ -918,7 +920,7 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
     PassParams pp{};
     pp.spp = spp; pp.max_depth = max_depth; pp.camera_max_depth = camera_max_depth;
     pp.seed_lo = (uint32_t)seed; pp.seed_hi = (uint32_t)(seed >> 32); pp.sample_base = sample_base;
-    pp.moments = ctx->moments; pp.count_stats = ctx->count_stats;
+    pp.moments = ctx->moments; pp.count_stats = ctx->count_stats; pp.pixel_major = ctx->pixel_major;
 
     const unsigned long long npix = (unsigned long long)ctx->W * ctx->H;
     Ctl init{};
@@ -971,7 +973,7 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
             if (ctx->count_stats & 1) k_extend<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
             else k_extend<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
             if (timing) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); }
-            k_shade<<<gridStream, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, ctx->C, pp);
+            k_shade<<<std::min((P + 255) / 256, ctx->num_sms * 2 * RTX_SHADE_BLOCKS), 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, ctx->C, pp);
             if (timing) { cudaEventRecord(ev[5], st); cudaEventRecord(ev[6], st); }
             if (ctx->S.n_lights > 0) {
                 if (ctx->count_stats & 2) k_connect<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, ctx->S, pp, ctx->trace_spill);

@@ -89,7 +89,7 @@ struct Pool {
 struct PassParams {
     int spp, max_depth, camera_max_depth;
     uint32_t seed_lo, seed_hi, sample_base;
-    int moments, count_stats;
+    int moments, count_stats, pixel_major;
 };
 
 // warp-aggregated queue append: one atomic per warp (ballot + popc), returns this lane's position
@@ -160,8 +160,11 @@ __global__ void __launch_bounds__(256) k_generate(Ctl* ctl, Pool pool, int cur, 
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_gen; i += gridDim.x * blockDim.x) {
     unsigned long long pid = ctl->gen_base + (unsigned long long)i;
     unsigned npix = (unsigned)C.width * (unsigned)C.height;
-    uint32_t sample = pp.sample_base + (uint32_t)(pid / npix);
-    uint32_t pixel = (uint32_t)(pid % npix);
+    // path order: pixel-major (all samples of a pixel are consecutive paths) keeps the pixels in flight few, so the radiance
+    // atomics stay in L2 and neighbouring lanes start with nearly the same ray; sample-major is the other order
+    uint32_t sample, pixel;
+    if (pp.pixel_major) { pixel = (uint32_t)(pid / (unsigned)pp.spp); sample = pp.sample_base + (uint32_t)(pid % (unsigned)pp.spp); }
+    else { sample = pp.sample_base + (uint32_t)(pid / npix); pixel = (uint32_t)(pid % npix); }
     int px = pixel % C.width, py = pixel / C.width;
     uint4 r0 = philox4x32(pixel, sample, 0, STREAM_CAMERA, pp.seed_lo, pp.seed_hi);
     double offx = u01(r0.x) - 0.5, offy = u01(r0.y) - 0.5, tm = u01(r0.z);
@@ -340,7 +343,10 @@ __device__ __forceinline__ D3 unit_sphere(uint32_t a, uint32_t b) {
 }
 
 // ---- K4: shade — one thread per queue element, queues concatenated in material order --------------------------------
-__global__ void __launch_bounds__(256) k_shade(Ctl* ctl, Pool pool, int cur, DevScene S, DevCamera C, PassParams pp) {
+#ifndef RTX_SHADE_BLOCKS
+#define RTX_SHADE_BLOCKS 2   /* resident 256-thread blocks per SM k_shade is compiled for */
+#endif
+__global__ void __launch_bounds__(256, RTX_SHADE_BLOCKS) k_shade(Ctl* ctl, Pool pool, int cur, DevScene S, DevCamera C, PassParams pp) {
   const int n_rounded = (ctl->n_active + 31) & ~31;   // whole warps stay together for the queue appends
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rounded; i += gridDim.x * blockDim.x) {
     // locate (queue, index): prefix over the six queue counts
