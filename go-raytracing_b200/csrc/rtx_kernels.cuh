@@ -76,6 +76,7 @@ struct Pool {
     float* target;    // where radiance goes: float4 per pixel (accumulation buffer) or, with moments, float4 per sample of this pass
     int moments;
     uint32_t npix, sample_base;
+    __device__ __forceinline__ char* records(int which) const { return which ? rec[1] : rec[0]; }   // (no dynamic indexing of a kernel parameter)
     __device__ __forceinline__ float* contribution_target(uint32_t pixel, uint32_t sample) const {
         return target + 4 * (moments ? (size_t)(sample - sample_base) * npix + pixel : (size_t)pixel);
     }
@@ -155,7 +156,7 @@ __device__ __forceinline__ RayD camera_ray(const DevCamera& C, int i, int j, dou
 // The stream kernels (generate / shade / accumulate) run on a fixed grid (a few blocks per SM) and stride over the work the
 // device-side control block announces: the host never learns the queue lengths, and a launch sized for the whole pool
 // (16 K blocks) costs ~70 us of block scheduling even when a handful of paths are left.
-__global__ void __launch_bounds__(256) k_generate(Ctl* ctl, Pool pool, int cur, DevCamera C, PassParams pp) {
+__global__ void __launch_bounds__(256, 4) k_generate(Ctl* ctl, Pool pool, int cur, DevCamera C, PassParams pp) {
   const int n_gen = ctl->n_gen, n_cont = ctl->n_cont;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_gen; i += gridDim.x * blockDim.x) {
     unsigned long long pid = ctl->gen_base + (unsigned long long)i;
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(256) k_generate(Ctl* ctl, Pool pool, int cur, 
         lx = rr * cs; ly = rr * sn;
     }
     RayD r = camera_ray(C, px, py, offx, offy, tm, lx, ly);
-    char* rec = pool.rec[cur] + (size_t)(n_cont + i) * RTX_REC_BYTES;   // appended behind the survivors
+    char* rec = pool.records(cur) + (size_t)(n_cont + i) * RTX_REC_BYTES;   // appended behind the survivors
     st256d(rec, r.ox, r.oy, r.oz, r.tm);
     st256d(rec + 32, r.dx, r.dy, r.dz, __longlong_as_double((long long)(((unsigned long long)sample << 32) | pixel)));
     *reinterpret_cast<float4*>(rec + 64) = make_float4(1.f, 1.f, 1.f, __int_as_float(0 | (1 << 16)));
@@ -204,7 +205,7 @@ extern __shared__ __align__(16) unsigned char rtx_smem[];  // the trace kernels'
 // ---- K2: extend — closest hit of every active path, then binning into material-sorted shading queues -------------
 struct ExtendPolicy {
     static constexpr bool ANY_HIT = false;
-    Ctl* ctl; Pool pool; const char* rec; const DevScene* S; uint32_t seed_lo, seed_hi;
+    Ctl* ctl; char* hit; int* q_mat; int capacity; const char* rec; const DevScene* S; uint32_t seed_lo, seed_hi;
     __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:451
     __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
         const char* q = rec + (size_t)job * RTX_REC_BYTES;
@@ -228,7 +229,7 @@ struct ExtendPolicy {
                 HitInfo hi;
                 finalize_hit(*S, r, best_to_hit(b), false, hi);
                 const long long bits = (long long)(unsigned)hi.mat | (hi.front ? (1LL << 31) : 0);
-                char* h = pool.hit + (size_t)job * RTX_HIT_BYTES;
+                char* h = hit + (size_t)job * RTX_HIT_BYTES;
                 st256d(h, hi.P.x, hi.P.y, hi.P.z, b.t);
                 st256d(h + 32, hi.N.x, hi.N.y, hi.N.z, __longlong_as_double(bits));
                 const int mt = S->mats[hi.mat].type;
@@ -240,14 +241,14 @@ struct ExtendPolicy {
 #pragma unroll
         for (int k = 0; k < Q_COUNT; k++) {
             const int pos = warp_append(&ctl->n_mat[k], q == k);
-            if (q == k) pool.q_mat[(size_t)k * pool.capacity + pos] = job;
+            if (q == k) q_mat[(size_t)k * capacity + pos] = job;
         }
     }
 };
 
 template <bool COUNT>
 __global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_extend(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, PassParams pp, int* spill) {
-    ExtendPolicy P{ctl, pool, pool.rec[cur], &S, pp.seed_lo, pp.seed_hi};
+    ExtendPolicy P{ctl, pool.hit, pool.q_mat, pool.capacity, pool.records(cur), &S, pp.seed_lo, pp.seed_hi};
     TraceCounters tc = {0, 0, 0, 0, 0};
     const int n = ctl->n_active;
     trace_persistent<ExtendPolicy, COUNT, RTX_TRACE_SLOTS>(S, P, &ctl->cur_extend, n, tc, spill, rtx_smem);
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(256, RTX_SHADE_BLOCKS) k_shade(Ctl* ctl, Pool 
     float3 env_c = make_float3(0, 0, 0), area_c = make_float3(0, 0, 0);
     if (valid) {
         const int job = pool.q_mat[(size_t)type * pool.capacity + idx];
-        const char* rec = pool.rec[cur] + (size_t)job * RTX_REC_BYTES;
+        const char* rec = pool.records(cur) + (size_t)job * RTX_REC_BYTES;
         const D4 ro4 = ld256d(rec), rd4 = ld256d(rec + 32);
         D3 rd = d3(rd4.x, rd4.y, rd4.z);
         tm = ro4.w; pixbits = rd4.w;
@@ -509,7 +510,7 @@ __global__ void __launch_bounds__(256, RTX_SHADE_BLOCKS) k_shade(Ctl* ctl, Pool 
     // survivors: the next ray goes to the next free record of the other buffer, in the order the warps arrive
     const int pos = warp_append(&ctl->n_next, cont);
     if (cont) {
-        char* out = pool.rec[cur ^ 1] + (size_t)pos * RTX_REC_BYTES;
+        char* out = pool.records(cur ^ 1) + (size_t)pos * RTX_REC_BYTES;
         st256d(out, P.x, P.y, P.z, tm);
         st256d(out + 32, nd.x, nd.y, nd.z, pixbits);
         *reinterpret_cast<float4*>(out + 64) = th;
