@@ -64,6 +64,7 @@ struct rtx_ctx {
     Ctl* ctl_host = nullptr;  // pinned
     int count_stats = 0, time_kernels = 1, blas_leaf = 4;
     float4* per_sample = nullptr; size_t per_sample_cap = 0;   // moments mode: per-sample radiance sums of the running pass (grow-only)
+    int flat_max_entries = 16, scene_flat = 0, scene_has_mesh = 0;   // worlds of <= flat_max_entries entries without a mesh are traced by the flat kernels (trace_flat)
     int pixel_major = 1;  // path order of k_generate: all samples of a pixel consecutively (1) or sample-major (0)
     int bvh_device = 1;   // mesh BLAS construction on the device (rtx_bvh_gpu.cuh); 0 = host builder (rtx_bvh.hpp), kept for A/B
     double ms_upload_blas = 0, ms_upload_total = 0;
@@ -249,6 +250,11 @@ int32_t rtx_set_option(rtx_ctx* ctx, const char* key, int64_t value) {
     else if (k == "time_kernels") ctx->time_kernels = value != 0;
     else if (k == "l2_persist") { ctx->l2_persist = value != 0; ctx->window_set = false; }  // L2 persisting window over the scene geometry (default off)
     else if (k == "pixel_major") ctx->pixel_major = value != 0;
+    else if (k == "flat_max_entries") {   // 0 = always traverse the hierarchy
+        if (value < 0 || value > 64) return fail(ctx, RTX_ERR_INVALID, "flat_max_entries must be in 0..64");
+        ctx->flat_max_entries = (int)value;
+        ctx->scene_flat = ctx->have_scene && !ctx->scene_has_mesh && ctx->S.n_entries <= ctx->flat_max_entries;
+    }
     else if (k == "bvh_device") ctx->bvh_device = value != 0;  // takes effect at the next rtx_scene_upload
     else if (k == "blas_leaf") {  // triangles per BLAS leaf (1..8); takes effect at the next rtx_scene_upload
         if (value < 1 || value > 8) return fail(ctx, RTX_ERR_INVALID, "blas_leaf must be in 1..8");
@@ -757,6 +763,9 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     ctx->S = S;
     ctx->have_scene = true;
     ctx->blas_depth = maxBlasDepth; ctx->built_on_device = deviceBuild ? 1 : 0;
+    ctx->scene_has_mesh = 0;
+    for (int e = 0; e < d->n_entries; e++) ctx->scene_has_mesh |= d->entry_geom_kind[e] == RTX_GEOM_MESH;
+    ctx->scene_flat = !ctx->scene_has_mesh && d->n_entries <= ctx->flat_max_entries;
     ctx->ms_upload_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tUpload0).count();
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
     return RTX_OK;
@@ -970,13 +979,19 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
             if (timing) cudaEventRecord(ev[0], st);
             k_generate<<<gridStream, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->C, pp);
             if (timing) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
-            if (ctx->count_stats & 1) k_extend<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
+            if (ctx->scene_flat) {
+                if (ctx->count_stats & 1) k_extend_flat<true><<<gridStream, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, pp);
+                else k_extend_flat<false><<<gridStream, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, pp);
+            } else if (ctx->count_stats & 1) k_extend<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
             else k_extend<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
             if (timing) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); }
             k_shade<<<std::min((P + 255) / 256, ctx->num_sms * 2 * RTX_SHADE_BLOCKS), 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, ctx->C, pp);
             if (timing) { cudaEventRecord(ev[5], st); cudaEventRecord(ev[6], st); }
             if (ctx->S.n_lights > 0) {
-                if (ctx->count_stats & 2) k_connect<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, ctx->S, pp, ctx->trace_spill);
+                if (ctx->scene_flat) {
+                    if (ctx->count_stats & 2) k_connect_flat<true><<<gridStream, 256, 0, st>>>(ctx->ctl, pool, ctx->S, pp);
+                    else k_connect_flat<false><<<gridStream, 256, 0, st>>>(ctx->ctl, pool, ctx->S, pp);
+                } else if (ctx->count_stats & 2) k_connect<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, ctx->S, pp, ctx->trace_spill);
                 else k_connect<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, ctx->S, pp, ctx->trace_spill);
                 launches++;
             }
@@ -1079,8 +1094,11 @@ int32_t rtx_trace_closest(rtx_ctx* ctx, const double* rays, int64_t n, double tm
     CU(sc.out(&dFront, (unsigned char*)front, n)); CU(sc.out(&dUV, uv, 2 * n)); CU(sc.out(&dP, p, 3 * n));
     if (n > (int64_t)1 << 30) return fail(ctx, RTX_ERR_INVALID, "rtx_trace_closest: at most 2^30 rays per call");
     CU(cudaMemsetAsync(ctx->batch_cursor, 0, sizeof(int), ctx->stream));
-    k_trace_closest<<<ctx->trace_grid, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, ctx->stream>>>(ctx->S, dRays, (int)n, tmin, tmax, ctx->batch_cursor, ctx->trace_spill,
-                                                                                               dEntry, dPrim, dT, dN, dFront, dUV, dP);
+    if (ctx->scene_flat)
+        k_trace_closest_flat<<<std::min((int)((n + 255) / 256), ctx->num_sms * 8), 256, 0, ctx->stream>>>(ctx->S, dRays, (int)n, tmin, tmax, dEntry, dPrim, dT, dN, dFront, dUV, dP);
+    else
+        k_trace_closest<<<ctx->trace_grid, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, ctx->stream>>>(ctx->S, dRays, (int)n, tmin, tmax, ctx->batch_cursor, ctx->trace_spill,
+                                                                                                   dEntry, dPrim, dT, dN, dFront, dUV, dP);
     CU(cudaGetLastError());
     BACK(dEntry, entry_id, n); BACK(dPrim, prim_id, n); BACK(dT, t, n); BACK(dN, normal, 3 * n); BACK(dFront, front, n); BACK(dUV, uv, 2 * n); BACK(dP, p, 3 * n);
     CU(cudaStreamSynchronize(ctx->stream));

@@ -256,6 +256,16 @@ __global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_extend(
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->ext_rays, (unsigned long long)n);
 }
 
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_extend_flat(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, PassParams pp) {
+    ExtendPolicy P{ctl, pool.hit, pool.q_mat, pool.capacity, pool.records(cur), &S, pp.seed_lo, pp.seed_hi};
+    TraceCounters tc = {0, 0, 0, 0, 0};
+    const int n = ctl->n_active;
+    trace_flat<ExtendPolicy, COUNT>(S, P, n, tc);
+    if (COUNT) flush_counters(ctl, tc);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->ext_rays, (unsigned long long)n);
+}
+
 // ---- textures (rt/texture.go:43-45, :63-77) ----------------------------------------------------------------------
 __device__ __forceinline__ float3 tex_value(const DevScene& S, int id, D3 p) {
     DTexture t = S.texs[id];
@@ -574,6 +584,16 @@ __global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_connect
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->shadow_rays, (unsigned long long)n);
 }
 
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_connect_flat(Ctl* ctl, Pool pool, const __grid_constant__ DevScene S, PassParams pp) {
+    ConnectPolicy P{pool, pp.seed_lo, pp.seed_hi};
+    TraceCounters tc = {0, 0, 0, 0, 0};
+    const int n = ctl->n_shadow;
+    trace_flat<ConnectPolicy, COUNT>(S, P, n, tc);
+    if (COUNT) flush_counters(ctl, tc);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->shadow_rays, (unsigned long long)n);
+}
+
 // ---- K6a: end of a pass — every pixel received `spp` samples; with moments, fold the per-sample sums into sum and sum of squares ----
 __global__ void __launch_bounds__(256) k_pass_finish(float4* accum, float4* accum_sq, const float4* per_sample, int npix, int spp, int moments) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -641,6 +661,13 @@ __global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_trace_c
     BatchPolicy P{&S, rays, tmin, tmax, entry_id, prim_id, t, normal, front, uv, p};
     TraceCounters tc = {0, 0, 0, 0, 0};
     trace_persistent<BatchPolicy, false, RTX_TRACE_SLOTS>(S, P, cursor, n, tc, spill, rtx_smem);
+}
+
+__global__ void __launch_bounds__(256) k_trace_closest_flat(const __grid_constant__ DevScene S, const double* rays, int n, double tmin, double tmax, int* entry_id, int* prim_id,
+        double* t, double* normal, unsigned char* front, double* uv, double* p) {
+    BatchPolicy P{&S, rays, tmin, tmax, entry_id, prim_id, t, normal, front, uv, p};
+    TraceCounters tc = {0, 0, 0, 0, 0};
+    trace_flat<BatchPolicy, false>(S, P, n, tc);
 }
 
 __global__ void k_camera_rays(DevCamera C, const int* ij, const double* sq, const double* disk, const double* tm, long long n, double* out) {

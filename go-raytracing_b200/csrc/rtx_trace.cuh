@@ -183,29 +183,14 @@ struct TracePool {
     }
 };
 
-// Every world entry that is not a mesh instance — a primitive, a Box list, a Volume — tested against the ray of pool slot
-// `s`: the rare, bulky part of the ENTRY phase (float64 sphere / quad / plane tests, the
-// Volume free-flight with its log). Measured both ways on B200: inlined 1039 Mrays/s, out of line (-DRTX_ENTRY_OOL) 958 on
-// cornell-lucy. State travels through the shared-memory pool; Sp points at the kernel's __grid_constant__ parameter.
-template <int NSLOTS>
-#ifndef RTX_ENTRY_OOL
-__device__ __forceinline__
-#else
-__device__ __noinline__
-#endif
-bool entry_other(const DevScene* Sp, unsigned char* smem, int s, int ei, double tmin, uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
-                 uint32_t c2, bool transparent, TraceCounters* tcp) {
-    const DevScene& S = *Sp;
-    const TracePool<NSLOTS> T(smem);
-    const DEntry e = S.entries[ei];
-    RayD r, r2;
-    T.load_ray(s, r);
-    r2 = r;
+// A world entry that is not a mesh instance — a primitive, a Box list, a Volume — against the world ray `r` (registers
+// only): the reference's Hit of that object with the interval [tmin, B.t] (rt/hittable_list.go:31-45, rt/volume.go:34-79,
+// the wrappers of rt/transform.go). `vr` is only read for volumes.
+__device__ __forceinline__ void entry_core(const DevScene& S, int ei, const DEntry& e, const RayD& r, Best& B, double tmin, const VolumeRng& vr, TraceCounters* tcp) {
+    RayD r2 = r;
     xform_ray(S, ei, e, r2);
-    Best B;
-    T.load_best(s, B);
     if (e.volume >= 0) {
-        if (!transparent) {
+        if (!vr.transparent) {
             // rt/volume.go:34-79
             double t1 = isect_boundary(S, e, r2, -RTX_INF_D, RTX_INF_D, tcp);
             if (t1 == t1) {
@@ -217,7 +202,6 @@ bool entry_other(const DevScene* Sp, unsigned char* smem, int s, int ei, double 
                         if (t1 < 0) t1 = 0;
                         const double rayLength = sqrt(r.dx * r.dx + r.dy * r.dy + r.dz * r.dz);
                         const double inside = (t2 - t1) * rayLength;
-                        VolumeRng vr; vr.k0 = k0; vr.k1 = k1; vr.c0 = c0; vr.c1 = c1; vr.c2 = c2; vr.transparent = false;
                         const double2 uu = rtx_volume_uniform(vr, ei);
                         const double nid = S.volumes[e.volume].neg_inv_density;
                         double hd = nid * log(uu.x);
@@ -235,8 +219,63 @@ bool entry_other(const DevScene* Sp, unsigned char* smem, int s, int ei, double 
     } else {
         B.test_prim(S, e.kind, e.index, r2, tmin, ei, e.rank, 0, 0, tcp);
     }
+}
+
+// The same for the ray of pool slot `s` of the persistent kernels: the rare, bulky part of the ENTRY phase (float64 sphere /
+// quad / plane tests, the Volume free-flight with its log). Measured both ways on B200: inlined 1039 Mrays/s, out of line
+// (-DRTX_ENTRY_OOL) 958 on cornell-lucy. State travels through the shared-memory pool; Sp points at the kernel's
+// __grid_constant__ parameter.
+template <int NSLOTS>
+#ifndef RTX_ENTRY_OOL
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+bool entry_other(const DevScene* Sp, unsigned char* smem, int s, int ei, double tmin, uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
+                 uint32_t c2, bool transparent, TraceCounters* tcp) {
+    const DevScene& S = *Sp;
+    const TracePool<NSLOTS> T(smem);
+    const DEntry e = S.entries[ei];
+    RayD r;
+    T.load_ray(s, r);
+    Best B;
+    T.load_best(s, B);
+    VolumeRng vr; vr.k0 = k0; vr.k1 = k1; vr.c0 = c0; vr.c1 = c1; vr.c2 = c2; vr.transparent = transparent;
+    entry_core(S, ei, e, r, B, tmin, vr, tcp);
     T.store_best(s, B);
     return B.have;
+}
+
+// Scenes whose whole world is a handful of primitives (no mesh): the TLAS would be a single leaf, so the query is the
+// reference's HittableList.Hit loop itself — one thread per ray, every entry in turn, no pool, no stack, no divergence
+// between lanes beyond the tests' own early-outs. Results are identical to the hierarchy's (closest hits do not depend on
+// the order of the tests; exact ties are resolved by rank as everywhere).
+template <class Policy, bool COUNT>
+__device__ __forceinline__ void trace_flat(const DevScene& S, Policy& P, int njobs, TraceCounters& tc) {
+    TraceCounters* const tcp = COUNT ? &tc : nullptr;
+    const double tmin = P.tmin();
+    const int nrounded = (njobs + 31) & ~31;   // whole warps reach the warp-collective retire
+    for (int job = blockIdx.x * blockDim.x + threadIdx.x; job < nrounded; job += gridDim.x * blockDim.x) {
+        const bool valid = job < njobs;
+        RayD r;
+        Best B;
+        r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = r.tm = 0;
+        B.reset(0);
+        if (valid) {
+            double tmax;
+            P.load(job, r, tmax);
+            B.reset(tmax);
+            for (int ei = 0; ei < S.n_entries; ei++) {
+                const DEntry e = S.entries[ei];
+                if (e.kind == RTX_GEOM_LIST && e.b == 0) continue;
+                VolumeRng vr = {0, 0, 0, 0, 0, true};
+                if (e.volume >= 0) vr = P.volume_rng(job);
+                entry_core(S, ei, e, r, B, tmin, vr, tcp);
+                if (Policy::ANY_HIT && B.have) break;
+            }
+        }
+        P.retire(valid ? job : -1, valid, r, B);
+    }
 }
 
 template <class Policy, bool COUNT, int NSLOTS>

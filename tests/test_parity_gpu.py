@@ -186,6 +186,42 @@ def test_device_bvh_build(grt, orc, ctx):
     assert (ho["entry"] >= 0).mean() > 0.02
 
 
+@pytest.mark.parametrize("name", ["cornell", "cornell-glossy", "hdri-test"])
+def test_flat_and_hierarchy_paths_agree(grt, orc, ctx, name):
+    """Worlds of a handful of entries are traced by the flat kernels (one thread per ray over every entry, trace_flat); the
+    same rays through the BVH kernels (flat_max_entries = 0) must give bit-identical hit records, and both match the oracle."""
+    rng = np.random.default_rng(21)
+    sc = grt.config_scene(name, width=CONFIG_SMALL[name], spp=1)
+    o = orc.OracleScene(sc.desc_ptr, sc.cam_ptr)
+    ij, sq, disk, tm = camera_batch(sc.width, sc.height, 50000, rng)
+    rays = o.camera_rays(ij, sq, disk, tm)
+    ho = o.trace_closest(rays)
+    scatter, shadow = secondary_rays(ho, rng, 30000)
+    res = {}
+    try:
+        for flat in (16, 0):
+            ctx.set_option("flat_max_entries", flat)
+            ctx.load(sc)
+            res[flat] = [ctx.trace_closest(rays), ctx.trace_closest(scatter), ctx.trace_closest(shadow, 0.001, 300.0)]
+        for a, b in zip(res[16], res[0]):
+            for k in ("entry", "prim", "t", "normal", "p", "front"):
+                assert np.array_equal(a[k], b[k]), f"{name}: flat and hierarchy kernels disagree on {k}"
+        assert_level1(res[16][0], ho, f"{name} flat primary")
+        assert_level1(res[16][1], o.trace_closest(scatter), f"{name} flat scatter")
+        # and a rendered pass through either pair of kernels has the same mean (same Philox counters, float32 atomics order aside)
+        means = {}
+        for flat in (16, 0):
+            ctx.set_option("flat_max_entries", flat)
+            ctx.load(sc)
+            ctx.clear(); ctx.render_pass(8, sc.cam.max_depth, seed=5)
+            s, _, n = ctx.resolve_accum()
+            assert np.all(n == 8)
+            means[flat] = s
+        assert np.allclose(means[16], means[0], rtol=2e-5, atol=1e-5)
+    finally:
+        ctx.set_option("flat_max_entries", 16)
+
+
 def test_level1_axis_parallel_rays_cull(grt, orc, ctx):
     """Directions with one or two exactly-zero components (wall normal + an axis-aligned scatter direction: d = (0,0,-2))
     must give the reference's hits AND must still be culled by the float32 box test on the degenerate axes: a ray whose
