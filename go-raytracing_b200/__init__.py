@@ -400,7 +400,7 @@ def make_camera(width, aspect, spp, depth, vfov, look_from, look_at, vup=(0, 1, 
 
 
 class NamedScene:
-    """One of the five configured scenes built by the C++ host mirror (rt_scenes.cpp) and flattened."""
+    """A scene function of rt/scenes.go built by the C++ host mirror (rt_scenes.cpp) and flattened."""
 
     def __init__(self, name: str, width: int = 0, aspect: float = 16.0 / 9.0, spp: int = 0, depth: int = 0, seed: int = 0x5EED,
                  use_bvh: bool = True, asset_root: Optional[str] = None):
@@ -586,6 +586,14 @@ CONFIGS = {
     "cornell-lucy": dict(scene="cornell-lucy", width=1200, aspect=16.0 / 9.0, spp=500, depth=50),
     "hdri-test": dict(scene="hdri-test", width=3840, aspect=16.0 / 9.0, spp=1024, depth=20),
 }
+# the other scene functions of rt/scenes.go the device vocabulary covers, at the scenes' own resolution / quality
+CONFIGS.update({
+    "checkered": dict(scene="checkered", width=600, aspect=16.0 / 9.0, spp=100, depth=50),
+    "simple": dict(scene="simple", width=400, aspect=16.0 / 9.0, spp=100, depth=50),
+    "quads": dict(scene="quads", width=400, aspect=1.0, spp=100, depth=50),
+    "glossy-metal": dict(scene="glossy-metal", width=640, aspect=16.0 / 9.0, spp=100, depth=10),
+    "cornell-smoke": dict(scene="cornell-smoke", width=600, aspect=1.0, spp=150, depth=5),
+})
 
 
 def config_scene(name: str, width: Optional[int] = None, spp: Optional[int] = None, depth: Optional[int] = None, seed: int = 0x5EED) -> NamedScene:

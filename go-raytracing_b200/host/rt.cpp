@@ -3,9 +3,12 @@
 #include "rt.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <future>
 #include <sstream>
 #include <sys/stat.h>
 
@@ -223,7 +226,9 @@ void stableSort(std::vector<BvhPrim>& a, size_t lo, size_t hi, std::vector<BvhPr
     while (j < hi) tmp[k++] = a[j++];
     for (size_t t = lo; t < hi; t++) a[t] = tmp[t];
 }
-BVHNodePtr buildBVHNode(const std::vector<HittablePtr>& objects, std::vector<BvhPrim>& prims, size_t lo, size_t hi, std::vector<BvhPrim>& tmp) {
+// The two halves of a split are independent (disjoint ranges of `prims` and `tmp`): the top levels of a big mesh run them on
+// separate threads (the reference's recursion is sequential; the tree is the same).
+BVHNodePtr buildBVHNode(const std::vector<HittablePtr>& objects, std::vector<BvhPrim>& prims, size_t lo, size_t hi, std::vector<BvhPrim>& tmp, int depth = 0) {
     size_t n = hi - lo;
     AABB bounds = prims[lo].bbox;
     AABB cb = NewAABBFromPoints(prims[lo].centroid, prims[lo].centroid);
@@ -246,8 +251,14 @@ BVHNodePtr buildBVHNode(const std::vector<HittablePtr>& objects, std::vector<Bvh
         return axis == 0 ? a.centroid.X < b.centroid.X : axis == 1 ? a.centroid.Y < b.centroid.Y : a.centroid.Z < b.centroid.Z;
     });
     size_t mid = lo + n / 2;
-    node->left = buildBVHNode(objects, prims, lo, mid, tmp);
-    node->right = buildBVHNode(objects, prims, mid, hi, tmp);
+    if (n >= 16384 && depth < 4) {
+        auto left = std::async(std::launch::async, [&, depth] { return buildBVHNode(objects, prims, lo, mid, tmp, depth + 1); });
+        node->right = buildBVHNode(objects, prims, mid, hi, tmp, depth + 1);
+        node->left = left.get();
+    } else {
+        node->left = buildBVHNode(objects, prims, lo, mid, tmp, depth + 1);
+        node->right = buildBVHNode(objects, prims, mid, hi, tmp, depth + 1);
+    }
     return node;
 }
 }  // namespace
@@ -268,6 +279,7 @@ BVHNodePtr NewBVHNodeFromList(const HittableListPtr& list) { return NewBVHNode(l
 
 // ---- rt/obj_loader.go ------------------------------------------------------------------------------------
 HittablePtr LoadOBJ(const std::string& filename, MaterialPtr material) {
+    const auto t0 = std::chrono::steady_clock::now();
     FILE* f = std::fopen(filename.c_str(), "rb");
     if (!f) throw std::runtime_error("failed to open OBJ file: " + filename);
     std::vector<Point3> vertices;
@@ -322,7 +334,12 @@ HittablePtr LoadOBJ(const std::string& filename, MaterialPtr material) {
         }
     }
     std::fclose(f);
-    return NewBVHNode(triangles, 0, triangles.size());
+    const auto t1 = std::chrono::steady_clock::now();
+    HittablePtr root = NewBVHNode(triangles, 0, triangles.size());
+    if (std::getenv("RT_DEBUG_TIMING"))
+        std::fprintf(stderr, "[rt] LoadOBJ %s: parse %.3f s, NewBVHNode %.3f s (%zu triangles)\n", filename.c_str(),
+                     std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count(), triangles.size());
+    return root;
 }
 HittablePtr LoadOBJWithTransform(const std::string& filename, MaterialPtr material, const Transform* transform) {
     HittablePtr mesh = LoadOBJ(filename, material);

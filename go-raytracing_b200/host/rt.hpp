@@ -310,6 +310,11 @@ Scene HDRITestScene(const std::string& hdrPath);              // rt/scenes.go:40
 Scene CornellBoxScene();                                      // rt/scenes.go:463
 Scene CornellBoxGlossy();                                     // rt/scenes.go:606
 Scene CornellBoxLucy(const std::string& objPath);             // rt/scenes.go:714
+Scene CheckeredSpheresScene();                                 // rt/scenes.go:132
+Scene SimpleScene();                                           // rt/scenes.go:172
+Scene QuadsScene();                                            // rt/scenes.go:274
+Scene GlossyMetalTest();                                       // rt/scenes.go:564
+Scene CornellSmoke();                                          // rt/scenes.go:820
 Scene LoadSceneByName(const std::string& name, const std::string& assetRoot, uint64_t seed);  // main.go:108
 
 // ---- flattening: pointer graph -> rtx_scene_desc ----------------------------------------------------------

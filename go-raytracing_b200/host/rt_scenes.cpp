@@ -1,4 +1,5 @@
-// rt_scenes.cpp — the five configured scenes of BASELINE.json, mirrored from rt/scenes.go.
+// rt_scenes.cpp — the five configured scenes of BASELINE.json and the other scene functions of rt/scenes.go whose vocabulary
+// the device path covers (CheckeredSpheres, Simple, Quads, GlossyMetalTest, CornellSmoke), mirrored from the reference.
 // RandomScene draws from a seeded SplitMix64 stream in the reference's draw order (the reference uses
 // Go's auto-seeded global source, rt/utils.go:18, so its geometry differs run to run).
 #include <sys/stat.h>
@@ -178,6 +179,71 @@ Scene CornellBoxLucy(const std::string& objPath) {  // rt/scenes.go:714-817
     return {world, cam};
 }
 
+// ---- the remaining scene functions the device vocabulary covers ------------------------------------------------
+Scene CheckeredSpheresScene() {  // rt/scenes.go:132-170
+    auto world = NewHittableList();
+    auto checker = NewLambertianTexture(NewCheckerTextureFromColors(0.32, {0.2, 0.3, 0.1}, {0.9, 0.9, 0.9}));
+    world->Add(NewSphere({0, -10, 0}, 10, checker));
+    world->Add(NewSphere({0, 10, 0}, 10, checker));
+    auto cam = NewCameraBuilder().SetResolution(600, 16.0 / 9.0).SetQuality(100, 50).SetPosition({13, 2, 3}, {0, 0, 0}, {0, 1, 0}).SetLens(20, 0, 10)
+                   .EnableSkyGradient(true).Build();
+    return {world, cam};
+}
+
+Scene SimpleScene() {  // rt/scenes.go:172-209 (a hollow glass sphere: the inner bubble has ior 1/1.5)
+    auto world = NewHittableList();
+    world->Add(NewPlane({0, -0.5, -1}, {0, 1, 0}, NewLambertian({0.8, 0.8, 0.0})));
+    world->Add(NewSphere({0, 0, -1}, 0.5, NewLambertian({0.1, 0.2, 0.5})));
+    world->Add(NewSphere({-1, 0, -1}, 0.5, NewDielectric(1.5)));
+    world->Add(NewSphere({-1, 0, -1}, 0.4, NewDielectric(1.0 / 1.5)));
+    world->Add(NewSphere({1, 0, -1}, 0.5, NewMetal({0.8, 0.6, 0.2}, 0.0)));
+    auto cam = NewCameraBuilder().SetResolution(400, 16.0 / 9.0).SetQuality(100, 50).SetPosition({0, 0, 2}, {0, 0, -1}, {0, 1, 0}).SetLens(90, 0, 10)
+                   .EnableSkyGradient(true).Build();
+    return {world, cam};
+}
+
+Scene QuadsScene() {  // rt/scenes.go:274-311
+    auto world = NewHittableList();
+    world->Add(NewQuad({-3, -2, 5}, {0, 0, -4}, {0, 4, 0}, NewLambertian({1.0, 0.2, 0.2})));
+    world->Add(NewQuad({-2, -2, 0}, {4, 0, 0}, {0, 4, 0}, NewLambertian({0.2, 1.0, 0.2})));
+    world->Add(NewQuad({3, -2, 1}, {0, 0, 4}, {0, 4, 0}, NewLambertian({0.2, 0.2, 1.0})));
+    world->Add(NewQuad({-2, 3, 1}, {4, 0, 0}, {0, 0, 4}, NewLambertian({1.0, 0.5, 0.0})));
+    world->Add(NewQuad({-2, -3, 5}, {4, 0, 0}, {0, 0, -4}, NewLambertian({0.2, 0.8, 0.8})));
+    auto cam = NewCameraBuilder().SetResolution(400, 1.0).SetQuality(100, 50).SetPosition({0, 0, 9}, {0, 0, 0}, {0, 1, 0}).SetLens(80, 0, 10)
+                   .EnableSkyGradient(true).Build();
+    return {world, cam};
+}
+
+Scene GlossyMetalTest() {  // rt/scenes.go:564-604
+    auto world = NewHittableList();
+    world->Add(NewPlane({0, 0, 0}, {0, 1, 0}, NewLambertian({0.5, 0.5, 0.5})));
+    world->Add(NewSphere({-2.5, 1, 0}, 1.0, NewMetal({0.8, 0.6, 0.2}, 0.0)));
+    world->Add(NewSphere({0, 1, 0}, 1.0, NewMetal({0.8, 0.6, 0.2}, 0.2)));
+    world->Add(NewSphere({2.5, 1, 0}, 1.0, NewMetal({0.8, 0.6, 0.2}, 0.5)));
+    auto areaLight = NewQuad({-2, 5, -2}, {4, 0, 0}, {0, 0, 4}, NewDiffuseLightColor({4, 4, 4}));
+    world->Add(areaLight);
+    auto cam = NewCameraBuilder().SetResolution(640, 16.0 / 9.0).SetQuality(100, 10).SetPosition({0, 2, 10}, {0, 1, 0}, {0, 1, 0}).SetLens(40, 0, 10)
+                   .SetBackground({0, 0, 0}).AddLight(areaLight).Build();
+    return {world, cam};
+}
+
+Scene CornellSmoke() {  // rt/scenes.go:820-925: two rotated boxes of participating medium (black and white smoke)
+    auto world = NewHittableList();
+    auto white = NewLambertian({0.73, 0.73, 0.73});
+    auto red = NewLambertian({0.65, 0.05, 0.05});
+    auto green = NewLambertian({0.12, 0.45, 0.15});
+    auto areaLight = NewQuad({113, 554, 127}, {330, 0, 0}, {0, 0, 305}, NewDiffuseLight(NewSolidColor({3, 3, 3})));
+    world->Add(areaLight);
+    addCornellWalls(world, green, red, white);
+    auto box1 = NewTransform().SetRotationY(15).SetPosition({265, 0, 295}).Apply(Box({0, 0, 0}, {165, 330, 165}, white));
+    world->Add(NewVolumeFromColor(box1, 0.01, {0, 0, 0}));
+    auto box2 = NewTransform().SetRotationY(-18).SetPosition({130, 0, 65}).Apply(Box({0, 0, 0}, {165, 165, 165}, white));
+    world->Add(NewVolumeFromColor(box2, 0.01, {1, 1, 1}));
+    auto cam = NewCameraBuilder().SetResolution(600, 1.0).SetQuality(150, 5).SetPosition({278, 278, -800}, {278, 278, 0}, {0, 1, 0}).SetLens(40, 0, 10)
+                   .SetBackground({0, 0, 0}).AddLight(areaLight).Build();
+    return {world, cam};
+}
+
 static bool bigFile(const std::string& p) {
     struct stat st;
     return ::stat(p.c_str(), &st) == 0 && st.st_size > 1024;  // the shipped lucy_low.obj is a 133-byte Git-LFS pointer
@@ -190,6 +256,13 @@ Scene LoadSceneByName(const std::string& nameIn, const std::string& assetRoot, u
     if (name == "random" || name == "randomscene") return RandomScene(seed);
     if (name == "cornell" || name == "cornell-box") return CornellBoxScene();
     if (name == "cornell-glossy") return CornellBoxGlossy();
+    if (name == "checkered" || name == "checker" || name == "checkered-spheres") return CheckeredSpheresScene();
+    if (name == "simple" || name == "simple-scene") return SimpleScene();
+    if (name == "quads" || name == "quads-scene") return QuadsScene();
+    if (name == "cornell-smoke" || name == "cornell-fog") return CornellSmoke();
+    if (name == "glossy-metal" || name == "glossy-metal-test") return GlossyMetalTest();
+    if (name == "perlin" || name == "perlin-spheres" || name == "earth" || name == "earth-scene" || name == "primitives" || name == "primitives-scene")
+        throw std::runtime_error("scene '" + nameIn + "' uses vocabulary outside the device path (NoiseTexture / ImageTexture / Circle): see DESIGN.md section 8");
     if (name == "cornell-lucy") {
         std::string real = root + "/assets/models/lucy_low.obj", standin = root + "/assets/models/lucy_standin.obj";
         return CornellBoxLucy(bigFile(real) ? real : standin);

@@ -74,6 +74,28 @@ def test_scene_shapes(grt):
     assert (h.width, h.height) == (800, 450)
 
 
+def test_other_scene_shapes(grt):
+    # the scene functions beyond BASELINE's five (rt/scenes.go:132-311, :564-604, :820-925)
+    q = grt.config_scene("quads")
+    assert (q.width, q.height) == (400, 400) and q.desc.n_quads == 5 and q.desc.n_entries == 5 and q.cam.use_sky_gradient == 1 and q.cam.vfov == 80.0
+    s_ = grt.config_scene("simple")
+    assert s_.desc.n_spheres == 4 and s_.desc.n_planes == 1 and (s_.width, s_.height) == (400, 225)
+    iors = sorted(s_.desc.mat_ior[i] for i in range(s_.desc.n_materials) if s_.desc.mat_type[i] == grt.MAT_DIELECTRIC)
+    assert iors == [1.0 / 1.5, 1.5]                                     # hollow glass sphere: bubble of ior 1/1.5 inside
+    ck = grt.config_scene("checkered")
+    assert ck.desc.n_spheres == 2 and any(ck.desc.tex_type[i] == grt.TEX_CHECKER for i in range(ck.desc.n_textures))
+    gm = grt.config_scene("glossy-metal")
+    assert gm.desc.n_lights == 1 and gm.desc.light_quad[0] == 0 and gm.desc.n_spheres == 3 and (gm.width, gm.height) == (640, 360)
+    sm = grt.config_scene("cornell-smoke")
+    d = sm.desc
+    assert d.n_entries == 8 and d.n_volumes == 2 and d.n_quads == 6 + 12 and d.n_lights == 1
+    assert [d.entry_volume[i] for i in range(8)] == [-1] * 6 + [0, 1] and [d.entry_xf_count[i] for i in range(8)] == [0] * 6 + [2, 2]
+    assert d.vol_neg_inv_density[0] == -1.0 / 0.01 and (sm.cam.samples_per_pixel, sm.cam.max_depth) == (150, 5)
+    for name in ("primitives", "perlin", "earth"):                       # outside the device vocabulary: an error, never a fallback
+        with pytest.raises(RuntimeError):
+            grt.NamedScene(name, 64)
+
+
 def test_lucy_instances(grt):
     s = grt.config_scene("cornell-lucy", width=120, spp=1)
     d = s.desc
@@ -94,6 +116,8 @@ def test_lucy_instances(grt):
 def test_unsupported_objects_are_flatten_errors(grt):
     H = grt.host()
     assert H.rth_scene_named(b"earth", b".", 1, 1, 0, 1.0, 0, 0) is None
+    assert b"outside the device path" in H.rth_last_error()
+    assert H.rth_scene_named(b"no-such-scene", b".", 1, 1, 0, 1.0, 0, 0) is None
     assert b"unknown scene" in H.rth_last_error()
 
 

@@ -52,13 +52,15 @@ def secondary_rays(ho, rng, n):
     return scatter, shadow
 
 
-CONFIG_SMALL = {"cornell": 160, "cornell-glossy": 160, "random": 200, "hdri-test": 240}
+CONFIG_SMALL = {"cornell": 160, "cornell-glossy": 160, "random": 200, "hdri-test": 240,
+                "checkered": 200, "simple": 200, "quads": 160, "glossy-metal": 200, "cornell-smoke": 160}
+OTHER_SCENES = ["checkered", "simple", "quads", "glossy-metal", "cornell-smoke"]   # rt/scenes.go functions beyond BASELINE's five
 
 
 # ------------------------------------------------------------------------------------------------------------
 # level 1
 # ------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["cornell", "cornell-glossy", "random", "hdri-test"])
+@pytest.mark.parametrize("name", ["cornell", "cornell-glossy", "random", "hdri-test"] + OTHER_SCENES)
 def test_level1_configured_scenes(grt, orc, ctx, name):
     rng = np.random.default_rng(1)
     sc = grt.config_scene(name, width=CONFIG_SMALL[name])
@@ -363,7 +365,9 @@ def check_statistical(ctx, o, spp_g, spp_o, depth, cam_depth=None, seed=5, frac_
     # Pixels with (numerically) no variance in either render — black background, saturated emitters, the constant blue
     # channel of the sky gradient — must agree outright. The device accumulates float32 sums, so a channel that is
     # exactly constant in the float64 oracle still shows a ~1e-7 relative spread there: it is not a live pixel.
-    live = se > 1e-5 * np.maximum(1.0, np.abs(mo))
+    # (relative to the pixel's own level with a floor: a dim but genuinely noisy pixel — the far ground of glossy-metal at 1e-4 —
+    # is live and goes through the z-test like any other)
+    live = se > 1e-5 * np.maximum(1e-3, np.abs(mo))
     assert np.allclose(mg[~live], mo[~live], rtol=1e-4, atol=1e-5)
     z = (mg[live] - mo[live]) / se[live]
     frac = np.mean(np.abs(z) > 3)
@@ -395,6 +399,17 @@ def check_statistical(ctx, o, spp_g, spp_o, depth, cam_depth=None, seed=5, frac_
 @pytest.mark.parametrize("name,width,spp,depth", [("cornell", 96, 128, 10), ("cornell-glossy", 96, 128, 5), ("random", 120, 96, 50),
                                                  ("hdri-test", 128, 96, 20)])
 def test_level2_configured_scenes(grt, orc, ctx, name, width, spp, depth):
+    sc = grt.config_scene(name, width=width, spp=spp, depth=depth)
+    ctx.load(sc)
+    o = orc.OracleScene(sc.desc_ptr, sc.cam_ptr)
+    check_statistical(ctx, o, spp, spp, depth)
+
+
+@pytest.mark.parametrize("name,width,spp,depth", [("checkered", 96, 64, 20), ("simple", 96, 96, 30), ("quads", 80, 64, 20), ("glossy-metal", 96, 128, 10),
+                                                 ("cornell-smoke", 80, 128, 5)])
+def test_level2_other_scenes(grt, orc, ctx, name, width, spp, depth):
+    """The remaining scene functions of rt/scenes.go inside the device vocabulary: nested dielectrics (hollow glass sphere),
+    a planar light over fuzzy metals, two rotated boxes of smoke (Volume over Translate(RotateY(Box)))."""
     sc = grt.config_scene(name, width=width, spp=spp, depth=depth)
     ctx.load(sc)
     o = orc.OracleScene(sc.desc_ptr, sc.cam_ptr)
