@@ -171,27 +171,48 @@ __device__ __forceinline__ int bin_of(float c, float lo, float k) {
     int b = (int)((c - lo) * k);
     return b < 0 ? 0 : (b > NB - 1 ? NB - 1 : b);
 }
+// Every triangle of a splitting node drops its box into one bin per axis. On the top levels a block's 256 consecutive
+// positions belong to one node: the block then bins into shared memory and flushes 336 words with one global atomic each,
+// instead of 256 x 21 global atomics onto the same few addresses (k_bin was 3/4 of the build time before: 5.3 of 7 ms for
+// 280 K triangles). Blocks that straddle nodes (the deep levels, where contention is low anyway) go to global memory directly.
 __global__ void __launch_bounds__(256) k_bin(const float4* b0, const float2* b1, const int* node_of, int n, BNodes N, int lb, unsigned* bins) {
+    __shared__ unsigned sbin[NODE_BIN_WORDS];
+    __shared__ int s_node;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    const int nd = node_of[p];
-    if (nd < 0) return;
-    const float4 a = b0[p];
-    const float2 b = b1[p];
-    const float4 n0 = N.b0[nd];
-    const float2 n1 = N.b1[nd];
-    const float plo[3] = {a.x, a.y, a.z}, phi[3] = {a.w, b.x, b.y};
-    const float nlo[3] = {n0.x, n0.y, n0.z}, nhi[3] = {n0.w, n1.x, n1.y};
-    unsigned* nb = bins + (size_t)(nd - lb) * NODE_BIN_WORDS;
+    const int nd = p < n ? node_of[p] : -2;          // -1: finished leaf, -2: past the end
+    if (threadIdx.x == 0) s_node = nd;
+    for (int i = threadIdx.x; i < NODE_BIN_WORDS; i += blockDim.x) { const int w = i % BIN_WORDS; sbin[i] = w < 3 ? RTX_O_PINF : w < 6 ? RTX_O_NINF : 0u; }
+    __syncthreads();
+    const int nd0 = s_node;
+    const bool uniform = __syncthreads_and(nd == nd0 || nd == -2) && nd0 >= 0;
+    if (nd >= 0) {
+        const float4 a = b0[p];
+        const float2 b = b1[p];
+        const float4 n0 = N.b0[nd];
+        const float2 n1 = N.b1[nd];
+        const float plo[3] = {a.x, a.y, a.z}, phi[3] = {a.w, b.x, b.y};
+        const float nlo[3] = {n0.x, n0.y, n0.z}, nhi[3] = {n0.w, n1.x, n1.y};
+        unsigned* nb = uniform ? sbin : bins + (size_t)(nd - lb) * NODE_BIN_WORDS;
 #pragma unroll
-    for (int ax = 0; ax < 3; ax++) {
-        const float ext = nhi[ax] - nlo[ax];
-        if (!(ext > 0.f)) continue;
-        const int bi = bin_of(0.5f * (plo[ax] + phi[ax]), nlo[ax], (float)NB / ext);
-        unsigned* q = nb + (ax * NB + bi) * BIN_WORDS;
-        atomicMin(q + 0, f2o(plo[0])); atomicMin(q + 1, f2o(plo[1])); atomicMin(q + 2, f2o(plo[2]));
-        atomicMax(q + 3, f2o(phi[0])); atomicMax(q + 4, f2o(phi[1])); atomicMax(q + 5, f2o(phi[2]));
-        atomicAdd(q + 6, 1u);
+        for (int ax = 0; ax < 3; ax++) {
+            const float ext = nhi[ax] - nlo[ax];
+            if (!(ext > 0.f)) continue;
+            const int bi = bin_of(0.5f * (plo[ax] + phi[ax]), nlo[ax], (float)NB / ext);
+            unsigned* q = nb + (ax * NB + bi) * BIN_WORDS;
+            atomicMin(q + 0, f2o(plo[0])); atomicMin(q + 1, f2o(plo[1])); atomicMin(q + 2, f2o(plo[2]));
+            atomicMax(q + 3, f2o(phi[0])); atomicMax(q + 4, f2o(phi[1])); atomicMax(q + 5, f2o(phi[2]));
+            atomicAdd(q + 6, 1u);
+        }
+    }
+    if (!uniform) return;   // (block-uniform)
+    __syncthreads();
+    unsigned* gb = bins + (size_t)(nd0 - lb) * NODE_BIN_WORDS;
+    for (int i = threadIdx.x; i < NODE_BIN_WORDS; i += blockDim.x) {
+        const int w = i % BIN_WORDS;
+        if (sbin[i - w + 6] == 0u) continue;   // empty bin
+        if (w < 3) atomicMin(gb + i, sbin[i]);
+        else if (w < 6) atomicMax(gb + i, sbin[i]);
+        else atomicAdd(gb + i, sbin[i]);
     }
 }
 struct FBox {
