@@ -22,10 +22,10 @@ REPO_ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("RTX_B200_LIB") or os.path.join(_HERE, "csrc", "librtx_b200.so")  # env override: A/B builds of the same library
 HOST_LIB_PATH = os.path.join(_HERE, "csrc", "librt_host.so")
 
-RTX_ABI_VERSION = 1
+RTX_ABI_VERSION = 2
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_DIFFUSE_LIGHT, MAT_ISOTROPIC = range(5)
-TEX_SOLID, TEX_CHECKER = 0, 1
-GEOM_SPHERE, GEOM_QUAD, GEOM_TRIANGLE, GEOM_PLANE, GEOM_LIST, GEOM_MESH = range(6)
+TEX_SOLID, TEX_CHECKER, TEX_NOISE = 0, 1, 2
+GEOM_SPHERE, GEOM_QUAD, GEOM_TRIANGLE, GEOM_PLANE, GEOM_LIST, GEOM_MESH, GEOM_CIRCLE = range(7)
 XF_TRANSLATE, XF_ROTATE_Y, XF_SCALE = 0, 1, 2
 
 _pd = C.POINTER(C.c_double)
@@ -51,6 +51,8 @@ class SceneDesc(C.Structure):
         ("n_lights", C.c_int32), ("light_quad", _pi),
         ("env_width", C.c_int32), ("env_height", C.c_int32), ("env_rgb", _pd), ("env_rotation", C.c_double),
         ("env_importance_sampling", C.c_int32),
+        ("n_circles", C.c_int32), ("circle_center", _pd), ("circle_normal", _pd), ("circle_radius", _pd), ("circle_mat", _pi),
+        ("n_perlin", C.c_int32), ("perlin_vec", _pd), ("perlin_perm", _pi),
     ]
 
 
@@ -184,7 +186,8 @@ class SceneBuilder:
         self.world_is_bvh = world_is_bvh
         self.tex = []      # (type, color, inv_scale, even, odd)
         self.mat = []      # (type, tex, albedo, fuzz, ior)
-        self.sph, self.quad, self.tri, self.plane = [], [], [], []
+        self.sph, self.quad, self.tri, self.plane, self.circ = [], [], [], [], []
+        self.perlin = []   # (vec[256][3], perm[3][256])
         self.groups, self.items = [], []
         self.xf = []
         self.vol = []
@@ -199,6 +202,23 @@ class SceneBuilder:
     def checker(self, scale, c1, c2):
         e, o = self.solid(c1), self.solid(c2)
         self.tex.append((TEX_CHECKER, (0, 0, 0), 1.0 / scale, e, o))
+        return len(self.tex) - 1
+
+    def noise(self, scale, seed=1):
+        """NoiseTexture (rt/texture.go:24-29, :81-85) with a Perlin table drawn here from a seeded generator in the reference's
+        draw order (rt/noise.go:15-28: 256 unit vectors from [-1,1)^3, then Fisher-Yates permutations X, Y, Z)."""
+        rng = np.random.default_rng(seed)
+        vec = rng.random((256, 3)) * 2.0 - 1.0
+        vec /= np.sqrt((vec * vec).sum(axis=1, keepdims=True))
+        perm = np.zeros((3, 256), dtype=np.int32)
+        for a in range(3):
+            p = np.arange(256, dtype=np.int32)
+            for i in range(255, 0, -1):
+                t = int(rng.integers(0, i + 1))
+                p[i], p[t] = p[t], p[i]
+            perm[a] = p
+        self.perlin.append((vec, perm))
+        self.tex.append((TEX_NOISE, (0, 0, 0), float(scale), len(self.perlin) - 1, -1))
         return len(self.tex) - 1
 
     def material(self, kind, *args):
@@ -235,6 +255,23 @@ class SceneBuilder:
         n = n / np.sqrt((n * n).sum())
         self.plane.append((tuple(point), tuple(n), mat))
         return len(self.plane) - 1
+
+    def circle(self, center, normal, radius, mat):
+        n = np.asarray(normal, dtype=np.float64)
+        n = n / np.sqrt((n * n).sum())
+        self.circ.append((tuple(center), tuple(n), float(radius), mat))
+        return len(self.circ) - 1
+
+    def pyramid_group(self, base_center, base_size, height, mat):
+        """rt.Pyramid (rt/primitives.go:39-71): a base quad and four triangles in one HittableList."""
+        cx, cy, cz = (float(v) for v in base_center)
+        h = base_size / 2
+        items = [(GEOM_QUAD, self.quadp((cx - base_size / 2, cy, cz - base_size / 2), (base_size, 0, 0), (0, 0, base_size), mat))]
+        apex = (cx, cy + height, cz)
+        corners = [(cx + h, cy, cz - h), (cx + h, cy, cz + h), (cx - h, cy, cz + h), (cx - h, cy, cz - h)]
+        for i in range(4):
+            items.append((GEOM_TRIANGLE, self.triangle(corners[i], corners[(i + 1) % 4], apex, mat)))
+        return self.list_group(items)
 
     def list_group(self, items: Sequence[tuple]):
         begin = len(self.items)
@@ -363,6 +400,14 @@ class BuiltScene:
         d.entry_rank = None
         d.n_lights = len(b.lights)
         d.light_quad = P("lights", b.lights, np.int32)
+        d.n_circles = len(b.circ)
+        d.circle_center = P("circ_c", [c[0] for c in b.circ], np.float64)
+        d.circle_normal = P("circ_n", [c[1] for c in b.circ], np.float64)
+        d.circle_radius = P("circ_r", [c[2] for c in b.circ], np.float64)
+        d.circle_mat = P("circ_m", [c[3] for c in b.circ], np.int32)
+        d.n_perlin = len(b.perlin)
+        d.perlin_vec = P("perlin_vec", [pv[0] for pv in b.perlin], np.float64)
+        d.perlin_perm = P("perlin_perm", [pv[1] for pv in b.perlin], np.int32)
         if b.env is not None:
             rgb, rot, is_ = b.env
             k["env"] = rgb
@@ -593,6 +638,8 @@ CONFIGS.update({
     "quads": dict(scene="quads", width=400, aspect=1.0, spp=100, depth=50),
     "glossy-metal": dict(scene="glossy-metal", width=640, aspect=16.0 / 9.0, spp=100, depth=10),
     "cornell-smoke": dict(scene="cornell-smoke", width=600, aspect=1.0, spp=150, depth=5),
+    "perlin": dict(scene="perlin", width=600, aspect=16.0 / 9.0, spp=100, depth=50),
+    "primitives": dict(scene="primitives", width=800, aspect=16.0 / 9.0, spp=300, depth=25),
 })
 
 

@@ -284,6 +284,9 @@ static Box prim_box(const rtx_scene_desc* d, int kind, int idx) {
         }
     } else if (kind == RTX_GEOM_TRIANGLE) {
         b.grow(d->tri_v0 + 3 * idx); b.grow(d->tri_v1 + 3 * idx); b.grow(d->tri_v2 + 3 * idx);
+    } else if (kind == RTX_GEOM_CIRCLE) {   // center -/+ (r, r, r), rt/circle.go:22-26
+        const double r = d->circle_radius[idx];
+        for (int a = 0; a < 3; a++) { b.lo[a] = d->circle_center[3 * idx + a] - std::fabs(r); b.hi[a] = d->circle_center[3 * idx + a] + std::fabs(r); }
     } else {
         for (int a = 0; a < 3; a++) { b.lo[a] = -INFINITY; b.hi[a] = INFINITY; }
     }
@@ -337,6 +340,8 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     for (int i = 0; i < d->n_textures; i++) {
         if (d->tex_type[i] == RTX_TEX_CHECKER) {
             if (d->tex_even[i] < 0 || d->tex_even[i] >= d->n_textures || d->tex_odd[i] < 0 || d->tex_odd[i] >= d->n_textures) return bad("checker child out of range");
+        } else if (d->tex_type[i] == RTX_TEX_NOISE) {
+            if (d->tex_even[i] < 0 || d->tex_even[i] >= d->n_perlin || !d->perlin_vec || !d->perlin_perm) return bad("noise texture without a Perlin table");
         } else if (d->tex_type[i] != RTX_TEX_SOLID) return fail(ctx, RTX_ERR_UNSUPPORTED, "texture type %d is outside the device path", d->tex_type[i]);
     }
     for (int i = 0; i < d->n_materials; i++) {
@@ -346,13 +351,16 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
             return bad("material texture out of range");
     }
     auto matok = [&](const int32_t* m, int n) { for (int i = 0; i < n; i++) if (m[i] < 0 || m[i] >= d->n_materials) return false; return true; };
-    if (!matok(d->sph_mat, d->n_spheres) || !matok(d->quad_mat, d->n_quads) || !matok(d->tri_mat, d->n_tris) || !matok(d->plane_mat, d->n_planes) ||
+    if (!matok(d->sph_mat, d->n_spheres) || !matok(d->quad_mat, d->n_quads) || !matok(d->tri_mat, d->n_tris) || !matok(d->plane_mat, d->n_planes) || !matok(d->circle_mat, d->n_circles) ||
         !matok(d->vol_mat, d->n_volumes))
         return bad("material index out of range");
-    auto primCount = [&](int kind) { return kind == RTX_GEOM_SPHERE ? d->n_spheres : kind == RTX_GEOM_QUAD ? d->n_quads : kind == RTX_GEOM_TRIANGLE ? d->n_tris : d->n_planes; };
+    auto isPrim = [](int kind) { return (kind >= RTX_GEOM_SPHERE && kind <= RTX_GEOM_PLANE) || kind == RTX_GEOM_CIRCLE; };
+    auto primCount = [&](int kind) {
+        return kind == RTX_GEOM_SPHERE ? d->n_spheres : kind == RTX_GEOM_QUAD ? d->n_quads : kind == RTX_GEOM_TRIANGLE ? d->n_tris : kind == RTX_GEOM_CIRCLE ? d->n_circles : d->n_planes;
+    };
     for (int i = 0; i < d->n_list_items; i++) {
         int k = d->list_item_kind[i];
-        if (k < RTX_GEOM_SPHERE || k > RTX_GEOM_PLANE || d->list_item_index[i] < 0 || d->list_item_index[i] >= primCount(k)) return bad("list item out of range");
+        if (!isPrim(k) || d->list_item_index[i] < 0 || d->list_item_index[i] >= primCount(k)) return bad("list item out of range");
     }
     for (int g = 0; g < d->n_groups; g++) {
         int lim = d->group_kind[g] == RTX_GEOM_LIST ? d->n_list_items : d->n_tris;
@@ -364,8 +372,8 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
         if (d->xf_type[x] < RTX_XF_TRANSLATE || d->xf_type[x] > RTX_XF_SCALE) return fail(ctx, RTX_ERR_UNSUPPORTED, "transform op %d is outside the device path", d->xf_type[x]);
     for (int e = 0; e < d->n_entries; e++) {
         int k = d->entry_geom_kind[e], gi = d->entry_geom_index[e];
-        if (k < RTX_GEOM_SPHERE || k > RTX_GEOM_MESH) return bad("entry kind invalid");
-        if (k <= RTX_GEOM_PLANE ? (gi < 0 || gi >= primCount(k)) : (gi < 0 || gi >= d->n_groups || d->group_kind[gi] != k)) return bad("entry geometry out of range");
+        if (k < RTX_GEOM_SPHERE || k > RTX_GEOM_CIRCLE) return bad("entry kind invalid");
+        if (isPrim(k) ? (gi < 0 || gi >= primCount(k)) : (gi < 0 || gi >= d->n_groups || d->group_kind[gi] != k)) return bad("entry geometry out of range");
         if (d->entry_xf_count[e] < 0 || d->entry_xf_begin[e] < 0 || d->entry_xf_begin[e] + d->entry_xf_count[e] > d->n_xforms) return bad("entry transform range invalid");
         if (d->entry_volume[e] >= d->n_volumes) return bad("entry volume out of range");
         if (d->entry_volume[e] >= 0 && (k == RTX_GEOM_MESH || k == RTX_GEOM_PLANE))
@@ -413,6 +421,18 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     std::vector<int> planeMat(d->plane_mat, d->plane_mat + d->n_planes);
     for (int i = 0; i < d->n_planes; i++)
         for (int a = 0; a < 3; a++) { planes[8 * i + a] = d->plane_point[3 * i + a]; planes[8 * i + 3 + a] = d->plane_normal[3 * i + a]; }
+
+    std::vector<double> circles((size_t)8 * d->n_circles);
+    std::vector<int> circleMat(d->circle_mat, d->circle_mat + d->n_circles);
+    for (int i = 0; i < d->n_circles; i++) {  // NewCircle rt/circle.go:14-31
+        const double *c = d->circle_center + 3 * i, *n = d->circle_normal + 3 * i;
+        double* o = circles.data() + 8 * (size_t)i;
+        for (int a = 0; a < 3; a++) { o[a] = c[a]; o[3 + a] = n[a]; }
+        o[6] = d->circle_radius[i];
+        o[7] = n[0] * c[0] + n[1] * c[1] + n[2] * c[2];
+    }
+    std::vector<double> perlinVec(d->n_perlin > 0 ? d->perlin_vec : nullptr, d->n_perlin > 0 ? d->perlin_vec + (size_t)768 * d->n_perlin : nullptr);
+    std::vector<int> perlinPerm(d->n_perlin > 0 ? d->perlin_perm : nullptr, d->n_perlin > 0 ? d->perlin_perm + (size_t)768 * d->n_perlin : nullptr);
 
     // ---- triangles: meshes are permuted into BLAS leaf order; loose triangles (world entries / Box-list items) follow
     std::vector<Node4> nodes;                       // host-built nodes: every BLAS with the host builder, and always the TLAS
@@ -560,7 +580,7 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
         E.xf_begin = d->entry_xf_begin[e]; E.xf_count = d->entry_xf_count[e]; E.volume = d->entry_volume[e]; E.rank = e;
         Box b;
         b.reset();
-        if (k <= RTX_GEOM_PLANE) {
+        if (isPrim(k)) {
             E.index = devPrim(k, gi);
             b = prim_box(d, k, gi);
         } else if (k == RTX_GEOM_LIST) {
@@ -701,6 +721,7 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
                      bQuads = pad(quads.size() * sizeof(double)), bInfo = pad((size_t)totalTris * sizeof(int4));
         const size_t geom = std::max<size_t>(bNodes + bTris + bSph + bQuads, 256);
         WANT(entries, S.entries); WANT(unbounded, S.unbounded); WANT(sphMat, S.sph_mat); WANT(quadMat, S.quad_mat); WANT(planes, S.planes); WANT(planeMat, S.plane_mat);
+        WANT(circles, S.circles); WANT(circleMat, S.circle_mat); WANT(perlinVec, S.perlin_vec); WANT(perlinPerm, S.perlin_perm);
         WANT(listItems, S.list_items); WANT(xfs, S.xforms); WANT(xfCanon, S.xf_canon); WANT(vols, S.volumes); WANT(mats, S.mats); WANT(texs, S.texs);
         WANT(lights, S.light_quads); WANT(envTex, S.env_tex); WANT(marg, S.env_marg); WANT(cond, S.env_cond); WANT(pdf, S.env_pdf);
 #undef WANT

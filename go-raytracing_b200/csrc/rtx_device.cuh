@@ -83,6 +83,10 @@ struct DevScene {
     const int4* tri_info;   // x: primitive id inside its geometry (face order), y: material, z: rank, w: -
     const double* planes;   // 8 doubles: point, normal, -,-
     const int* plane_mat;
+    const double* circles;  // 8 doubles: center, unit normal, radius, D = normal . center (rt/circle.go:14-20)
+    const int* circle_mat;
+    const double* perlin_vec;  // [n][256][3] (rt/noise.go:9)
+    const int* perlin_perm;    // [n][3][256]
     const int2* list_items;  // (kind, device index)
     const DXform* xforms;
     const double* xf_canon;  // 8 doubles per entry: offset xyz, sin, cos, inverse scale xyz (identity values where an op is absent)
@@ -118,11 +122,11 @@ struct RayF {  // float32 ray for the box tests: t_plane = fma(plane, i, c), wit
 struct Hit {
     double t;
     int entry;  // -1 = miss
-    int kind;   // RTX_GEOM_SPHERE..PLANE of the primitive that was hit, or 6 = volume medium
+    int kind;   // RTX_GEOM_SPHERE..PLANE / RTX_GEOM_CIRCLE of the primitive that was hit, or RTX_KIND_VOLUME
     int prim;   // device primitive index (spheres/quads/tris/planes arrays)
     int item;   // primitive id inside the entry's geometry (list item / mesh face / 0)
 };
-#define RTX_KIND_VOLUME 6
+#define RTX_KIND_VOLUME 15   /* internal: the hit is a Volume medium (not an RTX_GEOM_* value) */
 
 struct TraceCounters {
     unsigned nodes, tris, spheres, quads, planes;
@@ -265,7 +269,21 @@ __device__ __forceinline__ double isect_plane(const double* p, const RayD& r) {
     return dot(sub(ld3(p), o), n) / denom;
 }
 
-__device__ __forceinline__ bool kind_closed(int kind) { return kind == RTX_GEOM_QUAD || kind == RTX_GEOM_TRIANGLE || kind == RTX_KIND_VOLUME; }
+// rt/circle.go:33-52 (closed interval: rayT.Contains)
+__device__ __forceinline__ double isect_circle(const double* c, const RayD& r, double tmin, double tmax) {
+    const D4 c0 = ldg256d(c), c1 = ldg256d(c + 4);   // center.xyz n.x | n.yz radius D
+    D3 n = d3(c0.w, c1.x, c1.y), o = d3(r.ox, r.oy, r.oz), d = d3(r.dx, r.dy, r.dz);
+    double denom = dot(n, d);
+    if (fabs(denom) < 1e-8) return RTX_NAN_D;
+    double t = (c1.w - dot(n, o)) / denom;
+    if (!(tmin <= t && t <= tmax)) return RTX_NAN_D;
+    D3 P = add(o, scale(d, t));
+    double dist = sqrt(len2(sub(P, d3(c0.x, c0.y, c0.z))));
+    if (dist > c1.z) return RTX_NAN_D;
+    return t;
+}
+
+__device__ __forceinline__ bool kind_closed(int kind) { return kind == RTX_GEOM_QUAD || kind == RTX_GEOM_TRIANGLE || kind == RTX_GEOM_CIRCLE || kind == RTX_KIND_VOLUME; }
 
 // Generic primitive t with the reference's interval convention against [tmin, tmax]. Out of line (one copy of the
 // four float64 tests in each kernel keeps the trace loop inside the instruction cache); everything travels in registers.
@@ -275,6 +293,7 @@ __device__ __noinline__ double isect_prim_ool(int kind, const double* p, double 
     double t;
     if (kind == RTX_GEOM_SPHERE) return isect_sphere(p, r, tmin, tmax);
     if (kind == RTX_GEOM_QUAD) return isect_quad(p, r, tmin, tmax, nullptr);
+    if (kind == RTX_GEOM_CIRCLE) return isect_circle(p, r, tmin, tmax);
     if (kind == RTX_GEOM_TRIANGLE) {
         t = isect_tri(p, r, nullptr);
         return (tmin <= t && t <= tmax) ? t : RTX_NAN_D;
@@ -287,6 +306,7 @@ __device__ __forceinline__ double isect_prim(const DevScene& S, int kind, int id
     if (kind == RTX_GEOM_SPHERE) { if (tc) tc->spheres++; p = S.spheres + 8 * (size_t)idx; }
     else if (kind == RTX_GEOM_QUAD) { if (tc) tc->quads++; p = S.quads + 16 * (size_t)idx; }
     else if (kind == RTX_GEOM_TRIANGLE) { if (tc) tc->tris++; p = S.tris + RTX_TRI_D * (size_t)idx; }
+    else if (kind == RTX_GEOM_CIRCLE) { if (tc) tc->quads++; p = S.circles + 8 * (size_t)idx; }   // counted with the quads (planar, 64-128 B)
     else { if (tc) tc->planes++; p = S.planes + 8 * (size_t)idx; }
     return isect_prim_ool(kind, p, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tm, tmin, tmax);
 }
@@ -389,6 +409,17 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const RayD& rw, 
         { const D4 tn = ldg256d(S.tris + RTX_TRI_D * (size_t)h.prim + 8); n = d3(tn.y, tn.z, tn.w); }
         out.mat = S.tri_info[h.prim].y;
         if (want_uv) { double uv[2] = {0, 0}; isect_tri(S.tris + RTX_TRI_D * (size_t)h.prim, r, uv); out.u = uv[0]; out.v = uv[1]; }
+    } else if (h.kind == RTX_GEOM_CIRCLE) {
+        const double* c = S.circles + 8 * (size_t)h.prim;
+        n = ld3(c + 3);
+        out.mat = S.circle_mat[h.prim];
+        if (want_uv) {  // rt/circle.go:59-72
+            D3 uu = fabs(n.y) > 0.9 ? unit(cross(d3(1, 0, 0), n)) : unit(cross(d3(0, 1, 0), n));
+            D3 vv = cross(n, uu);
+            D3 lp = sub(P, ld3(c));
+            out.u = (dot(lp, uu) / c[6] + 1.0) * 0.5;
+            out.v = (dot(lp, vv) / c[6] + 1.0) * 0.5;
+        }
     } else {
         n = ld3(S.planes + 8 * (size_t)h.prim + 3);
         out.mat = S.plane_mat[h.prim];

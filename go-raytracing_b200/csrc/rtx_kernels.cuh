@@ -267,6 +267,23 @@ __global__ void __launch_bounds__(256) k_extend_flat(Ctl* ctl, Pool pool, int cu
 }
 
 // ---- textures (rt/texture.go:43-45, :63-77) ----------------------------------------------------------------------
+// Perlin noise with the caller's tables (rt/noise.go:30-92), float64, reference operation order
+__device__ __noinline__ double perlin_noise(const double* vec, const int* perm, double px, double py, double pz) {
+    const double fx = floor(px), fy = floor(py), fz = floor(pz);
+    const double u = px - fx, v = py - fy, w = pz - fz;
+    const int i = (int)fx, j = (int)fy, k = (int)fz;
+    double accum = 0.0;
+    for (int di = 0; di < 2; di++)
+        for (int dj = 0; dj < 2; dj++)
+            for (int dk = 0; dk < 2; dk++) {
+                const int idx = perm[(i + di) & 255] ^ perm[256 + ((j + dj) & 255)] ^ perm[512 + ((k + dk) & 255)];
+                const double* c = vec + 3 * idx;
+                const double wx = u - (double)di, wy = v - (double)dj, wz = w - (double)dk;
+                accum += ((double)di * u + (1 - (double)di) * (1 - u)) * ((double)dj * v + (1 - (double)dj) * (1 - v)) *
+                         ((double)dk * w + (1 - (double)dk) * (1 - w)) * (c[0] * wx + c[1] * wy + c[2] * wz);
+            }
+    return accum;
+}
 __device__ __forceinline__ float3 tex_value(const DevScene& S, int id, D3 p) {
     DTexture t = S.texs[id];
     for (int guard = 0; guard < 8 && t.type == RTX_TEX_CHECKER; guard++) {
@@ -275,6 +292,19 @@ __device__ __forceinline__ float3 tex_value(const DevScene& S, int id, D3 p) {
         long long zi = (long long)floor(t.inv_scale * p.z + 1e-4);
         bool even = ((xi + yi + zi) % 2) == 0;
         t = S.texs[even ? t.even : t.odd];
+    }
+    if (t.type == RTX_TEX_NOISE) {  // NoiseTexture.Value rt/texture.go:81-85: 0.5 (1 + sin(scale z + 10 turb(scale p, 7)))
+        const double* vec = S.perlin_vec + (size_t)t.even * 768;
+        const int* perm = S.perlin_perm + (size_t)t.even * 768;
+        const double sc = t.inv_scale;   // NoiseTexture.scale (not inverted)
+        double accum = 0.0, weight = 1.0, qx = sc * p.x, qy = sc * p.y, qz = sc * p.z;   // Perlin.Turb rt/noise.go:55-65
+        for (int oct = 0; oct < 7; oct++) {
+            accum += weight * perlin_noise(vec, perm, qx, qy, qz);
+            weight *= 0.5;
+            qx = 2 * qx; qy = 2 * qy; qz = 2 * qz;
+        }
+        const float tv = (float)(0.5 * (1.0 + sin(sc * p.z + 10.0 * fabs(accum))));
+        return make_float3(tv, tv, tv);
     }
     return make_float3(t.color[0], t.color[1], t.color[2]);
 }

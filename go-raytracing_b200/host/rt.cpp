@@ -58,6 +58,33 @@ Vec3 AABB::Centroid() const { return {(X.Min + X.Max) * 0.5, (Y.Min + Y.Max) * 0
 
 // ---- textures / materials --------------------------------------------------------------------------------
 TexturePtr NewSolidColor(Color albedo) { return std::make_shared<SolidColor>(albedo); }
+TexturePtr NewNoiseTexture(double scale, uint64_t seed) {  // rt/texture.go:24-29 + NewPerlin rt/noise.go:15-28 (same draw order, seeded SplitMix64)
+    uint64_t st = seed;
+    auto next = [&st]() {
+        uint64_t z = (st += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    auto uniform = [&]() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); };
+    auto p = std::make_shared<Perlin>();
+    for (int i = 0; i < 256; i++) {  // RandomVec3Range(-1, 1).Unit()
+        Vec3 v{-1 + 2 * uniform(), -1 + 2 * uniform(), -1 + 2 * uniform()};
+        p->randvec[i] = v.Unit();
+    }
+    int* perms[3] = {p->permX, p->permY, p->permZ};
+    for (int a = 0; a < 3; a++) {  // perlinGeneratePerm + permute :67-78
+        for (int i = 0; i < 256; i++) perms[a][i] = i;
+        for (int i = 255; i > 0; i--) {
+            int target = (int)(uniform() * (double)(i + 1));   // RandomInt(0, i)
+            if (target > i) target = i;
+            std::swap(perms[a][i], perms[a][target]);
+        }
+    }
+    auto t = std::make_shared<NoiseTexture>();
+    t->noise = p; t->scale = scale;
+    return t;
+}
 TexturePtr NewCheckerTexture(double scale, TexturePtr even, TexturePtr odd) { return std::make_shared<CheckerTexture>(scale, even, odd); }
 TexturePtr NewCheckerTextureFromColors(double scale, Color c1, Color c2) { return NewCheckerTexture(scale, NewSolidColor(c1), NewSolidColor(c2)); }
 
@@ -125,6 +152,23 @@ HittableListPtr NewHittableList() { return std::make_shared<HittableList>(); }
 void HittableList::Add(HittablePtr o) {
     Objects.push_back(o);
     bbox = NewAABBFromBoxes(bbox, o->BoundingBox());
+}
+std::shared_ptr<Circle> NewCircle(Point3 center, Vec3 normal, double radius, MaterialPtr mat) {  // rt/circle.go:14-31
+    auto c = std::make_shared<Circle>();
+    c->normal = normal.Unit(); c->center = center; c->radius = radius; c->mat = mat;
+    Vec3 rvec{radius, radius, radius};
+    c->bbox = NewAABBFromPoints(center.Sub(rvec), center.Add(rvec));
+    return c;
+}
+HittablePtr Pyramid(Point3 baseCenter, double baseSize, double height, MaterialPtr mat) {  // rt/primitives.go:39-71
+    auto sides = NewHittableList();
+    sides->Add(NewQuad({baseCenter.X - baseSize / 2, baseCenter.Y, baseCenter.Z - baseSize / 2}, {baseSize, 0, 0}, {0, 0, baseSize}, mat));
+    Point3 apex{baseCenter.X, baseCenter.Y + height, baseCenter.Z};
+    double halfSize = baseSize / 2;
+    Point3 corners[4] = {{baseCenter.X + halfSize, baseCenter.Y, baseCenter.Z - halfSize}, {baseCenter.X + halfSize, baseCenter.Y, baseCenter.Z + halfSize},
+                         {baseCenter.X - halfSize, baseCenter.Y, baseCenter.Z + halfSize}, {baseCenter.X - halfSize, baseCenter.Y, baseCenter.Z - halfSize}};
+    for (int i = 0; i < 4; i++) sides->Add(NewTriangle(corners[i], corners[(i + 1) % 4], apex, mat));
+    return sides;
 }
 HittablePtr Box(Point3 a, Point3 b, MaterialPtr mat) {  // rt/primitives.go:5-37
     auto sides = NewHittableList();

@@ -83,6 +83,15 @@ struct CheckerTexture : Texture {
     TexturePtr even, odd;
     CheckerTexture(double scale, TexturePtr e, TexturePtr o) : invScale(1.0 / scale), even(e), odd(o) {}
 };
+struct Perlin {  // rt/noise.go:8-28. The reference fills the tables from Go's auto-seeded global source; here from a seeded stream in the same draw order
+    Vec3 randvec[256];
+    int permX[256], permY[256], permZ[256];
+};
+struct NoiseTexture : Texture {  // rt/texture.go:19-29
+    std::shared_ptr<Perlin> noise;
+    double scale;
+};
+TexturePtr NewNoiseTexture(double scale, uint64_t seed = 0x5EEDull);
 TexturePtr NewSolidColor(Color albedo);
 TexturePtr NewCheckerTexture(double scale, TexturePtr even, TexturePtr odd);
 TexturePtr NewCheckerTextureFromColors(double scale, Color c1, Color c2);
@@ -152,6 +161,14 @@ struct Plane : Hittable {  // rt/plane.go
     MaterialPtr Mat;
     AABB BoundingBox() const override;
 };
+struct Circle : Hittable {  // rt/circle.go
+    Point3 center;
+    Vec3 normal;  // unit
+    double radius;
+    MaterialPtr mat;
+    AABB bbox;
+    AABB BoundingBox() const override { return bbox; }
+};
 struct HittableList : Hittable {  // rt/hittable_list.go
     std::vector<HittablePtr> Objects;
     AABB bbox;
@@ -207,6 +224,8 @@ std::shared_ptr<Triangle> NewTriangle(Point3 v0, Point3 v1, Point3 v2, MaterialP
 std::shared_ptr<Plane> NewPlane(Point3 point, Vec3 normal, MaterialPtr mat);
 HittableListPtr NewHittableList();
 HittablePtr Box(Point3 a, Point3 b, MaterialPtr mat);  // rt/primitives.go:5
+std::shared_ptr<Circle> NewCircle(Point3 center, Vec3 normal, double radius, MaterialPtr mat);  // rt/circle.go:14
+HittablePtr Pyramid(Point3 baseCenter, double baseSize, double height, MaterialPtr mat);         // rt/primitives.go:39
 std::shared_ptr<Translate> NewTranslate(HittablePtr obj, Vec3 offset);
 std::shared_ptr<RotateY> Ry(HittablePtr obj, double angleDegrees);
 std::shared_ptr<Scale> NewScale(HittablePtr obj, Vec3 factor);
@@ -310,6 +329,8 @@ Scene HDRITestScene(const std::string& hdrPath);              // rt/scenes.go:40
 Scene CornellBoxScene();                                      // rt/scenes.go:463
 Scene CornellBoxGlossy();                                     // rt/scenes.go:606
 Scene CornellBoxLucy(const std::string& objPath);             // rt/scenes.go:714
+Scene PerlinSpheresScene(uint64_t seed = 0x5EEDull);           // rt/scenes.go:242
+Scene PrimitivesScene();                                       // rt/scenes.go:313
 Scene CheckeredSpheresScene();                                 // rt/scenes.go:132
 Scene SimpleScene();                                           // rt/scenes.go:172
 Scene QuadsScene();                                            // rt/scenes.go:274
@@ -331,6 +352,10 @@ struct FlatScene {
     std::vector<int32_t> tri_mat, tri_rank;
     std::vector<double> plane_point, plane_normal;
     std::vector<int32_t> plane_mat;
+    std::vector<double> circle_center, circle_normal, circle_radius;
+    std::vector<int32_t> circle_mat;
+    std::vector<double> perlin_vec;
+    std::vector<int32_t> perlin_perm;
     std::vector<int32_t> group_kind, group_begin, group_count, list_item_kind, list_item_index;
     std::vector<int32_t> xf_type;
     std::vector<double> xf_a, xf_b;

@@ -14,7 +14,8 @@ struct Flattener {
     FlatScene& fs;
     std::unordered_map<const Texture*, int> texIds;
     std::unordered_map<const Material*, int> matIds;
-    std::unordered_map<const Hittable*, int> sphIds, quadIds, triIds, planeIds, groupIds;
+    std::unordered_map<const Hittable*, int> sphIds, quadIds, triIds, planeIds, circleIds, groupIds;
+    std::unordered_map<const Perlin*, int> perlinIds;
     explicit Flattener(FlatScene& f) : fs(f) {}
 
     static void push3(std::vector<double>& v, const Vec3& a) { v.push_back(a.X); v.push_back(a.Y); v.push_back(a.Z); }
@@ -29,7 +30,18 @@ struct Flattener {
         if (auto s = dynamic_cast<const SolidColor*>(t.get())) { type = RTX_TEX_SOLID; c = s->Albedo; }
         else if (auto ch = dynamic_cast<const CheckerTexture*>(t.get())) {
             type = RTX_TEX_CHECKER; inv = ch->invScale; even = texture(ch->even); odd = texture(ch->odd);
-        } else throw std::runtime_error("flatten: unsupported Texture type (only SolidColor and CheckerTexture are on the device path)");
+        } else if (auto nt = dynamic_cast<const NoiseTexture*>(t.get())) {   // scale travels in tex_inv_scale (not inverted), the table index in tex_even
+            type = RTX_TEX_NOISE; inv = nt->scale;
+            auto pit = perlinIds.find(nt->noise.get());
+            if (pit == perlinIds.end()) {
+                even = (int)(fs.perlin_perm.size() / 768);
+                for (int k = 0; k < 256; k++) push3(fs.perlin_vec, nt->noise->randvec[k]);
+                for (int k = 0; k < 256; k++) fs.perlin_perm.push_back(nt->noise->permX[k]);
+                for (int k = 0; k < 256; k++) fs.perlin_perm.push_back(nt->noise->permY[k]);
+                for (int k = 0; k < 256; k++) fs.perlin_perm.push_back(nt->noise->permZ[k]);
+                perlinIds[nt->noise.get()] = even;
+            } else even = pit->second;
+        } else throw std::runtime_error("flatten: unsupported Texture type (SolidColor, CheckerTexture and NoiseTexture are on the device path)");
         int id = (int)fs.tex_type.size();
         fs.tex_type.push_back(type); push3(fs.tex_color, c); fs.tex_inv_scale.push_back(inv);
         fs.tex_even.push_back(even); fs.tex_odd.push_back(odd);
@@ -84,6 +96,16 @@ struct Flattener {
             push3(fs.tri_v0, t->v0); push3(fs.tri_v1, t->v1); push3(fs.tri_v2, t->v2);
             fs.tri_mat.push_back(material(t->mat)); fs.tri_rank.push_back(0);
             triIds[h] = index;
+            return true;
+        }
+        if (auto c = dynamic_cast<const Circle*>(h)) {
+            kind = RTX_GEOM_CIRCLE;
+            auto it = circleIds.find(h);
+            if (it != circleIds.end()) { index = it->second; return true; }
+            index = (int)fs.circle_mat.size();
+            push3(fs.circle_center, c->center); push3(fs.circle_normal, c->normal); fs.circle_radius.push_back(c->radius);
+            fs.circle_mat.push_back(material(c->mat));
+            circleIds[h] = index;
             return true;
         }
         if (auto p = dynamic_cast<const Plane*>(h)) {
@@ -224,6 +246,9 @@ rtx_scene_desc FlatScene::Desc() const {
     d.n_tris = (int)tri_mat.size(); d.tri_v0 = tri_v0.data(); d.tri_v1 = tri_v1.data(); d.tri_v2 = tri_v2.data();
     d.tri_mat = tri_mat.data(); d.tri_rank = tri_rank.data();
     d.n_planes = (int)plane_mat.size(); d.plane_point = plane_point.data(); d.plane_normal = plane_normal.data(); d.plane_mat = plane_mat.data();
+    d.n_circles = (int)circle_mat.size(); d.circle_center = circle_center.data(); d.circle_normal = circle_normal.data();
+    d.circle_radius = circle_radius.data(); d.circle_mat = circle_mat.data();
+    d.n_perlin = (int)(perlin_perm.size() / 768); d.perlin_vec = perlin_vec.data(); d.perlin_perm = perlin_perm.data();
     d.n_groups = (int)group_kind.size(); d.group_kind = group_kind.data(); d.group_begin = group_begin.data(); d.group_count = group_count.data();
     d.n_list_items = (int)list_item_kind.size(); d.list_item_kind = list_item_kind.data(); d.list_item_index = list_item_index.data();
     d.n_xforms = (int)xf_type.size(); d.xf_type = xf_type.data(); d.xf_a = xf_a.data(); d.xf_b = xf_b.data();

@@ -1,5 +1,6 @@
 // rt_scenes.cpp — the five configured scenes of BASELINE.json and the other scene functions of rt/scenes.go whose vocabulary
-// the device path covers (CheckeredSpheres, Simple, Quads, GlossyMetalTest, CornellSmoke), mirrored from the reference.
+// the device path covers (CheckeredSpheres, Simple, PerlinSpheres, Quads, Primitives, GlossyMetalTest, CornellSmoke), mirrored
+// from the reference. EarthScene needs ImageTexture (JPEG decode) and stays outside.
 // RandomScene draws from a seeded SplitMix64 stream in the reference's draw order (the reference uses
 // Go's auto-seeded global source, rt/utils.go:18, so its geometry differs run to run).
 #include <sys/stat.h>
@@ -180,6 +181,38 @@ Scene CornellBoxLucy(const std::string& objPath) {  // rt/scenes.go:714-817
 }
 
 // ---- the remaining scene functions the device vocabulary covers ------------------------------------------------
+Scene PerlinSpheresScene(uint64_t seed) {  // rt/scenes.go:242-272 (the Perlin tables come from a seeded stream, see NewNoiseTexture)
+    auto world = NewHittableList();
+    auto perl = NewLambertianTexture(NewNoiseTexture(4.0, seed));
+    world->Add(NewSphere({0, 2, 0}, 2, perl));
+    world->Add(NewPlane({0, 0, -1}, {0, 1, 0}, perl));
+    auto cam = NewCameraBuilder().SetResolution(600, 16.0 / 9.0).SetQuality(100, 50).SetPosition({13, 2, -10}, {0, 1.5, 0}, {0, 1, 0}).SetLens(20, 0, 10)
+                   .EnableSkyGradient(true).Build();
+    return {world, cam};
+}
+
+Scene PrimitivesScene() {  // rt/scenes.go:313-404: plane, Circle, Pyramid, glass sphere, Box, area light, mirror sphere
+    auto world = NewHittableList();
+    auto red = NewLambertian({0.8, 0.1, 0.1});
+    auto green = NewLambertian({0.1, 0.8, 0.1});
+    auto blue = NewLambertian({0.1, 0.1, 0.8});
+    auto metal = NewMetal({1.0, 1.0, 1.0}, 0);
+    auto lightMat = NewDiffuseLight(NewSolidColor({2, 2, 2}));
+    auto checker = NewLambertianTexture(NewCheckerTextureFromColors(1.0, {0.0, 0.0, 0.0}, {0.9, 0.9, 0.9}));
+    world->Add(NewPlane({0, -1, 0}, {0, 1, 0}, checker));
+    world->Add(NewCircle({-5, 0, 0}, {0, 1, 0}, 0.9, red));
+    world->Add(Pyramid({-2.5, -1, 0}, 1.4, 1.8, green));
+    world->Add(NewSphere({0, 0.6, 0}, 0.8, NewDielectric(1.5)));
+    const double cubeX = 2.5, cubeSize = 1.0;
+    world->Add(Box({cubeX - cubeSize / 2, -1, -cubeSize / 2}, {cubeX + cubeSize / 2, -1 + cubeSize, cubeSize / 2}, blue));
+    auto areaLight = NewQuad({-2, 5, -2}, {4, 0, 0}, {0, 0, 4}, lightMat);
+    world->Add(areaLight);
+    world->Add(NewSphere({5, 0.6, 0}, 0.8, metal));
+    auto cam = NewCameraBuilder().SetResolution(800, 16.0 / 9.0).SetQuality(300, 25).SetPosition({0, 2, 10}, {0, 0, 0}, {0, 1, 0}).SetLens(45, 0, 10)
+                   .SetBackground({0, 0, 0}).EnableSkyGradient(true).AddLight(areaLight).Build();
+    return {world, cam};
+}
+
 Scene CheckeredSpheresScene() {  // rt/scenes.go:132-170
     auto world = NewHittableList();
     auto checker = NewLambertianTexture(NewCheckerTextureFromColors(0.32, {0.2, 0.3, 0.1}, {0.9, 0.9, 0.9}));
@@ -261,8 +294,10 @@ Scene LoadSceneByName(const std::string& nameIn, const std::string& assetRoot, u
     if (name == "quads" || name == "quads-scene") return QuadsScene();
     if (name == "cornell-smoke" || name == "cornell-fog") return CornellSmoke();
     if (name == "glossy-metal" || name == "glossy-metal-test") return GlossyMetalTest();
-    if (name == "perlin" || name == "perlin-spheres" || name == "earth" || name == "earth-scene" || name == "primitives" || name == "primitives-scene")
-        throw std::runtime_error("scene '" + nameIn + "' uses vocabulary outside the device path (NoiseTexture / ImageTexture / Circle): see DESIGN.md section 8");
+    if (name == "perlin" || name == "perlin-spheres") return PerlinSpheresScene(seed);
+    if (name == "primitives" || name == "primitives-scene") return PrimitivesScene();
+    if (name == "earth" || name == "earth-scene")
+        throw std::runtime_error("scene '" + nameIn + "' uses vocabulary outside the device path (ImageTexture): see DESIGN.md section 8");
     if (name == "cornell-lucy") {
         std::string real = root + "/assets/models/lucy_low.obj", standin = root + "/assets/models/lucy_standin.obj";
         return CornellBoxLucy(bigFile(real) ? real : standin);

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RTX_ABI_VERSION 1
+#define RTX_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------------------ */
 enum {
@@ -41,10 +41,11 @@ enum {
 /* Materials: rt/material.go:33 (Lambertian) :86 (Metal) :146 (Dielectric) :202 (DiffuseLight) :243 (Isotropic) */
 enum { RTX_MAT_LAMBERTIAN = 0, RTX_MAT_METAL = 1, RTX_MAT_DIELECTRIC = 2, RTX_MAT_DIFFUSE_LIGHT = 3, RTX_MAT_ISOTROPIC = 4 };
 /* Textures: rt/texture.go:9 (SolidColor) :13 (CheckerTexture) */
-enum { RTX_TEX_SOLID = 0, RTX_TEX_CHECKER = 1 };
+enum { RTX_TEX_SOLID = 0, RTX_TEX_CHECKER = 1, RTX_TEX_NOISE = 2 };
 /* Hittables: rt/sphere.go:6, rt/quad.go:5, rt/triangle.go:8, rt/plane.go:5, rt/hittable_list.go:3 (Box = list of 6 quads,
  * rt/primitives.go:5), rt/bvh.go:13 (mesh BVH returned by LoadOBJ, rt/obj_loader.go:109) */
-enum { RTX_GEOM_SPHERE = 0, RTX_GEOM_QUAD = 1, RTX_GEOM_TRIANGLE = 2, RTX_GEOM_PLANE = 3, RTX_GEOM_LIST = 4, RTX_GEOM_MESH = 5 };
+enum { RTX_GEOM_SPHERE = 0, RTX_GEOM_QUAD = 1, RTX_GEOM_TRIANGLE = 2, RTX_GEOM_PLANE = 3, RTX_GEOM_LIST = 4, RTX_GEOM_MESH = 5,
+       RTX_GEOM_CIRCLE = 6 /* a primitive like 0-3 (rt/circle.go); numbered after the groups to keep ABI 1 values */ };
 /* Instance wrappers: rt/transform.go:78 (Translate) :113 (RotateY) :360 (Scale) */
 enum { RTX_XF_TRANSLATE = 0, RTX_XF_ROTATE_Y = 1, RTX_XF_SCALE = 2 };
 
@@ -113,7 +114,7 @@ typedef struct rtx_scene_desc {
     const int32_t* group_begin;   /* [n] LIST: first index into list_item_*; MESH: first triangle */
     const int32_t* group_count;   /* [n] */
     int32_t n_list_items;
-    const int32_t* list_item_kind;  /* [n_list_items] RTX_GEOM_SPHERE..RTX_GEOM_PLANE */
+    const int32_t* list_item_kind;  /* [n_list_items] RTX_GEOM_SPHERE..RTX_GEOM_PLANE or RTX_GEOM_CIRCLE */
     const int32_t* list_item_index; /* [n_list_items] index into that primitive array */
 
     /* instance transform ops, referenced by entries as ranges, OUTERMOST FIRST */
@@ -130,7 +131,7 @@ typedef struct rtx_scene_desc {
     /* world entries, insertion order */
     int32_t n_entries;
     const int32_t* entry_geom_kind;  /* [n] RTX_GEOM_*                                      */
-    const int32_t* entry_geom_index; /* [n] primitive index (kinds 0-3) or group index (4,5) */
+    const int32_t* entry_geom_index; /* [n] primitive index (kinds 0-3, 6) or group index (4,5) */
     const int32_t* entry_xf_begin;   /* [n] */
     const int32_t* entry_xf_count;   /* [n] */
     const int32_t* entry_volume;     /* [n] -1 or volume index: entry is Volume{boundary = this geometry} */
@@ -146,6 +147,20 @@ typedef struct rtx_scene_desc {
     const double* env_rgb;          /* [3*w*h] decoded linear pixels, row-major, y = 0 top (rt/image_loader.go:374-382) */
     double env_rotation;            /* radians (rt/hdri.go:51) */
     int32_t env_importance_sampling; /* HDRIEnvironment.useImportanceSampling */
+
+    /* ---- ABI 2 ---- */
+    /* Circle (rt/circle.go:5-31): a disk. Entries / list items of kind RTX_GEOM_CIRCLE index these arrays. */
+    int32_t n_circles;
+    const double* circle_center;  /* [3*n] */
+    const double* circle_normal;  /* [3*n] already unit (NewCircle normalises, rt/circle.go:16) */
+    const double* circle_radius;  /* [n] */
+    const int32_t* circle_mat;    /* [n] */
+    /* Perlin tables of NoiseTexture (rt/noise.go:8-28). The reference fills them from Go's auto-seeded global source; the
+     * caller passes the tables it drew, so that every consumer of the scene sees the same noise. A texture of type
+     * RTX_TEX_NOISE uses tex_inv_scale[i] as NoiseTexture.scale (not inverted) and tex_even[i] as its table index. */
+    int32_t n_perlin;
+    const double* perlin_vec;     /* [n][256][3] unit vectors (Perlin.randvec) */
+    const int32_t* perlin_perm;   /* [n][3][256] permX, permY, permZ */
 } rtx_scene_desc;
 
 /* Camera public fields (rt/camera.go:18-40). The library re-derives Initialize() (rt/camera.go:286-344)

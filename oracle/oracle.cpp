@@ -229,6 +229,48 @@ struct CheckerTexture : Texture {
     }
 };
 
+// ---- rt/noise.go, rt/texture.go:19-29, :81-85 -------------------------------------------------------------------------
+struct Perlin {  // the tables come with the scene (the reference draws them from Go's global source, rt/noise.go:15-28)
+    Vec3 randvec[256];
+    int permX[256], permY[256], permZ[256];
+    double Noise(const Point3& pt) const {  // :30-53
+        double u = pt.X - std::floor(pt.X), v = pt.Y - std::floor(pt.Y), w = pt.Z - std::floor(pt.Z);
+        int i = (int)std::floor(pt.X), j = (int)std::floor(pt.Y), k = (int)std::floor(pt.Z);
+        Vec3 c[2][2][2];
+        for (int di = 0; di < 2; di++)
+            for (int dj = 0; dj < 2; dj++)
+                for (int dk = 0; dk < 2; dk++) c[di][dj][dk] = randvec[permX[(i + di) & 255] ^ permY[(j + dj) & 255] ^ permZ[(k + dk) & 255]];
+        double accum = 0.0;  // perlinInterp :79-92
+        for (int a = 0; a < 2; a++)
+            for (int b = 0; b < 2; b++)
+                for (int dk = 0; dk < 2; dk++) {
+                    Vec3 weightV{u - (double)a, v - (double)b, w - (double)dk};
+                    accum += ((double)a * u + (1 - (double)a) * (1 - u)) * ((double)b * v + (1 - (double)b) * (1 - v)) *
+                             ((double)dk * w + (1 - (double)dk) * (1 - w)) * Dot(c[a][b][dk], weightV);
+                }
+        return accum;
+    }
+    double Turb(const Point3& pt, int depth) const {  // :55-65
+        double accum = 0.0, weight = 1.0;
+        Point3 tempPt = pt;
+        for (int i = 0; i < depth; i++) {
+            accum += weight * Noise(tempPt);
+            weight *= 0.5;
+            tempPt = tempPt.Scale(2);
+        }
+        return std::fabs(accum);
+    }
+};
+struct NoiseTexture : Texture {
+    const Perlin* noise;
+    double scale;
+    Color Value(double, double, const Point3& p) const override {  // rt/texture.go:81-85
+        double s = scale * p.Z + 10.0 * noise->Turb(p.Scale(scale), 7);
+        double turbValue = 0.5 * (1.0 + std::sin(s));
+        return Color{1, 1, 1}.Scale(turbValue);
+    }
+};
+
 // ---- rt/hittable.go --------------------------------------------------------------------------------------------------
 struct Material;
 struct HitRecord {
@@ -478,6 +520,43 @@ struct Plane : Hittable {
         rec->T = t; rec->P = r.At(t);
         rec->SetFaceNormal(r, Normal);
         rec->Mat = Mat;
+        rec->prim = id;
+        return true;
+    }
+};
+
+// ---- rt/circle.go ------------------------------------------------------------------------------------------------------------
+struct Circle : Hittable {
+    Point3 center;
+    Vec3 normal;
+    double radius, D;
+    const Material* mat;
+    AABB bbox;
+    int id = 0;
+    static Circle* New(Point3 center, Vec3 normal, double radius, const Material* m) {  // :14-31
+        auto c = new Circle();
+        c->normal = normal.Unit(); c->center = center; c->radius = radius; c->mat = m;
+        c->D = Dot(c->normal, center);
+        Vec3 rvec{radius, radius, radius};
+        c->bbox = AABBFromPoints(center.Sub(rvec), center.Add(rvec));
+        return c;
+    }
+    AABB BoundingBox() const override { return bbox; }
+    bool Hit(const Ray& r, Interval rayT, HitRecord* rec) const override {  // :36-74
+        double denom = Dot(normal, r.dir);
+        if (std::fabs(denom) < 1e-8) return false;
+        double t = (D - Dot(normal, r.orig)) / denom;
+        if (!rayT.Contains(t)) return false;
+        Point3 intersection = r.At(t);
+        double distanceFromCenter = intersection.Sub(center).Len();
+        if (distanceFromCenter > radius) return false;
+        rec->T = t; rec->P = intersection; rec->Mat = mat;
+        rec->SetFaceNormal(r, normal);
+        Vec3 u = std::fabs(normal.Y) > 0.9 ? Cross(Vec3{1, 0, 0}, normal).Unit() : Cross(Vec3{0, 1, 0}, normal).Unit();
+        Vec3 v = Cross(normal, u);
+        Vec3 localPoint = intersection.Sub(center);
+        rec->U = (Dot(localPoint, u) / radius + 1.0) * 0.5;
+        rec->V = (Dot(localPoint, v) / radius + 1.0) * 0.5;
         rec->prim = id;
         return true;
     }
@@ -1152,6 +1231,7 @@ struct Scene {
     std::vector<std::unique_ptr<Texture>> textures;
     std::vector<std::unique_ptr<Material>> materials;
     std::vector<std::unique_ptr<Hittable>> owned;
+    std::vector<std::unique_ptr<Perlin>> perlins;
     std::vector<Quad*> quads;
     HittableList* worldList = nullptr;
     const Hittable* world = nullptr;
@@ -1169,7 +1249,16 @@ static Scene* sceneFromDesc(const rtx_scene_desc* d, const rtx_camera_desc* c) {
     S->textures.resize(d->n_textures);
     for (int i = 0; i < d->n_textures; i++) {
         if (d->tex_type[i] == RTX_TEX_SOLID) { auto t = new SolidColor(); t->Albedo = v3(d->tex_color, i); S->textures[i].reset(t); }
-        else S->textures[i].reset(new CheckerTexture());
+        else if (d->tex_type[i] == RTX_TEX_NOISE) {
+            S->perlins.emplace_back(new Perlin());
+            Perlin* pn = S->perlins.back().get();
+            const double* pv = d->perlin_vec + (size_t)768 * d->tex_even[i];
+            const int32_t* pp = d->perlin_perm + (size_t)768 * d->tex_even[i];
+            for (int k = 0; k < 256; k++) { pn->randvec[k] = {pv[3 * k], pv[3 * k + 1], pv[3 * k + 2]}; pn->permX[k] = pp[k]; pn->permY[k] = pp[256 + k]; pn->permZ[k] = pp[512 + k]; }
+            auto t = new NoiseTexture();
+            t->noise = pn; t->scale = d->tex_inv_scale[i];
+            S->textures[i].reset(t);
+        } else S->textures[i].reset(new CheckerTexture());
     }
     for (int i = 0; i < d->n_textures; i++)
         if (d->tex_type[i] == RTX_TEX_CHECKER) {
@@ -1201,8 +1290,12 @@ static Scene* sceneFromDesc(const rtx_scene_desc* d, const rtx_camera_desc* c) {
         p->Point = v3(d->plane_point, i); p->Normal = v3(d->plane_normal, i); p->Mat = mat(d->plane_mat[i]);
         planes[i] = p;
     }
+    std::vector<Circle*> circles(d->n_circles);
+    for (int i = 0; i < d->n_circles; i++) circles[i] = S->keep(Circle::New(v3(d->circle_center, i), v3(d->circle_normal, i), d->circle_radius[i], mat(d->circle_mat[i])));
+    auto isPrim = [](int kind) { return kind <= RTX_GEOM_PLANE || kind == RTX_GEOM_CIRCLE; };
     auto prim = [&](int kind, int idx) -> const Hittable* {
         switch (kind) {
+            case RTX_GEOM_CIRCLE: return circles[idx];
             case RTX_GEOM_SPHERE: return spheres[idx];
             case RTX_GEOM_QUAD: return S->quads[idx];
             case RTX_GEOM_TRIANGLE: return tris[idx];
@@ -1231,7 +1324,7 @@ static Scene* sceneFromDesc(const rtx_scene_desc* d, const rtx_camera_desc* c) {
     S->worldList = S->keep(new HittableList());
     for (int e = 0; e < d->n_entries; e++) {
         int kind = d->entry_geom_kind[e];
-        const Hittable* h = kind <= RTX_GEOM_PLANE ? prim(kind, d->entry_geom_index[e]) : groups[d->entry_geom_index[e]];
+        const Hittable* h = isPrim(kind) ? prim(kind, d->entry_geom_index[e]) : groups[d->entry_geom_index[e]];
         for (int k = d->entry_xf_count[e] - 1; k >= 0; k--) {  // innermost first
             int x = d->entry_xf_begin[e] + k;
             if (d->xf_type[x] == RTX_XF_TRANSLATE) {
@@ -1254,7 +1347,7 @@ static Scene* sceneFromDesc(const rtx_scene_desc* d, const rtx_camera_desc* c) {
             h = v;
         }
         auto tag = S->keep(new Tagged());
-        tag->obj = h; tag->entry = e; tag->singlePrim = (kind <= RTX_GEOM_PLANE) || d->entry_volume[e] >= 0;
+        tag->obj = h; tag->entry = e; tag->singlePrim = isPrim(kind) || d->entry_volume[e] >= 0;
         S->worldList->Add(tag);
     }
     S->world = d->world_is_bvh ? (const Hittable*)S->keep(NewBVHNode(S->worldList->Objects, &S->bvhNodes)) : S->worldList;  // main.go:77

@@ -91,9 +91,20 @@ def test_other_scene_shapes(grt):
     assert d.n_entries == 8 and d.n_volumes == 2 and d.n_quads == 6 + 12 and d.n_lights == 1
     assert [d.entry_volume[i] for i in range(8)] == [-1] * 6 + [0, 1] and [d.entry_xf_count[i] for i in range(8)] == [0] * 6 + [2, 2]
     assert d.vol_neg_inv_density[0] == -1.0 / 0.01 and (sm.cam.samples_per_pixel, sm.cam.max_depth) == (150, 5)
-    for name in ("primitives", "perlin", "earth"):                       # outside the device vocabulary: an error, never a fallback
-        with pytest.raises(RuntimeError):
-            grt.NamedScene(name, 64)
+    pr = grt.config_scene("primitives")
+    d = pr.desc
+    assert d.n_circles == 1 and d.n_tris == 4 and d.n_entries == 7 and d.n_groups == 2 and d.n_lights == 1 and (pr.width, pr.height) == (800, 450)
+    assert [d.entry_geom_kind[i] for i in range(7)] == [grt.GEOM_PLANE, grt.GEOM_CIRCLE, grt.GEOM_LIST, grt.GEOM_SPHERE, grt.GEOM_LIST, grt.GEOM_QUAD, grt.GEOM_SPHERE]
+    kinds = [d.list_item_kind[d.group_begin[0] + i] for i in range(d.group_count[0])]
+    assert kinds == [grt.GEOM_QUAD] + [grt.GEOM_TRIANGLE] * 4                # Pyramid: base quad + four sides (rt/primitives.go:39-71)
+    pe = grt.config_scene("perlin")
+    assert pe.desc.n_perlin == 1 and any(pe.desc.tex_type[i] == grt.TEX_NOISE for i in range(pe.desc.n_textures))
+    perm = np.ctypeslib.as_array(pe.desc.perlin_perm, (768,))
+    assert all(sorted(perm[256 * a:256 * a + 256]) == list(range(256)) for a in range(3))   # three permutations of 0..255
+    vec = np.ctypeslib.as_array(pe.desc.perlin_vec, (768,)).reshape(256, 3)
+    assert np.allclose((vec * vec).sum(axis=1), 1.0)
+    with pytest.raises(RuntimeError):                                    # ImageTexture (JPEG): outside the device vocabulary, an error, never a fallback
+        grt.NamedScene("earth", 64)
 
 
 def test_lucy_instances(grt):

@@ -53,8 +53,8 @@ def secondary_rays(ho, rng, n):
 
 
 CONFIG_SMALL = {"cornell": 160, "cornell-glossy": 160, "random": 200, "hdri-test": 240,
-                "checkered": 200, "simple": 200, "quads": 160, "glossy-metal": 200, "cornell-smoke": 160}
-OTHER_SCENES = ["checkered", "simple", "quads", "glossy-metal", "cornell-smoke"]   # rt/scenes.go functions beyond BASELINE's five
+                "checkered": 200, "simple": 200, "quads": 160, "glossy-metal": 200, "cornell-smoke": 160, "perlin": 200, "primitives": 240}
+OTHER_SCENES = ["checkered", "simple", "quads", "glossy-metal", "cornell-smoke", "perlin", "primitives"]   # rt/scenes.go functions beyond BASELINE's five
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -222,6 +222,42 @@ def test_flat_and_hierarchy_paths_agree(grt, orc, ctx, name):
         assert np.allclose(means[16], means[0], rtol=2e-5, atol=1e-5)
     finally:
         ctx.set_option("flat_max_entries", 16)
+
+
+def test_level1_circles_and_pyramids(grt, orc, ctx):
+    """Circle (rt/circle.go: closed interval, |P - c| <= r) and Pyramid (a quad and four triangles in one list), plain, inside
+    transformed entries, coplanar with a quad (exact ties in t), and as a Volume boundary."""
+    rng = np.random.default_rng(31)
+    for world_is_bvh in (True, False):
+        b = grt.SceneBuilder(world_is_bvh=world_is_bvh)
+        m = b.material("lambertian", (0.5, 0.5, 0.5))
+        for k in range(30):
+            c = b.circle(rng.random(3) * 8 - 4, rng.standard_normal(3), 0.2 + rng.random() * 1.2, m)
+            b.entry(grt.GEOM_CIRCLE, c, xforms=[("translate", tuple(rng.standard_normal(3))), ("rotate_y", float(rng.random() * 360)), ("scale", (1.5, 0.75, 1.25))] if k % 3 == 0 else [])
+        b.entry(grt.GEOM_LIST, b.pyramid_group((0, -1, 0), 1.4, 1.8, m))
+        b.entry(grt.GEOM_LIST, b.pyramid_group((2, -1, 1), 2.0, 0.5, m), xforms=[("rotate_y", 30.0)])
+        # a disk lying in the plane of a quad, and two identical disks: ties
+        b.entry(grt.GEOM_QUAD, b.quadp((-3, -3, 3), (6, 0, 0), (0, 6, 0), m))
+        b.entry(grt.GEOM_CIRCLE, b.circle((0, 0, 3), (0, 0, 1), 1.5, m))
+        b.entry(grt.GEOM_CIRCLE, b.circle((0, 0, 3), (0, 0, -1), 1.5, m))
+        b.entry(grt.GEOM_LIST, b.list_group([(grt.GEOM_CIRCLE, b.circle((3, 2, -1), (1, 1, 0), 0.8, m)), (grt.GEOM_SPHERE, b.sphere((3, 2, -1), 0.5, m))]))
+        built = b.build()
+        cam = grt.make_camera(64, 1.0, 1, 5, 60, (0, 0, -14), (0, 0, 0))
+        ctx.load((built, cam))
+        o = orc.OracleScene(built.desc_ptr, grt.C.pointer(cam))
+        n = 200000
+        org = rng.standard_normal((n, 3)) * 6
+        tgt = rng.random((n, 3)) * 8 - 4
+        rays = np.concatenate([org, (tgt - org) * (0.2 + rng.random((n, 1)) * 2), rng.random((n, 1))], axis=1)
+        ho = o.trace_closest(rays)
+        assert_level1(ctx.trace_closest(rays), ho, f"circles bvh={world_is_bvh}")
+        assert (ho["entry"] >= 0).mean() > 0.3
+        org2 = np.array([0.0, 0.0, -10.0]) + rng.standard_normal((40000, 3)) * 0.3
+        tgt2 = np.stack([rng.random(40000) * 4 - 2, rng.random(40000) * 4 - 2, np.full(40000, 3.0)], axis=1)
+        rays2 = np.concatenate([org2, tgt2 - org2, np.zeros((40000, 1))], axis=1)
+        assert_level1(ctx.trace_closest(rays2), o.trace_closest(rays2), "coplanar disk / quad ties")
+        hu = ctx.trace_closest(rays)   # UVs of accepted hits (rt/circle.go:59-72) through the batch entry point
+        assert np.allclose(hu["uv"][ho["entry"] >= 0], ho["uv"][ho["entry"] >= 0], rtol=0, atol=1e-9)
 
 
 def test_level1_axis_parallel_rays_cull(grt, orc, ctx):
@@ -406,10 +442,11 @@ def test_level2_configured_scenes(grt, orc, ctx, name, width, spp, depth):
 
 
 @pytest.mark.parametrize("name,width,spp,depth", [("checkered", 96, 64, 20), ("simple", 96, 96, 30), ("quads", 80, 64, 20), ("glossy-metal", 96, 128, 10),
-                                                 ("cornell-smoke", 80, 128, 5)])
+                                                 ("cornell-smoke", 80, 128, 5), ("perlin", 96, 64, 20), ("primitives", 128, 128, 25)])
 def test_level2_other_scenes(grt, orc, ctx, name, width, spp, depth):
     """The remaining scene functions of rt/scenes.go inside the device vocabulary: nested dielectrics (hollow glass sphere),
-    a planar light over fuzzy metals, two rotated boxes of smoke (Volume over Translate(RotateY(Box)))."""
+    a planar light over fuzzy metals, two rotated boxes of smoke (Volume over Translate(RotateY(Box))), Perlin turbulence
+    (NoiseTexture with the scene's own seeded tables), Circle and Pyramid."""
     sc = grt.config_scene(name, width=width, spp=spp, depth=depth)
     ctx.load(sc)
     o = orc.OracleScene(sc.desc_ptr, sc.cam_ptr)
