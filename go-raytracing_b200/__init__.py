@@ -24,7 +24,7 @@ HOST_LIB_PATH = os.path.join(_HERE, "csrc", "librt_host.so")
 
 RTX_ABI_VERSION = 2
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_DIFFUSE_LIGHT, MAT_ISOTROPIC = range(5)
-TEX_SOLID, TEX_CHECKER, TEX_NOISE = 0, 1, 2
+TEX_SOLID, TEX_CHECKER, TEX_NOISE, TEX_IMAGE = 0, 1, 2, 3
 GEOM_SPHERE, GEOM_QUAD, GEOM_TRIANGLE, GEOM_PLANE, GEOM_LIST, GEOM_MESH, GEOM_CIRCLE = range(7)
 XF_TRANSLATE, XF_ROTATE_Y, XF_SCALE = 0, 1, 2
 
@@ -53,6 +53,7 @@ class SceneDesc(C.Structure):
         ("env_importance_sampling", C.c_int32),
         ("n_circles", C.c_int32), ("circle_center", _pd), ("circle_normal", _pd), ("circle_radius", _pd), ("circle_mat", _pi),
         ("n_perlin", C.c_int32), ("perlin_vec", _pd), ("perlin_perm", _pi),
+        ("n_images", C.c_int32), ("image_width", _pi), ("image_height", _pi), ("image_offset", C.POINTER(C.c_int64)), ("image_rgb", _pd),
     ]
 
 
@@ -188,6 +189,7 @@ class SceneBuilder:
         self.mat = []      # (type, tex, albedo, fuzz, ior)
         self.sph, self.quad, self.tri, self.plane, self.circ = [], [], [], [], []
         self.perlin = []   # (vec[256][3], perm[3][256])
+        self.images = []   # float64 [H][W][3], ImageLoader.data (after the reference's sqrt on load)
         self.groups, self.items = [], []
         self.xf = []
         self.vol = []
@@ -221,6 +223,14 @@ class SceneBuilder:
         self.tex.append((TEX_NOISE, (0, 0, 0), float(scale), len(self.perlin) - 1, -1))
         return len(self.tex) - 1
 
+    def image(self, rgb8):
+        """ImageTexture over an 8-bit RGB image [H][W][3]: ImageLoader.Load converts to sqrt(v / 255) (rt/image_loader.go:62-70)."""
+        a = np.asarray(rgb8)
+        assert a.ndim == 3 and a.shape[2] == 3
+        self.images.append(np.ascontiguousarray(np.sqrt(a.astype(np.float64) / 255.0)))
+        self.tex.append((TEX_IMAGE, (0, 0, 0), 0.0, len(self.images) - 1, -1))
+        return len(self.tex) - 1
+
     def material(self, kind, *args):
         if kind == "lambertian":
             tex = args[0] if isinstance(args[0], int) else self.solid(args[0])
@@ -230,7 +240,7 @@ class SceneBuilder:
         elif kind == "dielectric":
             self.mat.append((MAT_DIELECTRIC, -1, (0, 0, 0), 0.0, float(args[0])))
         elif kind == "light":
-            self.mat.append((MAT_DIFFUSE_LIGHT, self.solid(args[0]), (0, 0, 0), 0.0, 0.0))
+            self.mat.append((MAT_DIFFUSE_LIGHT, args[0] if isinstance(args[0], int) else self.solid(args[0]), (0, 0, 0), 0.0, 0.0))
         elif kind == "isotropic":
             self.mat.append((MAT_ISOTROPIC, self.solid(args[0]), (0, 0, 0), 0.0, 0.0))
         else:
@@ -408,6 +418,13 @@ class BuiltScene:
         d.n_perlin = len(b.perlin)
         d.perlin_vec = P("perlin_vec", [pv[0] for pv in b.perlin], np.float64)
         d.perlin_perm = P("perlin_perm", [pv[1] for pv in b.perlin], np.int32)
+        d.n_images = len(b.images)
+        d.image_width = P("img_w", [im.shape[1] for im in b.images], np.int32)
+        d.image_height = P("img_h", [im.shape[0] for im in b.images], np.int32)
+        offs = np.cumsum([0] + [im.shape[0] * im.shape[1] for im in b.images])[:-1] if b.images else np.zeros(0)
+        k["img_off"] = np.ascontiguousarray(np.asarray(offs if len(offs) else [0], dtype=np.int64))
+        d.image_offset = k["img_off"].ctypes.data_as(C.POINTER(C.c_int64))
+        d.image_rgb = P("img_rgb", np.concatenate([im.reshape(-1) for im in b.images]) if b.images else [], np.float64)
         if b.env is not None:
             rgb, rot, is_ = b.env
             k["env"] = rgb
@@ -639,6 +656,7 @@ CONFIGS.update({
     "glossy-metal": dict(scene="glossy-metal", width=640, aspect=16.0 / 9.0, spp=100, depth=10),
     "cornell-smoke": dict(scene="cornell-smoke", width=600, aspect=1.0, spp=150, depth=5),
     "perlin": dict(scene="perlin", width=600, aspect=16.0 / 9.0, spp=100, depth=50),
+    "earth": dict(scene="earth", width=800, aspect=16.0 / 9.0, spp=100, depth=50),
     "primitives": dict(scene="primitives", width=800, aspect=16.0 / 9.0, spp=300, depth=25),
 })
 

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -181,8 +182,8 @@ int32_t rtx_create(int32_t device_id, rtx_ctx** out) {
     {   // persistent trace kernels: opt in to the large dynamic shared-memory pool, size the grid to one resident wave
         const int smem = (int)RTX_TRACE_SMEM_BYTES;
         int occ = 0, minOcc = 1 << 30;
-        const void* kernels[5] = {(const void*)k_extend<false>, (const void*)k_extend<true>, (const void*)k_connect<false>, (const void*)k_connect<true>,
-                                  (const void*)k_trace_closest};
+        const void* kernels[6] = {(const void*)k_extend<false>, (const void*)k_extend<true>, (const void*)k_extend<false, true>, (const void*)k_connect<false>,
+                                  (const void*)k_connect<true>, (const void*)k_trace_closest};
         // developer knob: shared-memory carve-out in KB (the rest of the 256 KB array is L1); fewer resident blocks, more L1
         const char* carveEnv = getenv("RTX_TRACE_CARVEOUT_KB");
         const int carveKB = carveEnv ? atoi(carveEnv) : 0;
@@ -342,6 +343,10 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
             if (d->tex_even[i] < 0 || d->tex_even[i] >= d->n_textures || d->tex_odd[i] < 0 || d->tex_odd[i] >= d->n_textures) return bad("checker child out of range");
         } else if (d->tex_type[i] == RTX_TEX_NOISE) {
             if (d->tex_even[i] < 0 || d->tex_even[i] >= d->n_perlin || !d->perlin_vec || !d->perlin_perm) return bad("noise texture without a Perlin table");
+        } else if (d->tex_type[i] == RTX_TEX_IMAGE) {
+            const int im = d->tex_even[i];
+            if (im < 0 || im >= d->n_images || !d->image_rgb || !d->image_width || !d->image_height || !d->image_offset || d->image_width[im] <= 0 || d->image_height[im] <= 0)
+                return bad("image texture without image data");
         } else if (d->tex_type[i] != RTX_TEX_SOLID) return fail(ctx, RTX_ERR_UNSUPPORTED, "texture type %d is outside the device path", d->tex_type[i]);
     }
     for (int i = 0; i < d->n_materials; i++) {
@@ -349,6 +354,19 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
         if (t < RTX_MAT_LAMBERTIAN || t > RTX_MAT_ISOTROPIC) return fail(ctx, RTX_ERR_UNSUPPORTED, "material type %d is outside the device path", t);
         if ((t == RTX_MAT_LAMBERTIAN || t == RTX_MAT_DIFFUSE_LIGHT || t == RTX_MAT_ISOTROPIC) && (d->mat_tex[i] < 0 || d->mat_tex[i] >= d->n_textures))
             return bad("material texture out of range");
+    }
+    {   // Plane.Hit does not write rec.U / rec.V (rt/plane.go:24-42): an image texture there would read whatever an earlier,
+        // farther hit of the same query left in the record — order-dependent in the reference, so it stays outside the device path
+        std::function<bool(int, int)> hasImage = [&](int t, int depth) {
+            if (t < 0 || t >= d->n_textures || depth > 8) return false;
+            if (d->tex_type[t] == RTX_TEX_IMAGE) return true;
+            return d->tex_type[t] == RTX_TEX_CHECKER && (hasImage(d->tex_even[t], depth + 1) || hasImage(d->tex_odd[t], depth + 1));
+        };
+        for (int i = 0; i < d->n_planes; i++) {
+            const int m = d->plane_mat[i];
+            if (m >= 0 && m < d->n_materials && hasImage(d->mat_tex[m], 0))
+                return fail(ctx, RTX_ERR_UNSUPPORTED, "plane %d: an ImageTexture on a Plane is outside the device path (Plane.Hit leaves U/V unwritten)", i);
+        }
     }
     auto matok = [&](const int32_t* m, int n) { for (int i = 0; i < n; i++) if (m[i] < 0 || m[i] >= d->n_materials) return false; return true; };
     if (!matok(d->sph_mat, d->n_spheres) || !matok(d->quad_mat, d->n_quads) || !matok(d->tri_mat, d->n_tris) || !matok(d->plane_mat, d->n_planes) || !matok(d->circle_mat, d->n_circles) ||
@@ -433,6 +451,15 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     }
     std::vector<double> perlinVec(d->n_perlin > 0 ? d->perlin_vec : nullptr, d->n_perlin > 0 ? d->perlin_vec + (size_t)768 * d->n_perlin : nullptr);
     std::vector<int> perlinPerm(d->n_perlin > 0 ? d->perlin_perm : nullptr, d->n_perlin > 0 ? d->perlin_perm + (size_t)768 * d->n_perlin : nullptr);
+
+    std::vector<float4> imgRgb;
+    std::vector<int4> imgDim(d->n_images);
+    for (int i = 0; i < d->n_images; i++) {
+        const size_t first = imgRgb.size(), npx = (size_t)d->image_width[i] * d->image_height[i];
+        const double* src = d->image_rgb + 3 * (size_t)d->image_offset[i];
+        imgDim[i] = make_int4(d->image_width[i], d->image_height[i], (int)(first & 0xffffffffu), (int)(first >> 32));
+        for (size_t k = 0; k < npx; k++) imgRgb.push_back(make_float4((float)src[3 * k], (float)src[3 * k + 1], (float)src[3 * k + 2], 0.f));
+    }
 
     // ---- triangles: meshes are permuted into BLAS leaf order; loose triangles (world entries / Box-list items) follow
     std::vector<Node4> nodes;                       // host-built nodes: every BLAS with the host builder, and always the TLAS
@@ -722,6 +749,7 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
         const size_t geom = std::max<size_t>(bNodes + bTris + bSph + bQuads, 256);
         WANT(entries, S.entries); WANT(unbounded, S.unbounded); WANT(sphMat, S.sph_mat); WANT(quadMat, S.quad_mat); WANT(planes, S.planes); WANT(planeMat, S.plane_mat);
         WANT(circles, S.circles); WANT(circleMat, S.circle_mat); WANT(perlinVec, S.perlin_vec); WANT(perlinPerm, S.perlin_perm);
+        WANT(imgRgb, S.img_rgb); WANT(imgDim, S.img_dim);
         WANT(listItems, S.list_items); WANT(xfs, S.xforms); WANT(xfCanon, S.xf_canon); WANT(vols, S.volumes); WANT(mats, S.mats); WANT(texs, S.texs);
         WANT(lights, S.light_quads); WANT(envTex, S.env_tex); WANT(marg, S.env_marg); WANT(cond, S.env_cond); WANT(pdf, S.env_pdf);
 #undef WANT
@@ -770,6 +798,7 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     S.n_entries = d->n_entries;
     S.n_unbounded = (int)unbounded.size();
     S.n_lights = d->n_lights;
+    S.n_images = d->n_images;
     S.vol_draws = d->world_is_bvh ? 2 : 1;
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->ms_upload_blas = 0;
@@ -1000,7 +1029,10 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
             if (timing) cudaEventRecord(ev[0], st);
             k_generate<<<gridStream, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->C, pp);
             if (timing) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
-            if (ctx->scene_flat) {
+            if (ctx->S.n_images > 0) {   // hit records carry (u, v); this variant is not instrumented
+                if (ctx->scene_flat) k_extend_flat<false, true><<<gridStream, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, pp);
+                else k_extend<false, true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
+            } else if (ctx->scene_flat) {
                 if (ctx->count_stats & 1) k_extend_flat<true><<<gridStream, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, pp);
                 else k_extend_flat<false><<<gridStream, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, pp);
             } else if (ctx->count_stats & 1) k_extend<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);

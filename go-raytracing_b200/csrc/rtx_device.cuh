@@ -87,6 +87,9 @@ struct DevScene {
     const int* circle_mat;
     const double* perlin_vec;  // [n][256][3] (rt/noise.go:9)
     const int* perlin_perm;    // [n][3][256]
+    const float4* img_rgb;     // ImageLoader.data of every image, back to back
+    const int4* img_dim;       // (width, height, first pixel lo, first pixel hi)
+    int n_images;              // > 0: hit records carry (u, v)
     const int2* list_items;  // (kind, device index)
     const DXform* xforms;
     const double* xf_canon;  // 8 doubles per entry: offset xyz, sin, cos, inverse scale xyz (identity values where an op is absent)

@@ -203,7 +203,8 @@ extern __shared__ __align__(16) unsigned char rtx_smem[];  // the trace kernels'
 #define RTX_TRACE_SMEM_BYTES ((size_t)RTX_TRACE_SLOTS * RTX_SLOT_WORDS * 4 + RTX_POOL_EXTRA_BYTES)
 
 // ---- K2: extend — closest hit of every active path, then binning into material-sorted shading queues -------------
-struct ExtendPolicy {
+template <bool UV>
+struct ExtendPolicyT {
     static constexpr bool ANY_HIT = false;
     Ctl* ctl; char* hit; int* q_mat; int capacity; const char* rec; const DevScene* S; uint32_t seed_lo, seed_hi;
     __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:451
@@ -227,10 +228,12 @@ struct ExtendPolicy {
                 q = Q_MISS;
             } else {
                 HitInfo hi;
-                finalize_hit(*S, r, best_to_hit(b), false, hi);
+                finalize_hit(*S, r, best_to_hit(b), UV, hi);
                 const long long bits = (long long)(unsigned)hi.mat | (hi.front ? (1LL << 31) : 0);
                 char* h = hit + (size_t)job * RTX_HIT_BYTES;
-                st256d(h, hi.P.x, hi.P.y, hi.P.z, b.t);
+                // the fourth word: t, or — in scenes with image textures — the hit's (u, v) as two float32 (texel lookup only)
+                const double w4 = UV ? __longlong_as_double(((long long)__float_as_uint((float)hi.v) << 32) | (long long)__float_as_uint((float)hi.u)) : b.t;
+                st256d(h, hi.P.x, hi.P.y, hi.P.z, w4);
                 st256d(h + 32, hi.N.x, hi.N.y, hi.N.z, __longlong_as_double(bits));
                 const int mt = S->mats[hi.mat].type;
                 q = mt == RTX_MAT_LAMBERTIAN ? Q_LAMBERTIAN : mt == RTX_MAT_METAL ? Q_METAL : mt == RTX_MAT_DIELECTRIC ? Q_DIELECTRIC
@@ -245,28 +248,31 @@ struct ExtendPolicy {
         }
     }
 };
+typedef ExtendPolicyT<false> ExtendPolicy;
 
-template <bool COUNT>
+// UV = true: the variant for scenes with image textures (hit records carry (u, v); sphere UVs cost an acos and an atan2 per hit)
+template <bool COUNT, bool UV = false>
 __global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_extend(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, PassParams pp, int* spill) {
-    ExtendPolicy P{ctl, pool.hit, pool.q_mat, pool.capacity, pool.records(cur), &S, pp.seed_lo, pp.seed_hi};
+    ExtendPolicyT<UV> P{ctl, pool.hit, pool.q_mat, pool.capacity, pool.records(cur), &S, pp.seed_lo, pp.seed_hi};
     TraceCounters tc = {0, 0, 0, 0, 0};
     const int n = ctl->n_active;
-    trace_persistent<ExtendPolicy, COUNT, RTX_TRACE_SLOTS>(S, P, &ctl->cur_extend, n, tc, spill, rtx_smem);
+    trace_persistent<ExtendPolicyT<UV>, COUNT, RTX_TRACE_SLOTS>(S, P, &ctl->cur_extend, n, tc, spill, rtx_smem);
     if (COUNT) flush_counters(ctl, tc);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->ext_rays, (unsigned long long)n);
 }
 
-template <bool COUNT>
+template <bool COUNT, bool UV = false>
 __global__ void __launch_bounds__(256) k_extend_flat(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, PassParams pp) {
-    ExtendPolicy P{ctl, pool.hit, pool.q_mat, pool.capacity, pool.records(cur), &S, pp.seed_lo, pp.seed_hi};
+    ExtendPolicyT<UV> P{ctl, pool.hit, pool.q_mat, pool.capacity, pool.records(cur), &S, pp.seed_lo, pp.seed_hi};
     TraceCounters tc = {0, 0, 0, 0, 0};
     const int n = ctl->n_active;
-    trace_flat<ExtendPolicy, COUNT>(S, P, n, tc);
+    trace_flat<ExtendPolicyT<UV>, COUNT>(S, P, n, tc);
     if (COUNT) flush_counters(ctl, tc);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->ext_rays, (unsigned long long)n);
 }
 
 // ---- textures (rt/texture.go:43-45, :63-77) ----------------------------------------------------------------------
+__device__ __forceinline__ int clampi_img(int x, int high) { return x < 0 ? 0 : (x < high ? x : high - 1); }  // rt/image_loader.go:112-120
 // Perlin noise with the caller's tables (rt/noise.go:30-92), float64, reference operation order
 __device__ __noinline__ double perlin_noise(const double* vec, const int* perm, double px, double py, double pz) {
     const double fx = floor(px), fy = floor(py), fz = floor(pz);
@@ -284,7 +290,7 @@ __device__ __noinline__ double perlin_noise(const double* vec, const int* perm, 
             }
     return accum;
 }
-__device__ __forceinline__ float3 tex_value(const DevScene& S, int id, D3 p) {
+__device__ __forceinline__ float3 tex_value(const DevScene& S, int id, D3 p, float u = 0.f, float v = 0.f) {
     DTexture t = S.texs[id];
     for (int guard = 0; guard < 8 && t.type == RTX_TEX_CHECKER; guard++) {
         long long xi = (long long)floor(t.inv_scale * p.x + 1e-4);
@@ -305,6 +311,15 @@ __device__ __forceinline__ float3 tex_value(const DevScene& S, int id, D3 p) {
         }
         const float tv = (float)(0.5 * (1.0 + sin(sc * p.z + 10.0 * fabs(accum))));
         return make_float3(tv, tv, tv);
+    }
+    if (t.type == RTX_TEX_IMAGE) {  // ImageTexture.Value rt/image_texture.go:27-43 + ImageLoader.PixelData rt/image_loader.go:97-120
+        const int4 dim = S.img_dim[t.even];
+        const double uu = u < 0.f ? 0.0 : (u > 1.f ? 1.0 : (double)u);
+        const double vv = 1.0 - (v < 0.f ? 0.0 : (v > 1.f ? 1.0 : (double)v));   // flip V to image coordinates
+        const int i = clampi_img((int)(uu * (double)dim.x), dim.x), j = clampi_img((int)(vv * (double)dim.y), dim.y);
+        const size_t first = ((size_t)(unsigned)dim.w << 32) | (unsigned)dim.z;
+        const float4 c = __ldg(S.img_rgb + first + (size_t)j * dim.x + i);
+        return make_float3(c.x, c.y, c.z);
     }
     return make_float3(t.color[0], t.color[1], t.color[2]);
 }
@@ -442,13 +457,15 @@ __global__ void __launch_bounds__(256, RTX_SHADE_BLOCKS) k_shade(Ctl* ctl, Pool 
             const D4 hp = ld256d(hrec), hn = ld256d(hrec + 32);
             P = d3(hp.x, hp.y, hp.z);
             D3 N = d3(hn.x, hn.y, hn.z);
+            float hu = 0.f, hv = 0.f;   // rec.U, rec.V: carried only in scenes with image textures
+            if (S.n_images > 0) { const long long uvb = __double_as_longlong(hp.w); hu = __uint_as_float((unsigned)uvb); hv = __uint_as_float((unsigned)(uvb >> 32)); }
             long long bits = __double_as_longlong(hn.w);
             int mat = (int)(bits & 0x7fffffff);
             bool front = (bits >> 31) & 1;
             DMaterial M = S.mats[mat];
             if (type == Q_LIGHT) {  // Scatter == false: rt/camera.go:473-481, rt/material.go:226-236
                 if (allow) {
-                    float3 e = tex_value(S, M.tex, P);
+                    float3 e = tex_value(S, M.tex, P, hu, hv);
                     pool.contribute(ps.x, ps.y, th.x * e.x, th.y * e.y, th.z * e.z);
                 }
             } else {
@@ -458,7 +475,7 @@ __global__ void __launch_bounds__(256, RTX_SHADE_BLOCKS) k_shade(Ctl* ctl, Pool 
                 if (type == Q_LAMBERTIAN) {  // rt/material.go:57-68
                     nd = add(N, unit_sphere(rs.x, rs.y));
                     if (fabs(nd.x) < 1e-8 && fabs(nd.y) < 1e-8 && fabs(nd.z) < 1e-8) nd = N;
-                    att = tex_value(S, M.tex, P);
+                    att = tex_value(S, M.tex, P, hu, hv);
                     if (S.n_lights > 0) {  // useMIS, rt/camera.go:487-517
                         const double PI = 3.14159265358979323846;
                         uint4 rn = philox4x32(ps.x, ps.y, (uint32_t)bounce, STREAM_NEE, pp.seed_lo, pp.seed_hi);
@@ -534,7 +551,7 @@ __global__ void __launch_bounds__(256, RTX_SHADE_BLOCKS) k_shade(Ctl* ctl, Pool 
                     }
                 } else {  // Q_ISOTROPIC rt/material.go:266-270
                     nd = unit_sphere(rs.x, rs.y);
-                    att = tex_value(S, M.tex, P);
+                    att = tex_value(S, M.tex, P, hu, hv);
                 }
                 if (!scattered) {
                     has_env = has_area = false;  // absorbed: emission of a scattering material is zero

@@ -58,6 +58,49 @@ Vec3 AABB::Centroid() const { return {(X.Min + X.Max) * 0.5, (Y.Min + Y.Max) * 0
 
 // ---- textures / materials --------------------------------------------------------------------------------
 TexturePtr NewSolidColor(Color albedo) { return std::make_shared<SolidColor>(albedo); }
+bool ImageLoader::Load(const std::string& filename) {  // rt/image_loader.go:44-73 (decode -> LinearToGamma(v / 65535 * 257) = sqrt(v8 / 255))
+    FILE* f = std::fopen(filename.c_str(), "rb");
+    if (!f) return false;
+    char magic[3] = {0, 0, 0};
+    int w = 0, h = 0, maxv = 0;
+    auto token = [&](int& out) {   // next integer, skipping whitespace and # comments
+        int c = std::fgetc(f);
+        while (c == ' ' || c == '\n' || c == '\r' || c == '\t' || c == '#') {
+            if (c == '#') while (c != '\n' && c != EOF) c = std::fgetc(f);
+            else c = std::fgetc(f);
+        }
+        if (c < '0' || c > '9') return false;
+        out = 0;
+        while (c >= '0' && c <= '9') { out = out * 10 + (c - '0'); c = std::fgetc(f); }
+        return true;   // the single whitespace after the token is consumed
+    };
+    bool ok = std::fread(magic, 1, 2, f) == 2 && magic[0] == 'P' && magic[1] == '6' && token(w) && token(h) && token(maxv) && w > 0 && h > 0 && maxv == 255;
+    std::vector<unsigned char> raw;
+    if (ok) {
+        raw.resize((size_t)3 * w * h);
+        ok = std::fread(raw.data(), 1, raw.size(), f) == raw.size();
+    }
+    std::fclose(f);
+    if (!ok) return false;
+    imageWidth = w; imageHeight = h;
+    data.resize(raw.size());
+    for (size_t i = 0; i < raw.size(); i++) {
+        double lin = (double)raw[i] * 257.0 / 65535.0;   // Go's RGBA() of an 8-bit channel is v * 257; / 65535
+        data[i] = lin > 0 ? std::sqrt(lin) : 0.0;       // LinearToGamma (rt/utils.go:85-90)
+    }
+    return true;
+}
+TexturePtr NewImageTextureFromImage(std::shared_ptr<ImageLoader> image) {
+    auto t = std::make_shared<ImageTexture>();
+    t->image = image;
+    return t;
+}
+TexturePtr NewImageTexture(const std::string& filename) {  // rt/image_texture.go:11-15; a missing file leaves an empty image (debug colours in the reference)
+    auto img = std::make_shared<ImageLoader>();
+    std::string path = FindAsset(filename, "images");
+    if (!path.empty()) img->Load(path);
+    return NewImageTextureFromImage(img);
+}
 TexturePtr NewNoiseTexture(double scale, uint64_t seed) {  // rt/texture.go:24-29 + NewPerlin rt/noise.go:15-28 (same draw order, seeded SplitMix64)
     uint64_t st = seed;
     auto next = [&st]() {

@@ -91,6 +91,19 @@ struct NoiseTexture : Texture {  // rt/texture.go:19-29
     std::shared_ptr<Perlin> noise;
     double scale;
 };
+struct ImageLoader {  // rt/image_loader.go:14-120. The reference decodes any format Go's image package knows; without an image
+    // decoder in this toolchain, Load reads binary PPM (P6, 8 bit) — tools/make_assets.py converts the reference's earthmap.jpg
+    int imageWidth = 0, imageHeight = 0;
+    std::vector<double> data;  // 3 per pixel: LinearToGamma(v / 255) as ImageLoader.Load stores it (:62-70)
+    bool Load(const std::string& filename);
+    int Width() const { return data.empty() ? 0 : imageWidth; }
+    int Height() const { return data.empty() ? 0 : imageHeight; }
+};
+struct ImageTexture : Texture {  // rt/image_texture.go
+    std::shared_ptr<ImageLoader> image;
+};
+TexturePtr NewImageTexture(const std::string& filename);                          // resolved with FindAsset(filename, "images")
+TexturePtr NewImageTextureFromImage(std::shared_ptr<ImageLoader> image);
 TexturePtr NewNoiseTexture(double scale, uint64_t seed = 0x5EEDull);
 TexturePtr NewSolidColor(Color albedo);
 TexturePtr NewCheckerTexture(double scale, TexturePtr even, TexturePtr odd);
@@ -329,6 +342,7 @@ Scene HDRITestScene(const std::string& hdrPath);              // rt/scenes.go:40
 Scene CornellBoxScene();                                      // rt/scenes.go:463
 Scene CornellBoxGlossy();                                     // rt/scenes.go:606
 Scene CornellBoxLucy(const std::string& objPath);             // rt/scenes.go:714
+Scene EarthScene(const std::string& imagePath);                 // rt/scenes.go:210
 Scene PerlinSpheresScene(uint64_t seed = 0x5EEDull);           // rt/scenes.go:242
 Scene PrimitivesScene();                                       // rt/scenes.go:313
 Scene CheckeredSpheresScene();                                 // rt/scenes.go:132
@@ -356,6 +370,9 @@ struct FlatScene {
     std::vector<int32_t> circle_mat;
     std::vector<double> perlin_vec;
     std::vector<int32_t> perlin_perm;
+    std::vector<int32_t> image_width, image_height;
+    std::vector<int64_t> image_offset;
+    std::vector<double> image_rgb;
     std::vector<int32_t> group_kind, group_begin, group_count, list_item_kind, list_item_index;
     std::vector<int32_t> xf_type;
     std::vector<double> xf_a, xf_b;

@@ -41,7 +41,15 @@ struct Flattener {
                 for (int k = 0; k < 256; k++) fs.perlin_perm.push_back(nt->noise->permZ[k]);
                 perlinIds[nt->noise.get()] = even;
             } else even = pit->second;
-        } else throw std::runtime_error("flatten: unsupported Texture type (SolidColor, CheckerTexture and NoiseTexture are on the device path)");
+        } else if (auto it2 = dynamic_cast<const ImageTexture*>(t.get())) {
+            if (!it2->image || it2->image->Height() <= 0)
+                throw std::runtime_error("flatten: ImageTexture without image data (the reference would draw its cyan debug colour; load the image first)");
+            type = RTX_TEX_IMAGE;
+            even = (int)fs.image_width.size();
+            fs.image_width.push_back(it2->image->imageWidth); fs.image_height.push_back(it2->image->imageHeight);
+            fs.image_offset.push_back((int64_t)(fs.image_rgb.size() / 3));
+            fs.image_rgb.insert(fs.image_rgb.end(), it2->image->data.begin(), it2->image->data.end());
+        } else throw std::runtime_error("flatten: unsupported Texture type (SolidColor, CheckerTexture, NoiseTexture and ImageTexture are on the device path)");
         int id = (int)fs.tex_type.size();
         fs.tex_type.push_back(type); push3(fs.tex_color, c); fs.tex_inv_scale.push_back(inv);
         fs.tex_even.push_back(even); fs.tex_odd.push_back(odd);
@@ -249,6 +257,8 @@ rtx_scene_desc FlatScene::Desc() const {
     d.n_circles = (int)circle_mat.size(); d.circle_center = circle_center.data(); d.circle_normal = circle_normal.data();
     d.circle_radius = circle_radius.data(); d.circle_mat = circle_mat.data();
     d.n_perlin = (int)(perlin_perm.size() / 768); d.perlin_vec = perlin_vec.data(); d.perlin_perm = perlin_perm.data();
+    d.n_images = (int)image_width.size(); d.image_width = image_width.data(); d.image_height = image_height.data();
+    d.image_offset = image_offset.data(); d.image_rgb = image_rgb.data();
     d.n_groups = (int)group_kind.size(); d.group_kind = group_kind.data(); d.group_begin = group_begin.data(); d.group_count = group_count.data();
     d.n_list_items = (int)list_item_kind.size(); d.list_item_kind = list_item_kind.data(); d.list_item_index = list_item_index.data();
     d.n_xforms = (int)xf_type.size(); d.xf_type = xf_type.data(); d.xf_a = xf_a.data(); d.xf_b = xf_b.data();

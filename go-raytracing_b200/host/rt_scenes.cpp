@@ -1,6 +1,6 @@
 // rt_scenes.cpp — the five configured scenes of BASELINE.json and the other scene functions of rt/scenes.go whose vocabulary
 // the device path covers (CheckeredSpheres, Simple, PerlinSpheres, Quads, Primitives, GlossyMetalTest, CornellSmoke), mirrored
-// from the reference. EarthScene needs ImageTexture (JPEG decode) and stays outside.
+// from the reference. EarthScene reads a PPM conversion of the reference's earthmap.jpg (no JPEG decoder in this toolchain).
 // RandomScene draws from a seeded SplitMix64 stream in the reference's draw order (the reference uses
 // Go's auto-seeded global source, rt/utils.go:18, so its geometry differs run to run).
 #include <sys/stat.h>
@@ -181,6 +181,16 @@ Scene CornellBoxLucy(const std::string& objPath) {  // rt/scenes.go:714-817
 }
 
 // ---- the remaining scene functions the device vocabulary covers ------------------------------------------------
+Scene EarthScene(const std::string& imagePath) {  // rt/scenes.go:210-240
+    auto world = NewHittableList();
+    auto img = std::make_shared<ImageLoader>();
+    if (!img->Load(imagePath)) throw std::runtime_error("EarthScene: cannot load " + imagePath + " (binary PPM; tools/make_assets.py writes it from the reference's earthmap.jpg)");
+    world->Add(NewSphere({0, 0, 0}, 2, NewLambertianTexture(NewImageTextureFromImage(img))));
+    auto cam = NewCameraBuilder().SetResolution(800, 16.0 / 9.0).SetQuality(100, 50).SetPosition({0, 0, 12}, {0, 0, 0}, {0, 1, 0}).SetLens(20, 0, 10)
+                   .EnableSkyGradient(true).Build();
+    return {world, cam};
+}
+
 Scene PerlinSpheresScene(uint64_t seed) {  // rt/scenes.go:242-272 (the Perlin tables come from a seeded stream, see NewNoiseTexture)
     auto world = NewHittableList();
     auto perl = NewLambertianTexture(NewNoiseTexture(4.0, seed));
@@ -296,8 +306,10 @@ Scene LoadSceneByName(const std::string& nameIn, const std::string& assetRoot, u
     if (name == "glossy-metal" || name == "glossy-metal-test") return GlossyMetalTest();
     if (name == "perlin" || name == "perlin-spheres") return PerlinSpheresScene(seed);
     if (name == "primitives" || name == "primitives-scene") return PrimitivesScene();
-    if (name == "earth" || name == "earth-scene")
-        throw std::runtime_error("scene '" + nameIn + "' uses vocabulary outside the device path (ImageTexture): see DESIGN.md section 8");
+    if (name == "earth" || name == "earth-scene") {
+        std::string real = root + "/assets/images/earthmap.ppm", standin = root + "/assets/images/synthetic_earth.ppm";
+        return EarthScene(bigFile(real) ? real : standin);
+    }
     if (name == "cornell-lucy") {
         std::string real = root + "/assets/models/lucy_low.obj", standin = root + "/assets/models/lucy_standin.obj";
         return CornellBoxLucy(bigFile(real) ? real : standin);

@@ -41,7 +41,7 @@ enum {
 /* Materials: rt/material.go:33 (Lambertian) :86 (Metal) :146 (Dielectric) :202 (DiffuseLight) :243 (Isotropic) */
 enum { RTX_MAT_LAMBERTIAN = 0, RTX_MAT_METAL = 1, RTX_MAT_DIELECTRIC = 2, RTX_MAT_DIFFUSE_LIGHT = 3, RTX_MAT_ISOTROPIC = 4 };
 /* Textures: rt/texture.go:9 (SolidColor) :13 (CheckerTexture) */
-enum { RTX_TEX_SOLID = 0, RTX_TEX_CHECKER = 1, RTX_TEX_NOISE = 2 };
+enum { RTX_TEX_SOLID = 0, RTX_TEX_CHECKER = 1, RTX_TEX_NOISE = 2, RTX_TEX_IMAGE = 3 };
 /* Hittables: rt/sphere.go:6, rt/quad.go:5, rt/triangle.go:8, rt/plane.go:5, rt/hittable_list.go:3 (Box = list of 6 quads,
  * rt/primitives.go:5), rt/bvh.go:13 (mesh BVH returned by LoadOBJ, rt/obj_loader.go:109) */
 enum { RTX_GEOM_SPHERE = 0, RTX_GEOM_QUAD = 1, RTX_GEOM_TRIANGLE = 2, RTX_GEOM_PLANE = 3, RTX_GEOM_LIST = 4, RTX_GEOM_MESH = 5,
@@ -161,6 +161,14 @@ typedef struct rtx_scene_desc {
     int32_t n_perlin;
     const double* perlin_vec;     /* [n][256][3] unit vectors (Perlin.randvec) */
     const int32_t* perlin_perm;   /* [n][3][256] permX, permY, permZ */
+    /* Images of ImageTexture (rt/image_texture.go, rt/image_loader.go:44-73): ImageLoader.data as the reference holds it,
+     * i.e. AFTER its load-time LinearToGamma (sqrt) of the 8-bit channels. A texture of type RTX_TEX_IMAGE uses
+     * tex_even[i] as its image index; it is looked up with the hit's (u, v) (sphere / quad / triangle / circle). */
+    int32_t n_images;
+    const int32_t* image_width;   /* [n] */
+    const int32_t* image_height;  /* [n] */
+    const int64_t* image_offset;  /* [n] first pixel of image i in image_rgb */
+    const double* image_rgb;      /* [3 * total pixels] row-major, y = 0 top */
 } rtx_scene_desc;
 
 /* Camera public fields (rt/camera.go:18-40). The library re-derives Initialize() (rt/camera.go:286-344)

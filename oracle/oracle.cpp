@@ -21,6 +21,7 @@
 #include <cstring>
 #include <fstream>
 #include <limits>
+#include <list>
 #include <memory>
 #include <sstream>
 #include <string>
@@ -268,6 +269,21 @@ struct NoiseTexture : Texture {
         double s = scale * p.Z + 10.0 * noise->Turb(p.Scale(scale), 7);
         double turbValue = 0.5 * (1.0 + std::sin(s));
         return Color{1, 1, 1}.Scale(turbValue);
+    }
+};
+
+// ---- rt/image_texture.go, rt/image_loader.go:97-120 ---------------------------------------------------------------------------------
+struct ImageTexture : Texture {
+    int width = 0, height = 0;
+    const double* data = nullptr;  // ImageLoader.data (3 doubles per pixel, after the load-time sqrt)
+    static int clampi(int x, int low, int high) { return x < low ? low : (x < high ? x : high - 1); }
+    Color Value(double u, double v, const Point3&) const override {  // rt/image_texture.go:27-43
+        if (height <= 0) return Color{0, 1, 1};
+        u = u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);
+        v = 1.0 - (v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v));
+        int i = clampi((int)(u * (double)width), 0, width), j = clampi((int)(v * (double)height), 0, height);
+        const double* px = data + 3 * ((size_t)j * width + i);
+        return Color{px[0], px[1], px[2]};
     }
 };
 
@@ -1232,6 +1248,7 @@ struct Scene {
     std::vector<std::unique_ptr<Material>> materials;
     std::vector<std::unique_ptr<Hittable>> owned;
     std::vector<std::unique_ptr<Perlin>> perlins;
+    std::list<std::vector<double>> imageData;
     std::vector<Quad*> quads;
     HittableList* worldList = nullptr;
     const Hittable* world = nullptr;
@@ -1257,6 +1274,14 @@ static Scene* sceneFromDesc(const rtx_scene_desc* d, const rtx_camera_desc* c) {
             for (int k = 0; k < 256; k++) { pn->randvec[k] = {pv[3 * k], pv[3 * k + 1], pv[3 * k + 2]}; pn->permX[k] = pp[k]; pn->permY[k] = pp[256 + k]; pn->permZ[k] = pp[512 + k]; }
             auto t = new NoiseTexture();
             t->noise = pn; t->scale = d->tex_inv_scale[i];
+            S->textures[i].reset(t);
+        } else if (d->tex_type[i] == RTX_TEX_IMAGE) {
+            auto t = new ImageTexture();
+            const int im = d->tex_even[i];
+            t->width = d->image_width[im]; t->height = d->image_height[im];
+            const double* src = d->image_rgb + 3 * (size_t)d->image_offset[im];
+            S->imageData.emplace_back(src, src + 3 * (size_t)t->width * t->height);   // the descriptor is only borrowed
+            t->data = S->imageData.back().data();
             S->textures[i].reset(t);
         } else S->textures[i].reset(new CheckerTexture());
     }

@@ -103,8 +103,10 @@ def test_other_scene_shapes(grt):
     assert all(sorted(perm[256 * a:256 * a + 256]) == list(range(256)) for a in range(3))   # three permutations of 0..255
     vec = np.ctypeslib.as_array(pe.desc.perlin_vec, (768,)).reshape(256, 3)
     assert np.allclose((vec * vec).sum(axis=1), 1.0)
-    with pytest.raises(RuntimeError):                                    # ImageTexture (JPEG): outside the device vocabulary, an error, never a fallback
-        grt.NamedScene("earth", 64)
+    ea = grt.config_scene("earth")                                       # ImageTexture over the PPM conversion of earthmap.jpg (or the stand-in)
+    assert ea.desc.n_images == 1 and ea.desc.n_spheres == 1 and ea.desc.image_width[0] >= 512 and (ea.width, ea.height) == (800, 450)
+    px = np.ctypeslib.as_array(ea.desc.image_rgb, (3 * ea.desc.image_width[0] * ea.desc.image_height[0],))
+    assert 0.0 <= px.min() and px.max() <= 1.0 and px.mean() > 0.2      # sqrt(v / 255): the reference's load-time gamma
 
 
 def test_lucy_instances(grt):
@@ -126,8 +128,9 @@ def test_lucy_instances(grt):
 
 def test_unsupported_objects_are_flatten_errors(grt):
     H = grt.host()
-    assert H.rth_scene_named(b"earth", b".", 1, 1, 0, 1.0, 0, 0) is None
-    assert b"outside the device path" in H.rth_last_error()
+    # asset root without the image: EarthScene cannot load its texture -> an error (the reference would render its cyan debug colour)
+    assert H.rth_scene_named(b"earth", b"/nonexistent-root", 1, 1, 0, 1.0, 0, 0) is None
+    assert b"cannot load" in H.rth_last_error()
     assert H.rth_scene_named(b"no-such-scene", b".", 1, 1, 0, 1.0, 0, 0) is None
     assert b"unknown scene" in H.rth_last_error()
 

@@ -53,8 +53,8 @@ def secondary_rays(ho, rng, n):
 
 
 CONFIG_SMALL = {"cornell": 160, "cornell-glossy": 160, "random": 200, "hdri-test": 240,
-                "checkered": 200, "simple": 200, "quads": 160, "glossy-metal": 200, "cornell-smoke": 160, "perlin": 200, "primitives": 240}
-OTHER_SCENES = ["checkered", "simple", "quads", "glossy-metal", "cornell-smoke", "perlin", "primitives"]   # rt/scenes.go functions beyond BASELINE's five
+                "checkered": 200, "simple": 200, "quads": 160, "glossy-metal": 200, "cornell-smoke": 160, "perlin": 200, "primitives": 240, "earth": 200}
+OTHER_SCENES = ["checkered", "simple", "quads", "glossy-metal", "cornell-smoke", "perlin", "primitives", "earth"]   # rt/scenes.go functions beyond BASELINE's five
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -442,7 +442,7 @@ def test_level2_configured_scenes(grt, orc, ctx, name, width, spp, depth):
 
 
 @pytest.mark.parametrize("name,width,spp,depth", [("checkered", 96, 64, 20), ("simple", 96, 96, 30), ("quads", 80, 64, 20), ("glossy-metal", 96, 128, 10),
-                                                 ("cornell-smoke", 80, 128, 5), ("perlin", 96, 64, 20), ("primitives", 128, 128, 25)])
+                                                 ("cornell-smoke", 80, 128, 5), ("perlin", 96, 64, 20), ("primitives", 128, 128, 25), ("earth", 96, 64, 20)])
 def test_level2_other_scenes(grt, orc, ctx, name, width, spp, depth):
     """The remaining scene functions of rt/scenes.go inside the device vocabulary: nested dielectrics (hollow glass sphere),
     a planar light over fuzzy metals, two rotated boxes of smoke (Volume over Translate(RotateY(Box))), Perlin turbulence
@@ -451,6 +451,42 @@ def test_level2_other_scenes(grt, orc, ctx, name, width, spp, depth):
     ctx.load(sc)
     o = orc.OracleScene(sc.desc_ptr, sc.cam_ptr)
     check_statistical(ctx, o, spp, spp, depth)
+
+
+def test_level2_image_textures_on_every_uv_primitive(grt, orc, ctx):
+    """ImageTexture (rt/image_texture.go) looks the hit's (u, v) up: sphere (acos / atan2), quad (alpha, beta), triangle
+    (barycentric), circle (local frame), plain and inside a transformed entry, as albedo and as the emission of a light;
+    a high-contrast image so that a wrong (u, v) convention shows up as a bias. An image on a Plane is refused."""
+    rng = np.random.default_rng(41)
+    img = np.zeros((32, 64, 3), dtype=np.uint8)
+    img[::2, ::2] = (250, 30, 30); img[1::2, ::2] = (30, 250, 30); img[::2, 1::2] = (30, 30, 250); img[1::2, 1::2] = (240, 240, 240)
+    img[:8] //= 3                                                     # a gradient in v so that a flipped V is visible
+    b = grt.SceneBuilder(world_is_bvh=True)
+    tex = b.image(img)
+    m = b.material("lambertian", tex)
+    lm = b.material("light", tex)
+    white = b.material("lambertian", (0.7, 0.7, 0.7))
+    b.entry(grt.GEOM_SPHERE, b.sphere((-2.5, 1, 0), 1.0, m))
+    b.entry(grt.GEOM_QUAD, b.quadp((-1, 0, 0), (2, 0, 0), (0, 2, 0), m))
+    b.entry(grt.GEOM_TRIANGLE, b.triangle((1.5, 0, 0), (3.5, 0, 0), (2.5, 2, 0), m))
+    b.entry(grt.GEOM_CIRCLE, b.circle((0, 3.2, 0), (0, 0.2, -1), 0.9, m))
+    b.entry(grt.GEOM_SPHERE, b.sphere((0, 0, 0), 0.8, m), xforms=[("translate", (2.5, 3.2, 0)), ("rotate_y", 40.0), ("scale", (1.0, 0.6, 1.0))])
+    b.entry(grt.GEOM_QUAD, b.quadp((-6, -0.01, -6), (12, 0, 0), (0, 0, 12), white))
+    lq = b.quadp((-2, 6, -3), (4, 0, 0), (0, 0, 2), lm)
+    b.entry(grt.GEOM_QUAD, lq)
+    b.light(lq)
+    built = b.build()
+    cam = grt.make_camera(112, 1.0, 96, 8, 50, (0, 2, -9), (0, 1.8, 0), sky=True)
+    ctx.load((built, cam))
+    o = orc.OracleScene(built.desc_ptr, grt.C.pointer(cam))
+    rays = o.camera_rays(*camera_batch(112, 112, 40000, rng))
+    assert_level1(ctx.trace_closest(rays), o.trace_closest(rays), "image-texture scene")
+    check_statistical(ctx, o, 96, 96, 8)
+    bad = grt.SceneBuilder()
+    bad.entry(grt.GEOM_PLANE, bad.planep((0, 0, 0), (0, 1, 0), bad.material("lambertian", bad.image(img))))
+    with pytest.raises(grt.RtxError):
+        ctx.upload(bad.build().desc_ptr)
+    ctx.load((built, cam))                                             # leave the shared context with a valid scene
 
 
 def test_level2_reduced_depth_pass_sees_the_sky(grt, orc, ctx):

@@ -20,6 +20,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_HDR = "/root/reference/assets/hdri/abandoned_hall_01_1k.hdr"
+REF_EARTH = "/root/reference/assets/images/earthmap.jpg"
 
 
 def make_lucy_standin(path, n_theta=400, n_rows=350, seed=1234):
@@ -120,6 +121,12 @@ def make_synthetic_hdr(path, W=1024, H=512, seed=7):
                     f.write(bytes([len(chunk)]) + chunk)
 
 
+def write_ppm(path, rgb8):
+    with open(path, "wb") as f:
+        f.write(b"P6\n%d %d\n255\n" % (rgb8.shape[1], rgb8.shape[0]))
+        f.write(np.ascontiguousarray(rgb8, dtype=np.uint8).tobytes())
+
+
 def ensure_assets(verbose=False):
     made = []
     obj = os.path.join(ROOT, "assets/models/lucy_standin.obj")
@@ -134,6 +141,29 @@ def ensure_assets(verbose=False):
     if not os.path.exists(real) and os.path.exists(REF_HDR):
         shutil.copyfile(REF_HDR, real)
         made.append(real + " (copied from the reference checkout)")
+    # ImageTexture of EarthScene: the host mirror reads binary PPM (no JPEG decoder in the toolchain). The reference's
+    # earthmap.jpg is converted when the checkout is present; a synthetic continents-and-oceans map stands in otherwise.
+    os.makedirs(os.path.join(ROOT, "assets/images"), exist_ok=True)
+    earth = os.path.join(ROOT, "assets/images/earthmap.ppm")
+    if not os.path.exists(earth) and os.path.exists(REF_EARTH):
+        try:
+            from PIL import Image
+            im = np.asarray(Image.open(REF_EARTH).convert("RGB"), dtype=np.uint8)
+            write_ppm(earth, im)
+            made.append(f"{earth} ({im.shape[1]}x{im.shape[0]}, decoded from the reference's earthmap.jpg)")
+        except Exception as e:  # noqa: BLE001
+            made.append(f"earthmap.jpg not converted: {e}")
+    syn_earth = os.path.join(ROOT, "assets/images/synthetic_earth.ppm")
+    if not os.path.exists(syn_earth):
+        yy, xx = np.mgrid[0:256, 0:512]
+        lat, lon = (yy / 256.0 - 0.5) * np.pi, xx / 512.0 * 2 * np.pi
+        land = (np.sin(3 * lon + 1.0) * np.cos(2 * lat) + 0.5 * np.sin(7 * lon - 2 * lat) + 0.3 * np.cos(5 * lat + lon)) > 0.25
+        im = np.zeros((256, 512, 3), dtype=np.uint8)
+        im[...] = (20, 60, 150)
+        im[land] = (40, 140, 50)
+        im[np.abs(lat) > 1.25] = (235, 240, 245)
+        write_ppm(syn_earth, im)
+        made.append(syn_earth)
     if verbose:
         for m in made:
             print("made", m)
