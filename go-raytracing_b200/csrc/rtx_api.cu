@@ -49,7 +49,6 @@ struct rtx_ctx {
     cudaStream_t stream = nullptr;      // stream in use
     cudaStream_t own_stream = nullptr;  // created by rtx_create
     std::string err;
-    std::vector<void*> scene_allocs;
     DevScene S{};
     bool have_scene = false, have_camera = false;
     DevCamera C{};
@@ -101,26 +100,7 @@ static int32_t fail(rtx_ctx* ctx, int32_t code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(ctx, RTX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
-template <class T>
-static int32_t upload(rtx_ctx* ctx, const std::vector<T>& v, const T** out, bool scene = true) {
-    *out = nullptr;
-    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
-    void* p = nullptr;
-    CU(cudaMalloc(&p, bytes));
-    if (scene) ctx->scene_allocs.push_back(p);
-    if (!v.empty()) CU(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-    *out = (const T*)p;
-    return RTX_OK;
-}
-#define UP(vec, field)                                                    \
-    do {                                                                  \
-        int32_t rc_ = upload(ctx, vec, &field);                           \
-        if (rc_ != RTX_OK) return rc_;                                    \
-    } while (0)
-
 static void free_scene(rtx_ctx* ctx) {   // the slabs are kept for the next upload (grow-only); rtx_destroy releases them
-    for (void* p : ctx->scene_allocs) cudaFree(p);
-    ctx->scene_allocs.clear();
     ctx->have_scene = false;
 }
 static void free_pool(rtx_ctx* ctx) {
@@ -591,7 +571,6 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
             for (int k = 0; k < count; k++) pushTri(begin + perm[k], perm[k], ranks[perm[k]]);
         }
     }
-    const size_t hostMeshTris = triInfo.size();   // 0 with the device builder
     for (int ti : looseList) pushTri(ti, 0, 0);
     auto devPrim = [&](int kind, int idx) { return kind == RTX_GEOM_TRIANGLE ? looseOfDesc[idx] : idx; };
     std::vector<int2> listItems(d->n_list_items);
@@ -792,7 +771,6 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
             CU(put(it.src, it.bytes, dst));
             *it.field = dst;
         }
-        (void)hostMeshTris;
     }
     S.tlas_root = tlasRoot;
     S.n_entries = d->n_entries;
