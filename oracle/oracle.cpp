@@ -1593,6 +1593,11 @@ void orc_refract(const double* uv, const double* n, double eta, double* out) {
     Vec3 r = Refract({uv[0], uv[1], uv[2]}, {n[0], n[1], n[2]}, eta);
     out[0] = r.X; out[1] = r.Y; out[2] = r.Z;
 }
+// Texture.Value of texture `tex` of a scene built from a descriptor (NoiseTexture / ImageTexture KATs).
+void orc_texture_value(orc_scene* h, int32_t tex, double u, double v, const double* p, double* out) {
+    Color c = h->S->textures[tex]->Value(u, v, {p[0], p[1], p[2]});
+    out[0] = c.X; out[1] = c.Y; out[2] = c.Z;
+}
 void orc_checker(double scale, const double* even, const double* odd, const double* p, double* out) {
     SolidColor e, o;
     e.Albedo = {even[0], even[1], even[2]};

@@ -50,6 +50,7 @@ def lib():
         L.orc_reflectance.restype = C.c_double
         L.orc_reflectance.argtypes = [C.c_double, C.c_double]
         L.orc_refract.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+        L.orc_texture_value.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         L.orc_checker.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_prim_hit.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
         _lib = L
@@ -110,6 +111,11 @@ class OracleScene:
         return dict(sum=s, sumsq=q, seconds=sec,
                     counters=dict(RayCount=int(cnt[0]), BVHIntersections=int(cnt[1]), SamplesComputed=int(cnt[2]),
                                   PixelsRendered=int(cnt[3]), ShadowQueries=int(cnt[4])))
+
+    def texture_value(self, tex, u, v, p):
+        pp, out = _d(p), np.zeros(3)
+        lib().orc_texture_value(self._h, int(tex), float(u), float(v), pp.ctypes.data, out.ctypes.data)
+        return out
 
     def hdri_total_power(self):
         return self._L.orc_hdri_total_power(self._h)

@@ -88,6 +88,43 @@ def test_interval_conventions(orc):
     assert not hit
 
 
+def test_circle_noise_image_known_answers(orc, grt):
+    """Hand-derivable answers for the vocabulary added with ABI 2 (rt/circle.go, rt/noise.go, rt/image_texture.go)."""
+    b = grt.SceneBuilder(world_is_bvh=False)
+    m = b.material("lambertian", (0.5, 0.5, 0.5))
+    b.entry(grt.GEOM_CIRCLE, b.circle((0, 0, 0), (0, 0, 2), 1.0, m))          # the constructor normalises the normal
+    noise = b.noise(4.0, seed=3)
+    img = np.zeros((2, 4, 3), dtype=np.uint8)
+    img[0, :, 0] = (0, 64, 128, 255); img[1, :, 1] = 255                       # top row: red ramp; bottom row: green
+    image = b.image(img)
+    built = b.build()
+    cam = grt.make_camera(16, 1.0, 1, 5, 40, (0, 0, -5), (0, 0, 0))
+    o = orc.OracleScene(built.desc_ptr, grt.C.pointer(cam))
+    rays = np.array([[0.0, 0, -5, 0, 0, 1, 0], [1.0, 0, -5, 0, 0, 1, 0], [1.0000001, 0, -5, 0, 0, 1, 0], [0.6, 0.8, -5, 0, 0, 2, 0], [0.5, 0.5, 3, 0, 0, -1, 0],
+                     [0, 0, -5, 1, 0, 0, 0]])
+    h = o.trace_closest(rays, 0.001, 5.0)                                      # t == max is inside (Contains)
+    assert list(h["entry"]) == [0, 0, -1, 0, 0, -1]                            # |P - c| == r hits, just outside misses, parallel misses
+    assert list(h["t"][[0, 1, 3, 4]]) == [5.0, 5.0, 2.5, 3.0]
+    assert np.array_equal(h["normal"][0], [0, 0, -1]) and h["front"][0] == 0   # SetFaceNormal: d.n > 0 -> back face, normal turned against the ray
+    assert np.array_equal(h["normal"][4], [0, 0, 1]) and h["front"][4] == 1
+    assert len(o.trace_closest(rays[:1], 0.001, 4.999)["t"]) == 1 and o.trace_closest(rays[:1], 0.001, 4.999)["entry"][0] == -1
+    # circle UVs (rt/circle.go:59-72): normal.y <= 0.9 -> u axis = unit((0,1,0) x n) = (1,0,0), v axis = n x u = (0,1,0)
+    assert np.allclose(h["uv"][3], [(0.6 + 1) / 2, (0.8 + 1) / 2]) and np.allclose(h["uv"][0], [0.5, 0.5])
+    # Perlin noise vanishes on the integer lattice (every weight vector is zero where its trilinear factor is not):
+    # turb = 0 and NoiseTexture.Value = 0.5 (1 + sin(scale z)) there  (rt/noise.go:30-65, rt/texture.go:81-85)
+    for p in ([0, 0, 0], [0.25, 0.5, 0.75], [-1.5, 2.0, 0.25]):               # scale 4: 4p is a lattice point for all octaves
+        assert np.allclose(o.texture_value(noise, 0, 0, p), 0.5 * (1 + np.sin(4.0 * p[2])), atol=1e-12)
+    vals = np.array([o.texture_value(noise, 0, 0, [0.13 * k, 0.07 * k, 0.11 * k])[0] for k in range(1, 200)])
+    assert vals.min() >= 0 and vals.max() <= 1 and vals.std() > 0.1            # and it is not constant elsewhere
+    # ImageTexture: u -> column int(u W), v flipped -> row int((1 - v) H), clamped; texel = sqrt(v8 / 255) (load-time gamma)
+    assert np.allclose(o.texture_value(image, 0.0, 1.0, [0, 0, 0]), [0, 0, 0])
+    assert np.allclose(o.texture_value(image, 0.30, 0.75, [0, 0, 0]), [np.sqrt(64 / 255), 0, 0])
+    assert np.allclose(o.texture_value(image, 1.0, 0.99, [0, 0, 0]), [1, 0, 0])        # u = 1 -> column W clamps to W - 1
+    assert np.allclose(o.texture_value(image, 0.6, 0.25, [0, 0, 0]), [0, 1, 0])        # lower half of v -> bottom row
+    assert np.allclose(o.texture_value(image, -3.0, 7.0, [0, 0, 0]), [0, 0, 0])        # clamped to (0, 1) -> top-left texel
+    o.close()
+
+
 def test_checker_parity(orc):
     even, odd = [1, 0, 0], [0, 0, 1]
     assert tuple(orc.checker(1.0, even, odd, [0.5, 0.5, 0.5])) == (1, 0, 0)
