@@ -226,3 +226,23 @@ def test_oracle_vs_reference_image_png(orc, grt):
     ratio = ours[m] / ref[m]
     assert 0.985 < ratio.mean() < 1.015
     assert ratio.min() > 0.9 and ratio.max() < 1.1
+
+
+GOLDEN_SCENES = ["cornell", "random", "cornell-glossy", "cornell-lucy", "hdri-test", "cornell-smoke", "primitives", "earth"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_SCENES)
+def test_oracle_reproduces_golden_rays(orc, grt, name):
+    """tests/golden/level1_<scene>.npz (tools/make_golden_rays.py): committed ray batches with the hit records the oracle
+    produced when they were made. The oracle must keep reproducing them bit for bit (ids, t, front face); the GPU suite
+    holds the CUDA path to the same files."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"level1_{name}.npz"))
+    sc = grt.config_scene(name, width=int(g["width"]), spp=1)
+    o = orc.OracleScene(sc.desc_ptr, sc.cam_ptr)
+    h = o.trace_closest(g["rays"])
+    assert np.array_equal(h["entry"], g["entry"]) and np.array_equal(h["prim"], g["prim"])
+    hit = g["entry"] >= 0
+    assert np.array_equal(h["t"][hit], g["t"][hit]) and np.array_equal(h["front"][hit], g["front"][hit])
+    assert hit.mean() > 0.25
+    o.close()

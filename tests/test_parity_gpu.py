@@ -260,6 +260,22 @@ def test_level1_circles_and_pyramids(grt, orc, ctx):
         assert np.allclose(hu["uv"][ho["entry"] >= 0], ho["uv"][ho["entry"] >= 0], rtol=0, atol=1e-9)
 
 
+@pytest.mark.parametrize("name", ["cornell", "random", "cornell-glossy", "cornell-lucy", "hdri-test", "cornell-smoke", "primitives", "earth"])
+def test_level1_golden_fixtures(grt, ctx, name):
+    """The CUDA path against the committed fixtures of tests/golden/ (made by tools/make_golden_rays.py from the oracle, which
+    the CPU suite holds to the same files): primary rays with lens / time jitter and scatter rays leaving the surfaces.
+    No oracle call here: ids and front faces bit-exact, t to 1e-12 relative (north star: 1e-5)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"level1_{name}.npz"))
+    sc = grt.config_scene(name, width=int(g["width"]), spp=1)
+    ctx.load(sc)
+    h = ctx.trace_closest(g["rays"])
+    assert np.array_equal(h["entry"], g["entry"]) and np.array_equal(h["prim"], g["prim"])
+    hit = g["entry"] >= 0
+    assert np.array_equal(h["front"][hit], g["front"][hit])
+    assert np.all(np.abs(h["t"][hit] - g["t"][hit]) <= TIGHT * np.abs(g["t"][hit]))
+
+
 def test_level1_axis_parallel_rays_cull(grt, orc, ctx):
     """Directions with one or two exactly-zero components (wall normal + an axis-aligned scatter direction: d = (0,0,-2))
     must give the reference's hits AND must still be culled by the float32 box test on the degenerate axes: a ray whose
