@@ -116,6 +116,9 @@ struct Best {
 #ifndef RTX_N_FAST
 #define RTX_N_FAST 0   /* lanes with a NODE-ready slot from which the NODE phase is taken without a vote (0 = always vote) */
 #endif
+#ifndef RTX_ANYHIT_SORT
+#define RTX_ANYHIT_SORT 0   /* cornell-lucy k_connect: 2646 (sorted) -> 2689 Mrays/s */
+#endif
 #define RTX_PH_N 0
 #define RTX_PH_T 1
 #define RTX_PH_E 2
@@ -393,7 +396,9 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                     if (COUNT) tc.nodes++;
                     node_test(S.nodes, node, f, ftmin, ftmax, d, ch);
 #define RTX_CSWAP(i, j) if (d[j] < d[i]) { float td = d[i]; d[i] = d[j]; d[j] = td; int tcx = ch[i]; ch[i] = ch[j]; ch[j] = tcx; }
-                    RTX_CSWAP(0, 1) RTX_CSWAP(2, 3) RTX_CSWAP(0, 2) RTX_CSWAP(1, 3) RTX_CSWAP(1, 2)
+                    // closest-hit queries visit the children front to back; an any-hit query only needs SOME hit, so the order is
+                    // irrelevant to the result (RTX_ANYHIT_SORT = 0 drops the sorting network there)
+                    if (RTX_ANYHIT_SORT || !Policy::ANY_HIT) { RTX_CSWAP(0, 1) RTX_CSWAP(2, 3) RTX_CSWAP(0, 2) RTX_CSWAP(1, 3) RTX_CSWAP(1, 2) }
 #undef RTX_CSWAP
                     if (sp + 3 <= RTX_SMEM_STACK) {
                         int* const st = T.stack + s;
