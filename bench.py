@@ -327,9 +327,13 @@ def main():
             r = cal.render(2, depth, seed=1, threads=threads, moments=False)
             cpu_spp = max(1, min(spp, int(15.0 * (2 * cal.width * cal.height / max(r["seconds"], 1e-6)) / npix)))
         r = o.render(cpu_spp, depth, seed=args.seed, threads=threads, use_atomics=True, moments=False)
+        r2 = o.render(cpu_spp, depth, seed=args.seed + 1, threads=threads, use_atomics=False, moments=False)
         cpu = {"value": npix * cpu_spp / r["seconds"] / 1e6, "unit": "Mpaths/s", "cores": threads, "kind": "port",
                "sample": f"{sc.width}x{sc.height}, {cpu_spp} of {spp} spp, depth {depth}, full resolution, {r['seconds']:.1f} s",
-               "mrays_per_s": (r["counters"]["RayCount"] - r["counters"]["SamplesComputed"] + r["counters"]["ShadowQueries"]) / r["seconds"] / 1e6}
+               "mrays_per_s": (r["counters"]["RayCount"] - r["counters"]["SamplesComputed"] + r["counters"]["ShadowQueries"]) / r["seconds"] / 1e6,
+               "value_without_global_atomics": npix * cpu_spp / r2["seconds"] / 1e6,
+               "note": "value: the restatement with the reference's global atomic counters (rt/bvh.go:220, rt/camera.go:439,448) at the same sites; "
+                       "value_without_global_atomics: the same pass with those counters removed (SURVEY 8d)"}
 
     if rank == 0:
         sec = dev_ms / 1e3
