@@ -156,6 +156,7 @@ def host() -> C.CDLL:
         H.rth_image_height.argtypes = [C.c_void_p]
         H.rth_image_height_for.argtypes = [C.c_int32, C.c_double]
         H.rth_bucket_render.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64, _pd, C.c_char_p]
+        H.rth_bucket_render_progressive.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         H.rth_load_hdr.argtypes = [C.c_char_p, _pi, _pi, C.c_void_p, C.c_int64]
         H.rth_write_png.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_int32]
         _host_cache = H
@@ -487,6 +488,16 @@ class NamedScene:
         if rc != 0:
             raise RuntimeError(host().rth_last_error().decode())
         return pix, sec.value
+
+    def bucket_render_progressive(self, seed=1):
+        """The display-loop use: Update() is ticked without ever blocking on a pass and the framebuffer is copied every tick.
+        Returns (final RGBA8 image, ticks that returned while a pass was running, distinct finished passes seen on the way)."""
+        pix = np.zeros((self.height, self.width, 4), dtype=np.uint8)
+        ticks, frames = C.c_int32(0), C.c_int32(0)
+        rc = host().rth_bucket_render_progressive(self._h, seed, pix.ctypes.data, pix.nbytes, C.byref(ticks), C.byref(frames))
+        if rc != 0:
+            raise RuntimeError(host().rth_last_error().decode())
+        return pix, ticks.value, frames.value
 
     def close(self):
         if self._h:

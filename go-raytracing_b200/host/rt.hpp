@@ -14,6 +14,10 @@
 #include <cmath>
 #include <cstdint>
 #include <limits>
+#include <atomic>
+#include <chrono>
+#include <mutex>
+#include <thread>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -393,26 +397,39 @@ class BucketRenderer {
 public:
     BucketRenderer(CameraPtr camera, HittablePtr world, int bucketSize, int numWorkers, int deviceId = 0);
     ~BucketRenderer();
-    int Update();                 // one tick of the pass state machine (rt/bucket_renderer.go:127-164); 0 = ok
-    void RenderToCompletion();    // headless helper: Update() until IsCompleted()
+    // One tick of the pass state machine (rt/bucket_renderer.go:127-164). NEVER blocks on a pass: like the reference, which
+    // renders in goroutines, the first call starts pass 0 on a worker thread, later calls poll `passComplete`, publish the
+    // finished pass into the framebuffer under the mutex and start the next one. A display loop calls it once per frame.
+    // Returns 0, or -1 once a pass failed (LastError()).
+    int Update();
+    void RenderToCompletion();    // headless helper: Update() until IsCompleted(), sleeping between polls
     bool IsCompleted() const { return completed_; }
+    int CurrentPass() const { return currentPass_; }
     double GetRenderDurationSeconds() const { return duration_s_; }
     int SaveImage(const std::string& filename) const;  // binary PPM (P6) or PNG by extension
-    const std::vector<uint8_t>& Pix() const { return pix_; }  // framebuffer.Pix, RGBA8 stride 4*W
+    std::vector<uint8_t> CopyFramebuffer() const;      // framebuffer.Pix (RGBA8, stride 4*W) under the mutex: safe while a pass runs (Draw, :303)
+    const std::vector<uint8_t>& Pix() const { return pix_; }  // unlocked view: only when no pass is running (after IsCompleted())
     int Width() const { return w_; }
     int Height() const { return h_; }
     rtx_ctx* Context() { return ctx_; }
+    const std::string& LastError() const { return err_; }
     uint64_t seed = 0x9E3779B97F4A7C15ull;
 
 private:
-    void renderPass();
+    void renderPass(int pass);   // worker thread: one rtx_render_pass + resolve into back_, then passComplete = true
+    void join();
     CameraPtr camera_;
     std::shared_ptr<FlatScene> flat_;
     rtx_ctx* ctx_ = nullptr;
     int w_ = 0, h_ = 0, currentPass_ = 0, totalPasses_ = 3;
-    bool completed_ = false;
+    bool completed_ = false, renderStarted_ = false;
     double duration_s_ = 0;
-    std::vector<uint8_t> pix_;
+    std::chrono::steady_clock::time_point renderStart_;
+    std::vector<uint8_t> pix_, back_;   // framebuffer shown / pass being resolved
+    mutable std::mutex mu_;             // protects pix_ (rt/bucket_renderer.go:51)
+    std::atomic<bool> passComplete_{false};
+    std::thread worker_;
+    std::string err_;
 };
 std::shared_ptr<BucketRenderer> NewBucketRenderer(CameraPtr camera, HittablePtr world, int bucketSize, int numWorkers);
 // ProgressiveRenderer (rt/renderer.go:27) keeps its API and routes to the same device pass.

@@ -3,6 +3,9 @@
 // boundary (that is include/rtx_b200.h); it only exposes host logic that a Go caller has natively.
 #include <cstring>
 
+#include <chrono>
+#include <thread>
+
 #include "rt.hpp"
 
 using namespace rt;
@@ -66,6 +69,37 @@ int32_t rth_bucket_render(rth_scene* s, uint64_t seed, uint8_t* pix, int64_t nby
         std::memcpy(pix, r.Pix().data(), r.Pix().size());
         if (seconds) *seconds = r.GetRenderDurationSeconds();
         if (save_path && *save_path && r.SaveImage(save_path) != 0) { g_err = "SaveImage failed"; return RTX_ERR_INVALID; }
+        return RTX_OK;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return RTX_ERR_INVALID;
+    }
+}
+
+// The display-loop use of the renderer (main.go's ebiten game loop calls Update / Draw every frame): ticks Update() without ever
+// blocking on a pass and copies the framebuffer each tick, like Draw does. Reports how many ticks returned while a pass was
+// still running and how many different finished passes were observed in the framebuffer on the way (the preview arrives first).
+int32_t rth_bucket_render_progressive(rth_scene* s, uint64_t seed, uint8_t* pix, int64_t nbytes, int32_t* ticks_while_rendering, int32_t* frames_seen) {
+    try {
+        BucketRenderer r(s->scene.camera, s->world, 32, 1);
+        r.seed = seed;
+        int ticks = 0, frames = 0;
+        uint64_t last = 0;
+        while (!r.IsCompleted()) {
+            if (r.Update() != 0) { g_err = r.LastError(); return RTX_ERR_INVALID; }
+            if (!r.IsCompleted()) ticks++;
+            std::vector<uint8_t> fb = r.CopyFramebuffer();
+            uint64_t hsh = 1469598103934665603ull;
+            for (size_t i = 0; i < fb.size(); i += 97) hsh = (hsh ^ fb[i]) * 1099511628211ull;
+            bool blank = true;
+            for (size_t i = 0; i < fb.size() && blank; i += 4) blank = fb[i] == 0 && fb[i + 1] == 0 && fb[i + 2] == 0 && fb[i + 3] == 0;
+            if (!blank && hsh != last) { frames++; last = hsh; }
+            std::this_thread::sleep_for(std::chrono::microseconds(500));
+        }
+        if ((int64_t)r.Pix().size() != nbytes) { g_err = "pix size mismatch"; return RTX_ERR_INVALID; }
+        std::memcpy(pix, r.Pix().data(), r.Pix().size());
+        if (ticks_while_rendering) *ticks_while_rendering = ticks;
+        if (frames_seen) *frames_seen = frames;
         return RTX_OK;
     } catch (const std::exception& e) {
         g_err = e.what();

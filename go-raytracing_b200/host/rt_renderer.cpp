@@ -1,7 +1,7 @@
 // rt_renderer.cpp — BucketRenderer / ProgressiveRenderer mirrors (rt/bucket_renderer.go, rt/renderer.go).
 //
-// The constructor, the 3-pass state machine of Update() and SaveImage/IsCompleted/GetRenderDuration keep the
-// reference's behaviour; the body of renderPass (rt/bucket_renderer.go:170-214: worker goroutines, 32x32 tiles,
+// The constructor, the 3-pass state machine of Update() — non-blocking, a worker thread per pass like the reference's
+// goroutines — and SaveImage/IsCompleted/GetRenderDuration keep the reference's behaviour; the body of renderPass (rt/bucket_renderer.go:170-214: worker goroutines, 32x32 tiles,
 // GetRay/RayColor per sample, gamma + RGBA8 pack) is ONE call into the CUDA library per pass.
 // bucketSize / numWorkers are accepted and ignored (the device schedules its own work).
 // The ebiten Draw()/stats-bar overlay is display cosmetics and out of scope.
@@ -30,34 +30,71 @@ BucketRenderer::BucketRenderer(CameraPtr camera, HittablePtr world, int /*bucket
     check(ctx_, rtx_image_size(ctx_, &w, &h), "rtx_image_size");
     w_ = w; h_ = h;
     pix_.assign((size_t)4 * w * h, 0);  // image.NewRGBA (rt/bucket_renderer.go:55)
+    back_.assign((size_t)4 * w * h, 0);
 }
 BucketRenderer::~BucketRenderer() {
+    join();
     if (ctx_) rtx_destroy(ctx_);
 }
+void BucketRenderer::join() {
+    if (worker_.joinable()) worker_.join();
+}
 
-void BucketRenderer::renderPass() {  // rt/bucket_renderer.go:170-191 pass schedule
+void BucketRenderer::renderPass(int pass) {  // rt/bucket_renderer.go:170-214: the pass schedule; the worker pool is ONE device call
     int spp, depth;
-    switch (currentPass_) {
+    switch (pass) {
         case 0: spp = 1; depth = 3; break;
         case 1: spp = std::max(1, camera_->SamplesPerPixel / 4); depth = std::max(3, camera_->MaxDepth / 2); break;
         default: spp = camera_->SamplesPerPixel; depth = camera_->MaxDepth; break;
     }
-    check(ctx_, rtx_accum_clear(ctx_), "rtx_accum_clear");  // each pass overwrites the framebuffer (:291-300)
-    check(ctx_, rtx_render_pass(ctx_, spp, depth, camera_->MaxDepth, seed + (uint64_t)currentPass_, 0), "rtx_render_pass");
-    check(ctx_, rtx_resolve_rgba8(ctx_, spp, pix_.data(), (int64_t)pix_.size()), "rtx_resolve_rgba8");
+    try {
+        check(ctx_, rtx_accum_clear(ctx_), "rtx_accum_clear");  // each pass overwrites the framebuffer (:291-300)
+        check(ctx_, rtx_render_pass(ctx_, spp, depth, camera_->MaxDepth, seed + (uint64_t)pass, 0), "rtx_render_pass");
+        check(ctx_, rtx_resolve_rgba8(ctx_, spp, back_.data(), (int64_t)back_.size()), "rtx_resolve_rgba8");
+        std::lock_guard<std::mutex> lk(mu_);
+        pix_.swap(back_);   // the finished pass becomes visible to Draw / CopyFramebuffer at once
+    } catch (const std::exception& e) {
+        std::lock_guard<std::mutex> lk(mu_);
+        err_ = e.what();
+    }
+    passComplete_.store(true);
 }
 
-int BucketRenderer::Update() {  // rt/bucket_renderer.go:127-164, one pass per tick
-    if (completed_) return 0;
-    auto t0 = std::chrono::steady_clock::now();
-    renderPass();
-    duration_s_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    currentPass_++;
-    if (currentPass_ >= totalPasses_) completed_ = true;
+int BucketRenderer::Update() {  // rt/bucket_renderer.go:127-164
+    if (completed_) return err_.empty() ? 0 : -1;
+    if (!renderStarted_) {   // first tick: start pass 0 in the background (go r.renderMultiPass())
+        renderStarted_ = true;
+        renderStart_ = std::chrono::steady_clock::now();
+        passComplete_.store(false);
+        worker_ = std::thread(&BucketRenderer::renderPass, this, currentPass_);
+        return 0;
+    }
+    if (passComplete_.load() && currentPass_ < totalPasses_) {
+        join();
+        passComplete_.store(false);
+        currentPass_++;
+        bool failed;
+        { std::lock_guard<std::mutex> lk(mu_); failed = !err_.empty(); }
+        if (currentPass_ < totalPasses_ && !failed) {
+            worker_ = std::thread(&BucketRenderer::renderPass, this, currentPass_);
+        } else {
+            completed_ = true;
+            duration_s_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - renderStart_).count();
+            return failed ? -1 : 0;
+        }
+    }
     return 0;
 }
 void BucketRenderer::RenderToCompletion() {
-    while (!completed_) Update();
+    while (!completed_) {
+        Update();
+        if (!completed_) std::this_thread::sleep_for(std::chrono::microseconds(200));
+    }
+    if (!err_.empty()) throw std::runtime_error(err_);
+}
+std::vector<uint8_t> BucketRenderer::CopyFramebuffer() const {
+    std::lock_guard<std::mutex> lk(mu_);
+    return pix_;
 }
 
 std::shared_ptr<BucketRenderer> NewBucketRenderer(CameraPtr camera, HittablePtr world, int bucketSize, int numWorkers) {

@@ -650,3 +650,18 @@ def test_bucket_renderer_mirror(grt, orc):
     ref = orc.resolve_rgba8(r["sum"], 32).astype(np.float64)
     a = pix[..., :3].astype(np.float64)
     assert abs(a.mean() - ref[..., :3].mean()) < 4.0         # 8-bit gamma-encoded levels
+
+
+def test_bucket_renderer_update_never_blocks(grt, orc):
+    """Update() is the display loop's tick (rt/bucket_renderer.go:127-164) and must not wait for a pass —
+    the reference renders in goroutines and polls `passComplete`. A pass long enough to be observed (cornell-lucy, 1200x675,
+    48 spp final pass) is ticked at ~2 kHz: many ticks return while passes run, the 1-spp preview and the quarter-spp pass are
+    visible in the framebuffer before the final one, and the final image equals the blocking helper's."""
+    sc = grt.config_scene("cornell-lucy", spp=48, depth=50)
+    pix, ticks, frames = sc.bucket_render_progressive(seed=4)
+    assert pix.shape == (sc.height, sc.width, 4) and np.all(pix[..., 3] == 255)
+    assert ticks >= 20, f"only {ticks} ticks returned while rendering: Update() blocks"
+    assert frames >= 3, f"{frames} distinct framebuffers seen: the passes are not published progressively"
+    ref, _ = sc.bucket_render(seed=4)
+    # same seeds -> same Philox streams; float32 atomics order may flip the last bit of a few 8-bit pixels
+    assert np.mean(pix != ref) < 0.01 and np.abs(pix.astype(np.int32) - ref.astype(np.int32)).max() <= 2
