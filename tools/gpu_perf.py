@@ -13,7 +13,7 @@ for kv in os.environ.get("RTX_OPTS", "").split(","):
         k, v = kv.split("="); ctx.set_option(k, int(v))
 sc = grt.config_scene(name)
 ctx.load(sc)
-depth = sc.cam.max_depth
+depth = int(os.environ.get('RTX_DEPTH', sc.cam.max_depth))
 for rep in range(2):
     ctx.clear()
     ctx.render_pass(spp, depth, seed=7 + rep)
