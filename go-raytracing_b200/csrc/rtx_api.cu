@@ -432,6 +432,8 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     std::vector<double> perlinVec(d->n_perlin > 0 ? d->perlin_vec : nullptr, d->n_perlin > 0 ? d->perlin_vec + (size_t)768 * d->n_perlin : nullptr);
     std::vector<int> perlinPerm(d->n_perlin > 0 ? d->perlin_perm : nullptr, d->n_perlin > 0 ? d->perlin_perm + (size_t)768 * d->n_perlin : nullptr);
 
+    std::vector<int4> flatSimple;   // filled after the entries are known
+    std::vector<int> flatComplex;
     std::vector<float4> imgRgb;
     std::vector<int4> imgDim(d->n_images);
     for (int i = 0; i < d->n_images; i++) {
@@ -632,6 +634,13 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
         }
         for (int e = 0; e < d->n_entries; e++) entries[e].rank = ranks[e];
     }
+    // the flat kernels' lists: bare primitives (inlined tests) and everything else (generic entry test); empty lists are skipped
+    for (int e = 0; e < d->n_entries; e++) {
+        const DEntry& E = entries[e];
+        if (E.kind == RTX_GEOM_MESH || (E.kind == RTX_GEOM_LIST && E.b == 0)) continue;
+        if (E.kind != RTX_GEOM_LIST && (E.xf_count & 0xffff) == 0 && E.volume < 0) flatSimple.push_back(make_int4(E.kind, E.index, e, E.rank));
+        else flatComplex.push_back(e);
+    }
     // ---- TLAS over bounded entries; unbounded ones (planes) are tested for every ray
     std::vector<int> unbounded, boundedIdx;
     std::vector<Box> tb;
@@ -728,7 +737,7 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
         const size_t geom = std::max<size_t>(bNodes + bTris + bSph + bQuads, 256);
         WANT(entries, S.entries); WANT(unbounded, S.unbounded); WANT(sphMat, S.sph_mat); WANT(quadMat, S.quad_mat); WANT(planes, S.planes); WANT(planeMat, S.plane_mat);
         WANT(circles, S.circles); WANT(circleMat, S.circle_mat); WANT(perlinVec, S.perlin_vec); WANT(perlinPerm, S.perlin_perm);
-        WANT(imgRgb, S.img_rgb); WANT(imgDim, S.img_dim);
+        WANT(imgRgb, S.img_rgb); WANT(imgDim, S.img_dim); WANT(flatSimple, S.flat_simple); WANT(flatComplex, S.flat_complex);
         WANT(listItems, S.list_items); WANT(xfs, S.xforms); WANT(xfCanon, S.xf_canon); WANT(vols, S.volumes); WANT(mats, S.mats); WANT(texs, S.texs);
         WANT(lights, S.light_quads); WANT(envTex, S.env_tex); WANT(marg, S.env_marg); WANT(cond, S.env_cond); WANT(pdf, S.env_pdf);
 #undef WANT
@@ -777,6 +786,7 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     S.n_unbounded = (int)unbounded.size();
     S.n_lights = d->n_lights;
     S.n_images = d->n_images;
+    S.n_flat_simple = (int)flatSimple.size(); S.n_flat_complex = (int)flatComplex.size();
     S.vol_draws = d->world_is_bvh ? 2 : 1;
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->ms_upload_blas = 0;

@@ -87,6 +87,9 @@ struct DevScene {
     const int* circle_mat;
     const double* perlin_vec;  // [n][256][3] (rt/noise.go:9)
     const int* perlin_perm;    // [n][3][256]
+    const int4* flat_simple;   // world entries that are a bare primitive (no wrapper, no Volume): (kind, primitive, entry, rank) — the flat kernels' fast path
+    const int* flat_complex;   // the other entries (Box lists, wrapped primitives, volumes)
+    int n_flat_simple, n_flat_complex;
     const float4* img_rgb;     // ImageLoader.data of every image, back to back
     const int4* img_dim;       // (width, height, first pixel lo, first pixel hi)
     int n_images;              // > 0: hit records carry (u, v)
@@ -225,6 +228,25 @@ __device__ __forceinline__ double isect_sphere(const double* s, const RayD& r, d
     if (!(tmin < root && root < tmax)) {
         root = (h + sq) / a;
         if (!(tmin < root && root < tmax)) return RTX_NAN_D;
+    }
+    return root;
+}
+// The same with an optionally closed upper end: a sphere found at exactly the current best t must still reach the tie rule
+// (Best::offer) — what Best::tmax_for does with nextafter, without the nextafter.
+__device__ __forceinline__ double isect_sphere_incl(const double* s, const RayD& r, double tmin, double tmax, bool incl) {
+    D3 c = d3(s[0] + r.tm * s[3], s[1] + r.tm * s[4], s[2] + r.tm * s[5]);
+    D3 o = d3(r.ox, r.oy, r.oz), d = d3(r.dx, r.dy, r.dz);
+    D3 oc = sub(c, o);
+    double a = len2(d);
+    double h = dot(d, oc);
+    double cc = len2(oc) - s[6] * s[6];
+    double disc = h * h - a * cc;
+    if (disc < 0) return RTX_NAN_D;
+    double sq = sqrt(disc);
+    double root = (h - sq) / a;
+    if (!(tmin < root && (root < tmax || (incl && root == tmax)))) {
+        root = (h + sq) / a;
+        if (!(tmin < root && (root < tmax || (incl && root == tmax)))) return RTX_NAN_D;
     }
     return root;
 }

@@ -268,14 +268,42 @@ __device__ __forceinline__ void trace_flat(const DevScene& S, Policy& P, int njo
             double tmax;
             P.load(job, r, tmax);
             B.reset(tmax);
-            for (int ei = 0; ei < S.n_entries; ei++) {
-                const DEntry e = S.entries[ei];
-                if (e.kind == RTX_GEOM_LIST && e.b == 0) continue;
-                VolumeRng vr = {0, 0, 0, 0, 0, true};
-                if (e.volume >= 0) vr = P.volume_rng(job);
-                entry_core(S, ei, e, r, B, tmin, vr, tcp);
+            // bare primitives (the usual case: spheres, walls, the ground plane): the test is inlined and selected by a branch
+            // every lane takes alike; no wrapper chain, no entry record, no out-of-line dispatch
+            for (int k = 0; k < S.n_flat_simple; k++) {
+                const int4 fe = __ldg(S.flat_simple + k);   // kind, primitive, entry, rank
+                const bool incl = B.have;                   // an open-interval primitive may still tie with the current best (Best::tmax_for)
+                double t;
+                if (fe.x == RTX_GEOM_SPHERE) {
+                    if (COUNT) tc.spheres++;
+                    t = isect_sphere_incl(S.spheres + 8 * (size_t)fe.y, r, tmin, B.t, incl);
+                } else if (fe.x == RTX_GEOM_QUAD) {
+                    if (COUNT) tc.quads++;
+                    t = isect_quad(S.quads + 16 * (size_t)fe.y, r, tmin, B.t, nullptr);
+                } else if (fe.x == RTX_GEOM_PLANE) {
+                    if (COUNT) tc.planes++;
+                    t = isect_plane(S.planes + 8 * (size_t)fe.y, r);
+                    if (!(tmin < t && (t < B.t || (incl && t == B.t)))) t = RTX_NAN_D;
+                } else if (fe.x == RTX_GEOM_CIRCLE) {
+                    if (COUNT) tc.quads++;
+                    t = isect_circle(S.circles + 8 * (size_t)fe.y, r, tmin, B.t);
+                } else {
+                    if (COUNT) tc.tris++;
+                    t = isect_tri(S.tris + RTX_TRI_D * (size_t)fe.y, r, nullptr);
+                    if (!(tmin <= t && t <= B.t)) t = RTX_NAN_D;
+                }
+                B.offer(t, fe.z, fe.w, fe.x, fe.y, 0, 0);
                 if (Policy::ANY_HIT && B.have) break;
             }
+            if (!(Policy::ANY_HIT && B.have))
+                for (int k = 0; k < S.n_flat_complex; k++) {
+                    const int ei = S.flat_complex[k];
+                    const DEntry e = S.entries[ei];
+                    VolumeRng vr = {0, 0, 0, 0, 0, true};
+                    if (e.volume >= 0) vr = P.volume_rng(job);
+                    entry_core(S, ei, e, r, B, tmin, vr, tcp);
+                    if (Policy::ANY_HIT && B.have) break;
+                }
         }
         P.retire(valid ? job : -1, valid, r, B);
     }
