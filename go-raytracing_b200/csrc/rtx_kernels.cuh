@@ -64,7 +64,7 @@ struct Ctl {  // device-resident control block of the wavefront loop
 // Radiance never travels with the path: every contribution (environment / emission at the end of a path, next-event
 // estimation when its shadow ray arrives unoccluded) is added where it arises, with float atomics, to the pixel's sum —
 // or, when per-sample moments are requested (parity tests), to a per-sample sum that a final pass squares and folds in.
-#define RTX_REC_BYTES 128      /* [ox oy oz time][dx dy dz (pixel | sample << 32)][throughput rgb, bounce | allowLightHits << 16][-] */
+#define RTX_REC_BYTES 96       /* [ox oy oz time][dx dy dz (pixel | sample << 32)][throughput rgb, bounce | allowLightHits << 16]; packed (128-byte stride: hdri-test -10 %) */
 #define RTX_HIT_BYTES 64       /* [Px Py Pz t][Nx Ny Nz (material | front << 31)] */
 #define RTX_SHADOW_BYTES 96    /* [ox oy oz tmax][dx dy dz (pixel | sample << 32)][contribution rgb, bounce][-] */
 struct Pool {
