@@ -602,10 +602,10 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
         entryBox[e] = xform_box(d, b, E.xf_begin, E.xf_count);
     }
     // canonical [Translate][RotateY][Scale] chains (outermost first) get a one-load record, see xform_ray
-    std::vector<double> xfCanon((size_t)8 * std::max(d->n_entries, 1), 0.0);
+    std::vector<double> xfCanon((size_t)12 * std::max(d->n_entries, 1), 0.0);
     for (int e = 0; e < d->n_entries; e++) {
-        double* q = xfCanon.data() + 8 * (size_t)e;
-        q[0] = q[1] = q[2] = 0; q[3] = 0; q[4] = 1; q[5] = q[6] = q[7] = 1;
+        double* q = xfCanon.data() + 12 * (size_t)e;
+        q[0] = q[1] = q[2] = 0; q[3] = 0; q[4] = 1; q[5] = q[6] = q[7] = 1; q[8] = q[9] = q[10] = 1; q[11] = 0;
         int n = entries[e].xf_count, stage = 0;
         bool canon = n > 0 && n <= 3;
         for (int k = 0; k < n && canon; k++) {
@@ -615,7 +615,10 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
             stage = want + 1;
             if (t == RTX_XF_TRANSLATE) { q[0] = d->xf_a[3 * x]; q[1] = d->xf_a[3 * x + 1]; q[2] = d->xf_a[3 * x + 2]; }
             else if (t == RTX_XF_ROTATE_Y) { q[3] = d->xf_a[3 * x]; q[4] = d->xf_a[3 * x + 1]; }
-            else if (d->xf_b) { q[5] = d->xf_b[3 * x]; q[6] = d->xf_b[3 * x + 1]; q[7] = d->xf_b[3 * x + 2]; }
+            else if (d->xf_b) {
+                q[5] = d->xf_b[3 * x]; q[6] = d->xf_b[3 * x + 1]; q[7] = d->xf_b[3 * x + 2];
+                q[8] = d->xf_a[3 * x]; q[9] = d->xf_a[3 * x + 1]; q[10] = d->xf_a[3 * x + 2]; q[11] = 1;   // Factor, and "a Scale is present"
+            }
             else canon = false;
         }
         if (n > 0xffff) return fail(ctx, RTX_ERR_UNSUPPORTED, "entry %d: transform chain too long", e);

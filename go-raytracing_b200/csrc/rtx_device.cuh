@@ -95,7 +95,7 @@ struct DevScene {
     int n_images;              // > 0: hit records carry (u, v)
     const int2* list_items;  // (kind, device index)
     const DXform* xforms;
-    const double* xf_canon;  // 8 doubles per entry: offset xyz, sin, cos, inverse scale xyz (identity values where an op is absent)
+    const double* xf_canon;  // 12 doubles per entry: offset xyz, sin | cos, inverse scale xyz | scale xyz, has-scale flag (identity values where an op is absent)
     const DVolume* volumes;
     const DMaterial* mats;
     const DTexture* texs;
@@ -181,7 +181,7 @@ __device__ __forceinline__ void xform_ray_chain(const DevScene& S, const DEntry&
 __device__ __forceinline__ void xform_ray(const DevScene& S, int ei, const DEntry& e, RayD& r) {
     if (e.xf_count == 0) return;
     if (e.xf_count & RTX_XF_CANON) {
-        const D4 a = ldg256d(S.xf_canon + 8 * (size_t)ei), b = ldg256d(S.xf_canon + 8 * (size_t)ei + 4);  // (offx,offy,offz,sin) (cos,invx,invy,invz)
+        const D4 a = ldg256d(S.xf_canon + 12 * (size_t)ei), b = ldg256d(S.xf_canon + 12 * (size_t)ei + 4);  // (offx,offy,offz,sin) (cos,invx,invy,invz)
         const double tx = r.ox - a.x, ty = r.oy - a.y, tz = r.oz - a.z;
         const double sn = a.w, cs = b.x;
         const double ox = cs * tx - sn * tz, oz = sn * tx + cs * tz;
@@ -193,7 +193,24 @@ __device__ __forceinline__ void xform_ray(const DevScene& S, int ei, const DEntr
     xform_ray_chain(S, e, r);
 }
 // hit point and normal back to world space, innermost first
-__device__ __forceinline__ void xform_back(const DevScene& S, const DEntry& e, D3& P, D3& N) {
+__device__ __forceinline__ void xform_back_chain(const DevScene& S, const DEntry& e, D3& P, D3& N);
+// Canonical chains ([Translate][RotateY][Scale], see xform_ray): one 96-byte record instead of a loop over op records. Absent
+// Translate / RotateY hold identity values (x + 0, 1 * x + 0 * z: exact); an absent Scale is skipped, because its
+// renormalisation of the normal (rt/transform.go:437) is not an identity in floating point.
+__device__ __forceinline__ void xform_back(const DevScene& S, int ei, const DEntry& e, D3& P, D3& N) {
+    if (!(e.xf_count & RTX_XF_CANON)) { xform_back_chain(S, e, P, N); return; }
+    const D4 a = ldg256d(S.xf_canon + 12 * (size_t)ei), b = ldg256d(S.xf_canon + 12 * (size_t)ei + 4), c = ldg256d(S.xf_canon + 12 * (size_t)ei + 8);
+    if (c.w != 0.0) {   // Scale (innermost): rt/transform.go:430-438
+        P.x *= c.x; P.y *= c.y; P.z *= c.z;
+        N = unit(d3(N.x * b.y, N.y * b.z, N.z * b.w));
+    }
+    const double sn = a.w, cs = b.x;   // RotateY: rt/transform.go:176-184
+    const double px = cs * P.x + sn * P.z, pz = -sn * P.x + cs * P.z;
+    const double nx = cs * N.x + sn * N.z, nz = -sn * N.x + cs * N.z;
+    P.x = px; P.z = pz; N.x = nx; N.z = nz;
+    P.x += a.x; P.y += a.y; P.z += a.z;   // Translate: rt/transform.go:99
+}
+__device__ __forceinline__ void xform_back_chain(const DevScene& S, const DEntry& e, D3& P, D3& N) {
     for (int k = RTX_XF_COUNT(e) - 1; k >= 0; k--) {
         const DXform& x = S.xforms[e.xf_begin + k];
         if (x.type == RTX_XF_TRANSLATE) {
@@ -451,6 +468,6 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const RayD& rw, 
     }
     out.front = dot(d, n) < 0;  // SetFaceNormal with the object-space ray (rt/hittable.go:20-30); never recomputed afterwards
     if (!out.front) n = d3(-n.x, -n.y, -n.z);
-    if (e.xf_count) xform_back(S, e, P, n);
+    if (e.xf_count) xform_back(S, h.entry, e, P, n);
     out.P = P; out.N = n;
 }
