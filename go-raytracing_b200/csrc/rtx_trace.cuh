@@ -591,9 +591,16 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                     for (int q = 0; q < S.n_unbounded; q++) {
                         const int ei = S.unbounded[q];
                         const DEntry e = S.entries[ei];
-                        RayD ro = r;
-                        xform_ray(S, ei, e, ro);
-                        B.test_prim(S, e.kind, e.index, ro, tmin, ei, e.rank, 0, 0, tcp);
+                        if (e.xf_count == 0) {   // the bare ground plane of RandomScene / HDRITestScene: inlined
+                            if (COUNT) tc.planes++;
+                            double t = isect_plane(S.planes + 8 * (size_t)e.index, r);
+                            if (!(tmin < t && (t < B.t || (B.have && t == B.t)))) t = RTX_NAN_D;
+                            B.offer(t, ei, e.rank, RTX_GEOM_PLANE, e.index, 0, 0);
+                        } else {
+                            RayD ro = r;
+                            xform_ray(S, ei, e, ro);
+                            B.test_prim(S, e.kind, e.index, ro, tmin, ei, e.rank, 0, 0, tcp);
+                        }
                     }
                     int node;
                     if ((Policy::ANY_HIT && B.have) || S.tlas_root < 0) node = RTX_ST_DONE;
