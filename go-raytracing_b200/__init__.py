@@ -159,6 +159,7 @@ def host() -> C.CDLL:
         H.rth_bucket_render_progressive.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         H.rth_load_hdr.argtypes = [C.c_char_p, _pi, _pi, C.c_void_p, C.c_int64]
         H.rth_write_png.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_int32]
+        H.rth_parse_obj.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, _pd]
         _host_cache = H
     return _host_cache
 
@@ -670,6 +671,20 @@ CONFIGS.update({
     "earth": dict(scene="earth", width=800, aspect=16.0 / 9.0, spp=100, depth=50),
     "primitives": dict(scene="primitives", width=800, aspect=16.0 / 9.0, spp=300, depth=25),
 })
+
+
+def parse_obj(path: str, threads: int = 0):
+    """The text parse of the host mirror's LoadOBJ (rt/obj_loader.go:15-102) on `threads` threads (0 = all, 1 = the reference's
+    sequential scan): (vertices [n, 3] float64, triangle vertex indices [m, 3] uint32, seconds). Raises RuntimeError with the
+    reference's message on malformed input."""
+    H = host()
+    nv, nt, sec = C.c_int64(0), C.c_int64(0), C.c_double(0)
+    if H.rth_parse_obj(path.encode(), threads, C.byref(nv), C.byref(nt), None, 0, None, 0, C.byref(sec)) != 0:
+        raise RuntimeError(H.rth_last_error().decode())
+    v, t = np.zeros((nv.value, 3), np.float64), np.zeros((nt.value, 3), np.uint32)
+    if H.rth_parse_obj(path.encode(), threads, C.byref(nv), C.byref(nt), v.ctypes.data, nv.value, t.ctypes.data, nt.value, C.byref(sec)) != 0:
+        raise RuntimeError(H.rth_last_error().decode())
+    return v, t, sec.value
 
 
 def config_scene(name: str, width: Optional[int] = None, spp: Optional[int] = None, depth: Optional[int] = None, seed: int = 0x5EED) -> NamedScene:

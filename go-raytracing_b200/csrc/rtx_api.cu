@@ -48,6 +48,9 @@ struct rtx_ctx {
     uchar4* rgba_dev = nullptr;   // resolve target, sized with the accumulation buffer
     cudaStream_t stream = nullptr;      // stream in use
     cudaStream_t own_stream = nullptr;  // created by rtx_create
+    cudaStream_t connect_stream = nullptr;   // k_connect of iteration i runs here, beside generate / extend / shade of iteration i + 1
+    cudaEvent_t ev_shaded = nullptr, ev_connected[2] = {nullptr, nullptr};
+    int overlap_connect = 1;
     std::string err;
     DevScene S{};
     bool have_scene = false, have_camera = false;
@@ -77,6 +80,7 @@ struct rtx_ctx {
     int num_sms = 0;
     int* batch_cursor = nullptr;  // job cursor of k_trace_closest
     int* trace_spill = nullptr;   // global overflow columns of the trace kernels' shared-memory stacks
+    int* trace_spill2 = nullptr;  // the same for k_connect (it may run beside k_extend)
     int trace_grid = 0;           // persistent grid: SMs x resident blocks
     void* geom_arena = nullptr;   // nodes + triangles + spheres + quads in one allocation: the L2 persisting window
     size_t geom_bytes = 0;
@@ -146,13 +150,24 @@ int32_t rtx_create(int32_t device_id, rtx_ctx** out) {
     if (device_id < 0 || device_id >= n) return fail(nullptr, RTX_ERR_INVALID, "rtx_create: device %d out of range [0,%d)", device_id, n);
     rtx_ctx* ctx = new rtx_ctx();
     ctx->device = device_id;
-    if ((e = cudaSetDevice(device_id)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+    int prLo = 0, prHi = 0;
+    cudaSetDevice(device_id);
+    cudaDeviceGetStreamPriorityRange(&prLo, &prHi);   // numerically lower = higher priority
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess || (e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prHi)) != cudaSuccess ||
         (e = cudaMalloc((void**)&ctx->ctl, sizeof(Ctl))) != cudaSuccess || (e = cudaMallocHost((void**)&ctx->ctl_host, sizeof(Ctl))) != cudaSuccess) {
         fail(nullptr, RTX_ERR_CUDA, "rtx_create: %s", cudaGetErrorString(e));
         delete ctx;
         return RTX_ERR_CUDA;
     }
     ctx->own_stream = ctx->stream;
+    if ((e = cudaStreamCreateWithPriority(&ctx->connect_stream, cudaStreamNonBlocking, prLo)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_shaded, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_connected[0], cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_connected[1], cudaEventDisableTiming)) != cudaSuccess) {
+        fail(nullptr, RTX_ERR_CUDA, "rtx_create: %s", cudaGetErrorString(e));
+        rtx_destroy(ctx);
+        return RTX_ERR_CUDA;
+    }
     cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device_id);
     if (ctx->num_sms <= 0 || cudaMalloc((void**)&ctx->batch_cursor, sizeof(int)) != cudaSuccess) {
         fail(nullptr, RTX_ERR_CUDA, "rtx_create: device query / allocation failed");
@@ -181,7 +196,8 @@ int32_t rtx_create(int32_t device_id, rtx_ctx** out) {
         ctx->trace_grid = ctx->num_sms * minOcc;
         if (getenv("RTX_DEBUG_BATCH")) fprintf(stderr, "[rtx] trace kernels: %d blocks/SM, %d B dynamic smem per block, grid %d\n", minOcc, smem, ctx->trace_grid);
         size_t spillInts = (size_t)ctx->trace_grid * RTX_TRACE_SLOTS * (RTX_STACK_SIZE - RTX_SMEM_STACK);
-        if ((e = cudaMalloc((void**)&ctx->trace_spill, spillInts * sizeof(int))) != cudaSuccess) {
+        if ((e = cudaMalloc((void**)&ctx->trace_spill, spillInts * sizeof(int))) != cudaSuccess ||
+            (e = cudaMalloc((void**)&ctx->trace_spill2, spillInts * sizeof(int))) != cudaSuccess) {
             fail(nullptr, RTX_ERR_CUDA, "rtx_create: %s", cudaGetErrorString(e));
             rtx_destroy(ctx);
             return RTX_ERR_CUDA;
@@ -213,6 +229,10 @@ int32_t rtx_destroy(rtx_ctx* ctx) {
     if (ctx->ctl) cudaFree(ctx->ctl);
     if (ctx->batch_cursor) cudaFree(ctx->batch_cursor);
     if (ctx->trace_spill) cudaFree(ctx->trace_spill);
+    if (ctx->trace_spill2) cudaFree(ctx->trace_spill2);
+    if (ctx->ev_shaded) cudaEventDestroy(ctx->ev_shaded);
+    for (auto ev : ctx->ev_connected) if (ev) cudaEventDestroy(ev);
+    if (ctx->connect_stream) cudaStreamDestroy(ctx->connect_stream);
     if (ctx->ctl_host) cudaFreeHost(ctx->ctl_host);
     for (auto ev : ctx->events) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -231,6 +251,7 @@ int32_t rtx_set_option(rtx_ctx* ctx, const char* key, int64_t value) {
     else if (k == "time_kernels") ctx->time_kernels = value != 0;
     else if (k == "l2_persist") { ctx->l2_persist = value != 0; ctx->window_set = false; }  // L2 persisting window over the scene geometry (default off)
     else if (k == "pixel_major") ctx->pixel_major = value != 0;
+    else if (k == "overlap_connect") ctx->overlap_connect = value != 0;   // k_connect on its own stream beside the next iteration (default on)
     else if (k == "flat_max_entries") {   // 0 = always traverse the hierarchy
         if (value < 0 || value > 64) return fail(ctx, RTX_ERR_INVALID, "flat_max_entries must be in 0..64");
         ctx->flat_max_entries = (int)value;
@@ -933,7 +954,7 @@ static int32_t ensure_pool(rtx_ctx* ctx) {
     CU(alloc((void**)&p.rec[1], P * RTX_REC_BYTES));
     CU(alloc((void**)&p.hit, P * RTX_HIT_BYTES));
     CU(alloc((void**)&p.q_mat, (size_t)Q_COUNT * P * sizeof(int)));
-    CU(alloc((void**)&p.shadow, 2 * P * RTX_SHADOW_BYTES));
+    CU(alloc((void**)&p.shadow, 2 * 2 * P * RTX_SHADOW_BYTES));   // two halves by iteration parity
     p.capacity = (int)P;
     ctx->pool = p;
     return RTX_OK;
@@ -1010,13 +1031,25 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
     // fixed grids: the stream kernels stride over device-side counts, the trace kernels are persistent (one resident wave of
     // warps pulls rays from a device-side cursor); the host only polls the control block every BATCH iterations
     const int gridStream = std::min((P + 255) / 256, ctx->num_sms * 8), gridTrace = ctx->trace_grid;
+    // The shadow rays of iteration i only feed the accumulation buffer, so k_connect(i) runs on a second stream beside
+    // k_generate / k_extend / k_shade of iteration i + 1: its blocks move in as the persistent k_extend blocks of the next
+    // iteration drain (the tail of a persistent launch otherwise leaves SMs idle), and the render stream has the higher
+    // priority, so the critical chain extend -> shade -> extend is served first. Shadow requests, their count and the job
+    // cursor are double-buffered by iteration parity; iteration i + 2 waits for k_connect(i).
+    const bool overlap = ctx->overlap_connect && ctx->S.n_lights > 0;
+    cudaStream_t sc = overlap ? ctx->connect_stream : st;
+    int* const spillC = overlap ? ctx->trace_spill2 : ctx->trace_spill;
+    bool pending[2] = {false, false};
     long long iter = 0;
     for (;;) {
         int used = 0;
         for (int b = 0; b < BATCH; b++, iter++) {
             const int cur = (int)(iter & 1);   // rec[cur]: this iteration's paths; rec[cur ^ 1]: where k_shade writes the survivors
             cudaEvent_t* ev = timing ? &ctx->events[4 + (size_t)b * EV_KINDS * 2] : nullptr;
-            k_iter_begin<<<1, 32, 0, st>>>(ctx->ctl, P);
+            if (pending[cur]) { CU(cudaStreamWaitEvent(st, ctx->ev_connected[cur], 0)); pending[cur] = false; }
+            Pool poolI = pool;
+            poolI.shadow = pool.shadow + (size_t)cur * 2 * (size_t)P * RTX_SHADOW_BYTES;
+            k_iter_begin<<<1, 32, 0, st>>>(ctx->ctl, P, cur);
             if (timing) cudaEventRecord(ev[0], st);
             k_generate<<<gridStream, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->C, pp);
             if (timing) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
@@ -1029,20 +1062,26 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
             } else if (ctx->count_stats & 1) k_extend<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
             else k_extend<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
             if (timing) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); }
-            k_shade<<<std::min((P + 255) / 256, ctx->num_sms * 2 * RTX_SHADE_BLOCKS), 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, ctx->C, pp);
-            if (timing) { cudaEventRecord(ev[5], st); cudaEventRecord(ev[6], st); }
+            k_shade<<<std::min((P + 255) / 256, ctx->num_sms * 2 * RTX_SHADE_BLOCKS), 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+            if (timing) cudaEventRecord(ev[5], st);
             if (ctx->S.n_lights > 0) {
+                if (overlap) { CU(cudaEventRecord(ctx->ev_shaded, st)); CU(cudaStreamWaitEvent(sc, ctx->ev_shaded, 0)); }
+                if (timing) cudaEventRecord(ev[6], sc);
                 if (ctx->scene_flat) {
-                    if (ctx->count_stats & 2) k_connect_flat<true><<<gridStream, 256, 0, st>>>(ctx->ctl, pool, ctx->S, pp);
-                    else k_connect_flat<false><<<gridStream, 256, 0, st>>>(ctx->ctl, pool, ctx->S, pp);
-                } else if (ctx->count_stats & 2) k_connect<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, ctx->S, pp, ctx->trace_spill);
-                else k_connect<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, ctx->S, pp, ctx->trace_spill);
+                    if (ctx->count_stats & 2) k_connect_flat<true><<<gridStream, 256, 0, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp);
+                    else k_connect_flat<false><<<gridStream, 256, 0, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp);
+                } else if (ctx->count_stats & 2) k_connect<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
+                else k_connect<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
+                if (timing) cudaEventRecord(ev[7], sc);
+                if (overlap) { CU(cudaEventRecord(ctx->ev_connected[cur], sc)); pending[cur] = true; }
                 launches++;
-            }
-            if (timing) cudaEventRecord(ev[7], st);
+            } else if (timing) { cudaEventRecord(ev[6], st); cudaEventRecord(ev[7], st); }
             launches += 4;
             used++;
         }
+        // join: the control block read below must include the connect kernels of this batch (statistics, timing events)
+        for (int c = 0; c < 2; c++)
+            if (pending[c]) { CU(cudaStreamWaitEvent(st, ctx->ev_connected[c], 0)); pending[c] = false; }
         CU(cudaMemcpyAsync(ctx->ctl_host, ctx->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (timing)
@@ -1054,7 +1093,7 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
                 }
         if (getenv("RTX_DEBUG_BATCH"))
             fprintf(stderr, "[rtx] iter %lld: ms gen/ext/shade/conn %.2f/%.2f/%.2f/%.2f active %d next %d shadow %d cursor %llu\n", iter, msKind[0], msKind[1],
-                    msKind[2], msKind[3], ctx->ctl_host->n_active, ctx->ctl_host->n_next, ctx->ctl_host->n_shadow, ctx->ctl_host->cursor);
+                    msKind[2], msKind[3], ctx->ctl_host->n_active, ctx->ctl_host->n_next, ctx->ctl_host->n_shadow[0], ctx->ctl_host->cursor);
         if (ctx->ctl_host->done) break;
     }
     if (spp > 0) {

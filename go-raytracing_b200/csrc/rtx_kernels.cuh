@@ -47,10 +47,11 @@ struct DevCamera {  // post-Initialize state (rt/camera.go:41-56)
 struct Ctl {  // device-resident control block of the wavefront loop
     unsigned long long cursor, total;  // next path id / paths of this pass
     unsigned long long gen_base;
-    int n_active, n_cont, n_gen, n_next, n_shadow;
+    int n_active, n_cont, n_gen, n_next;
+    int n_shadow[2];   // by iteration parity: k_connect of iteration i may still run while iteration i + 1 is generated, extended and shaded
     int n_mat[Q_COUNT];
     int done, pad;
-    int cur_extend, cur_connect;  // job cursors of the persistent trace kernels
+    int cur_extend, cur_connect[2];  // job cursors of the persistent trace kernels (k_connect: by iteration parity)
     // statistics
     unsigned long long ext_rays, shadow_rays, nodes, tris, spheres, quads, planes, iterations;
 };
@@ -106,7 +107,7 @@ __device__ __forceinline__ int warp_append(int* counter, bool pred) {
 }
 
 // ---- K0: iteration bookkeeping ---------------------------------------------------------------------------------
-__global__ void k_iter_begin(Ctl* ctl, int capacity) {
+__global__ void k_iter_begin(Ctl* ctl, int capacity, int par) {
     if (threadIdx.x != 0) return;
     int n_cont = ctl->n_next;   // survivors: records [0, n_cont) of the buffer k_shade just wrote
     unsigned long long remaining = ctl->total - ctl->cursor;
@@ -116,8 +117,8 @@ __global__ void k_iter_begin(Ctl* ctl, int capacity) {
     ctl->n_cont = n_cont;
     ctl->n_gen = n_gen;
     ctl->n_active = n_cont + n_gen;
-    ctl->n_next = 0; ctl->n_shadow = 0;
-    ctl->cur_extend = 0; ctl->cur_connect = 0;
+    ctl->n_next = 0; ctl->n_shadow[par] = 0;
+    ctl->cur_extend = 0; ctl->cur_connect[par] = 0;
     for (int i = 0; i < Q_COUNT; i++) ctl->n_mat[i] = 0;
     ctl->done = (n_cont + n_gen == 0);
     ctl->iterations += (n_cont + n_gen != 0);
@@ -573,14 +574,14 @@ __global__ void __launch_bounds__(256, RTX_SHADE_BLOCKS) k_shade(Ctl* ctl, Pool 
         *reinterpret_cast<float4*>(out + 64) = th;
     }
     {   // shadow requests carry everything k_connect needs (origin = the hit point, where the contribution goes)
-        int sp = warp_append(&ctl->n_shadow, has_env);
+        int sp = warp_append(&ctl->n_shadow[cur], has_env);
         if (has_env) {
             char* q = pool.shadow + (size_t)sp * RTX_SHADOW_BYTES;
             st256d(q, P.x, P.y, P.z, RTX_INF_D);
             st256d(q + 32, env_dir.x, env_dir.y, env_dir.z, pixbits);
             *reinterpret_cast<float4*>(q + 64) = make_float4(env_c.x, env_c.y, env_c.z, __int_as_float(bounce0));
         }
-        sp = warp_append(&ctl->n_shadow, has_area);
+        sp = warp_append(&ctl->n_shadow[cur], has_area);
         if (has_area) {
             char* q = pool.shadow + (size_t)sp * RTX_SHADOW_BYTES;
             st256d(q, P.x, P.y, P.z, area_tmax);
@@ -622,20 +623,20 @@ struct ConnectPolicy {
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_connect(Ctl* ctl, Pool pool, const __grid_constant__ DevScene S, PassParams pp, int* spill) {
+__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_connect(Ctl* ctl, Pool pool, int par, const __grid_constant__ DevScene S, PassParams pp, int* spill) {
     ConnectPolicy P{pool, pp.seed_lo, pp.seed_hi};
     TraceCounters tc = {0, 0, 0, 0, 0};
-    const int n = ctl->n_shadow;
-    trace_persistent<ConnectPolicy, COUNT, RTX_TRACE_SLOTS>(S, P, &ctl->cur_connect, n, tc, spill, rtx_smem);
+    const int n = ctl->n_shadow[par];
+    trace_persistent<ConnectPolicy, COUNT, RTX_TRACE_SLOTS>(S, P, &ctl->cur_connect[par], n, tc, spill, rtx_smem);
     if (COUNT) flush_counters(ctl, tc);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->shadow_rays, (unsigned long long)n);
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(256) k_connect_flat(Ctl* ctl, Pool pool, const __grid_constant__ DevScene S, PassParams pp) {
+__global__ void __launch_bounds__(256) k_connect_flat(Ctl* ctl, Pool pool, int par, const __grid_constant__ DevScene S, PassParams pp) {
     ConnectPolicy P{pool, pp.seed_lo, pp.seed_hi};
     TraceCounters tc = {0, 0, 0, 0, 0};
-    const int n = ctl->n_shadow;
+    const int n = ctl->n_shadow[par];
     trace_flat<ConnectPolicy, COUNT>(S, P, n, tc);
     if (COUNT) flush_counters(ctl, tc);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->shadow_rays, (unsigned long long)n);

@@ -364,75 +364,7 @@ BVHNodePtr NewBVHNode(const std::vector<HittablePtr>& objects, size_t start, siz
 }
 BVHNodePtr NewBVHNodeFromList(const HittableListPtr& list) { return NewBVHNode(list->Objects, 0, list->Objects.size()); }
 
-// ---- rt/obj_loader.go ------------------------------------------------------------------------------------
-HittablePtr LoadOBJ(const std::string& filename, MaterialPtr material) {
-    const auto t0 = std::chrono::steady_clock::now();
-    FILE* f = std::fopen(filename.c_str(), "rb");
-    if (!f) throw std::runtime_error("failed to open OBJ file: " + filename);
-    std::vector<Point3> vertices;
-    std::vector<HittablePtr> triangles;
-    std::vector<char> line(1 << 16);
-    std::vector<long> indices;
-    int lineNum = 0;
-    while (std::fgets(line.data(), (int)line.size(), f)) {
-        lineNum++;
-        char* p = line.data();
-        while (*p == ' ' || *p == '\t') p++;
-        if (*p == 0 || *p == '\n' || *p == '\r' || *p == '#') continue;
-        if (p[0] == 'v' && (p[1] == ' ' || p[1] == '\t')) {
-            char* e;
-            double x = std::strtod(p + 1, &e);
-            char* e2;
-            double y = std::strtod(e, &e2);
-            char* e3;
-            double z = std::strtod(e2, &e3);
-            if (e == p + 1 || e2 == e || e3 == e2) {
-                std::fclose(f);
-                throw std::runtime_error("invalid vertex at line " + std::to_string(lineNum));
-            }
-            vertices.push_back({x, y, z});
-        } else if (p[0] == 'f' && (p[1] == ' ' || p[1] == '\t')) {
-            indices.clear();
-            char* q = p + 1;
-            while (true) {
-                while (*q == ' ' || *q == '\t') q++;
-                if (*q == 0 || *q == '\n' || *q == '\r') break;
-                char* e;
-                long idx = std::strtol(q, &e, 10);
-                if (e == q) {
-                    std::fclose(f);
-                    throw std::runtime_error("invalid face index at line " + std::to_string(lineNum));
-                }
-                if (idx < 0) idx = (long)vertices.size() + idx + 1;  // negative = from the end
-                indices.push_back(idx - 1);
-                while (*e && *e != ' ' && *e != '\t' && *e != '\n' && *e != '\r') e++;  // skip /vt/vn
-                q = e;
-            }
-            if (indices.size() < 3) continue;
-            for (size_t i = 1; i + 1 < indices.size(); i++) {  // fan triangulation, rt/obj_loader.go:79-97
-                long i0 = indices[0], i1 = indices[i], i2 = indices[i + 1];
-                long nv = (long)vertices.size();
-                if (i0 < 0 || i0 >= nv || i1 < 0 || i1 >= nv || i2 < 0 || i2 >= nv) {
-                    std::fclose(f);
-                    throw std::runtime_error("vertex index out of bounds at line " + std::to_string(lineNum));
-                }
-                triangles.push_back(NewTriangle(vertices[i0], vertices[i1], vertices[i2], material));
-            }
-        }
-    }
-    std::fclose(f);
-    const auto t1 = std::chrono::steady_clock::now();
-    HittablePtr root = NewBVHNode(triangles, 0, triangles.size());
-    if (std::getenv("RT_DEBUG_TIMING"))
-        std::fprintf(stderr, "[rt] LoadOBJ %s: parse %.3f s, NewBVHNode %.3f s (%zu triangles)\n", filename.c_str(),
-                     std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count(), triangles.size());
-    return root;
-}
-HittablePtr LoadOBJWithTransform(const std::string& filename, MaterialPtr material, const Transform* transform) {
-    HittablePtr mesh = LoadOBJ(filename, material);
-    if (transform) return transform->Apply(mesh);
-    return mesh;
-}
+// rt/obj_loader.go: rt_obj.cpp (parallel text parse)
 
 // ---- rt/image_loader.go:122-383 -----------------------------------------------------------------------------
 static bool fileExists(const std::string& p) {

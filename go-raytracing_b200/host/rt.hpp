@@ -263,7 +263,9 @@ struct Transform {  // rt/transform.go:9-71
 };
 inline Transform NewTransform() { return Transform{}; }
 
-HittablePtr LoadOBJ(const std::string& filename, MaterialPtr material);  // rt/obj_loader.go:15 (throws on error)
+HittablePtr LoadOBJ(const std::string& filename, MaterialPtr material);  // rt/obj_loader.go:15 (throws on error); rt_obj.cpp
+// the text parse of LoadOBJ on `threads` threads (0 = all, 1 = the reference's sequential scan): vertices and 3 vertex indices per triangle, file order
+void ParseOBJ(const std::string& filename, int threads, std::vector<Point3>& vertices, std::vector<uint32_t>& tri_indices);
 HittablePtr LoadOBJWithTransform(const std::string& filename, MaterialPtr material, const Transform* transform);
 
 // ---- rt/image_loader.go (HDR part) + rt/hdri.go (state only; the distribution is built by the library) --

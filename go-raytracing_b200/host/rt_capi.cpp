@@ -120,6 +120,26 @@ int32_t rth_load_hdr(const char* path, int32_t* w, int32_t* h, double* rgb_out, 
     return RTX_OK;
 }
 
+// ParseOBJ for tests and timing: counts always, arrays when the capacities suffice. seconds = wall time of the parse alone.
+int32_t rth_parse_obj(const char* path, int32_t threads, int64_t* n_vertices, int64_t* n_triangles, double* vertices_out, int64_t vcap,
+                      uint32_t* indices_out, int64_t tcap, double* seconds) {
+    try {
+        std::vector<Point3> v;
+        std::vector<uint32_t> idx;
+        const auto t0 = std::chrono::steady_clock::now();
+        ParseOBJ(path, threads, v, idx);
+        if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        *n_vertices = (int64_t)v.size(); *n_triangles = (int64_t)idx.size() / 3;
+        if (vertices_out && vcap >= (int64_t)v.size())
+            for (size_t i = 0; i < v.size(); i++) { vertices_out[3 * i] = v[i].X; vertices_out[3 * i + 1] = v[i].Y; vertices_out[3 * i + 2] = v[i].Z; }
+        if (indices_out && tcap >= (int64_t)idx.size() / 3) std::memcpy(indices_out, idx.data(), idx.size() * sizeof(uint32_t));
+        return RTX_OK;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return RTX_ERR_INVALID;
+    }
+}
+
 int32_t rth_write_png(const char* path, const uint8_t* rgba, int32_t w, int32_t h) { return WritePNG(path, rgba, w, h); }
 
 }  // extern "C"

@@ -142,3 +142,92 @@ def test_png_writer(grt, tmp_path):
     p = str(tmp_path / "t.png")
     assert grt.host().rth_write_png(p.encode(), img.ctypes.data, 7, 5) == 0
     assert np.array_equal(np.asarray(Image.open(p)), img)
+
+
+# ---- LoadOBJ: the parallel text parse gives what the reference's sequential scan gives (rt/obj_loader.go:15-102) ----
+def _write_obj(path, n_blocks, rng, crlf=False, tail=""):
+    """Blocks of 4 vertices followed by faces in every index style the reference accepts; returns (vertices, triangles)."""
+    eol = "\r\n" if crlf else "\n"
+    lines, verts, tris = ["# test mesh", "", "   # indented comment", "o thing", "vn 0 1 0", "vt 0.5 0.5"], [], []
+    for b in range(n_blocks):
+        base = len(verts)
+        for k in range(4):
+            # shortest round-trip, fixed, scientific, integer: the short forms take the parser's exact fast path, repr goes to strtod
+            fmt = ("{!r}", "{:.6f}", "{:+.4e}", "{:.0f}")[(b + k) % 4]
+            toks = [fmt.format(float(c)) for c in rng.normal(size=3) * (10 if k else 1e-3)]
+            lines.append(f"v {toks[0]} {toks[1]}\t{toks[2]}" + (" 1.0" if k == 0 else ""))   # a 4th field (w) is ignored
+            verts.append(tuple(float(t) for t in toks))
+        style = b % 5
+        if style == 0:
+            lines.append(f"f {base + 1} {base + 2} {base + 3}"); tris.append((base, base + 1, base + 2))
+        elif style == 1:   # negative indices count from the vertices read so far
+            lines.append("f -4 -3 -2"); tris.append((base, base + 1, base + 2))
+        elif style == 2:   # v/vt/vn, quad -> fan of two
+            lines.append(f"  f {base + 1}/1/1 {base + 2}/1/1 {base + 3}//1 {base + 4}/1")
+            tris += [(base, base + 1, base + 2), (base, base + 2, base + 3)]
+        elif style == 3:   # reference to a much earlier vertex, mixed signs
+            lines.append(f"f 1 -1 {base + 2}"); tris.append((0, base + 3, base + 1))
+        else:              # fewer than three indices: skipped without a word (rt/obj_loader.go:56-58)
+            lines.append(f"f {base + 1} {base + 2}")
+    with open(path, "w", newline="") as f:
+        f.write(eol.join(lines) + eol + tail)
+    return np.array(verts), np.array(tris, dtype=np.uint32)
+
+
+@pytest.mark.parametrize("crlf", [False, True])
+def test_obj_parse_parallel_equals_sequential(grt, tmp_path, crlf):
+    rng = np.random.default_rng(5)
+    path = str(tmp_path / "m.obj")
+    verts, tris = _write_obj(path, 12000, rng, crlf=crlf, tail="f 1 2 3")   # > 2 MB of text: several chunks; last line without a newline
+    tris = np.vstack([tris, [[0, 1, 2]]]).astype(np.uint32)
+    v1, t1, _ = grt.parse_obj(path, threads=1)
+    assert np.array_equal(v1, verts) and np.array_equal(t1, tris)          # bit-exact doubles (repr round-trips), file order
+    for th in (2, 3, 8):
+        v, t, _ = grt.parse_obj(path, threads=th)
+        assert np.array_equal(v, v1) and np.array_equal(t, t1), th
+
+
+def test_obj_parse_errors_are_the_first_by_line(grt, tmp_path):
+    rng = np.random.default_rng(6)
+    path = str(tmp_path / "e.obj")
+    _write_obj(path, 12000, rng)
+    text = open(path).read().split("\n")
+    n = len(text)
+
+    def run(edit):
+        t = list(text)
+        for line, s in edit.items():
+            t[line - 1] = s
+        p = str(tmp_path / "e2.obj")
+        open(p, "w").write("\n".join(t))
+        msgs = set()
+        for th in (1, 8):
+            with pytest.raises(RuntimeError) as e:
+                grt.parse_obj(p, threads=th)
+            msgs.add(str(e.value))
+        assert len(msgs) == 1, msgs
+        return msgs.pop()
+
+    late, early = n - 100, 200
+    assert run({late: "v 1.0 2.0"}) == f"invalid vertex at line {late}"
+    assert run({late: "v 1.0 2.0 3.0x"}) == f"invalid vertex coordinates at line {late}"
+    assert run({late: "f 1 2 x3"}) == f"invalid face index at line {late}"
+    assert run({early: f"f 1 2 {10 ** 6}"}) == f"vertex index out of bounds at line {early}"
+    # a face may only use vertices that precede it in the file (the bounds check runs against the vertices read so far)
+    assert run({early: "f 1 2 40000"}) == f"vertex index out of bounds at line {early}"
+    assert run({early: "f 1 2 -100000"}) == f"vertex index out of bounds at line {early}"
+    # two errors in different chunks: the earlier line wins, whichever kind it is
+    assert run({early: "f 1 2 40000", late: "v oops 1 2"}) == f"vertex index out of bounds at line {early}"
+    assert run({early: "v oops 1 2", late: "f 1 2 40000"}) == f"invalid vertex coordinates at line {early}"
+    with pytest.raises(RuntimeError, match="failed to open OBJ file"):
+        grt.parse_obj(str(tmp_path / "missing.obj"))
+
+
+def test_obj_parse_of_the_benchmark_mesh(grt):
+    import make_assets
+    make_assets.ensure_assets()
+    path = os.path.join(ROOT, "assets", "models", "lucy_standin.obj")
+    v1, t1, s1 = grt.parse_obj(path, threads=1)
+    v8, t8, s8 = grt.parse_obj(path, threads=0)
+    assert len(t1) >= 270000 and np.array_equal(v1, v8) and np.array_equal(t1, t8)
+    print(f"lucy stand-in: {len(v1)} vertices, {len(t1)} triangles; parse {s1 * 1e3:.0f} ms on 1 thread, {s8 * 1e3:.0f} ms on all")
