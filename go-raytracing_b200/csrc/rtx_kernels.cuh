@@ -400,22 +400,47 @@ __device__ __forceinline__ D3 unit_sphere(uint32_t a, uint32_t b) {
 }
 
 // ---- K4: shade — one thread per queue element, queues concatenated in material order --------------------------------
+#ifndef RTX_SHADE_PREFETCH
+#define RTX_SHADE_PREFETCH 1
+#endif
 #ifndef RTX_SHADE_BLOCKS
 #define RTX_SHADE_BLOCKS 2   /* resident 256-thread blocks per SM k_shade is compiled for */
 #endif
 __global__ void __launch_bounds__(256, RTX_SHADE_BLOCKS) k_shade(Ctl* ctl, Pool pool, int cur, DevScene S, DevCamera C, PassParams pp) {
   const int n_rounded = (ctl->n_active + 31) & ~31;   // whole warps stay together for the queue appends
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rounded; i += gridDim.x * blockDim.x) {
-    // locate (queue, index): prefix over the six queue counts
-    int type = -1, idx = i;
+  int nq[Q_COUNT];
 #pragma unroll
-    for (int k = 0; k < Q_COUNT; k++) {
-        int c = ctl->n_mat[k];
-        if (type < 0) {
-            if (idx < c) type = k;
-            else idx -= c;
+  for (int k = 0; k < Q_COUNT; k++) nq[k] = ctl->n_mat[k];
+  // (queue, job) of element i of the concatenated queues: prefix over the six queue counts
+  auto locate = [&](int i, int& type) {
+      type = -1;
+      int idx = i;
+#pragma unroll
+      for (int k = 0; k < Q_COUNT; k++)
+          if (type < 0) {
+              if (idx < nq[k]) type = k;
+              else idx -= nq[k];
+          }
+      return type >= 0 ? pool.q_mat[(size_t)type * pool.capacity + idx] : -1;
+  };
+  const int stride = gridDim.x * blockDim.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int type_next = -1;
+  int job_next = i < n_rounded ? locate(i, type_next) : -1;
+  for (; i < n_rounded; i += stride) {
+    const int type = type_next, job_cur = job_next;
+    // software pipeline: the records of this thread's NEXT element are gathers through the queue (two dependent hops); its
+    // queue slot is read now and its record lines are prefetched into L1 while this element is shaded
+    job_next = -1; type_next = -1;
+    if (RTX_SHADE_PREFETCH && i + stride < n_rounded) {
+        job_next = locate(i + stride, type_next);
+        if (job_next >= 0) {
+            const char* nrec = pool.records(cur) + (size_t)job_next * RTX_REC_BYTES;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nrec));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nrec + 64));
+            if (type_next != Q_MISS) asm volatile("prefetch.global.L1 [%0];" ::"l"(pool.hit + (size_t)job_next * RTX_HIT_BYTES));
         }
-    }
+    } else if (i + stride < n_rounded) job_next = locate(i + stride, type_next);
     bool valid = type >= 0;
     bool cont = false;
     // the path's next record (written only if it survives) and, for the shadow requests, its identity and hit point
@@ -429,7 +454,7 @@ __global__ void __launch_bounds__(256, RTX_SHADE_BLOCKS) k_shade(Ctl* ctl, Pool 
     double area_tmax = 0;
     float3 env_c = make_float3(0, 0, 0), area_c = make_float3(0, 0, 0);
     if (valid) {
-        const int job = pool.q_mat[(size_t)type * pool.capacity + idx];
+        const int job = job_cur;
         const char* rec = pool.records(cur) + (size_t)job * RTX_REC_BYTES;
         const D4 ro4 = ld256d(rec), rd4 = ld256d(rec + 32);
         D3 rd = d3(rd4.x, rd4.y, rd4.z);
