@@ -122,6 +122,9 @@ struct Best {
 #ifndef RTX_E_BARE_FAST
 #define RTX_E_BARE_FAST 2   /* ENTRY phase fast path: 0 off, 1 bare quads only, 2 every bare primitive */
 #endif
+#ifndef RTX_E_ROOT_STEP
+#define RTX_E_ROOT_STEP 1   /* ENTRY of a mesh instance tests the BLAS root's children before committing to the instance */
+#endif
 #define RTX_PH_N 0
 #define RTX_PH_T 1
 #define RTX_PH_E 2
@@ -503,13 +506,40 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                         RayD r2; RayF f;
                         T.load_ray(s, r2);
                         xform_ray(S, ei, e, r2);
+                        make_rayf(r2, f);
+#if RTX_E_ROOT_STEP
+                        // The instance's world-space box (the TLAS leaf) is loose around a rotated statue: test the BLAS root's four
+                        // children here, with the object-space ray already in registers. If none is hit the instance is never
+                        // entered — the stored world ray is untouched, no sentinel, no NODE round, no round to come back — and
+                        // otherwise the NODE phase starts one level down.
+                        float d[4]; int ch[4];
+                        if (COUNT) tc.nodes++;
+                        node_test(S.nodes, e.a, f, ftmin, T.ft[s], d, ch);
+#define RTX_CSWAP(i, j) if (d[j] < d[i]) { float td = d[i]; d[i] = d[j]; d[j] = td; int tcx = ch[i]; ch[i] = ch[j]; ch[j] = tcx; }
+                        if (RTX_ANYHIT_SORT || !Policy::ANY_HIT) { RTX_CSWAP(0, 1) RTX_CSWAP(2, 3) RTX_CSWAP(0, 2) RTX_CSWAP(1, 3) RTX_CSWAP(1, 2) }
+                        else { RTX_CSWAP(0, 1) RTX_CSWAP(2, 3) RTX_CSWAP(0, 2) }   // the minimum in front: d[0] < INF iff any child is hit
+#undef RTX_CSWAP
+                        if (!(d[0] < INF)) {
+                            RTX_POP();
+                        } else {
+                            // nothing left in the TLAS: the query ends inside the instance (retire re-reads the world ray), no way back needed
+                            if (RTX_SKIP_LAST_SENTINEL == 0 || sp > 0) RTX_PUSH(RTX_ST_SENTINEL);
+                            if (d[3] < INF) RTX_PUSH(ch[3]);
+                            if (d[2] < INF) RTX_PUSH(ch[2]);
+                            if (d[1] < INF) RTX_PUSH(ch[1]);
+                            node = ch[0];
+                            T.store_ray(s, r2, false); T.store_rayf(s, f);
+                            T.cur[s] = ei;
+                            in_inst = true;
+                        }
+#else
                         // nothing left in the TLAS: the query ends inside the instance (retire re-reads the world ray), no way back needed
                         if (RTX_SKIP_LAST_SENTINEL == 0 || sp > 0) RTX_PUSH(RTX_ST_SENTINEL);
-                        make_rayf(r2, f);
                         T.store_ray(s, r2, false); T.store_rayf(s, f);
                         T.cur[s] = ei;
                         node = e.a;
                         in_inst = true;
+#endif
                     } else if (RTX_E_BARE_FAST && e.kind != RTX_GEOM_LIST && e.xf_count == 0 && e.volume < 0 && (RTX_E_BARE_FAST > 1 || e.kind == RTX_GEOM_QUAD)) {
                         // a bare primitive (the walls of every Cornell box, the spheres of RandomScene): the test inlined, without the
                         // generic entry machinery (wrapper chain, Volume / list handling, out-of-line dispatch, nextafter);
