@@ -62,7 +62,9 @@ struct rtx_ctx {
     // path pool
     Pool pool{};
     std::vector<void*> pool_allocs;
-    int64_t pool_paths = 1 << 23;  // in-flight paths per iteration: persistent trace launches have a fixed tail, so few big launches beat many small ones (cornell-lucy, 64 spp: 2 Mi 187, 4 Mi 198, 8 Mi 204 Mpaths/s)
+    // in-flight paths per iteration (upper limit; a pass of fewer paths gets a pool of its own size): persistent trace launches have a fixed
+    // tail, so few big launches beat many small ones (cornell-lucy 64 spp: 2 Mi 187, 4 Mi 198, 8 Mi 204; 256 spp: 8 Mi 244, 16 Mi 248, 32 Mi 250 Mpaths/s)
+    int64_t pool_paths = 1 << 24;
     Ctl* ctl = nullptr;       // device
     Ctl* ctl_host = nullptr;  // pinned
     int count_stats = 0, time_kernels = 1, blas_leaf = 4;
@@ -940,10 +942,15 @@ int32_t rtx_accum_device_ptr(rtx_ctx* ctx, void** sum_dev, void** sumsq_dev, int
     return RTX_OK;
 }
 
-static int32_t ensure_pool(rtx_ctx* ctx) {
-    if (ctx->pool.capacity == ctx->pool_paths) return RTX_OK;
+static int32_t ensure_pool(rtx_ctx* ctx, unsigned long long paths_of_pass) {
+    // capacity: the configured limit, or less when the whole pass is smaller (a 400x225 preview does not need gigabytes);
+    // grow-only below the limit, so the passes of one render (1 spp, spp/4, spp) allocate at most once per size step
+    unsigned long long want = std::min<unsigned long long>((unsigned long long)ctx->pool_paths, std::max<unsigned long long>(paths_of_pass, 1ull << 16));
+    want = (want + 0xffffull) & ~0xffffull;
+    want = std::min<unsigned long long>(want, (unsigned long long)ctx->pool_paths);
+    if (ctx->pool.capacity > 0 && (unsigned long long)ctx->pool.capacity >= want && ctx->pool.capacity <= ctx->pool_paths) return RTX_OK;
     free_pool(ctx);
-    size_t P = (size_t)ctx->pool_paths;
+    size_t P = (size_t)want;
     Pool p{};
     auto alloc = [&](void** out, size_t bytes) {
         cudaError_t e = cudaMalloc(out, bytes);
@@ -966,7 +973,7 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
     if (!ctx->have_scene || !ctx->have_camera) return fail(ctx, RTX_ERR_STATE, "rtx_render_pass: scene and camera must be set first");
     if (spp < 0 || max_depth < 0) return fail(ctx, RTX_ERR_INVALID, "rtx_render_pass: negative spp/depth");
     CU(cudaSetDevice(ctx->device));
-    int32_t rc = ensure_pool(ctx);
+    int32_t rc = ensure_pool(ctx, (unsigned long long)ctx->W * ctx->H * (unsigned long long)std::max(spp, 0));
     if (rc != RTX_OK) return rc;
     cudaStream_t st = ctx->stream;
     if (ctx->l2_persist && (!ctx->window_set || ctx->window_stream != st) && ctx->geom_bytes > 0) {

@@ -520,8 +520,14 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                         else { RTX_CSWAP(0, 1) RTX_CSWAP(2, 3) RTX_CSWAP(0, 2) }   // the minimum in front: d[0] < INF iff any child is hit
 #undef RTX_CSWAP
                         if (!(d[0] < INF)) {
+#ifdef RTX_DEBUG_ENTRY_COUNT
+                            if (COUNT) tc.planes++;
+#endif
                             RTX_POP();
                         } else {
+#ifdef RTX_DEBUG_ENTRY_COUNT
+                            if (COUNT) tc.spheres++;
+#endif
                             // nothing left in the TLAS: the query ends inside the instance (retire re-reads the world ray), no way back needed
                             if (RTX_SKIP_LAST_SENTINEL == 0 || sp > 0) RTX_PUSH(RTX_ST_SENTINEL);
                             if (d[3] < INF) RTX_PUSH(ch[3]);
