@@ -13,10 +13,10 @@ if [ "$2" != "noncu" ]; then
 python bench.py --spp 4 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $out/${tag}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --spp 4 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $out/${tag}_ncu_l.log 2>&1
-# launch 10 of a 64-spp pass: the stream is still full (8,388,608 rays with the default pool), bounces are mixed
-python tools/gpu_perf.py cornell-lucy 64 > $out/${tag}_plain2.log 2>&1 &&
+# launch 10 of a 64-spp pass: the stream is still full (8,388,608 rays with pool_paths = 2^23), bounces are mixed
+RTX_OPTS=pool_paths=8388608 python tools/gpu_perf.py cornell-lucy 64 > $out/${tag}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_extend -s 10 -c 1 -f -o $out/${tag}_prof_extend \
-    python tools/gpu_perf.py cornell-lucy 64 > $out/${tag}_ncu.log 2>&1
+    env RTX_OPTS=pool_paths=8388608 python tools/gpu_perf.py cornell-lucy 64 > $out/${tag}_ncu.log 2>&1
 tail -2 $out/${tag}_ncu.log
 fi
 # per-scene throughput table (short passes) and pool-size A/B
