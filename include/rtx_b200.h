@@ -283,7 +283,8 @@ int32_t rtx_hdri_total_power(const rtx_ctx* ctx, double* total_power);          
 int32_t rtx_set_stream(rtx_ctx* ctx, void* cuda_stream);
 
 int32_t rtx_get_stats(rtx_ctx* ctx, rtx_stats* out);
-/* Tunables: "pool_paths" (in-flight path slots), "count_stats" (per-ray traversal counters: bit 0 extension rays, bit 1 shadow
+/* Tunables: "pool_paths" (upper limit of in-flight path slots), "overlap_connect" (shadow rays on a second stream beside the next
+ * wavefront iteration, default 1; the pass is complete on the context's stream when rtx_render_pass returns either way), "count_stats" (per-ray traversal counters: bit 0 extension rays, bit 1 shadow
  * rays), "time_kernels" (CUDA-event time per kernel kind, default 1). Returns RTX_ERR_INVALID for unknown keys. */
 int32_t rtx_set_option(rtx_ctx* ctx, const char* key, int64_t value);
 
