@@ -158,6 +158,7 @@ def main():
             run_reference(args, grt, cfg)
         return 0
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines must not share stdout with the JSON line
     import torch
     mg = importlib.import_module("go-raytracing_b200.multigpu")
     rank, world, local = mg.init_from_env("nccl")
