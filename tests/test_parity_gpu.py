@@ -583,6 +583,34 @@ def test_sample_slices_add_up_and_are_deterministic(grt, ctx):
     assert np.all(n3 == 16) and np.allclose(full, small, rtol=2e-5, atol=1e-5)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,width,spp,depth", [("cornell", 160, 16, 10), ("cornell-lucy", 200, 8, 12), ("cornell-glossy", 160, 16, 5)])
+def test_connect_stream_is_result_neutral(grt, name, width, spp, depth):
+    """k_connect of iteration i runs on a second stream beside iteration i + 1 (shadow requests double-buffered by iteration
+    parity). The contributions are the same set either way — only the order of the float atomics differs — also when a small
+    pool forces many iterations, and the ray counts are identical."""
+    sc = grt.config_scene(name, width=width, spp=spp, depth=depth)
+    out = {}
+    for overlap in (1, 0):
+        for pool in (0, 8192):
+            c = grt.Context(0)
+            c.set_option("overlap_connect", overlap)
+            if pool:
+                c.set_option("pool_paths", pool)
+            c.load(sc)
+            c.render_pass(spp, depth, seed=21)
+            acc, _, n = c.resolve_accum()
+            st = c.stats()
+            c.close()
+            assert np.all(n == spp)
+            out[(overlap, pool)] = (acc, st["extension_rays"], st["shadow_rays"])
+    ref = out[(0, 0)]
+    assert ref[2] > 0
+    for k, v in out.items():
+        assert v[1] == ref[1] and v[2] == ref[2], k
+        assert np.allclose(v[0], ref[0], rtol=5e-5, atol=2e-5), k
+
+
 def test_full_size_lucy_properties(grt, ctx):
     """BASELINE's headline configuration at its full resolution (1200x675, depth 50, 280 K-triangle mesh x 10 instances), checked
     through size-independent properties: every pixel receives exactly spp samples; two sample slices add up to the whole
