@@ -51,6 +51,8 @@ struct rtx_ctx {
     cudaStream_t connect_stream = nullptr;   // k_connect of iteration i runs here, beside generate / extend / shade of iteration i + 1
     cudaEvent_t ev_shaded = nullptr, ev_connected[2] = {nullptr, nullptr};
     int overlap_connect = 1;
+    int shade_split = 0;      // k_shade as one launch per material queue (1) or one launch over all queues (0, the default: hdri-test 61.5 against 64.0 ms of shading per 64 spp, random 3.1 against 3.9 — the one-material kernels need 48-80 registers instead of 128, but six short launches have six tails)
+    unsigned mat_kinds = ~0u;  // bit q: some material of the uploaded scene shades through queue q
     std::string err;
     DevScene S{};
     bool have_scene = false, have_camera = false;
@@ -253,6 +255,7 @@ int32_t rtx_set_option(rtx_ctx* ctx, const char* key, int64_t value) {
     else if (k == "time_kernels") ctx->time_kernels = value != 0;
     else if (k == "l2_persist") { ctx->l2_persist = value != 0; ctx->window_set = false; }  // L2 persisting window over the scene geometry (default off)
     else if (k == "pixel_major") ctx->pixel_major = value != 0;
+    else if (k == "shade_split") ctx->shade_split = value != 0;
     else if (k == "overlap_connect") ctx->overlap_connect = value != 0;   // k_connect on its own stream beside the next iteration (default on)
     else if (k == "flat_max_entries") {   // 0 = always traverse the hierarchy
         if (value < 0 || value > 64) return fail(ctx, RTX_ERR_INVALID, "flat_max_entries must be in 0..64");
@@ -411,7 +414,10 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
         for (int c = 0; c < 3; c++) texs[i].color[c] = (float)d->tex_color[3 * i + c];
     }
     std::vector<DMaterial> mats(d->n_materials);
+    ctx->mat_kinds = 1u << Q_MISS;
     for (int i = 0; i < d->n_materials; i++) {
+        const int mt = d->mat_type[i];   // the queue k_extend bins a hit on this material into (rtx_kernels.cuh: ExtendPolicy::retire)
+        ctx->mat_kinds |= 1u << (mt == RTX_MAT_LAMBERTIAN ? Q_LAMBERTIAN : mt == RTX_MAT_METAL ? Q_METAL : mt == RTX_MAT_DIELECTRIC ? Q_DIELECTRIC : mt == RTX_MAT_DIFFUSE_LIGHT ? Q_LIGHT : Q_ISOTROPIC);
         mats[i].type = d->mat_type[i]; mats[i].tex = d->mat_tex[i]; mats[i].fuzz = d->mat_fuzz[i]; mats[i].ior = d->mat_ior[i]; mats[i].pad = 0;
         for (int c = 0; c < 3; c++) mats[i].albedo[c] = (float)d->mat_albedo[3 * i + c];
     }
@@ -1069,7 +1075,17 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
             } else if (ctx->count_stats & 1) k_extend<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
             else k_extend<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
             if (timing) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); }
-            k_shade<<<std::min((P + 255) / 256, ctx->num_sms * 2 * RTX_SHADE_BLOCKS), 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+            if (ctx->shade_split) {   // one launch per material queue (launches over empty queues return at once)
+                const int gs = std::min((P + 255) / 256, ctx->num_sms * 2 * RTX_SHADE_BLOCKS_Q);
+                k_shade<Q_MISS><<<gs, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+                k_shade<Q_LAMBERTIAN><<<gs, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+                if (ctx->mat_kinds & (1 << Q_METAL)) k_shade<Q_METAL><<<gs, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+                if (ctx->mat_kinds & (1 << Q_DIELECTRIC)) k_shade<Q_DIELECTRIC><<<gs, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+                if (ctx->mat_kinds & (1 << Q_LIGHT)) k_shade<Q_LIGHT><<<gs, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+                if (ctx->mat_kinds & (1 << Q_ISOTROPIC)) k_shade<Q_ISOTROPIC><<<gs, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+                launches += 1 + __builtin_popcount(ctx->mat_kinds & ((1 << Q_METAL) | (1 << Q_DIELECTRIC) | (1 << Q_LIGHT) | (1 << Q_ISOTROPIC)));
+            } else
+            k_shade<-1><<<std::min((P + 255) / 256, ctx->num_sms * 2 * RTX_SHADE_BLOCKS), 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
             if (timing) cudaEventRecord(ev[5], st);
             if (ctx->S.n_lights > 0) {
                 if (overlap) { CU(cudaEventRecord(ctx->ev_shaded, st)); CU(cudaStreamWaitEvent(sc, ctx->ev_shaded, 0)); }

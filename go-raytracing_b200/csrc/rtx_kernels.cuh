@@ -406,13 +406,25 @@ __device__ __forceinline__ D3 unit_sphere(uint32_t a, uint32_t b) {
 #ifndef RTX_SHADE_BLOCKS
 #define RTX_SHADE_BLOCKS 2   /* resident 256-thread blocks per SM k_shade is compiled for */
 #endif
-__global__ void __launch_bounds__(256, RTX_SHADE_BLOCKS) k_shade(Ctl* ctl, Pool pool, int cur, DevScene S, DevCamera C, PassParams pp) {
-  const int n_rounded = (ctl->n_active + 31) & ~31;   // whole warps stay together for the queue appends
+// QT < 0: one launch walks all six queues back to back. QT >= 0: the launch shades queue QT only — the material is a compile-time
+// constant, every other material's code is gone, and the kernel is compiled for RTX_SHADE_BLOCKS_Q resident blocks (k_shade waits
+// on gathers through the queues: ncu long_scoreboard 16 cycles per issue at 16 warps per SM; the one-material kernels fit more warps).
+#ifndef RTX_SHADE_BLOCKS_Q
+#define RTX_SHADE_BLOCKS_Q 3
+#endif
+template <int QT>
+__global__ void __launch_bounds__(256, QT < 0 ? RTX_SHADE_BLOCKS : (QT == Q_LAMBERTIAN ? RTX_SHADE_BLOCKS : RTX_SHADE_BLOCKS_Q)) k_shade(Ctl* ctl, Pool pool, int cur, DevScene S, DevCamera C, PassParams pp) {
+  const int n_items = QT < 0 ? ctl->n_active : ctl->n_mat[QT < 0 ? 0 : QT];
+  const int n_rounded = (n_items + 31) & ~31;   // whole warps stay together for the queue appends
   int nq[Q_COUNT];
 #pragma unroll
   for (int k = 0; k < Q_COUNT; k++) nq[k] = ctl->n_mat[k];
   // (queue, job) of element i of the concatenated queues: prefix over the six queue counts
   auto locate = [&](int i, int& type) {
+      if (QT >= 0) {
+          type = i < n_items ? QT : -1;
+          return type >= 0 ? pool.q_mat[(size_t)QT * pool.capacity + i] : -1;
+      }
       type = -1;
       int idx = i;
 #pragma unroll
@@ -428,7 +440,7 @@ __global__ void __launch_bounds__(256, RTX_SHADE_BLOCKS) k_shade(Ctl* ctl, Pool 
   int type_next = -1;
   int job_next = i < n_rounded ? locate(i, type_next) : -1;
   for (; i < n_rounded; i += stride) {
-    const int type = type_next, job_cur = job_next;
+    const int type = QT >= 0 ? QT : type_next, job_cur = job_next;   // (an element past the end of a one-material queue has job -1)
     // software pipeline: the records of this thread's NEXT element are gathers through the queue (two dependent hops); its
     // queue slot is read now and its record lines are prefetched into L1 while this element is shaded
     job_next = -1; type_next = -1;
@@ -441,7 +453,7 @@ __global__ void __launch_bounds__(256, RTX_SHADE_BLOCKS) k_shade(Ctl* ctl, Pool 
             if (type_next != Q_MISS) asm volatile("prefetch.global.L1 [%0];" ::"l"(pool.hit + (size_t)job_next * RTX_HIT_BYTES));
         }
     } else if (i + stride < n_rounded) job_next = locate(i + stride, type_next);
-    bool valid = type >= 0;
+    bool valid = QT >= 0 ? job_cur >= 0 : type >= 0;
     bool cont = false;
     // the path's next record (written only if it survives) and, for the shadow requests, its identity and hit point
     D3 P = d3(0, 0, 0), nd = d3(0, 0, 0);
