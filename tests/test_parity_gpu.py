@@ -611,6 +611,38 @@ def test_connect_stream_is_result_neutral(grt, name, width, spp, depth):
         assert np.allclose(v[0], ref[0], rtol=5e-5, atol=2e-5), k
 
 
+def test_gpu_vs_reference_image_png(grt, ctx):
+    """The CUDA path against an output of the reference itself: the committed image.png is the final pass of `-scene hdri-test`
+    (800x450, 200 spp, depth 20; rows 420..449 destroyed by the stats bar). Same scene, same spp on the device; 30x30 block
+    means of linear radiance (per pixel clamped like the 8-bit file) must agree like the oracle's do (test_oracle_kat.py)."""
+    import json, os
+    from conftest import ROOT
+    gold = os.path.join(ROOT, "tests", "golden", "image_png_region_means.json")
+    hdr = os.path.join(ROOT, "assets", "hdri", "abandoned_hall_01_1k.hdr")
+    if not os.path.exists(gold) or not os.path.exists(hdr) or os.path.getsize(hdr) < (1 << 20):
+        pytest.skip("needs the reference HDRI and tests/golden/image_png_region_means.json")
+    g = json.load(open(gold))
+    spp = 200
+    sc = grt.NamedScene("hdri-test", 800, 16.0 / 9.0, spp, 20)
+    assert (sc.width, sc.height) == (g["width"], g["height"])
+    ctx.load(sc)
+    ctx.clear(); ctx.render_pass(spp, 20, seed=11)
+    acc, _, n = ctx.resolve_accum()
+    assert np.all(n == spp)
+    lin = np.clip(acc / spp, 0.0, 0.999 ** 2)  # Interval{0,0.999}.Clamp after sqrt
+    bs, rows, cols = g["block"], g["rows"], g["cols"]
+    ours = np.zeros((rows, cols, 3))
+    for by in range(rows):
+        for bx in range(cols):
+            ours[by, bx] = lin[by * bs:(by + 1) * bs, bx * bs:(bx + 1) * bs].mean(axis=(0, 1))
+    ref = np.array(g["means"])
+    assert ours[:3].max() < 1e-3 and ref[:3].max() < 1e-3   # phantom HDRI: the sky rows are black in both
+    m = ref > 0.05
+    ratio = ours[m] / ref[m]
+    assert 0.985 < ratio.mean() < 1.015, ratio.mean()
+    assert ratio.min() > 0.9 and ratio.max() < 1.1, (ratio.min(), ratio.max())
+
+
 def test_full_size_lucy_properties(grt, ctx):
     """BASELINE's headline configuration at its full resolution (1200x675, depth 50, 280 K-triangle mesh x 10 instances), checked
     through size-independent properties: every pixel receives exactly spp samples; two sample slices add up to the whole
