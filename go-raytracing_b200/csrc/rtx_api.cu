@@ -51,6 +51,7 @@ struct rtx_ctx {
     cudaStream_t connect_stream = nullptr;   // k_connect of iteration i runs here, beside generate / extend / shade of iteration i + 1
     cudaEvent_t ev_shaded = nullptr, ev_connected[2] = {nullptr, nullptr};
     int overlap_connect = 1;
+    int fuse_flat = 1;        // flat worlds: closest hit and shading in one kernel (k_bounce_flat); 0 = k_extend_flat + k_shade
     int shade_split = 0;      // k_shade as one launch per material queue (1) or one launch over all queues (0, the default: hdri-test 61.5 against 64.0 ms of shading per 64 spp, random 3.1 against 3.9 — the one-material kernels need 48-80 registers instead of 128, but six short launches have six tails)
     unsigned mat_kinds = ~0u;  // bit q: some material of the uploaded scene shades through queue q
     std::string err;
@@ -255,6 +256,7 @@ int32_t rtx_set_option(rtx_ctx* ctx, const char* key, int64_t value) {
     else if (k == "time_kernels") ctx->time_kernels = value != 0;
     else if (k == "l2_persist") { ctx->l2_persist = value != 0; ctx->window_set = false; }  // L2 persisting window over the scene geometry (default off)
     else if (k == "pixel_major") ctx->pixel_major = value != 0;
+    else if (k == "fuse_flat") ctx->fuse_flat = value != 0;
     else if (k == "shade_split") ctx->shade_split = value != 0;
     else if (k == "overlap_connect") ctx->overlap_connect = value != 0;   // k_connect on its own stream beside the next iteration (default on)
     else if (k == "flat_max_entries") {   // 0 = always traverse the hierarchy
@@ -1064,8 +1066,16 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
             poolI.shadow = pool.shadow + (size_t)cur * 2 * (size_t)P * RTX_SHADOW_BYTES;
             k_iter_begin<<<1, 32, 0, st>>>(ctx->ctl, P, cur);
             if (timing) cudaEventRecord(ev[0], st);
-            k_generate<<<gridStream, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->C, pp);
+            const bool fused = ctx->scene_flat && ctx->fuse_flat;   // k_bounce_flat generates the fresh paths itself
+            if (!fused) k_generate<<<gridStream, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->C, pp);
             if (timing) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
+            if (fused) {   // generate + trace + shade in one kernel: fresh paths and hits stay in registers
+                if (ctx->S.n_images > 0) k_bounce_flat<false, true><<<gridStream, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+                else if (ctx->count_stats & 1) k_bounce_flat<true><<<gridStream, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+                else k_bounce_flat<false><<<gridStream, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+                if (timing) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); }
+                launches -= 2;
+            } else {
             if (ctx->S.n_images > 0) {   // hit records carry (u, v); this variant is not instrumented
                 if (ctx->scene_flat) k_extend_flat<false, true><<<gridStream, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, pp);
                 else k_extend<false, true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
@@ -1086,6 +1096,7 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
                 launches += 1 + __builtin_popcount(ctx->mat_kinds & ((1 << Q_METAL) | (1 << Q_DIELECTRIC) | (1 << Q_LIGHT) | (1 << Q_ISOTROPIC)));
             } else
             k_shade<-1><<<std::min((P + 255) / 256, ctx->num_sms * 2 * RTX_SHADE_BLOCKS), 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+            }
             if (timing) cudaEventRecord(ev[5], st);
             if (ctx->S.n_lights > 0) {
                 if (overlap) { CU(cudaEventRecord(ctx->ev_shaded, st)); CU(cudaStreamWaitEvent(sc, ctx->ev_shaded, 0)); }

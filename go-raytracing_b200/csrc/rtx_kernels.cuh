@@ -157,10 +157,8 @@ __device__ __forceinline__ RayD camera_ray(const DevCamera& C, int i, int j, dou
 // The stream kernels (generate / shade / accumulate) run on a fixed grid (a few blocks per SM) and stride over the work the
 // device-side control block announces: the host never learns the queue lengths, and a launch sized for the whole pool
 // (16 K blocks) costs ~70 us of block scheduling even when a handful of paths are left.
-__global__ void __launch_bounds__(256, 4) k_generate(Ctl* ctl, Pool pool, int cur, DevCamera C, PassParams pp) {
-  const int n_gen = ctl->n_gen, n_cont = ctl->n_cont;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_gen; i += gridDim.x * blockDim.x) {
-    unsigned long long pid = ctl->gen_base + (unsigned long long)i;
+// camera path `pid` of the pass: its primary ray and its (pixel | sample << 32) identity
+__device__ __forceinline__ RayD generate_path(const DevCamera& C, const PassParams& pp, unsigned long long pid, unsigned long long& pixsample) {
     unsigned npix = (unsigned)C.width * (unsigned)C.height;
     // path order: pixel-major (all samples of a pixel are consecutive paths) keeps the pixels in flight few, so the radiance
     // atomics stay in L2 and neighbouring lanes start with nearly the same ray; sample-major is the other order
@@ -178,11 +176,19 @@ __global__ void __launch_bounds__(256, 4) k_generate(Ctl* ctl, Pool pool, int cu
         sincospif(2.0f * u01f(r1.x), &sn, &cs);
         lx = rr * cs; ly = rr * sn;
     }
-    RayD r = camera_ray(C, px, py, offx, offy, tm, lx, ly);
+    pixsample = ((unsigned long long)sample << 32) | pixel;
+    return camera_ray(C, px, py, offx, offy, tm, lx, ly);
+}
+#define RTX_FRESH_PATH_FLAGS (0 | (1 << 16))   /* bounce 0, light hits allowed */
+__global__ void __launch_bounds__(256, 4) k_generate(Ctl* ctl, Pool pool, int cur, DevCamera C, PassParams pp) {
+  const int n_gen = ctl->n_gen, n_cont = ctl->n_cont;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_gen; i += gridDim.x * blockDim.x) {
+    unsigned long long ps;
+    const RayD r = generate_path(C, pp, ctl->gen_base + (unsigned long long)i, ps);
     char* rec = pool.records(cur) + (size_t)(n_cont + i) * RTX_REC_BYTES;   // appended behind the survivors
     st256d(rec, r.ox, r.oy, r.oz, r.tm);
-    st256d(rec + 32, r.dx, r.dy, r.dz, __longlong_as_double((long long)(((unsigned long long)sample << 32) | pixel)));
-    *reinterpret_cast<float4*>(rec + 64) = make_float4(1.f, 1.f, 1.f, __int_as_float(0 | (1 << 16)));
+    st256d(rec + 32, r.dx, r.dy, r.dz, __longlong_as_double((long long)ps));
+    *reinterpret_cast<float4*>(rec + 64) = make_float4(1.f, 1.f, 1.f, __int_as_float(RTX_FRESH_PATH_FLAGS));
   }
 }
 
@@ -406,6 +412,194 @@ __device__ __forceinline__ D3 unit_sphere(uint32_t a, uint32_t b) {
 #ifndef RTX_SHADE_BLOCKS
 #define RTX_SHADE_BLOCKS 2   /* resident 256-thread blocks per SM k_shade is compiled for */
 #endif
+// What one shaded element carries out of the material code: the path's next record (written only if it survives) and up to two
+// shadow requests per Lambertian hit, in fixed registers (no dynamically indexed arrays: those live in local memory).
+struct ShadeVars {
+    bool cont, has_env, has_area;
+    D3 P, nd, env_dir, area_dir;
+    double tm, pixbits, area_tmax;
+    float4 th;
+    int bounce0;
+    float3 env_c, area_c;
+    __device__ __forceinline__ void reset() {
+        cont = has_env = has_area = false;
+        P = nd = env_dir = area_dir = d3(0, 0, 0);
+        tm = pixbits = area_tmax = 0;
+        th = make_float4(0, 0, 0, 0);
+        bounce0 = 0;
+        env_c = area_c = make_float3(0, 0, 0);
+    }
+};
+
+// rayColorInternal for one ray whose query is finished (rt/camera.go:443-518): `type` is its shading queue; V.tm / V.pixbits / V.th hold
+// the path record's time, pixel | sample and throughput | flags; P_in, N, (hu, hv), mat, front are the hit (unused for Q_MISS).
+__device__ __forceinline__ void shade_element(const DevScene& S, const DevCamera& C, const PassParams& pp, const Pool& pool, const int type, const D3 rd,
+                                              const D3 P_in, const D3 N, const float hu, const float hv, const int mat, const bool front, ShadeVars& V) {
+    bool& cont = V.cont; bool& has_env = V.has_env; bool& has_area = V.has_area;
+    D3& nd = V.nd; D3& env_dir = V.env_dir; D3& area_dir = V.area_dir;
+    double& area_tmax = V.area_tmax;
+    float4& th = V.th;
+    int& bounce0 = V.bounce0;
+    float3& env_c = V.env_c; float3& area_c = V.area_c;
+    const double pixbits = V.pixbits;
+    int flags = __float_as_int(th.w);
+    int bounce = flags & 0xffff;
+    bounce0 = bounce;
+    bool allow = (flags >> 16) & 1;
+    const unsigned long long psb = (unsigned long long)__double_as_longlong(pixbits);
+    uint2 ps = make_uint2((uint32_t)psb, (uint32_t)(psb >> 32));
+    if (type == Q_MISS) {  // rt/camera.go:451-466
+        float3 col;
+        if (S.env_w > 0) {
+            bool primary = (bounce == 0) && (pp.max_depth == pp.camera_max_depth);  // depth == c.MaxDepth
+            if (C.phantom && primary) col = make_float3(0, 0, 0);
+            else col = env_lookup(S, rd);
+        } else if (C.use_sky) {  // SkyGradient :520-526
+            D3 ud = unit(rd);
+            float t = (float)(0.5 * (ud.y + 1.0));
+            col = make_float3((1.f - t) + 0.5f * t, (1.f - t) + 0.7f * t, (1.f - t) + 1.0f * t);
+        } else col = make_float3(C.background[0], C.background[1], C.background[2]);
+        pool.contribute(ps.x, ps.y, th.x * col.x, th.y * col.y, th.z * col.z);
+    } else {
+        V.P = P_in;
+        const D3 P = P_in;
+        DMaterial M = S.mats[mat];
+        if (type == Q_LIGHT) {  // Scatter == false: rt/camera.go:473-481, rt/material.go:226-236
+            if (allow) {
+                float3 e = tex_value(S, M.tex, P, hu, hv);
+                pool.contribute(ps.x, ps.y, th.x * e.x, th.y * e.y, th.z * e.z);
+            }
+        } else {
+            uint4 rs = philox4x32(ps.x, ps.y, (uint32_t)bounce, STREAM_SCATTER, pp.seed_lo, pp.seed_hi);
+            float3 att;
+            bool scattered = true, next_allow = true;
+            if (type == Q_LAMBERTIAN) {  // rt/material.go:57-68
+                nd = add(N, unit_sphere(rs.x, rs.y));
+                if (fabs(nd.x) < 1e-8 && fabs(nd.y) < 1e-8 && fabs(nd.z) < 1e-8) nd = N;
+                att = tex_value(S, M.tex, P, hu, hv);
+                if (S.n_lights > 0) {  // useMIS, rt/camera.go:487-517
+                    const double PI = 3.14159265358979323846;
+                    uint4 rn = philox4x32(ps.x, ps.y, (uint32_t)bounce, STREAM_NEE, pp.seed_lo, pp.seed_hi);
+                    int li = (int)(u01(rn.x) * (double)S.n_lights);
+                    if (li >= S.n_lights) li = S.n_lights - 1;
+                    if (S.env_w > 0 && S.env_is && S.env_total != 0) {  // sampleHDRILight :565-607
+                        D3 ldir; float3 em; double pdfH;
+                        env_sample(S, u01(rs.z), u01(rs.w), ldir, em, pdfH);
+                        double cosT = dot(N, ldir);
+                        if (cosT > 0) {
+                            double pdfB = cosT / PI;  // Lambertian.PDF rt/material.go:70-76
+                            double w = pdfH / (pdfH + pdfB);
+                            double s = cosT / pdfH * w;
+                            float3 cc = make_float3(fminf((float)(em.x * s) * att.x, 20.f), fminf((float)(em.y * s) * att.y, 20.f), fminf((float)(em.z * s) * att.z, 20.f));
+                            env_dir = ldir;
+                            env_c = make_float3(th.x * cc.x, th.y * cc.y, th.z * cc.z);
+                            has_env = true;
+                        }
+                    }
+                    int lq = S.light_quads[li];
+                    if (lq >= 0) {  // sampleAreaLight :610-678
+                        const double* q = S.quads + 16 * (size_t)lq;
+                        D3 lp = add(add(ld3(q), scale(ld3(q + 3), u01(rn.y))), scale(ld3(q + 6), u01(rn.z)));  // SamplePoint rt/quad.go:87-92
+                        D3 toL = sub(lp, P);
+                        double dist = sqrt(len2(toL));
+                        D3 ldir = unit(toL);
+                        double cosT = dot(N, ldir);
+                        double cosL = fabs(dot(ld3(q + 12), d3(-ldir.x, -ldir.y, -ldir.z)));
+                        if (cosT > 0 && !(cosL < 0.001)) {
+                            float3 em = tex_value(S, S.mats[S.quad_mat[lq]].tex, lp);  // lightQuad.mat.Emitted(0,0,lightPoint)
+                            if (S.mats[S.quad_mat[lq]].type != RTX_MAT_DIFFUSE_LIGHT) em = make_float3(0, 0, 0);
+                            double area = sqrt(len2(cross(ld3(q + 3), ld3(q + 6))));
+                            double pdfL = (dist * dist) / (cosL * area);
+                            double pdfB = cosT / PI;
+                            double w = pdfL / (pdfL + pdfB);
+                            double s = cosT / pdfL * w;
+                            double nl = (double)S.n_lights;
+                            float3 cc = make_float3(fminf((float)(em.x * s * att.x * nl), 20.f), fminf((float)(em.y * s * att.y * nl), 20.f),
+                                                    fminf((float)(em.z * s * att.z * nl), 20.f));
+                            area_dir = ldir; area_tmax = dist - 0.001;
+                            area_c = make_float3(th.x * cc.x, th.y * cc.y, th.z * cc.z);
+                            has_area = true;
+                        }
+                    }
+                    next_allow = false;  // indirect path must not pick up the light again (:514)
+                }
+            } else if (type == Q_METAL) {  // rt/material.go:113-119
+                double dn = dot(rd, N);
+                D3 refl = sub(rd, scale(N, 2 * dn));
+                nd = add(unit(refl), scale(unit_sphere(rs.x, rs.y), M.fuzz));
+                att = make_float3(M.albedo[0], M.albedo[1], M.albedo[2]);
+                scattered = dot(nd, N) > 0;
+            } else if (type == Q_DIELECTRIC) {  // rt/material.go:164-188
+                att = make_float3(1.f, 1.f, 1.f);
+                double ri = front ? 1.0 / M.ior : M.ior;
+                D3 ud = unit(rd);
+                double cosT = fmin(dot(d3(-ud.x, -ud.y, -ud.z), N), 1.0);
+                double sinT = sqrt(1.0 - cosT * cosT);
+                bool cannot = ri * sinT > 1.0;
+                bool reflect = cannot;
+                if (!cannot) {
+                    double r0 = (1 - ri) / (1 + ri);
+                    r0 = r0 * r0;
+                    double om = 1 - cosT;
+                    double refl = r0 + (1 - r0) * (om * om * om * om * om);
+                    reflect = refl > u01(rs.x);
+                }
+                if (reflect) nd = sub(ud, scale(N, 2 * dot(ud, N)));
+                else {  // Refract rt/vec3.go:110-117
+                    D3 perp = scale(add(ud, scale(N, cosT)), ri);
+                    D3 par = scale(N, -sqrt(fabs(1.0 - len2(perp))));
+                    nd = add(perp, par);
+                }
+            } else {  // Q_ISOTROPIC rt/material.go:266-270
+                nd = unit_sphere(rs.x, rs.y);
+                att = tex_value(S, M.tex, P, hu, hv);
+            }
+            if (!scattered) {
+                has_env = has_area = false;  // absorbed: emission of a scattering material is zero
+            } else {
+                th.x *= att.x; th.y *= att.y; th.z *= att.z;
+                bounce++;
+                th.w = __int_as_float((bounce & 0xffff) | (next_allow ? (1 << 16) : 0));
+                cont = bounce < pp.max_depth;  // rayColorInternal(depth <= 0) returns black (:444-446)
+            }
+        }
+    }
+}
+
+// Warp-collective: appends the survivor's next record to the other record buffer and the shadow requests to this iteration's half.
+__device__ __forceinline__ void shade_commit(Ctl* ctl, const Pool& pool, const int cur, const ShadeVars& V) {
+    const bool cont = V.cont, has_env = V.has_env, has_area = V.has_area;
+    const D3 P = V.P, nd = V.nd, env_dir = V.env_dir, area_dir = V.area_dir;
+    const double tm = V.tm, pixbits = V.pixbits, area_tmax = V.area_tmax;
+    const float4 th = V.th;
+    const int bounce0 = V.bounce0;
+    const float3 env_c = V.env_c, area_c = V.area_c;
+    // survivors: the next ray goes to the next free record of the other buffer, in the order the warps arrive
+    const int pos = warp_append(&ctl->n_next, cont);
+    if (cont) {
+        char* out = pool.records(cur ^ 1) + (size_t)pos * RTX_REC_BYTES;
+        st256d(out, P.x, P.y, P.z, tm);
+        st256d(out + 32, nd.x, nd.y, nd.z, pixbits);
+        *reinterpret_cast<float4*>(out + 64) = th;
+    }
+    {   // shadow requests carry everything k_connect needs (origin = the hit point, where the contribution goes)
+        int sp = warp_append(&ctl->n_shadow[cur], has_env);
+        if (has_env) {
+            char* q = pool.shadow + (size_t)sp * RTX_SHADOW_BYTES;
+            st256d(q, P.x, P.y, P.z, RTX_INF_D);
+            st256d(q + 32, env_dir.x, env_dir.y, env_dir.z, pixbits);
+            *reinterpret_cast<float4*>(q + 64) = make_float4(env_c.x, env_c.y, env_c.z, __int_as_float(bounce0));
+        }
+        sp = warp_append(&ctl->n_shadow[cur], has_area);
+        if (has_area) {
+            char* q = pool.shadow + (size_t)sp * RTX_SHADOW_BYTES;
+            st256d(q, P.x, P.y, P.z, area_tmax);
+            st256d(q + 32, area_dir.x, area_dir.y, area_dir.z, pixbits);
+            *reinterpret_cast<float4*>(q + 64) = make_float4(area_c.x, area_c.y, area_c.z, __int_as_float(bounce0));
+        }
+    }
+}
+
 // QT < 0: one launch walks all six queues back to back. QT >= 0: the launch shades queue QT only — the material is a compile-time
 // constant, every other material's code is gone, and the kernel is compiled for RTX_SHADE_BLOCKS_Q resident blocks (k_shade waits
 // on gathers through the queues: ncu long_scoreboard 16 cycles per issue at 16 warps per SM; the one-material kernels fit more warps).
@@ -454,179 +648,96 @@ __global__ void __launch_bounds__(256, QT < 0 ? RTX_SHADE_BLOCKS : (QT == Q_LAMB
         }
     } else if (i + stride < n_rounded) job_next = locate(i + stride, type_next);
     bool valid = QT >= 0 ? job_cur >= 0 : type >= 0;
-    bool cont = false;
-    // the path's next record (written only if it survives) and, for the shadow requests, its identity and hit point
-    D3 P = d3(0, 0, 0), nd = d3(0, 0, 0);
-    double tm = 0, pixbits = 0;
-    float4 th = make_float4(0, 0, 0, 0);
-    int bounce0 = 0;
-    // up to two shadow requests per Lambertian hit, in fixed registers (no dynamically indexed arrays: those live in local memory)
-    bool has_env = false, has_area = false;
-    D3 env_dir = d3(0, 0, 0), area_dir = d3(0, 0, 0);
-    double area_tmax = 0;
-    float3 env_c = make_float3(0, 0, 0), area_c = make_float3(0, 0, 0);
+    ShadeVars V;
+    V.reset();
     if (valid) {
         const int job = job_cur;
         const char* rec = pool.records(cur) + (size_t)job * RTX_REC_BYTES;
         const D4 ro4 = ld256d(rec), rd4 = ld256d(rec + 32);
-        D3 rd = d3(rd4.x, rd4.y, rd4.z);
-        tm = ro4.w; pixbits = rd4.w;
-        th = *reinterpret_cast<const float4*>(rec + 64);
-        int flags = __float_as_int(th.w);
-        int bounce = flags & 0xffff;
-        bounce0 = bounce;
-        bool allow = (flags >> 16) & 1;
-        const unsigned long long psb = (unsigned long long)__double_as_longlong(pixbits);
-        uint2 ps = make_uint2((uint32_t)psb, (uint32_t)(psb >> 32));
-        if (type == Q_MISS) {  // rt/camera.go:451-466
-            float3 col;
-            if (S.env_w > 0) {
-                bool primary = (bounce == 0) && (pp.max_depth == pp.camera_max_depth);  // depth == c.MaxDepth
-                if (C.phantom && primary) col = make_float3(0, 0, 0);
-                else col = env_lookup(S, rd);
-            } else if (C.use_sky) {  // SkyGradient :520-526
-                D3 ud = unit(rd);
-                float t = (float)(0.5 * (ud.y + 1.0));
-                col = make_float3((1.f - t) + 0.5f * t, (1.f - t) + 0.7f * t, (1.f - t) + 1.0f * t);
-            } else col = make_float3(C.background[0], C.background[1], C.background[2]);
-            pool.contribute(ps.x, ps.y, th.x * col.x, th.y * col.y, th.z * col.z);
-        } else {
+        V.tm = ro4.w; V.pixbits = rd4.w;
+        V.th = *reinterpret_cast<const float4*>(rec + 64);
+        D3 P = d3(0, 0, 0), N = d3(0, 0, 0);
+        float hu = 0.f, hv = 0.f;   // rec.U, rec.V: carried only in scenes with image textures
+        int mat = 0;
+        bool front = false;
+        if (type != Q_MISS) {
             const char* hrec = pool.hit + (size_t)job * RTX_HIT_BYTES;
             const D4 hp = ld256d(hrec), hn = ld256d(hrec + 32);
             P = d3(hp.x, hp.y, hp.z);
-            D3 N = d3(hn.x, hn.y, hn.z);
-            float hu = 0.f, hv = 0.f;   // rec.U, rec.V: carried only in scenes with image textures
+            N = d3(hn.x, hn.y, hn.z);
             if (S.n_images > 0) { const long long uvb = __double_as_longlong(hp.w); hu = __uint_as_float((unsigned)uvb); hv = __uint_as_float((unsigned)(uvb >> 32)); }
-            long long bits = __double_as_longlong(hn.w);
-            int mat = (int)(bits & 0x7fffffff);
-            bool front = (bits >> 31) & 1;
-            DMaterial M = S.mats[mat];
-            if (type == Q_LIGHT) {  // Scatter == false: rt/camera.go:473-481, rt/material.go:226-236
-                if (allow) {
-                    float3 e = tex_value(S, M.tex, P, hu, hv);
-                    pool.contribute(ps.x, ps.y, th.x * e.x, th.y * e.y, th.z * e.z);
-                }
-            } else {
-                uint4 rs = philox4x32(ps.x, ps.y, (uint32_t)bounce, STREAM_SCATTER, pp.seed_lo, pp.seed_hi);
-                float3 att;
-                bool scattered = true, next_allow = true;
-                if (type == Q_LAMBERTIAN) {  // rt/material.go:57-68
-                    nd = add(N, unit_sphere(rs.x, rs.y));
-                    if (fabs(nd.x) < 1e-8 && fabs(nd.y) < 1e-8 && fabs(nd.z) < 1e-8) nd = N;
-                    att = tex_value(S, M.tex, P, hu, hv);
-                    if (S.n_lights > 0) {  // useMIS, rt/camera.go:487-517
-                        const double PI = 3.14159265358979323846;
-                        uint4 rn = philox4x32(ps.x, ps.y, (uint32_t)bounce, STREAM_NEE, pp.seed_lo, pp.seed_hi);
-                        int li = (int)(u01(rn.x) * (double)S.n_lights);
-                        if (li >= S.n_lights) li = S.n_lights - 1;
-                        if (S.env_w > 0 && S.env_is && S.env_total != 0) {  // sampleHDRILight :565-607
-                            D3 ldir; float3 em; double pdfH;
-                            env_sample(S, u01(rs.z), u01(rs.w), ldir, em, pdfH);
-                            double cosT = dot(N, ldir);
-                            if (cosT > 0) {
-                                double pdfB = cosT / PI;  // Lambertian.PDF rt/material.go:70-76
-                                double w = pdfH / (pdfH + pdfB);
-                                double s = cosT / pdfH * w;
-                                float3 cc = make_float3(fminf((float)(em.x * s) * att.x, 20.f), fminf((float)(em.y * s) * att.y, 20.f), fminf((float)(em.z * s) * att.z, 20.f));
-                                env_dir = ldir;
-                                env_c = make_float3(th.x * cc.x, th.y * cc.y, th.z * cc.z);
-                                has_env = true;
-                            }
-                        }
-                        int lq = S.light_quads[li];
-                        if (lq >= 0) {  // sampleAreaLight :610-678
-                            const double* q = S.quads + 16 * (size_t)lq;
-                            D3 lp = add(add(ld3(q), scale(ld3(q + 3), u01(rn.y))), scale(ld3(q + 6), u01(rn.z)));  // SamplePoint rt/quad.go:87-92
-                            D3 toL = sub(lp, P);
-                            double dist = sqrt(len2(toL));
-                            D3 ldir = unit(toL);
-                            double cosT = dot(N, ldir);
-                            double cosL = fabs(dot(ld3(q + 12), d3(-ldir.x, -ldir.y, -ldir.z)));
-                            if (cosT > 0 && !(cosL < 0.001)) {
-                                float3 em = tex_value(S, S.mats[S.quad_mat[lq]].tex, lp);  // lightQuad.mat.Emitted(0,0,lightPoint)
-                                if (S.mats[S.quad_mat[lq]].type != RTX_MAT_DIFFUSE_LIGHT) em = make_float3(0, 0, 0);
-                                double area = sqrt(len2(cross(ld3(q + 3), ld3(q + 6))));
-                                double pdfL = (dist * dist) / (cosL * area);
-                                double pdfB = cosT / PI;
-                                double w = pdfL / (pdfL + pdfB);
-                                double s = cosT / pdfL * w;
-                                double nl = (double)S.n_lights;
-                                float3 cc = make_float3(fminf((float)(em.x * s * att.x * nl), 20.f), fminf((float)(em.y * s * att.y * nl), 20.f),
-                                                        fminf((float)(em.z * s * att.z * nl), 20.f));
-                                area_dir = ldir; area_tmax = dist - 0.001;
-                                area_c = make_float3(th.x * cc.x, th.y * cc.y, th.z * cc.z);
-                                has_area = true;
-                            }
-                        }
-                        next_allow = false;  // indirect path must not pick up the light again (:514)
-                    }
-                } else if (type == Q_METAL) {  // rt/material.go:113-119
-                    double dn = dot(rd, N);
-                    D3 refl = sub(rd, scale(N, 2 * dn));
-                    nd = add(unit(refl), scale(unit_sphere(rs.x, rs.y), M.fuzz));
-                    att = make_float3(M.albedo[0], M.albedo[1], M.albedo[2]);
-                    scattered = dot(nd, N) > 0;
-                } else if (type == Q_DIELECTRIC) {  // rt/material.go:164-188
-                    att = make_float3(1.f, 1.f, 1.f);
-                    double ri = front ? 1.0 / M.ior : M.ior;
-                    D3 ud = unit(rd);
-                    double cosT = fmin(dot(d3(-ud.x, -ud.y, -ud.z), N), 1.0);
-                    double sinT = sqrt(1.0 - cosT * cosT);
-                    bool cannot = ri * sinT > 1.0;
-                    bool reflect = cannot;
-                    if (!cannot) {
-                        double r0 = (1 - ri) / (1 + ri);
-                        r0 = r0 * r0;
-                        double om = 1 - cosT;
-                        double refl = r0 + (1 - r0) * (om * om * om * om * om);
-                        reflect = refl > u01(rs.x);
-                    }
-                    if (reflect) nd = sub(ud, scale(N, 2 * dot(ud, N)));
-                    else {  // Refract rt/vec3.go:110-117
-                        D3 perp = scale(add(ud, scale(N, cosT)), ri);
-                        D3 par = scale(N, -sqrt(fabs(1.0 - len2(perp))));
-                        nd = add(perp, par);
-                    }
-                } else {  // Q_ISOTROPIC rt/material.go:266-270
-                    nd = unit_sphere(rs.x, rs.y);
-                    att = tex_value(S, M.tex, P, hu, hv);
-                }
-                if (!scattered) {
-                    has_env = has_area = false;  // absorbed: emission of a scattering material is zero
-                } else {
-                    th.x *= att.x; th.y *= att.y; th.z *= att.z;
-                    bounce++;
-                    th.w = __int_as_float((bounce & 0xffff) | (next_allow ? (1 << 16) : 0));
-                    cont = bounce < pp.max_depth;  // rayColorInternal(depth <= 0) returns black (:444-446)
-                }
-            }
+            const long long bits = __double_as_longlong(hn.w);
+            mat = (int)(bits & 0x7fffffff);
+            front = (bits >> 31) & 1;
         }
+        shade_element(S, C, pp, pool, type, d3(rd4.x, rd4.y, rd4.z), P, N, hu, hv, mat, front, V);
     }
-    // survivors: the next ray goes to the next free record of the other buffer, in the order the warps arrive
-    const int pos = warp_append(&ctl->n_next, cont);
-    if (cont) {
-        char* out = pool.records(cur ^ 1) + (size_t)pos * RTX_REC_BYTES;
-        st256d(out, P.x, P.y, P.z, tm);
-        st256d(out + 32, nd.x, nd.y, nd.z, pixbits);
-        *reinterpret_cast<float4*>(out + 64) = th;
-    }
-    {   // shadow requests carry everything k_connect needs (origin = the hit point, where the contribution goes)
-        int sp = warp_append(&ctl->n_shadow[cur], has_env);
-        if (has_env) {
-            char* q = pool.shadow + (size_t)sp * RTX_SHADOW_BYTES;
-            st256d(q, P.x, P.y, P.z, RTX_INF_D);
-            st256d(q + 32, env_dir.x, env_dir.y, env_dir.z, pixbits);
-            *reinterpret_cast<float4*>(q + 64) = make_float4(env_c.x, env_c.y, env_c.z, __int_as_float(bounce0));
-        }
-        sp = warp_append(&ctl->n_shadow[cur], has_area);
-        if (has_area) {
-            char* q = pool.shadow + (size_t)sp * RTX_SHADOW_BYTES;
-            st256d(q, P.x, P.y, P.z, area_tmax);
-            st256d(q + 32, area_dir.x, area_dir.y, area_dir.z, pixbits);
-            *reinterpret_cast<float4*>(q + 64) = make_float4(area_c.x, area_c.y, area_c.z, __int_as_float(bounce0));
-        }
-    }
+    shade_commit(ctl, pool, cur, V);
   }
+}
+
+// ---- K2+K4 fused, for the worlds the flat kernels trace (a handful of entries, no mesh) ------------------------------------
+// There the query is cheap and every lane runs the same loop, so the hit never has to leave the registers: the thread that traced the ray
+// shades it (same shade_element, same Philox counters: the paths are the ones the separate kernels produce) and appends the survivor. The hit
+// record (64 B written, 64 B read), the queue slot and the second read of the path record disappear — for these scenes both separate kernels
+// are HBM-bound (profiles/r01_k_shade_hdri.md) — at the price of shading without material-sorted warps.
+template <bool UV>
+struct BouncePolicyT {
+    static constexpr bool ANY_HIT = false;
+    Ctl* ctl; Pool pool; int cur; const DevScene* S; const DevCamera* C; PassParams pp;
+    int n_cont; unsigned long long gen_base;   // jobs >= n_cont are fresh camera paths: generated here, never written as records
+    mutable double pixbits_; mutable float4 th_;   // identity and throughput | flags of the job this thread is working on (load -> retire)
+    __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:451
+    __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
+        if (job >= n_cont) {
+            unsigned long long ps;
+            r = generate_path(*C, pp, gen_base + (unsigned long long)(job - n_cont), ps);
+            pixbits_ = __longlong_as_double((long long)ps);
+            th_ = make_float4(1.f, 1.f, 1.f, __int_as_float(RTX_FRESH_PATH_FLAGS));
+        } else {
+            const char* q = pool.records(cur) + (size_t)job * RTX_REC_BYTES;
+            const D4 a = ld256d(q), c = ld256d(q + 32);
+            r.ox = a.x; r.oy = a.y; r.oz = a.z; r.tm = a.w; r.dx = c.x; r.dy = c.y; r.dz = c.z;
+            pixbits_ = c.w;
+            th_ = *reinterpret_cast<const float4*>(q + 64);
+        }
+        tmax = RTX_INF_D;
+    }
+    __device__ __forceinline__ VolumeRng volume_rng(int) const {
+        const unsigned long long ps = (unsigned long long)__double_as_longlong(pixbits_);
+        const int bounce = __float_as_int(th_.w) & 0xffff;
+        VolumeRng vr; vr.k0 = pp.seed_lo; vr.k1 = pp.seed_hi; vr.c0 = (uint32_t)ps; vr.c1 = (uint32_t)(ps >> 32); vr.c2 = (uint32_t)bounce * 4u; vr.transparent = false;
+        return vr;
+    }
+    __device__ __forceinline__ void retire(int, bool valid, const RayD& r, const Best& b) const {
+        ShadeVars V;
+        V.reset();
+        if (valid) {
+            V.tm = r.tm; V.pixbits = pixbits_;
+            V.th = th_;
+            int type = Q_MISS;
+            HitInfo hi;
+            hi.P = hi.N = d3(0, 0, 0); hi.mat = 0; hi.front = false; hi.u = hi.v = 0;
+            if (b.entry >= 0) {
+                finalize_hit(*S, r, best_to_hit(b), UV, hi);
+                const int mt = S->mats[hi.mat].type;
+                type = mt == RTX_MAT_LAMBERTIAN ? Q_LAMBERTIAN : mt == RTX_MAT_METAL ? Q_METAL : mt == RTX_MAT_DIELECTRIC ? Q_DIELECTRIC
+                     : mt == RTX_MAT_DIFFUSE_LIGHT ? Q_LIGHT : Q_ISOTROPIC;
+            }
+            shade_element(*S, *C, pp, pool, type, d3(r.dx, r.dy, r.dz), hi.P, hi.N, UV ? (float)hi.u : 0.f, UV ? (float)hi.v : 0.f, hi.mat, hi.front, V);
+        }
+        shade_commit(ctl, pool, cur, V);
+    }
+};
+
+template <bool COUNT, bool UV = false>
+__global__ void __launch_bounds__(256) k_bounce_flat(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, const __grid_constant__ DevCamera C, PassParams pp) {
+    BouncePolicyT<UV> P{ctl, pool, cur, &S, &C, pp, ctl->n_cont, ctl->gen_base, 0.0, make_float4(0.f, 0.f, 0.f, 0.f)};
+    TraceCounters tc = {0, 0, 0, 0, 0};
+    const int n = ctl->n_active;
+    trace_flat<BouncePolicyT<UV>, COUNT>(S, P, n, tc);
+    if (COUNT) flush_counters(ctl, tc);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->ext_rays, (unsigned long long)n);
 }
 
 // ---- K3: connect — shadow rays of next-event estimation (any hit in [0.001, tmax]) ----------------------------------
