@@ -730,8 +730,11 @@ struct BouncePolicyT {
     }
 };
 
+#ifndef RTX_BOUNCE_BLOCKS
+#define RTX_BOUNCE_BLOCKS 2   /* resident 256-thread blocks per SM k_bounce_flat is compiled for */
+#endif
 template <bool COUNT, bool UV = false>
-__global__ void __launch_bounds__(256) k_bounce_flat(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, const __grid_constant__ DevCamera C, PassParams pp) {
+__global__ void __launch_bounds__(256, RTX_BOUNCE_BLOCKS) k_bounce_flat(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, const __grid_constant__ DevCamera C, PassParams pp) {
     BouncePolicyT<UV> P{ctl, pool, cur, &S, &C, pp, ctl->n_cont, ctl->gen_base, 0.0, make_float4(0.f, 0.f, 0.f, 0.f)};
     TraceCounters tc = {0, 0, 0, 0, 0};
     const int n = ctl->n_active;
