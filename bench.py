@@ -309,7 +309,13 @@ def main():
 
     # the stream kernels (HBM-bound): algorithmic bytes of this rank's slice / their CUDA-event time
     roofline_stream = None
-    if roofline is not None:
+    fused_flat = roofline is not None and my_ms_shade < 1e-3 * max(sum(s["ms_total"] for s in stats), 1e-9)
+    if fused_flat:   # a world of a handful of entries: one kernel per bounce generates, traces and shades (k_bounce_flat); no separate stream kernels
+        roofline["kernel"] = "k_bounce_flat"
+        roofline["note"] = ("flat world: camera-path generation, closest hit and shading run in ONE kernel per bounce, hits never leave the registers; "
+                            "algorithmic bytes as for k_extend (primitive records every ray tests + per-ray state): they are served by L1, the figure says "
+                            "that the scene traffic is not HBM traffic")
+    elif roofline is not None:
         my_paths = npix * count * args.steps
         shade_bytes = my_ext_rays * (4 + REC_BYTES + HIT_BYTES) + max(my_ext_rays - my_paths, 0) * REC_BYTES + my_sh_rays * SHADOW_BYTES
         gen_bytes = my_paths * REC_BYTES
