@@ -17,13 +17,9 @@
 // The traversal stack lives in shared memory, one column per thread (bank-conflict free). Exactness: see rtx_device.cuh —
 // float32 box tests only cull, every accepted hit is decided by the float64 primitive tests.
 #pragma once
-#include <type_traits>
-
 #include "rtx_device.cuh"
 
-#ifndef RTX_TRACE_THREADS
 #define RTX_TRACE_THREADS 128
-#endif
 #ifndef RTX_TRACE_SLOTS
 #define RTX_TRACE_SLOTS 224   /* ray slots per 128-thread block (shared-memory ray pool, see trace_persistent); multiple of 32, <= 256 (A/B on cornell-lucy: 256: 1370, 224: 1401 Mrays/s: a little more L1) */
 #endif
@@ -111,8 +107,14 @@ struct Best {
 #ifndef RTX_T_STEPS
 #define RTX_T_STEPS 4   /* triangles per TRI round (1: 1282, 2: 1303-1332, 4: 1373 Mrays/s) */
 #endif
+#ifndef RTX_PARTNERS
+#define RTX_PARTNERS 0   /* partner columns a lane may claim from when its own column has no ready slot of the voted phase (0..3) */
+#endif
 #ifndef RTX_SKIP_LAST_SENTINEL
 #define RTX_SKIP_LAST_SENTINEL 1
+#endif
+#ifndef RTX_N_FAST
+#define RTX_N_FAST 0   /* lanes with a NODE-ready slot from which the NODE phase is taken without a vote (0 = always vote) */
 #endif
 #ifndef RTX_ANYHIT_SORT
 #define RTX_ANYHIT_SORT 0   /* cornell-lucy k_connect: 2646 (sorted) -> 2689 Mrays/s */
@@ -129,13 +131,13 @@ struct Best {
 #define RTX_PH_R 3
 #define RTX_PH_NONE 4   /* parked: idle slot after the job queue ran dry */
 #define RTX_SLOT_WORDS (9 + 1 + 1 + 4 + 14 + 2 + 6 + RTX_SMEM_STACK)   /* 32-bit words of shared memory per ray slot */
-#define RTX_POOL_EXTRA_BYTES 512                                        /* column states + flags */
+#define RTX_POOL_EXTRA_BYTES 256                                        /* column states + flags */
 #define RTX_PH_BUSY 5   /* claimed by a warp for the current round */
 
 template <int NSLOTS>
 struct TracePool {
     static constexpr int NS = NSLOTS;
-    static_assert(NSLOTS % 32 == 0 && NSLOTS <= 512, "slots per block: a multiple of 32, at most 16 per bank column");
+    static_assert(NSLOTS % 32 == 0 && NSLOTS <= 256, "slots per block: a multiple of 32, at most 8 per bank column");
     float* f;      // [9][NS]  ix iy iz cnx cny cnz cfx cfy cfz
     int* off;      // [NS]     offx | offy << 8 | offz << 16
     float* ft;     // [NS]
@@ -144,7 +146,7 @@ struct TracePool {
     double* bt;    // [NS]
     int *be, *bk, *bp, *bi, *bre, *brp;  // best: entry, kind | have << 8, prim, item, rank_e, rank_p
     int* stack;    // [RTX_SMEM_STACK][NS]
-    unsigned long long* col; // [32]  packed phase nibbles of the NS/32 slots of each bank column (block-shared scheduling state; the low word when NS <= 256)
+    unsigned* col; // [32]  packed phase nibbles of the NS/32 slots of each bank column (block-shared scheduling state)
     int* flags;    // [32]  flags[0]: job queue ran dry
     __device__ __forceinline__ explicit TracePool(unsigned char* base) {
         double* d = reinterpret_cast<double*>(base);
@@ -157,8 +159,7 @@ struct TracePool {
         off = q; q += NS; node = q; q += NS; sp = q; q += NS; cur = q; q += NS; job = q; q += NS;
         be = q; q += NS; bk = q; q += NS; bp = q; q += NS; bi = q; q += NS; bre = q; q += NS; brp = q; q += NS;
         stack = q; q += RTX_SMEM_STACK * NS;
-        q += (reinterpret_cast<size_t>(q) & 4) ? 1 : 0;   // 8-byte alignment of the column words
-        col = reinterpret_cast<unsigned long long*>(q); q += 64;
+        col = reinterpret_cast<unsigned*>(q); q += 32;
         flags = q;
     }
     __device__ __forceinline__ void load_rayf(int s, RayF& x) const {
@@ -333,20 +334,15 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
     // conflict-free — and claims it with a compare-and-swap (phase -> BUSY). So each lane chooses among 4K candidates
     // instead of its own K, and the four warps of a block usually run different phases at the same time.
     constexpr int NCOL = NS / 32;
-    static_assert(NCOL <= 16, "one 64-bit state word per column holds at most 16 slots");
-    // the column word: 32 bits while 8 nibbles suffice, 64 bits for bigger blocks (256 threads sharing up to 512 slots)
-    typedef typename std::conditional<(NCOL <= 8), unsigned, unsigned long long>::type CW;
-    constexpr CW ONES = (CW)0x1111111111111111ull, HIGHS = (CW)0x8888888888888888ull;
-    CW ALL_PARKED = 0;
-    for (int jx = 0; jx < (int)(2 * sizeof(CW)); jx++) ALL_PARKED |= (CW)RTX_PH_NONE << (4 * jx);   // nibbles beyond NCOL stay parked
+    static_assert(NCOL <= 8, "one 32-bit state word per column holds at most 8 slots");
+    constexpr unsigned ALL_PARKED = 0x44444444u;
     const unsigned warp = threadIdx.x >> 5;
-    volatile CW* const colstate = reinterpret_cast<volatile CW*>(T.col);
-    CW* const colstate_a = reinterpret_cast<CW*>(T.col);
+    volatile unsigned* const colstate = T.col;
     volatile int* const dry = T.flags;
     if (threadIdx.x < 32) {
-        CW w0 = ALL_PARKED;
-        for (int jx = 0; jx < NCOL; jx++) w0 = (w0 & ~((CW)0xf << (4 * jx))) | ((CW)RTX_PH_R << (4 * jx));
-        colstate_a[threadIdx.x] = w0;
+        unsigned w0 = ALL_PARKED;
+        for (int j = 0; j < NCOL; j++) w0 = (w0 & ~(0xfu << (4 * j))) | ((unsigned)RTX_PH_R << (4 * j));
+        T.col[threadIdx.x] = w0;
         T.flags[threadIdx.x] = 0;
     }
     for (int i = threadIdx.x; i < NS; i += RTX_TRACE_THREADS) T.node[i] = RTX_ST_IDLE;
@@ -358,15 +354,21 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                        else node = RTX_ST_DONE; } while (0)
 #define RTX_CLASSIFY(nd, inst) ((nd) >= 0 ? RTX_PH_N : (nd) == RTX_ST_DONE ? RTX_PH_R : (nd) == RTX_ST_SENTINEL ? RTX_PH_E : (inst) ? RTX_PH_T : RTX_PH_E)
 
-#define RTX_HASZERO_NIB(x) ((((x) - ONES) & ~(x)) & HIGHS)   /* lowest set bit marks the lowest zero nibble exactly */
+#define RTX_HASZERO_NIB(x) ((((x) - 0x11111111u) & ~(x)) & 0x88888888u)   /* lowest set bit marks the lowest zero nibble exactly */
     for (;;) {
         // ---- vote: one REDUX over packed per-phase counts of lanes whose column holds a ready slot ------------------------
-        CW w = colstate[lane];
+        unsigned w = colstate[lane];
         int phase;
-        {
+        // fast path: when at least RTX_N_FAST lanes have a NODE-ready slot the NODE phase runs without a full vote (one ballot
+        // instead of four zero-nibble tests, a REDUX and the arg-max). The rarer phases then wait until NODE runs short of
+        // lanes, which also lets them collect more lanes per round.
+        if (RTX_N_FAST > 0 && __popc(__ballot_sync(FULL, RTX_HASZERO_NIB(w) != 0u)) >= RTX_N_FAST) {
+            phase = RTX_PH_N;
+            round++;
+        } else {
             unsigned present = 0;
 #pragma unroll
-            for (unsigned X = 0; X < 4; X++) present |= RTX_HASZERO_NIB(w ^ ((CW)X * ONES)) ? (1u << (8 * X)) : 0u;
+            for (unsigned X = 0; X < 4; X++) present |= RTX_HASZERO_NIB(w ^ (X * 0x11111111u)) ? (1u << (8 * X)) : 0u;
             const unsigned c = __reduce_add_sync(FULL, present);
             if (c == 0) {
                 if (__all_sync(FULL, w == ALL_PARKED)) break;   // every slot of the block is parked: queue dry, all rays retired
@@ -380,23 +382,31 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                       cE = (((c >> 16) & 0xff) << 2) | ((round + 2) & 3), cR = (((c >> 24) & 0xff) << 2) | ((round + 3) & 3);
             phase = (cN >= cT && cN >= cE && cN >= cR) ? RTX_PH_N : (cT >= cE && cT >= cR) ? RTX_PH_T : (cE >= cR) ? RTX_PH_E : RTX_PH_R;
         }
-        // claim one ready slot of my column (search start rotates so that no slot index is favoured)
+        // claim one ready slot of my column (search start rotates so that no slot index is favoured); a lane whose own column
+        // has none tries its RTX_PARTNERS partner columns (lane ^ 16, ^ 8, ^ 24): at worst a 2-way bank conflict with the
+        // partner lane, against an idle lane for the whole round
         int j = -1;
-        const unsigned col = lane;
+        unsigned col = lane;
         {
-            constexpr unsigned NIB = 2 * sizeof(CW);   // nibbles per word
-            const unsigned rot = (round % NIB) * 4u;
-            const CW pat = (CW)phase * ONES;
-            for (;;) {
-                const CW wr = rot ? (CW)((w >> rot) | (w << (4 * NIB - rot))) : w;
-                const CW hz = RTX_HASZERO_NIB(wr ^ pat);
-                if (!hz) break;
-                const unsigned first = sizeof(CW) == 8 ? (unsigned)(__ffsll((long long)hz) - 1) : (unsigned)(__ffs((int)hz) - 1);
-                const int jj = (int)(((first >> 2) + (rot >> 2)) & (NIB - 1));
-                const CW neww = w ^ ((CW)(phase ^ RTX_PH_BUSY) << (4 * jj));
-                const CW old = atomicCAS(colstate_a + col, w, neww);
-                if (old == w) { j = jj; break; }
-                w = old;
+            const unsigned rot = (round % NCOL) * 4u;
+            const unsigned pat = (unsigned)phase * 0x11111111u;
+#pragma unroll
+            for (int attempt = 0; attempt <= RTX_PARTNERS; attempt++) {
+                if (attempt > 0) {
+                    if (j >= 0) break;
+                    col = lane ^ (attempt == 1 ? 16u : attempt == 2 ? 8u : 24u);
+                    w = colstate[col];
+                }
+                for (;;) {
+                    const unsigned wr = __funnelshift_r(w, w, rot);
+                    const unsigned hz = RTX_HASZERO_NIB(wr ^ pat);
+                    if (!hz) break;
+                    const int jj = (int)((((unsigned)(__ffs(hz) - 1) >> 2) + (rot >> 2)) & 7u);
+                    const unsigned neww = w ^ ((unsigned)(phase ^ RTX_PH_BUSY) << (4 * jj));
+                    const unsigned old = atomicCAS(const_cast<unsigned*>(colstate) + col, w, neww);
+                    if (old == w) { j = jj; break; }
+                    w = old;
+                }
             }
         }
         const bool mine = j >= 0;
@@ -645,7 +655,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
         }
         if (mine) {   // publish: slot state first, then its phase nibble (BUSY -> newst)
             __threadfence_block();
-            atomicXor(colstate_a + col, (CW)(RTX_PH_BUSY ^ newst) << (4 * j));
+            atomicXor(const_cast<unsigned*>(colstate) + col, (unsigned)(RTX_PH_BUSY ^ newst) << (4 * j));
         }
     }
 #undef RTX_HASZERO_NIB
