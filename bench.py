@@ -309,7 +309,7 @@ def main():
 
     # the stream kernels (HBM-bound): algorithmic bytes of this rank's slice / their CUDA-event time
     roofline_stream = None
-    fused_flat = roofline is not None and my_ms_shade < 1e-3 * max(sum(s["ms_total"] for s in stats), 1e-9)
+    fused_flat = roofline is not None and my_ms_shade < 0.02 * max(sum(s["ms_total"] for s in stats), 1e-9)
     if fused_flat:   # a world of a handful of entries: one kernel per bounce generates, traces and shades (k_bounce_flat); no separate stream kernels
         roofline["kernel"] = "k_bounce_flat"
         roofline["note"] = ("flat world: camera-path generation, closest hit and shading run in ONE kernel per bounce, hits never leave the registers; "
