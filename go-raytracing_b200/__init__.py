@@ -159,6 +159,7 @@ def host() -> C.CDLL:
         H.rth_bucket_render_progressive.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         H.rth_load_hdr.argtypes = [C.c_char_p, _pi, _pi, C.c_void_p, C.c_int64]
         H.rth_write_png.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_int32]
+        H.rth_stats_bar.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_char_p]
         H.rth_parse_obj.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, _pd]
         _host_cache = H
     return _host_cache
@@ -671,6 +672,14 @@ CONFIGS.update({
     "earth": dict(scene="earth", width=800, aspect=16.0 / 9.0, spp=100, depth=50),
     "primitives": dict(scene="primitives", width=800, aspect=16.0 / 9.0, spp=300, depth=25),
 })
+
+
+def stats_bar(pix: np.ndarray, spp: int, depth: int, seconds: float, workers: int) -> str:
+    """drawStatsToFramebuffer (rt/bucket_renderer.go:375-407) on an [H, W, 4] uint8 image, in place; returns the stats line."""
+    assert pix.dtype == np.uint8 and pix.ndim == 3 and pix.shape[2] == 4 and pix.flags.c_contiguous
+    buf = C.create_string_buffer(256)
+    host().rth_stats_bar(pix.ctypes.data, pix.shape[1], pix.shape[0], spp, depth, seconds, workers, buf)
+    return buf.value.decode()
 
 
 def parse_obj(path: str, threads: int = 0):

@@ -416,6 +416,12 @@ public:
     rtx_ctx* Context() { return ctx_; }
     const std::string& LastError() const { return err_; }
     uint64_t seed = 0x9E3779B97F4A7C15ull;
+    // What the reference's Update() does when the last pass ends (rt/bucket_renderer.go:151-155): burn the stats bar into the bottom 30
+    // rows and save "image.png". Off by default in this mirror so that tests and benchmarks see the rendered pixels only;
+    // a display front-end sets burnStats = true, autoSave = "image.png" to behave exactly like the reference.
+    bool burnStats = false;
+    std::string autoSave;
+    void DrawStatsToFramebuffer();   // rt/bucket_renderer.go:375-407 (black bar, white 7x13 text "WxH | SPP:n | Depth:d | 100.0% | time | Workers: n")
 
 private:
     void renderPass(int pass);   // worker thread: one rtx_render_pass + resolve into back_, then passComplete = true
@@ -423,7 +429,7 @@ private:
     CameraPtr camera_;
     std::shared_ptr<FlatScene> flat_;
     rtx_ctx* ctx_ = nullptr;
-    int w_ = 0, h_ = 0, currentPass_ = 0, totalPasses_ = 3;
+    int w_ = 0, h_ = 0, currentPass_ = 0, totalPasses_ = 3, numWorkers_ = 0;
     bool completed_ = false, renderStarted_ = false;
     double duration_s_ = 0;
     std::chrono::steady_clock::time_point renderStart_;
@@ -438,5 +444,8 @@ std::shared_ptr<BucketRenderer> NewBucketRenderer(CameraPtr camera, HittablePtr 
 std::shared_ptr<BucketRenderer> NewProgressiveRenderer(CameraPtr camera, HittablePtr world);
 
 int WritePNG(const std::string& path, const uint8_t* rgba, int w, int h);
+std::string FormatDuration(double seconds);                                                                    // rt/utils.go:50-61
+std::string StatsBarText(int width, int height, int spp, int depth, double seconds, int numWorkers);          // rt/bucket_renderer.go:391-398
+void DrawStatsBar(uint8_t* rgba, int w, int h, const std::string& text);                                       // rt/bucket_renderer.go:378-406
 
 }  // namespace rt

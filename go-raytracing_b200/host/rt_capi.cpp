@@ -140,6 +140,14 @@ int32_t rth_parse_obj(const char* path, int32_t threads, int64_t* n_vertices, in
     }
 }
 
+// drawStatsToFramebuffer on a caller-owned RGBA8 image; text_out (>= 256 bytes, may be NULL) receives the stats line.
+int32_t rth_stats_bar(uint8_t* rgba, int32_t w, int32_t h, int32_t spp, int32_t depth, double seconds, int32_t workers, char* text_out) {
+    const std::string t = StatsBarText(w, h, spp, depth, seconds, workers);
+    DrawStatsBar(rgba, w, h, t);
+    if (text_out) std::snprintf(text_out, 256, "%s", t.c_str());
+    return RTX_OK;
+}
+
 int32_t rth_write_png(const char* path, const uint8_t* rgba, int32_t w, int32_t h) { return WritePNG(path, rgba, w, h); }
 
 }  // extern "C"

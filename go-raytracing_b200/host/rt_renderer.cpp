@@ -4,7 +4,8 @@
 // goroutines — and SaveImage/IsCompleted/GetRenderDuration keep the reference's behaviour; the body of renderPass (rt/bucket_renderer.go:170-214: worker goroutines, 32x32 tiles,
 // GetRay/RayColor per sample, gamma + RGBA8 pack) is ONE call into the CUDA library per pass.
 // bucketSize / numWorkers are accepted and ignored (the device schedules its own work).
-// The ebiten Draw()/stats-bar overlay is display cosmetics and out of scope.
+// The stats bar the reference burns into the saved image (drawStatsToFramebuffer, rt/bucket_renderer.go:375-407) is
+// DrawStatsToFramebuffer() below; the live ebiten overlay of Draw() (:303-373) belongs to the display and stays in Go.
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -17,7 +18,7 @@ static void check(rtx_ctx* ctx, int32_t rc, const char* what) {
     if (rc != RTX_OK) throw std::runtime_error(std::string(what) + ": " + rtx_last_error(ctx));
 }
 
-BucketRenderer::BucketRenderer(CameraPtr camera, HittablePtr world, int /*bucketSize*/, int /*numWorkers*/, int deviceId) : camera_(camera) {
+BucketRenderer::BucketRenderer(CameraPtr camera, HittablePtr world, int /*bucketSize*/, int numWorkers, int deviceId) : camera_(camera), numWorkers_(numWorkers) {
     flat_ = Flatten(world, *camera);
     int32_t rc = rtx_create(deviceId, &ctx_);
     if (rc != RTX_OK) throw std::runtime_error(std::string("rtx_create: ") + rtx_last_error(nullptr));
@@ -80,6 +81,10 @@ int BucketRenderer::Update() {  // rt/bucket_renderer.go:127-164
         } else {
             completed_ = true;
             duration_s_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - renderStart_).count();
+            if (!failed) {   // rt/bucket_renderer.go:151-155: the bar is burnt in, then the image is saved
+                if (burnStats) DrawStatsToFramebuffer();
+                if (!autoSave.empty()) SaveImage(autoSave);
+            }
             return failed ? -1 : 0;
         }
     }
@@ -102,6 +107,81 @@ std::shared_ptr<BucketRenderer> NewBucketRenderer(CameraPtr camera, HittablePtr 
 }
 std::shared_ptr<BucketRenderer> NewProgressiveRenderer(CameraPtr camera, HittablePtr world) {
     return std::make_shared<BucketRenderer>(camera, world, 0, 0);
+}
+
+// ---- stats bar (rt/bucket_renderer.go:375-407, rt/utils.go:50-61) -------------------------------------------
+std::string FormatDuration(double seconds) {
+    // time.Duration is whole nanoseconds; Hours()/Minutes()/Seconds() are float divisions truncated by int()
+    const long long total = (long long)seconds;
+    const int hours = (int)(total / 3600), minutes = (int)((total / 60) % 60), secs = (int)(total % 60);
+    char buf[64];
+    if (hours > 0) std::snprintf(buf, sizeof buf, "%dh %dm %ds", hours, minutes, secs);
+    else if (minutes > 0) std::snprintf(buf, sizeof buf, "%dm %ds", minutes, secs);
+    else std::snprintf(buf, sizeof buf, "%.2fs", seconds);
+    return buf;
+}
+std::string StatsBarText(int width, int height, int spp, int depth, double seconds, int numWorkers) {
+    char buf[256];
+    std::snprintf(buf, sizeof buf, "%dx%d | SPP:%d | Depth:%d | 100.0%% | %s | Workers: %d", width, height, spp, depth,
+                  FormatDuration(seconds).c_str(), numWorkers);
+    return buf;
+}
+// basicfont.Face7x13 (the X11 misc-fixed 7x13 face, public domain): one byte per row, bit 7 = leftmost pixel, 13 rows per
+// 7-pixel-wide cell. Only the characters the stats line can contain; the rows of all but '7', '9' and 'm' are pinned by the bar of
+// the reference's committed image.png (tests/golden/image_png_stats_bar.json), those three follow the font's BDF source.
+struct Glyph7x13 { char c; uint8_t rows[13]; };
+static const Glyph7x13 kGlyphs[] = {
+    {'%', {0x00, 0x00, 0x44, 0xA4, 0x48, 0x10, 0x10, 0x20, 0x48, 0x94, 0x88, 0x00, 0x00}},
+    {'.', {0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x10, 0x38, 0x10, 0x00}},
+    {'0', {0x00, 0x00, 0x30, 0x48, 0x84, 0x84, 0x84, 0x84, 0x84, 0x48, 0x30, 0x00, 0x00}},
+    {'1', {0x00, 0x00, 0x10, 0x30, 0x50, 0x10, 0x10, 0x10, 0x10, 0x10, 0x7C, 0x00, 0x00}},
+    {'2', {0x00, 0x00, 0x78, 0x84, 0x84, 0x04, 0x08, 0x30, 0x40, 0x80, 0xFC, 0x00, 0x00}},
+    {'3', {0x00, 0x00, 0xFC, 0x04, 0x08, 0x10, 0x38, 0x04, 0x04, 0x84, 0x78, 0x00, 0x00}},
+    {'4', {0x00, 0x00, 0x08, 0x18, 0x28, 0x48, 0x88, 0x88, 0xFC, 0x08, 0x08, 0x00, 0x00}},
+    {'5', {0x00, 0x00, 0xFC, 0x80, 0x80, 0xB8, 0xC4, 0x04, 0x04, 0x84, 0x78, 0x00, 0x00}},
+    {'6', {0x00, 0x00, 0x38, 0x40, 0x80, 0x80, 0xB8, 0xC4, 0x84, 0x84, 0x78, 0x00, 0x00}},
+    {'7', {0x00, 0x00, 0xFC, 0x04, 0x08, 0x08, 0x10, 0x10, 0x20, 0x20, 0x20, 0x00, 0x00}},
+    {'8', {0x00, 0x00, 0x78, 0x84, 0x84, 0x84, 0x78, 0x84, 0x84, 0x84, 0x78, 0x00, 0x00}},
+    {'9', {0x00, 0x00, 0x78, 0x84, 0x84, 0x8C, 0x74, 0x04, 0x04, 0x08, 0x70, 0x00, 0x00}},
+    {':', {0x00, 0x00, 0x00, 0x00, 0x10, 0x38, 0x10, 0x00, 0x00, 0x10, 0x38, 0x10, 0x00}},
+    {'D', {0x00, 0x00, 0xF8, 0x44, 0x44, 0x44, 0x44, 0x44, 0x44, 0x44, 0xF8, 0x00, 0x00}},
+    {'P', {0x00, 0x00, 0xF8, 0x84, 0x84, 0x84, 0xF8, 0x80, 0x80, 0x80, 0x80, 0x00, 0x00}},
+    {'S', {0x00, 0x00, 0x78, 0x84, 0x80, 0x80, 0x78, 0x04, 0x04, 0x84, 0x78, 0x00, 0x00}},
+    {'W', {0x00, 0x00, 0x84, 0x84, 0x84, 0x84, 0xB4, 0xB4, 0xCC, 0xCC, 0x84, 0x00, 0x00}},
+    {'e', {0x00, 0x00, 0x00, 0x00, 0x00, 0x78, 0x84, 0xFC, 0x80, 0x84, 0x78, 0x00, 0x00}},
+    {'h', {0x00, 0x00, 0x80, 0x80, 0x80, 0xB8, 0xC4, 0x84, 0x84, 0x84, 0x84, 0x00, 0x00}},
+    {'k', {0x00, 0x00, 0x80, 0x80, 0x80, 0x88, 0x90, 0xE0, 0x90, 0x88, 0x84, 0x00, 0x00}},
+    {'m', {0x00, 0x00, 0x00, 0x00, 0x00, 0xEC, 0x92, 0x92, 0x92, 0x92, 0x82, 0x00, 0x00}},
+    {'o', {0x00, 0x00, 0x00, 0x00, 0x00, 0x78, 0x84, 0x84, 0x84, 0x84, 0x78, 0x00, 0x00}},
+    {'p', {0x00, 0x00, 0x00, 0x00, 0x00, 0xB8, 0xC4, 0x84, 0xC4, 0xB8, 0x80, 0x80, 0x80}},
+    {'r', {0x00, 0x00, 0x00, 0x00, 0x00, 0xB8, 0x44, 0x40, 0x40, 0x40, 0x40, 0x00, 0x00}},
+    {'s', {0x00, 0x00, 0x00, 0x00, 0x00, 0x78, 0x84, 0x60, 0x18, 0x84, 0x78, 0x00, 0x00}},
+    {'t', {0x00, 0x00, 0x00, 0x40, 0x40, 0xF0, 0x40, 0x40, 0x40, 0x44, 0x38, 0x00, 0x00}},
+    {'x', {0x00, 0x00, 0x00, 0x00, 0x00, 0x84, 0x48, 0x30, 0x30, 0x48, 0x84, 0x00, 0x00}},
+    {'|', {0x00, 0x00, 0x10, 0x10, 0x10, 0x10, 0x10, 0x10, 0x10, 0x10, 0x10, 0x00, 0x00}},
+};
+void DrawStatsBar(uint8_t* pix, int w, int h, const std::string& text) {
+    const int barHeight = 30, barY = h - barHeight;
+    auto set = [&](int x, int y, uint8_t v) {   // image.RGBA.Set ignores points outside the image
+        if (x < 0 || y < 0 || x >= w || y >= h) return;
+        uint8_t* p = pix + 4 * ((size_t)y * w + x);
+        p[0] = p[1] = p[2] = v; p[3] = 255;
+    };
+    for (int y = barY; y < h; y++)
+        for (int x = 0; x < w; x++) set(x, y, 0);
+    // text.Draw at (15, barY + 10): the origin is the top-left corner of the first 7x13 cell, white, no anti-aliasing
+    for (size_t i = 0; i < text.size(); i++) {
+        const Glyph7x13* g = nullptr;
+        for (const Glyph7x13& k : kGlyphs) if (k.c == text[i]) { g = &k; break; }
+        if (!g) continue;   // ' ' and anything the format string cannot produce
+        for (int ry = 0; ry < 13; ry++)
+            for (int rx = 0; rx < 7; rx++)
+                if (g->rows[ry] & (0x80 >> rx)) set(15 + 7 * (int)i + rx, barY + 10 + ry, 255);
+    }
+}
+void BucketRenderer::DrawStatsToFramebuffer() {
+    std::lock_guard<std::mutex> lk(mu_);
+    DrawStatsBar(pix_.data(), w_, h_, StatsBarText(w_, h_, camera_->SamplesPerPixel, camera_->MaxDepth, duration_s_, numWorkers_));
 }
 
 // ---- PNG (stored deflate blocks; rt/bucket_renderer.go:417-438 uses image/png) ------------------------------

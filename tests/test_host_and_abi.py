@@ -2,6 +2,7 @@
 to run without a device (no fallback), and the C++ host mirror of the Go rt API builds / flattens the configured
 scenes the way the reference's scene functions describe them (rt/scenes.go)."""
 import ctypes as C
+import json
 import os
 import re
 
@@ -142,6 +143,28 @@ def test_png_writer(grt, tmp_path):
     p = str(tmp_path / "t.png")
     assert grt.host().rth_write_png(p.encode(), img.ctypes.data, 7, 5) == 0
     assert np.array_equal(np.asarray(Image.open(p)), img)
+
+
+def test_stats_bar_matches_reference_image(grt):
+    """drawStatsToFramebuffer (rt/bucket_renderer.go:375-407): the bottom 30 rows of the reference's committed image.png are a
+    black bar with the stats line in basicfont.Face7x13 — the one bit-exact golden in the reference tree
+    (tests/golden/image_png_stats_bar.json, tools/make_golden.py). Layout, text and every glyph used must match bit for bit."""
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "image_png_stats_bar.json")))
+    W, H = g["width"], g["height"]
+    pix = np.full((H, W, 4), 77, np.uint8)
+    text = grt.stats_bar(pix, g["spp"], g["depth"], g["seconds"], g["workers"])
+    assert text == g["text"]
+    want = np.unpackbits(np.frombuffer(bytes.fromhex(g["bits_hex"]), np.uint8))[:30 * W].reshape(30, W).astype(bool)
+    bar = pix[H - 30:]
+    assert np.all(bar[..., 3] == 255) and np.all(pix[:H - 30] == 77)            # only the bar is touched
+    assert np.array_equal(bar[..., 0] == 255, want) and np.all((bar[..., :3] == 0) | (bar[..., :3] == 255))
+    assert np.array_equal(bar[..., 0], bar[..., 1]) and np.array_equal(bar[..., 0], bar[..., 2])
+    # FormatDuration (rt/utils.go:50-61) and clipping of images shorter than the bar (image.RGBA.Set ignores outside points)
+    small = np.zeros((20, 64, 4), np.uint8)
+    assert grt.stats_bar(small, 10, 5, 3725.9, 8) == "64x20 | SPP:10 | Depth:5 | 100.0% | 1h 2m 5s | Workers: 8"
+    assert np.all(small[..., 3] == 255)
+    assert grt.stats_bar(small, 10, 5, 125.5, 8).split(" | ")[4] == "2m 5s"
+    assert grt.stats_bar(small, 10, 5, 0.066, 8).split(" | ")[4] == "0.07s"
 
 
 # ---- LoadOBJ: the parallel text parse gives what the reference's sequential scan gives (rt/obj_loader.go:15-102) ----

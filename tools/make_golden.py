@@ -12,6 +12,7 @@ from PIL import Image
 
 REF = "/root/reference/image.png"
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "image_png_region_means.json")
+OUT_BAR = os.path.join(os.path.dirname(OUT), "image_png_stats_bar.json")
 
 
 def main():
@@ -25,6 +26,15 @@ def main():
     json.dump(dict(source="byvfx/go-raytracing image.png (hdri-test 800x450, 200 spp, depth 20)", width=W, height=H, block=bs, rows=rows,
                    cols=cols, means=means), open(OUT, "w"))
     print("wrote", OUT, rows, "x", cols, "blocks")
+    # The stats bar of the same image (rows 420..449: drawStatsToFramebuffer, rt/bucket_renderer.go:375-407) is pure black and white:
+    # one bit per pixel, the only bit-exact golden the reference tree offers. Pins DrawStatsBar's layout and 7x13 glyph rows.
+    raw = np.asarray(Image.open(REF).convert("RGB"))[420:450]
+    assert set(np.unique(raw)) <= {0, 255}
+    bits = np.packbits((raw[..., 0] == 255).astype(np.uint8), axis=None)
+    json.dump(dict(source="byvfx/go-raytracing image.png rows 420..449 (white = 1), np.packbits row-major", width=W, height=H, bar_rows=30,
+                   text="800x450 | SPP:200 | Depth:20 | 100.0% | 30.61s | Workers: 32", spp=200, depth=20, seconds=30.61, workers=32,
+                   bits_hex=bits.tobytes().hex()), open(OUT_BAR, "w"))
+    print("wrote", OUT_BAR)
 
 
 if __name__ == "__main__":
