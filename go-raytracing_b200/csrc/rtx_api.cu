@@ -15,6 +15,13 @@
 #include "rtx_kernels.cuh"
 #include "rtx_bvh_gpu.cuh"
 
+#ifndef RTX_PRETEST_BARE_DEFAULT
+#define RTX_PRETEST_BARE_DEFAULT 0
+#endif
+#ifndef RTX_FUSE_TREE_DEFAULT
+#define RTX_FUSE_TREE_DEFAULT 0
+#endif
+
 using rtxbvh::Box;
 using rtxbvh::Node4;
 
@@ -52,6 +59,8 @@ struct rtx_ctx {
     cudaEvent_t ev_shaded = nullptr, ev_connected[2] = {nullptr, nullptr};
     int overlap_connect = 1;
     int fuse_flat = 1;        // flat worlds: closest hit and shading in one kernel (k_bounce_flat); 0 = k_extend_flat + k_shade
+    int fuse_tree = RTX_FUSE_TREE_DEFAULT;   // hierarchy worlds: shading inside the persistent trace kernel's RETIRE phase (k_bounce); 0 = k_extend + k_shade
+    int pretest_bare = RTX_PRETEST_BARE_DEFAULT;   // hierarchy worlds with a mesh: up to this many bare bounded primitives (the Cornell walls) leave the TLAS and are tested for every ray when it enters the pool (0 = all entries in the TLAS)
     int shade_split = 0;      // k_shade as one launch per material queue (1) or one launch over all queues (0, the default: hdri-test 61.5 against 64.0 ms of shading per 64 spp, random 3.1 against 3.9 — the one-material kernels need 48-80 registers instead of 128, but six short launches have six tails)
     unsigned mat_kinds = ~0u;  // bit q: some material of the uploaded scene shades through queue q
     std::string err;
@@ -182,8 +191,9 @@ int32_t rtx_create(int32_t device_id, rtx_ctx** out) {
     {   // persistent trace kernels: opt in to the large dynamic shared-memory pool, size the grid to one resident wave
         const int smem = (int)RTX_TRACE_SMEM_BYTES;
         int occ = 0, minOcc = 1 << 30;
-        const void* kernels[6] = {(const void*)k_extend<false>, (const void*)k_extend<true>, (const void*)k_extend<false, true>, (const void*)k_connect<false>,
-                                  (const void*)k_connect<true>, (const void*)k_trace_closest};
+        const void* kernels[] = {(const void*)k_extend<false>, (const void*)k_extend<true>, (const void*)k_extend<false, true>, (const void*)k_connect<false>,
+                                 (const void*)k_connect<true>, (const void*)k_trace_closest, (const void*)k_bounce<false>, (const void*)k_bounce<true>,
+                                 (const void*)k_bounce<false, true>};
         // developer knob: shared-memory carve-out in KB (the rest of the 256 KB array is L1); fewer resident blocks, more L1
         const char* carveEnv = getenv("RTX_TRACE_CARVEOUT_KB");
         const int carveKB = carveEnv ? atoi(carveEnv) : 0;
@@ -258,6 +268,11 @@ int32_t rtx_set_option(rtx_ctx* ctx, const char* key, int64_t value) {
     else if (k == "pixel_major") ctx->pixel_major = value != 0;
     else if (k == "fuse_flat") ctx->fuse_flat = value != 0;
     else if (k == "shade_split") ctx->shade_split = value != 0;
+    else if (k == "fuse_tree") ctx->fuse_tree = value != 0;
+    else if (k == "pretest_bare") {   // takes effect at the next rtx_scene_upload
+        if (value < 0 || value > 64) return fail(ctx, RTX_ERR_INVALID, "pretest_bare must be in 0..64");
+        ctx->pretest_bare = (int)value;
+    }
     else if (k == "overlap_connect") ctx->overlap_connect = value != 0;   // k_connect on its own stream beside the next iteration (default on)
     else if (k == "flat_max_entries") {   // 0 = always traverse the hierarchy
         if (value < 0 || value > 64) return fail(ctx, RTX_ERR_INVALID, "flat_max_entries must be in 0..64");
@@ -678,9 +693,21 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     // ---- TLAS over bounded entries; unbounded ones (planes) are tested for every ray
     std::vector<int> unbounded, boundedIdx;
     std::vector<Box> tb;
+    // Bare bounded primitives beside a mesh (the walls of CornellBoxLucy): a TLAS leaf costs such a ray an ENTRY round of the persistent
+    // kernel that only a few lanes share, while the same float64 test at refill runs for every lane of the warp and hands the traversal a
+    // finite interval from its first node on. Closest hits and any-hit answers do not depend on where an entry is tested.
+    auto bareBounded = [&](int e) {
+        const DEntry& E = entries[e];
+        return E.kind != RTX_GEOM_LIST && E.kind != RTX_GEOM_MESH && E.xf_count == 0 && E.volume < 0 && entryBox[e].finite();
+    };
+    int nBare = 0;
+    bool hasMesh = false;
+    for (int e = 0; e < d->n_entries; e++) { nBare += bareBounded(e) ? 1 : 0; hasMesh |= entries[e].kind == RTX_GEOM_MESH && entries[e].a >= 0; }
+    const bool pretest = hasMesh && nBare > 0 && nBare <= ctx->pretest_bare;
     for (int e = 0; e < d->n_entries; e++) {
         bool empty = (entries[e].kind == RTX_GEOM_LIST && entries[e].b == 0) || (entries[e].kind == RTX_GEOM_MESH && entries[e].a < 0);
         if (empty) continue;
+        if (pretest && bareBounded(e)) { unbounded.push_back(e); continue; }
         if (!entryBox[e].finite()) {
             if (entries[e].kind == RTX_GEOM_MESH || entries[e].volume >= 0) return fail(ctx, RTX_ERR_UNSUPPORTED, "entry %d: unbounded mesh/volume", e);
             if (entries[e].kind == RTX_GEOM_LIST) return fail(ctx, RTX_ERR_UNSUPPORTED, "entry %d: a HittableList containing an infinite Plane is outside the device path", e);
@@ -1075,6 +1102,12 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
                 else k_bounce_flat<false><<<gridStream, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
                 if (timing) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); }
                 launches -= 2;
+            } else if (!ctx->scene_flat && ctx->fuse_tree) {   // trace + shade in the persistent kernel: the hit never leaves the lane that found it
+                if (ctx->S.n_images > 0) k_bounce<false, true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
+                else if (ctx->count_stats & 1) k_bounce<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
+                else k_bounce<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
+                if (timing) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); }
+                launches -= 1;
             } else {
             if (ctx->S.n_images > 0) {   // hit records carry (u, v); this variant is not instrumented
                 if (ctx->scene_flat) k_extend_flat<false, true><<<gridStream, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, pp);

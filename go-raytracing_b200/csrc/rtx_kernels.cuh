@@ -743,6 +743,70 @@ __global__ void __launch_bounds__(256, RTX_BOUNCE_BLOCKS) k_bounce_flat(Ctl* ctl
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->ext_rays, (unsigned long long)n);
 }
 
+// ---- K2+K4 fused for hierarchy worlds (option fuse_tree) ---------------------------------------------------------------------------
+// The persistent trace kernel with shading in its RETIRE phase: the lane that retires a finished query shades it (same shade_element,
+// same Philox counters, so the paths are the ones k_extend + k_shade produce) and appends the survivor and its shadow requests. The hit
+// record (64 B written, 64 B read back), the queue slots and k_shade's gather of the path record disappear, and the HBM-bound shading
+// stream runs inside the latency-bound traversal instead of after it. The material code is one out-of-line call (bounce_shade), so the
+// traversal loop keeps its registers; what the call needs travels through local memory.
+template <bool UV>
+__device__ __noinline__ void bounce_shade(const DevScene* S, const DevCamera* C, const PassParams* pp, const Pool* pool, const char* rec, const RayD* rp,
+                                          const Best* bp, ShadeVars* Vp) {
+    const RayD r = *rp;
+    const Best b = *bp;
+    ShadeVars V;
+    V.reset();
+    V.tm = r.tm;
+    V.pixbits = *reinterpret_cast<const double*>(rec + 56);
+    V.th = *reinterpret_cast<const float4*>(rec + 64);
+    int type = Q_MISS;
+    HitInfo hi;
+    hi.P = hi.N = d3(0, 0, 0); hi.mat = 0; hi.front = false; hi.u = hi.v = 0;
+    if (b.entry >= 0) {
+        finalize_hit(*S, r, best_to_hit(b), UV, hi);
+        const int mt = S->mats[hi.mat].type;
+        type = mt == RTX_MAT_LAMBERTIAN ? Q_LAMBERTIAN : mt == RTX_MAT_METAL ? Q_METAL : mt == RTX_MAT_DIELECTRIC ? Q_DIELECTRIC
+             : mt == RTX_MAT_DIFFUSE_LIGHT ? Q_LIGHT : Q_ISOTROPIC;
+    }
+    shade_element(*S, *C, *pp, *pool, type, d3(r.dx, r.dy, r.dz), hi.P, hi.N, UV ? (float)hi.u : 0.f, UV ? (float)hi.v : 0.f, hi.mat, hi.front, V);
+    *Vp = V;
+}
+template <bool UV>
+struct BounceTreePolicyT {
+    static constexpr bool ANY_HIT = false;
+    Ctl* ctl; const Pool* pool; int cur; const DevScene* S; const DevCamera* C; const PassParams* pp; const char* rec;
+    __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:451
+    __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
+        const char* q = rec + (size_t)job * RTX_REC_BYTES;
+        const D4 a = ld256d(q), c = ld256d(q + 32);
+        r.ox = a.x; r.oy = a.y; r.oz = a.z; r.tm = a.w; r.dx = c.x; r.dy = c.y; r.dz = c.z;
+        tmax = RTX_INF_D;
+    }
+    __device__ __forceinline__ VolumeRng volume_rng(int job) const {
+        const char* q = rec + (size_t)job * RTX_REC_BYTES;
+        const unsigned long long ps = (unsigned long long)__double_as_longlong(ld256d(q + 32).w);
+        const int bounce = __float_as_int(reinterpret_cast<const float4*>(q + 64)->w) & 0xffff;
+        VolumeRng vr; vr.k0 = pp->seed_lo; vr.k1 = pp->seed_hi; vr.c0 = (uint32_t)ps; vr.c1 = (uint32_t)(ps >> 32); vr.c2 = (uint32_t)bounce * 4u; vr.transparent = false;
+        return vr;
+    }
+    __device__ __forceinline__ void retire(int job, bool valid, const RayD& r, const Best& b) const {
+        ShadeVars V;
+        if (valid) bounce_shade<UV>(S, C, pp, pool, rec + (size_t)job * RTX_REC_BYTES, &r, &b, &V);
+        else V.reset();
+        shade_commit(ctl, *pool, cur, V);
+    }
+};
+template <bool COUNT, bool UV = false>
+__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_bounce(Ctl* ctl, const __grid_constant__ Pool pool, int cur, const __grid_constant__ DevScene S,
+                                                                               const __grid_constant__ DevCamera C, const __grid_constant__ PassParams pp, int* spill) {
+    BounceTreePolicyT<UV> P{ctl, &pool, cur, &S, &C, &pp, pool.records(cur)};
+    TraceCounters tc = {0, 0, 0, 0, 0};
+    const int n = ctl->n_active;
+    trace_persistent<BounceTreePolicyT<UV>, COUNT, RTX_TRACE_SLOTS>(S, P, &ctl->cur_extend, n, tc, spill, rtx_smem);
+    if (COUNT) flush_counters(ctl, tc);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->ext_rays, (unsigned long long)n);
+}
+
 // ---- K3: connect — shadow rays of next-event estimation (any hit in [0.001, tmax]) ----------------------------------
 struct ConnectPolicy {
     static constexpr bool ANY_HIT = true;

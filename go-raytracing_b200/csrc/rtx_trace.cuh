@@ -623,15 +623,21 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                     double tmax;
                     P.load(my, r, tmax);
                     B.reset(tmax);
-                    // entries with unbounded geometry (infinite Plane, rt/plane.go:17) are tested for every ray
+                    // entries tested for every ray: unbounded geometry (infinite Plane, rt/plane.go:17) and, with option pretest_bare, the
+                    // few bare primitives beside a mesh (the Cornell walls) that rtx_scene_upload kept out of the TLAS
                     for (int q = 0; q < S.n_unbounded; q++) {
                         const int ei = S.unbounded[q];
                         const DEntry e = S.entries[ei];
-                        if (e.xf_count == 0) {   // the bare ground plane of RandomScene / HDRITestScene: inlined
+                        if (e.xf_count == 0 && e.kind == RTX_GEOM_PLANE) {   // the bare ground plane of RandomScene / HDRITestScene: inlined
                             if (COUNT) tc.planes++;
                             double t = isect_plane(S.planes + 8 * (size_t)e.index, r);
                             if (!(tmin < t && (t < B.t || (B.have && t == B.t)))) t = RTX_NAN_D;
                             B.offer(t, ei, e.rank, RTX_GEOM_PLANE, e.index, 0, 0);
+                        } else if (e.xf_count == 0 && e.kind == RTX_GEOM_QUAD) {
+                            if (COUNT) tc.quads++;
+                            const double t = isect_quad(S.quads + 16 * (size_t)e.index, r, tmin, B.t, nullptr);
+                            B.offer(t, ei, e.rank, RTX_GEOM_QUAD, e.index, 0, 0);
+                            if (Policy::ANY_HIT && B.have) break;
                         } else {
                             RayD ro = r;
                             xform_ray(S, ei, e, ro);

@@ -584,6 +584,69 @@ def test_sample_slices_add_up_and_are_deterministic(grt, ctx):
 
 
 @pytest.mark.gpu
+def test_pretested_bare_entries_are_result_neutral(grt, orc):
+    """Option pretest_bare: the few bare primitives beside a mesh (the walls and the light of CornellBoxLucy) leave the TLAS and are
+    tested for every ray when it enters the trace pool. Where an entry is tested changes neither closest hits nor any-hit answers:
+    hit records are bit-identical with the option on and off (and match the oracle), a rendered pass traces the same rays."""
+    rng = np.random.default_rng(77)
+    sc = grt.config_scene("cornell-lucy", width=160, spp=4, depth=12)
+    o = orc.OracleScene(sc.desc_ptr, sc.cam_ptr)
+    ij, sq, disk, tm = camera_batch(sc.width, sc.height, 40000, rng)
+    rays = o.camera_rays(ij, sq, disk, tm)
+    ho = o.trace_closest(rays)
+    scatter, shadow = secondary_rays(ho, rng, 30000)
+    res, acc = {}, {}
+    for pre in (0, 8):
+        c = grt.Context(0)
+        c.set_option("pretest_bare", pre)
+        c.load(sc)
+        res[pre] = [c.trace_closest(rays), c.trace_closest(scatter), c.trace_closest(shadow, 0.001, 300.0)]
+        c.render_pass(4, 12, seed=9)
+        a, _, n = c.resolve_accum()
+        st = c.stats()
+        acc[pre] = (a, st["extension_rays"], st["shadow_rays"], st["tlas_nodes"])
+        c.close()
+    assert acc[8][3] < acc[0][3], "the option did not take the bare entries out of the TLAS"
+    for a, b in zip(res[0], res[8]):
+        for k in ("entry", "prim", "t", "normal", "p", "front"):
+            assert np.array_equal(a[k], b[k]), f"pretest_bare changes {k}"
+    assert_level1(res[8][0], ho, "cornell-lucy pretest primary")
+    assert_level1(res[8][1], o.trace_closest(scatter), "cornell-lucy pretest scatter")
+    assert acc[0][1] == acc[8][1] and acc[0][2] == acc[8][2]
+    assert np.allclose(acc[0][0], acc[8][0], rtol=5e-5, atol=2e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,width,spp,depth", [("cornell-lucy", 200, 8, 12), ("random", 160, 16, 20), ("cornell-smoke", 120, 16, 5),
+                                                  ("earth", 160, 8, 10), ("primitives", 160, 8, 10)])
+def test_fused_tree_bounce_is_result_neutral(grt, name, width, spp, depth):
+    """Hierarchy worlds can shade inside the persistent trace kernel (option fuse_tree: k_bounce, the hit never leaves the lane that
+    found it) instead of k_extend -> hit records / material queues -> k_shade. Same shade code, same Philox counters: the paths,
+    the ray counts and the contributions are the same set, only the order of the float atomics differs — also with a small pool
+    (many iterations), with volumes, image textures (u, v) and every material."""
+    sc = grt.config_scene(name, width=width, spp=spp, depth=depth)
+    out = {}
+    for fuse in (0, 1):
+        for pool in (0, 8192):
+            c = grt.Context(0)
+            c.set_option("fuse_tree", fuse)
+            c.set_option("flat_max_entries", 0)   # small worlds through the hierarchy kernels too
+            if pool:
+                c.set_option("pool_paths", pool)
+            c.load(sc)
+            c.render_pass(spp, depth, seed=33)
+            acc, _, n = c.resolve_accum()
+            st = c.stats()
+            c.close()
+            assert np.all(n == spp)
+            out[(fuse, pool)] = (acc, st["extension_rays"], st["shadow_rays"])
+    ref = out[(0, 0)]
+    for k, v in out.items():
+        assert v[1] == ref[1] and v[2] == ref[2], k
+        assert np.allclose(v[0], ref[0], rtol=5e-5, atol=2e-5), k
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name,width,spp,depth", [("cornell", 160, 16, 10), ("cornell-lucy", 200, 8, 12), ("cornell-glossy", 160, 16, 5)])
 def test_connect_stream_is_result_neutral(grt, name, width, spp, depth):
     """k_connect of iteration i runs on a second stream beside iteration i + 1 (shadow requests double-buffered by iteration
