@@ -61,6 +61,8 @@ struct rtx_ctx {
     int fuse_flat = 1;        // flat worlds: closest hit and shading in one kernel (k_bounce_flat); 0 = k_extend_flat + k_shade
     int fuse_tree = RTX_FUSE_TREE_DEFAULT;   // hierarchy worlds: shading inside the persistent trace kernel's RETIRE phase (k_bounce); 0 = k_extend + k_shade
     int pretest_bare = RTX_PRETEST_BARE_DEFAULT;   // hierarchy worlds with a mesh: up to this many bare bounded primitives (the Cornell walls) leave the TLAS and are tested for every ray when it enters the pool (0 = all entries in the TLAS)
+    int lean_flat = 1;        // flat worlds: the one-kernel bounce is compiled per scene vocabulary (RTX_FV_*), the smallest covering variant runs; 0 = always the all-features kernel
+    unsigned feat_mask = RTX_F_ALL;   // RTX_F_* bits the uploaded scene needs
     int shade_split = 0;      // k_shade as one launch per material queue (1) or one launch over all queues (0, the default: hdri-test 61.5 against 64.0 ms of shading per 64 spp, random 3.1 against 3.9 — the one-material kernels need 48-80 registers instead of 128, but six short launches have six tails)
     unsigned mat_kinds = ~0u;  // bit q: some material of the uploaded scene shades through queue q
     std::string err;
@@ -93,6 +95,7 @@ struct rtx_ctx {
     std::vector<cudaEvent_t> events;
     int num_sms = 0;
     int* batch_cursor = nullptr;  // job cursor of k_trace_closest
+    int trace_grid_lean = 0;      // grid of the lean variants of the persistent trace kernels
     int* trace_spill = nullptr;   // global overflow columns of the trace kernels' shared-memory stacks
     int* trace_spill2 = nullptr;  // the same for k_connect (it may run beside k_extend)
     int trace_grid = 0;           // persistent grid: SMs x resident blocks
@@ -154,6 +157,16 @@ int32_t rtx_abi_version(void) { return RTX_ABI_VERSION; }
 
 const char* rtx_last_error(const rtx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+// Which kernel variant covers the uploaded scene and the camera: 0 = RTX_F_ALL, 1 = RTX_FV_LUCY, 2 = RTX_FV_SKY, 3 = RTX_FV_BOX
+static int lean_variant(const rtx_ctx* ctx) {
+    if (!ctx->lean_flat) return 0;
+    const unsigned need = ctx->feat_mask | ((ctx->have_camera && (ctx->C.camera_motion || ctx->C.free_camera)) ? RTX_F_CAM_SLOW : 0u);
+    if (!(need & ~RTX_FV_LUCY)) return 1;
+    if (!(need & ~RTX_FV_SKY)) return 2;
+    if (!(need & ~RTX_FV_BOX)) return 3;
+    return 0;
+}
+
 int32_t rtx_create(int32_t device_id, rtx_ctx** out) {
     if (!out) return fail(nullptr, RTX_ERR_INVALID, "rtx_create: out is NULL");
     *out = nullptr;
@@ -188,12 +201,17 @@ int32_t rtx_create(int32_t device_id, rtx_ctx** out) {
         rtx_destroy(ctx);
         return RTX_ERR_CUDA;
     }
-    {   // persistent trace kernels: opt in to the large dynamic shared-memory pool, size the grid to one resident wave
-        const int smem = (int)RTX_TRACE_SMEM_BYTES;
+    for (int group = 0; group < 2; group++) {   // persistent trace kernels: opt in to the large dynamic shared-memory pool, size the grid to one resident wave
+        const int smem = group == 0 ? (int)RTX_TRACE_SMEM_BYTES : (int)RTX_TRACE_SMEM_BYTES_LEAN;
         int occ = 0, minOcc = 1 << 30;
-        const void* kernels[] = {(const void*)k_extend<false>, (const void*)k_extend<true>, (const void*)k_extend<false, true>, (const void*)k_connect<false>,
-                                 (const void*)k_connect<true>, (const void*)k_trace_closest, (const void*)k_bounce<false>, (const void*)k_bounce<true>,
-                                 (const void*)k_bounce<false, true>};
+        const std::vector<const void*> kernels = group == 0
+            ? std::vector<const void*>{(const void*)k_extend<false>, (const void*)k_extend<true>, (const void*)k_extend<false, true>, (const void*)k_connect<false>,
+                                 (const void*)k_connect<true>, (const void*)k_trace_closest<>, (const void*)k_bounce<false>, (const void*)k_bounce<true>,
+                                 (const void*)k_bounce<false, true>}
+            // the lean variants (RTX_FV_*) need fewer registers: their own block count, pool size and grid
+            : std::vector<const void*>{(const void*)k_extend<false, false, RTX_FV_LUCY>, (const void*)k_extend<false, false, RTX_FV_SKY>,
+                                 (const void*)k_connect<false, RTX_FV_LUCY>, (const void*)k_connect<false, RTX_FV_SKY>, (const void*)k_trace_closest<RTX_FV_LUCY>,
+                                 (const void*)k_trace_closest<RTX_FV_SKY>};
         // developer knob: shared-memory carve-out in KB (the rest of the 256 KB array is L1); fewer resident blocks, more L1
         const char* carveEnv = getenv("RTX_TRACE_CARVEOUT_KB");
         const int carveKB = carveEnv ? atoi(carveEnv) : 0;
@@ -208,9 +226,11 @@ int32_t rtx_create(int32_t device_id, rtx_ctx** out) {
             minOcc = std::min(minOcc, occ);
         }
         if (carveKB > 0) minOcc = std::max(1, std::min(minOcc, (int)((size_t)carveKB * 1024 / (smem + 1024))));
-        ctx->trace_grid = ctx->num_sms * minOcc;
-        if (getenv("RTX_DEBUG_BATCH")) fprintf(stderr, "[rtx] trace kernels: %d blocks/SM, %d B dynamic smem per block, grid %d\n", minOcc, smem, ctx->trace_grid);
-        size_t spillInts = (size_t)ctx->trace_grid * RTX_TRACE_SLOTS * (RTX_STACK_SIZE - RTX_SMEM_STACK);
+        (group == 0 ? ctx->trace_grid : ctx->trace_grid_lean) = ctx->num_sms * minOcc;
+        if (getenv("RTX_DEBUG_BATCH")) fprintf(stderr, "[rtx] trace kernels (%s): %d blocks/SM, %d B dynamic smem per block, grid %d\n", group ? "lean" : "full", minOcc, smem, ctx->num_sms * minOcc);
+    }
+    {
+        size_t spillInts = std::max((size_t)ctx->trace_grid * RTX_TRACE_SLOTS, (size_t)ctx->trace_grid_lean * RTX_TRACE_SLOTS_LEAN) * (RTX_STACK_SIZE - RTX_SMEM_STACK);
         if ((e = cudaMalloc((void**)&ctx->trace_spill, spillInts * sizeof(int))) != cudaSuccess ||
             (e = cudaMalloc((void**)&ctx->trace_spill2, spillInts * sizeof(int))) != cudaSuccess) {
             fail(nullptr, RTX_ERR_CUDA, "rtx_create: %s", cudaGetErrorString(e));
@@ -269,6 +289,7 @@ int32_t rtx_set_option(rtx_ctx* ctx, const char* key, int64_t value) {
     else if (k == "fuse_flat") ctx->fuse_flat = value != 0;
     else if (k == "shade_split") ctx->shade_split = value != 0;
     else if (k == "fuse_tree") ctx->fuse_tree = value != 0;
+    else if (k == "lean" || k == "lean_flat") ctx->lean_flat = value != 0;
     else if (k == "pretest_bare") {   // takes effect at the next rtx_scene_upload
         if (value < 0 || value > 64) return fail(ctx, RTX_ERR_INVALID, "pretest_bare must be in 0..64");
         ctx->pretest_bare = (int)value;
@@ -865,6 +886,23 @@ int32_t rtx_scene_upload(rtx_ctx* ctx, const rtx_scene_desc* d) {
     ctx->scene_has_mesh = 0;
     for (int e = 0; e < d->n_entries; e++) ctx->scene_has_mesh |= d->entry_geom_kind[e] == RTX_GEOM_MESH;
     ctx->scene_flat = !ctx->scene_has_mesh && d->n_entries <= ctx->flat_max_entries;
+    {   // the vocabulary a flat-world kernel variant has to contain (RTX_F_*)
+        unsigned f = 0;
+        for (const int4& fe : flatSimple)
+            f |= fe.x == RTX_GEOM_QUAD ? RTX_F_QUAD : fe.x == RTX_GEOM_SPHERE ? RTX_F_SPHERE : fe.x == RTX_GEOM_PLANE ? RTX_F_PLANE : RTX_F_OTHER_PRIM;
+        if (!flatComplex.empty() || d->n_volumes > 0) f |= RTX_F_COMPLEX;
+        for (int e = 0; e < d->n_entries; e++)
+            if (entries[e].kind == RTX_GEOM_MESH) f |= RTX_F_MESH | (entries[e].xf_count ? RTX_F_XFORM : 0u);
+        if (pretest)   // pre-tested kinds other than quads go through the generic test of the refill
+            for (int e : unbounded) if (entries[e].kind != RTX_GEOM_QUAD && entries[e].kind != RTX_GEOM_PLANE) f |= RTX_F_COMPLEX;
+        if (d->env_width > 0 && d->env_height > 0 && d->env_rgb) f |= RTX_F_ENV;
+        if (d->n_lights > 0) f |= RTX_F_LIGHTS;
+        for (int i = 0; i < d->n_textures; i++)
+            if (d->tex_type[i] == RTX_TEX_NOISE || d->tex_type[i] == RTX_TEX_IMAGE) f |= RTX_F_TEX_X;
+        for (int i = 0; i < d->n_materials; i++)
+            f |= d->mat_type[i] == RTX_MAT_METAL ? RTX_F_METAL : d->mat_type[i] == RTX_MAT_DIELECTRIC ? RTX_F_DIELECTRIC : d->mat_type[i] == RTX_MAT_ISOTROPIC ? RTX_F_ISOTROPIC : 0u;
+        ctx->feat_mask = f;
+    }
     ctx->ms_upload_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tUpload0).count();
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
     return RTX_OK;
@@ -1072,12 +1110,14 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
     CU(cudaEventRecord(evStart, st));
     // fixed grids: the stream kernels stride over device-side counts, the trace kernels are persistent (one resident wave of
     // warps pulls rays from a device-side cursor); the host only polls the control block every BATCH iterations
-    const int gridStream = std::min((P + 255) / 256, ctx->num_sms * 8), gridTrace = ctx->trace_grid;
+    const int gridStream = std::min((P + 255) / 256, ctx->num_sms * 8), gridTrace = ctx->trace_grid, gridTraceLean = ctx->trace_grid_lean;
     // The shadow rays of iteration i only feed the accumulation buffer, so k_connect(i) runs on a second stream beside
     // k_generate / k_extend / k_shade of iteration i + 1: its blocks move in as the persistent k_extend blocks of the next
     // iteration drain (the tail of a persistent launch otherwise leaves SMs idle), and the render stream has the higher
     // priority, so the critical chain extend -> shade -> extend is served first. Shadow requests, their count and the job
     // cursor are double-buffered by iteration parity; iteration i + 2 waits for k_connect(i).
+    const int lean = lean_variant(ctx);                              // kernel variant by scene vocabulary (0 = all features)
+    const int leanShade = ctx->S.n_images > 0 ? 0 : lean;            // image textures travel with the UV kernels, which exist in full only
     const bool overlap = ctx->overlap_connect && ctx->S.n_lights > 0;
     cudaStream_t sc = overlap ? ctx->connect_stream : st;
     int* const spillC = overlap ? ctx->trace_spill2 : ctx->trace_spill;
@@ -1099,7 +1139,11 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
             if (fused) {   // generate + trace + shade in one kernel: fresh paths and hits stay in registers
                 if (ctx->S.n_images > 0) k_bounce_flat<false, true><<<gridStream, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
                 else if (ctx->count_stats & 1) k_bounce_flat<true><<<gridStream, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
-                else k_bounce_flat<false><<<gridStream, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+                else {
+                    if (lean == 2) k_bounce_flat<false, false, RTX_FV_SKY><<<gridStream, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+                    else if (lean == 3 || lean == 1) k_bounce_flat<false, false, RTX_FV_BOX><<<gridStream, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+                    else k_bounce_flat<false><<<gridStream, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+                }
                 if (timing) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); }
                 launches -= 2;
             } else if (!ctx->scene_flat && ctx->fuse_tree) {   // trace + shade in the persistent kernel: the hit never leaves the lane that found it
@@ -1116,6 +1160,8 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
                 if (ctx->count_stats & 1) k_extend_flat<true><<<gridStream, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, pp);
                 else k_extend_flat<false><<<gridStream, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, pp);
             } else if (ctx->count_stats & 1) k_extend<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
+            else if (lean == 1) k_extend<false, false, RTX_FV_LUCY><<<gridTraceLean, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_LEAN, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
+            else if (lean == 2) k_extend<false, false, RTX_FV_SKY><<<gridTraceLean, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_LEAN, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
             else k_extend<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
             if (timing) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); }
             if (ctx->shade_split) {   // one launch per material queue (launches over empty queues return at once)
@@ -1128,7 +1174,13 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
                 if (ctx->mat_kinds & (1 << Q_ISOTROPIC)) k_shade<Q_ISOTROPIC><<<gs, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
                 launches += 1 + __builtin_popcount(ctx->mat_kinds & ((1 << Q_METAL) | (1 << Q_DIELECTRIC) | (1 << Q_LIGHT) | (1 << Q_ISOTROPIC)));
             } else
-            k_shade<-1><<<std::min((P + 255) / 256, ctx->num_sms * 2 * RTX_SHADE_BLOCKS), 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+            {
+                const int gsh = std::min((P + 255) / 256, ctx->num_sms * 2 * (leanShade ? RTX_SHADE_BLOCKS_LEAN : RTX_SHADE_BLOCKS));
+                if (leanShade == 1) k_shade<-1, RTX_FV_LUCY><<<gsh, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+                else if (leanShade == 2) k_shade<-1, RTX_FV_SKY><<<gsh, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+                else if (leanShade == 3) k_shade<-1, RTX_FV_BOX><<<gsh, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+                else k_shade<-1><<<gsh, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+            }
             }
             if (timing) cudaEventRecord(ev[5], st);
             if (ctx->S.n_lights > 0) {
@@ -1136,8 +1188,11 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
                 if (timing) cudaEventRecord(ev[6], sc);
                 if (ctx->scene_flat) {
                     if (ctx->count_stats & 2) k_connect_flat<true><<<gridStream, 256, 0, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp);
+                    else if (lean == 3 || lean == 1) k_connect_flat<false, RTX_FV_BOX><<<gridStream, 256, 0, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp);
                     else k_connect_flat<false><<<gridStream, 256, 0, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp);
                 } else if (ctx->count_stats & 2) k_connect<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
+                else if (lean == 1) k_connect<false, RTX_FV_LUCY><<<gridTraceLean, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_LEAN, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
+                else if (lean == 2) k_connect<false, RTX_FV_SKY><<<gridTraceLean, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_LEAN, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
                 else k_connect<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
                 if (timing) cudaEventRecord(ev[7], sc);
                 if (overlap) { CU(cudaEventRecord(ctx->ev_connected[cur], sc)); pending[cur] = true; }
@@ -1244,11 +1299,17 @@ int32_t rtx_trace_closest(rtx_ctx* ctx, const double* rays, int64_t n, double tm
     CU(sc.out(&dFront, (unsigned char*)front, n)); CU(sc.out(&dUV, uv, 2 * n)); CU(sc.out(&dP, p, 3 * n));
     if (n > (int64_t)1 << 30) return fail(ctx, RTX_ERR_INVALID, "rtx_trace_closest: at most 2^30 rays per call");
     CU(cudaMemsetAsync(ctx->batch_cursor, 0, sizeof(int), ctx->stream));
-    if (ctx->scene_flat)
-        k_trace_closest_flat<<<std::min((int)((n + 255) / 256), ctx->num_sms * 8), 256, 0, ctx->stream>>>(ctx->S, dRays, (int)n, tmin, tmax, dEntry, dPrim, dT, dN, dFront, dUV, dP);
-    else
-        k_trace_closest<<<ctx->trace_grid, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, ctx->stream>>>(ctx->S, dRays, (int)n, tmin, tmax, ctx->batch_cursor, ctx->trace_spill,
-                                                                                                   dEntry, dPrim, dT, dN, dFront, dUV, dP);
+    const int lean = lean_variant(ctx);   // the variant a rendered pass of this scene runs: the bit-exact tests cover the lean code
+    const int gf = std::min((int)((n + 255) / 256), ctx->num_sms * 8);
+#define RTX_TC_FLAT(F) k_trace_closest_flat<F><<<gf, 256, 0, ctx->stream>>>(ctx->S, dRays, (int)n, tmin, tmax, dEntry, dPrim, dT, dN, dFront, dUV, dP)
+#define RTX_TC_TREE(F) k_trace_closest<F><<<(F) == RTX_F_ALL ? ctx->trace_grid : ctx->trace_grid_lean, RTX_TRACE_THREADS, (F) == RTX_F_ALL ? RTX_TRACE_SMEM_BYTES : RTX_TRACE_SMEM_BYTES_LEAN, ctx->stream>>>(ctx->S, dRays, (int)n, tmin, tmax, ctx->batch_cursor, ctx->trace_spill, dEntry, dPrim, dT, dN, dFront, dUV, dP)
+    if (ctx->scene_flat) {
+        if (lean == 2) RTX_TC_FLAT(RTX_FV_SKY); else if (lean == 3 || lean == 1) RTX_TC_FLAT(RTX_FV_BOX); else RTX_TC_FLAT(RTX_F_ALL);
+    } else {
+        if (lean == 1) RTX_TC_TREE(RTX_FV_LUCY); else if (lean == 2) RTX_TC_TREE(RTX_FV_SKY); else RTX_TC_TREE(RTX_F_ALL);
+    }
+#undef RTX_TC_FLAT
+#undef RTX_TC_TREE
     CU(cudaGetLastError());
     BACK(dEntry, entry_id, n); BACK(dPrim, prim_id, n); BACK(dT, t, n); BACK(dN, normal, 3 * n); BACK(dFront, front, n); BACK(dUV, uv, 2 * n); BACK(dP, p, 3 * n);
     CU(cudaStreamSynchronize(ctx->stream));

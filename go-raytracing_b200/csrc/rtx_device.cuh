@@ -417,10 +417,30 @@ struct HitInfo {
     bool front;
     double u, v;
 };
+// Compile-time scene vocabulary of the one-kernel bounce of flat worlds (k_bounce_flat<.., FEAT>): a variant only contains the code of
+// the primitive kinds, materials, textures and light samplers its mask names, and rtx_render_pass picks the smallest variant that covers
+// the scene (ncu: the all-features kernel is 9904 SASS instructions and stalls 2 cycles per issue on instruction fetch, profiles/r01_k_bounce_flat_hdri.md).
+// Pruned branches are unreachable for a covered scene, so every variant computes what RTX_F_ALL computes.
+#define RTX_F_QUAD 1u
+#define RTX_F_SPHERE 2u
+#define RTX_F_PLANE 4u
+#define RTX_F_OTHER_PRIM 8u    /* Circle, bare Triangle */
+#define RTX_F_COMPLEX 16u      /* Box / Pyramid lists, wrapper chains, Volumes */
+#define RTX_F_ENV 32u          /* HDRI environment: lookup at a miss, importance sampling */
+#define RTX_F_LIGHTS 64u       /* registered area lights: next-event estimation */
+#define RTX_F_TEX_X 128u       /* NoiseTexture, ImageTexture */
+#define RTX_F_CAM_SLOW 256u    /* camera motion / free camera */
+#define RTX_F_METAL 512u
+#define RTX_F_DIELECTRIC 1024u
+#define RTX_F_ISOTROPIC 2048u
+#define RTX_F_MESH 4096u        /* OBJ meshes: BLAS traversal, the TRI phase, instance entry / exit */
+#define RTX_F_XFORM 8192u       /* wrapper chains on mesh instances (wrapped primitives and lists count as RTX_F_COMPLEX) */
+#define RTX_F_ALL 0xffffffffu
+template <unsigned FEAT = RTX_F_ALL>
 __device__ __forceinline__ void finalize_hit(const DevScene& S, const RayD& rw, const Hit& h, bool want_uv, HitInfo& out) {
     DEntry e = S.entries[h.entry];
     out.u = 0; out.v = 0;
-    if (h.kind == RTX_KIND_VOLUME) {  // rt/volume.go:72-76
+    if ((FEAT & RTX_F_COMPLEX) && h.kind == RTX_KIND_VOLUME) {  // rt/volume.go:72-76
         out.P = d3(rw.ox + h.t * rw.dx, rw.oy + h.t * rw.dy, rw.oz + h.t * rw.dz);
         out.N = d3(1, 0, 0);
         out.front = true;
@@ -428,11 +448,11 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const RayD& rw, 
         return;
     }
     RayD r = rw;
-    xform_ray(S, h.entry, e, r);
+    if (FEAT & (RTX_F_COMPLEX | RTX_F_XFORM)) xform_ray(S, h.entry, e, r);
     D3 o = d3(r.ox, r.oy, r.oz), d = d3(r.dx, r.dy, r.dz);
     D3 P = add(o, scale(d, h.t));  // r.At(t), rt/ray.go:21
     D3 n;
-    if (h.kind == RTX_GEOM_SPHERE) {
+    if ((FEAT & RTX_F_SPHERE) && h.kind == RTX_GEOM_SPHERE) {
         const double* s = S.spheres + 8 * (size_t)h.prim;
         D3 c = d3(s[0] + r.tm * s[3], s[1] + r.tm * s[4], s[2] + r.tm * s[5]);
         n = scale(sub(P, c), 1 / s[6]);  // Div(Radius)
@@ -442,16 +462,16 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const RayD& rw, 
             double theta = acos(-n.y), phi = atan2(-n.z, n.x) + PI;
             out.u = phi / (2 * PI); out.v = theta / PI;
         }
-    } else if (h.kind == RTX_GEOM_QUAD) {
+    } else if ((FEAT & RTX_F_QUAD) && h.kind == RTX_GEOM_QUAD) {
         const double* q = S.quads + 16 * (size_t)h.prim;
         n = ld3(q + 12);
         out.mat = S.quad_mat[h.prim];
         if (want_uv) { double uv[2] = {0, 0}; isect_quad(q, r, -RTX_INF_D, RTX_INF_D, uv); out.u = uv[0]; out.v = uv[1]; }
-    } else if (h.kind == RTX_GEOM_TRIANGLE) {
+    } else if ((FEAT & (RTX_F_OTHER_PRIM | RTX_F_COMPLEX | RTX_F_MESH)) && h.kind == RTX_GEOM_TRIANGLE) {
         { const D4 tn = ldg256d(S.tris + RTX_TRI_D * (size_t)h.prim + 8); n = d3(tn.y, tn.z, tn.w); }
         out.mat = S.tri_info[h.prim].y;
         if (want_uv) { double uv[2] = {0, 0}; isect_tri(S.tris + RTX_TRI_D * (size_t)h.prim, r, uv); out.u = uv[0]; out.v = uv[1]; }
-    } else if (h.kind == RTX_GEOM_CIRCLE) {
+    } else if ((FEAT & (RTX_F_OTHER_PRIM | RTX_F_COMPLEX)) && h.kind == RTX_GEOM_CIRCLE) {
         const double* c = S.circles + 8 * (size_t)h.prim;
         n = ld3(c + 3);
         out.mat = S.circle_mat[h.prim];
@@ -462,12 +482,14 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const RayD& rw, 
             out.u = (dot(lp, uu) / c[6] + 1.0) * 0.5;
             out.v = (dot(lp, vv) / c[6] + 1.0) * 0.5;
         }
-    } else {
+    } else if (FEAT & RTX_F_PLANE) {
         n = ld3(S.planes + 8 * (size_t)h.prim + 3);
         out.mat = S.plane_mat[h.prim];
+    } else {
+        n = d3(0, 1, 0); out.mat = 0;   // unreachable for a scene the mask covers
     }
     out.front = dot(d, n) < 0;  // SetFaceNormal with the object-space ray (rt/hittable.go:20-30); never recomputed afterwards
     if (!out.front) n = d3(-n.x, -n.y, -n.z);
-    if (e.xf_count) xform_back(S, h.entry, e, P, n);
+    if ((FEAT & (RTX_F_COMPLEX | RTX_F_XFORM)) && e.xf_count) xform_back(S, h.entry, e, P, n);
     out.P = P; out.N = n;
 }

@@ -125,10 +125,11 @@ __global__ void k_iter_begin(Ctl* ctl, int capacity, int par) {
 }
 
 // ---- K1: camera ray generation (rt/camera.go:368-435) ----------------------------------------------------------
+template <unsigned FEAT = RTX_F_ALL>
 __device__ __forceinline__ RayD camera_ray(const DevCamera& C, int i, int j, double offx, double offy, double tm, double px, double py) {
     D3 center, du, dv, uu, vv;
     D3 p00;
-    if (!C.camera_motion && !C.free_camera) {
+    if (!(FEAT & RTX_F_CAM_SLOW) || (!C.camera_motion && !C.free_camera)) {
         center = ld3(C.center); du = ld3(C.du); dv = ld3(C.dv); uu = ld3(C.u); vv = ld3(C.v); p00 = ld3(C.pixel00);
     } else {  // slow path :390-417
         center = add(ld3(C.look_from), scale(ld3(C.look_vel), tm));
@@ -158,6 +159,7 @@ __device__ __forceinline__ RayD camera_ray(const DevCamera& C, int i, int j, dou
 // device-side control block announces: the host never learns the queue lengths, and a launch sized for the whole pool
 // (16 K blocks) costs ~70 us of block scheduling even when a handful of paths are left.
 // camera path `pid` of the pass: its primary ray and its (pixel | sample << 32) identity
+template <unsigned FEAT = RTX_F_ALL>
 __device__ __forceinline__ RayD generate_path(const DevCamera& C, const PassParams& pp, unsigned long long pid, unsigned long long& pixsample) {
     unsigned npix = (unsigned)C.width * (unsigned)C.height;
     // path order: pixel-major (all samples of a pixel are consecutive paths) keeps the pixels in flight few, so the radiance
@@ -177,7 +179,7 @@ __device__ __forceinline__ RayD generate_path(const DevCamera& C, const PassPara
         lx = rr * cs; ly = rr * sn;
     }
     pixsample = ((unsigned long long)sample << 32) | pixel;
-    return camera_ray(C, px, py, offx, offy, tm, lx, ly);
+    return camera_ray<FEAT>(C, px, py, offx, offy, tm, lx, ly);
 }
 #define RTX_FRESH_PATH_FLAGS (0 | (1 << 16))   /* bounce 0, light hits allowed */
 __global__ void __launch_bounds__(256, 4) k_generate(Ctl* ctl, Pool pool, int cur, DevCamera C, PassParams pp) {
@@ -206,11 +208,19 @@ __device__ __forceinline__ Hit best_to_hit(const Best& b) {
     return h;
 }
 
+// the lean kernel variants (rtx_render_pass picks the first whose mask covers the scene and the camera; RTX_F_ALL is the fallback)
+#define RTX_FV_LUCY (RTX_F_QUAD | RTX_F_MESH | RTX_F_XFORM | RTX_F_LIGHTS)                       /* CornellBoxLucy: walls, light, mesh instances, Lambertian */
+#define RTX_FV_SKY (RTX_F_SPHERE | RTX_F_PLANE | RTX_F_ENV | RTX_F_METAL | RTX_F_DIELECTRIC)   /* RandomScene, HDRITestScene, SimpleScene, CheckeredSpheres */
+#define RTX_FV_BOX (RTX_F_QUAD | RTX_F_SPHERE | RTX_F_LIGHTS | RTX_F_METAL | RTX_F_DIELECTRIC)  /* CornellBoxGlossy, QuadsScene */
+
 extern __shared__ __align__(16) unsigned char rtx_smem[];  // the trace kernels' ray pool (TracePool)
 #define RTX_TRACE_SMEM_BYTES ((size_t)RTX_TRACE_SLOTS * RTX_SLOT_WORDS * 4 + RTX_POOL_EXTRA_BYTES)
+#define RTX_TRACE_SMEM_BYTES_LEAN ((size_t)RTX_TRACE_SLOTS_LEAN * RTX_SLOT_WORDS * 4 + RTX_POOL_EXTRA_BYTES)
+#define RTX_TRACE_BLOCKS_OF(FEAT) ((FEAT) == RTX_F_ALL ? RTX_TRACE_BLOCKS : RTX_TRACE_BLOCKS_LEAN)
+#define RTX_TRACE_SLOTS_OF(FEAT) ((FEAT) == RTX_F_ALL ? RTX_TRACE_SLOTS : RTX_TRACE_SLOTS_LEAN)
 
 // ---- K2: extend — closest hit of every active path, then binning into material-sorted shading queues -------------
-template <bool UV>
+template <bool UV, unsigned FEAT = RTX_F_ALL>
 struct ExtendPolicyT {
     static constexpr bool ANY_HIT = false;
     Ctl* ctl; char* hit; int* q_mat; int capacity; const char* rec; const DevScene* S; uint32_t seed_lo, seed_hi;
@@ -235,7 +245,7 @@ struct ExtendPolicyT {
                 q = Q_MISS;
             } else {
                 HitInfo hi;
-                finalize_hit(*S, r, best_to_hit(b), UV, hi);
+                finalize_hit<FEAT>(*S, r, best_to_hit(b), UV, hi);
                 const long long bits = (long long)(unsigned)hi.mat | (hi.front ? (1LL << 31) : 0);
                 char* h = hit + (size_t)job * RTX_HIT_BYTES;
                 // the fourth word: t, or — in scenes with image textures — the hit's (u, v) as two float32 (texel lookup only)
@@ -258,12 +268,13 @@ struct ExtendPolicyT {
 typedef ExtendPolicyT<false> ExtendPolicy;
 
 // UV = true: the variant for scenes with image textures (hit records carry (u, v); sphere UVs cost an acos and an atan2 per hit)
-template <bool COUNT, bool UV = false>
-__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_extend(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, PassParams pp, int* spill) {
-    ExtendPolicyT<UV> P{ctl, pool.hit, pool.q_mat, pool.capacity, pool.records(cur), &S, pp.seed_lo, pp.seed_hi};
+// FEAT: the scene vocabulary the variant contains (RTX_F_*, rtx_device.cuh); rtx_render_pass picks the smallest covering one
+template <bool COUNT, bool UV = false, unsigned FEAT = RTX_F_ALL>
+__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS_OF(FEAT)) k_extend(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, PassParams pp, int* spill) {
+    ExtendPolicyT<UV, FEAT> P{ctl, pool.hit, pool.q_mat, pool.capacity, pool.records(cur), &S, pp.seed_lo, pp.seed_hi};
     TraceCounters tc = {0, 0, 0, 0, 0};
     const int n = ctl->n_active;
-    trace_persistent<ExtendPolicyT<UV>, COUNT, RTX_TRACE_SLOTS>(S, P, &ctl->cur_extend, n, tc, spill, rtx_smem);
+    trace_persistent<ExtendPolicyT<UV, FEAT>, COUNT, RTX_TRACE_SLOTS_OF(FEAT), FEAT>(S, P, &ctl->cur_extend, n, tc, spill, rtx_smem);
     if (COUNT) flush_counters(ctl, tc);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->ext_rays, (unsigned long long)n);
 }
@@ -297,6 +308,7 @@ __device__ __noinline__ double perlin_noise(const double* vec, const int* perm, 
             }
     return accum;
 }
+template <unsigned FEAT = RTX_F_ALL>
 __device__ __forceinline__ float3 tex_value(const DevScene& S, int id, D3 p, float u = 0.f, float v = 0.f) {
     DTexture t = S.texs[id];
     for (int guard = 0; guard < 8 && t.type == RTX_TEX_CHECKER; guard++) {
@@ -306,7 +318,7 @@ __device__ __forceinline__ float3 tex_value(const DevScene& S, int id, D3 p, flo
         bool even = ((xi + yi + zi) % 2) == 0;
         t = S.texs[even ? t.even : t.odd];
     }
-    if (t.type == RTX_TEX_NOISE) {  // NoiseTexture.Value rt/texture.go:81-85: 0.5 (1 + sin(scale z + 10 turb(scale p, 7)))
+    if ((FEAT & RTX_F_TEX_X) && t.type == RTX_TEX_NOISE) {  // NoiseTexture.Value rt/texture.go:81-85: 0.5 (1 + sin(scale z + 10 turb(scale p, 7)))
         const double* vec = S.perlin_vec + (size_t)t.even * 768;
         const int* perm = S.perlin_perm + (size_t)t.even * 768;
         const double sc = t.inv_scale;   // NoiseTexture.scale (not inverted)
@@ -319,7 +331,7 @@ __device__ __forceinline__ float3 tex_value(const DevScene& S, int id, D3 p, flo
         const float tv = (float)(0.5 * (1.0 + sin(sc * p.z + 10.0 * fabs(accum))));
         return make_float3(tv, tv, tv);
     }
-    if (t.type == RTX_TEX_IMAGE) {  // ImageTexture.Value rt/image_texture.go:27-43 + ImageLoader.PixelData rt/image_loader.go:97-120
+    if ((FEAT & RTX_F_TEX_X) && t.type == RTX_TEX_IMAGE) {  // ImageTexture.Value rt/image_texture.go:27-43 + ImageLoader.PixelData rt/image_loader.go:97-120
         const int4 dim = S.img_dim[t.even];
         const double uu = u < 0.f ? 0.0 : (u > 1.f ? 1.0 : (double)u);
         const double vv = 1.0 - (v < 0.f ? 0.0 : (v > 1.f ? 1.0 : (double)v));   // flip V to image coordinates
@@ -433,6 +445,7 @@ struct ShadeVars {
 
 // rayColorInternal for one ray whose query is finished (rt/camera.go:443-518): `type` is its shading queue; V.tm / V.pixbits / V.th hold
 // the path record's time, pixel | sample and throughput | flags; P_in, N, (hu, hv), mat, front are the hit (unused for Q_MISS).
+template <unsigned FEAT = RTX_F_ALL>
 __device__ __forceinline__ void shade_element(const DevScene& S, const DevCamera& C, const PassParams& pp, const Pool& pool, const int type, const D3 rd,
                                               const D3 P_in, const D3 N, const float hu, const float hv, const int mat, const bool front, ShadeVars& V) {
     bool& cont = V.cont; bool& has_env = V.has_env; bool& has_area = V.has_area;
@@ -450,7 +463,7 @@ __device__ __forceinline__ void shade_element(const DevScene& S, const DevCamera
     uint2 ps = make_uint2((uint32_t)psb, (uint32_t)(psb >> 32));
     if (type == Q_MISS) {  // rt/camera.go:451-466
         float3 col;
-        if (S.env_w > 0) {
+        if ((FEAT & RTX_F_ENV) && S.env_w > 0) {
             bool primary = (bounce == 0) && (pp.max_depth == pp.camera_max_depth);  // depth == c.MaxDepth
             if (C.phantom && primary) col = make_float3(0, 0, 0);
             else col = env_lookup(S, rd);
@@ -466,7 +479,7 @@ __device__ __forceinline__ void shade_element(const DevScene& S, const DevCamera
         DMaterial M = S.mats[mat];
         if (type == Q_LIGHT) {  // Scatter == false: rt/camera.go:473-481, rt/material.go:226-236
             if (allow) {
-                float3 e = tex_value(S, M.tex, P, hu, hv);
+                float3 e = tex_value<FEAT>(S, M.tex, P, hu, hv);
                 pool.contribute(ps.x, ps.y, th.x * e.x, th.y * e.y, th.z * e.z);
             }
         } else {
@@ -476,13 +489,13 @@ __device__ __forceinline__ void shade_element(const DevScene& S, const DevCamera
             if (type == Q_LAMBERTIAN) {  // rt/material.go:57-68
                 nd = add(N, unit_sphere(rs.x, rs.y));
                 if (fabs(nd.x) < 1e-8 && fabs(nd.y) < 1e-8 && fabs(nd.z) < 1e-8) nd = N;
-                att = tex_value(S, M.tex, P, hu, hv);
-                if (S.n_lights > 0) {  // useMIS, rt/camera.go:487-517
+                att = tex_value<FEAT>(S, M.tex, P, hu, hv);
+                if ((FEAT & RTX_F_LIGHTS) && S.n_lights > 0) {  // useMIS, rt/camera.go:487-517
                     const double PI = 3.14159265358979323846;
                     uint4 rn = philox4x32(ps.x, ps.y, (uint32_t)bounce, STREAM_NEE, pp.seed_lo, pp.seed_hi);
                     int li = (int)(u01(rn.x) * (double)S.n_lights);
                     if (li >= S.n_lights) li = S.n_lights - 1;
-                    if (S.env_w > 0 && S.env_is && S.env_total != 0) {  // sampleHDRILight :565-607
+                    if ((FEAT & RTX_F_ENV) && S.env_w > 0 && S.env_is && S.env_total != 0) {  // sampleHDRILight :565-607
                         D3 ldir; float3 em; double pdfH;
                         env_sample(S, u01(rs.z), u01(rs.w), ldir, em, pdfH);
                         double cosT = dot(N, ldir);
@@ -506,7 +519,7 @@ __device__ __forceinline__ void shade_element(const DevScene& S, const DevCamera
                         double cosT = dot(N, ldir);
                         double cosL = fabs(dot(ld3(q + 12), d3(-ldir.x, -ldir.y, -ldir.z)));
                         if (cosT > 0 && !(cosL < 0.001)) {
-                            float3 em = tex_value(S, S.mats[S.quad_mat[lq]].tex, lp);  // lightQuad.mat.Emitted(0,0,lightPoint)
+                            float3 em = tex_value<FEAT>(S, S.mats[S.quad_mat[lq]].tex, lp);  // lightQuad.mat.Emitted(0,0,lightPoint)
                             if (S.mats[S.quad_mat[lq]].type != RTX_MAT_DIFFUSE_LIGHT) em = make_float3(0, 0, 0);
                             double area = sqrt(len2(cross(ld3(q + 3), ld3(q + 6))));
                             double pdfL = (dist * dist) / (cosL * area);
@@ -523,13 +536,13 @@ __device__ __forceinline__ void shade_element(const DevScene& S, const DevCamera
                     }
                     next_allow = false;  // indirect path must not pick up the light again (:514)
                 }
-            } else if (type == Q_METAL) {  // rt/material.go:113-119
+            } else if ((FEAT & RTX_F_METAL) && type == Q_METAL) {  // rt/material.go:113-119
                 double dn = dot(rd, N);
                 D3 refl = sub(rd, scale(N, 2 * dn));
                 nd = add(unit(refl), scale(unit_sphere(rs.x, rs.y), M.fuzz));
                 att = make_float3(M.albedo[0], M.albedo[1], M.albedo[2]);
                 scattered = dot(nd, N) > 0;
-            } else if (type == Q_DIELECTRIC) {  // rt/material.go:164-188
+            } else if ((FEAT & RTX_F_DIELECTRIC) && type == Q_DIELECTRIC) {  // rt/material.go:164-188
                 att = make_float3(1.f, 1.f, 1.f);
                 double ri = front ? 1.0 / M.ior : M.ior;
                 D3 ud = unit(rd);
@@ -550,10 +563,10 @@ __device__ __forceinline__ void shade_element(const DevScene& S, const DevCamera
                     D3 par = scale(N, -sqrt(fabs(1.0 - len2(perp))));
                     nd = add(perp, par);
                 }
-            } else {  // Q_ISOTROPIC rt/material.go:266-270
+            } else if (FEAT & RTX_F_ISOTROPIC) {  // Q_ISOTROPIC rt/material.go:266-270
                 nd = unit_sphere(rs.x, rs.y);
-                att = tex_value(S, M.tex, P, hu, hv);
-            }
+                att = tex_value<FEAT>(S, M.tex, P, hu, hv);
+            } else { att = make_float3(0.f, 0.f, 0.f); scattered = false; }   // a material outside the variant's vocabulary: unreachable for a covered scene
             if (!scattered) {
                 has_env = has_area = false;  // absorbed: emission of a scattering material is zero
             } else {
@@ -606,8 +619,11 @@ __device__ __forceinline__ void shade_commit(Ctl* ctl, const Pool& pool, const i
 #ifndef RTX_SHADE_BLOCKS_Q
 #define RTX_SHADE_BLOCKS_Q 3
 #endif
-template <int QT>
-__global__ void __launch_bounds__(256, QT < 0 ? RTX_SHADE_BLOCKS : (QT == Q_LAMBERTIAN ? RTX_SHADE_BLOCKS : RTX_SHADE_BLOCKS_Q)) k_shade(Ctl* ctl, Pool pool, int cur, DevScene S, DevCamera C, PassParams pp) {
+#ifndef RTX_SHADE_BLOCKS_LEAN
+#define RTX_SHADE_BLOCKS_LEAN RTX_SHADE_BLOCKS
+#endif
+template <int QT, unsigned FEAT = RTX_F_ALL>
+__global__ void __launch_bounds__(256, FEAT != RTX_F_ALL ? RTX_SHADE_BLOCKS_LEAN : QT < 0 ? RTX_SHADE_BLOCKS : (QT == Q_LAMBERTIAN ? RTX_SHADE_BLOCKS : RTX_SHADE_BLOCKS_Q)) k_shade(Ctl* ctl, Pool pool, int cur, DevScene S, DevCamera C, PassParams pp) {
   const int n_items = QT < 0 ? ctl->n_active : ctl->n_mat[QT < 0 ? 0 : QT];
   const int n_rounded = (n_items + 31) & ~31;   // whole warps stay together for the queue appends
   int nq[Q_COUNT];
@@ -670,7 +686,7 @@ __global__ void __launch_bounds__(256, QT < 0 ? RTX_SHADE_BLOCKS : (QT == Q_LAMB
             mat = (int)(bits & 0x7fffffff);
             front = (bits >> 31) & 1;
         }
-        shade_element(S, C, pp, pool, type, d3(rd4.x, rd4.y, rd4.z), P, N, hu, hv, mat, front, V);
+        shade_element<FEAT>(S, C, pp, pool, type, d3(rd4.x, rd4.y, rd4.z), P, N, hu, hv, mat, front, V);
     }
     shade_commit(ctl, pool, cur, V);
   }
@@ -681,7 +697,7 @@ __global__ void __launch_bounds__(256, QT < 0 ? RTX_SHADE_BLOCKS : (QT == Q_LAMB
 // shades it (same shade_element, same Philox counters: the paths are the ones the separate kernels produce) and appends the survivor. The hit
 // record (64 B written, 64 B read), the queue slot and the second read of the path record disappear — for these scenes both separate kernels
 // are HBM-bound (profiles/r01_k_shade_hdri.md) — at the price of shading without material-sorted warps.
-template <bool UV>
+template <bool UV, unsigned FEAT = RTX_F_ALL>
 struct BouncePolicyT {
     static constexpr bool ANY_HIT = false;
     Ctl* ctl; Pool pool; int cur; const DevScene* S; const DevCamera* C; PassParams pp;
@@ -691,7 +707,7 @@ struct BouncePolicyT {
     __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
         if (job >= n_cont) {
             unsigned long long ps;
-            r = generate_path(*C, pp, gen_base + (unsigned long long)(job - n_cont), ps);
+            r = generate_path<FEAT>(*C, pp, gen_base + (unsigned long long)(job - n_cont), ps);
             pixbits_ = __longlong_as_double((long long)ps);
             th_ = make_float4(1.f, 1.f, 1.f, __int_as_float(RTX_FRESH_PATH_FLAGS));
         } else {
@@ -719,12 +735,12 @@ struct BouncePolicyT {
             HitInfo hi;
             hi.P = hi.N = d3(0, 0, 0); hi.mat = 0; hi.front = false; hi.u = hi.v = 0;
             if (b.entry >= 0) {
-                finalize_hit(*S, r, best_to_hit(b), UV, hi);
+                finalize_hit<FEAT>(*S, r, best_to_hit(b), UV, hi);
                 const int mt = S->mats[hi.mat].type;
                 type = mt == RTX_MAT_LAMBERTIAN ? Q_LAMBERTIAN : mt == RTX_MAT_METAL ? Q_METAL : mt == RTX_MAT_DIELECTRIC ? Q_DIELECTRIC
                      : mt == RTX_MAT_DIFFUSE_LIGHT ? Q_LIGHT : Q_ISOTROPIC;
             }
-            shade_element(*S, *C, pp, pool, type, d3(r.dx, r.dy, r.dz), hi.P, hi.N, UV ? (float)hi.u : 0.f, UV ? (float)hi.v : 0.f, hi.mat, hi.front, V);
+            shade_element<FEAT>(*S, *C, pp, pool, type, d3(r.dx, r.dy, r.dz), hi.P, hi.N, UV ? (float)hi.u : 0.f, UV ? (float)hi.v : 0.f, hi.mat, hi.front, V);
         }
         shade_commit(ctl, pool, cur, V);
     }
@@ -733,12 +749,16 @@ struct BouncePolicyT {
 #ifndef RTX_BOUNCE_BLOCKS
 #define RTX_BOUNCE_BLOCKS 2   /* resident 256-thread blocks per SM k_bounce_flat is compiled for */
 #endif
-template <bool COUNT, bool UV = false>
-__global__ void __launch_bounds__(256, RTX_BOUNCE_BLOCKS) k_bounce_flat(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, const __grid_constant__ DevCamera C, PassParams pp) {
-    BouncePolicyT<UV> P{ctl, pool, cur, &S, &C, pp, ctl->n_cont, ctl->gen_base, 0.0, make_float4(0.f, 0.f, 0.f, 0.f)};
+// the lean variants (rtx_render_pass picks the first whose mask covers the scene and the camera; RTX_F_ALL is the fallback)
+#ifndef RTX_BOUNCE_BLOCKS_LEAN
+#define RTX_BOUNCE_BLOCKS_LEAN 4   /* resident 256-thread blocks of the lean variants (104-120 registers uncapped). hdri-test 64 spp, Mpaths/s: all-features kernel 4147; lean with 2 blocks 6180, 3 blocks (78 registers) 6564-6667, 4 blocks (64 registers, 24 B of spills) 6675; cornell-glossy 2092 / 2480 / 2917 / 3132 */
+#endif
+template <bool COUNT, bool UV = false, unsigned FEAT = RTX_F_ALL>
+__global__ void __launch_bounds__(256, FEAT == RTX_F_ALL ? RTX_BOUNCE_BLOCKS : RTX_BOUNCE_BLOCKS_LEAN) k_bounce_flat(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, const __grid_constant__ DevCamera C, PassParams pp) {
+    BouncePolicyT<UV, FEAT> P{ctl, pool, cur, &S, &C, pp, ctl->n_cont, ctl->gen_base, 0.0, make_float4(0.f, 0.f, 0.f, 0.f)};
     TraceCounters tc = {0, 0, 0, 0, 0};
     const int n = ctl->n_active;
-    trace_flat<BouncePolicyT<UV>, COUNT>(S, P, n, tc);
+    trace_flat<BouncePolicyT<UV, FEAT>, COUNT, FEAT>(S, P, n, tc);
     if (COUNT) flush_counters(ctl, tc);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->ext_rays, (unsigned long long)n);
 }
@@ -837,22 +857,22 @@ struct ConnectPolicy {
     }
 };
 
-template <bool COUNT>
-__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_connect(Ctl* ctl, Pool pool, int par, const __grid_constant__ DevScene S, PassParams pp, int* spill) {
+template <bool COUNT, unsigned FEAT = RTX_F_ALL>
+__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS_OF(FEAT)) k_connect(Ctl* ctl, Pool pool, int par, const __grid_constant__ DevScene S, PassParams pp, int* spill) {
     ConnectPolicy P{pool, pp.seed_lo, pp.seed_hi};
     TraceCounters tc = {0, 0, 0, 0, 0};
     const int n = ctl->n_shadow[par];
-    trace_persistent<ConnectPolicy, COUNT, RTX_TRACE_SLOTS>(S, P, &ctl->cur_connect[par], n, tc, spill, rtx_smem);
+    trace_persistent<ConnectPolicy, COUNT, RTX_TRACE_SLOTS_OF(FEAT), FEAT>(S, P, &ctl->cur_connect[par], n, tc, spill, rtx_smem);
     if (COUNT) flush_counters(ctl, tc);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->shadow_rays, (unsigned long long)n);
 }
 
-template <bool COUNT>
+template <bool COUNT, unsigned FEAT = RTX_F_ALL>
 __global__ void __launch_bounds__(256) k_connect_flat(Ctl* ctl, Pool pool, int par, const __grid_constant__ DevScene S, PassParams pp) {
     ConnectPolicy P{pool, pp.seed_lo, pp.seed_hi};
     TraceCounters tc = {0, 0, 0, 0, 0};
     const int n = ctl->n_shadow[par];
-    trace_flat<ConnectPolicy, COUNT>(S, P, n, tc);
+    trace_flat<ConnectPolicy, COUNT, FEAT>(S, P, n, tc);
     if (COUNT) flush_counters(ctl, tc);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->shadow_rays, (unsigned long long)n);
 }
@@ -892,7 +912,8 @@ __global__ void k_resolve_rgba8(const float4* accum, int npix, double scale, uch
 }
 
 // ---- batch entry points for the parity tests ----------------------------------------------------------------------------
-struct BatchPolicy {
+template <unsigned FEAT = RTX_F_ALL>
+struct BatchPolicyT {
     static constexpr bool ANY_HIT = false;
     const DevScene* S; const double* rays; double t0, t1;
     int* entry_id; int* prim_id; double* t; double* normal; unsigned char* front; double* uv; double* p;
@@ -908,7 +929,7 @@ struct BatchPolicy {
         const size_t i = (size_t)job;
         const bool hit = b.entry >= 0;
         HitInfo hi;
-        if (hit) finalize_hit(*S, r, best_to_hit(b), true, hi);
+        if (hit) finalize_hit<FEAT>(*S, r, best_to_hit(b), true, hi);
         if (entry_id) entry_id[i] = hit ? b.entry : -1;
         if (prim_id) prim_id[i] = hit ? b.item : -1;
         if (t) t[i] = hit ? b.t : 0;
@@ -919,18 +940,22 @@ struct BatchPolicy {
     }
 };
 
-__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_trace_closest(const __grid_constant__ DevScene S, const double* rays, int n, double tmin, double tmax, int* cursor, int* spill,
+typedef BatchPolicyT<> BatchPolicy;
+// the level-1 parity entry runs the same kernel variant a rendered pass of the scene runs (FEAT), so the bit-exact tests cover the lean code
+template <unsigned FEAT = RTX_F_ALL>
+__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS_OF(FEAT)) k_trace_closest(const __grid_constant__ DevScene S, const double* rays, int n, double tmin, double tmax, int* cursor, int* spill,
         int* entry_id, int* prim_id, double* t, double* normal, unsigned char* front, double* uv, double* p) {
-    BatchPolicy P{&S, rays, tmin, tmax, entry_id, prim_id, t, normal, front, uv, p};
+    BatchPolicyT<FEAT> P{&S, rays, tmin, tmax, entry_id, prim_id, t, normal, front, uv, p};
     TraceCounters tc = {0, 0, 0, 0, 0};
-    trace_persistent<BatchPolicy, false, RTX_TRACE_SLOTS>(S, P, cursor, n, tc, spill, rtx_smem);
+    trace_persistent<BatchPolicyT<FEAT>, false, RTX_TRACE_SLOTS_OF(FEAT), FEAT>(S, P, cursor, n, tc, spill, rtx_smem);
 }
 
+template <unsigned FEAT = RTX_F_ALL>
 __global__ void __launch_bounds__(256) k_trace_closest_flat(const __grid_constant__ DevScene S, const double* rays, int n, double tmin, double tmax, int* entry_id, int* prim_id,
         double* t, double* normal, unsigned char* front, double* uv, double* p) {
-    BatchPolicy P{&S, rays, tmin, tmax, entry_id, prim_id, t, normal, front, uv, p};
+    BatchPolicyT<FEAT> P{&S, rays, tmin, tmax, entry_id, prim_id, t, normal, front, uv, p};
     TraceCounters tc = {0, 0, 0, 0, 0};
-    trace_flat<BatchPolicy, false>(S, P, n, tc);
+    trace_flat<BatchPolicyT<FEAT>, false, FEAT>(S, P, n, tc);
 }
 
 __global__ void k_camera_rays(DevCamera C, const int* ij, const double* sq, const double* disk, const double* tm, long long n, double* out) {

@@ -26,6 +26,15 @@
 #ifndef RTX_TRACE_BLOCKS
 #define RTX_TRACE_BLOCKS 4   /* resident blocks per SM the trace kernels are compiled for (caps registers at 65536 / (128 * blocks)) */
 #endif
+// The lean kernel variants (RTX_FV_*: compiled for one scene vocabulary) need 76-96 registers instead of 128, so six blocks stay resident
+// (24 warps per SM instead of 16) with 160 slots each. cornell-lucy 64 spp: all-features kernels 214.5 ms; lean, 4 blocks x 224 slots 204.6;
+// 5 x 192 196.6; 5 x 160 199.1; 6 x 160 194.3 ms. random: 14.7 / 13.9 / 13.4 / 13.3 / 13.0 ms.
+#ifndef RTX_TRACE_SLOTS_LEAN
+#define RTX_TRACE_SLOTS_LEAN 160
+#endif
+#ifndef RTX_TRACE_BLOCKS_LEAN
+#define RTX_TRACE_BLOCKS_LEAN 6
+#endif
 #define RTX_ST_SENTINEL ((int)0x80000000)  /* stack marker: instance finished, back to the TLAS */
 #define RTX_ST_DONE ((int)0x80000001)
 #define RTX_ST_IDLE ((int)0x80000002)
@@ -259,7 +268,7 @@ bool entry_other(const DevScene* Sp, unsigned char* smem, int s, int ei, double 
 // reference's HittableList.Hit loop itself — one thread per ray, every entry in turn, no pool, no stack, no divergence
 // between lanes beyond the tests' own early-outs. Results are identical to the hierarchy's (closest hits do not depend on
 // the order of the tests; exact ties are resolved by rank as everywhere).
-template <class Policy, bool COUNT>
+template <class Policy, bool COUNT, unsigned FEAT = RTX_F_ALL>
 __device__ __forceinline__ void trace_flat(const DevScene& S, Policy& P, int njobs, TraceCounters& tc) {
     TraceCounters* const tcp = COUNT ? &tc : nullptr;
     const double tmin = P.tmin();
@@ -280,28 +289,28 @@ __device__ __forceinline__ void trace_flat(const DevScene& S, Policy& P, int njo
                 const int4 fe = __ldg(S.flat_simple + k);   // kind, primitive, entry, rank
                 const bool incl = B.have;                   // an open-interval primitive may still tie with the current best (Best::tmax_for)
                 double t;
-                if (fe.x == RTX_GEOM_SPHERE) {
+                if ((FEAT & RTX_F_SPHERE) && fe.x == RTX_GEOM_SPHERE) {
                     if (COUNT) tc.spheres++;
                     t = isect_sphere_incl(S.spheres + 8 * (size_t)fe.y, r, tmin, B.t, incl);
-                } else if (fe.x == RTX_GEOM_QUAD) {
+                } else if ((FEAT & RTX_F_QUAD) && fe.x == RTX_GEOM_QUAD) {
                     if (COUNT) tc.quads++;
                     t = isect_quad(S.quads + 16 * (size_t)fe.y, r, tmin, B.t, nullptr);
-                } else if (fe.x == RTX_GEOM_PLANE) {
+                } else if ((FEAT & RTX_F_PLANE) && fe.x == RTX_GEOM_PLANE) {
                     if (COUNT) tc.planes++;
                     t = isect_plane(S.planes + 8 * (size_t)fe.y, r);
                     if (!(tmin < t && (t < B.t || (incl && t == B.t)))) t = RTX_NAN_D;
-                } else if (fe.x == RTX_GEOM_CIRCLE) {
+                } else if ((FEAT & RTX_F_OTHER_PRIM) && fe.x == RTX_GEOM_CIRCLE) {
                     if (COUNT) tc.quads++;
                     t = isect_circle(S.circles + 8 * (size_t)fe.y, r, tmin, B.t);
-                } else {
+                } else if (FEAT & RTX_F_OTHER_PRIM) {
                     if (COUNT) tc.tris++;
                     t = isect_tri(S.tris + RTX_TRI_D * (size_t)fe.y, r, nullptr);
                     if (!(tmin <= t && t <= B.t)) t = RTX_NAN_D;
-                }
+                } else t = RTX_NAN_D;   // a kind outside the variant's vocabulary: unreachable for a scene the mask covers
                 B.offer(t, fe.z, fe.w, fe.x, fe.y, 0, 0);
                 if (Policy::ANY_HIT && B.have) break;
             }
-            if (!(Policy::ANY_HIT && B.have))
+            if ((FEAT & RTX_F_COMPLEX) && !(Policy::ANY_HIT && B.have))
                 for (int k = 0; k < S.n_flat_complex; k++) {
                     const int ei = S.flat_complex[k];
                     const DEntry e = S.entries[ei];
@@ -315,7 +324,7 @@ __device__ __forceinline__ void trace_flat(const DevScene& S, Policy& P, int njo
     }
 }
 
-template <class Policy, bool COUNT, int NSLOTS>
+template <class Policy, bool COUNT, int NSLOTS, unsigned FEAT = RTX_F_ALL>
 __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, int* cursor, int njobs, TraceCounters& tc, int* spill, unsigned char* smem) {
     typedef TracePool<NSLOTS> Pool_;
     constexpr int NS = Pool_::NS;
@@ -453,7 +462,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                 T.node[s] = node; T.sp[s] = sp;
                 newst = RTX_CLASSIFY(node, inst);
             }
-        } else if (phase == RTX_PH_T) {
+        } else if ((FEAT & RTX_F_MESH) && phase == RTX_PH_T) {
             // ---- TRI: one triangle of the pending BLAS leaf per lane ------------------------------------------------
             if (mine) {
                 int node = T.node[s];
@@ -491,7 +500,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                 int node = T.node[s], sp = T.sp[s];
                 const int job = T.job[s];
                 bool in_inst = false;
-                if (node == RTX_ST_SENTINEL) {
+                if ((FEAT & RTX_F_MESH) && node == RTX_ST_SENTINEL) {
                     RayD r; RayF f;
                     double tmax_unused;
                     P.load(job, r, tmax_unused);
@@ -502,10 +511,10 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                 } else {
                     const int ei = ~node;
                     const DEntry e = S.entries[ei];
-                    if (e.volume < 0 && e.kind == RTX_GEOM_MESH) {
+                    if ((FEAT & RTX_F_MESH) && e.volume < 0 && e.kind == RTX_GEOM_MESH) {
                         RayD r2; RayF f;
                         T.load_ray(s, r2);
-                        xform_ray(S, ei, e, r2);
+                        if (FEAT & (RTX_F_XFORM | RTX_F_COMPLEX)) xform_ray(S, ei, e, r2);
                         make_rayf(r2, f);
 #if RTX_E_ROOT_STEP
                         // The instance's world-space box (the TLAS leaf) is loose around a rotated statue: test the BLAS root's four
@@ -555,35 +564,35 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                         Best B;
                         T.load_best(s, B);
                         double t;
-                        if (e.kind == RTX_GEOM_QUAD) {
+                        if ((FEAT & RTX_F_QUAD) && e.kind == RTX_GEOM_QUAD) {
                             if (COUNT) tc.quads++;
                             t = isect_quad(S.quads + 16 * (size_t)e.index, r, tmin, B.t, nullptr);
-                        } else if (e.kind == RTX_GEOM_SPHERE) {
+                        } else if ((FEAT & RTX_F_SPHERE) && e.kind == RTX_GEOM_SPHERE) {
                             if (COUNT) tc.spheres++;
                             t = isect_sphere_incl(S.spheres + 8 * (size_t)e.index, r, tmin, B.t, B.have);
-                        } else if (e.kind == RTX_GEOM_TRIANGLE) {
+                        } else if ((FEAT & RTX_F_OTHER_PRIM) && e.kind == RTX_GEOM_TRIANGLE) {
                             if (COUNT) tc.tris++;
                             t = isect_tri(S.tris + RTX_TRI_D * (size_t)e.index, r, nullptr);
                             if (!(tmin <= t && t <= B.t)) t = RTX_NAN_D;
-                        } else if (e.kind == RTX_GEOM_CIRCLE) {
+                        } else if ((FEAT & RTX_F_OTHER_PRIM) && e.kind == RTX_GEOM_CIRCLE) {
                             if (COUNT) tc.quads++;
                             t = isect_circle(S.circles + 8 * (size_t)e.index, r, tmin, B.t);
-                        } else {
+                        } else if (FEAT & RTX_F_PLANE) {
                             if (COUNT) tc.planes++;
                             t = isect_plane(S.planes + 8 * (size_t)e.index, r);
                             if (!(tmin < t && (t < B.t || (B.have && t == B.t)))) t = RTX_NAN_D;
-                        }
+                        } else t = RTX_NAN_D;   // a kind outside the variant's vocabulary: unreachable for a scene the mask covers
                         B.offer(t, ei, e.rank, e.kind, e.index, 0, 0);
                         T.store_best(s, B);
                         if (Policy::ANY_HIT && B.have) node = RTX_ST_DONE;
                         else RTX_POP();
-                    } else {
+                    } else if (FEAT & RTX_F_COMPLEX) {
                         VolumeRng vr = {0, 0, 0, 0, 0, true};
                         if (e.volume >= 0) vr = P.volume_rng(job);
                         const bool have = entry_other<NSLOTS>(&S, smem, s, ei, tmin, vr.k0, vr.k1, vr.c0, vr.c1, vr.c2, vr.transparent, tcp);
                         if (Policy::ANY_HIT && have) node = RTX_ST_DONE;
                         else RTX_POP();
-                    }
+                    } else RTX_POP();   // an entry outside the variant's vocabulary: unreachable for a scene the mask covers
                 }
                 T.node[s] = node; T.sp[s] = sp;
                 newst = RTX_CLASSIFY(node, in_inst);
@@ -628,17 +637,17 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                     for (int q = 0; q < S.n_unbounded; q++) {
                         const int ei = S.unbounded[q];
                         const DEntry e = S.entries[ei];
-                        if (e.xf_count == 0 && e.kind == RTX_GEOM_PLANE) {   // the bare ground plane of RandomScene / HDRITestScene: inlined
+                        if ((FEAT & RTX_F_PLANE) && e.xf_count == 0 && e.kind == RTX_GEOM_PLANE) {   // the bare ground plane of RandomScene / HDRITestScene: inlined
                             if (COUNT) tc.planes++;
                             double t = isect_plane(S.planes + 8 * (size_t)e.index, r);
                             if (!(tmin < t && (t < B.t || (B.have && t == B.t)))) t = RTX_NAN_D;
                             B.offer(t, ei, e.rank, RTX_GEOM_PLANE, e.index, 0, 0);
-                        } else if (e.xf_count == 0 && e.kind == RTX_GEOM_QUAD) {
+                        } else if ((FEAT & RTX_F_QUAD) && e.xf_count == 0 && e.kind == RTX_GEOM_QUAD) {
                             if (COUNT) tc.quads++;
                             const double t = isect_quad(S.quads + 16 * (size_t)e.index, r, tmin, B.t, nullptr);
                             B.offer(t, ei, e.rank, RTX_GEOM_QUAD, e.index, 0, 0);
                             if (Policy::ANY_HIT && B.have) break;
-                        } else {
+                        } else if (FEAT & RTX_F_COMPLEX) {   // a wrapped Plane (or, with pretest_bare, another bare kind)
                             RayD ro = r;
                             xform_ray(S, ei, e, ro);
                             B.test_prim(S, e.kind, e.index, ro, tmin, ei, e.rank, 0, 0, tcp);

@@ -584,6 +584,43 @@ def test_sample_slices_add_up_and_are_deterministic(grt, ctx):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name,width,spp,depth,flat", [("cornell-lucy", 200, 8, 12, 16), ("random", 160, 16, 20, 16), ("hdri-test", 240, 16, 20, 16),
+                                                       ("cornell-glossy", 160, 16, 5, 16), ("hdri-test", 160, 8, 20, 0), ("cornell", 160, 16, 10, 16),
+                                                       ("checkered", 160, 8, 20, 16), ("quads", 120, 8, 20, 0)])
+def test_lean_kernel_variants_are_result_neutral(grt, orc, name, width, spp, depth, flat):
+    """Kernels are compiled per scene vocabulary (RTX_FV_*: only the primitive kinds, materials, textures and light samplers the mask
+    names) and a pass runs the smallest variant that covers the scene; option lean = 0 forces the all-features kernels. A pruned branch
+    is unreachable for a covered scene, so hit records are bit-identical, a rendered pass traces the same rays, and the sums agree to
+    float-atomic order. Scenes outside every lean mask (cornell: Box lists, a Volume) must keep running the full kernels."""
+    rng = np.random.default_rng(5)
+    sc = grt.config_scene(name, width=width, spp=spp, depth=depth)
+    o = orc.OracleScene(sc.desc_ptr, sc.cam_ptr)
+    ij, sq, disk, tm = camera_batch(sc.width, sc.height, 20000, rng)
+    rays = o.camera_rays(ij, sq, disk, tm)
+    ho = o.trace_closest(rays)
+    scatter, _ = secondary_rays(ho, rng, 10000)
+    out = {}
+    for lean in (0, 1):
+        c = grt.Context(0)
+        c.set_option("lean", lean)
+        c.set_option("flat_max_entries", flat)
+        c.load(sc)
+        h1, h2 = c.trace_closest(rays), c.trace_closest(scatter)
+        c.render_pass(spp, depth, seed=12)
+        acc, _, n = c.resolve_accum()
+        st = c.stats()
+        c.close()
+        assert np.all(n == spp)
+        out[lean] = (h1, h2, acc, st["extension_rays"], st["shadow_rays"])
+    for a, b in ((out[0][0], out[1][0]), (out[0][1], out[1][1])):
+        for k in ("entry", "prim", "t", "normal", "p", "front", "uv"):
+            assert np.array_equal(a[k], b[k]), f"{name}: lean variant changes {k}"
+    assert_level1(out[1][0], ho, f"{name} lean primary")
+    assert out[0][3] == out[1][3] and out[0][4] == out[1][4]
+    assert np.allclose(out[0][2], out[1][2], rtol=5e-5, atol=2e-5)
+
+
+@pytest.mark.gpu
 def test_pretested_bare_entries_are_result_neutral(grt, orc):
     """Option pretest_bare: the few bare primitives beside a mesh (the walls and the light of CornellBoxLucy) leave the TLAS and are
     tested for every ray when it enters the trace pool. Where an entry is tested changes neither closest hits nor any-hit answers:

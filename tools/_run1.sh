@@ -1,10 +1,8 @@
-out=gpurun_out; mkdir -p $out
-RTX_OPTS=pool_paths=8388608 python tools/gpu_perf.py cornell-lucy 64 > $out/r01m_plain_lucy.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_connect -s 10 -c 1 -f -o $out/r01m_prof_connect \
-    env RTX_OPTS=pool_paths=8388608 python tools/gpu_perf.py cornell-lucy 64 > $out/r01m_ncu_connect.log 2>&1
-tail -2 $out/r01m_ncu_connect.log
-python tools/gpu_perf.py hdri-test 16 > $out/r01m_plain_hdri.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_bounce_flat -s 6 -c 1 -f -o $out/r01m_prof_bounce \
-    python tools/gpu_perf.py hdri-test 16 > $out/r01m_ncu_bounce.log 2>&1
-tail -2 $out/r01m_ncu_bounce.log
-ls -la $out/*.ncu-rep
+python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+P() { tail -1 | sed 's/ nodes\/ray.*//' | cut -c1-190; }
+for s in cornell-lucy random; do
+  python tools/gpu_perf.py $s 64 2>&1 | P
+  for v in t6s128 t7 t8; do RTX_B200_LIB=$PWD/build/ab/librtx_$v.so python tools/gpu_perf.py $s 64 2>&1 | P; done
+done
+for s in cornell hdri-test cornell-glossy; do python tools/gpu_perf.py $s 64 2>&1 | P; done
+python bench.py > gpurun_out/r01n_bench.json 2> gpurun_out/r01n_bench.err; echo "bench rc=$?"; cut -c1-1500 gpurun_out/r01n_bench.json
