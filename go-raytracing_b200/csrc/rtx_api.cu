@@ -157,13 +157,15 @@ int32_t rtx_abi_version(void) { return RTX_ABI_VERSION; }
 
 const char* rtx_last_error(const rtx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
-// Which kernel variant covers the uploaded scene and the camera: 0 = RTX_F_ALL, 1 = RTX_FV_LUCY, 2 = RTX_FV_SKY, 3 = RTX_FV_BOX
+// Which kernel variant covers the uploaded scene and the camera: 0 = RTX_F_ALL, 1 = RTX_FV_LUCY, 2 = RTX_FV_SKY, 3 = RTX_FV_BOX,
+// 4 = RTX_FV_CORNELL (flat kernels and k_shade only; the persistent trace kernels run it with all features)
 static int lean_variant(const rtx_ctx* ctx) {
     if (!ctx->lean_flat) return 0;
     const unsigned need = ctx->feat_mask | ((ctx->have_camera && (ctx->C.camera_motion || ctx->C.free_camera)) ? RTX_F_CAM_SLOW : 0u);
     if (!(need & ~RTX_FV_LUCY)) return 1;
     if (!(need & ~RTX_FV_SKY)) return 2;
     if (!(need & ~RTX_FV_BOX)) return 3;
+    if (!(need & ~RTX_FV_CORNELL)) return 4;
     return 0;
 }
 
@@ -1142,6 +1144,7 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
                 else {
                     if (lean == 2) k_bounce_flat<false, false, RTX_FV_SKY><<<gridStream, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
                     else if (lean == 3 || lean == 1) k_bounce_flat<false, false, RTX_FV_BOX><<<gridStream, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+                    else if (lean == 4) k_bounce_flat<false, false, RTX_FV_CORNELL><<<gridStream, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
                     else k_bounce_flat<false><<<gridStream, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
                 }
                 if (timing) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); }
@@ -1179,6 +1182,7 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
                 if (leanShade == 1) k_shade<-1, RTX_FV_LUCY><<<gsh, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
                 else if (leanShade == 2) k_shade<-1, RTX_FV_SKY><<<gsh, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
                 else if (leanShade == 3) k_shade<-1, RTX_FV_BOX><<<gsh, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
+                else if (leanShade == 4) k_shade<-1, RTX_FV_CORNELL><<<gsh, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
                 else k_shade<-1><<<gsh, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
             }
             }
@@ -1189,6 +1193,7 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
                 if (ctx->scene_flat) {
                     if (ctx->count_stats & 2) k_connect_flat<true><<<gridStream, 256, 0, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp);
                     else if (lean == 3 || lean == 1) k_connect_flat<false, RTX_FV_BOX><<<gridStream, 256, 0, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp);
+                    else if (lean == 4) k_connect_flat<false, RTX_FV_CORNELL><<<gridStream, 256, 0, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp);
                     else k_connect_flat<false><<<gridStream, 256, 0, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp);
                 } else if (ctx->count_stats & 2) k_connect<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
                 else if (lean == 1) k_connect<false, RTX_FV_LUCY><<<gridTraceLean, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_LEAN, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
@@ -1304,7 +1309,7 @@ int32_t rtx_trace_closest(rtx_ctx* ctx, const double* rays, int64_t n, double tm
 #define RTX_TC_FLAT(F) k_trace_closest_flat<F><<<gf, 256, 0, ctx->stream>>>(ctx->S, dRays, (int)n, tmin, tmax, dEntry, dPrim, dT, dN, dFront, dUV, dP)
 #define RTX_TC_TREE(F) k_trace_closest<F><<<(F) == RTX_F_ALL ? ctx->trace_grid : ctx->trace_grid_lean, RTX_TRACE_THREADS, (F) == RTX_F_ALL ? RTX_TRACE_SMEM_BYTES : RTX_TRACE_SMEM_BYTES_LEAN, ctx->stream>>>(ctx->S, dRays, (int)n, tmin, tmax, ctx->batch_cursor, ctx->trace_spill, dEntry, dPrim, dT, dN, dFront, dUV, dP)
     if (ctx->scene_flat) {
-        if (lean == 2) RTX_TC_FLAT(RTX_FV_SKY); else if (lean == 3 || lean == 1) RTX_TC_FLAT(RTX_FV_BOX); else RTX_TC_FLAT(RTX_F_ALL);
+        if (lean == 2) RTX_TC_FLAT(RTX_FV_SKY); else if (lean == 3 || lean == 1) RTX_TC_FLAT(RTX_FV_BOX); else if (lean == 4) RTX_TC_FLAT(RTX_FV_CORNELL); else RTX_TC_FLAT(RTX_F_ALL);
     } else {
         if (lean == 1) RTX_TC_TREE(RTX_FV_LUCY); else if (lean == 2) RTX_TC_TREE(RTX_FV_SKY); else RTX_TC_TREE(RTX_F_ALL);
     }

@@ -212,6 +212,7 @@ __device__ __forceinline__ Hit best_to_hit(const Best& b) {
 #define RTX_FV_LUCY (RTX_F_QUAD | RTX_F_MESH | RTX_F_XFORM | RTX_F_LIGHTS)                       /* CornellBoxLucy: walls, light, mesh instances, Lambertian */
 #define RTX_FV_SKY (RTX_F_SPHERE | RTX_F_PLANE | RTX_F_ENV | RTX_F_METAL | RTX_F_DIELECTRIC)   /* RandomScene, HDRITestScene, SimpleScene, CheckeredSpheres */
 #define RTX_FV_BOX (RTX_F_QUAD | RTX_F_SPHERE | RTX_F_LIGHTS | RTX_F_METAL | RTX_F_DIELECTRIC)  /* CornellBoxGlossy, QuadsScene */
+#define RTX_FV_CORNELL (RTX_F_QUAD | RTX_F_COMPLEX | RTX_F_LIGHTS | RTX_F_ISOTROPIC)             /* CornellBoxScene, CornellSmoke: walls, rotated Box lists, Volumes (flat kernels only) */
 
 extern __shared__ __align__(16) unsigned char rtx_smem[];  // the trace kernels' ray pool (TracePool)
 #define RTX_TRACE_SMEM_BYTES ((size_t)RTX_TRACE_SLOTS * RTX_SLOT_WORDS * 4 + RTX_POOL_EXTRA_BYTES)
@@ -754,7 +755,7 @@ struct BouncePolicyT {
 #define RTX_BOUNCE_BLOCKS_LEAN 4   /* resident 256-thread blocks of the lean variants (104-120 registers uncapped). hdri-test 64 spp, Mpaths/s: all-features kernel 4147; lean with 2 blocks 6180, 3 blocks (78 registers) 6564-6667, 4 blocks (64 registers, 24 B of spills) 6675; cornell-glossy 2092 / 2480 / 2917 / 3132 */
 #endif
 template <bool COUNT, bool UV = false, unsigned FEAT = RTX_F_ALL>
-__global__ void __launch_bounds__(256, FEAT == RTX_F_ALL ? RTX_BOUNCE_BLOCKS : RTX_BOUNCE_BLOCKS_LEAN) k_bounce_flat(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, const __grid_constant__ DevCamera C, PassParams pp) {
+__global__ void __launch_bounds__(256, (FEAT & RTX_F_COMPLEX) ? RTX_BOUNCE_BLOCKS : RTX_BOUNCE_BLOCKS_LEAN) k_bounce_flat(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, const __grid_constant__ DevCamera C, PassParams pp) {
     BouncePolicyT<UV, FEAT> P{ctl, pool, cur, &S, &C, pp, ctl->n_cont, ctl->gen_base, 0.0, make_float4(0.f, 0.f, 0.f, 0.f)};
     TraceCounters tc = {0, 0, 0, 0, 0};
     const int n = ctl->n_active;
