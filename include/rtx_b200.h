@@ -285,7 +285,7 @@ int32_t rtx_set_stream(rtx_ctx* ctx, void* cuda_stream);
 int32_t rtx_get_stats(rtx_ctx* ctx, rtx_stats* out);
 /* Tunables: "pool_paths" (upper limit of in-flight path slots), "overlap_connect" (shadow rays on a second stream beside the next
  * wavefront iteration, default 1; the pass is complete on the context's stream when rtx_render_pass returns either way), "count_stats" (per-ray traversal counters: bit 0 extension rays, bit 1 shadow
- * rays), "time_kernels" (CUDA-event time per kernel kind, default 1), "fuse_tree" (hierarchy worlds shade inside the persistent trace
+ * rays), "time_kernels" (CUDA-event time per kernel kind, default 1), "lean" (kernel variants compiled per scene vocabulary, default 1; 0 = all-features kernels), "fuse_tree" (hierarchy worlds shade inside the persistent trace
  * kernel, default 0), "pretest_bare" (bare primitives beside a mesh are tested at pool entry instead of through the TLAS, default 0;
  * takes effect at the next rtx_scene_upload). Returns RTX_ERR_INVALID for unknown keys. */
 int32_t rtx_set_option(rtx_ctx* ctx, const char* key, int64_t value);
