@@ -159,6 +159,11 @@ def main():
         return 0
 
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines must not share stdout with the JSON line
+    # ... and because NCCL still wrote its version line to file descriptor 1 on the GPU box (NCCL_DEBUG=VERSION in the environment), everything any
+    # library prints while the bench runs goes to stderr; the real stdout comes back for the one JSON line
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     mg = importlib.import_module("go-raytracing_b200.multigpu")
     rank, world, local = mg.init_from_env("nccl")
@@ -359,6 +364,10 @@ def main():
             "wall_ms_per_step": wall * 1e3 / args.steps, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches) + args.steps,
             "roofline": roofline, "roofline_stream": roofline_stream, "cpu_baseline": cpu,
         }
+        sys.stdout.flush()
+        import ctypes
+        ctypes.CDLL(None).fflush(None)   # what C libraries still hold in their stdio buffers leaves through stderr too
+        os.dup2(_real_stdout, 1)
         print(json.dumps(line), flush=True)
     barrier()
     ctx.close()
