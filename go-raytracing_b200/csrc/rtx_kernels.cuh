@@ -226,6 +226,11 @@ struct ExtendPolicyT {
     static constexpr bool ANY_HIT = false;
     Ctl* ctl; char* hit; int* q_mat; int capacity; const char* rec; const DevScene* S; uint32_t seed_lo, seed_hi;
     __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:451
+    __device__ __forceinline__ void prefetch(int job) const {
+        const char* q = rec + (size_t)job * RTX_REC_BYTES;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(q + 64));
+    }
     __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
         const char* q = rec + (size_t)job * RTX_REC_BYTES;
         const D4 a = ld256d(q), c = ld256d(q + 32);
@@ -705,6 +710,12 @@ struct BouncePolicyT {
     int n_cont; unsigned long long gen_base;   // jobs >= n_cont are fresh camera paths: generated here, never written as records
     mutable double pixbits_; mutable float4 th_;   // identity and throughput | flags of the job this thread is working on (load -> retire)
     __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:451
+    __device__ __forceinline__ void prefetch(int job) const {
+        if (job >= n_cont) return;   // a fresh camera path: generated, not loaded
+        const char* q = pool.records(cur) + (size_t)job * RTX_REC_BYTES;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(q + 64));
+    }
     __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
         if (job >= n_cont) {
             unsigned long long ps;
@@ -833,6 +844,11 @@ struct ConnectPolicy {
     static constexpr bool ANY_HIT = true;
     Pool pool; uint32_t seed_lo, seed_hi;
     __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:579, :636
+    __device__ __forceinline__ void prefetch(int job) const {
+        const char* q = pool.shadow + (size_t)job * RTX_SHADOW_BYTES;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(q + 64));
+    }
     __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
         const char* q = pool.shadow + (size_t)job * RTX_SHADOW_BYTES;
         const D4 o0 = ld256d(q), d0 = ld256d(q + 32);
@@ -919,6 +935,7 @@ struct BatchPolicyT {
     const DevScene* S; const double* rays; double t0, t1;
     int* entry_id; int* prim_id; double* t; double* normal; unsigned char* front; double* uv; double* p;
     __device__ __forceinline__ double tmin() const { return t0; }
+    __device__ __forceinline__ void prefetch(int) const {}
     __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
         const double* q = rays + 7 * (size_t)job;
         r.ox = q[0]; r.oy = q[1]; r.oz = q[2]; r.dx = q[3]; r.dy = q[4]; r.dz = q[5]; r.tm = q[6];

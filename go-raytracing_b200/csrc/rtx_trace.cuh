@@ -101,6 +101,7 @@ struct Best {
 //   void   load(int job, RayD& r, double& tmax) const;      world-space ray of job `job` (called again when an instance ends)
 //   VolumeRng volume_rng(int job) const;
 //   void   retire(int job, bool valid, const RayD& r, const Best& b);   warp-collective: every lane calls it, `valid` lanes own a finished query
+//   void   prefetch(int job) const;                         trace_flat only: hint that `job` is loaded next (may do nothing)
 //
 // Ray pool. Every lane owns K ray slots whose whole state lives in shared memory (slot = k * 128 + thread: each field
 // is an array over slots, so a warp touching "its" slots of one k is bank-conflict free). Registers only hold a ray while
@@ -320,6 +321,11 @@ __device__ __forceinline__ void trace_flat(const DevScene& S, Policy& P, int njo
                     if (Policy::ANY_HIT && B.have) break;
                 }
         }
+#ifndef RTX_FLAT_PREFETCH
+#define RTX_FLAT_PREFETCH 0   /* measured: hdri-test 6933 Mpaths/s without, 6672 with; cornell-glossy 3146 / 3118 */
+#endif
+        // (off) the record of this thread's next job requested before the retire, whose warp-aggregated append waits for an atomic's return
+        if (RTX_FLAT_PREFETCH && job + (int)(gridDim.x * blockDim.x) < njobs) P.prefetch(job + (int)(gridDim.x * blockDim.x));
         P.retire(valid ? job : -1, valid, r, B);
     }
 }
