@@ -95,7 +95,7 @@ struct rtx_ctx {
     std::vector<cudaEvent_t> events;
     int num_sms = 0;
     int* batch_cursor = nullptr;  // job cursor of k_trace_closest
-    int trace_grid_lean = 0;      // grid of the lean variants of the persistent trace kernels
+    int trace_grid_sky = 0, trace_grid_lucy = 0;   // grids of the lean variants of the persistent trace kernels
     int* trace_spill = nullptr;   // global overflow columns of the trace kernels' shared-memory stacks
     int* trace_spill2 = nullptr;  // the same for k_connect (it may run beside k_extend)
     int trace_grid = 0;           // persistent grid: SMs x resident blocks
@@ -203,17 +203,16 @@ int32_t rtx_create(int32_t device_id, rtx_ctx** out) {
         rtx_destroy(ctx);
         return RTX_ERR_CUDA;
     }
-    for (int group = 0; group < 2; group++) {   // persistent trace kernels: opt in to the large dynamic shared-memory pool, size the grid to one resident wave
-        const int smem = group == 0 ? (int)RTX_TRACE_SMEM_BYTES : (int)RTX_TRACE_SMEM_BYTES_LEAN;
+    for (int group = 0; group < 3; group++) {   // persistent trace kernels: opt in to the large dynamic shared-memory pool, size the grid to one resident wave
+        // group 0: all-features kernels; the lean variants (RTX_FV_*) need fewer registers and smaller slots: their own block count, pool size and grid (1: SKY, 2: LUCY)
+        const int smem = group == 0 ? (int)RTX_TRACE_SMEM_BYTES : group == 1 ? (int)RTX_TRACE_SMEM_BYTES_OF(RTX_FV_SKY) : (int)RTX_TRACE_SMEM_BYTES_OF(RTX_FV_LUCY);
         int occ = 0, minOcc = 1 << 30;
         const std::vector<const void*> kernels = group == 0
             ? std::vector<const void*>{(const void*)k_extend<false>, (const void*)k_extend<true>, (const void*)k_extend<false, true>, (const void*)k_connect<false>,
                                  (const void*)k_connect<true>, (const void*)k_trace_closest<>, (const void*)k_bounce<false>, (const void*)k_bounce<true>,
                                  (const void*)k_bounce<false, true>}
-            // the lean variants (RTX_FV_*) need fewer registers: their own block count, pool size and grid
-            : std::vector<const void*>{(const void*)k_extend<false, false, RTX_FV_LUCY>, (const void*)k_extend<false, false, RTX_FV_SKY>,
-                                 (const void*)k_connect<false, RTX_FV_LUCY>, (const void*)k_connect<false, RTX_FV_SKY>, (const void*)k_trace_closest<RTX_FV_LUCY>,
-                                 (const void*)k_trace_closest<RTX_FV_SKY>};
+            : group == 1 ? std::vector<const void*>{(const void*)k_extend<false, false, RTX_FV_SKY>, (const void*)k_connect<false, RTX_FV_SKY>, (const void*)k_trace_closest<RTX_FV_SKY>}
+                         : std::vector<const void*>{(const void*)k_extend<false, false, RTX_FV_LUCY>, (const void*)k_connect<false, RTX_FV_LUCY>, (const void*)k_trace_closest<RTX_FV_LUCY>};
         // developer knob: shared-memory carve-out in KB (the rest of the 256 KB array is L1); fewer resident blocks, more L1
         const char* carveEnv = getenv("RTX_TRACE_CARVEOUT_KB");
         const int carveKB = carveEnv ? atoi(carveEnv) : 0;
@@ -228,11 +227,11 @@ int32_t rtx_create(int32_t device_id, rtx_ctx** out) {
             minOcc = std::min(minOcc, occ);
         }
         if (carveKB > 0) minOcc = std::max(1, std::min(minOcc, (int)((size_t)carveKB * 1024 / (smem + 1024))));
-        (group == 0 ? ctx->trace_grid : ctx->trace_grid_lean) = ctx->num_sms * minOcc;
-        if (getenv("RTX_DEBUG_BATCH")) fprintf(stderr, "[rtx] trace kernels (%s): %d blocks/SM, %d B dynamic smem per block, grid %d\n", group ? "lean" : "full", minOcc, smem, ctx->num_sms * minOcc);
+        (group == 0 ? ctx->trace_grid : group == 1 ? ctx->trace_grid_sky : ctx->trace_grid_lucy) = ctx->num_sms * minOcc;
+        if (getenv("RTX_DEBUG_BATCH")) fprintf(stderr, "[rtx] trace kernels (%s): %d blocks/SM, %d B dynamic smem per block, grid %d\n", group == 0 ? "full" : group == 1 ? "sky" : "lucy", minOcc, smem, ctx->num_sms * minOcc);
     }
     {
-        size_t spillInts = std::max((size_t)ctx->trace_grid * RTX_TRACE_SLOTS, (size_t)ctx->trace_grid_lean * RTX_TRACE_SLOTS_LEAN) * (RTX_STACK_SIZE - RTX_SMEM_STACK);
+        size_t spillInts = std::max((size_t)ctx->trace_grid * RTX_TRACE_SLOTS, (size_t)std::max(ctx->trace_grid_sky, ctx->trace_grid_lucy) * RTX_TRACE_SLOTS_LEAN) * (RTX_STACK_SIZE - RTX_SMEM_STACK);
         if ((e = cudaMalloc((void**)&ctx->trace_spill, spillInts * sizeof(int))) != cudaSuccess ||
             (e = cudaMalloc((void**)&ctx->trace_spill2, spillInts * sizeof(int))) != cudaSuccess) {
             fail(nullptr, RTX_ERR_CUDA, "rtx_create: %s", cudaGetErrorString(e));
@@ -1112,7 +1111,7 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
     CU(cudaEventRecord(evStart, st));
     // fixed grids: the stream kernels stride over device-side counts, the trace kernels are persistent (one resident wave of
     // warps pulls rays from a device-side cursor); the host only polls the control block every BATCH iterations
-    const int gridStream = std::min((P + 255) / 256, ctx->num_sms * 8), gridTrace = ctx->trace_grid, gridTraceLean = ctx->trace_grid_lean;
+    const int gridStream = std::min((P + 255) / 256, ctx->num_sms * 8), gridTrace = ctx->trace_grid;
     // The shadow rays of iteration i only feed the accumulation buffer, so k_connect(i) runs on a second stream beside
     // k_generate / k_extend / k_shade of iteration i + 1: its blocks move in as the persistent k_extend blocks of the next
     // iteration drain (the tail of a persistent launch otherwise leaves SMs idle), and the render stream has the higher
@@ -1163,8 +1162,8 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
                 if (ctx->count_stats & 1) k_extend_flat<true><<<gridStream, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, pp);
                 else k_extend_flat<false><<<gridStream, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, pp);
             } else if (ctx->count_stats & 1) k_extend<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
-            else if (lean == 1) k_extend<false, false, RTX_FV_LUCY><<<gridTraceLean, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_LEAN, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
-            else if (lean == 2) k_extend<false, false, RTX_FV_SKY><<<gridTraceLean, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_LEAN, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
+            else if (lean == 1) k_extend<false, false, RTX_FV_LUCY><<<ctx->trace_grid_lucy, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_LUCY), st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
+            else if (lean == 2) k_extend<false, false, RTX_FV_SKY><<<ctx->trace_grid_sky, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_SKY), st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
             else k_extend<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
             if (timing) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); }
             if (ctx->shade_split) {   // one launch per material queue (launches over empty queues return at once)
@@ -1196,8 +1195,8 @@ int32_t rtx_render_pass(rtx_ctx* ctx, int32_t spp, int32_t max_depth, int32_t ca
                     else if (lean == 4) k_connect_flat<false, RTX_FV_CORNELL><<<gridStream, 256, 0, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp);
                     else k_connect_flat<false><<<gridStream, 256, 0, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp);
                 } else if (ctx->count_stats & 2) k_connect<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
-                else if (lean == 1) k_connect<false, RTX_FV_LUCY><<<gridTraceLean, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_LEAN, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
-                else if (lean == 2) k_connect<false, RTX_FV_SKY><<<gridTraceLean, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_LEAN, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
+                else if (lean == 1) k_connect<false, RTX_FV_LUCY><<<ctx->trace_grid_lucy, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_LUCY), sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
+                else if (lean == 2) k_connect<false, RTX_FV_SKY><<<ctx->trace_grid_sky, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_SKY), sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
                 else k_connect<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
                 if (timing) cudaEventRecord(ev[7], sc);
                 if (overlap) { CU(cudaEventRecord(ctx->ev_connected[cur], sc)); pending[cur] = true; }
@@ -1307,7 +1306,7 @@ int32_t rtx_trace_closest(rtx_ctx* ctx, const double* rays, int64_t n, double tm
     const int lean = lean_variant(ctx);   // the variant a rendered pass of this scene runs: the bit-exact tests cover the lean code
     const int gf = std::min((int)((n + 255) / 256), ctx->num_sms * 8);
 #define RTX_TC_FLAT(F) k_trace_closest_flat<F><<<gf, 256, 0, ctx->stream>>>(ctx->S, dRays, (int)n, tmin, tmax, dEntry, dPrim, dT, dN, dFront, dUV, dP)
-#define RTX_TC_TREE(F) k_trace_closest<F><<<(F) == RTX_F_ALL ? ctx->trace_grid : ctx->trace_grid_lean, RTX_TRACE_THREADS, (F) == RTX_F_ALL ? RTX_TRACE_SMEM_BYTES : RTX_TRACE_SMEM_BYTES_LEAN, ctx->stream>>>(ctx->S, dRays, (int)n, tmin, tmax, ctx->batch_cursor, ctx->trace_spill, dEntry, dPrim, dT, dN, dFront, dUV, dP)
+#define RTX_TC_TREE(F) k_trace_closest<F><<<(F) == RTX_F_ALL ? ctx->trace_grid : (F) == RTX_FV_SKY ? ctx->trace_grid_sky : ctx->trace_grid_lucy, RTX_TRACE_THREADS, (F) == RTX_F_ALL ? RTX_TRACE_SMEM_BYTES : RTX_TRACE_SMEM_BYTES_OF(F), ctx->stream>>>(ctx->S, dRays, (int)n, tmin, tmax, ctx->batch_cursor, ctx->trace_spill, dEntry, dPrim, dT, dN, dFront, dUV, dP)
     if (ctx->scene_flat) {
         if (lean == 2) RTX_TC_FLAT(RTX_FV_SKY); else if (lean == 3 || lean == 1) RTX_TC_FLAT(RTX_FV_BOX); else if (lean == 4) RTX_TC_FLAT(RTX_FV_CORNELL); else RTX_TC_FLAT(RTX_F_ALL);
     } else {

@@ -216,8 +216,8 @@ __device__ __forceinline__ Hit best_to_hit(const Best& b) {
 
 extern __shared__ __align__(16) unsigned char rtx_smem[];  // the trace kernels' ray pool (TracePool)
 #define RTX_TRACE_SMEM_BYTES ((size_t)RTX_TRACE_SLOTS * RTX_SLOT_WORDS * 4 + RTX_POOL_EXTRA_BYTES)
-#define RTX_TRACE_SMEM_BYTES_LEAN ((size_t)RTX_TRACE_SLOTS_LEAN * RTX_SLOT_WORDS * 4 + RTX_POOL_EXTRA_BYTES)
-#define RTX_TRACE_BLOCKS_OF(FEAT) ((FEAT) == RTX_F_ALL ? RTX_TRACE_BLOCKS : RTX_TRACE_BLOCKS_LEAN)
+#define RTX_TRACE_SMEM_BYTES_OF(FEAT) ((size_t)RTX_TRACE_SLOTS_OF(FEAT) * RTX_SLOT_WORDS_OF(FEAT) * 4 + RTX_POOL_EXTRA_BYTES)
+#define RTX_TRACE_BLOCKS_OF(FEAT) ((FEAT) == RTX_F_ALL ? RTX_TRACE_BLOCKS : RTX_FEAT_HAS_TIME(FEAT) ? RTX_TRACE_BLOCKS_LEAN : RTX_TRACE_BLOCKS_LEAN_NT)
 #define RTX_TRACE_SLOTS_OF(FEAT) ((FEAT) == RTX_F_ALL ? RTX_TRACE_SLOTS : RTX_TRACE_SLOTS_LEAN)
 
 // ---- K2: extend — closest hit of every active path, then binning into material-sorted shading queues -------------

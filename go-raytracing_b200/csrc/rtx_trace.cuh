@@ -35,6 +35,9 @@
 #ifndef RTX_TRACE_BLOCKS_LEAN
 #define RTX_TRACE_BLOCKS_LEAN 6
 #endif
+#ifndef RTX_TRACE_BLOCKS_LEAN_NT
+#define RTX_TRACE_BLOCKS_LEAN_NT 7   /* lean variants whose slots do not carry the ray time (50 words): 7 x 160 slots fit the 228 KB of an SM */
+#endif
 #define RTX_ST_SENTINEL ((int)0x80000000)  /* stack marker: instance finished, back to the TLAS */
 #define RTX_ST_DONE ((int)0x80000001)
 #define RTX_ST_IDLE ((int)0x80000002)
@@ -140,19 +143,25 @@ struct Best {
 #define RTX_PH_E 2
 #define RTX_PH_R 3
 #define RTX_PH_NONE 4   /* parked: idle slot after the job queue ran dry */
-#define RTX_SLOT_WORDS (9 + 1 + 1 + 4 + 14 + 2 + 6 + RTX_SMEM_STACK)   /* 32-bit words of shared memory per ray slot */
+// 32-bit words of shared memory per ray slot: float32 ray 9, box offsets | stack pointer 1, ft 1, node / cur / job 3, current-space ray 12 (+ 2 for the ray
+// time, which only moving spheres and Volumes read: vocabularies without them do not carry it), best t 2, best ids 6, stack
+#define RTX_FEAT_HAS_TIME(FEAT) (((FEAT) & (RTX_F_SPHERE | RTX_F_COMPLEX)) != 0)
+#define RTX_SLOT_WORDS_T(TIME) (9 + 1 + 1 + 3 + 12 + ((TIME) ? 2 : 0) + 2 + 6 + RTX_SMEM_STACK)
+#define RTX_SLOT_WORDS_OF(FEAT) RTX_SLOT_WORDS_T(RTX_FEAT_HAS_TIME(FEAT))
+#define RTX_SLOT_WORDS RTX_SLOT_WORDS_T(true)
 #define RTX_POOL_EXTRA_BYTES 256                                        /* column states + flags */
 #define RTX_PH_BUSY 5   /* claimed by a warp for the current round */
 
-template <int NSLOTS>
+template <int NSLOTS, bool TIME = true>
 struct TracePool {
     static constexpr int NS = NSLOTS;
     static_assert(NSLOTS % 32 == 0 && NSLOTS <= 256, "slots per block: a multiple of 32, at most 8 per bank column");
     float* f;      // [9][NS]  ix iy iz cnx cny cnz cfx cfy cfz
     int* off;      // [NS]     offx | offy << 8 | offz << 16
     float* ft;     // [NS]
-    int *node, *sp, *cur, *job;
-    double* r;     // [7][NS]  current-space ray ox oy oz dx dy dz, and the ray time
+    int *node, *cur, *job;
+    unsigned char* spb;  // stack pointer of slot s: byte 3 of off[s] (spb[4 * s + 3]); the NODE phase reads it with the offsets, nobody else pays a word for it
+    double* r;     // [7][NS]  current-space ray ox oy oz dx dy dz, and (TIME) the ray time
     double* bt;    // [NS]
     int *be, *bk, *bp, *bi, *bre, *brp;  // best: entry, kind | have << 8, prim, item, rank_e, rank_p
     int* stack;    // [RTX_SMEM_STACK][NS]
@@ -160,13 +169,14 @@ struct TracePool {
     int* flags;    // [32]  flags[0]: job queue ran dry
     __device__ __forceinline__ explicit TracePool(unsigned char* base) {
         double* d = reinterpret_cast<double*>(base);
-        r = d; d += 7 * NS;
+        r = d; d += (TIME ? 7 : 6) * NS;
         bt = d; d += NS;
         float* w = reinterpret_cast<float*>(d);
         f = w; w += 9 * NS;
         ft = w; w += NS;
         int* q = reinterpret_cast<int*>(w);
-        off = q; q += NS; node = q; q += NS; sp = q; q += NS; cur = q; q += NS; job = q; q += NS;
+        off = q; q += NS; node = q; q += NS; cur = q; q += NS; job = q; q += NS;
+        spb = reinterpret_cast<unsigned char*>(off);
         be = q; q += NS; bk = q; q += NS; bp = q; q += NS; bi = q; q += NS; bre = q; q += NS; brp = q; q += NS;
         stack = q; q += RTX_SMEM_STACK * NS;
         col = reinterpret_cast<unsigned*>(q); q += 32;
@@ -181,14 +191,14 @@ struct TracePool {
     __device__ __forceinline__ void store_rayf(int s, const RayF& x) const {
         f[s] = x.ix; f[NS + s] = x.iy; f[2 * NS + s] = x.iz; f[3 * NS + s] = x.cnx; f[4 * NS + s] = x.cny; f[5 * NS + s] = x.cnz;
         f[6 * NS + s] = x.cfx; f[7 * NS + s] = x.cfy; f[8 * NS + s] = x.cfz;
-        off[s] = x.offx | (x.offy << 8) | (x.offz << 16);
+        off[s] = x.offx | (x.offy << 8) | (x.offz << 16);   // clears the stack-pointer byte: every caller stores sp after the ray
     }
     __device__ __forceinline__ void load_ray(int s, RayD& x) const {
-        x.ox = r[s]; x.oy = r[NS + s]; x.oz = r[2 * NS + s]; x.dx = r[3 * NS + s]; x.dy = r[4 * NS + s]; x.dz = r[5 * NS + s]; x.tm = r[6 * NS + s];
+        x.ox = r[s]; x.oy = r[NS + s]; x.oz = r[2 * NS + s]; x.dx = r[3 * NS + s]; x.dy = r[4 * NS + s]; x.dz = r[5 * NS + s]; x.tm = TIME ? r[(TIME ? 6 : 0) * NS + s] : 0.0;
     }
     __device__ __forceinline__ void store_ray(int s, const RayD& x, bool with_time) const {
         r[s] = x.ox; r[NS + s] = x.oy; r[2 * NS + s] = x.oz; r[3 * NS + s] = x.dx; r[4 * NS + s] = x.dy; r[5 * NS + s] = x.dz;
-        if (with_time) r[6 * NS + s] = x.tm;
+        if (TIME && with_time) r[(TIME ? 6 : 0) * NS + s] = x.tm;
     }
     __device__ __forceinline__ void load_best(int s, Best& b) const {
         b.t = bt[s]; b.ft = ft[s]; b.entry = be[s];
@@ -244,7 +254,7 @@ __device__ __forceinline__ void entry_core(const DevScene& S, int ei, const DEnt
 // quad / plane tests, the Volume free-flight with its log). Measured both ways on B200: inlined 1039 Mrays/s, out of line
 // (-DRTX_ENTRY_OOL) 958 on cornell-lucy. State travels through the shared-memory pool; Sp points at the kernel's
 // __grid_constant__ parameter.
-template <int NSLOTS>
+template <int NSLOTS, bool TIME>
 #ifndef RTX_ENTRY_OOL
 __device__ __forceinline__
 #else
@@ -253,7 +263,7 @@ __device__ __noinline__
 bool entry_other(const DevScene* Sp, unsigned char* smem, int s, int ei, double tmin, uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
                  uint32_t c2, bool transparent, TraceCounters* tcp) {
     const DevScene& S = *Sp;
-    const TracePool<NSLOTS> T(smem);
+    const TracePool<NSLOTS, TIME> T(smem);
     const DEntry e = S.entries[ei];
     RayD r;
     T.load_ray(s, r);
@@ -332,7 +342,7 @@ __device__ __forceinline__ void trace_flat(const DevScene& S, Policy& P, int njo
 
 template <class Policy, bool COUNT, int NSLOTS, unsigned FEAT = RTX_F_ALL>
 __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, int* cursor, int njobs, TraceCounters& tc, int* spill, unsigned char* smem) {
-    typedef TracePool<NSLOTS> Pool_;
+    typedef TracePool<NSLOTS, RTX_FEAT_HAS_TIME(FEAT)> Pool_;
     constexpr int NS = Pool_::NS;
     const Pool_ T(smem);
     const unsigned FULL = 0xffffffffu;
@@ -432,7 +442,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
         if (phase == RTX_PH_N) {
             // ---- NODE: one 4-wide node per lane -----------------------------------------------------------------------
             if (mine) {
-                int node = T.node[s], sp = T.sp[s];
+                int node = T.node[s], sp = T.spb[4 * s + 3];
                 const bool inst = T.cur[s] >= 0;
                 RayF f;
                 T.load_rayf(s, f);
@@ -465,7 +475,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                         else RTX_POP();
                     }
                 }
-                T.node[s] = node; T.sp[s] = sp;
+                T.node[s] = node; T.spb[4 * s + 3] = (unsigned char)sp;
                 newst = RTX_CLASSIFY(node, inst);
             }
         } else if ((FEAT & RTX_F_MESH) && phase == RTX_PH_T) {
@@ -494,7 +504,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                         bt = B.t;
                     }
                     if (Policy::ANY_HIT && have) { node = RTX_ST_DONE; break; }
-                    if (rem == 0) { int sp = T.sp[s]; RTX_POP(); T.sp[s] = sp; break; }
+                    if (rem == 0) { int sp = T.spb[4 * s + 3]; RTX_POP(); T.spb[4 * s + 3] = (unsigned char)sp; break; }
                     node = ~(((ti + 1) << 3) | (rem - 1));
                 }
                 T.node[s] = node;
@@ -503,7 +513,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
         } else if (phase == RTX_PH_E) {
             // ---- ENTRY: a world entry (TLAS leaf), or the end of an instance -----------------------------------------
             if (mine) {
-                int node = T.node[s], sp = T.sp[s];
+                int node = T.node[s], sp = T.spb[4 * s + 3];
                 const int job = T.job[s];
                 bool in_inst = false;
                 if ((FEAT & RTX_F_MESH) && node == RTX_ST_SENTINEL) {
@@ -595,12 +605,12 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                     } else if (FEAT & RTX_F_COMPLEX) {
                         VolumeRng vr = {0, 0, 0, 0, 0, true};
                         if (e.volume >= 0) vr = P.volume_rng(job);
-                        const bool have = entry_other<NSLOTS>(&S, smem, s, ei, tmin, vr.k0, vr.k1, vr.c0, vr.c1, vr.c2, vr.transparent, tcp);
+                        const bool have = entry_other<NSLOTS, RTX_FEAT_HAS_TIME(FEAT)>(&S, smem, s, ei, tmin, vr.k0, vr.k1, vr.c0, vr.c1, vr.c2, vr.transparent, tcp);
                         if (Policy::ANY_HIT && have) node = RTX_ST_DONE;
                         else RTX_POP();
                     } else RTX_POP();   // an entry outside the variant's vocabulary: unreachable for a scene the mask covers
                 }
-                T.node[s] = node; T.sp[s] = sp;
+                T.node[s] = node; T.spb[4 * s + 3] = (unsigned char)sp;
                 newst = RTX_CLASSIFY(node, in_inst);
             }
         } else {
@@ -663,7 +673,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                     if ((Policy::ANY_HIT && B.have) || S.tlas_root < 0) node = RTX_ST_DONE;
                     else { node = S.tlas_root; make_rayf(r, f); T.store_rayf(s, f); }
                     T.store_ray(s, r, true); T.store_best(s, B);
-                    T.node[s] = node; T.sp[s] = 0; T.cur[s] = -1; T.job[s] = my;
+                    T.node[s] = node; T.spb[4 * s + 3] = 0; T.cur[s] = -1; T.job[s] = my;
                     newst = RTX_CLASSIFY(node, false);
                 }
                 if (base + cnt >= njobs) {
