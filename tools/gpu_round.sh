@@ -18,6 +18,12 @@ RTX_OPTS=pool_paths=8388608 python tools/gpu_perf.py cornell-lucy 64 > $out/${ta
 ncu --set full --clock-control none --import-source on -k regex:k_extend -s 10 -c 1 -f -o $out/${tag}_prof_extend \
     env RTX_OPTS=pool_paths=8388608 python tools/gpu_perf.py cornell-lucy 64 > $out/${tag}_ncu.log 2>&1
 tail -2 $out/${tag}_ncu.log
+# the other two kernels that carry a BASELINE config: shadow rays of cornell-lucy, the one-kernel bounce of hdri-test
+ncu --set full --clock-control none --import-source on -k regex:k_connect -s 10 -c 1 -f -o $out/${tag}_prof_connect \
+    env RTX_OPTS=pool_paths=8388608 python tools/gpu_perf.py cornell-lucy 64 > $out/${tag}_ncu_connect.log 2>&1
+python tools/gpu_perf.py hdri-test 16 > $out/${tag}_plain3.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_bounce_flat -s 6 -c 1 -f -o $out/${tag}_prof_bounce \
+    python tools/gpu_perf.py hdri-test 16 > $out/${tag}_ncu_bounce.log 2>&1
 fi
 # per-scene throughput table (short passes) and pool-size A/B
 for s in cornell random cornell-glossy cornell-lucy hdri-test; do python tools/gpu_perf.py $s 64 2>&1 | tail -1; done > $out/${tag}_scenes.log
