@@ -81,6 +81,8 @@ class Stats(C.Structure):
         ("ms_generate", C.c_double), ("ms_extend", C.c_double), ("ms_shade", C.c_double), ("ms_connect", C.c_double), ("ms_total", C.c_double),
         ("tlas_nodes", C.c_uint32), ("blas_nodes", C.c_uint32), ("n_entries", C.c_uint32), ("n_tris", C.c_uint32),
         ("blas_depth", C.c_uint32), ("bvh_on_device", C.c_uint32), ("ms_bvh_build", C.c_double), ("ms_scene_upload", C.c_double),
+        ("ms_tail", C.c_double), ("ms_reduce", C.c_double), ("ms_resolve", C.c_double), ("tail_iterations", C.c_uint64),
+        ("n_devices", C.c_uint32), ("pad_", C.c_uint32),
     ]
 
     def as_dict(self):
@@ -92,7 +94,7 @@ ABI_SYMBOLS = [
     "rtx_create", "rtx_destroy", "rtx_last_error", "rtx_abi_version", "rtx_scene_upload", "rtx_camera_set", "rtx_image_size",
     "rtx_render_pass", "rtx_accum_clear", "rtx_accum_enable_moments", "rtx_accum_device_ptr", "rtx_resolve_rgba8", "rtx_resolve_accum",
     "rtx_trace_closest", "rtx_camera_rays", "rtx_hdri_sample", "rtx_hdri_pdf", "rtx_hdri_lookup", "rtx_hdri_total_power",
-    "rtx_get_stats", "rtx_set_option", "rtx_set_stream",
+    "rtx_get_stats", "rtx_set_option", "rtx_set_stream", "rtx_create_multi", "rtx_device_count",
 ]
 
 _lib_cache = None
@@ -114,6 +116,7 @@ def lib() -> C.CDLL:
         L.rtx_last_error.restype = C.c_char_p
         L.rtx_last_error.argtypes = [C.c_void_p]
         L.rtx_create.argtypes = [C.c_int32, C.POINTER(C.c_void_p)]
+        L.rtx_create_multi.argtypes = [_pi, C.c_int32, C.POINTER(C.c_void_p)]
         L.rtx_destroy.argtypes = [C.c_void_p]
         L.rtx_scene_upload.argtypes = [C.c_void_p, C.POINTER(SceneDesc)]
         L.rtx_camera_set.argtypes = [C.c_void_p, C.POINTER(CameraDesc)]
@@ -520,17 +523,29 @@ class RtxError(RuntimeError):
     pass
 
 
-class Context:
-    """One GPU context of the CUDA library (rtx_ctx)."""
+def device_count() -> int:
+    return int(lib().rtx_device_count())
 
-    def __init__(self, device: int = 0):
+
+class Context:
+    """One context of the CUDA library (rtx_ctx): one GPU, or — `devices=[...]` — several GPUs of the box behind one context
+    (rtx_create_multi: the library slices the samples of a pass over the devices and sums the buffers with one ncclReduce)."""
+
+    def __init__(self, device: int = 0, devices: Optional[Sequence[int]] = None):
         self._L = lib()
         h = C.c_void_p()
-        rc = self._L.rtx_create(device, C.byref(h))
+        if devices is not None:
+            ids = (C.c_int32 * len(devices))(*devices)
+            rc = self._L.rtx_create_multi(ids, len(devices), C.byref(h))
+            what, device = f"rtx_create_multi({list(devices)})", devices[0]
+        else:
+            rc = self._L.rtx_create(device, C.byref(h))
+            what = f"rtx_create({device})"
         if rc != 0:
-            raise RtxError(f"rtx_create({device}) = {rc}: {self._L.rtx_last_error(None).decode()}")
+            raise RtxError(f"{what} = {rc}: {self._L.rtx_last_error(None).decode()}")
         self._h = h
         self.device = device
+        self.devices = list(devices) if devices is not None else [device]
         self.width = self.height = 0
 
     def _check(self, rc, what):

@@ -54,7 +54,14 @@ struct Ctl {  // device-resident control block of the wavefront loop
     int cur_extend, cur_connect[2];  // job cursors of the persistent trace kernels (k_connect: by iteration parity)
     // statistics
     unsigned long long ext_rays, shadow_rays, nodes, tris, spheres, quads, planes, iterations;
+    // the tail of a pass: iterations after its last camera path was generated (the stream only shrinks), timed on the device
+    unsigned long long t_tail_begin, t_end, tail_iterations;
 };
+__device__ __forceinline__ unsigned long long rtx_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 // Path state: a STREAM, not a slot pool. The in-flight paths of one wavefront iteration are the records [0, n_active) of
 // rec[cur]: the survivors of the previous iteration (written by k_shade in the order it appended them) followed by the
@@ -67,6 +74,7 @@ struct Ctl {  // device-resident control block of the wavefront loop
 // or, when per-sample moments are requested (parity tests), to a per-sample sum that a final pass squares and folds in.
 #define RTX_REC_BYTES 96       /* [ox oy oz time][dx dy dz (pixel | sample << 32)][throughput rgb, bounce | allowLightHits << 16]; packed (128-byte stride: hdri-test -10 %) */
 #define RTX_HIT_BYTES 64       /* [Px Py Pz t][Nx Ny Nz (material | front << 31)] */
+#define RTX_HIT_BYTES_UV 96    /* scenes with image textures: + [u v - -] in float64 — ImageTexture.Value computes int(u * W), int((1 - v) * H) in float64 (rt/image_texture.go:27-43) */
 #define RTX_SHADOW_BYTES 96    /* [ox oy oz tmax][dx dy dz (pixel | sample << 32)][contribution rgb, bounce][-] */
 struct Pool {
     int capacity;
@@ -76,6 +84,7 @@ struct Pool {
     char* shadow;     // [2P] shadow requests of the current iteration, self-contained
     float* target;    // where radiance goes: float4 per pixel (accumulation buffer) or, with moments, float4 per sample of this pass
     int moments;
+    int hit_bytes;    // stride of `hit`: RTX_HIT_BYTES, or RTX_HIT_BYTES_UV in scenes with image textures
     uint32_t npix, sample_base;
     __device__ __forceinline__ char* records(int which) const { return which ? rec[1] : rec[0]; }   // (no dynamic indexing of a kernel parameter)
     __device__ __forceinline__ float* contribution_target(uint32_t pixel, uint32_t sample) const {
@@ -122,6 +131,11 @@ __global__ void k_iter_begin(Ctl* ctl, int capacity, int par) {
     for (int i = 0; i < Q_COUNT; i++) ctl->n_mat[i] = 0;
     ctl->done = (n_cont + n_gen == 0);
     ctl->iterations += (n_cont + n_gen != 0);
+    if (n_gen == 0) {   // nothing left to generate: the drain
+        if (ctl->t_tail_begin == 0) ctl->t_tail_begin = rtx_globaltimer();
+        if (n_cont != 0) ctl->tail_iterations++;
+        else if (ctl->t_end == 0) ctl->t_end = rtx_globaltimer();
+    }
 }
 
 // ---- K1: camera ray generation (rt/camera.go:368-435) ----------------------------------------------------------
@@ -253,11 +267,10 @@ struct ExtendPolicyT {
                 HitInfo hi;
                 finalize_hit<FEAT>(*S, r, best_to_hit(b), UV, hi);
                 const long long bits = (long long)(unsigned)hi.mat | (hi.front ? (1LL << 31) : 0);
-                char* h = hit + (size_t)job * RTX_HIT_BYTES;
-                // the fourth word: t, or — in scenes with image textures — the hit's (u, v) as two float32 (texel lookup only)
-                const double w4 = UV ? __longlong_as_double(((long long)__float_as_uint((float)hi.v) << 32) | (long long)__float_as_uint((float)hi.u)) : b.t;
-                st256d(h, hi.P.x, hi.P.y, hi.P.z, w4);
+                char* h = hit + (size_t)job * (UV ? RTX_HIT_BYTES_UV : RTX_HIT_BYTES);
+                st256d(h, hi.P.x, hi.P.y, hi.P.z, b.t);
                 st256d(h + 32, hi.N.x, hi.N.y, hi.N.z, __longlong_as_double(bits));
+                if (UV) st256d(h + 64, hi.u, hi.v, 0.0, 0.0);   // scenes with image textures: the hit's (u, v) in float64, like rec.U / rec.V
                 const int mt = S->mats[hi.mat].type;
                 q = mt == RTX_MAT_LAMBERTIAN ? Q_LAMBERTIAN : mt == RTX_MAT_METAL ? Q_METAL : mt == RTX_MAT_DIELECTRIC ? Q_DIELECTRIC
                     : mt == RTX_MAT_DIFFUSE_LIGHT ? Q_LIGHT : Q_ISOTROPIC;
@@ -315,7 +328,7 @@ __device__ __noinline__ double perlin_noise(const double* vec, const int* perm, 
     return accum;
 }
 template <unsigned FEAT = RTX_F_ALL>
-__device__ __forceinline__ float3 tex_value(const DevScene& S, int id, D3 p, float u = 0.f, float v = 0.f) {
+__device__ __forceinline__ float3 tex_value(const DevScene& S, int id, D3 p, double u = 0.0, double v = 0.0) {
     DTexture t = S.texs[id];
     for (int guard = 0; guard < 8 && t.type == RTX_TEX_CHECKER; guard++) {
         long long xi = (long long)floor(t.inv_scale * p.x + 1e-4);
@@ -339,8 +352,8 @@ __device__ __forceinline__ float3 tex_value(const DevScene& S, int id, D3 p, flo
     }
     if ((FEAT & RTX_F_TEX_X) && t.type == RTX_TEX_IMAGE) {  // ImageTexture.Value rt/image_texture.go:27-43 + ImageLoader.PixelData rt/image_loader.go:97-120
         const int4 dim = S.img_dim[t.even];
-        const double uu = u < 0.f ? 0.0 : (u > 1.f ? 1.0 : (double)u);
-        const double vv = 1.0 - (v < 0.f ? 0.0 : (v > 1.f ? 1.0 : (double)v));   // flip V to image coordinates
+        const double uu = u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);                  // Interval{0,1}.Clamp, float64 like the reference
+        const double vv = 1.0 - (v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v));           // flip V to image coordinates
         const int i = clampi_img((int)(uu * (double)dim.x), dim.x), j = clampi_img((int)(vv * (double)dim.y), dim.y);
         const size_t first = ((size_t)(unsigned)dim.w << 32) | (unsigned)dim.z;
         const float4 c = __ldg(S.img_rgb + first + (size_t)j * dim.x + i);
@@ -453,7 +466,7 @@ struct ShadeVars {
 // the path record's time, pixel | sample and throughput | flags; P_in, N, (hu, hv), mat, front are the hit (unused for Q_MISS).
 template <unsigned FEAT = RTX_F_ALL>
 __device__ __forceinline__ void shade_element(const DevScene& S, const DevCamera& C, const PassParams& pp, const Pool& pool, const int type, const D3 rd,
-                                              const D3 P_in, const D3 N, const float hu, const float hv, const int mat, const bool front, ShadeVars& V) {
+                                              const D3 P_in, const D3 N, const double hu, const double hv, const int mat, const bool front, ShadeVars& V) {
     bool& cont = V.cont; bool& has_env = V.has_env; bool& has_area = V.has_area;
     D3& nd = V.nd; D3& env_dir = V.env_dir; D3& area_dir = V.area_dir;
     double& area_tmax = V.area_tmax;
@@ -666,7 +679,7 @@ __global__ void __launch_bounds__(256, FEAT != RTX_F_ALL ? RTX_SHADE_BLOCKS_LEAN
             const char* nrec = pool.records(cur) + (size_t)job_next * RTX_REC_BYTES;
             asm volatile("prefetch.global.L1 [%0];" ::"l"(nrec));
             asm volatile("prefetch.global.L1 [%0];" ::"l"(nrec + 64));
-            if (type_next != Q_MISS) asm volatile("prefetch.global.L1 [%0];" ::"l"(pool.hit + (size_t)job_next * RTX_HIT_BYTES));
+            if (type_next != Q_MISS) asm volatile("prefetch.global.L1 [%0];" ::"l"(pool.hit + (size_t)job_next * pool.hit_bytes));
         }
     } else if (i + stride < n_rounded) job_next = locate(i + stride, type_next);
     bool valid = QT >= 0 ? job_cur >= 0 : type >= 0;
@@ -679,15 +692,15 @@ __global__ void __launch_bounds__(256, FEAT != RTX_F_ALL ? RTX_SHADE_BLOCKS_LEAN
         V.tm = ro4.w; V.pixbits = rd4.w;
         V.th = *reinterpret_cast<const float4*>(rec + 64);
         D3 P = d3(0, 0, 0), N = d3(0, 0, 0);
-        float hu = 0.f, hv = 0.f;   // rec.U, rec.V: carried only in scenes with image textures
+        double hu = 0.0, hv = 0.0;   // rec.U, rec.V: carried only in scenes with image textures (96-byte hit records)
         int mat = 0;
         bool front = false;
         if (type != Q_MISS) {
-            const char* hrec = pool.hit + (size_t)job * RTX_HIT_BYTES;
+            const char* hrec = pool.hit + (size_t)job * pool.hit_bytes;
             const D4 hp = ld256d(hrec), hn = ld256d(hrec + 32);
             P = d3(hp.x, hp.y, hp.z);
             N = d3(hn.x, hn.y, hn.z);
-            if (S.n_images > 0) { const long long uvb = __double_as_longlong(hp.w); hu = __uint_as_float((unsigned)uvb); hv = __uint_as_float((unsigned)(uvb >> 32)); }
+            if (S.n_images > 0) { const D4 huv = ld256d(hrec + 64); hu = huv.x; hv = huv.y; }
             const long long bits = __double_as_longlong(hn.w);
             mat = (int)(bits & 0x7fffffff);
             front = (bits >> 31) & 1;
@@ -752,7 +765,7 @@ struct BouncePolicyT {
                 type = mt == RTX_MAT_LAMBERTIAN ? Q_LAMBERTIAN : mt == RTX_MAT_METAL ? Q_METAL : mt == RTX_MAT_DIELECTRIC ? Q_DIELECTRIC
                      : mt == RTX_MAT_DIFFUSE_LIGHT ? Q_LIGHT : Q_ISOTROPIC;
             }
-            shade_element<FEAT>(*S, *C, pp, pool, type, d3(r.dx, r.dy, r.dz), hi.P, hi.N, UV ? (float)hi.u : 0.f, UV ? (float)hi.v : 0.f, hi.mat, hi.front, V);
+            shade_element<FEAT>(*S, *C, pp, pool, type, d3(r.dx, r.dy, r.dz), hi.P, hi.N, UV ? hi.u : 0.0, UV ? hi.v : 0.0, hi.mat, hi.front, V);
         }
         shade_commit(ctl, pool, cur, V);
     }
@@ -800,7 +813,7 @@ __device__ __noinline__ void bounce_shade(const DevScene* S, const DevCamera* C,
         type = mt == RTX_MAT_LAMBERTIAN ? Q_LAMBERTIAN : mt == RTX_MAT_METAL ? Q_METAL : mt == RTX_MAT_DIELECTRIC ? Q_DIELECTRIC
              : mt == RTX_MAT_DIFFUSE_LIGHT ? Q_LIGHT : Q_ISOTROPIC;
     }
-    shade_element(*S, *C, *pp, *pool, type, d3(r.dx, r.dy, r.dz), hi.P, hi.N, UV ? (float)hi.u : 0.f, UV ? (float)hi.v : 0.f, hi.mat, hi.front, V);
+    shade_element(*S, *C, *pp, *pool, type, d3(r.dx, r.dy, r.dz), hi.P, hi.N, UV ? hi.u : 0.0, UV ? hi.v : 0.0, hi.mat, hi.front, V);
     *Vp = V;
 }
 template <bool UV>

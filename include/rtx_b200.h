@@ -214,6 +214,14 @@ typedef struct rtx_stats {
     uint32_t bvh_on_device;    /* 1: built by the device builder (replaces NewBVHNodeFromList, rt/bvh.go:64) */
     double ms_bvh_build;       /* device time of all mesh builds (0 with the host builder)                   */
     double ms_scene_upload;    /* host wall time of the whole rtx_scene_upload call                          */
+    /* ---- appended in round 2 (the fields above keep their offsets) ---- */
+    double ms_tail;            /* last pass: device time from the launch that generated the pass's last camera path to the end
+                                  of the pass — the drain iterations in which the stream only shrinks                        */
+    double ms_reduce;          /* multi-device contexts: the NCCL sum-reduce of the accumulation buffers after the last pass */
+    double ms_resolve;         /* last rtx_resolve_rgba8: kernel + device-to-host copy (CUDA events)                         */
+    uint64_t tail_iterations;  /* wavefront iterations of the last pass after its last camera path was generated            */
+    uint32_t n_devices;        /* 1, or the device count of an rtx_create_multi context                                      */
+    uint32_t pad_;
 } rtx_stats;
 
 typedef struct rtx_ctx rtx_ctx;
@@ -221,6 +229,17 @@ typedef struct rtx_ctx rtx_ctx;
 /* ---- lifecycle ---------------------------------------------------------------------- */
 /* Replaces: NewBucketRenderer's allocation half (rt/bucket_renderer.go:54-74). One context = one GPU. */
 int32_t rtx_create(int32_t device_id, rtx_ctx** out);
+/* The same for N GPUs of one box behind ONE context: the reference is one process whose renderPass fans the
+ * work out to its worker goroutines (rt/bucket_renderer.go:193-213, numWorkers from main.go:83-93); here renderPass fans the pass
+ * out to `n` devices. Every call on the returned context acts on all of them: rtx_scene_upload / rtx_camera_set replicate the
+ * scene, rtx_render_pass gives device g the sample slice [sample_base + g*spp/n, sample_base + (g+1)*spp/n) on a host thread of
+ * its own and then sums the accumulation buffers onto device_ids[0] with ONE ncclReduce over NVLink (NCCL is loaded with
+ * dlopen("libnccl.so.2") here, so single-GPU users never need it); resolve, statistics and the batch entry points read
+ * device_ids[0]. n == 1 is rtx_create. Device ids must be distinct. */
+int32_t rtx_create_multi(const int32_t* device_ids, int32_t n, rtx_ctx** out);
+int32_t rtx_device_count(void);   /* CUDA devices visible to the process (0 when there is none: rtx_create then fails) */
+/* Waits for the context's own streams only; a caller-owned stream passed to rtx_set_stream must still be alive or must have been
+ * replaced with NULL before it was destroyed. */
 int32_t rtx_destroy(rtx_ctx* ctx);
 const char* rtx_last_error(const rtx_ctx* ctx); /* ctx may be NULL: last create error of this thread */
 int32_t rtx_abi_version(void);

@@ -22,4 +22,4 @@ for rep in range(2):
     print(f"[{name} {sc.width}x{sc.height} {spp}spp d{depth} {os.environ.get('RTX_OPTS','')} {os.path.basename(os.environ.get('RTX_B200_LIB','default'))}] "
           f"{st['ms_total']:.1f} ms: {st['paths']/st['ms_total']/1e3:.1f} Mpaths/s {rays/st['ms_total']/1e3:.0f} Mrays/s | "
           f"ms gen/ext/shade/conn {st['ms_generate']:.1f}/{st['ms_extend']:.1f}/{st['ms_shade']:.1f}/{st['ms_connect']:.1f} | "
-          f"ext {st['extension_rays']/max(st['ms_extend'],1e-9)/1e3:.0f} Mr/s conn {st['shadow_rays']/max(st['ms_connect'],1e-9)/1e3:.0f} Mr/s iters {st['wavefront_iterations']} nodes/ray {st['nodes_visited']/max(rays,1):.2f} tris/ray {st['tri_tests']/max(rays,1):.2f} quads/ray {st['quad_tests']/max(rays,1):.2f} spheres/ray {st['sphere_tests']/max(rays,1):.3f} planes/ray {st['plane_tests']/max(rays,1):.3f}", flush=True)
+          f"tail {st['ms_tail']:.2f} ms / {st['tail_iterations']} it | ext {st['extension_rays']/max(st['ms_extend'],1e-9)/1e3:.0f} Mr/s conn {st['shadow_rays']/max(st['ms_connect'],1e-9)/1e3:.0f} Mr/s iters {st['wavefront_iterations']} nodes/ray {st['nodes_visited']/max(rays,1):.2f} tris/ray {st['tri_tests']/max(rays,1):.2f} quads/ray {st['quad_tests']/max(rays,1):.2f} spheres/ray {st['sphere_tests']/max(rays,1):.3f} planes/ray {st['plane_tests']/max(rays,1):.3f}", flush=True)
