@@ -1,0 +1,251 @@
+"""Known-answer tests of the integrator that are derived from the REFERENCE SOURCE and closed-form optics, not from
+oracle/oracle.cpp: each expected image below is computed here in numpy from the formulas of rt/camera.go and rt/material.go.
+The oracle (CPU, `-m "not gpu"`) and the CUDA path (`-m gpu`) must each reproduce them, so a misreading shared by the two
+restatements — both written from the same reading of the Go code — no longer passes unnoticed.
+
+KATs
+  nee_quad      E[ min(20, nL * att * E * cos/p_L * p_L / (p_L + cos/pi)) ] for a Lambertian floor under one quad light at depth 1,
+                by deterministic quadrature over the pixel footprint and the light (rt/camera.go:610-678, rt/quad.go:87-97,
+                Lambertian.PDF rt/material.go:70-76) — including the per-component clamp at 20 BEFORE the throughput multiply;
+  furnace       a Lambertian / fuzz-1 Metal / Dielectric sphere inside a closed DiffuseLight sphere without registered lights:
+                albedo * E exactly (zero variance), albedo * E * (1 + cos theta_i) / 2 (Metal.Scatter absorbs when
+                dot(scattered, n) <= 0, rt/material.go:113-119; the normal component of a uniform unit vector is uniform on
+                [-1, 1]), and E (rt/material.go:164-188 attenuates by 1);
+  one_sided_mis with a registered light a Lambertian hit switches emission off for the BSDF-sampled continuation
+                (rt/camera.go:477-480, :514) while an escaping ray still collects the full background (:453-466).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+PI_GO = 3.1415926535897932385
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the pinhole camera of rt/camera.go:286-344 / :368-386, written from the source (fast path, no defocus)
+# ---------------------------------------------------------------------------------------------------------------
+def unit(a):
+    a = np.asarray(a, dtype=np.float64)
+    return a / np.sqrt((a * a).sum(axis=-1, keepdims=True))
+
+
+def camera_rays(W, aspect, vfov, look_from, look_at, vup, focus, sub, corners=False):
+    """Ray origin and directions [H, W, sub, sub, 3] through a sub x sub midpoint grid of every pixel's jitter square
+    (corners=True: a grid that includes the square's edges, for footprint masks)."""
+    H = max(int(W / aspect), 1)
+    lf, la, up = (np.asarray(x, dtype=np.float64) for x in (look_from, look_at, vup))
+    vh = 2 * math.tan(vfov * PI_GO / 180.0 / 2) * focus
+    vw = vh * (W / H)
+    w = unit(lf - la); u = unit(np.cross(up, w)); v = np.cross(w, u)
+    du, dv = u * vw / W, -v * vh / H
+    p00 = lf - w * focus - u * vw / 2 + v * vh / 2 + 0.5 * (du + dv)
+    off = np.linspace(-0.5, 0.5, sub) if corners else (np.arange(sub) + 0.5) / sub - 0.5
+    jj, ii, sy, sx = np.meshgrid(np.arange(H), np.arange(W), off, off, indexing="ij")
+    ps = p00 + (ii + sx)[..., None] * du + (jj + sy)[..., None] * dv
+    return lf, ps - lf, H
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# KAT 1: next-event estimation towards one quad light
+# ---------------------------------------------------------------------------------------------------------------
+NEE = dict(W=24, aspect=1.0, vfov=70.0, look_from=(0.0, 1.5, 0.0), look_at=(0.0, 0.0, 0.0), vup=(0.0, 0.0, 1.0), focus=1.0,
+           albedo=(0.6, 0.5, 0.4), emit=(400.0, 30.0, 12.0), lq=((-0.5, 2.0, -0.5), (1.0, 0.0, 0.0), (0.0, 0.0, 1.0)))
+
+
+def nee_scene(grt, spp):
+    b = grt.SceneBuilder(world_is_bvh=False)
+    floor = b.material("lambertian", NEE["albedo"])
+    lm = b.material("light", NEE["emit"])
+    b.entry(grt.GEOM_QUAD, b.quadp((-40, 0, -40), (80, 0, 0), (0, 0, 80), floor))
+    lq = b.quadp(*NEE["lq"], lm)
+    b.entry(grt.GEOM_QUAD, lq)
+    b.light(lq)
+    cam = grt.make_camera(NEE["W"], NEE["aspect"], spp, 1, NEE["vfov"], NEE["look_from"], NEE["look_at"], vup=NEE["vup"], focus_dist=NEE["focus"])
+    return b.build(), cam
+
+
+def nee_expected(sub=6, m=48):
+    """Pixel means at depth 1 by midpoint quadrature: sub x sub points of the jitter square, m x m points of the light."""
+    o, d, H = camera_rays(NEE["W"], NEE["aspect"], NEE["vfov"], NEE["look_from"], NEE["look_at"], NEE["vup"], NEE["focus"], sub)
+    t = -o[1] / d[..., 1]                                # the floor y = 0
+    P = o + t[..., None] * d                             # [H, W, s, s, 3]
+    n = np.array([0.0, 1.0, 0.0])                        # floor normal against the ray (the camera is above)
+    Q, u, v = (np.asarray(x, dtype=np.float64) for x in NEE["lq"])
+    nl = unit(np.cross(u, v)); area = np.linalg.norm(np.cross(u, v))
+    g = (np.arange(m) + 0.5) / m
+    a, bb = np.meshgrid(g, g, indexing="ij")
+    L = Q + a[..., None] * u + bb[..., None] * v          # light points, SamplePoint rt/quad.go:87-92
+    toL = L[None, None, None, None] - P[:, :, :, :, None, None, :]
+    dist = np.sqrt((toL * toL).sum(-1))
+    ld = toL / dist[..., None]
+    cos_t = (ld * n).sum(-1)
+    cos_l = np.abs((-ld * nl).sum(-1))
+    ok = (cos_t > 0) & ~(cos_l < 0.001)
+    pdf_l = dist * dist / (np.maximum(cos_l, 1e-300) * area)
+    pdf_b = np.maximum(cos_t, 0) / PI_GO                 # Lambertian.PDF
+    s = np.where(ok, cos_t / pdf_l * (pdf_l / (pdf_l + pdf_b)), 0.0)
+    out = np.zeros(P.shape[:2] + (3,))
+    for c in range(3):                                   # contribution = emission * s * attenuation * nLights, clamped per component
+        out[..., c] = np.minimum(NEE["emit"][c] * s * NEE["albedo"][c] * 1.0, 20.0).mean(axis=(2, 3, 4, 5))
+    return out
+
+
+def check_nee(mean_img, spp, who):
+    exp = nee_expected()
+    assert mean_img.shape == exp.shape
+    assert exp[..., 0].max() == 20.0 and exp[..., 1].max() < 20.0, "the KAT must exercise the clamp in one channel and not in another"
+    rel = np.abs(mean_img.mean(axis=(0, 1)) - exp.mean(axis=(0, 1))) / exp.mean(axis=(0, 1))
+    assert np.all(rel < 0.005), f"{who}: image mean {mean_img.mean(axis=(0, 1))} vs quadrature {exp.mean(axis=(0, 1))} ({rel})"
+    blk = lambda x: x.reshape(6, 4, 6, 4, 3).mean(axis=(1, 3))
+    brel = np.abs(blk(mean_img) - blk(exp)) / np.maximum(blk(exp), 1e-3 * exp.max())
+    assert brel.max() < 0.02, f"{who}: 4x4 block means differ from the quadrature by up to {brel.max():.4f}"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# KAT 2-4: furnace
+# ---------------------------------------------------------------------------------------------------------------
+FUR = dict(W=32, aspect=1.0, vfov=30.0, look_from=(0.0, 0.0, 6.0), look_at=(0.0, 0.0, 0.0), vup=(0.0, 1.0, 0.0), focus=1.0, E=(0.8, 0.9, 1.0))
+
+
+def furnace_scene(grt, kind, spp, depth):
+    b = grt.SceneBuilder(world_is_bvh=False)
+    if kind == "lambertian": m = b.material("lambertian", (0.3, 0.5, 0.7))
+    elif kind == "metal1": m = b.material("metal", (0.9, 0.6, 0.3), 1.0)
+    elif kind == "metal0": m = b.material("metal", (0.9, 0.6, 0.3), 0.0)
+    else: m = b.material("dielectric", 1.5)
+    b.entry(grt.GEOM_SPHERE, b.sphere((0, 0, 0), 1.0, m))
+    b.entry(grt.GEOM_SPHERE, b.sphere((0, 0, 0), 100.0, b.material("light", FUR["E"])))   # seen from inside: DiffuseLight emits on both faces
+    cam = grt.make_camera(FUR["W"], FUR["aspect"], spp, depth, FUR["vfov"], FUR["look_from"], FUR["look_at"], vup=FUR["vup"], focus_dist=FUR["focus"])
+    return b.build(), cam
+
+
+def furnace_expected(kind, sub=8):
+    o, d, H = camera_rays(FUR["W"], FUR["aspect"], FUR["vfov"], FUR["look_from"], FUR["look_at"], FUR["vup"], FUR["focus"], sub)
+    a = (d * d).sum(-1); h = -(d * o).sum(-1); c = (o * o).sum() - 1.0          # unit sphere at the origin: oc = -o
+    disc = h * h - a * c
+    hit = disc > 0
+    t = (h - np.sqrt(np.maximum(disc, 0))) / a
+    n = o + t[..., None] * d
+    cos_i = -(unit(d) * n).sum(-1)
+    E = np.asarray(FUR["E"])
+    if kind == "lambertian": f = np.asarray((0.3, 0.5, 0.7))[None, None, None, None] * np.ones_like(cos_i)[..., None]
+    elif kind == "metal1": f = np.asarray((0.9, 0.6, 0.3)) * ((1.0 + cos_i) / 2.0)[..., None]
+    elif kind == "metal0": f = np.asarray((0.9, 0.6, 0.3)) * np.ones_like(cos_i)[..., None]
+    else: f = np.ones(cos_i.shape + (3,))
+    img = np.where(hit[..., None], f * E, E)
+    oc, dc, _ = camera_rays(FUR["W"], FUR["aspect"], FUR["vfov"], FUR["look_from"], FUR["look_at"], FUR["vup"], FUR["focus"], 9, corners=True)
+    hc = (-(dc * oc).sum(-1)) ** 2 - (dc * dc).sum(-1) * ((oc * oc).sum() - 1.0) > 0       # footprint masks: the whole jitter square, edges included
+    inside, outside = hc.all(axis=(2, 3)), (~hc).all(axis=(2, 3))
+    return img.mean(axis=(2, 3)), inside, outside
+
+
+def check_furnace(mean_img, kind, who):
+    exp, inside, outside = furnace_expected(kind)
+    assert inside.sum() > 50 and outside.sum() > 200
+    assert np.allclose(mean_img[outside], exp[outside], rtol=2e-6, atol=0), f"{who}: background pixels must be the emission exactly"
+    if kind in ("lambertian", "metal0", "dielectric"):
+        # deterministic: every sample of such a pixel returns albedo * E (float32 accumulation on the device: 1e-5)
+        tol = 2e-5 if kind != "dielectric" else 2e-3     # glass: a path may still be inside when the depth limit cuts it (total internal reflection)
+        assert np.allclose(mean_img[inside], exp[inside], rtol=tol, atol=0), f"{who} {kind}: {np.abs(mean_img[inside] / exp[inside] - 1).max()}"
+    else:
+        got, want = mean_img[inside].mean(axis=0), exp[inside].mean(axis=0)
+        assert np.all(np.abs(got / want - 1) < 0.004), f"{who} metal fuzz 1: mean over the disc {got} vs albedo E (1 + cos) / 2 = {want}"
+        # and pixel by pixel within the Bernoulli noise of the absorption test
+        p = exp[inside][:, 0] / (0.9 * FUR["E"][0])
+        return p
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# KAT 5: what a registered light switches off, and what it does not
+# ---------------------------------------------------------------------------------------------------------------
+def mis_scene(grt, spp, register_light, sky_sphere):
+    b = grt.SceneBuilder(world_is_bvh=False)
+    floor = b.material("lambertian", (0.5, 0.4, 0.3))
+    b.entry(grt.GEOM_QUAD, b.quadp((-50, 0, -50), (100, 0, 0), (0, 0, 100), floor))
+    black = b.quadp((-0.1, 3.0, -0.1), (0.2, 0, 0), (0, 0, 0.2), b.material("light", (0, 0, 0)))   # a (registered) light that emits nothing
+    b.entry(grt.GEOM_QUAD, black)
+    if register_light: b.light(black)
+    if sky_sphere: b.entry(grt.GEOM_SPHERE, b.sphere((0, 0, 0), 200.0, b.material("light", (0.7, 0.8, 0.9))))
+    cam = grt.make_camera(16, 1.0, spp, 2, 40.0, (0, 1.0, 0), (0, 0, 0), vup=(0, 0, 1), focus_dist=1.0, background=(0.7, 0.8, 0.9))
+    return b.build(), cam
+
+
+MIS_CASES = {   # (register_light, sky_sphere) -> expected floor radiance at depth 2, as a multiple of albedo * (0.7, 0.8, 0.9)
+    (False, True): 1.0,    # no NEE: the BSDF-sampled ray reaches the emissive sphere and collects it
+    (True, True): 0.0,     # NEE ran (and found a black light): the continuation is not allowed to see emitters
+    (True, False): 1.0,    # ... but an ESCAPING continuation still collects the full background
+    (False, False): 1.0,
+}
+
+
+def check_mis(mean_img, case, who):
+    want = MIS_CASES[case] * np.asarray((0.5, 0.4, 0.3)) * np.asarray((0.7, 0.8, 0.9))
+    # (the black 0.2 x 0.2 quad hides 0.04 / (9 pi) = 0.14 % of the cosine-weighted hemisphere above the floor)
+    got = mean_img.mean(axis=(0, 1))
+    assert np.allclose(got, want, rtol=0.015, atol=1e-6), f"{who} {case}: floor radiance {got}, expected {want}"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# runners
+# ---------------------------------------------------------------------------------------------------------------
+def oracle_mean(orc, built, cam, spp, depth, seed=5):
+    o = orc.OracleScene(built.desc_ptr, C.pointer(cam))
+    r = o.render(spp, depth, seed=seed, threads=0, use_atomics=False, moments=False)
+    return r["sum"] / spp
+
+
+def gpu_mean(ctx, built, cam, spp, depth, seed=5):
+    ctx.load((built, cam))
+    ctx.enable_moments(False)
+    ctx.clear()
+    ctx.render_pass(spp, depth, seed=seed)
+    s, _, cnt = ctx.resolve_accum()
+    assert np.all(cnt == spp)
+    return s.astype(np.float64) / spp
+
+
+def test_nee_quadrature_is_converged():
+    """The quadrature itself: doubling both grids moves no pixel by more than 0.1 %."""
+    a, b = nee_expected(sub=4, m=32), nee_expected(sub=6, m=48)
+    assert np.abs(a - b).max() < 1e-3 * b.max()
+
+
+def test_nee_kat_oracle(grt, orc):
+    built, cam = nee_scene(grt, 4096)
+    check_nee(oracle_mean(orc, built, cam, 4096, 1), 4096, "oracle")
+
+
+@pytest.mark.parametrize("kind", ["lambertian", "metal0", "metal1", "dielectric"])
+def test_furnace_kat_oracle(grt, orc, kind):
+    spp = 2048 if kind == "metal1" else 64
+    built, cam = furnace_scene(grt, kind, spp, 50)
+    check_furnace(oracle_mean(orc, built, cam, spp, 50), kind, "oracle")
+
+
+@pytest.mark.parametrize("case", sorted(MIS_CASES))
+def test_one_sided_mis_kat_oracle(grt, orc, case):
+    built, cam = mis_scene(grt, 512, *case)
+    check_mis(oracle_mean(orc, built, cam, 512, 2), case, "oracle")
+
+
+@pytest.mark.gpu
+def test_nee_kat_gpu(grt, ctx):
+    built, cam = nee_scene(grt, 16384)
+    check_nee(gpu_mean(ctx, built, cam, 16384, 1), 16384, "gpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["lambertian", "metal0", "metal1", "dielectric"])
+def test_furnace_kat_gpu(grt, ctx, kind):
+    spp = 8192 if kind == "metal1" else 64
+    built, cam = furnace_scene(grt, kind, spp, 50)
+    check_furnace(gpu_mean(ctx, built, cam, spp, 50), kind, "gpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(MIS_CASES))
+def test_one_sided_mis_kat_gpu(grt, ctx, case):
+    built, cam = mis_scene(grt, 2048, *case)
+    check_mis(gpu_mean(ctx, built, cam, 2048, 2), case, "gpu")
