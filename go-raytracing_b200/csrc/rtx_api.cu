@@ -30,6 +30,7 @@ using rtxbvh::Box;
 using rtxbvh::Node4;
 
 static thread_local std::string g_create_error;
+static inline float __int_as_float_host(int v) { float f; std::memcpy(&f, &v, sizeof f); return f; }
 
 struct DevBuf {
     void* p = nullptr;
@@ -89,6 +90,7 @@ struct rtx_ctx {
     float4* per_sample = nullptr; size_t per_sample_cap = 0;   // moments mode: per-sample radiance sums of the running pass (grow-only)
     int flat_max_entries = 16, scene_flat = 0, scene_has_mesh = 0;   // worlds of <= flat_max_entries entries without a mesh are traced by the flat kernels (trace_flat)
     int pixel_major = 1;  // path order of k_generate: all samples of a pixel consecutively (1) or sample-major (0)
+    int tlas_flat_max = RTX_TLAS_FLAT_MAX;   // mesh worlds with at most this many bounded entries: top level as a per-ray sorted list (0 = hierarchy)
     int bvh_device = 1;   // mesh BLAS construction on the device (rtx_bvh_gpu.cuh); 0 = host builder (rtx_bvh.hpp), kept for A/B
     double ms_upload_blas = 0, ms_upload_total = 0;
     int blas_depth = 0, built_on_device = 0;
@@ -397,6 +399,10 @@ static int32_t set_option_single(rtx_ctx* ctx, const char* key, int64_t value) {
         ctx->scene_flat = ctx->have_scene && !ctx->scene_has_mesh && ctx->S.n_entries <= ctx->flat_max_entries;
     }
     else if (k == "bvh_device") ctx->bvh_device = value != 0;  // takes effect at the next rtx_scene_upload
+    else if (k == "tlas_flat_max") {   // takes effect at the next rtx_scene_upload
+        if (value < 0 || value > RTX_SMEM_STACK) return fail(ctx, RTX_ERR_INVALID, "tlas_flat_max must be in 0..%d", RTX_SMEM_STACK);
+        ctx->tlas_flat_max = (int)value;
+    }
     else if (k == "blas_leaf") {  // triangles per BLAS leaf (1..8); takes effect at the next rtx_scene_upload
         if (value < 1 || value > 8) return fail(ctx, RTX_ERR_INVALID, "blas_leaf must be in 1..8");
         ctx->blas_leaf = (int)value;
@@ -838,7 +844,8 @@ static int32_t scene_upload_single(rtx_ctx* ctx, const rtx_scene_desc* d) {
     size_t before = nodes.size();
     int tlasRoot = rtxbvh::build_bvh4(tb, 1, nodes, perm, [&](int first, int) { return first; }, &tlasDepth);
     // worst-case traversal stack: up to 3 deferred children per level on both levels + the instance marker
-    if (3 * (tlasDepth + maxBlasDepth) + 2 > RTX_STACK_SIZE)
+    const bool flatTop = hasMesh && ctx->tlas_flat_max > 0 && (int)boundedIdx.size() <= std::min(ctx->tlas_flat_max, RTX_SMEM_STACK) && d->n_entries <= 256;
+    if (3 * (tlasDepth + maxBlasDepth) + 2 > RTX_STACK_SIZE || (flatTop && (int)boundedIdx.size() + 3 * maxBlasDepth + 2 > RTX_STACK_SIZE))
         return fail(ctx, RTX_ERR_UNSUPPORTED, "BVH too deep for the device traversal stack (TLAS depth %d, BLAS depth %d, stack %d)", tlasDepth,
                     maxBlasDepth, RTX_STACK_SIZE);
     // leaf codes reference positions in `perm`; rewrite them to entry indices
@@ -850,6 +857,14 @@ static int32_t scene_upload_single(rtx_ctx* ctx, const rtx_scene_desc* d) {
     ctx->n_entries = d->n_entries;
     ctx->n_tris = (uint32_t)totalTris;
 
+    // a mesh world with a handful of bounded entries: the top level also goes up as a flat list of entry boxes (DevScene::tlas_boxes)
+    std::vector<float4> tlasBoxes;
+    if (flatTop)
+        for (size_t k = 0; k < boundedIdx.size(); k++) {
+            const Box& b = tb[k];
+            tlasBoxes.push_back(make_float4(rtxbvh::round_down(b.lo[0]), rtxbvh::round_down(b.lo[1]), rtxbvh::round_down(b.lo[2]), __int_as_float_host(boundedIdx[k])));
+            tlasBoxes.push_back(make_float4(rtxbvh::round_up(b.hi[0]), rtxbvh::round_up(b.hi[1]), rtxbvh::round_up(b.hi[2]), 0.f));
+        }
     std::vector<DXform> xfs(d->n_xforms);
     for (int x = 0; x < d->n_xforms; x++) {
         xfs[x].type = d->xf_type[x]; xfs[x].pad = 0;
@@ -917,6 +932,7 @@ static int32_t scene_upload_single(rtx_ctx* ctx, const rtx_scene_desc* d) {
         WANT(circles, S.circles); WANT(circleMat, S.circle_mat); WANT(perlinVec, S.perlin_vec); WANT(perlinPerm, S.perlin_perm);
         WANT(imgRgb, S.img_rgb); WANT(imgDim, S.img_dim); WANT(flatSimple, S.flat_simple); WANT(flatComplex, S.flat_complex);
         WANT(listItems, S.list_items); WANT(xfs, S.xforms); WANT(xfCanon, S.xf_canon); WANT(vols, S.volumes); WANT(mats, S.mats); WANT(texs, S.texs);
+        WANT(tlasBoxes, S.tlas_boxes);
         WANT(lights, S.light_quads); WANT(envTex, S.env_tex); WANT(marg, S.env_marg); WANT(cond, S.env_cond); WANT(pdf, S.env_pdf);
 #undef WANT
         size_t total = geom + bInfo;
@@ -962,6 +978,7 @@ static int32_t scene_upload_single(rtx_ctx* ctx, const rtx_scene_desc* d) {
     S.tlas_root = tlasRoot;
     S.n_entries = d->n_entries;
     S.n_unbounded = (int)unbounded.size();
+    S.n_tlas_flat = (int)(tlasBoxes.size() / 2);
     S.n_lights = d->n_lights;
     S.n_images = d->n_images;
     S.n_flat_simple = (int)flatSimple.size(); S.n_flat_complex = (int)flatComplex.size();

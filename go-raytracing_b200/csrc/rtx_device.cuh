@@ -12,7 +12,7 @@
 
 #include "../../include/rtx_b200.h"
 
-#define RTX_STACK_SIZE 48   /* checked against the built hierarchy at upload (rtx_api.cu) */
+#define RTX_STACK_SIZE 64   /* checked against the built hierarchy at upload (rtx_api.cu) */
 #define RTX_TRI_D 12        /* doubles per triangle record */
 
 // ---- 256-bit global loads / stores (sm_100: LDG.E.256 / STG.E.256) --------------------------------------------------------
@@ -75,6 +75,11 @@ struct DevScene {
     const DEntry* entries;
     const int* unbounded;  // entries tested for every ray (infinite Plane: universe bbox, rt/plane.go:17)
     int n_unbounded;
+    // Worlds of a few bounded entries around a mesh (CornellBoxLucy: 6 quads + 10 instances): the top level is a LIST, not a
+    // hierarchy. Every ray tests all entry boxes when it enters the ray pool — all lanes of the refill, no NODE rounds — and
+    // starts with its entries on the stack, nearest first, each carrying its entry distance (see RTX_TLAS_CODE in rtx_trace.cuh).
+    const float4* tlas_boxes;   // [2 * n_tlas_flat]: (lo.xyz, entry index as int bits) (hi.xyz, -), float32 rounded outward
+    int n_tlas_flat;            // 0: the top level is traversed as a hierarchy from tlas_root
     const double* spheres;  // 8 doubles: c0.xyz, vel.xyz, radius, -
     const int* sph_mat;
     const double* quads;    // 16 doubles: Q, u, v, w, normal, D (rt/quad.go:16-33)

@@ -138,6 +138,16 @@ struct Best {
 #ifndef RTX_E_ROOT_STEP
 #define RTX_E_ROOT_STEP 1   /* ENTRY of a mesh instance tests the BLAS root's children before committing to the instance */
 #endif
+#ifndef RTX_TLAS_FLAT_MAX
+#define RTX_TLAS_FLAT_MAX 16   /* bounded world entries up to which a mesh world's top level is a sorted list built at refill (0 = always a hierarchy); at most RTX_SMEM_STACK */
+#endif
+// Stack code of a top-level entry in flat-TLAS mode: bit 31 (leaf class), bits 30..8 = the upper 23 bits of the float32 entry distance
+// (truncated, i.e. rounded DOWN for the positive distances that occur: still a lower bound), bits 7..0 = world entry index. The distance
+// is at least tmin > 0, so bits 30..8 are never all zero and the code cannot collide with RTX_ST_SENTINEL / DONE / IDLE. Codes of one
+// ray order like their distances when compared as unsigned integers.
+#define RTX_TLAS_CODE(tn, ei) ((int)(0x80000000u | ((unsigned)__float_as_int(tn) & 0x7fffff00u) | (unsigned)(ei)))
+#define RTX_TLAS_CODE_DIST(code) (__int_as_float((code) & 0x7fffff00))
+#define RTX_TLAS_CODE_ENTRY(code) ((code) & 0xff)
 #define RTX_PH_N 0
 #define RTX_PH_T 1
 #define RTX_PH_E 2
@@ -351,6 +361,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
     const float ftmin = __double2float_rd(tmin);
     const float INF = __int_as_float(0x7f800000);
     TraceCounters* const tcp = COUNT ? &tc : nullptr;
+    const bool flatTlas = (FEAT & RTX_F_MESH) && RTX_TLAS_FLAT_MAX > 0 && S.n_tlas_flat > 0;   // uniform: the top level is a sorted list on each ray's stack
     const size_t spill_stride = (size_t)gridDim.x * NS;
     int* const spill_col = spill + (size_t)blockIdx.x * NS;
 
@@ -377,6 +388,9 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
 #define RTX_PUSH(v) do { if (sp < RTX_SMEM_STACK) T.stack[sp * NS + s] = (v); else spill_col[(size_t)(sp - RTX_SMEM_STACK) * spill_stride + s] = (v); sp++; } while (0)
 #define RTX_POP() do { if (sp > 0) { sp--; node = sp < RTX_SMEM_STACK ? T.stack[sp * NS + s] : spill_col[(size_t)(sp - RTX_SMEM_STACK) * spill_stride + s]; } \
                        else node = RTX_ST_DONE; } while (0)
+// pop at the top level: in flat-TLAS mode the entries are sorted nearest first and carry their entry distance, so when the next one lies
+// beyond the best hit the query is finished (ft: float32 upper bound of the best t, re-read because the phase may just have improved it)
+#define RTX_POP_TOP() do { RTX_POP(); if (flatTlas && node != RTX_ST_DONE && RTX_TLAS_CODE_DIST(node) > T.ft[s]) { node = RTX_ST_DONE; sp = 0; } } while (0)
 #define RTX_CLASSIFY(nd, inst) ((nd) >= 0 ? RTX_PH_N : (nd) == RTX_ST_DONE ? RTX_PH_R : (nd) == RTX_ST_SENTINEL ? RTX_PH_E : (inst) ? RTX_PH_T : RTX_PH_E)
 
 #define RTX_HASZERO_NIB(x) ((((x) - 0x11111111u) & ~(x)) & 0x88888888u)   /* lowest set bit marks the lowest zero nibble exactly */
@@ -475,6 +489,9 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                         else RTX_POP();
                     }
                 }
+                // flat top level: the instance is exhausted and the nearest top-level entry still waiting lies beyond the best hit (they are
+                // sorted, so all of them do): the query is finished without the round that would restore the world ray
+                if ((FEAT & RTX_F_MESH) && flatTlas && node == RTX_ST_SENTINEL && (sp == 0 || RTX_TLAS_CODE_DIST(T.stack[(sp - 1) * NS + s]) > ftmax)) node = RTX_ST_DONE;
                 T.node[s] = node; T.spb[4 * s + 3] = (unsigned char)sp;
                 newst = RTX_CLASSIFY(node, inst);
             }
@@ -504,7 +521,13 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                         bt = B.t;
                     }
                     if (Policy::ANY_HIT && have) { node = RTX_ST_DONE; break; }
-                    if (rem == 0) { int sp = T.spb[4 * s + 3]; RTX_POP(); T.spb[4 * s + 3] = (unsigned char)sp; break; }
+                    if (rem == 0) {
+                        int sp = T.spb[4 * s + 3];
+                        RTX_POP();
+                        if (flatTlas && node == RTX_ST_SENTINEL && (sp == 0 || RTX_TLAS_CODE_DIST(T.stack[(sp - 1) * NS + s]) > T.ft[s])) node = RTX_ST_DONE;   // as in the NODE phase
+                        T.spb[4 * s + 3] = (unsigned char)sp;
+                        break;
+                    }
                     node = ~(((ti + 1) << 3) | (rem - 1));
                 }
                 T.node[s] = node;
@@ -523,9 +546,9 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                     make_rayf(r, f);
                     T.store_ray(s, r, false); T.store_rayf(s, f);
                     T.cur[s] = -1;
-                    RTX_POP();
+                    RTX_POP_TOP();
                 } else {
-                    const int ei = ~node;
+                    const int ei = flatTlas ? RTX_TLAS_CODE_ENTRY(node) : ~node;
                     const DEntry e = S.entries[ei];
                     if ((FEAT & RTX_F_MESH) && e.volume < 0 && e.kind == RTX_GEOM_MESH) {
                         RayD r2; RayF f;
@@ -548,7 +571,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
 #ifdef RTX_DEBUG_ENTRY_COUNT
                             if (COUNT) tc.planes++;
 #endif
-                            RTX_POP();
+                            RTX_POP_TOP();
                         } else {
 #ifdef RTX_DEBUG_ENTRY_COUNT
                             if (COUNT) tc.spheres++;
@@ -601,14 +624,14 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                         B.offer(t, ei, e.rank, e.kind, e.index, 0, 0);
                         T.store_best(s, B);
                         if (Policy::ANY_HIT && B.have) node = RTX_ST_DONE;
-                        else RTX_POP();
+                        else RTX_POP_TOP();
                     } else if (FEAT & RTX_F_COMPLEX) {
                         VolumeRng vr = {0, 0, 0, 0, 0, true};
                         if (e.volume >= 0) vr = P.volume_rng(job);
                         const bool have = entry_other<NSLOTS, RTX_FEAT_HAS_TIME(FEAT)>(&S, smem, s, ei, tmin, vr.k0, vr.k1, vr.c0, vr.c1, vr.c2, vr.transparent, tcp);
                         if (Policy::ANY_HIT && have) node = RTX_ST_DONE;
-                        else RTX_POP();
-                    } else RTX_POP();   // an entry outside the variant's vocabulary: unreachable for a scene the mask covers
+                        else RTX_POP_TOP();
+                    } else RTX_POP_TOP();   // an entry outside the variant's vocabulary: unreachable for a scene the mask covers
                 }
                 T.node[s] = node; T.spb[4 * s + 3] = (unsigned char)sp;
                 newst = RTX_CLASSIFY(node, in_inst);
@@ -669,11 +692,34 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                             B.test_prim(S, e.kind, e.index, ro, tmin, ei, e.rank, 0, 0, tcp);
                         }
                     }
-                    int node;
-                    if ((Policy::ANY_HIT && B.have) || S.tlas_root < 0) node = RTX_ST_DONE;
+                    int node, sp = 0;
+                    if ((Policy::ANY_HIT && B.have) || (S.tlas_root < 0 && !flatTlas)) node = RTX_ST_DONE;
+                    else if (flatTlas) {
+                        // the top level as a list: every entry box against the ray (conservative float32 slabs, as node_test), the hit ones
+                        // pushed with their entry distance and kept sorted, nearest on top
+                        make_rayf(r, f); T.store_rayf(s, f);
+                        const bool sx = f.offx != 0, sy = f.offy != 0, sz = f.offz != 0;
+                        const float ftm = B.ft;
+                        for (int q = 0; q < S.n_tlas_flat; q++) {
+                            const float4 lo = __ldg(S.tlas_boxes + 2 * q), hi = __ldg(S.tlas_boxes + 2 * q + 1);
+                            float tn = fmaxf(fmaxf(fmaf(sx ? hi.x : lo.x, f.ix, f.cnx), fmaf(sy ? hi.y : lo.y, f.iy, f.cny)), fmaxf(fmaf(sz ? hi.z : lo.z, f.iz, f.cnz), ftmin));
+                            float tf = fminf(fminf(fmaf(sx ? lo.x : hi.x, f.ix, f.cfx), fmaf(sy ? lo.y : hi.y, f.iy, f.cfy)), fminf(fmaf(sz ? lo.z : hi.z, f.iz, f.cfz), ftm));
+                            tn = fmaf(-fabsf(tn), RTX_BOX_EPS, tn);
+                            tf = fmaf(fabsf(tf), RTX_BOX_EPS, tf);
+                            if (COUNT && (q & 3) == 0) tc.nodes++;   // four 32-byte entry boxes = the bytes of one 4-wide node
+                            if (tn <= tf) {
+                                const int code = RTX_TLAS_CODE(fmaxf(tn, 1e-30f), __float_as_int(lo.w));
+                                int k = sp;
+                                while (k > 0 && (unsigned)T.stack[(k - 1) * NS + s] < (unsigned)code) { T.stack[k * NS + s] = T.stack[(k - 1) * NS + s]; k--; }
+                                T.stack[k * NS + s] = code;
+                                sp++;
+                            }
+                        }
+                        if (sp > 0) { sp--; node = T.stack[sp * NS + s]; } else node = RTX_ST_DONE;
+                    }
                     else { node = S.tlas_root; make_rayf(r, f); T.store_rayf(s, f); }
                     T.store_ray(s, r, true); T.store_best(s, B);
-                    T.node[s] = node; T.spb[4 * s + 3] = 0; T.cur[s] = -1; T.job[s] = my;
+                    T.node[s] = node; T.spb[4 * s + 3] = (unsigned char)sp; T.cur[s] = -1; T.job[s] = my;
                     newst = RTX_CLASSIFY(node, false);
                 }
                 if (base + cnt >= njobs) {
@@ -691,6 +737,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
     }
 #undef RTX_HASZERO_NIB
 #undef RTX_PUSH
+#undef RTX_POP_TOP
 #undef RTX_POP
 #undef RTX_CLASSIFY
 }

@@ -144,7 +144,9 @@ def furnace_expected(kind, sub=8):
 def check_furnace(mean_img, kind, who):
     exp, inside, outside = furnace_expected(kind)
     assert inside.sum() > 50 and outside.sum() > 200
-    assert np.allclose(mean_img[outside], exp[outside], rtol=2e-6, atol=0), f"{who}: background pixels must be the emission exactly"
+    # (exactly in the float64 oracle; the device adds float32 samples with RED.ADD.F32: 64 additions of 0.8 round to 1e-6, the 8192 of
+    # the fuzzy-metal case drift by 6.5e-5 — at the configs' 10-1024 spp the accumulation error stays below 1e-5)
+    assert np.allclose(mean_img[outside], exp[outside], rtol=2e-4 if kind == "metal1" else 5e-6, atol=0), f"{who}: background pixels must be the emission"
     if kind in ("lambertian", "metal0", "dielectric"):
         # deterministic: every sample of such a pixel returns albedo * E (float32 accumulation on the device: 1e-5)
         tol = 2e-5 if kind != "dielectric" else 2e-3     # glass: a path may still be inside when the depth limit cuts it (total internal reflection)
