@@ -825,3 +825,42 @@ def test_bucket_renderer_update_never_blocks(grt, orc):
     ref, _ = sc.bucket_render(seed=4)
     # same seeds -> same Philox streams; float32 atomics order may flip the last bit of a few 8-bit pixels
     assert np.mean(pix != ref) < 0.01 and np.abs(pix.astype(np.int32) - ref.astype(np.int32)).max() <= 2
+
+
+# ------------------------------------------------------------------------------------------------------------
+# N devices behind one context (rtx_create_multi): needs at least two GPUs, skipped on a one-GPU box
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,width,spp,depth", [("cornell-glossy", 160, 16, 5), ("cornell-lucy", 200, 9, 12), ("random", 160, 7, 20)])
+def test_multi_device_context_equals_one_device(grt, name, width, spp, depth):
+    """rtx_create_multi: the library slices the samples of a pass over its devices (one host thread each) and sums the accumulation
+    buffers with one ncclReduce. Same Philox counters as one device -> the same image up to float32 summation order; the sample
+    count channel adds up exactly; a second pass accumulates on top of the first (the peers restart from zero after every reduce)."""
+    n = grt.device_count()
+    if n < 2:
+        pytest.skip("needs two CUDA devices")
+    devs = list(range(min(n, 4)))
+    sc = grt.config_scene(name, width=width, spp=spp, depth=depth)
+    one = grt.Context(0)
+    one.load(sc); one.clear(); one.enable_moments(True)
+    one.render_pass(spp, depth, seed=9)
+    one.render_pass(3, depth, seed=9, sample_base=spp)
+    s1, q1, c1 = one.resolve_accum(moments=True)
+    many = grt.Context(devices=devs)
+    many.load(sc); many.clear(); many.enable_moments(True)
+    many.render_pass(spp, depth, seed=9)            # spp is not a multiple of the device count in two of the cases: uneven slices
+    st = many.stats()
+    many.render_pass(3, depth, seed=9, sample_base=spp)
+    s2, q2, c2 = many.resolve_accum(moments=True)
+    assert st["n_devices"] == len(devs) and st["paths"] == sc.width * sc.height * spp and st["ms_reduce"] > 0
+    assert np.array_equal(c1, c2) and np.all(c2 == spp + 3)
+    assert np.allclose(s1, s2, rtol=2e-5, atol=1e-6), np.abs(s1 - s2).max()
+    assert np.allclose(q1, q2, rtol=2e-5, atol=1e-6)
+    pix1, pix2 = one.resolve_rgba8(spp + 3), many.resolve_rgba8(spp + 3)
+    assert np.abs(pix1.astype(int) - pix2.astype(int)).max() <= 1
+    # level 1 through the multi-device context (device 0 answers)
+    rng = np.random.default_rng(3)
+    ij, sq, disk, tm = camera_batch(sc.width, sc.height, 20000, rng)
+    rays = one.camera_rays(ij, sq, disk, tm)
+    h1, h2 = one.trace_closest(rays), many.trace_closest(rays)
+    assert np.array_equal(h1["entry"], h2["entry"]) and np.array_equal(h1["prim"], h2["prim"]) and np.array_equal(h1["t"], h2["t"])
+    one.close(); many.close()
