@@ -22,6 +22,9 @@
 #ifndef RTX_PRETEST_BARE_DEFAULT
 #define RTX_PRETEST_BARE_DEFAULT 0
 #endif
+#ifndef RTX_SIMPLE_BELOW_DEFAULT
+#define RTX_SIMPLE_BELOW_DEFAULT 0
+#endif
 #ifndef RTX_FUSE_TREE_DEFAULT
 #define RTX_FUSE_TREE_DEFAULT 0
 #endif
@@ -90,6 +93,7 @@ struct rtx_ctx {
     float4* per_sample = nullptr; size_t per_sample_cap = 0;   // moments mode: per-sample radiance sums of the running pass (grow-only)
     int flat_max_entries = 16, scene_flat = 0, scene_has_mesh = 0;   // worlds of <= flat_max_entries entries without a mesh are traced by the flat kernels (trace_flat)
     int pixel_major = 1;  // path order of k_generate: all samples of a pixel consecutively (1) or sample-major (0)
+    int simple_below = RTX_SIMPLE_BELOW_DEFAULT;   // hierarchy worlds: iterations of the drain with at most this many rays run the one-thread-per-ray trace kernels (0 = never)
     int tlas_flat_max = RTX_TLAS_FLAT_MAX;   // mesh worlds with at most this many bounded entries: top level as a per-ray sorted list (0 = hierarchy)
     int bvh_device = 1;   // mesh BLAS construction on the device (rtx_bvh_gpu.cuh); 0 = host builder (rtx_bvh.hpp), kept for A/B
     double ms_upload_blas = 0, ms_upload_total = 0;
@@ -392,6 +396,7 @@ static int32_t set_option_single(rtx_ctx* ctx, const char* key, int64_t value) {
         if (value < 0 || value > 64) return fail(ctx, RTX_ERR_INVALID, "pretest_bare must be in 0..64");
         ctx->pretest_bare = (int)value;
     }
+    else if (k == "simple_below") ctx->simple_below = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 30));
     else if (k == "overlap_connect") ctx->overlap_connect = value != 0;   // k_connect on its own stream beside the next iteration (default on)
     else if (k == "flat_max_entries") {   // 0 = always traverse the hierarchy
         if (value < 0 || value > 64) return fail(ctx, RTX_ERR_INVALID, "flat_max_entries must be in 0..64");
@@ -844,7 +849,7 @@ static int32_t scene_upload_single(rtx_ctx* ctx, const rtx_scene_desc* d) {
     size_t before = nodes.size();
     int tlasRoot = rtxbvh::build_bvh4(tb, 1, nodes, perm, [&](int first, int) { return first; }, &tlasDepth);
     // worst-case traversal stack: up to 3 deferred children per level on both levels + the instance marker
-    const bool flatTop = hasMesh && ctx->tlas_flat_max > 0 && (int)boundedIdx.size() <= std::min(ctx->tlas_flat_max, RTX_SMEM_STACK) && d->n_entries <= 256;
+    const bool flatTop = hasMesh && ctx->tlas_flat_max > 0 && (int)boundedIdx.size() <= std::min(ctx->tlas_flat_max, 16) && d->n_entries <= 256;
     if (3 * (tlasDepth + maxBlasDepth) + 2 > RTX_STACK_SIZE || (flatTop && (int)boundedIdx.size() + 3 * maxBlasDepth + 2 > RTX_STACK_SIZE))
         return fail(ctx, RTX_ERR_UNSUPPORTED, "BVH too deep for the device traversal stack (TLAS depth %d, BLAS depth %d, stack %d)", tlasDepth,
                     maxBlasDepth, RTX_STACK_SIZE);
@@ -932,7 +937,6 @@ static int32_t scene_upload_single(rtx_ctx* ctx, const rtx_scene_desc* d) {
         WANT(circles, S.circles); WANT(circleMat, S.circle_mat); WANT(perlinVec, S.perlin_vec); WANT(perlinPerm, S.perlin_perm);
         WANT(imgRgb, S.img_rgb); WANT(imgDim, S.img_dim); WANT(flatSimple, S.flat_simple); WANT(flatComplex, S.flat_complex);
         WANT(listItems, S.list_items); WANT(xfs, S.xforms); WANT(xfCanon, S.xf_canon); WANT(vols, S.volumes); WANT(mats, S.mats); WANT(texs, S.texs);
-        WANT(tlasBoxes, S.tlas_boxes);
         WANT(lights, S.light_quads); WANT(envTex, S.env_tex); WANT(marg, S.env_marg); WANT(cond, S.env_cond); WANT(pdf, S.env_pdf);
 #undef WANT
         size_t total = geom + bInfo;
@@ -979,6 +983,7 @@ static int32_t scene_upload_single(rtx_ctx* ctx, const rtx_scene_desc* d) {
     S.n_entries = d->n_entries;
     S.n_unbounded = (int)unbounded.size();
     S.n_tlas_flat = (int)(tlasBoxes.size() / 2);
+    for (size_t k = 0; k < tlasBoxes.size() && k < 32; k++) S.tlas_boxes[k] = tlasBoxes[k];
     S.n_lights = d->n_lights;
     S.n_images = d->n_images;
     S.n_flat_simple = (int)flatSimple.size(); S.n_flat_complex = (int)flatComplex.size();
@@ -1258,6 +1263,7 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
     int* const spillC = overlap ? ctx->trace_spill2 : ctx->trace_spill;
     bool pending[2] = {false, false};
     long long iter = 0;
+    const long long debugIter = getenv("RTX_DEBUG_ITER") ? atoll(getenv("RTX_DEBUG_ITER")) : -1;
     // The drain: once the pass's last camera path has been generated the stream only shrinks, and the host knows an upper bound of the
     // rays in flight (the survivor count of the last polled iteration). Grids are then sized for that bound instead of for the pool:
     // a launch of 1036 persistent blocks (or 1184 stream blocks) for a few thousand rays is mostly block scheduling.
@@ -1265,6 +1271,7 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
     for (;;) {
         int used = 0;
         auto shrink = [&](int fullGrid, int perBlock) { return std::max(1, std::min(fullGrid, (int)(((long long)activeBound + perBlock - 1) / perBlock))); };
+        const bool smallBatch = !ctx->scene_flat && !ctx->fuse_tree && ctx->count_stats == 0 && ctx->S.n_images == 0 && activeBound <= ctx->simple_below;
         const int gStreamB = shrink(gridStream, 256), gTraceB = shrink(gridTrace, 32), gLucyB = shrink(ctx->trace_grid_lucy, 32), gSkyB = shrink(ctx->trace_grid_sky, 32);
         for (int b = 0; b < BATCH; b++, iter++) {
             const int cur = (int)(iter & 1);   // rec[cur]: this iteration's paths; rec[cur ^ 1]: where k_shade writes the survivors
@@ -1301,6 +1308,10 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
             } else if (ctx->scene_flat) {
                 if (ctx->count_stats & 1) k_extend_flat<true><<<gStreamB, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, pp);
                 else k_extend_flat<false><<<gStreamB, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, pp);
+            } else if (smallBatch) {   // the drain: one thread per ray (trace_simple)
+                if (lean == 1) k_extend_simple<false, RTX_FV_LUCY><<<gStreamB, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, pp);
+                else if (lean == 2) k_extend_simple<false, RTX_FV_SKY><<<gStreamB, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, pp);
+                else k_extend_simple<false><<<gStreamB, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->S, pp);
             } else if (ctx->count_stats & 1) k_extend<true><<<gTraceB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
             else if (lean == 1) k_extend<false, false, RTX_FV_LUCY><<<gLucyB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_LUCY), st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
             else if (lean == 2) k_extend<false, false, RTX_FV_SKY><<<gSkyB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_SKY), st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
@@ -1334,6 +1345,10 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
                     else if (lean == 3 || lean == 1) k_connect_flat<false, RTX_FV_BOX><<<gStreamB, 256, 0, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp);
                     else if (lean == 4) k_connect_flat<false, RTX_FV_CORNELL><<<gStreamB, 256, 0, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp);
                     else k_connect_flat<false><<<gStreamB, 256, 0, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp);
+                } else if (smallBatch) {
+                    if (lean == 1) k_connect_simple<RTX_FV_LUCY><<<gStreamB, 256, 0, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp);
+                    else if (lean == 2) k_connect_simple<RTX_FV_SKY><<<gStreamB, 256, 0, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp);
+                    else k_connect_simple<><<<gStreamB, 256, 0, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp);
                 } else if (ctx->count_stats & 2) k_connect<true><<<gTraceB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
                 else if (lean == 1) k_connect<false, RTX_FV_LUCY><<<gLucyB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_LUCY), sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
                 else if (lean == 2) k_connect<false, RTX_FV_SKY><<<gSkyB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_SKY), sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
@@ -1344,6 +1359,12 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
             } else if (timing) { cudaEventRecord(ev[6], st); cudaEventRecord(ev[7], st); }
             launches += 4;
             used++;
+            if (debugIter >= 0 && iter == debugIter) {   // developer aid (RTX_DEBUG_ITER=k): the job counts of iteration k, e.g. of the launch an ncu capture picked
+                Ctl snap;
+                cudaStreamSynchronize(st); cudaStreamSynchronize(sc);
+                cudaMemcpy(&snap, ctx->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[rtx] iteration %lld: extension rays %d, shadow rays %d\n", iter, snap.n_active, snap.n_shadow[cur]);
+            }
         }
         // join: the control block read below must include the connect kernels of this batch (statistics, timing events)
         for (int c = 0; c < 2; c++)

@@ -78,7 +78,9 @@ struct DevScene {
     // Worlds of a few bounded entries around a mesh (CornellBoxLucy: 6 quads + 10 instances): the top level is a LIST, not a
     // hierarchy. Every ray tests all entry boxes when it enters the ray pool — all lanes of the refill, no NODE rounds — and
     // starts with its entries on the stack, nearest first, each carrying its entry distance (see RTX_TLAS_CODE in rtx_trace.cuh).
-    const float4* tlas_boxes;   // [2 * n_tlas_flat]: (lo.xyz, entry index as int bits) (hi.xyz, -), float32 rounded outward
+    // The boxes travel INSIDE this struct (a __grid_constant__ kernel parameter, i.e. the constant bank): the refill loop indexes them with
+    // a warp-uniform counter, so they are uniform-datapath operands instead of 32 global loads per ray.
+    float4 tlas_boxes[2 * 16];  // [2 * n_tlas_flat]: (lo.xyz, entry index as int bits) (hi.xyz, -), float32 rounded outward
     int n_tlas_flat;            // 0: the top level is traversed as a hierarchy from tlas_root
     const double* spheres;  // 8 doubles: c0.xyz, vel.xyz, radius, -
     const int* sph_mat;

@@ -298,6 +298,16 @@ __global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS_OF(FEAT)) 
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->ext_rays, (unsigned long long)n);
 }
 
+// small batches (the drain of a pass): one thread per ray, see trace_simple
+template <bool UV = false, unsigned FEAT = RTX_F_ALL>
+__global__ void __launch_bounds__(256) k_extend_simple(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, PassParams pp) {
+    ExtendPolicyT<UV, FEAT> P{ctl, pool.hit, pool.q_mat, pool.capacity, pool.records(cur), &S, pp.seed_lo, pp.seed_hi};
+    TraceCounters tc = {0, 0, 0, 0, 0};
+    const int n = ctl->n_active;
+    trace_simple<ExtendPolicyT<UV, FEAT>, false, FEAT>(S, P, n, tc);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->ext_rays, (unsigned long long)n);
+}
+
 template <bool COUNT, bool UV = false>
 __global__ void __launch_bounds__(256) k_extend_flat(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, PassParams pp) {
     ExtendPolicyT<UV> P{ctl, pool.hit, pool.q_mat, pool.capacity, pool.records(cur), &S, pp.seed_lo, pp.seed_hi};
@@ -894,6 +904,15 @@ __global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS_OF(FEAT)) 
     const int n = ctl->n_shadow[par];
     trace_persistent<ConnectPolicy, COUNT, RTX_TRACE_SLOTS_OF(FEAT), FEAT>(S, P, &ctl->cur_connect[par], n, tc, spill, rtx_smem);
     if (COUNT) flush_counters(ctl, tc);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->shadow_rays, (unsigned long long)n);
+}
+
+template <unsigned FEAT = RTX_F_ALL>
+__global__ void __launch_bounds__(256) k_connect_simple(Ctl* ctl, Pool pool, int par, const __grid_constant__ DevScene S, PassParams pp) {
+    ConnectPolicy P{pool, pp.seed_lo, pp.seed_hi};
+    TraceCounters tc = {0, 0, 0, 0, 0};
+    const int n = ctl->n_shadow[par];
+    trace_simple<ConnectPolicy, false, FEAT>(S, P, n, tc);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->shadow_rays, (unsigned long long)n);
 }
 

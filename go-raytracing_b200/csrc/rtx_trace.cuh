@@ -350,6 +350,93 @@ __device__ __forceinline__ void trace_flat(const DevScene& S, Policy& P, int njo
     }
 }
 
+// The drain of a pass (a few thousand to a few hundred thousand rays per iteration) is latency-bound in the persistent kernel: its rays
+// are spread one per lane over the pool and every round serves a handful of lanes, so a launch cannot finish faster than ~60 rounds
+// whatever the ray count (measured: 230 us for 100 K rays). For such batches the plain shape wins: ONE THREAD PER RAY, the whole query
+// in registers and a local-memory stack, no pool, no votes — a launch then lasts as long as its longest ray (tens of microseconds).
+// Same primitive tests, same tie rules (Best::offer), same two-level traversal: hit records are bit-identical to trace_persistent's
+// (test_small_batch_kernels_are_result_neutral; closest hits do not depend on the order of the tests).
+template <class Policy, bool COUNT, unsigned FEAT = RTX_F_ALL>
+__device__ __forceinline__ void trace_simple(const DevScene& S, Policy& P, int njobs, TraceCounters& tc) {
+    TraceCounters* const tcp = COUNT ? &tc : nullptr;
+    const double tmin = P.tmin();
+    const float ftmin = __double2float_rd(tmin);
+    const float INF = __int_as_float(0x7f800000);
+    const int nrounded = (njobs + 31) & ~31;   // whole warps reach the warp-collective retire
+    for (int job = blockIdx.x * blockDim.x + threadIdx.x; job < nrounded; job += gridDim.x * blockDim.x) {
+        const bool valid = job < njobs;
+        RayD rw;
+        Best B;
+        rw.ox = rw.oy = rw.oz = rw.dx = rw.dy = rw.dz = rw.tm = 0;
+        B.reset(0);
+        if (valid) {
+            double tmax;
+            P.load(job, rw, tmax);
+            B.reset(tmax);
+            for (int q = 0; q < S.n_unbounded; q++) {   // entries tested for every ray (infinite planes; pre-tested bare primitives)
+                const int ei = S.unbounded[q];
+                const DEntry e = S.entries[ei];
+                RayD ro = rw;
+                if (FEAT & (RTX_F_COMPLEX | RTX_F_XFORM)) xform_ray(S, ei, e, ro);
+                B.test_prim(S, e.kind, e.index, ro, tmin, ei, e.rank, 0, 0, tcp);
+                if (Policy::ANY_HIT && B.have) break;
+            }
+            int stk[RTX_STACK_SIZE];
+            int sp = 0, cur = -1;
+            RayD r = rw;     // current-space ray (world, or the object space of instance `cur`)
+            RayF f;
+            make_rayf(r, f);
+            if (S.tlas_root >= 0 && !(Policy::ANY_HIT && B.have)) stk[sp++] = S.tlas_root;
+            while (sp > 0) {
+                const int node = stk[--sp];
+                if (node >= 0) {
+                    float d[4]; int ch[4];
+                    if (COUNT) tc.nodes++;
+                    node_test(S.nodes, node, f, ftmin, B.ft, d, ch);
+#define RTX_CSWAP(i, j) if (d[j] < d[i]) { float td = d[i]; d[i] = d[j]; d[j] = td; int tcx = ch[i]; ch[i] = ch[j]; ch[j] = tcx; }
+                    if (!Policy::ANY_HIT) { RTX_CSWAP(0, 1) RTX_CSWAP(2, 3) RTX_CSWAP(0, 2) RTX_CSWAP(1, 3) RTX_CSWAP(1, 2) }
+#undef RTX_CSWAP
+                    if (d[3] < INF) stk[sp++] = ch[3];
+                    if (d[2] < INF) stk[sp++] = ch[2];
+                    if (d[1] < INF) stk[sp++] = ch[1];
+                    if (d[0] < INF) stk[sp++] = ch[0];
+                } else if ((FEAT & RTX_F_MESH) && node == RTX_ST_SENTINEL) {   // the instance is exhausted: back to the world ray
+                    r = rw; make_rayf(r, f); cur = -1;
+                } else if ((FEAT & RTX_F_MESH) && cur >= 0) {                  // a BLAS leaf
+                    const int code = ~node;
+                    const int first = code >> 3, cnt = (code & 7) + 1;
+                    for (int k = 0; k < cnt; k++) {
+                        const int ti = first + k;
+                        if (COUNT) tc.tris++;
+                        const double t = isect_tri(S.tris + RTX_TRI_D * (size_t)ti, r, nullptr);
+                        if (tmin <= t && t <= B.t) {
+                            const int4 info = __ldg(S.tri_info + ti);
+                            B.offer(t, cur, S.entries[cur].rank, RTX_GEOM_TRIANGLE, ti, info.x, info.z);
+                        }
+                    }
+                    if (Policy::ANY_HIT && B.have) break;
+                } else {                                                          // a world entry
+                    const int ei = ~node;
+                    const DEntry e = S.entries[ei];
+                    if ((FEAT & RTX_F_MESH) && e.volume < 0 && e.kind == RTX_GEOM_MESH) {
+                        RayD r2 = rw;
+                        if (FEAT & (RTX_F_XFORM | RTX_F_COMPLEX)) xform_ray(S, ei, e, r2);
+                        r = r2; make_rayf(r, f); cur = ei;
+                        stk[sp++] = RTX_ST_SENTINEL;
+                        stk[sp++] = e.a;
+                    } else {
+                        VolumeRng vr = {0, 0, 0, 0, 0, true};
+                        if ((FEAT & RTX_F_COMPLEX) && e.volume >= 0) vr = P.volume_rng(job);
+                        if ((FEAT & RTX_F_COMPLEX) || e.kind != RTX_GEOM_LIST) entry_core(S, ei, e, rw, B, tmin, vr, tcp);
+                        if (Policy::ANY_HIT && B.have) break;
+                    }
+                }
+            }
+        }
+        P.retire(valid ? job : -1, valid, rw, B);
+    }
+}
+
 template <class Policy, bool COUNT, int NSLOTS, unsigned FEAT = RTX_F_ALL>
 __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, int* cursor, int njobs, TraceCounters& tc, int* spill, unsigned char* smem) {
     typedef TracePool<NSLOTS, RTX_FEAT_HAS_TIME(FEAT)> Pool_;
@@ -701,7 +788,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                         const bool sx = f.offx != 0, sy = f.offy != 0, sz = f.offz != 0;
                         const float ftm = B.ft;
                         for (int q = 0; q < S.n_tlas_flat; q++) {
-                            const float4 lo = __ldg(S.tlas_boxes + 2 * q), hi = __ldg(S.tlas_boxes + 2 * q + 1);
+                            const float4 lo = S.tlas_boxes[2 * q], hi = S.tlas_boxes[2 * q + 1];
                             float tn = fmaxf(fmaxf(fmaf(sx ? hi.x : lo.x, f.ix, f.cnx), fmaf(sy ? hi.y : lo.y, f.iy, f.cny)), fmaxf(fmaf(sz ? hi.z : lo.z, f.iz, f.cnz), ftmin));
                             float tf = fminf(fminf(fmaf(sx ? lo.x : hi.x, f.ix, f.cfx), fmaf(sy ? lo.y : hi.y, f.iy, f.cfy)), fminf(fmaf(sz ? lo.z : hi.z, f.iz, f.cfz), ftm));
                             tn = fmaf(-fabsf(tn), RTX_BOX_EPS, tn);

@@ -864,3 +864,27 @@ def test_multi_device_context_equals_one_device(grt, name, width, spp, depth):
     h1, h2 = one.trace_closest(rays), many.trace_closest(rays)
     assert np.array_equal(h1["entry"], h2["entry"]) and np.array_equal(h1["prim"], h2["prim"]) and np.array_equal(h1["t"], h2["t"])
     one.close(); many.close()
+
+
+@pytest.mark.parametrize("name,width,spp,depth", [("cornell-lucy", 200, 8, 12), ("random", 160, 16, 20), ("cornell-smoke", 120, 16, 5), ("primitives", 160, 8, 12)])
+def test_small_batch_and_flat_top_level_are_result_neutral(grt, name, width, spp, depth):
+    """Two ways the hierarchy worlds are traced besides the persistent kernel with a hierarchical top level: the drain of a pass runs a
+    one-thread-per-ray kernel (option simple_below: here forced for EVERY iteration), and mesh worlds of <= 16 bounded entries take their
+    top level as a per-ray sorted list (option tlas_flat_max: here switched off). Same primitive tests and tie rules, same Philox counters:
+    the same rays are traced, and the sums agree to float-atomic order."""
+    sc = grt.config_scene(name, width=width, spp=spp, depth=depth)
+    out = {}
+    for key, opts in (("default", {}), ("simple", {"simple_below": 1 << 30, "flat_max_entries": 0}), ("hierarchy", {"tlas_flat_max": 0, "flat_max_entries": 0, "simple_below": 0})):
+        c = grt.Context(0)
+        for k, v in opts.items():
+            c.set_option(k, v)
+        c.load(sc)
+        c.render_pass(spp, depth, seed=12)
+        acc, _, n = c.resolve_accum()
+        st = c.stats()
+        c.close()
+        assert np.all(n == spp)
+        out[key] = (acc, st["extension_rays"], st["shadow_rays"])
+    for key in ("simple", "hierarchy"):
+        assert out[key][1] == out["default"][1] and out[key][2] == out["default"][2], f"{name}: {key} traces a different number of rays"
+        assert np.allclose(out[key][0], out["default"][0], rtol=5e-5, atol=2e-5), f"{name}: {key} changes the image"
