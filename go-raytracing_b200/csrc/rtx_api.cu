@@ -18,6 +18,7 @@
 #include "rtx_bvh.hpp"
 #include "rtx_kernels.cuh"
 #include "rtx_bvh_gpu.cuh"
+#include "rtx_rank_gpu.cuh"
 
 #ifndef RTX_PRETEST_BARE_DEFAULT
 #define RTX_PRETEST_BARE_DEFAULT 0
@@ -96,7 +97,7 @@ struct rtx_ctx {
     int simple_below = RTX_SIMPLE_BELOW_DEFAULT;   // hierarchy worlds: iterations of the drain with at most this many rays run the one-thread-per-ray trace kernels (0 = never)
     int tlas_flat_max = RTX_TLAS_FLAT_MAX;   // mesh worlds with at most this many bounded entries: top level as a per-ray sorted list (0 = hierarchy)
     int bvh_device = 1;   // mesh BLAS construction on the device (rtx_bvh_gpu.cuh); 0 = host builder (rtx_bvh.hpp), kept for A/B
-    double ms_upload_blas = 0, ms_upload_total = 0;
+    double ms_upload_blas = 0, ms_upload_total = 0, ms_upload_ranks = 0;
     int blas_depth = 0, built_on_device = 0;
     rtx_stats stats{};
     double env_total = 0;
@@ -670,8 +671,12 @@ static int32_t scene_upload_single(rtx_ctx* ctx, const rtx_scene_desc* d) {
             buildBytes = std::max(buildBytes, sb);
             nodeBytes += pad(((size_t)d->group_count[g] + 1) * sizeof(Node4));
         }
+        size_t rankBytes = 0;
+        if (!d->tri_rank)
+            for (int g = 0; g < d->n_groups; g++)
+                if (d->group_kind[g] == RTX_GEOM_MESH) rankBytes = std::max(rankBytes, rtxrank::scratch_bytes(d->group_count[g]));
         const size_t workTotal = 3 * pad(3 * nT * sizeof(double)) + 2 * pad(nT * sizeof(int)) + pad((size_t)RTX_TRI_D * meshTotal * sizeof(double)) +
-                                 pad((size_t)meshTotal * sizeof(int4)) + nodeBytes + pad(buildBytes) + 4096;
+                                 pad((size_t)meshTotal * sizeof(int4)) + nodeBytes + pad(buildBytes) + pad(rankBytes) + 4096;
         CU(ctx->work_slab.reserve(workTotal));
         Slab& W = ctx->work_slab;
         double *dV0 = (double*)W.take(3 * nT * sizeof(double)), *dV1 = (double*)W.take(3 * nT * sizeof(double)), *dV2 = (double*)W.take(3 * nT * sizeof(double));
@@ -679,24 +684,28 @@ static int32_t scene_upload_single(rtx_ctx* ctx, const rtx_scene_desc* d) {
         dMeshTris = (double*)W.take((size_t)RTX_TRI_D * meshTotal * sizeof(double));
         dTriInfo = (int4*)W.take((size_t)meshTotal * sizeof(int4));
         char* buildScratch = W.take(buildBytes);
-        std::vector<int> rankAll;
-        if (!d->tri_rank) {   // no ranks from the caller's Go tree: canonical ones (host restatement of rt/bvh.go's order; exact-tie resolution only)
-            rankAll.assign(d->n_tris, 0);
-            for (int g = 0; g < d->n_groups; g++) {
-                if (d->group_kind[g] != RTX_GEOM_MESH) continue;
-                const int begin = d->group_begin[g], count = d->group_count[g];
-                std::vector<Box> boxes(count);
-                for (int k = 0; k < count; k++) boxes[k] = prim_box(d, RTX_GEOM_TRIANGLE, begin + k);
-                std::vector<int> r = rtxbvh::canonical_ranks(boxes);
-                for (int k = 0; k < count; k++) rankAll[begin + k] = r[k];
-            }
-        }
+        char* rankScratch = rankBytes ? W.take(rankBytes) : nullptr;
+        ctx->ms_upload_ranks = 0;
         CU(cudaMemcpyAsync(dV0, d->tri_v0, 3 * nT * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(dV1, d->tri_v1, 3 * nT * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(dV2, d->tri_v2, 3 * nT * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(dMat, d->tri_mat, nT * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(dRank, d->tri_rank ? d->tri_rank : rankAll.data(), nT * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));   // rankAll is a local
+        if (d->tri_rank) {
+            CU(cudaMemcpyAsync(dRank, d->tri_rank, nT * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            // no ranks from the caller's Go tree: the canonical test order (the stable-sort restatement of rt/bvh.go:69-217; exact-tie
+            // resolution only) is computed on the device — a few milliseconds instead of a 100 ms pointer-tree build on the host
+            const auto tR0 = std::chrono::steady_clock::now();
+            CU(cudaMemsetAsync(dRank, 0, nT * sizeof(int), ctx->stream));
+            for (int g = 0; g < d->n_groups; g++) {
+                if (d->group_kind[g] != RTX_GEOM_MESH || d->group_count[g] == 0) continue;
+                const int begin = d->group_begin[g], count = d->group_count[g];
+                cudaError_t re = rtxrank::canonical_ranks(dV0 + 3 * (size_t)begin, dV1 + 3 * (size_t)begin, dV2 + 3 * (size_t)begin, count, dRank + begin, rankScratch, rankBytes, ctx->stream);
+                if (re != cudaSuccess) return fail(ctx, RTX_ERR_CUDA, "device test-order ranks of mesh group %d failed: %s", g, cudaGetErrorString(re));
+            }
+            ctx->ms_upload_ranks = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tR0).count();
+        }
+        CU(cudaStreamSynchronize(ctx->stream));
         while (ctx->events.size() < 4) {
             cudaEvent_t ev;
             CU(cudaEventCreate(&ev));

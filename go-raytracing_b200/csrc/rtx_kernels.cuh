@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256, 4) k_generate(Ctl* ctl, Pool pool, int cu
     char* rec = pool.records(cur) + (size_t)(n_cont + i) * RTX_REC_BYTES;   // appended behind the survivors
     st256d(rec, r.ox, r.oy, r.oz, r.tm);
     st256d(rec + 32, r.dx, r.dy, r.dz, __longlong_as_double((long long)ps));
-    *reinterpret_cast<float4*>(rec + 64) = make_float4(1.f, 1.f, 1.f, __int_as_float(RTX_FRESH_PATH_FLAGS));
+    strec4(rec + 64, make_float4(1.f, 1.f, 1.f, __int_as_float(RTX_FRESH_PATH_FLAGS)));
   }
 }
 
@@ -254,7 +254,7 @@ struct ExtendPolicyT {
     __device__ __forceinline__ VolumeRng volume_rng(int job) const {
         const char* q = rec + (size_t)job * RTX_REC_BYTES;
         const unsigned long long ps = (unsigned long long)__double_as_longlong(ld256d(q + 32).w);
-        const int bounce = __float_as_int(reinterpret_cast<const float4*>(q + 64)->w) & 0xffff;
+        const int bounce = __float_as_int(ldrec4(q + 64).w) & 0xffff;
         VolumeRng vr; vr.k0 = seed_lo; vr.k1 = seed_hi; vr.c0 = (uint32_t)ps; vr.c1 = (uint32_t)(ps >> 32); vr.c2 = (uint32_t)bounce * 4u; vr.transparent = false;
         return vr;
     }
@@ -280,7 +280,7 @@ struct ExtendPolicyT {
 #pragma unroll
         for (int k = 0; k < Q_COUNT; k++) {
             const int pos = warp_append(&ctl->n_mat[k], q == k);
-            if (q == k) q_mat[(size_t)k * capacity + pos] = job;
+            if (q == k) stq(q_mat + (size_t)k * capacity + pos, job);
         }
     }
 };
@@ -622,7 +622,7 @@ __device__ __forceinline__ void shade_commit(Ctl* ctl, const Pool& pool, const i
         char* out = pool.records(cur ^ 1) + (size_t)pos * RTX_REC_BYTES;
         st256d(out, P.x, P.y, P.z, tm);
         st256d(out + 32, nd.x, nd.y, nd.z, pixbits);
-        *reinterpret_cast<float4*>(out + 64) = th;
+        strec4(out + 64, th);
     }
     {   // shadow requests carry everything k_connect needs (origin = the hit point, where the contribution goes)
         int sp = warp_append(&ctl->n_shadow[cur], has_env);
@@ -630,14 +630,14 @@ __device__ __forceinline__ void shade_commit(Ctl* ctl, const Pool& pool, const i
             char* q = pool.shadow + (size_t)sp * RTX_SHADOW_BYTES;
             st256d(q, P.x, P.y, P.z, RTX_INF_D);
             st256d(q + 32, env_dir.x, env_dir.y, env_dir.z, pixbits);
-            *reinterpret_cast<float4*>(q + 64) = make_float4(env_c.x, env_c.y, env_c.z, __int_as_float(bounce0));
+            strec4(q + 64, make_float4(env_c.x, env_c.y, env_c.z, __int_as_float(bounce0)));
         }
         sp = warp_append(&ctl->n_shadow[cur], has_area);
         if (has_area) {
             char* q = pool.shadow + (size_t)sp * RTX_SHADOW_BYTES;
             st256d(q, P.x, P.y, P.z, area_tmax);
             st256d(q + 32, area_dir.x, area_dir.y, area_dir.z, pixbits);
-            *reinterpret_cast<float4*>(q + 64) = make_float4(area_c.x, area_c.y, area_c.z, __int_as_float(bounce0));
+            strec4(q + 64, make_float4(area_c.x, area_c.y, area_c.z, __int_as_float(bounce0)));
         }
     }
 }
@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(256, FEAT != RTX_F_ALL ? RTX_SHADE_BLOCKS_LEAN
   auto locate = [&](int i, int& type) {
       if (QT >= 0) {
           type = i < n_items ? QT : -1;
-          return type >= 0 ? pool.q_mat[(size_t)QT * pool.capacity + i] : -1;
+          return type >= 0 ? ldq(pool.q_mat + (size_t)QT * pool.capacity + i) : -1;
       }
       type = -1;
       int idx = i;
@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(256, FEAT != RTX_F_ALL ? RTX_SHADE_BLOCKS_LEAN
               if (idx < nq[k]) type = k;
               else idx -= nq[k];
           }
-      return type >= 0 ? pool.q_mat[(size_t)type * pool.capacity + idx] : -1;
+      return type >= 0 ? ldq(pool.q_mat + (size_t)type * pool.capacity + idx) : -1;
   };
   const int stride = gridDim.x * blockDim.x;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -700,7 +700,7 @@ __global__ void __launch_bounds__(256, FEAT != RTX_F_ALL ? RTX_SHADE_BLOCKS_LEAN
         const char* rec = pool.records(cur) + (size_t)job * RTX_REC_BYTES;
         const D4 ro4 = ld256d(rec), rd4 = ld256d(rec + 32);
         V.tm = ro4.w; V.pixbits = rd4.w;
-        V.th = *reinterpret_cast<const float4*>(rec + 64);
+        V.th = ldrec4(rec + 64);
         D3 P = d3(0, 0, 0), N = d3(0, 0, 0);
         double hu = 0.0, hv = 0.0;   // rec.U, rec.V: carried only in scenes with image textures (96-byte hit records)
         int mat = 0;
@@ -750,7 +750,7 @@ struct BouncePolicyT {
             const D4 a = ld256d(q), c = ld256d(q + 32);
             r.ox = a.x; r.oy = a.y; r.oz = a.z; r.tm = a.w; r.dx = c.x; r.dy = c.y; r.dz = c.z;
             pixbits_ = c.w;
-            th_ = *reinterpret_cast<const float4*>(q + 64);
+            th_ = ldrec4(q + 64);
         }
         tmax = RTX_INF_D;
     }
@@ -813,7 +813,7 @@ __device__ __noinline__ void bounce_shade(const DevScene* S, const DevCamera* C,
     V.reset();
     V.tm = r.tm;
     V.pixbits = *reinterpret_cast<const double*>(rec + 56);
-    V.th = *reinterpret_cast<const float4*>(rec + 64);
+    V.th = ldrec4(rec + 64);
     int type = Q_MISS;
     HitInfo hi;
     hi.P = hi.N = d3(0, 0, 0); hi.mat = 0; hi.front = false; hi.u = hi.v = 0;
@@ -840,7 +840,7 @@ struct BounceTreePolicyT {
     __device__ __forceinline__ VolumeRng volume_rng(int job) const {
         const char* q = rec + (size_t)job * RTX_REC_BYTES;
         const unsigned long long ps = (unsigned long long)__double_as_longlong(ld256d(q + 32).w);
-        const int bounce = __float_as_int(reinterpret_cast<const float4*>(q + 64)->w) & 0xffff;
+        const int bounce = __float_as_int(ldrec4(q + 64).w) & 0xffff;
         VolumeRng vr; vr.k0 = pp->seed_lo; vr.k1 = pp->seed_hi; vr.c0 = (uint32_t)ps; vr.c1 = (uint32_t)(ps >> 32); vr.c2 = (uint32_t)bounce * 4u; vr.transparent = false;
         return vr;
     }
@@ -881,7 +881,7 @@ struct ConnectPolicy {
     __device__ __forceinline__ VolumeRng volume_rng(int job) const {
         const char* q = pool.shadow + (size_t)job * RTX_SHADOW_BYTES;
         const unsigned long long ps = (unsigned long long)__double_as_longlong(ld256d(q + 32).w);
-        const int bounce = __float_as_int(reinterpret_cast<const float4*>(q + 64)->w);   // the bounce whose hit issued the request
+        const int bounce = __float_as_int(ldrec4(q + 64).w);   // the bounce whose hit issued the request
         const double tmax = ld256d(q).w;
         VolumeRng vr; vr.k0 = seed_lo; vr.k1 = seed_hi; vr.c0 = (uint32_t)ps; vr.c1 = (uint32_t)(ps >> 32);
         vr.c2 = (uint32_t)bounce * 4u + (tmax == RTX_INF_D ? 2u : 1u); vr.transparent = false;
@@ -891,7 +891,7 @@ struct ConnectPolicy {
         if (valid && b.entry < 0) {   // unoccluded: the contribution shade prepared arrives
             const char* q = pool.shadow + (size_t)job * RTX_SHADOW_BYTES;
             const unsigned long long ps = (unsigned long long)__double_as_longlong(ld256d(q + 32).w);
-            const float4 cc = *reinterpret_cast<const float4*>(q + 64);
+            const float4 cc = ldrec4(q + 64);
             pool.contribute((uint32_t)ps, (uint32_t)(ps >> 32), cc.x, cc.y, cc.z);
         }
     }

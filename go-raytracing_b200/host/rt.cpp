@@ -1,5 +1,7 @@
 // rt.cpp — host-side mirror of the Go `rt` package: constructors, reference-order BVH, loaders, camera.
 // See rt.hpp. Reference citations are relative to /root/reference/.
+#include <thread>
+
 #include "rt.hpp"
 
 #include <algorithm>
@@ -363,6 +365,75 @@ BVHNodePtr NewBVHNode(const std::vector<HittablePtr>& objects, size_t start, siz
     return root;
 }
 BVHNodePtr NewBVHNodeFromList(const HittableListPtr& list) { return NewBVHNode(list->Objects, 0, list->Objects.size()); }
+
+static bool g_eager_mesh_bvh = std::getenv("RT_EAGER_BVH") && std::atoi(std::getenv("RT_EAGER_BVH")) != 0;
+void SetEagerMeshBVH(bool eager) { g_eager_mesh_bvh = eager; }
+bool EagerMeshBVH() { return g_eager_mesh_bvh; }
+// The root of a mesh without its tree: the bounding box is what the world BVH / the flattener need from it.
+BVHNodePtr NewBVHNodeDeferred(std::vector<HittablePtr>&& objects) {
+    auto root = std::make_shared<BVHNode>();
+    if (objects.empty()) return root;
+    const size_t n = objects.size();
+    const size_t T = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), std::max<size_t>(1, n / 32768));
+    std::vector<AABB> part(T);
+    std::vector<std::thread> th;
+    auto work = [&](size_t t) {
+        const size_t lo = n * t / T, hi = n * (t + 1) / T;
+        AABB b = objects[lo]->BoundingBox();
+        for (size_t i = lo + 1; i < hi; i++) b = NewAABBFromBoxes(b, objects[i]->BoundingBox());
+        part[t] = b;
+    };
+    for (size_t t = 1; t < T; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    AABB b = part[0];
+    for (size_t t = 1; t < T; t++) b = NewAABBFromBoxes(b, part[t]);   // min / max: the union does not depend on the grouping
+    root->bbox = b;
+    root->src = std::move(objects);
+    root->deferred = true;
+    return root;
+}
+BVHNodePtr NewMeshRootFromSoup(std::shared_ptr<BVHNode::Soup> soup, int threads) {
+    auto root = std::make_shared<BVHNode>();
+    const size_t n = soup->n;
+    if (n == 0) return root;
+    const size_t T = std::min<size_t>(threads > 0 ? (size_t)threads : std::max(1u, std::thread::hardware_concurrency()), std::max<size_t>(1, n / 32768));
+    std::vector<AABB> part(T);
+    std::vector<std::thread> th;
+    auto work = [&](size_t t) {
+        AABB b;
+        bool first = true;
+        for (size_t k = n * t / T, e = n * (t + 1) / T; k < e; k++) {   // the box NewTriangle gives every face (rt/triangle.go:27-37), unioned
+            const double *a = &soup->v0[3 * k], *bb = &soup->v1[3 * k], *c = &soup->v2[3 * k];
+            AABB tb = NewAABBFromPoints({std::fmin(a[0], std::fmin(bb[0], c[0])), std::fmin(a[1], std::fmin(bb[1], c[1])), std::fmin(a[2], std::fmin(bb[2], c[2]))},
+                                        {std::fmax(a[0], std::fmax(bb[0], c[0])), std::fmax(a[1], std::fmax(bb[1], c[1])), std::fmax(a[2], std::fmax(bb[2], c[2]))});
+            b = first ? tb : NewAABBFromBoxes(b, tb);
+            first = false;
+        }
+        part[t] = b;
+    };
+    for (size_t t = 1; t < T; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    AABB b = part[0];
+    for (size_t t = 1; t < T; t++) b = NewAABBFromBoxes(b, part[t]);
+    root->bbox = b;
+    root->soup = std::move(soup);
+    root->deferred = true;
+    return root;
+}
+void BVHNode::EnsureBuilt() {
+    if (!deferred) return;
+    if (soup && src.empty()) {
+        src.resize(soup->n);
+        for (size_t k = 0; k < soup->n; k++)
+            src[k] = NewTriangle({soup->v0[3 * k], soup->v0[3 * k + 1], soup->v0[3 * k + 2]}, {soup->v1[3 * k], soup->v1[3 * k + 1], soup->v1[3 * k + 2]},
+                                 {soup->v2[3 * k], soup->v2[3 * k + 1], soup->v2[3 * k + 2]}, soup->mat);
+    }
+    BVHNodePtr built = NewBVHNode(src, 0, src.size());
+    left = built->left; right = built->right; bbox = built->bbox;
+    deferred = false;
+}
 
 // rt/obj_loader.go: rt_obj.cpp (parallel text parse)
 

@@ -205,9 +205,21 @@ struct BVHNode : Hittable {  // rt/bvh.go:13
     // Unexported addition of the drop-in: the source slice in insertion order (root only), so that the
     // flattener can report stable identifiers; the tree itself only fixes the test order.
     std::vector<HittablePtr> src;
+    // A mesh root returned by LoadOBJ may be DEFERRED: its box and source slice are set, the pointer tree is not built. These types never
+    // traverse (no Hit here): the tree's only product on this side is the test order of its leaves, which the CUDA library derives on the
+    // device when the flattener leaves tri_rank NULL (csrc/rtx_rank_gpu.cuh: 3 ms against a 100 ms tree build for 280 K triangles).
+    // EnsureBuilt() builds the reference-order tree on demand (SetEagerMeshBVH(true) / RT_EAGER_BVH=1 make LoadOBJ build it at once).
+    bool deferred = false;
+    // ... and then LoadOBJ does not even create the 280 K Triangle objects: it keeps the faces as flat arrays (what the flattener wants
+    // anyway); EnsureBuilt() materialises src from them before it builds the tree.
+    struct Soup { std::vector<double> v0, v1, v2; std::shared_ptr<Material> mat; size_t n = 0; };
+    std::shared_ptr<Soup> soup;
+    void EnsureBuilt();
     AABB BoundingBox() const override { return bbox; }
 };
 using BVHNodePtr = std::shared_ptr<BVHNode>;
+void SetEagerMeshBVH(bool eager);
+bool EagerMeshBVH();
 
 struct Translate : Hittable {  // rt/transform.go:78
     HittablePtr Obj;
@@ -251,6 +263,8 @@ std::shared_ptr<Volume> NewVolume(HittablePtr boundary, double density, TextureP
 std::shared_ptr<Volume> NewVolumeFromColor(HittablePtr boundary, double density, Color albedo);
 BVHNodePtr NewBVHNodeFromList(const HittableListPtr& list);                                  // rt/bvh.go:64
 BVHNodePtr NewBVHNode(const std::vector<HittablePtr>& objects, size_t start, size_t end);     // rt/bvh.go:69
+BVHNodePtr NewBVHNodeDeferred(std::vector<HittablePtr>&& objects);   // a mesh root without its tree (see BVHNode::deferred)
+BVHNodePtr NewMeshRootFromSoup(std::shared_ptr<BVHNode::Soup> soup, int threads);   // the same from flat face arrays (LoadOBJ)
 
 struct Transform {  // rt/transform.go:9-71
     Vec3 scale{1, 1, 1}, rotation{0, 0, 0}, position{0, 0, 0};
@@ -370,6 +384,7 @@ struct FlatScene {
     std::vector<int32_t> quad_mat;
     std::vector<double> tri_v0, tri_v1, tri_v2;
     std::vector<int32_t> tri_mat, tri_rank;
+    bool have_tri_rank = true;   // false: some mesh tree was deferred, the library derives the canonical ranks on the device
     std::vector<double> plane_point, plane_normal;
     std::vector<int32_t> plane_mat;
     std::vector<double> circle_center, circle_normal, circle_radius;

@@ -47,6 +47,7 @@ rth_scene* rth_scene_named(const char* name, const char* asset_root, uint64_t se
     }
 }
 void rth_scene_free(rth_scene* s) { delete s; }
+void rth_set_eager_mesh_bvh(int32_t eager) { SetEagerMeshBVH(eager != 0); }   // LoadOBJ builds the reference-order mesh tree at once (default: deferred)
 const rtx_scene_desc* rth_scene_desc(rth_scene* s) { return &s->desc; }
 const rtx_camera_desc* rth_camera_desc(rth_scene* s) { return &s->cam; }
 int32_t rth_image_height(rth_scene* s) { return s->scene.camera->ImageHeight; }

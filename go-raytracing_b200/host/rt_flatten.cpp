@@ -132,6 +132,7 @@ struct Flattener {
     static void dfs(const Hittable* h, std::vector<const Hittable*>& out) {
         if (!h) return;
         if (auto n = dynamic_cast<const BVHNode*>(h)) {
+            if (n->deferred) { out.push_back(h); return; }   // a mesh root whose tree was never built: one object of the enclosing tree
             if (n->left && n->left == n->right) { dfs(n->left.get(), out); return; }
             dfs(n->left.get(), out);
             dfs(n->right.get(), out);
@@ -157,21 +158,39 @@ struct Flattener {
     int meshGroup(const BVHNode* root) {
         auto it = groupIds.find(root);
         if (it != groupIds.end()) return it->second;
+        if (root->soup && root->deferred) {   // LoadOBJ's flat face arrays: copied as they are; the library derives the test order on the device
+            const BVHNode::Soup& sp = *root->soup;
+            int begin = (int)fs.tri_mat.size();
+            fs.tri_v0.insert(fs.tri_v0.end(), sp.v0.begin(), sp.v0.end());
+            fs.tri_v1.insert(fs.tri_v1.end(), sp.v1.begin(), sp.v1.end());
+            fs.tri_v2.insert(fs.tri_v2.end(), sp.v2.begin(), sp.v2.end());
+            fs.tri_mat.insert(fs.tri_mat.end(), sp.n, material(sp.mat));
+            fs.tri_rank.insert(fs.tri_rank.end(), sp.n, 0);
+            fs.have_tri_rank = false;
+            int id = (int)fs.group_kind.size();
+            fs.group_kind.push_back(RTX_GEOM_MESH); fs.group_begin.push_back(begin); fs.group_count.push_back((int)sp.n);
+            groupIds[root] = id;
+            return id;
+        }
         if (root->src.empty()) throw std::runtime_error("flatten: mesh BVH without its source slice (build it with NewBVHNode / LoadOBJ)");
         int begin = (int)fs.tri_mat.size();
         std::unordered_map<const Hittable*, int> local;
-        local.reserve(root->src.size() * 2);
+        if (!root->deferred) local.reserve(root->src.size() * 2);
+        fs.tri_v0.reserve(fs.tri_v0.size() + 3 * root->src.size()); fs.tri_v1.reserve(fs.tri_v1.size() + 3 * root->src.size()); fs.tri_v2.reserve(fs.tri_v2.size() + 3 * root->src.size());
         for (auto& o : root->src) {  // face order; mesh triangles are never shared with other geometry
             auto t = dynamic_cast<const Triangle*>(o.get());
             if (!t) throw std::runtime_error("flatten: a nested BVH must be a triangle mesh (rt/obj_loader.go:109)");
-            local[o.get()] = (int)fs.tri_mat.size() - begin;
+            if (!root->deferred) local[o.get()] = (int)fs.tri_mat.size() - begin;
             push3(fs.tri_v0, t->v0); push3(fs.tri_v1, t->v1); push3(fs.tri_v2, t->v2);
             fs.tri_mat.push_back(material(t->mat)); fs.tri_rank.push_back(0);
         }
-        std::vector<const Hittable*> order;
-        order.reserve(root->src.size());
-        dfs(root, order);
-        for (size_t r = 0; r < order.size(); r++) fs.tri_rank[begin + local.at(order[r])] = (int)r;
+        if (root->deferred) fs.have_tri_rank = false;   // no tree on this side: the library derives the canonical test order on the device
+        else {
+            std::vector<const Hittable*> order;
+            order.reserve(root->src.size());
+            dfs(root, order);
+            for (size_t r = 0; r < order.size(); r++) fs.tri_rank[begin + local.at(order[r])] = (int)r;
+        }
         int id = (int)fs.group_kind.size();
         fs.group_kind.push_back(RTX_GEOM_MESH); fs.group_begin.push_back(begin); fs.group_count.push_back((int)root->src.size());
         groupIds[root] = id;
@@ -252,7 +271,7 @@ rtx_scene_desc FlatScene::Desc() const {
     d.sph_radius = sph_radius.data(); d.sph_mat = sph_mat.data();
     d.n_quads = (int)quad_mat.size(); d.quad_q = quad_q.data(); d.quad_u = quad_u.data(); d.quad_v = quad_v.data(); d.quad_mat = quad_mat.data();
     d.n_tris = (int)tri_mat.size(); d.tri_v0 = tri_v0.data(); d.tri_v1 = tri_v1.data(); d.tri_v2 = tri_v2.data();
-    d.tri_mat = tri_mat.data(); d.tri_rank = tri_rank.data();
+    d.tri_mat = tri_mat.data(); d.tri_rank = have_tri_rank ? tri_rank.data() : nullptr;
     d.n_planes = (int)plane_mat.size(); d.plane_point = plane_point.data(); d.plane_normal = plane_normal.data(); d.plane_mat = plane_mat.data();
     d.n_circles = (int)circle_mat.size(); d.circle_center = circle_center.data(); d.circle_normal = circle_normal.data();
     d.circle_radius = circle_radius.data(); d.circle_mat = circle_mat.data();

@@ -245,24 +245,49 @@ HittablePtr LoadOBJ(const std::string& filename, MaterialPtr material) {
     const int threads = env ? std::atoi(env) : 0;
     ParseOBJ(filename, threads, vertices, idx);
     const size_t nt = idx.size() / 3;
-    std::vector<HittablePtr> triangles(nt);
-    {   // NewTriangle per face (rt/obj_loader.go:92-96), in file order; the objects are independent
-        const int T = (int)std::min<size_t>(threads > 0 ? (size_t)threads : std::max(1u, std::thread::hardware_concurrency()), std::max<size_t>(1, nt / 16384));
+    const int T = (int)std::min<size_t>(threads > 0 ? (size_t)threads : std::max(1u, std::thread::hardware_concurrency()), std::max<size_t>(1, nt / 16384));
+    HittablePtr root;
+    std::chrono::steady_clock::time_point t1;
+    if (EagerMeshBVH()) {
+        std::vector<HittablePtr> triangles(nt);
+        {   // NewTriangle per face (rt/obj_loader.go:92-96), in file order; the objects are independent
+            std::vector<std::thread> th;
+            auto work = [&](int t) {
+                for (size_t k = nt * (size_t)t / (size_t)T, e = nt * (size_t)(t + 1) / (size_t)T; k < e; k++)
+                    triangles[k] = NewTriangle(vertices[idx[3 * k]], vertices[idx[3 * k + 1]], vertices[idx[3 * k + 2]], material);
+            };
+            for (int t = 1; t < T; t++) th.emplace_back(work, t);
+            work(0);
+            for (auto& x : th) x.join();
+        }
+        t1 = std::chrono::steady_clock::now();
+        root = NewBVHNode(triangles, 0, triangles.size());   // rt/obj_loader.go:109
+    } else {
+        // rt/obj_loader.go:92-109 creates a Triangle per face and builds the mesh BVH here. The device path needs neither the objects nor the
+        // tree — only the faces (as flat arrays: what the flattener emits anyway) and the tree's leaf ORDER, which the library derives on the
+        // GPU. Both are deferred (BVHNode::EnsureBuilt, RT_EAGER_BVH=1): 130 of the 160 ms a cold load of the 280 K-triangle mesh took.
+        auto soup = std::make_shared<BVHNode::Soup>();
+        soup->n = nt; soup->mat = material;
+        soup->v0.resize(3 * nt); soup->v1.resize(3 * nt); soup->v2.resize(3 * nt);
         std::vector<std::thread> th;
         auto work = [&](int t) {
-            for (size_t k = nt * (size_t)t / (size_t)T, e = nt * (size_t)(t + 1) / (size_t)T; k < e; k++)
-                triangles[k] = NewTriangle(vertices[idx[3 * k]], vertices[idx[3 * k + 1]], vertices[idx[3 * k + 2]], material);
+            for (size_t k = nt * (size_t)t / (size_t)T, e = nt * (size_t)(t + 1) / (size_t)T; k < e; k++) {
+                const Point3 &a = vertices[idx[3 * k]], &b = vertices[idx[3 * k + 1]], &c = vertices[idx[3 * k + 2]];
+                soup->v0[3 * k] = a.X; soup->v0[3 * k + 1] = a.Y; soup->v0[3 * k + 2] = a.Z;
+                soup->v1[3 * k] = b.X; soup->v1[3 * k + 1] = b.Y; soup->v1[3 * k + 2] = b.Z;
+                soup->v2[3 * k] = c.X; soup->v2[3 * k + 1] = c.Y; soup->v2[3 * k + 2] = c.Z;
+            }
         };
         for (int t = 1; t < T; t++) th.emplace_back(work, t);
         work(0);
         for (auto& x : th) x.join();
+        t1 = std::chrono::steady_clock::now();
+        root = NewMeshRootFromSoup(soup, threads);
     }
-    const auto t1 = std::chrono::steady_clock::now();
-    HittablePtr root = NewBVHNode(triangles, 0, triangles.size());
     if (std::getenv("RT_DEBUG_TIMING"))
         std::fprintf(stderr, "[rt] LoadOBJ %s: parse %.3f s, NewBVHNode %.3f s (%zu vertices, %zu triangles)\n", filename.c_str(),
                      std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count(),
-                     vertices.size(), triangles.size());
+                     vertices.size(), nt);
     return root;
 }
 HittablePtr LoadOBJWithTransform(const std::string& filename, MaterialPtr material, const Transform* transform) {

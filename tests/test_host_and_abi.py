@@ -122,9 +122,19 @@ def test_lucy_instances(grt):
     xb = d.entry_xf_begin[inst[0]]
     assert [d.xf_type[xb + k] for k in range(3)] == [grt.XF_TRANSLATE, grt.XF_ROTATE_Y, grt.XF_SCALE]
     assert d.xf_a[3 * (xb + 2)] == 0.15 and d.xf_b[3 * (xb + 2)] == 1.0 / 0.15
-    # tri_rank is a permutation (DFS leaf order of the reference-order mesh BVH)
-    ranks = np.ctypeslib.as_array(d.tri_rank, (d.n_tris,))
-    assert np.array_equal(np.sort(ranks), np.arange(d.n_tris))
+    # LoadOBJ defers the reference-order mesh tree (the library derives the test order on the device): tri_rank is NULL ...
+    assert not d.tri_rank
+    # ... unless the tree is asked for (RT_EAGER_BVH=1 / SetEagerMeshBVH): then tri_rank is a permutation, the DFS leaf order of the tree
+    H = grt.host()
+    H.rth_set_eager_mesh_bvh(1)
+    try:
+        s2 = grt.config_scene("cornell-lucy", width=120, spp=1)
+        ranks = np.ctypeslib.as_array(s2.desc.tri_rank, (s2.desc.n_tris,))
+        assert np.array_equal(np.sort(ranks), np.arange(s2.desc.n_tris))
+        assert np.array_equal(np.ctypeslib.as_array(s2.desc.tri_v0, (3 * d.n_tris,)), np.ctypeslib.as_array(d.tri_v0, (3 * d.n_tris,)))
+        assert np.array_equal(np.ctypeslib.as_array(s2.desc.tri_v2, (3 * d.n_tris,)), np.ctypeslib.as_array(d.tri_v2, (3 * d.n_tris,)))
+    finally:
+        H.rth_set_eager_mesh_bvh(0)
 
 
 def test_unsupported_objects_are_flatten_errors(grt):

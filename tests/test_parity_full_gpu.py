@@ -125,8 +125,12 @@ def test_converged_bias_bound(grt, orc, ctx, name, depth, spp_g, spp_o):
     bz = (blk(mg) - blk(mo))[ok] / bse[ok]
     frac3 = np.mean(np.abs(bz) > 3)
     print(f"[bias {name}] {ok.sum()} live block channels: fraction beyond 3 sigma {frac3:.4f}, max |z| {np.abs(bz).max():.2f}, rms z {np.sqrt(np.mean(bz ** 2)):.3f}")
-    assert frac3 <= 0.01 and np.abs(bz).max() < 5.0, f"{name}: block means outside 3 sigma: {frac3:.4f}, max {np.abs(bz).max():.2f}"
-    assert np.sqrt(np.mean(bz ** 2)) < 1.15, f"{name}: rms block z {np.sqrt(np.mean(bz ** 2)):.3f} (1 = same expectation)"
+    # 48 blocks x 3 strongly correlated channels: one block beyond 3 sigma shows up as 3 of 144 (2.1 %), which a heavy-tailed scene
+    # (cornell: fog, a small bright light) produces in about one run in eight with identical estimators. So: at most one such block, none
+    # beyond 5 sigma, and the bulk of the distribution — the median |z| (0.674 for a Gaussian) and the rms — where a common expectation puts it.
+    assert frac3 <= 0.022 and np.abs(bz).max() < 5.0, f"{name}: block means outside 3 sigma: {frac3:.4f}, max {np.abs(bz).max():.2f}"
+    assert np.median(np.abs(bz)) < 0.85, f"{name}: median |z| of the block means {np.median(np.abs(bz)):.3f} (0.674 = same expectation)"
+    assert np.sqrt(np.mean(bz ** 2)) < 1.25, f"{name}: rms block z {np.sqrt(np.mean(bz ** 2)):.3f} (1 = same expectation)"
 
 
 # ------------------------------------------------------------------------------------------------------------
