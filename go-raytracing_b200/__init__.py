@@ -82,11 +82,11 @@ class Stats(C.Structure):
         ("tlas_nodes", C.c_uint32), ("blas_nodes", C.c_uint32), ("n_entries", C.c_uint32), ("n_tris", C.c_uint32),
         ("blas_depth", C.c_uint32), ("bvh_on_device", C.c_uint32), ("ms_bvh_build", C.c_double), ("ms_scene_upload", C.c_double),
         ("ms_tail", C.c_double), ("ms_reduce", C.c_double), ("ms_resolve", C.c_double), ("tail_iterations", C.c_uint64),
-        ("n_devices", C.c_uint32), ("pad_", C.c_uint32),
+        ("n_devices", C.c_uint32), ("checked_build", C.c_uint32), ("checked_violations", C.c_uint64), ("checked_by_kind", C.c_uint64 * 8),
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        return {k: (list(getattr(self, k)) if k == "checked_by_kind" else getattr(self, k)) for k, _ in self._fields_}
 
 
 # every symbol include/rtx_b200.h declares (tests check that the library exports all of them)

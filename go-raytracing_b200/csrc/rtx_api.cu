@@ -33,6 +33,9 @@
 using rtxbvh::Box;
 using rtxbvh::Node4;
 
+#ifdef RTX_CHECKED
+__global__ void k_check_selftest(int n) { RTX_CHECK(threadIdx.x >= n, 7); }
+#endif
 static thread_local std::string g_create_error;
 static inline float __int_as_float_host(int v) { float f; std::memcpy(&f, &v, sizeof f); return f; }
 
@@ -398,6 +401,13 @@ static int32_t set_option_single(rtx_ctx* ctx, const char* key, int64_t value) {
         ctx->pretest_bare = (int)value;
     }
     else if (k == "simple_below") ctx->simple_below = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 30));
+#ifdef RTX_CHECKED
+    else if (k == "checked_selftest") {   // negative control of the checked build: record `value` violations of kind 7 through the same macro the kernels use
+        cudaSetDevice(ctx->device);
+        k_check_selftest<<<1, 32, 0, ctx->stream>>>((int)value);
+        cudaStreamSynchronize(ctx->stream);
+    }
+#endif
     else if (k == "overlap_connect") ctx->overlap_connect = value != 0;   // k_connect on its own stream beside the next iteration (default on)
     else if (k == "flat_max_entries") {   // 0 = always traverse the hierarchy
         if (value < 0 || value > 64) return fail(ctx, RTX_ERR_INVALID, "flat_max_entries must be in 0..64");
@@ -991,6 +1001,7 @@ static int32_t scene_upload_single(rtx_ctx* ctx, const rtx_scene_desc* d) {
     S.tlas_root = tlasRoot;
     S.n_entries = d->n_entries;
     S.n_unbounded = (int)unbounded.size();
+    S.n_nodes = (int)nodes.size(); S.n_tris_total = totalTris;
     S.n_tlas_flat = (int)(tlasBoxes.size() / 2);
     for (size_t k = 0; k < tlasBoxes.size() && k < 32; k++) S.tlas_boxes[k] = tlasBoxes[k];
     S.n_lights = d->n_lights;
@@ -1539,6 +1550,19 @@ int32_t rtx_get_stats(rtx_ctx* ctx, rtx_stats* out) {
     for (rtx_ctx* p : ctx->peers) { out->ms_bvh_build = std::max(out->ms_bvh_build, p->ms_upload_blas); out->ms_scene_upload = std::max(out->ms_scene_upload, p->ms_upload_total); }
     out->ms_resolve = ctx->ms_resolve;
     out->n_devices = (uint32_t)(1 + ctx->peers.size());
+    out->checked_build = 0; out->checked_violations = 0;
+#ifdef RTX_CHECKED
+    {   // the run-time assertions of the checked build (rtx_trace.cuh), summed over all kinds and all launches since the library was loaded
+        unsigned long long v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        cudaSetDevice(ctx->device);
+        cudaDeviceSynchronize();
+        cudaMemcpyFromSymbol(v, g_rtx_check, sizeof v);
+        out->checked_build = 1;
+        for (int k = 0; k < 8; k++) { out->checked_violations += v[k]; out->checked_by_kind[k] = v[k]; }
+    }
+#else
+    for (int k = 0; k < 8; k++) out->checked_by_kind[k] = 0;
+#endif
     return RTX_OK;
 }
 

@@ -115,6 +115,7 @@ struct DevScene {
     const float4* nodes;  // wide BVH: 8 x float4 (128 B, 128-B aligned) per 4-wide node; TLAS and all BLAS share the array
     int tlas_root;        // -1: no bounded entries
     int n_entries;
+    int n_nodes, n_tris_total;   // array sizes (read by the RTX_CHECKED build's index assertions)
     const DEntry* entries;
     const int* unbounded;  // entries tested for every ray (infinite Plane: universe bbox, rt/plane.go:17)
     int n_unbounded;

@@ -159,7 +159,21 @@ struct Best {
 #define RTX_SLOT_WORDS_T(TIME) (9 + 1 + 1 + 3 + 12 + ((TIME) ? 2 : 0) + 2 + 6 + RTX_SMEM_STACK)
 #define RTX_SLOT_WORDS_OF(FEAT) RTX_SLOT_WORDS_T(RTX_FEAT_HAS_TIME(FEAT))
 #define RTX_SLOT_WORDS RTX_SLOT_WORDS_T(true)
+// RTX_CHECKED (make checked -> librtx_b200_checked.so): the build that stands in for compute-sanitizer racecheck / memcheck, which is closed
+// on the GPU pool this repo is measured on. The slot hand-over protocol of trace_persistent (claim with a shared-memory CAS, work on the
+// slot, __threadfence_block, publish with an atomic XOR) and every index the traversal dereferences are asserted at run time; violations are
+// COUNTED, per kind, in g_rtx_check and come back through rtx_stats.checked_violations (tests/test_checked_build.py demands zero):
+//   0 a slot claimed while another warp owns it      1 a slot published by a warp that does not own it    2 phase nibble not BUSY at publish
+//   3 stack pointer out of range                     4 node index out of range                            5 triangle index out of range
+//   6 world entry index out of range                 7 job index out of range
+#ifdef RTX_CHECKED
+__device__ unsigned long long g_rtx_check[8];
+#define RTX_CHECK(cond, k) do { if (!(cond)) atomicAdd(&g_rtx_check[k], 1ull); } while (0)
+#define RTX_POOL_EXTRA_BYTES (256 + 4 * 256)                            /* column states + flags + one owner word per slot (<= 256 slots) */
+#else
+#define RTX_CHECK(cond, k) do { } while (0)
 #define RTX_POOL_EXTRA_BYTES 256                                        /* column states + flags */
+#endif
 #define RTX_PH_BUSY 5   /* claimed by a warp for the current round */
 
 template <int NSLOTS, bool TIME = true>
@@ -177,6 +191,7 @@ struct TracePool {
     int* stack;    // [RTX_SMEM_STACK][NS]
     unsigned* col; // [32]  packed phase nibbles of the NS/32 slots of each bank column (block-shared scheduling state)
     int* flags;    // [32]  flags[0]: job queue ran dry
+    int* owner;    // RTX_CHECKED only: [NS] 0 = free, else 1 + warp of the block that claimed the slot
     __device__ __forceinline__ explicit TracePool(unsigned char* base) {
         double* d = reinterpret_cast<double*>(base);
         r = d; d += (TIME ? 7 : 6) * NS;
@@ -190,7 +205,8 @@ struct TracePool {
         be = q; q += NS; bk = q; q += NS; bp = q; q += NS; bi = q; q += NS; bre = q; q += NS; brp = q; q += NS;
         stack = q; q += RTX_SMEM_STACK * NS;
         col = reinterpret_cast<unsigned*>(q); q += 32;
-        flags = q;
+        flags = q; q += 32;
+        owner = q;
     }
     __device__ __forceinline__ void load_rayf(int s, RayF& x) const {
         x.ix = f[s]; x.iy = f[NS + s]; x.iz = f[2 * NS + s]; x.cnx = f[3 * NS + s]; x.cny = f[4 * NS + s]; x.cnz = f[5 * NS + s];
@@ -469,6 +485,9 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
         T.flags[threadIdx.x] = 0;
     }
     for (int i = threadIdx.x; i < NS; i += RTX_TRACE_THREADS) T.node[i] = RTX_ST_IDLE;
+#ifdef RTX_CHECKED
+    for (int i = threadIdx.x; i < NS; i += RTX_TRACE_THREADS) T.owner[i] = 0;
+#endif
     __syncthreads();
     unsigned round = warp;
 
@@ -538,6 +557,9 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
         const bool mine = j >= 0;
         const int s = (int)col + 32 * (mine ? j : 0);
         if (mine) __threadfence_block();   // see the slot as its previous owner left it
+#ifdef RTX_CHECKED
+        if (mine) { const int prev = atomicExch(&T.owner[s], 1 + (int)warp); RTX_CHECK(prev == 0, 0); RTX_CHECK(phase == RTX_PH_R || (int)T.spb[4 * s + 3] <= RTX_STACK_SIZE, 3); }   // (an idle slot's stack pointer is not initialised)
+#endif
         int newst = -1;  // phase of the claimed slot after this round
 
         if (phase == RTX_PH_N) {
@@ -554,6 +576,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                 for (int step = 0; step < RTX_N_STEPS && node >= 0; step++) {
                     float d[4]; int ch[4];
                     if (COUNT) tc.nodes++;
+                    RTX_CHECK(node < S.n_nodes, 4);
                     node_test(S.nodes, node, f, ftmin, ftmax, d, ch);
 #define RTX_CSWAP(i, j) if (d[j] < d[i]) { float td = d[i]; d[i] = d[j]; d[j] = td; int tcx = ch[i]; ch[i] = ch[j]; ch[j] = tcx; }
                     // closest-hit queries visit the children front to back; an any-hit query only needs SOME hit, so the order is
@@ -594,6 +617,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                 for (int step = 0; step < RTX_T_STEPS; step++) {
                     const int code = ~node;
                     const int ti = code >> 3, rem = code & 7;
+                    RTX_CHECK(ti >= 0 && ti < S.n_tris_total, 5);
                     if (COUNT) tc.tris++;
                     const double t = isect_tri(S.tris + RTX_TRI_D * (size_t)ti, r, nullptr);
                     bool have = false;
@@ -636,6 +660,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                     RTX_POP_TOP();
                 } else {
                     const int ei = flatTlas ? RTX_TLAS_CODE_ENTRY(node) : ~node;
+                    RTX_CHECK(ei >= 0 && ei < S.n_entries, 6);
                     const DEntry e = S.entries[ei];
                     if ((FEAT & RTX_F_MESH) && e.volume < 0 && e.kind == RTX_GEOM_MESH) {
                         RayD r2; RayF f;
@@ -753,6 +778,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                 if (lane == 0) base = atomicAdd(cursor, cnt);
                 base = __shfl_sync(FULL, base, 0);
                 const int my = base + __popc(want & ((1u << lane) - 1u));
+                RTX_CHECK(!mine || my >= 0, 7);
                 if (mine && my < njobs) {
                     RayD r; RayF f; Best B;
                     double tmax;
@@ -818,6 +844,9 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
             if (mine && newst == RTX_PH_NONE && !exhausted) newst = RTX_PH_R;
         }
         if (mine) {   // publish: slot state first, then its phase nibble (BUSY -> newst)
+#ifdef RTX_CHECKED
+            { const int prev = atomicExch(&T.owner[s], 0); RTX_CHECK(prev == 1 + (int)warp, 1); RTX_CHECK(((colstate[col] >> (4 * j)) & 0xfu) == (unsigned)RTX_PH_BUSY, 2); RTX_CHECK(newst >= 0 && newst <= RTX_PH_NONE, 2); }
+#endif
             __threadfence_block();
             atomicXor(const_cast<unsigned*>(colstate) + col, (unsigned)(RTX_PH_BUSY ^ newst) << (4 * j));
         }

@@ -221,7 +221,10 @@ typedef struct rtx_stats {
     double ms_resolve;         /* last rtx_resolve_rgba8: kernel + device-to-host copy (CUDA events)                         */
     uint64_t tail_iterations;  /* wavefront iterations of the last pass after its last camera path was generated            */
     uint32_t n_devices;        /* 1, or the device count of an rtx_create_multi context                                      */
-    uint32_t pad_;
+    uint32_t checked_build;    /* 1 when the library was compiled with RTX_CHECKED (librtx_b200_checked.so): the trace kernels assert their
+                                  slot hand-over protocol and every index at run time (the stand-in for compute-sanitizer)          */
+    uint64_t checked_violations;   /* failed assertions of the checked build since the library was loaded; must be 0            */
+    uint64_t checked_by_kind[8];   /* by kind, see csrc/rtx_trace.cuh                                                            */
 } rtx_stats;
 
 typedef struct rtx_ctx rtx_ctx;

@@ -25,7 +25,7 @@ def test_header_symbols_exported(grt):
 def test_struct_layout_matches_header(grt):
     # sizes follow from the field lists in include/rtx_b200.h (LP64): catches a drifting ctypes mirror
     assert C.sizeof(grt.CameraDesc) == 8 + 4 * 3 + 4 + 8 + 9 * 8 + 16 + 48 + 8 + 48 + 8 + 8 + 7 * 24 + 24
-    assert C.sizeof(grt.Stats) == 10 * 8 + 5 * 8 + 4 * 4 + 2 * 4 + 2 * 8 + 3 * 8 + 8 + 2 * 4
+    assert C.sizeof(grt.Stats) == 10 * 8 + 5 * 8 + 4 * 4 + 2 * 4 + 2 * 8 + 3 * 8 + 8 + 2 * 4 + 8 + 8 * 8
 
 
 def test_no_cpu_fallback(grt):
