@@ -23,6 +23,9 @@
 #ifndef RTX_PRETEST_BARE_DEFAULT
 #define RTX_PRETEST_BARE_DEFAULT 0
 #endif
+#ifndef RTX_SHADE_DIRECT_DEFAULT
+#define RTX_SHADE_DIRECT_DEFAULT 1
+#endif
 #ifndef RTX_SIMPLE_BELOW_DEFAULT
 #define RTX_SIMPLE_BELOW_DEFAULT 0
 #endif
@@ -97,6 +100,7 @@ struct rtx_ctx {
     float4* per_sample = nullptr; size_t per_sample_cap = 0;   // moments mode: per-sample radiance sums of the running pass (grow-only)
     int flat_max_entries = 16, scene_flat = 0, scene_has_mesh = 0;   // worlds of <= flat_max_entries entries without a mesh are traced by the flat kernels (trace_flat)
     int pixel_major = 1;  // path order of k_generate: all samples of a pixel consecutively (1) or sample-major (0)
+    int shade_direct = RTX_SHADE_DIRECT_DEFAULT;   // hierarchy worlds: k_shade in stream order instead of through material-sorted queues
     int simple_below = RTX_SIMPLE_BELOW_DEFAULT;   // hierarchy worlds: iterations of the drain with at most this many rays run the one-thread-per-ray trace kernels (0 = never)
     int tlas_flat_max = RTX_TLAS_FLAT_MAX;   // mesh worlds with at most this many bounded entries: top level as a per-ray sorted list (0 = hierarchy)
     int bvh_device = 1;   // mesh BLAS construction on the device (rtx_bvh_gpu.cuh); 0 = host builder (rtx_bvh.hpp), kept for A/B
@@ -400,6 +404,7 @@ static int32_t set_option_single(rtx_ctx* ctx, const char* key, int64_t value) {
         if (value < 0 || value > 64) return fail(ctx, RTX_ERR_INVALID, "pretest_bare must be in 0..64");
         ctx->pretest_bare = (int)value;
     }
+    else if (k == "shade_direct") ctx->shade_direct = value != 0;
     else if (k == "simple_below") ctx->simple_below = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 30));
 #ifdef RTX_CHECKED
     else if (k == "checked_selftest") {   // negative control of the checked build: record `value` violations of kind 7 through the same macro the kernels use
@@ -511,6 +516,7 @@ static int32_t scene_upload_single(rtx_ctx* ctx, const rtx_scene_desc* d) {
                 return bad("image texture without image data");
         } else if (d->tex_type[i] != RTX_TEX_SOLID) return fail(ctx, RTX_ERR_UNSUPPORTED, "texture type %d is outside the device path", d->tex_type[i]);
     }
+    if (d->n_materials >= (1 << 28)) return bad("too many materials");   // a hit record packs the material index into 28 bits
     for (int i = 0; i < d->n_materials; i++) {
         int t = d->mat_type[i];
         if (t < RTX_MAT_LAMBERTIAN || t > RTX_MAT_ISOTROPIC) return fail(ctx, RTX_ERR_UNSUPPORTED, "material type %d is outside the device path", t);
@@ -1232,6 +1238,7 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
     pp.spp = spp; pp.max_depth = max_depth; pp.camera_max_depth = camera_max_depth;
     pp.seed_lo = (uint32_t)seed; pp.seed_hi = (uint32_t)(seed >> 32); pp.sample_base = sample_base;
     pp.moments = ctx->moments; pp.count_stats = ctx->count_stats; pp.pixel_major = ctx->pixel_major;
+    pp.shade_direct = (ctx->shade_direct && !ctx->shade_split && !ctx->scene_flat && !ctx->fuse_tree) ? 1 : 0;
 
     const unsigned long long npix = (unsigned long long)ctx->W * ctx->H;
     Ctl init{};

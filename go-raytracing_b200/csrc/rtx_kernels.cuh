@@ -101,6 +101,7 @@ struct PassParams {
     int spp, max_depth, camera_max_depth;
     uint32_t seed_lo, seed_hi, sample_base;
     int moments, count_stats, pixel_major;
+    int shade_direct;   // 1: k_shade walks the rays in STREAM order (the hit record carries its shading queue), 0: through the material-sorted queues
 };
 
 // warp-aggregated queue append: one atomic per warp (ballot + popc), returns this lane's position
@@ -238,7 +239,7 @@ extern __shared__ __align__(16) unsigned char rtx_smem[];  // the trace kernels'
 template <bool UV, unsigned FEAT = RTX_F_ALL>
 struct ExtendPolicyT {
     static constexpr bool ANY_HIT = false;
-    Ctl* ctl; char* hit; int* q_mat; int capacity; const char* rec; const DevScene* S; uint32_t seed_lo, seed_hi;
+    Ctl* ctl; char* hit; int* q_mat; int capacity; const char* rec; const DevScene* S; uint32_t seed_lo, seed_hi; int direct;
     __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:451
     __device__ __forceinline__ void prefetch(int job) const {
         const char* q = rec + (size_t)job * RTX_REC_BYTES;
@@ -261,21 +262,24 @@ struct ExtendPolicyT {
     __device__ __forceinline__ void retire(int job, bool valid, const RayD& r, const Best& b) const {
         int q = -1;
         if (valid) {
+            char* h = hit + (size_t)job * (UV ? RTX_HIT_BYTES_UV : RTX_HIT_BYTES);
             if (b.entry < 0) {
                 q = Q_MISS;
+                if (direct) st256d(h + 32, 0.0, 0.0, 0.0, __longlong_as_double((long long)Q_MISS << 28));   // stream-order shading reads the queue from the record
             } else {
                 HitInfo hi;
                 finalize_hit<FEAT>(*S, r, best_to_hit(b), UV, hi);
-                const long long bits = (long long)(unsigned)hi.mat | (hi.front ? (1LL << 31) : 0);
-                char* h = hit + (size_t)job * (UV ? RTX_HIT_BYTES_UV : RTX_HIT_BYTES);
-                st256d(h, hi.P.x, hi.P.y, hi.P.z, b.t);
-                st256d(h + 32, hi.N.x, hi.N.y, hi.N.z, __longlong_as_double(bits));
-                if (UV) st256d(h + 64, hi.u, hi.v, 0.0, 0.0);   // scenes with image textures: the hit's (u, v) in float64, like rec.U / rec.V
                 const int mt = S->mats[hi.mat].type;
                 q = mt == RTX_MAT_LAMBERTIAN ? Q_LAMBERTIAN : mt == RTX_MAT_METAL ? Q_METAL : mt == RTX_MAT_DIELECTRIC ? Q_DIELECTRIC
                     : mt == RTX_MAT_DIFFUSE_LIGHT ? Q_LIGHT : Q_ISOTROPIC;
+                // material (28 bits) | shading queue (3 bits) | front face
+                const long long bits = (long long)(unsigned)hi.mat | ((long long)q << 28) | (hi.front ? (1LL << 31) : 0);
+                st256d(h, hi.P.x, hi.P.y, hi.P.z, b.t);
+                st256d(h + 32, hi.N.x, hi.N.y, hi.N.z, __longlong_as_double(bits));
+                if (UV) st256d(h + 64, hi.u, hi.v, 0.0, 0.0);   // scenes with image textures: the hit's (u, v) in float64, like rec.U / rec.V
             }
         }
+        if (direct) return;   // stream-order shading: no queues (and no warp-aggregated atomics in the trace kernel's retire round)
         // material-sorted queues: one warp-aggregated append per queue
 #pragma unroll
         for (int k = 0; k < Q_COUNT; k++) {
@@ -290,7 +294,7 @@ typedef ExtendPolicyT<false> ExtendPolicy;
 // FEAT: the scene vocabulary the variant contains (RTX_F_*, rtx_device.cuh); rtx_render_pass picks the smallest covering one
 template <bool COUNT, bool UV = false, unsigned FEAT = RTX_F_ALL>
 __global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS_OF(FEAT)) k_extend(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, PassParams pp, int* spill) {
-    ExtendPolicyT<UV, FEAT> P{ctl, pool.hit, pool.q_mat, pool.capacity, pool.records(cur), &S, pp.seed_lo, pp.seed_hi};
+    ExtendPolicyT<UV, FEAT> P{ctl, pool.hit, pool.q_mat, pool.capacity, pool.records(cur), &S, pp.seed_lo, pp.seed_hi, pp.shade_direct};
     TraceCounters tc = {0, 0, 0, 0, 0};
     const int n = ctl->n_active;
     trace_persistent<ExtendPolicyT<UV, FEAT>, COUNT, RTX_TRACE_SLOTS_OF(FEAT), FEAT>(S, P, &ctl->cur_extend, n, tc, spill, rtx_smem);
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS_OF(FEAT)) 
 // small batches (the drain of a pass): one thread per ray, see trace_simple
 template <bool UV = false, unsigned FEAT = RTX_F_ALL>
 __global__ void __launch_bounds__(256) k_extend_simple(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, PassParams pp) {
-    ExtendPolicyT<UV, FEAT> P{ctl, pool.hit, pool.q_mat, pool.capacity, pool.records(cur), &S, pp.seed_lo, pp.seed_hi};
+    ExtendPolicyT<UV, FEAT> P{ctl, pool.hit, pool.q_mat, pool.capacity, pool.records(cur), &S, pp.seed_lo, pp.seed_hi, pp.shade_direct};
     TraceCounters tc = {0, 0, 0, 0, 0};
     const int n = ctl->n_active;
     trace_simple<ExtendPolicyT<UV, FEAT>, false, FEAT>(S, P, n, tc);
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(256) k_extend_simple(Ctl* ctl, Pool pool, int 
 
 template <bool COUNT, bool UV = false>
 __global__ void __launch_bounds__(256) k_extend_flat(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, PassParams pp) {
-    ExtendPolicyT<UV> P{ctl, pool.hit, pool.q_mat, pool.capacity, pool.records(cur), &S, pp.seed_lo, pp.seed_hi};
+    ExtendPolicyT<UV> P{ctl, pool.hit, pool.q_mat, pool.capacity, pool.records(cur), &S, pp.seed_lo, pp.seed_hi, pp.shade_direct};
     TraceCounters tc = {0, 0, 0, 0, 0};
     const int n = ctl->n_active;
     trace_flat<ExtendPolicyT<UV>, COUNT>(S, P, n, tc);
@@ -676,6 +680,35 @@ __global__ void __launch_bounds__(256, FEAT != RTX_F_ALL ? RTX_SHADE_BLOCKS_LEAN
   };
   const int stride = gridDim.x * blockDim.x;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (QT < 0 && pp.shade_direct) {
+      // STREAM ORDER (option shade_direct): thread i shades ray i; records and hit records are read front to back, fully coalesced, and the
+      // shading queue comes out of the hit record. The material-sorted order costs this HBM-bound kernel its bandwidth (gathers through the
+      // queues: 44 % of the copy peak over a pass) and costs the trace kernel an atomic round trip per retire round; what it buys — warps of
+      // one material — matters little to a kernel that issues 18 % of the time.
+      for (; i < n_rounded; i += stride) {
+          ShadeVars V;
+          V.reset();
+          if (i < n_items) {
+              const char* rec = pool.records(cur) + (size_t)i * RTX_REC_BYTES;
+              const char* hrec = pool.hit + (size_t)i * pool.hit_bytes;
+              const D4 ro4 = ld256d(rec), rd4 = ld256d(rec + 32), hn = ld256d(hrec + 32);
+              V.tm = ro4.w; V.pixbits = rd4.w;
+              V.th = ldrec4(rec + 64);
+              const long long bits = __double_as_longlong(hn.w);
+              const int type = (int)((bits >> 28) & 7);
+              D3 P = d3(0, 0, 0);
+              double hu = 0.0, hv = 0.0;
+              if (type != Q_MISS) {
+                  const D4 hp = ld256d(hrec);
+                  P = d3(hp.x, hp.y, hp.z);
+                  if (S.n_images > 0) { const D4 huv = ld256d(hrec + 64); hu = huv.x; hv = huv.y; }
+              }
+              shade_element<FEAT>(S, C, pp, pool, type, d3(rd4.x, rd4.y, rd4.z), P, d3(hn.x, hn.y, hn.z), hu, hv, (int)(bits & 0x0fffffff), (bits >> 31) & 1, V);
+          }
+          shade_commit(ctl, pool, cur, V);
+      }
+      return;
+  }
   int type_next = -1;
   int job_next = i < n_rounded ? locate(i, type_next) : -1;
   for (; i < n_rounded; i += stride) {
@@ -712,7 +745,7 @@ __global__ void __launch_bounds__(256, FEAT != RTX_F_ALL ? RTX_SHADE_BLOCKS_LEAN
             N = d3(hn.x, hn.y, hn.z);
             if (S.n_images > 0) { const D4 huv = ld256d(hrec + 64); hu = huv.x; hv = huv.y; }
             const long long bits = __double_as_longlong(hn.w);
-            mat = (int)(bits & 0x7fffffff);
+            mat = (int)(bits & 0x0fffffff);
             front = (bits >> 31) & 1;
         }
         shade_element<FEAT>(S, C, pp, pool, type, d3(rd4.x, rd4.y, rd4.z), P, N, hu, hv, mat, front, V);

@@ -115,7 +115,7 @@ struct Best {
 #define RTX_SMEM_STACK 16
 #endif
 #ifndef RTX_N_STEPS
-#define RTX_N_STEPS 3   /* node levels per NODE round (A/B on cornell-lucy: 1: 1041, 2: 1062, 3: 1090, 4: 1080 Mrays/s) */
+#define RTX_N_STEPS 4   /* node levels per NODE round (A/B on cornell-lucy: 1: 1041, 2: 1062, 3: 1090, 4: 1080 Mrays/s; with the flat top level — no TLAS nodes in the loop — 64 spp take 185.4 / 182.4 / 180.9 ms at 2 / 3 / 4) */
 #endif
 #ifndef RTX_T_STEPS
 #define RTX_T_STEPS 4   /* triangles per TRI round (1: 1282, 2: 1303-1332, 4: 1373 Mrays/s) */
@@ -148,6 +148,12 @@ struct Best {
 #define RTX_TLAS_CODE(tn, ei) ((int)(0x80000000u | ((unsigned)__float_as_int(tn) & 0x7fffff00u) | (unsigned)(ei)))
 #define RTX_TLAS_CODE_DIST(code) (__int_as_float((code) & 0x7fffff00))
 #define RTX_TLAS_CODE_ENTRY(code) ((code) & 0xff)
+#ifndef RTX_EARLY_TICKET
+#define RTX_EARLY_TICKET 1
+#endif
+#ifndef RTX_EARLY_LOAD
+#define RTX_EARLY_LOAD 0
+#endif
 #define RTX_PH_N 0
 #define RTX_PH_T 1
 #define RTX_PH_E 2
@@ -751,6 +757,23 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
         } else {
             // ---- RETIRE + REFILL (warp-collective; one slot per lane per round) ---------------------------------------
             const bool fin = mine && T.node[s] == RTX_ST_DONE;
+            // The ticket for the rays this round will load is drawn FIRST (RTX_EARLY_TICKET): every claimed slot is refilled, so the count is known,
+            // and the atomic's round trip to L2 (~700 cycles) then runs under the retire work below instead of in front of the refill.
+            bool exhausted = __any_sync(FULL, dry[0] != 0);
+            const unsigned want = __ballot_sync(FULL, mine);
+            const int cnt = __popc(want);
+            int base = 0;
+            if (RTX_EARLY_TICKET && !exhausted && lane == 0) base = atomicAdd(cursor, cnt);
+#if RTX_EARLY_LOAD
+            // ... and so are the new rays' records (RTX_EARLY_LOAD): a DRAM read of the path stream, requested before the retire work, used after it
+            RayD r_new; double tmax_new = 0;
+            int my_new = -1;
+            if (!exhausted) {
+                base = __shfl_sync(FULL, base, 0);
+                my_new = base + __popc(want & ((1u << lane) - 1u));
+                if (mine && my_new < njobs) P.load(my_new, r_new, tmax_new);
+            }
+#endif
             {
                 RayD rw;
                 Best B;
@@ -770,19 +793,24 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                 T.node[s] = RTX_ST_IDLE;
                 newst = RTX_PH_NONE;
             }
-            bool exhausted = __any_sync(FULL, dry[0] != 0);
             if (!exhausted) {
-                const unsigned want = __ballot_sync(FULL, mine);
-                const int cnt = __popc(want);
-                int base = 0;
-                if (lane == 0) base = atomicAdd(cursor, cnt);
+                if (!RTX_EARLY_TICKET && lane == 0) base = atomicAdd(cursor, cnt);
+#if RTX_EARLY_LOAD
+                const int my = my_new;
+#else
                 base = __shfl_sync(FULL, base, 0);
                 const int my = base + __popc(want & ((1u << lane) - 1u));
+#endif
                 RTX_CHECK(!mine || my >= 0, 7);
                 if (mine && my < njobs) {
-                    RayD r; RayF f; Best B;
+                    RayF f; Best B;
+#if RTX_EARLY_LOAD
+                    const RayD r = r_new; const double tmax = tmax_new;
+#else
+                    RayD r;
                     double tmax;
                     P.load(my, r, tmax);
+#endif
                     B.reset(tmax);
                     // entries tested for every ray: unbounded geometry (infinite Plane, rt/plane.go:17) and, with option pretest_bare, the
                     // few bare primitives beside a mesh (the Cornell walls) that rtx_scene_upload kept out of the TLAS
