@@ -252,6 +252,11 @@ struct ExtendPolicyT {
         r.ox = a.x; r.oy = a.y; r.oz = a.z; r.tm = a.w; r.dx = c.x; r.dy = c.y; r.dz = c.z;
         tmax = RTX_INF_D;
     }
+    __device__ __forceinline__ void prefetch_far(int job) const {   // a record a later refill will load: pulled from DRAM into L2 now
+        const char* q = rec + (size_t)job * RTX_REC_BYTES;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 32));
+    }
     __device__ __forceinline__ VolumeRng volume_rng(int job) const {
         const char* q = rec + (size_t)job * RTX_REC_BYTES;
         const unsigned long long ps = (unsigned long long)__double_as_longlong(ld256d(q + 32).w);
@@ -864,6 +869,7 @@ struct BounceTreePolicyT {
     static constexpr bool ANY_HIT = false;
     Ctl* ctl; const Pool* pool; int cur; const DevScene* S; const DevCamera* C; const PassParams* pp; const char* rec;
     __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:451
+    __device__ __forceinline__ void prefetch_far(int) const {}
     __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
         const char* q = rec + (size_t)job * RTX_REC_BYTES;
         const D4 a = ld256d(q), c = ld256d(q + 32);
@@ -910,6 +916,11 @@ struct ConnectPolicy {
         const D4 o0 = ld256d(q), d0 = ld256d(q + 32);
         r.ox = o0.x; r.oy = o0.y; r.oz = o0.z; r.dx = d0.x; r.dy = d0.y; r.dz = d0.z; r.tm = 0;  // NewRay(hitPoint, lightDir, 0)
         tmax = o0.w;
+    }
+    __device__ __forceinline__ void prefetch_far(int job) const {
+        const char* q = pool.shadow + (size_t)job * RTX_SHADOW_BYTES;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 32));
     }
     __device__ __forceinline__ VolumeRng volume_rng(int job) const {
         const char* q = pool.shadow + (size_t)job * RTX_SHADOW_BYTES;
@@ -1001,6 +1012,7 @@ struct BatchPolicyT {
     int* entry_id; int* prim_id; double* t; double* normal; unsigned char* front; double* uv; double* p;
     __device__ __forceinline__ double tmin() const { return t0; }
     __device__ __forceinline__ void prefetch(int) const {}
+    __device__ __forceinline__ void prefetch_far(int) const {}
     __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
         const double* q = rays + 7 * (size_t)job;
         r.ox = q[0]; r.oy = q[1]; r.oz = q[2]; r.dx = q[3]; r.dy = q[4]; r.dz = q[5]; r.tm = q[6];
