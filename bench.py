@@ -425,6 +425,9 @@ def main():
     inlib = None
     if world > 1:
         barrier()
+        # the other ranks must wait on the HOST: an NCCL barrier is a kernel that spins on their GPUs, which are exactly the devices rank 0 is
+        # about to render on
+        cpu_group = dist.new_group(backend="gloo")
         if rank == 0:
             try:
                 mctx = grt.Context(devices=list(range(world)))
@@ -444,6 +447,7 @@ def main():
                 mctx.close()
             except Exception as e:  # noqa: BLE001
                 inlib = {"error": str(e)[:200]}
+        dist.barrier(group=cpu_group)
         barrier()
 
     cpu = None

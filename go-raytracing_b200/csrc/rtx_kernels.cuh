@@ -625,29 +625,38 @@ __device__ __forceinline__ void shade_commit(Ctl* ctl, const Pool& pool, const i
     const float4 th = V.th;
     const int bounce0 = V.bounce0;
     const float3 env_c = V.env_c, area_c = V.area_c;
-    // survivors: the next ray goes to the next free record of the other buffer, in the order the warps arrive
-    const int pos = warp_append(&ctl->n_next, cont);
+    // Survivors go to the next free records of the other buffer, shadow requests to this iteration's half, in the order the warps arrive.
+    // Both tickets are drawn by one lane BACK TO BACK (one atomic per counter per warp; the two round trips to L2 overlap) before any
+    // lane uses either: with three dependent warp_append calls this HBM-bound kernel spent its time waiting on atomic returns.
+    const unsigned am = __activemask();
+    const unsigned mc = __ballot_sync(am, cont), me = __ballot_sync(am, has_env), ma = __ballot_sync(am, has_area);
+    const int lane = threadIdx.x & 31, leader = __ffs(am) - 1;
+    int bc = 0, bs = 0;
+    if (lane == leader) {
+        if (mc) bc = atomicAdd(&ctl->n_next, __popc(mc));
+        if (me | ma) bs = atomicAdd(&ctl->n_shadow[cur], __popc(me) + __popc(ma));
+    }
+    bc = __shfl_sync(am, bc, leader);
+    bs = __shfl_sync(am, bs, leader);
+    const unsigned below = (1u << lane) - 1u;
     if (cont) {
-        char* out = pool.records(cur ^ 1) + (size_t)pos * RTX_REC_BYTES;
+        char* out = pool.records(cur ^ 1) + (size_t)(bc + __popc(mc & below)) * RTX_REC_BYTES;
         st256d(out, P.x, P.y, P.z, tm);
         st256d(out + 32, nd.x, nd.y, nd.z, pixbits);
         strec4(out + 64, th);
     }
-    {   // shadow requests carry everything k_connect needs (origin = the hit point, where the contribution goes)
-        int sp = warp_append(&ctl->n_shadow[cur], has_env);
-        if (has_env) {
-            char* q = pool.shadow + (size_t)sp * RTX_SHADOW_BYTES;
-            st256d(q, P.x, P.y, P.z, RTX_INF_D);
-            st256d(q + 32, env_dir.x, env_dir.y, env_dir.z, pixbits);
-            strec4(q + 64, make_float4(env_c.x, env_c.y, env_c.z, __int_as_float(bounce0)));
-        }
-        sp = warp_append(&ctl->n_shadow[cur], has_area);
-        if (has_area) {
-            char* q = pool.shadow + (size_t)sp * RTX_SHADOW_BYTES;
-            st256d(q, P.x, P.y, P.z, area_tmax);
-            st256d(q + 32, area_dir.x, area_dir.y, area_dir.z, pixbits);
-            strec4(q + 64, make_float4(area_c.x, area_c.y, area_c.z, __int_as_float(bounce0)));
-        }
+    // shadow requests carry everything k_connect needs (origin = the hit point, where the contribution goes)
+    if (has_env) {
+        char* q = pool.shadow + (size_t)(bs + __popc(me & below)) * RTX_SHADOW_BYTES;
+        st256d(q, P.x, P.y, P.z, RTX_INF_D);
+        st256d(q + 32, env_dir.x, env_dir.y, env_dir.z, pixbits);
+        strec4(q + 64, make_float4(env_c.x, env_c.y, env_c.z, __int_as_float(bounce0)));
+    }
+    if (has_area) {
+        char* q = pool.shadow + (size_t)(bs + __popc(me) + __popc(ma & below)) * RTX_SHADOW_BYTES;
+        st256d(q, P.x, P.y, P.z, area_tmax);
+        st256d(q + 32, area_dir.x, area_dir.y, area_dir.z, pixbits);
+        strec4(q + 64, make_float4(area_c.x, area_c.y, area_c.z, __int_as_float(bounce0)));
     }
 }
 

@@ -96,6 +96,20 @@ __global__ void k_ranks(const int* idx, int n, int* rank) {
     if (i < n) rank[idx[i]] = i;
 }
 
+// Content hash of a device array of 64-bit words (order-independent sum of position-mixed words): the key under which rtx_scene_upload
+// remembers the test order of a mesh it has ranked before, so that re-uploading an unchanged scene does not sort it again.
+__global__ void k_hash64(const unsigned long long* w, size_t n, unsigned long long salt, unsigned long long* out) {
+    unsigned long long acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned long long z = w[i] ^ ((i + salt) * 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        acc += z ^ (z >> 31);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
 // Scratch bytes for a mesh of n triangles (an upper bound; the caller carves it from its work slab).
 inline size_t scratch_bytes(int n) {
     const size_t pad = 256;
