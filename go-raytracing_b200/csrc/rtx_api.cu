@@ -23,6 +23,9 @@
 #ifndef RTX_PRETEST_BARE_DEFAULT
 #define RTX_PRETEST_BARE_DEFAULT 0
 #endif
+#ifndef RTX_DRAIN_PER_BLOCK_DEFAULT
+#define RTX_DRAIN_PER_BLOCK_DEFAULT 32   /* rays per block the persistent grids of the drain are sized for */
+#endif
 #ifndef RTX_SHADE_DIRECT_DEFAULT
 #define RTX_SHADE_DIRECT_DEFAULT 1
 #endif
@@ -100,6 +103,7 @@ struct rtx_ctx {
     float4* per_sample = nullptr; size_t per_sample_cap = 0;   // moments mode: per-sample radiance sums of the running pass (grow-only)
     int flat_max_entries = 16, scene_flat = 0, scene_has_mesh = 0;   // worlds of <= flat_max_entries entries without a mesh are traced by the flat kernels (trace_flat)
     int pixel_major = 1;  // path order of k_generate: all samples of a pixel consecutively (1) or sample-major (0)
+    int tri_pretest = RTX_TRI_PRETEST;      // mesh worlds: float32 pre-test records for the TRI phase (takes effect at the next rtx_scene_upload)
     int shade_direct = RTX_SHADE_DIRECT_DEFAULT;   // hierarchy worlds: k_shade in stream order instead of through material-sorted queues
     int simple_below = RTX_SIMPLE_BELOW_DEFAULT;   // hierarchy worlds: iterations of the drain with at most this many rays run the one-thread-per-ray trace kernels (0 = never)
     int tlas_flat_max = RTX_TLAS_FLAT_MAX;   // mesh worlds with at most this many bounded entries: top level as a per-ray sorted list (0 = hierarchy)
@@ -410,6 +414,7 @@ static int32_t set_option_single(rtx_ctx* ctx, const char* key, int64_t value) {
         ctx->pretest_bare = (int)value;
     }
     else if (k == "shade_direct") ctx->shade_direct = value != 0;
+    else if (k == "tri_pretest") ctx->tri_pretest = value != 0;
     else if (k == "simple_below") ctx->simple_below = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 30));
 #ifdef RTX_CHECKED
     else if (k == "checked_selftest") {   // negative control of the checked build: record `value` violations of kind 7 through the same macro the kernels use
@@ -988,7 +993,8 @@ static int32_t scene_upload_single(rtx_ctx* ctx, const rtx_scene_desc* d) {
 #define WANT(vec, field) want((vec).data(), (vec).size() * sizeof((vec)[0]), (const void**)&(field))
         const size_t bNodes = pad(nodes.size() * sizeof(Node4)), bTris = pad((size_t)totalTris * RTX_TRI_D * sizeof(double)), bSph = pad(sph.size() * sizeof(double)),
                      bQuads = pad(quads.size() * sizeof(double)), bInfo = pad((size_t)totalTris * sizeof(int4));
-        const size_t geom = std::max<size_t>(bNodes + bTris + bSph + bQuads, 256);
+        const size_t bTris32 = (hasMesh && ctx->tri_pretest) ? pad((size_t)totalTris * 3 * sizeof(float4)) : 0;   // float32 pre-test records (mesh worlds)
+        const size_t geom = std::max<size_t>(bNodes + bTris + bSph + bQuads + bTris32, 256);
         WANT(entries, S.entries); WANT(unbounded, S.unbounded); WANT(sphMat, S.sph_mat); WANT(quadMat, S.quad_mat); WANT(planes, S.planes); WANT(planeMat, S.plane_mat);
         WANT(circles, S.circles); WANT(circleMat, S.circle_mat); WANT(perlinVec, S.perlin_vec); WANT(perlinPerm, S.perlin_perm);
         WANT(imgRgb, S.img_rgb); WANT(imgDim, S.img_dim); WANT(flatSimple, S.flat_simple); WANT(flatComplex, S.flat_complex);
@@ -1028,6 +1034,12 @@ static int32_t scene_upload_single(rtx_ctx* ctx, const rtx_scene_desc* d) {
         S.spheres = (const double*)(base + bNodes + bTris);
         S.quads = (const double*)(base + bNodes + bTris + bSph);
         S.tri_info = infoDev;
+        S.tris32 = nullptr;
+        if (bTris32 && totalTris > 0) {   // derived on the device from the float64 records just placed
+            float4* t32 = (float4*)(base + bNodes + bTris + bSph + bQuads);
+            k_tris32<<<(totalTris + 255) / 256, 256, 0, ctx->stream>>>(S.tris, totalTris, t32);
+            S.tris32 = t32;
+        }
         for (const Item& it : items) {
             char* dst = L.take(std::max<size_t>(it.bytes, 16));
             if (!dst) return fail(ctx, RTX_ERR_CUDA, "scene slab exhausted");
@@ -1286,8 +1298,6 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
         if (need > ctx->per_sample_cap) {
             CU(cudaStreamSynchronize(st));
             if (ctx->per_sample) cudaFree(ctx->per_sample);
-    if (ctx->rank_cache) cudaFree(ctx->rank_cache);
-    if (ctx->hash_dev) cudaFree(ctx->hash_dev);
             ctx->per_sample = nullptr; ctx->per_sample_cap = 0;
             CU(cudaMalloc((void**)&ctx->per_sample, need * sizeof(float4)));
             ctx->per_sample_cap = need;
@@ -1329,11 +1339,12 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
     // rays in flight (the survivor count of the last polled iteration). Grids are then sized for that bound instead of for the pool:
     // a launch of 1036 persistent blocks (or 1184 stream blocks) for a few thousand rays is mostly block scheduling.
     int activeBound = P;
+    const int drainPerBlock = getenv("RTX_DRAIN_PER_BLOCK") ? std::max(1, atoi(getenv("RTX_DRAIN_PER_BLOCK"))) : RTX_DRAIN_PER_BLOCK_DEFAULT;
     for (;;) {
         int used = 0;
         auto shrink = [&](int fullGrid, int perBlock) { return std::max(1, std::min(fullGrid, (int)(((long long)activeBound + perBlock - 1) / perBlock))); };
         const bool smallBatch = !ctx->scene_flat && !ctx->fuse_tree && ctx->count_stats == 0 && ctx->S.n_images == 0 && activeBound <= ctx->simple_below;
-        const int gStreamB = shrink(gridStream, 256), gTraceB = shrink(gridTrace, 32), gLucyB = shrink(ctx->trace_grid_lucy, 32), gSkyB = shrink(ctx->trace_grid_sky, 32);
+        const int gStreamB = shrink(gridStream, 256), gTraceB = shrink(gridTrace, drainPerBlock), gLucyB = shrink(ctx->trace_grid_lucy, drainPerBlock), gSkyB = shrink(ctx->trace_grid_sky, drainPerBlock);
         for (int b = 0; b < BATCH; b++, iter++) {
             const int cur = (int)(iter & 1);   // rec[cur]: this iteration's paths; rec[cur ^ 1]: where k_shade writes the survivors
             cudaEvent_t* ev = timing ? &ctx->events[4 + (size_t)b * EV_KINDS * 2] : nullptr;

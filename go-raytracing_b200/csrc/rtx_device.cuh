@@ -132,6 +132,8 @@ struct DevScene {
     const int* quad_mat;
     const double* tris;     // 12 doubles (96 B, 3 x LDG.256): v0, e1 = v1-v0, e2 = v2-v0, unit normal (rt/triangle.go:19-25)
     const int4* tri_info;   // x: primitive id inside its geometry (face order), y: material, z: rank, w: -
+    const float4* tris32;   // 3 x float4 (48 B) per triangle, same order as `tris`: (v0, M_v0) (e1, M_e1) (e2, M_e2) rounded to float32, M = largest
+                            // |component| — the record of the conservative float32 pre-test (tri_pretest_reject); NULL: no pre-test
     const double* planes;   // 8 doubles: point, normal, -,-
     const int* plane_mat;
     const double* circles;  // 8 doubles: center, unit normal, radius, D = normal . center (rt/circle.go:14-20)
@@ -354,6 +356,39 @@ __device__ __forceinline__ double isect_tri(const double* tp, const RayD& r, dou
     if (uv) { uv[0] = u; uv[1] = v; }
     return f * dot(e2, q);
 }
+// Conservative float32 pre-test of a triangle (48-byte float32 record, the float64 record only "when a candidate is
+// (re)tested in double"): true = the float64 test of rt/triangle.go:57-104 CERTAINLY rejects this ray for the interval [tmin, tmax], so
+// the 96-byte float64 record need not be fetched. The same Moller-Trumbore terms in float32, each compared against its acceptance bound
+// with an error margin. Margins (u = 2^-24; M_x = largest |component| of x; Ms = M_o + M_v0 bounds |o - v0|): rounding the float64 inputs
+// to float32, the products and the sums give |da| <= 48u Md Me1 Me2, |dU| <= 60u Ms Md Me2, |dV| <= 60u Ms Md Me1, |dT| <= 60u Ms Me1 Me2
+// (first order); the margins below use 128u = 2^-17... i.e. K = 64 x 2^-23, more than twice that. A NaN or an infinity anywhere makes
+// every comparison false: not rejected, the float64 test decides. |a| inside its margin: undecidable, the float64 test decides (it rejects
+// |a| < 1e-8 itself). tmin_f <= tmin and tmax_f >= tmax (rounded outward by the caller).
+#define RTX_TRI_PRETEST_K 7.62939453e-6f   /* 64 * 2^-23 */
+__device__ __forceinline__ bool tri_pretest_reject(const float4* __restrict__ t32, float ox, float oy, float oz, float dx, float dy, float dz, float Mo, float Md,
+                                                   float tmin_f, float tmax_f) {
+    const float4 A = __ldg(t32), B = __ldg(t32 + 1), C = __ldg(t32 + 2);
+    const float hx = dy * C.z - dz * C.y, hy = dz * C.x - dx * C.z, hz = dx * C.y - dy * C.x;
+    const float a = B.x * hx + B.y * hy + B.z * hz;
+    const float sx = ox - A.x, sy = oy - A.y, sz = oz - A.z;
+    const float U = sx * hx + sy * hy + sz * hz;
+    const float qx = sy * B.z - sz * B.y, qy = sz * B.x - sx * B.z, qz = sx * B.y - sy * B.x;
+    const float V = dx * qx + dy * qy + dz * qz;
+    const float Tt = C.x * qx + C.y * qy + C.z * qz;
+    const float Ms = Mo + A.w, k = RTX_TRI_PRETEST_K;
+    const float eA = k * Md * B.w * C.w + 1e-30f, eU = k * Md * C.w * Ms + 1e-30f, eV = k * Md * B.w * Ms + 1e-30f, eT = k * B.w * C.w * Ms + 1e-30f;
+    const float aa = fabsf(a);
+    if (!(aa > eA)) return false;
+    const float Us = a > 0.f ? U : -U, Vs = a > 0.f ? V : -V, Ts = a > 0.f ? Tt : -Tt;
+    if (Us < -eU) return true;                              // u < 0
+    if (Us > aa + eU + eA) return true;                     // u > 1
+    if (Vs < -eV) return true;                              // v < 0
+    if (Us + Vs > aa + eU + eV + eA) return true;           // u + v > 1
+    if (Ts < tmin_f * (aa - eA) - eT) return true;          // t < tmin
+    if (Ts > tmax_f * (aa + eA) + eT) return true;          // t > tmax
+    return false;
+}
+
 // rt/plane.go:24-34 (open interval applied by the caller)
 __device__ __forceinline__ double isect_plane(const double* p, const RayD& r) {
     D3 n = ld3(p + 3), o = d3(r.ox, r.oy, r.oz), d = d3(r.dx, r.dy, r.dz);

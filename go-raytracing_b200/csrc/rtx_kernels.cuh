@@ -979,6 +979,21 @@ __global__ void __launch_bounds__(256) k_connect_flat(Ctl* ctl, Pool pool, int p
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->shadow_rays, (unsigned long long)n);
 }
 
+// ---- scene upload: the float32 pre-test records from the float64 triangle records (tri_pretest_reject, rtx_device.cuh) ----------------------
+__global__ void __launch_bounds__(256) k_tris32(const double* tris, int n, float4* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* t = tris + RTX_TRI_D * (size_t)i;   // v0, e1, e2, n
+    float4 r[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float x = (float)t[3 * k], y = (float)t[3 * k + 1], z = (float)t[3 * k + 2];
+        const double m = fmax(fabs(t[3 * k]), fmax(fabs(t[3 * k + 1]), fabs(t[3 * k + 2])));
+        r[k] = make_float4(x, y, z, __double2float_ru(m));
+    }
+    out[3 * (size_t)i] = r[0]; out[3 * (size_t)i + 1] = r[1]; out[3 * (size_t)i + 2] = r[2];
+}
+
 // ---- K6a: end of a pass — every pixel received `spp` samples; with moments, fold the per-sample sums into sum and sum of squares ----
 __global__ void __launch_bounds__(256) k_pass_finish(float4* accum, float4* accum_sq, const float4* per_sample, int npix, int spp, int moments) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
