@@ -305,6 +305,7 @@ def main():
         for k in range(2):
             t0 = time.perf_counter()
             sc2 = grt.config_scene(args.workload, width=args.width or None, spp=args.spp or None, depth=args.depth or None)
+            ctx.set_option("drop_caches", 1)         # a cold upload derives the mesh's test order again
             t1 = time.perf_counter()
             ctx.load(sc2)
             t2 = time.perf_counter()

@@ -414,6 +414,7 @@ static int32_t set_option_single(rtx_ctx* ctx, const char* key, int64_t value) {
         ctx->pretest_bare = (int)value;
     }
     else if (k == "shade_direct") ctx->shade_direct = value != 0;
+    else if (k == "drop_caches") ctx->rank_cache_valid = false;   // forget what earlier uploads left behind (the cached test-order ranks): the next upload is a cold one
     else if (k == "tri_pretest") ctx->tri_pretest = value != 0;
     else if (k == "simple_below") ctx->simple_below = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 30));
 #ifdef RTX_CHECKED
