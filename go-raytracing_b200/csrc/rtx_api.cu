@@ -23,6 +23,9 @@
 #ifndef RTX_PRETEST_BARE_DEFAULT
 #define RTX_PRETEST_BARE_DEFAULT 0
 #endif
+#ifndef RTX_FUSE_DRAIN_DEFAULT
+#define RTX_FUSE_DRAIN_DEFAULT (1 << 19)
+#endif
 #ifndef RTX_DRAIN_PER_BLOCK_DEFAULT
 #define RTX_DRAIN_PER_BLOCK_DEFAULT 32   /* rays per block the persistent grids of the drain are sized for */
 #endif
@@ -104,6 +107,7 @@ struct rtx_ctx {
     int flat_max_entries = 16, scene_flat = 0, scene_has_mesh = 0;   // worlds of <= flat_max_entries entries without a mesh are traced by the flat kernels (trace_flat)
     int pixel_major = 1;  // path order of k_generate: all samples of a pixel consecutively (1) or sample-major (0)
     int tri_pretest = RTX_TRI_PRETEST;      // mesh worlds: float32 pre-test records for the TRI phase (takes effect at the next rtx_scene_upload)
+    int fuse_drain = RTX_FUSE_DRAIN_DEFAULT;   // hierarchy worlds: the last iterations of a pass run as ONE barrier-free persistent launch (k_drain) once at most this many rays are left (0 = off)
     int shade_direct = RTX_SHADE_DIRECT_DEFAULT;   // hierarchy worlds: k_shade in stream order instead of through material-sorted queues
     int simple_below = RTX_SIMPLE_BELOW_DEFAULT;   // hierarchy worlds: iterations of the drain with at most this many rays run the one-thread-per-ray trace kernels (0 = never)
     int tlas_flat_max = RTX_TLAS_FLAT_MAX;   // mesh worlds with at most this many bounded entries: top level as a per-ray sorted list (0 = hierarchy)
@@ -242,7 +246,7 @@ int32_t rtx_create(int32_t device_id, rtx_ctx** out) {
         const std::vector<const void*> kernels = group == 0
             ? std::vector<const void*>{(const void*)k_extend<false>, (const void*)k_extend<true>, (const void*)k_extend<false, true>, (const void*)k_connect<false>,
                                  (const void*)k_connect<true>, (const void*)k_trace_closest<>, (const void*)k_bounce<false>, (const void*)k_bounce<true>,
-                                 (const void*)k_bounce<false, true>}
+                                 (const void*)k_bounce<false, true>, (const void*)k_drain<false>, (const void*)k_drain<true>}
             : group == 1 ? std::vector<const void*>{(const void*)k_extend<false, false, RTX_FV_SKY>, (const void*)k_connect<false, RTX_FV_SKY>, (const void*)k_trace_closest<RTX_FV_SKY>}
                          : std::vector<const void*>{(const void*)k_extend<false, false, RTX_FV_LUCY>, (const void*)k_connect<false, RTX_FV_LUCY>, (const void*)k_trace_closest<RTX_FV_LUCY>};
         // developer knob: shared-memory carve-out in KB (the rest of the 256 KB array is L1); fewer resident blocks, more L1
@@ -414,6 +418,7 @@ static int32_t set_option_single(rtx_ctx* ctx, const char* key, int64_t value) {
         ctx->pretest_bare = (int)value;
     }
     else if (k == "shade_direct") ctx->shade_direct = value != 0;
+    else if (k == "fuse_drain") ctx->fuse_drain = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 26));
     else if (k == "drop_caches") ctx->rank_cache_valid = false;   // forget what earlier uploads left behind (the cached test-order ranks): the next upload is a cold one
     else if (k == "tri_pretest") ctx->tri_pretest = value != 0;
     else if (k == "simple_below") ctx->simple_below = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 30));
@@ -1340,13 +1345,16 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
     // rays in flight (the survivor count of the last polled iteration). Grids are then sized for that bound instead of for the pool:
     // a launch of 1036 persistent blocks (or 1184 stream blocks) for a few thousand rays is mostly block scheduling.
     int activeBound = P;
+    long long iterGenDone = -1;
     const int drainPerBlock = getenv("RTX_DRAIN_PER_BLOCK") ? std::max(1, atoi(getenv("RTX_DRAIN_PER_BLOCK"))) : RTX_DRAIN_PER_BLOCK_DEFAULT;
     for (;;) {
         int used = 0;
         auto shrink = [&](int fullGrid, int perBlock) { return std::max(1, std::min(fullGrid, (int)(((long long)activeBound + perBlock - 1) / perBlock))); };
         const bool smallBatch = !ctx->scene_flat && !ctx->fuse_tree && ctx->count_stats == 0 && ctx->S.n_images == 0 && activeBound <= ctx->simple_below;
         const int gStreamB = shrink(gridStream, 256), gTraceB = shrink(gridTrace, drainPerBlock), gLucyB = shrink(ctx->trace_grid_lucy, drainPerBlock), gSkyB = shrink(ctx->trace_grid_sky, drainPerBlock);
-        for (int b = 0; b < BATCH; b++, iter++) {
+        // iterations per host poll: 16 while camera paths are still generated; 4 once the stream only shrinks, so that the drain starts promptly
+        const int batchN = (ctx->fuse_drain > 0 && iterGenDone >= 0 && !ctx->scene_flat) ? 4 : BATCH;
+        for (int b = 0; b < batchN; b++, iter++) {
             const int cur = (int)(iter & 1);   // rec[cur]: this iteration's paths; rec[cur ^ 1]: where k_shade writes the survivors
             cudaEvent_t* ev = timing ? &ctx->events[4 + (size_t)b * EV_KINDS * 2] : nullptr;
             if (pending[cur]) { CUL(cudaStreamWaitEvent(st, ctx->ev_connected[cur], 0)); pending[cur] = false; }
@@ -1456,6 +1464,39 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
                     msKind[2], msKind[3], ctx->ctl_host->n_active, ctx->ctl_host->n_next, ctx->ctl_host->n_shadow[0], ctx->ctl_host->cursor);
         if (ctx->ctl_host->done) break;
         activeBound = ctx->ctl_host->cursor >= ctx->ctl_host->total ? std::max(ctx->ctl_host->n_next, 1) : P;
+        if (ctx->ctl_host->cursor >= ctx->ctl_host->total && iterGenDone < 0) iterGenDone = iter;   // every live path was generated before this iteration
+        // ---- the barrier-free drain: ONE persistent launch for all remaining bounces (k_drain, rtx_kernels.cuh) ------------------------------
+        // Its shadow requests all go to one half of the shadow buffer: every live path has at least (iter - iterGenDone) bounces behind it, so
+        // there are at most n_next x (max_depth - (iter - iterGenDone)) x requests-per-hit of them — the drain starts when that fits.
+        if (ctx->fuse_drain > 0 && iterGenDone >= 0 && !ctx->scene_flat && !ctx->fuse_tree && ctx->count_stats == 0 && ctx->ctl_host->n_next > 0) {
+            const long long remaining = std::max<long long>(1, (long long)max_depth - (iter - iterGenDone));
+            // (both halves of the shadow buffer, 2 x pool_has_shadow x P requests, hold them: the connect launches of earlier iterations are joined first)
+            const long long perHit = 1 + ((ctx->S.env_w > 0 && ctx->S.env_is) ? 1 : 0);
+            if (ctx->ctl_host->n_next <= ctx->fuse_drain &&
+                (ctx->S.n_lights == 0 || (long long)ctx->ctl_host->n_next * remaining * perHit <= 2ll * ctx->pool_has_shadow * (long long)P)) {
+                const int cur = 0;   // the drain's shadow requests start at the beginning of the buffer; cur_connect[0] / n_shadow[0] count them
+                for (int c = 0; c < 2; c++)
+                    if (pending[c]) { CUL(cudaStreamWaitEvent(st, ctx->ev_connected[c], 0)); pending[c] = false; }
+                Pool poolI = pool;
+                const int recCur = (int)(iter & 1);   // rec[recCur] holds the survivors of the last iteration
+                k_drain_begin<<<1, 32, 0, st>>>(ctx->ctl, cur);
+                if (ctx->S.n_images > 0) k_drain<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, recCur, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
+                else k_drain<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, recCur, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
+                if (ctx->S.n_lights > 0) {   // the shadow requests of the whole drain, one launch
+                    if (lean == 1) k_connect<false, RTX_FV_LUCY><<<ctx->trace_grid_lucy, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_LUCY), st>>>(ctx->ctl, poolI, cur, ctx->S, pp, ctx->trace_spill);
+                    else if (lean == 2) k_connect<false, RTX_FV_SKY><<<ctx->trace_grid_sky, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_SKY), st>>>(ctx->ctl, poolI, cur, ctx->S, pp, ctx->trace_spill);
+                    else k_connect<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, cur, ctx->S, pp, ctx->trace_spill);
+                    launches++;
+                }
+                k_drain_end<<<1, 32, 0, st>>>(ctx->ctl);
+                launches += 3;
+                for (int c = 0; c < 2; c++)
+                    if (pending[c]) { CUL(cudaStreamWaitEvent(st, ctx->ev_connected[c], 0)); pending[c] = false; }
+                CUL(cudaMemcpyAsync(ctx->ctl_host, ctx->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+                CUL(cudaStreamSynchronize(st));
+                break;
+            }
+        }
     }
     if (spp > 0) {
         k_pass_finish<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(ctx->accum, ctx->accum_sq, ctx->per_sample, (int)npix, spp, ctx->moments);

@@ -238,7 +238,7 @@ extern __shared__ __align__(16) unsigned char rtx_smem[];  // the trace kernels'
 // ---- K2: extend — closest hit of every active path, then binning into material-sorted shading queues -------------
 template <bool UV, unsigned FEAT = RTX_F_ALL>
 struct ExtendPolicyT {
-    static constexpr bool ANY_HIT = false;
+    static constexpr bool ANY_HIT = false, CONTINUES = false;
     Ctl* ctl; char* hit; int* q_mat; int capacity; const char* rec; const DevScene* S; uint32_t seed_lo, seed_hi; int direct;
     __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:451
     __device__ __forceinline__ void prefetch(int job) const {
@@ -775,7 +775,7 @@ __global__ void __launch_bounds__(256, FEAT != RTX_F_ALL ? RTX_SHADE_BLOCKS_LEAN
 // are HBM-bound (profiles/r01_k_shade_hdri.md) — at the price of shading without material-sorted warps.
 template <bool UV, unsigned FEAT = RTX_F_ALL>
 struct BouncePolicyT {
-    static constexpr bool ANY_HIT = false;
+    static constexpr bool ANY_HIT = false, CONTINUES = false;
     Ctl* ctl; Pool pool; int cur; const DevScene* S; const DevCamera* C; PassParams pp;
     int n_cont; unsigned long long gen_base;   // jobs >= n_cont are fresh camera paths: generated here, never written as records
     mutable double pixbits_; mutable float4 th_;   // identity and throughput | flags of the job this thread is working on (load -> retire)
@@ -852,15 +852,15 @@ __global__ void __launch_bounds__(256, (FEAT & RTX_F_COMPLEX) ? RTX_BOUNCE_BLOCK
 // stream runs inside the latency-bound traversal instead of after it. The material code is one out-of-line call (bounce_shade), so the
 // traversal loop keeps its registers; what the call needs travels through local memory.
 template <bool UV>
-__device__ __noinline__ void bounce_shade(const DevScene* S, const DevCamera* C, const PassParams* pp, const Pool* pool, const char* rec, const RayD* rp,
+__device__ __noinline__ void bounce_shade(const DevScene* S, const DevCamera* C, const PassParams* pp, const Pool* pool, double pixbits, float4 th, const RayD* rp,
                                           const Best* bp, ShadeVars* Vp) {
     const RayD r = *rp;
     const Best b = *bp;
     ShadeVars V;
     V.reset();
     V.tm = r.tm;
-    V.pixbits = *reinterpret_cast<const double*>(rec + 56);
-    V.th = ldrec4(rec + 64);
+    V.pixbits = pixbits;
+    V.th = th;
     int type = Q_MISS;
     HitInfo hi;
     hi.P = hi.N = d3(0, 0, 0); hi.mat = 0; hi.front = false; hi.u = hi.v = 0;
@@ -875,7 +875,7 @@ __device__ __noinline__ void bounce_shade(const DevScene* S, const DevCamera* C,
 }
 template <bool UV>
 struct BounceTreePolicyT {
-    static constexpr bool ANY_HIT = false;
+    static constexpr bool ANY_HIT = false, CONTINUES = false;
     Ctl* ctl; const Pool* pool; int cur; const DevScene* S; const DevCamera* C; const PassParams* pp; const char* rec;
     __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:451
     __device__ __forceinline__ void prefetch_far(int) const {}
@@ -894,8 +894,10 @@ struct BounceTreePolicyT {
     }
     __device__ __forceinline__ void retire(int job, bool valid, const RayD& r, const Best& b) const {
         ShadeVars V;
-        if (valid) bounce_shade<UV>(S, C, pp, pool, rec + (size_t)job * RTX_REC_BYTES, &r, &b, &V);
-        else V.reset();
+        if (valid) {
+            const char* q = rec + (size_t)job * RTX_REC_BYTES;
+            bounce_shade<UV>(S, C, pp, pool, ld256d(q + 32).w, ldrec4(q + 64), &r, &b, &V);
+        } else V.reset();
         shade_commit(ctl, *pool, cur, V);
     }
 };
@@ -910,9 +912,109 @@ __global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_bounce(
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->ext_rays, (unsigned long long)n);
 }
 
+// ---- the barrier-free drain of a pass (option fuse_drain) ------------------------------------------------------------------------------
+// Once a pass has generated its last camera path the stream only shrinks, and the wavefront loop runs mid-size batches (1 M ... 50 K rays) through
+// persistent launches that cannot finish faster than the ~60 rounds their slowest lanes need: 7.6 ms per pass at half rate.
+// Here ONE persistent launch finishes all remaining bounces. Its jobs are the survivors the last regular iteration left in rec[cur] (a static
+// queue); a ray that retires is shaded on the spot (bounce_shade, as k_bounce) and, when its path goes on, the next ray TAKES OVER THE SLOT
+// (Policy::CONTINUES in trace_persistent): no barrier between bounces, no queue traffic, and the drain lasts as long as the longest chain of paths
+// one slot gets. The path's record is updated in place (an instance exit re-reads the world ray from it). Shadow requests are collected and
+// traced by one k_connect launch afterwards. Same shade_element, same Philox counters: the same paths as the iteration loop would trace.
+template <bool UV>
+struct DrainPolicyT {
+    static constexpr bool ANY_HIT = false, CONTINUES = true;
+    Ctl* ctl; const Pool* pool; int cur; int par; const DevScene* S; const DevCamera* C; const PassParams* pp;   // cur: record buffer of the jobs; par: shadow counter
+    __device__ __forceinline__ double tmin() const { return 0.001; }
+    __device__ __forceinline__ char* record(int job) const { return pool->records(cur) + (size_t)job * RTX_REC_BYTES; }
+    // records are rewritten during the launch by whichever warp of the block retires the slot: read past L1
+    __device__ __forceinline__ static D4 ld256v(const void* p) {
+        D4 r;
+        asm volatile("ld.volatile.global.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+        asm volatile("ld.volatile.global.v2.f64 {%0,%1}, [%2];" : "=d"(r.z), "=d"(r.w) : "l"((const char*)p + 16) : "memory");
+        return r;
+    }
+    __device__ __forceinline__ static float4 ld128v(const void* p) {
+        float4 r;
+        asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+        return r;
+    }
+    __device__ __forceinline__ void load(int job, RayD& r, double& tmax) const {
+        const char* q = record(job);
+        const D4 a = ld256v(q), c = ld256v(q + 32);
+        r.ox = a.x; r.oy = a.y; r.oz = a.z; r.tm = a.w; r.dx = c.x; r.dy = c.y; r.dz = c.z;
+        tmax = RTX_INF_D;
+    }
+    __device__ __forceinline__ void prefetch_far(int) const {}
+    __device__ __forceinline__ VolumeRng volume_rng(int job) const {
+        const char* q = record(job);
+        const unsigned long long ps = (unsigned long long)__double_as_longlong(ld256v(q + 32).w);
+        const int bounce = __float_as_int(ld128v(q + 64).w) & 0xffff;
+        VolumeRng vr; vr.k0 = pp->seed_lo; vr.k1 = pp->seed_hi; vr.c0 = (uint32_t)ps; vr.c1 = (uint32_t)(ps >> 32); vr.c2 = (uint32_t)bounce * 4u; vr.transparent = false;
+        return vr;
+    }
+    // warp-collective; returns whether this lane's path goes on, with its next ray in r_next (and in its record)
+    __device__ __forceinline__ bool retire_continue(int job, bool valid, const RayD& r, const Best& b, RayD& r_next) const {
+        ShadeVars V;
+        if (valid) {
+            const char* q = record(job);
+            bounce_shade<UV>(S, C, pp, pool, ld256v(q + 32).w, ld128v(q + 64), &r, &b, &V);
+        } else V.reset();
+        const unsigned am = __activemask();
+        const unsigned me = __ballot_sync(am, V.has_env), ma = __ballot_sync(am, V.has_area), mv = __ballot_sync(am, valid);
+        const int lane = threadIdx.x & 31, leader = __ffs(am) - 1;
+        int bs = 0;
+        if (lane == leader) {
+            if (me | ma) bs = atomicAdd(&ctl->n_shadow[par], __popc(me) + __popc(ma));
+            if (mv) atomicAdd(&ctl->ext_rays, (unsigned long long)__popc(mv));
+        }
+        bs = __shfl_sync(am, bs, leader);
+        const unsigned below = (1u << lane) - 1u;
+        if (V.has_env) {
+            char* q = pool->shadow + (size_t)(bs + __popc(me & below)) * RTX_SHADOW_BYTES;
+            st256d(q, V.P.x, V.P.y, V.P.z, RTX_INF_D);
+            st256d(q + 32, V.env_dir.x, V.env_dir.y, V.env_dir.z, V.pixbits);
+            strec4(q + 64, make_float4(V.env_c.x, V.env_c.y, V.env_c.z, __int_as_float(V.bounce0)));
+        }
+        if (V.has_area) {
+            char* q = pool->shadow + (size_t)(bs + __popc(me) + __popc(ma & below)) * RTX_SHADOW_BYTES;
+            st256d(q, V.P.x, V.P.y, V.P.z, V.area_tmax);
+            st256d(q + 32, V.area_dir.x, V.area_dir.y, V.area_dir.z, V.pixbits);
+            strec4(q + 64, make_float4(V.area_c.x, V.area_c.y, V.area_c.z, __int_as_float(V.bounce0)));
+        }
+        if (V.cont) {   // the path's record, in place: its next ray, its throughput and bounce count
+            char* out = record(job);
+            st256d(out, V.P.x, V.P.y, V.P.z, V.tm);
+            st256d(out + 32, V.nd.x, V.nd.y, V.nd.z, V.pixbits);
+            strec4(out + 64, V.th);
+            __threadfence_block();
+            r_next.ox = V.P.x; r_next.oy = V.P.y; r_next.oz = V.P.z; r_next.dx = V.nd.x; r_next.dy = V.nd.y; r_next.dz = V.nd.z; r_next.tm = V.tm;
+        }
+        return V.cont;
+    }
+};
+template <bool UV = false>
+__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_drain(Ctl* ctl, const __grid_constant__ Pool pool, int cur, int par, const __grid_constant__ DevScene S,
+                                                                              const __grid_constant__ DevCamera C, const __grid_constant__ PassParams pp, int* spill) {
+    DrainPolicyT<UV> P{ctl, &pool, cur, par, &S, &C, &pp};
+    TraceCounters tc = {0, 0, 0, 0, 0};
+    trace_persistent<DrainPolicyT<UV>, false, RTX_TRACE_SLOTS>(S, P, &ctl->cur_extend, ctl->n_next, tc, spill, rtx_smem);
+}
+// before the drain: job cursor and shadow half; after it (and its k_connect): the books of the pass
+__global__ void k_drain_begin(Ctl* ctl, int par) {
+    if (threadIdx.x != 0) return;
+    ctl->cur_extend = 0; ctl->n_shadow[par] = 0; ctl->cur_connect[par] = 0;
+    if (ctl->t_tail_begin == 0) ctl->t_tail_begin = rtx_globaltimer();
+}
+__global__ void k_drain_end(Ctl* ctl) {
+    if (threadIdx.x != 0) return;
+    ctl->n_next = 0; ctl->n_active = 0; ctl->done = 1;
+    ctl->iterations += 1; ctl->tail_iterations += 1;
+    if (ctl->t_end == 0) ctl->t_end = rtx_globaltimer();
+}
+
 // ---- K3: connect — shadow rays of next-event estimation (any hit in [0.001, tmax]) ----------------------------------
 struct ConnectPolicy {
-    static constexpr bool ANY_HIT = true;
+    static constexpr bool ANY_HIT = true, CONTINUES = false;
     Pool pool; uint32_t seed_lo, seed_hi;
     __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:579, :636
     __device__ __forceinline__ void prefetch(int job) const {
@@ -1031,7 +1133,7 @@ __global__ void k_resolve_rgba8(const float4* accum, int npix, double scale, uch
 // ---- batch entry points for the parity tests ----------------------------------------------------------------------------
 template <unsigned FEAT = RTX_F_ALL>
 struct BatchPolicyT {
-    static constexpr bool ANY_HIT = false;
+    static constexpr bool ANY_HIT = false, CONTINUES = false;
     const DevScene* S; const double* rays; double t0, t1;
     int* entry_id; int* prim_id; double* t; double* normal; unsigned char* front; double* uv; double* p;
     __device__ __forceinline__ double tmin() const { return t0; }

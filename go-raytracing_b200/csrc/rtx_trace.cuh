@@ -166,9 +166,6 @@ struct Best {
 #ifndef RTX_SORT_FULL
 #define RTX_SORT_FULL 1   /* NODE phase: 1 = the four children of a node fully ordered front to back, 0 = only the nearest in front (3 of the 5 compare-exchanges) */
 #endif
-#ifndef RTX_EARLY_LOAD
-#define RTX_EARLY_LOAD 0
-#endif
 #define RTX_PH_N 0
 #define RTX_PH_T 1
 #define RTX_PH_E 2
@@ -793,23 +790,20 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
         } else {
             // ---- RETIRE + REFILL (warp-collective; one slot per lane per round) ---------------------------------------
             const bool fin = mine && T.node[s] == RTX_ST_DONE;
-            // The ticket for the rays this round will load is drawn FIRST (RTX_EARLY_TICKET): every claimed slot is refilled, so the count is known,
-            // and the atomic's round trip to L2 (~700 cycles) then runs under the retire work below instead of in front of the refill.
             bool exhausted = __any_sync(FULL, dry[0] != 0);
-            const unsigned want = __ballot_sync(FULL, mine);
-            const int cnt = __popc(want);
-            int base = 0;
-            if (RTX_EARLY_TICKET && !exhausted && lane == 0) base = atomicAdd(cursor, cnt);
-#if RTX_EARLY_LOAD
-            // ... and so are the new rays' records (RTX_EARLY_LOAD): a DRAM read of the path stream, requested before the retire work, used after it
-            RayD r_new; double tmax_new = 0;
-            int my_new = -1;
-            if (!exhausted) {
-                base = __shfl_sync(FULL, base, 0);
-                my_new = base + __popc(want & ((1u << lane) - 1u));
-                if (mine && my_new < njobs) P.load(my_new, r_new, tmax_new);
+            // Policy::CONTINUES (the drain of a pass, k_drain): a retiring ray is shaded on the spot and, when its path goes on, the NEXT ray of
+            // the path takes over the slot — no ticket, no record round trip; only lanes whose path ended draw a ticket for a new path.
+            bool cont_lane = false;
+            RayD r_cont;
+            unsigned want = 0;
+            int cnt = 0, base = 0;
+            if constexpr (!Policy::CONTINUES) {
+                // The ticket for the rays this round will load is drawn FIRST (RTX_EARLY_TICKET): every claimed slot is refilled, so the count is
+                // known, and the atomic's round trip to L2 (~700 cycles) then runs under the retire work below instead of in front of the refill.
+                want = __ballot_sync(FULL, mine);
+                cnt = __popc(want);
+                if (RTX_EARLY_TICKET && !exhausted && lane == 0) base = atomicAdd(cursor, cnt);
             }
-#endif
             {
                 RayD rw;
                 Best B;
@@ -823,32 +817,34 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                     if (T.cur[s] >= 0) P.load(job, rw, tmax_unused);  // an any-hit query may end inside an instance
                     else T.load_ray(s, rw);
                 }
-                P.retire(job, fin, rw, B);
+                if constexpr (Policy::CONTINUES) cont_lane = P.retire_continue(job, fin, rw, B, r_cont);
+                else P.retire(job, fin, rw, B);
             }
+            if constexpr (Policy::CONTINUES) {
+                want = __ballot_sync(FULL, mine && !cont_lane);
+                cnt = __popc(want);
+                if (!exhausted && cnt > 0 && lane == 0) base = atomicAdd(cursor, cnt);
+            }
+            const int job_held = (Policy::CONTINUES && cont_lane) ? T.job[s] : -1;
             if (mine) {
                 T.node[s] = RTX_ST_IDLE;
                 newst = RTX_PH_NONE;
             }
-            if (!exhausted) {
-                if (!RTX_EARLY_TICKET && lane == 0) base = atomicAdd(cursor, cnt);
-#if RTX_EARLY_LOAD
-                const int my = my_new;
-#else
-                base = __shfl_sync(FULL, base, 0);
-                const int my = base + __popc(want & ((1u << lane) - 1u));
-#endif
+            if (!exhausted || (Policy::CONTINUES && __any_sync(FULL, cont_lane))) {
+                if (!exhausted) {
+                    if (!Policy::CONTINUES && !RTX_EARLY_TICKET && lane == 0) base = atomicAdd(cursor, cnt);
+                    base = __shfl_sync(FULL, base, 0);
+                }
+                const int my = cont_lane ? job_held : (exhausted ? njobs : base + __popc(want & ((1u << lane) - 1u)));
                 RTX_CHECK(!mine || my >= 0, 7);
                 // the record a refill RTX_PREFETCH_DIST tickets from now will load (jobs are handed out in order): from DRAM into L2 meanwhile
-                if (RTX_PREFETCH_DIST > 0 && mine && my + RTX_PREFETCH_DIST < njobs) P.prefetch_far(my + RTX_PREFETCH_DIST);
-                if (mine && my < njobs) {
+                if (RTX_PREFETCH_DIST > 0 && mine && !cont_lane && my + RTX_PREFETCH_DIST < njobs) P.prefetch_far(my + RTX_PREFETCH_DIST);
+                if (mine && (cont_lane || my < njobs)) {
                     RayF f; Best B;
-#if RTX_EARLY_LOAD
-                    const RayD r = r_new; const double tmax = tmax_new;
-#else
                     RayD r;
                     double tmax;
-                    P.load(my, r, tmax);
-#endif
+                    if (Policy::CONTINUES && cont_lane) { r = r_cont; tmax = RTX_INF_D; }
+                    else P.load(my, r, tmax);
                     B.reset(tmax);
                     // entries tested for every ray: unbounded geometry (infinite Plane, rt/plane.go:17) and, with option pretest_bare, the
                     // few bare primitives beside a mesh (the Cornell walls) that rtx_scene_upload kept out of the TLAS
@@ -901,7 +897,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, Policy& P, i
                     T.node[s] = node; T.spb[4 * s + 3] = (unsigned char)sp; T.cur[s] = -1; T.job[s] = my;
                     newst = RTX_CLASSIFY(node, false);
                 }
-                if (base + cnt >= njobs) {
+                if (!exhausted && cnt > 0 && base + cnt >= njobs) {
                     exhausted = true;
                     if (lane == 0) dry[0] = 1;
                 }

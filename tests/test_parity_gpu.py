@@ -871,12 +871,14 @@ def test_small_batch_and_flat_top_level_are_result_neutral(grt, name, width, spp
     """Two ways the hierarchy worlds are traced besides the persistent kernel with a hierarchical top level: the drain of a pass runs a
     one-thread-per-ray kernel (option simple_below: here forced for EVERY iteration), and mesh worlds of <= 16 bounded entries take their
     top level as a per-ray sorted list (option tlas_flat_max: here switched off); k_shade walks the rays in stream order or through the
-    material-sorted queues (option shade_direct). Same primitive tests and tie rules, same Philox counters:
+    material-sorted queues (option shade_direct); the last iterations of a pass run as one barrier-free launch in which a path's next ray
+    takes over its slot (option fuse_drain). Same primitive tests and tie rules, same Philox counters:
     the same rays are traced, and the sums agree to float-atomic order."""
     sc = grt.config_scene(name, width=width, spp=spp, depth=depth)
     out = {}
     for key, opts in (("default", {}), ("simple", {"simple_below": 1 << 30, "flat_max_entries": 0}), ("hierarchy", {"tlas_flat_max": 0, "flat_max_entries": 0, "simple_below": 0}),
-                      ("stream-order shading", {"shade_direct": 1, "flat_max_entries": 0}), ("queue-order shading", {"shade_direct": 0, "flat_max_entries": 0})):
+                      ("stream-order shading", {"shade_direct": 1, "flat_max_entries": 0}), ("queue-order shading", {"shade_direct": 0, "flat_max_entries": 0}),
+                      ("no drain", {"fuse_drain": 0, "flat_max_entries": 0}), ("drain as early as it fits", {"fuse_drain": 1 << 26, "flat_max_entries": 0})):
         c = grt.Context(0)
         for k, v in opts.items():
             c.set_option(k, v)
@@ -887,6 +889,6 @@ def test_small_batch_and_flat_top_level_are_result_neutral(grt, name, width, spp
         c.close()
         assert np.all(n == spp)
         out[key] = (acc, st["extension_rays"], st["shadow_rays"])
-    for key in ("simple", "hierarchy", "stream-order shading", "queue-order shading"):
+    for key in ("simple", "hierarchy", "stream-order shading", "queue-order shading", "no drain", "drain as early as it fits"):
         assert out[key][1] == out["default"][1] and out[key][2] == out["default"][2], f"{name}: {key} traces a different number of rays"
         assert np.allclose(out[key][0], out["default"][0], rtol=5e-5, atol=2e-5), f"{name}: {key} changes the image"
