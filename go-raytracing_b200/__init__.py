@@ -94,7 +94,7 @@ ABI_SYMBOLS = [
     "rtx_create", "rtx_destroy", "rtx_last_error", "rtx_abi_version", "rtx_scene_upload", "rtx_camera_set", "rtx_image_size",
     "rtx_render_pass", "rtx_accum_clear", "rtx_accum_enable_moments", "rtx_accum_device_ptr", "rtx_resolve_rgba8", "rtx_resolve_accum",
     "rtx_trace_closest", "rtx_camera_rays", "rtx_hdri_sample", "rtx_hdri_pdf", "rtx_hdri_lookup", "rtx_hdri_total_power",
-    "rtx_get_stats", "rtx_set_option", "rtx_set_stream", "rtx_create_multi", "rtx_device_count",
+    "rtx_get_stats", "rtx_set_option", "rtx_set_stream", "rtx_create_multi", "rtx_device_count", "rtx_mesh_test_order",
 ]
 
 _lib_cache = None
@@ -660,6 +660,12 @@ class Context:
         v = C.c_double()
         self._check(self._L.rtx_hdri_total_power(self._h, C.byref(v)), "rtx_hdri_total_power")
         return v.value
+
+    def mesh_test_order(self, n_tris):
+        """rtx_mesh_test_order: the ranks the device derived for the mesh triangles of the scene just loaded."""
+        out = np.empty(int(n_tris), dtype=np.int32)
+        self._check(self._L.rtx_mesh_test_order(self._h, out.ctypes.data, int(n_tris)), "rtx_mesh_test_order")
+        return out
 
     def stats(self) -> dict:
         s = Stats()

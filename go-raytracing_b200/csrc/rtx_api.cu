@@ -131,7 +131,7 @@ struct rtx_ctx {
     cudaStream_t window_stream = nullptr; bool window_set = false;
     double ms_resolve = 0, ms_reduce = 0;
     // the test-order ranks the device derived for the last scene (rtx_rank_gpu.cuh), kept under a content hash of its triangle arrays
-    int* rank_cache = nullptr; size_t rank_cache_n = 0; unsigned long long rank_cache_key = 0; bool rank_cache_valid = false;
+    int* rank_cache = nullptr; size_t rank_cache_n = 0; unsigned long long rank_cache_key = 0; bool rank_cache_valid = false, ranks_from_device = false;
     unsigned long long* hash_dev = nullptr;
     int pool_has_shadow = 0, pool_hit_bytes = 0;   // what the allocated pool was sized for
     // rtx_create_multi: the context the caller holds is device_ids[0]'s; the other devices' contexts hang off it
@@ -276,6 +276,15 @@ int32_t rtx_create(int32_t device_id, rtx_ctx** out) {
         }
     }
     *out = ctx;
+    return RTX_OK;
+}
+int32_t rtx_mesh_test_order(rtx_ctx* ctx, int32_t* rank, int64_t n) {
+    if (!ctx || !rank || n < 0) return RTX_ERR_INVALID;
+    if (!ctx->have_scene || !ctx->rank_cache_valid || !ctx->ranks_from_device) return fail(ctx, RTX_ERR_STATE, "rtx_mesh_test_order: the last upload did not derive a test order on the device (tri_rank given, host build, or no mesh)");
+    if (n != (int64_t)ctx->rank_cache_n) return fail(ctx, RTX_ERR_INVALID, "rtx_mesh_test_order: the scene has %lld triangles, not %lld", (long long)ctx->rank_cache_n, (long long)n);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(rank, ctx->rank_cache, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return RTX_OK;
 }
 
@@ -517,6 +526,7 @@ static int32_t scene_upload_single(rtx_ctx* ctx, const rtx_scene_desc* d) {
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     free_scene(ctx);
+    ctx->ranks_from_device = false;
     DevScene S{};
 
     // ---- validation
@@ -722,6 +732,7 @@ static int32_t scene_upload_single(rtx_ctx* ctx, const rtx_scene_desc* d) {
         CU(cudaMemcpyAsync(dV1, d->tri_v1, 3 * nT * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(dV2, d->tri_v2, 3 * nT * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(dMat, d->tri_mat, nT * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->ranks_from_device = d->tri_rank == nullptr;
         if (d->tri_rank) {
             CU(cudaMemcpyAsync(dRank, d->tri_rank, nT * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         } else {

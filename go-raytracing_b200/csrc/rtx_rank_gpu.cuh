@@ -72,6 +72,52 @@ __global__ void k_axis(const double* cx, const double* cy, const double* cz, con
         axis[s] = (sz[0] > sz[1] && sz[0] > sz[2]) ? 0 : (sz[1] > sz[2] ? 1 : 2);
     }
 }
+// The few big segments of the top levels: PARTS blocks per segment, combined through 64-bit integer atomics on an order-preserving
+// image of the doubles (one block per segment took 0.46 ms for the 280 K-triangle root).
+#define RTX_RANK_WIDE_SEGS 16
+#define RTX_RANK_WIDE_PARTS 64
+__device__ inline unsigned long long ord_bits(double d) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ inline double ord_value(unsigned long long u) { return __longlong_as_double((long long)((u >> 63) ? (u & 0x7fffffffffffffffull) : ~u)); }
+__global__ void k_axis_init(unsigned long long* mm, int nseg) {
+    const int i = threadIdx.x;
+    if (i < nseg * 6) mm[i] = (i % 6) < 3 ? ~0ull : 0ull;
+}
+__global__ void k_axis_part(const double* cx, const double* cy, const double* cz, const int* seg_begin, const int* seg_end, unsigned long long* mm) {
+    const int s = blockIdx.x, b = seg_begin[s], m = seg_end[s] - b;
+    const int lo = b + (int)((long long)m * blockIdx.y / gridDim.y), hi = b + (int)((long long)m * (blockIdx.y + 1) / gridDim.y);
+    __shared__ double red[6][8];
+    double mn[3] = {1e308, 1e308, 1e308}, mx[3] = {-1e308, -1e308, -1e308};
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const double c[3] = {cx[i], cy[i], cz[i]};
+#pragma unroll
+        for (int a = 0; a < 3; a++) { mn[a] = fmin(mn[a], c[a]); mx[a] = fmax(mx[a], c[a]); }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fmin(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmax(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) for (int a = 0; a < 3; a++) { red[a][w] = mn[a]; red[3 + a][w] = mx[a]; }
+    __syncthreads();
+    if (threadIdx.x == 0 && hi > lo) {
+        for (int a = 0; a < 3; a++)
+            for (int k = 1; k < (int)blockDim.x / 32; k++) { mn[a] = fmin(mn[a], red[a][k]); mx[a] = fmax(mx[a], red[3 + a][k]); }
+        for (int a = 0; a < 3; a++) { atomicMin(&mm[s * 6 + a], ord_bits(mn[a])); atomicMax(&mm[s * 6 + 3 + a], ord_bits(mx[a])); }
+    }
+}
+__global__ void k_axis_finish(const unsigned long long* mm, int nseg, int* axis) {
+    const int s = threadIdx.x;
+    if (s >= nseg) return;
+    double sz[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) sz[a] = (ord_value(mm[s * 6 + 3 + a]) + 0.0001) - (ord_value(mm[s * 6 + a]) - 0.0001);
+    axis[s] = (sz[0] > sz[1] && sz[0] > sz[2]) ? 0 : (sz[1] > sz[2] ? 1 : 2);
+}
 __global__ void k_keys(const double* cx, const double* cy, const double* cz, const int* seg_begin, const int* axis, int nseg, int n_total, const int* seg_of, double* key, int* pos) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_total) return;
@@ -83,7 +129,7 @@ __global__ void k_keys(const double* cx, const double* cy, const double* cz, con
 }
 __global__ void k_mark_segments(const int* seg_begin, const int* seg_end, int nseg, int* seg_of) {
     const int s = blockIdx.x;
-    for (int i = seg_begin[s] + threadIdx.x; i < seg_end[s]; i += blockDim.x) seg_of[i] = s;
+    for (int i = seg_begin[s] + blockIdx.y * blockDim.x + threadIdx.x; i < seg_end[s]; i += blockDim.x * gridDim.y) seg_of[i] = s;
 }
 __global__ void k_gather(const int* pos, int n, const double* cx, const double* cy, const double* cz, const int* idx, double* ox, double* oy, double* oz, int* oidx) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -120,6 +166,7 @@ inline size_t scratch_bytes(int n) {
     b += 3 * ((size_t)n * sizeof(int) + pad);               // pos in / out, seg_of
     b += 2 * ((size_t)n * sizeof(int) + pad);               // segment begin / end (at most n / 2 segments per level)
     b += (size_t)n * sizeof(int) + pad;                     // axis per segment
+    b += RTX_RANK_WIDE_SEGS * 6 * sizeof(unsigned long long) + pad;   // centroid bounds of the wide top-level segments
     b += (size_t)n * 48 + (64u << 20);                      // cub temporary storage (segmented sort keeps copies of keys and values)
     return b;
 }
@@ -137,6 +184,7 @@ inline cudaError_t canonical_ranks(const double* v0, const double* v1, const dou
     int *posIn = (int*)take((size_t)n * sizeof(int)), *posOut = (int*)take((size_t)n * sizeof(int)), *segOf = (int*)take((size_t)n * sizeof(int));
     int *dBegin = (int*)take((size_t)n * sizeof(int)), *dEnd = (int*)take((size_t)n * sizeof(int));
     int* axis = (int*)take((size_t)(n / 2 + 1) * sizeof(int));
+    unsigned long long* mm = (unsigned long long*)take(RTX_RANK_WIDE_SEGS * 6 * sizeof(unsigned long long));
     char* cubTemp = sp;
     if (sp > scratch + scratch_size) return cudaErrorMemoryAllocation;
     const size_t cubBytesAvail = (size_t)(scratch + scratch_size - sp);
@@ -157,14 +205,27 @@ inline cudaError_t canonical_ranks(const double* v0, const double* v1, const dou
         if ((e = cudaMemcpyAsync(dBegin, keepAlive[keepAlive.size() - 2].data(), (size_t)nseg * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
         if ((e = cudaMemcpyAsync(dEnd, keepAlive.back().data(), (size_t)nseg * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(segOf, 0xff, (size_t)n * sizeof(int), st)) != cudaSuccess) return e;
-        k_mark_segments<<<nseg, 128, 0, st>>>(dBegin, dEnd, nseg, segOf);
-        if (nseg <= 2048) k_axis<256><<<nseg, 256, 0, st>>>(c[cur][0], c[cur][1], c[cur][2], dBegin, dEnd, nseg, axis);
+        const bool wide = nseg <= RTX_RANK_WIDE_SEGS;   // the top levels: a handful of segments of tens of thousands of triangles each
+        k_mark_segments<<<dim3(nseg, wide ? RTX_RANK_WIDE_PARTS : 1), 128, 0, st>>>(dBegin, dEnd, nseg, segOf);
+        if (wide) {
+            k_axis_init<<<1, RTX_RANK_WIDE_SEGS * 6, 0, st>>>(mm, nseg);
+            k_axis_part<<<dim3(nseg, RTX_RANK_WIDE_PARTS), 256, 0, st>>>(c[cur][0], c[cur][1], c[cur][2], dBegin, dEnd, mm);
+            k_axis_finish<<<1, RTX_RANK_WIDE_SEGS, 0, st>>>(mm, nseg, axis);
+        } else if (nseg <= 2048) k_axis<256><<<nseg, 256, 0, st>>>(c[cur][0], c[cur][1], c[cur][2], dBegin, dEnd, nseg, axis);
         else k_axis<32><<<(nseg + 7) / 8, 256, 0, st>>>(c[cur][0], c[cur][1], c[cur][2], dBegin, dEnd, nseg, axis);
         k_keys<<<G, T, 0, st>>>(c[cur][0], c[cur][1], c[cur][2], dBegin, axis, nseg, n, segOf, keyIn, posIn);
         // elements outside the level's segments (finished leaf ranges) keep their place: posOut starts as the identity
         if ((e = cudaMemcpyAsync(posOut, posIn, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
         size_t tb = cubBytesAvail;
-        if ((e = cub::DeviceSegmentedSort::StableSortPairs(cubTemp, tb, keyIn, keyOut, posIn, posOut, n, nseg, dBegin, dEnd, st)) != cudaSuccess) return e;
+        if (wide) {
+            // cub's segmented sort gives a segment of this size to ONE block (3.8 ms for the root of 280 K triangles); the device-wide
+            // radix sort is stable as well and orders doubles the same way (-0.0 = +0.0), one call per segment
+            for (int s = 0; s < nseg; s++) {
+                const int b = ab[s], m = ae[s] - ab[s];
+                tb = cubBytesAvail;
+                if ((e = cub::DeviceRadixSort::SortPairs(cubTemp, tb, keyIn + b, keyOut + b, posIn + b, posOut + b, m, 0, 64, st)) != cudaSuccess) return e;
+            }
+        } else if ((e = cub::DeviceSegmentedSort::StableSortPairs(cubTemp, tb, keyIn, keyOut, posIn, posOut, n, nseg, dBegin, dEnd, st)) != cudaSuccess) return e;
         k_gather<<<G, T, 0, st>>>(posOut, n, c[cur][0], c[cur][1], c[cur][2], idx[cur], c[cur ^ 1][0], c[cur ^ 1][1], c[cur ^ 1][2], idx[cur ^ 1]);
         cur ^= 1;
         std::vector<int> nb, ne;

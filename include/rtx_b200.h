@@ -299,6 +299,12 @@ int32_t rtx_hdri_pdf(rtx_ctx* ctx, const double* dir, int64_t n, double* pdf);
 int32_t rtx_hdri_lookup(rtx_ctx* ctx, const double* dir, int64_t n, double* rgb); /* Environment.Sample, rt/hdri.go:120 */
 int32_t rtx_hdri_total_power(const rtx_ctx* ctx, double* total_power);            /* rt/hdri.go:325 */
 
+/* The test order the last rtx_scene_upload derived ON THE DEVICE for its mesh triangles (desc.tri_rank == NULL, "bvh_device" = 1):
+ * rank[t] = position of triangle t (scene order) among the leaves of the tree NewBVHNode would build over its mesh
+ * (rt/bvh.go:69-217, stable sort), counted per mesh. n must be the scene's n_tris. RTX_ERR_STATE when the caller gave the ranks
+ * itself. Parity tests compare it with the host mirror's tree. */
+int32_t rtx_mesh_test_order(rtx_ctx* ctx, int32_t* rank, int64_t n);
+
 /* Run all subsequent work of this context on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL restores
  * the context's own stream). Lets the caller order the library's kernels with its own (e.g. the NCCL reduce of the
  * accumulation buffers issued by torch.distributed) and time them with events on that stream. */

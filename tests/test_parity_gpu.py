@@ -6,6 +6,8 @@ bit-exactly; t, normals and hit points within 1e-5 relative. The device evaluate
 reference's operation order, so the tests actually demand |dt| <= 1e-12 relative.
 Level 2: RNG streams differ, so images are compared statistically on per-pixel mean / variance of linear radiance.
 Tolerances are written next to each assertion."""
+import os
+
 import numpy as np
 import pytest
 
@@ -127,6 +129,54 @@ def _soup_scene(grt, rng, world_is_bvh=True, n_tri=3000, dup=True):
         for _ in range(2):
             b.entry(grt.GEOM_TRIANGLE, b.triangle((-6, -6, 6), (6, -6, 6), (0, 6, 6), m))
     return b.build()
+
+
+@pytest.mark.parametrize("mesh", ["standin", "grid with ties"])
+def test_device_test_order_equals_the_host_tree(grt, ctx, tmp_path, mesh):
+    """rtx_scene_upload without tri_rank derives the reference tree's leaf order on the device (rtx_rank_gpu.cuh: per level a
+    segmented longest-axis rule and a stable sort; the few wide segments of the top levels go through a device-wide radix sort).
+    It must be the permutation the host mirror reads off the tree it builds like rt/bvh.go:69-217 (RT_EAGER_BVH) — for the 280 K
+    stand-in mesh and for a regular grid in which thousands of centroids tie on every axis (stability decides) and some
+    triangles are exact duplicates."""
+    root = None
+    if mesh != "standin":
+        root = str(tmp_path)
+        os.makedirs(os.path.join(root, "assets", "models"))
+        nx, nz = 150, 120
+        lines = []
+        for i in range(nx + 1):
+            for k in range(nz + 1):
+                lines.append(f"v {i * 0.25:.2f} {((i * 7 + k * 3) % 5) * 0.5:.1f} {k * 0.25:.2f}")
+        vid = lambda i, k: i * (nz + 1) + k + 1
+        for i in range(nx):
+            for k in range(nz):
+                lines.append(f"f {vid(i, k)} {vid(i + 1, k)} {vid(i + 1, k + 1)} {vid(i, k + 1)}")   # a quad: fan of two triangles
+                if (i + k) % 17 == 0:
+                    lines.append(f"f {vid(i, k)} {vid(i + 1, k)} {vid(i + 1, k + 1)}")                # exact duplicate of the first
+        with open(os.path.join(root, "assets", "models", "lucy_low.obj"), "w") as f:
+            f.write("\n".join(lines) + "\n")
+    cfg = grt.CONFIGS["cornell-lucy"]
+    H = grt.host()
+    H.rth_set_eager_mesh_bvh(1)
+    try:
+        eager = grt.NamedScene(cfg["scene"], 96, cfg["aspect"], 1, 4, asset_root=root)
+        n = eager.desc.n_tris
+        want = np.ctypeslib.as_array(eager.desc.tri_rank, (n,)).copy()
+    finally:
+        H.rth_set_eager_mesh_bvh(0)
+    lazy = grt.NamedScene(cfg["scene"], 96, cfg["aspect"], 1, 4, asset_root=root)
+    assert not lazy.desc.tri_rank and lazy.desc.n_tris == n and n > (30000 if root else 250000)
+    os.environ["RTX_NO_RANK_CACHE"] = "1"
+    try:
+        ctx.load(lazy)
+        got = ctx.mesh_test_order(n)
+    finally:
+        del os.environ["RTX_NO_RANK_CACHE"]
+    assert np.array_equal(np.sort(got), np.arange(n))
+    assert np.array_equal(got, want), f"{int((got != want).sum())} of {n} ranks differ"
+    ctx.load(eager)                                   # ranks given by the caller: nothing derived on the device
+    with pytest.raises(grt.RtxError):
+        ctx.mesh_test_order(n)
 
 
 def test_device_bvh_build(grt, orc, ctx):
