@@ -1357,6 +1357,7 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
     // a launch of 1036 persistent blocks (or 1184 stream blocks) for a few thousand rays is mostly block scheduling.
     int activeBound = P;
     long long iterGenDone = -1;
+    const bool fusedTree = !ctx->scene_flat && ctx->fuse_tree;
     const int drainPerBlock = getenv("RTX_DRAIN_PER_BLOCK") ? std::max(1, atoi(getenv("RTX_DRAIN_PER_BLOCK"))) : RTX_DRAIN_PER_BLOCK_DEFAULT;
     for (;;) {
         int used = 0;
@@ -1371,11 +1372,15 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
             if (pending[cur]) { CUL(cudaStreamWaitEvent(st, ctx->ev_connected[cur], 0)); pending[cur] = false; }
             Pool poolI = pool;
             poolI.shadow = pool.shadow + (size_t)cur * (size_t)ctx->pool_has_shadow * (size_t)P * RTX_SHADOW_BYTES;
+            // timing events: the boundaries between the kernels of an iteration only (an event record between two launches costs the stream
+            // a few microseconds: eight per iteration were 4 % of hdri-test); an iteration starts where the previous one ended, so the
+            // one-warp k_iter_begin is counted with the kernel that follows it. Slots: 0 batch start, 1 after generate, 2 after extend /
+            // bounce, 3 after shade, 4 / 5 around connect.
+            if (timing && b == 0) cudaEventRecord(ev[0], st);
             k_iter_begin<<<1, 32, 0, st>>>(ctx->ctl, P, cur);
-            if (timing) cudaEventRecord(ev[0], st);
             const bool fused = ctx->scene_flat && ctx->fuse_flat;   // k_bounce_flat generates the fresh paths itself
             if (!fused) k_generate<<<gStreamB, 256, 0, st>>>(ctx->ctl, pool, cur, ctx->C, pp);
-            if (timing) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
+            if (timing && !fused && !fusedTree) cudaEventRecord(ev[1], st);
             if (fused) {   // generate + trace + shade in one kernel: fresh paths and hits stay in registers
                 if (ctx->S.n_images > 0) k_bounce_flat<false, true><<<gStreamB, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
                 else if (ctx->count_stats & 1) k_bounce_flat<true><<<gStreamB, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
@@ -1385,13 +1390,13 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
                     else if (lean == 4) k_bounce_flat<false, false, RTX_FV_CORNELL><<<gStreamB, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
                     else k_bounce_flat<false><<<gStreamB, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
                 }
-                if (timing) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); }
+                if (timing) cudaEventRecord(ev[2], st);
                 launches -= 2;
-            } else if (!ctx->scene_flat && ctx->fuse_tree) {   // trace + shade in the persistent kernel: the hit never leaves the lane that found it
+            } else if (fusedTree) {   // trace + shade in the persistent kernel: the hit never leaves the lane that found it
                 if (ctx->S.n_images > 0) k_bounce<false, true><<<gTraceB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
                 else if (ctx->count_stats & 1) k_bounce<true><<<gTraceB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
                 else k_bounce<false><<<gTraceB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
-                if (timing) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); }
+                if (timing) cudaEventRecord(ev[2], st);
                 launches -= 1;
             } else {
             if (ctx->S.n_images > 0) {   // hit records carry (u, v); this variant is not instrumented
@@ -1408,7 +1413,7 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
             else if (lean == 1) k_extend<false, false, RTX_FV_LUCY><<<gLucyB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_LUCY), st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
             else if (lean == 2) k_extend<false, false, RTX_FV_SKY><<<gSkyB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_SKY), st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
             else k_extend<false><<<gTraceB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, pool, cur, ctx->S, pp, ctx->trace_spill);
-            if (timing) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); }
+            if (timing) cudaEventRecord(ev[2], st);
             if (ctx->shade_split) {   // one launch per material queue (launches over empty queues return at once)
                 const int gs = shrink(std::min((P + 255) / 256, ctx->num_sms * 2 * RTX_SHADE_BLOCKS_Q), 256);
                 k_shade<Q_MISS><<<gs, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
@@ -1427,11 +1432,11 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
                 else if (leanShade == 4) k_shade<-1, RTX_FV_CORNELL><<<gsh, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
                 else k_shade<-1><<<gsh, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
             }
+            if (timing) cudaEventRecord(ev[3], st);
             }
-            if (timing) cudaEventRecord(ev[5], st);
             if (ctx->S.n_lights > 0) {
                 if (overlap) { CUL(cudaEventRecord(ctx->ev_shaded, st)); CUL(cudaStreamWaitEvent(sc, ctx->ev_shaded, 0)); }
-                if (timing) cudaEventRecord(ev[6], sc);
+                if (timing) cudaEventRecord(ev[4], sc);
                 if (ctx->scene_flat) {
                     if (ctx->count_stats & 2) k_connect_flat<true><<<gStreamB, 256, 0, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp);
                     else if (lean == 3 || lean == 1) k_connect_flat<false, RTX_FV_BOX><<<gStreamB, 256, 0, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp);
@@ -1445,10 +1450,10 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
                 else if (lean == 1) k_connect<false, RTX_FV_LUCY><<<gLucyB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_LUCY), sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
                 else if (lean == 2) k_connect<false, RTX_FV_SKY><<<gSkyB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_SKY), sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
                 else k_connect<false><<<gTraceB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, sc>>>(ctx->ctl, poolI, cur, ctx->S, pp, spillC);
-                if (timing) cudaEventRecord(ev[7], sc);
+                if (timing) cudaEventRecord(ev[5], sc);
                 if (overlap) { CUL(cudaEventRecord(ctx->ev_connected[cur], sc)); pending[cur] = true; }
                 launches++;
-            } else if (timing) { cudaEventRecord(ev[6], st); cudaEventRecord(ev[7], st); }
+            }
             launches += 4;
             used++;
             if (debugIter >= 0 && iter == debugIter) {   // developer aid (RTX_DEBUG_ITER=k): the job counts of iteration k, e.g. of the launch an ncu capture picked
@@ -1463,13 +1468,17 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
             if (pending[c]) { CUL(cudaStreamWaitEvent(st, ctx->ev_connected[c], 0)); pending[c] = false; }
         CUL(cudaMemcpyAsync(ctx->ctl_host, ctx->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
         CUL(cudaStreamSynchronize(st));
-        if (timing)
-            for (int b = 0; b < used; b++)
-                for (int k = 0; k < EV_KINDS; k++) {
-                    float ms = 0;
-                    cudaEventElapsedTime(&ms, ctx->events[4 + (size_t)b * EV_KINDS * 2 + 2 * k], ctx->events[4 + (size_t)b * EV_KINDS * 2 + 2 * k + 1]);
-                    msKind[k] += ms;
-                }
+        if (timing) {
+            const bool oneKernel = (ctx->scene_flat && ctx->fuse_flat) || fusedTree;   // generate / trace / shade in one launch: boundary 2 only
+            auto slot = [&](int b, int k) { return ctx->events[4 + (size_t)b * EV_KINDS * 2 + k]; };
+            auto span = [&](cudaEvent_t a, cudaEvent_t z) { float ms = 0; cudaEventElapsedTime(&ms, a, z); return (double)ms; };
+            for (int b = 0; b < used; b++) {
+                const cudaEvent_t start = b == 0 ? slot(0, 0) : slot(b - 1, oneKernel ? 2 : 3);
+                if (oneKernel) msKind[EV_EXT] += span(start, slot(b, 2));
+                else { msKind[EV_GEN] += span(start, slot(b, 1)); msKind[EV_EXT] += span(slot(b, 1), slot(b, 2)); msKind[EV_SHADE] += span(slot(b, 2), slot(b, 3)); }
+                if (ctx->S.n_lights > 0) msKind[EV_CONN] += span(slot(b, 4), slot(b, 5));
+            }
+        }
         if (getenv("RTX_DEBUG_BATCH"))
             fprintf(stderr, "[rtx] iter %lld: ms gen/ext/shade/conn %.2f/%.2f/%.2f/%.2f active %d next %d shadow %d cursor %llu\n", iter, msKind[0], msKind[1],
                     msKind[2], msKind[3], ctx->ctl_host->n_active, ctx->ctl_host->n_next, ctx->ctl_host->n_shadow[0], ctx->ctl_host->cursor);
@@ -1490,21 +1499,30 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
                     if (pending[c]) { CUL(cudaStreamWaitEvent(st, ctx->ev_connected[c], 0)); pending[c] = false; }
                 Pool poolI = pool;
                 const int recCur = (int)(iter & 1);   // rec[recCur] holds the survivors of the last iteration
+                cudaEvent_t* ev = timing ? &ctx->events[4] : nullptr;   // the slots of the batch just read: the drain's rays count as extension rays, its k_connect as connect
+                if (timing) cudaEventRecord(ev[0], st);
                 k_drain_begin<<<1, 32, 0, st>>>(ctx->ctl, cur);
                 if (ctx->S.n_images > 0) k_drain<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, recCur, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
                 else k_drain<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, recCur, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
+                if (timing) cudaEventRecord(ev[2], st);
                 if (ctx->S.n_lights > 0) {   // the shadow requests of the whole drain, one launch
                     if (lean == 1) k_connect<false, RTX_FV_LUCY><<<ctx->trace_grid_lucy, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_LUCY), st>>>(ctx->ctl, poolI, cur, ctx->S, pp, ctx->trace_spill);
                     else if (lean == 2) k_connect<false, RTX_FV_SKY><<<ctx->trace_grid_sky, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_SKY), st>>>(ctx->ctl, poolI, cur, ctx->S, pp, ctx->trace_spill);
                     else k_connect<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, cur, ctx->S, pp, ctx->trace_spill);
                     launches++;
                 }
+                if (timing) cudaEventRecord(ev[5], st);
                 k_drain_end<<<1, 32, 0, st>>>(ctx->ctl);
                 launches += 3;
                 for (int c = 0; c < 2; c++)
                     if (pending[c]) { CUL(cudaStreamWaitEvent(st, ctx->ev_connected[c], 0)); pending[c] = false; }
                 CUL(cudaMemcpyAsync(ctx->ctl_host, ctx->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
                 CUL(cudaStreamSynchronize(st));
+                if (timing) {
+                    float ms = 0;
+                    cudaEventElapsedTime(&ms, ev[0], ev[2]); msKind[EV_EXT] += ms;
+                    cudaEventElapsedTime(&ms, ev[2], ev[5]); msKind[EV_CONN] += ms;
+                }
                 break;
             }
         }

@@ -56,6 +56,7 @@ struct Ctl {  // device-resident control block of the wavefront loop
     unsigned long long ext_rays, shadow_rays, nodes, tris, spheres, quads, planes, iterations;
     // the tail of a pass: iterations after its last camera path was generated (the stream only shrinks), timed on the device
     unsigned long long t_tail_begin, t_end, tail_iterations;
+    int drain_bounce_min, drain_bounce_max;   // k_drain: shallowest / deepest bounce index it traced (its span = the per-bounce launches it replaced)
 };
 __device__ __forceinline__ unsigned long long rtx_globaltimer() {
     unsigned long long t;
@@ -963,9 +964,14 @@ struct DrainPolicyT {
         const unsigned me = __ballot_sync(am, V.has_env), ma = __ballot_sync(am, V.has_area), mv = __ballot_sync(am, valid);
         const int lane = threadIdx.x & 31, leader = __ffs(am) - 1;
         int bs = 0;
+        const int bmin = __reduce_min_sync(am, valid ? V.bounce0 : 0x7fffffff), bmax = __reduce_max_sync(am, valid ? V.bounce0 : -1);
         if (lane == leader) {
             if (me | ma) bs = atomicAdd(&ctl->n_shadow[par], __popc(me) + __popc(ma));
-            if (mv) atomicAdd(&ctl->ext_rays, (unsigned long long)__popc(mv));
+            if (mv) {
+                atomicAdd(&ctl->ext_rays, (unsigned long long)__popc(mv));
+                if (bmin < ctl->drain_bounce_min) atomicMin(&ctl->drain_bounce_min, bmin);
+                if (bmax > ctl->drain_bounce_max) atomicMax(&ctl->drain_bounce_max, bmax);
+            }
         }
         bs = __shfl_sync(am, bs, leader);
         const unsigned below = (1u << lane) - 1u;
@@ -1003,12 +1009,15 @@ __global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_drain(C
 __global__ void k_drain_begin(Ctl* ctl, int par) {
     if (threadIdx.x != 0) return;
     ctl->cur_extend = 0; ctl->n_shadow[par] = 0; ctl->cur_connect[par] = 0;
+    ctl->drain_bounce_min = 0x7fffffff; ctl->drain_bounce_max = -1;
     if (ctl->t_tail_begin == 0) ctl->t_tail_begin = rtx_globaltimer();
 }
 __global__ void k_drain_end(Ctl* ctl) {
     if (threadIdx.x != 0) return;
     ctl->n_next = 0; ctl->n_active = 0; ctl->done = 1;
-    ctl->iterations += 1; ctl->tail_iterations += 1;
+    // the bounce rounds the launch covered count as the wavefront iterations they replaced
+    const int rounds = ctl->drain_bounce_max >= ctl->drain_bounce_min ? ctl->drain_bounce_max - ctl->drain_bounce_min + 1 : 1;
+    ctl->iterations += rounds; ctl->tail_iterations += rounds;
     if (ctl->t_end == 0) ctl->t_end = rtx_globaltimer();
 }
 
