@@ -122,6 +122,7 @@ struct rtx_ctx {
     int num_sms = 0;
     int* batch_cursor = nullptr;  // job cursor of k_trace_closest
     int trace_grid_sky = 0, trace_grid_lucy = 0;   // grids of the lean variants of the persistent trace kernels
+    int drain_grid_sky = 0, drain_grid_lucy = 0;   // ... and of the lean drain kernels (k_drain)
     int* trace_spill = nullptr;   // global overflow columns of the trace kernels' shared-memory stacks
     int* trace_spill2 = nullptr;  // the same for k_connect (it may run beside k_extend)
     int trace_grid = 0;           // persistent grid: SMs x resident blocks
@@ -265,6 +266,20 @@ int32_t rtx_create(int32_t device_id, rtx_ctx** out) {
         if (carveKB > 0) minOcc = std::max(1, std::min(minOcc, (int)((size_t)carveKB * 1024 / (smem + 1024))));
         (group == 0 ? ctx->trace_grid : group == 1 ? ctx->trace_grid_sky : ctx->trace_grid_lucy) = ctx->num_sms * minOcc;
         if (getenv("RTX_DEBUG_BATCH")) fprintf(stderr, "[rtx] trace kernels (%s): %d blocks/SM, %d B dynamic smem per block, grid %d\n", group == 0 ? "full" : group == 1 ? "sky" : "lucy", minOcc, smem, ctx->num_sms * minOcc);
+    }
+    {   // the lean drain kernels: the lean pools with their own register budget, hence their own resident wave
+        const void* dk[2] = {(const void*)k_drain<false, RTX_FV_SKY>, (const void*)k_drain<false, RTX_FV_LUCY>};
+        const int dsm[2] = {(int)RTX_TRACE_SMEM_BYTES_OF(RTX_FV_SKY), (int)RTX_TRACE_SMEM_BYTES_OF(RTX_FV_LUCY)};
+        for (int k = 0; k < 2; k++) {
+            int occ = 0;
+            if ((e = cudaFuncSetAttribute(dk[k], cudaFuncAttributeMaxDynamicSharedMemorySize, dsm[k])) != cudaSuccess ||
+                (e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dk[k], RTX_TRACE_THREADS, dsm[k])) != cudaSuccess || occ < 1) {
+                fail(nullptr, RTX_ERR_CUDA, "rtx_create: drain kernel setup failed (%s, occupancy %d)", cudaGetErrorString(e), occ);
+                rtx_destroy(ctx);
+                return RTX_ERR_CUDA;
+            }
+            (k == 0 ? ctx->drain_grid_sky : ctx->drain_grid_lucy) = ctx->num_sms * occ;
+        }
     }
     {
         size_t spillInts = std::max((size_t)ctx->trace_grid * RTX_TRACE_SLOTS, (size_t)std::max(ctx->trace_grid_sky, ctx->trace_grid_lucy) * RTX_TRACE_SLOTS_LEAN) * (RTX_STACK_SIZE - RTX_SMEM_STACK);
@@ -1374,7 +1389,7 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
             poolI.shadow = pool.shadow + (size_t)cur * (size_t)ctx->pool_has_shadow * (size_t)P * RTX_SHADOW_BYTES;
             // timing events: the boundaries between the kernels of an iteration only (an event record between two launches costs the stream
             // a few microseconds: eight per iteration were 4 % of hdri-test); an iteration starts where the previous one ended, so the
-            // one-warp k_iter_begin is counted with the kernel that follows it. Slots: 0 batch start, 1 after generate, 2 after extend /
+            // one-warp k_iter_begin is counted with the kernel that follows it; the one-kernel paths record the two ends of a batch only. Slots: 0 batch start, 1 after generate, 2 after extend /
             // bounce, 3 after shade, 4 / 5 around connect.
             if (timing && b == 0) cudaEventRecord(ev[0], st);
             k_iter_begin<<<1, 32, 0, st>>>(ctx->ctl, P, cur);
@@ -1390,13 +1405,13 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
                     else if (lean == 4) k_bounce_flat<false, false, RTX_FV_CORNELL><<<gStreamB, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
                     else k_bounce_flat<false><<<gStreamB, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
                 }
-                if (timing) cudaEventRecord(ev[2], st);
+                if (timing && b == batchN - 1) cudaEventRecord(ev[2], st);   // one kernel per iteration: only the sum over the batch is wanted
                 launches -= 2;
             } else if (fusedTree) {   // trace + shade in the persistent kernel: the hit never leaves the lane that found it
                 if (ctx->S.n_images > 0) k_bounce<false, true><<<gTraceB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
                 else if (ctx->count_stats & 1) k_bounce<true><<<gTraceB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
                 else k_bounce<false><<<gTraceB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
-                if (timing) cudaEventRecord(ev[2], st);
+                if (timing && b == batchN - 1) cudaEventRecord(ev[2], st);
                 launches -= 1;
             } else {
             if (ctx->S.n_images > 0) {   // hit records carry (u, v); this variant is not instrumented
@@ -1472,9 +1487,10 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
             const bool oneKernel = (ctx->scene_flat && ctx->fuse_flat) || fusedTree;   // generate / trace / shade in one launch: boundary 2 only
             auto slot = [&](int b, int k) { return ctx->events[4 + (size_t)b * EV_KINDS * 2 + k]; };
             auto span = [&](cudaEvent_t a, cudaEvent_t z) { float ms = 0; cudaEventElapsedTime(&ms, a, z); return (double)ms; };
+            if (oneKernel && used > 0) msKind[EV_EXT] += span(slot(0, 0), slot(used - 1, 2));
             for (int b = 0; b < used; b++) {
-                const cudaEvent_t start = b == 0 ? slot(0, 0) : slot(b - 1, oneKernel ? 2 : 3);
-                if (oneKernel) msKind[EV_EXT] += span(start, slot(b, 2));
+                const cudaEvent_t start = b == 0 ? slot(0, 0) : slot(b - 1, 3);
+                if (oneKernel) {}
                 else { msKind[EV_GEN] += span(start, slot(b, 1)); msKind[EV_EXT] += span(slot(b, 1), slot(b, 2)); msKind[EV_SHADE] += span(slot(b, 2), slot(b, 3)); }
                 if (ctx->S.n_lights > 0) msKind[EV_CONN] += span(slot(b, 4), slot(b, 5));
             }
@@ -1503,6 +1519,8 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
                 if (timing) cudaEventRecord(ev[0], st);
                 k_drain_begin<<<1, 32, 0, st>>>(ctx->ctl, cur);
                 if (ctx->S.n_images > 0) k_drain<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, recCur, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
+                else if (lean == 1) k_drain<false, RTX_FV_LUCY><<<ctx->drain_grid_lucy, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_LUCY), st>>>(ctx->ctl, poolI, recCur, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
+                else if (lean == 2) k_drain<false, RTX_FV_SKY><<<ctx->drain_grid_sky, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_SKY), st>>>(ctx->ctl, poolI, recCur, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
                 else k_drain<false><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, recCur, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
                 if (timing) cudaEventRecord(ev[2], st);
                 if (ctx->S.n_lights > 0) {   // the shadow requests of the whole drain, one launch

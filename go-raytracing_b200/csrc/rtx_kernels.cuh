@@ -852,7 +852,7 @@ __global__ void __launch_bounds__(256, (FEAT & RTX_F_COMPLEX) ? RTX_BOUNCE_BLOCK
 // record (64 B written, 64 B read back), the queue slots and k_shade's gather of the path record disappear, and the HBM-bound shading
 // stream runs inside the latency-bound traversal instead of after it. The material code is one out-of-line call (bounce_shade), so the
 // traversal loop keeps its registers; what the call needs travels through local memory.
-template <bool UV>
+template <bool UV, unsigned FEAT = RTX_F_ALL>
 __device__ __noinline__ void bounce_shade(const DevScene* S, const DevCamera* C, const PassParams* pp, const Pool* pool, double pixbits, float4 th, const RayD* rp,
                                           const Best* bp, ShadeVars* Vp) {
     const RayD r = *rp;
@@ -866,12 +866,12 @@ __device__ __noinline__ void bounce_shade(const DevScene* S, const DevCamera* C,
     HitInfo hi;
     hi.P = hi.N = d3(0, 0, 0); hi.mat = 0; hi.front = false; hi.u = hi.v = 0;
     if (b.entry >= 0) {
-        finalize_hit(*S, r, best_to_hit(b), UV, hi);
+        finalize_hit<FEAT>(*S, r, best_to_hit(b), UV, hi);
         const int mt = S->mats[hi.mat].type;
         type = mt == RTX_MAT_LAMBERTIAN ? Q_LAMBERTIAN : mt == RTX_MAT_METAL ? Q_METAL : mt == RTX_MAT_DIELECTRIC ? Q_DIELECTRIC
              : mt == RTX_MAT_DIFFUSE_LIGHT ? Q_LIGHT : Q_ISOTROPIC;
     }
-    shade_element(*S, *C, *pp, *pool, type, d3(r.dx, r.dy, r.dz), hi.P, hi.N, UV ? hi.u : 0.0, UV ? hi.v : 0.0, hi.mat, hi.front, V);
+    shade_element<FEAT>(*S, *C, *pp, *pool, type, d3(r.dx, r.dy, r.dz), hi.P, hi.N, UV ? hi.u : 0.0, UV ? hi.v : 0.0, hi.mat, hi.front, V);
     *Vp = V;
 }
 template <bool UV>
@@ -921,7 +921,7 @@ __global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_bounce(
 // (Policy::CONTINUES in trace_persistent): no barrier between bounces, no queue traffic, and the drain lasts as long as the longest chain of paths
 // one slot gets. The path's record is updated in place (an instance exit re-reads the world ray from it). Shadow requests are collected and
 // traced by one k_connect launch afterwards. Same shade_element, same Philox counters: the same paths as the iteration loop would trace.
-template <bool UV>
+template <bool UV, unsigned FEAT = RTX_F_ALL>
 struct DrainPolicyT {
     static constexpr bool ANY_HIT = false, CONTINUES = true;
     Ctl* ctl; const Pool* pool; int cur; int par; const DevScene* S; const DevCamera* C; const PassParams* pp;   // cur: record buffer of the jobs; par: shadow counter
@@ -958,7 +958,7 @@ struct DrainPolicyT {
         ShadeVars V;
         if (valid) {
             const char* q = record(job);
-            bounce_shade<UV>(S, C, pp, pool, ld256v(q + 32).w, ld128v(q + 64), &r, &b, &V);
+            bounce_shade<UV, FEAT>(S, C, pp, pool, ld256v(q + 32).w, ld128v(q + 64), &r, &b, &V);
         } else V.reset();
         const unsigned am = __activemask();
         const unsigned me = __ballot_sync(am, V.has_env), ma = __ballot_sync(am, V.has_area), mv = __ballot_sync(am, valid);
@@ -998,12 +998,17 @@ struct DrainPolicyT {
         return V.cont;
     }
 };
-template <bool UV = false>
-__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS) k_drain(Ctl* ctl, const __grid_constant__ Pool pool, int cur, int par, const __grid_constant__ DevScene S,
+// resident blocks the lean drain variants are compiled for: shading runs inside the kernel, so they want more registers than the lean trace kernels
+#ifndef RTX_DRAIN_BLOCKS_LEAN
+#define RTX_DRAIN_BLOCKS_LEAN 5
+#endif
+#define RTX_DRAIN_BLOCKS_OF(FEAT) ((FEAT) == RTX_F_ALL ? RTX_TRACE_BLOCKS : RTX_DRAIN_BLOCKS_LEAN)
+template <bool UV = false, unsigned FEAT = RTX_F_ALL>
+__global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_DRAIN_BLOCKS_OF(FEAT)) k_drain(Ctl* ctl, const __grid_constant__ Pool pool, int cur, int par, const __grid_constant__ DevScene S,
                                                                               const __grid_constant__ DevCamera C, const __grid_constant__ PassParams pp, int* spill) {
-    DrainPolicyT<UV> P{ctl, &pool, cur, par, &S, &C, &pp};
+    DrainPolicyT<UV, FEAT> P{ctl, &pool, cur, par, &S, &C, &pp};
     TraceCounters tc = {0, 0, 0, 0, 0};
-    trace_persistent<DrainPolicyT<UV>, false, RTX_TRACE_SLOTS>(S, P, &ctl->cur_extend, ctl->n_next, tc, spill, rtx_smem);
+    trace_persistent<DrainPolicyT<UV, FEAT>, false, RTX_TRACE_SLOTS_OF(FEAT), FEAT>(S, P, &ctl->cur_extend, ctl->n_next, tc, spill, rtx_smem);
 }
 // before the drain: job cursor and shadow half; after it (and its k_connect): the books of the pass
 __global__ void k_drain_begin(Ctl* ctl, int par) {
