@@ -1373,6 +1373,8 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
     int activeBound = P;
     long long iterGenDone = -1;
     const bool fusedTree = !ctx->scene_flat && ctx->fuse_tree;
+    // one-kernel iterations with nothing else on the render stream: the two ends of a batch give the kernel's time
+    const bool sparseEvents = ((ctx->scene_flat && ctx->fuse_flat) || fusedTree) && !(ctx->S.n_lights > 0 && !overlap);
     const int drainPerBlock = getenv("RTX_DRAIN_PER_BLOCK") ? std::max(1, atoi(getenv("RTX_DRAIN_PER_BLOCK"))) : RTX_DRAIN_PER_BLOCK_DEFAULT;
     for (;;) {
         int used = 0;
@@ -1405,13 +1407,13 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
                     else if (lean == 4) k_bounce_flat<false, false, RTX_FV_CORNELL><<<gStreamB, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
                     else k_bounce_flat<false><<<gStreamB, 256, 0, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp);
                 }
-                if (timing && b == batchN - 1) cudaEventRecord(ev[2], st);   // one kernel per iteration: only the sum over the batch is wanted
+                if (timing && (!sparseEvents || b == batchN - 1)) cudaEventRecord(ev[2], st);   // one kernel per iteration: only the sum over the batch is wanted
                 launches -= 2;
             } else if (fusedTree) {   // trace + shade in the persistent kernel: the hit never leaves the lane that found it
                 if (ctx->S.n_images > 0) k_bounce<false, true><<<gTraceB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
                 else if (ctx->count_stats & 1) k_bounce<true><<<gTraceB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
                 else k_bounce<false><<<gTraceB, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
-                if (timing && b == batchN - 1) cudaEventRecord(ev[2], st);
+                if (timing && (!sparseEvents || b == batchN - 1)) cudaEventRecord(ev[2], st);
                 launches -= 1;
             } else {
             if (ctx->S.n_images > 0) {   // hit records carry (u, v); this variant is not instrumented
@@ -1487,10 +1489,12 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
             const bool oneKernel = (ctx->scene_flat && ctx->fuse_flat) || fusedTree;   // generate / trace / shade in one launch: boundary 2 only
             auto slot = [&](int b, int k) { return ctx->events[4 + (size_t)b * EV_KINDS * 2 + k]; };
             auto span = [&](cudaEvent_t a, cudaEvent_t z) { float ms = 0; cudaEventElapsedTime(&ms, a, z); return (double)ms; };
-            if (oneKernel && used > 0) msKind[EV_EXT] += span(slot(0, 0), slot(used - 1, 2));
+            if (sparseEvents && used > 0) msKind[EV_EXT] += span(slot(0, 0), slot(used - 1, 2));
             for (int b = 0; b < used; b++) {
-                const cudaEvent_t start = b == 0 ? slot(0, 0) : slot(b - 1, 3);
-                if (oneKernel) {}
+                // where the previous iteration ended on this stream: after its shade kernel, or after its connect kernel when that ran here too
+                const cudaEvent_t start = b == 0 ? slot(0, 0) : slot(b - 1, (ctx->S.n_lights > 0 && !overlap) ? 5 : 3);
+                if (sparseEvents) {}
+                else if (oneKernel) msKind[EV_EXT] += span(start, slot(b, 2));
                 else { msKind[EV_GEN] += span(start, slot(b, 1)); msKind[EV_EXT] += span(slot(b, 1), slot(b, 2)); msKind[EV_SHADE] += span(slot(b, 2), slot(b, 3)); }
                 if (ctx->S.n_lights > 0) msKind[EV_CONN] += span(slot(b, 4), slot(b, 5));
             }

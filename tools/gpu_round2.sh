@@ -20,3 +20,6 @@ python tools/ncu_to_json.py $out/${tag}_prof_bounce.ncu-rep k_bounce_flat $rh "n
 python tools/ncu_summary.py $out/${tag}_prof_extend.ncu-rep 120 > $out/${tag}_k_extend_sass.txt 2>&1
 python tools/ncu_summary.py $out/${tag}_prof_connect.ncu-rep 120 > $out/${tag}_k_connect_sass.txt 2>&1
 for s in cornell random cornell-glossy cornell-lucy hdri-test quads earth cornell-smoke checkered simple glossy-metal perlin primitives; do python tools/gpu_perf.py $s 64 2>&1 | tail -1 | cut -c1-230; done > $out/${tag}_scenes.log; cat $out/${tag}_scenes.log | cut -c1-120
+# the merge back is limited to 64 MiB: keep the k_extend report, drop the other two (their JSON / SASS summaries stay)
+rm -f $out/${tag}_prof_connect.ncu-rep $out/${tag}_prof_bounce.ncu-rep
+du -sh $out | tail -1
