@@ -232,7 +232,7 @@ GOLDEN_SCENES = ["cornell", "random", "cornell-glossy", "cornell-lucy", "hdri-te
 
 
 @pytest.mark.parametrize("name", GOLDEN_SCENES)
-def test_oracle_reproduces_golden_rays(orc, grt, name):
+def test_oracle_reproduces_self_generated_golden_rays(orc, grt, name):
     """tests/golden/level1_<scene>.npz (tools/make_golden_rays.py): committed ray batches with the hit records the oracle
     produced when they were made. The oracle must keep reproducing them bit for bit (ids, t, front face); the GPU suite
     holds the CUDA path to the same files."""

@@ -311,7 +311,7 @@ def test_level1_circles_and_pyramids(grt, orc, ctx):
 
 
 @pytest.mark.parametrize("name", ["cornell", "random", "cornell-glossy", "cornell-lucy", "hdri-test", "cornell-smoke", "primitives", "earth"])
-def test_level1_golden_fixtures(grt, ctx, name):
+def test_level1_self_generated_golden_fixtures(grt, ctx, name):
     """The CUDA path against the committed fixtures of tests/golden/ (made by tools/make_golden_rays.py from the oracle, which
     the CPU suite holds to the same files): primary rays with lens / time jitter and scatter rays leaving the surfaces.
     No oracle call here: ids and front faces bit-exact, t to 1e-12 relative (north star: 1e-5)."""
