@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Makes tests/golden/level1_<scene>.npz: a fixed batch of rays per scene (seeded camera rays with lens / time jitter, plus
 scatter rays leaving the hit points) and the hit records the CPU oracle computes for them: entry id, primitive id, t, front
-face. The fixtures are committed; `test_oracle_reproduces_golden_rays` (CPU) guards the oracle against drift and
+face. The fixtures are committed; `test_oracle_reproduces_self_generated_golden_rays` (CPU) guards the oracle against drift and
 `test_level1_self_generated_golden_fixtures` (GPU) holds the CUDA path to the same records without calling the oracle. Regenerate only when
 the oracle is deliberately changed: python tools/make_golden_rays.py"""
 import importlib
