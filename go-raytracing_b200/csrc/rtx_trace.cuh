@@ -19,7 +19,9 @@
 #pragma once
 #include "rtx_device.cuh"
 
+#ifndef RTX_TRACE_THREADS
 #define RTX_TRACE_THREADS 128
+#endif
 #ifndef RTX_TRACE_SLOTS
 #define RTX_TRACE_SLOTS 224   /* ray slots per 128-thread block (shared-memory ray pool, see trace_persistent); multiple of 32, <= 256 (A/B on cornell-lucy: 256: 1370, 224: 1401 Mrays/s: a little more L1) */
 #endif
