@@ -1477,7 +1477,7 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
                 Ctl snap;
                 cudaStreamSynchronize(st); cudaStreamSynchronize(sc);
                 cudaMemcpy(&snap, ctx->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost);
-                fprintf(stderr, "[rtx] iteration %lld: extension rays %d, shadow rays %d\n", iter, snap.n_active, snap.n_shadow[cur]);
+                fprintf(stderr, "[rtx] iteration %lld: extension rays %d, shadow rays %d\n", iter, snap.n_active, ctl_shadow(&snap, cur));
             }
         }
         // join: the control block read below must include the connect kernels of this batch (statistics, timing events)
@@ -1499,21 +1499,23 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
                 if (ctx->S.n_lights > 0) msKind[EV_CONN] += span(slot(b, 4), slot(b, 5));
             }
         }
+        const int lastPar = (int)((iter - 1) & 1);                       // parity of the last iteration issued
+        const int nNext = ctl_survivors(ctx->ctl_host, lastPar);         // its survivors: the rays of the next iteration
         if (getenv("RTX_DEBUG_BATCH"))
             fprintf(stderr, "[rtx] iter %lld: ms gen/ext/shade/conn %.2f/%.2f/%.2f/%.2f active %d next %d shadow %d cursor %llu\n", iter, msKind[0], msKind[1],
-                    msKind[2], msKind[3], ctx->ctl_host->n_active, ctx->ctl_host->n_next, ctx->ctl_host->n_shadow[0], ctx->ctl_host->cursor);
+                    msKind[2], msKind[3], ctx->ctl_host->n_active, nNext, ctl_shadow(ctx->ctl_host, lastPar), ctx->ctl_host->cursor);
         if (ctx->ctl_host->done) break;
-        activeBound = ctx->ctl_host->cursor >= ctx->ctl_host->total ? std::max(ctx->ctl_host->n_next, 1) : P;
+        activeBound = ctx->ctl_host->cursor >= ctx->ctl_host->total ? std::max(nNext, 1) : P;
         if (ctx->ctl_host->cursor >= ctx->ctl_host->total && iterGenDone < 0) iterGenDone = iter;   // every live path was generated before this iteration
         // ---- the barrier-free drain: ONE persistent launch for all remaining bounces (k_drain, rtx_kernels.cuh) ------------------------------
         // Its shadow requests all go to one half of the shadow buffer: every live path has at least (iter - iterGenDone) bounces behind it, so
         // there are at most n_next x (max_depth - (iter - iterGenDone)) x requests-per-hit of them — the drain starts when that fits.
-        if (ctx->fuse_drain > 0 && iterGenDone >= 0 && !ctx->scene_flat && !ctx->fuse_tree && ctx->count_stats == 0 && ctx->ctl_host->n_next > 0) {
+        if (ctx->fuse_drain > 0 && iterGenDone >= 0 && !ctx->scene_flat && !ctx->fuse_tree && ctx->count_stats == 0 && nNext > 0) {
             const long long remaining = std::max<long long>(1, (long long)max_depth - (iter - iterGenDone));
             // (both halves of the shadow buffer, 2 x pool_has_shadow x P requests, hold them: the connect launches of earlier iterations are joined first)
             const long long perHit = 1 + ((ctx->S.env_w > 0 && ctx->S.env_is) ? 1 : 0);
-            if (ctx->ctl_host->n_next <= ctx->fuse_drain &&
-                (ctx->S.n_lights == 0 || (long long)ctx->ctl_host->n_next * remaining * perHit <= 2ll * ctx->pool_has_shadow * (long long)P)) {
+            if (nNext <= ctx->fuse_drain &&
+                (ctx->S.n_lights == 0 || (long long)nNext * remaining * perHit <= 2ll * ctx->pool_has_shadow * (long long)P)) {
                 const int cur = 0;   // the drain's shadow requests start at the beginning of the buffer; cur_connect[0] / n_shadow[0] count them
                 for (int c = 0; c < 2; c++)
                     if (pending[c]) { CUL(cudaStreamWaitEvent(st, ctx->ev_connected[c], 0)); pending[c] = false; }
@@ -1521,7 +1523,7 @@ static int32_t render_pass_single(rtx_ctx* ctx, int32_t spp, int32_t max_depth, 
                 const int recCur = (int)(iter & 1);   // rec[recCur] holds the survivors of the last iteration
                 cudaEvent_t* ev = timing ? &ctx->events[4] : nullptr;   // the slots of the batch just read: the drain's rays count as extension rays, its k_connect as connect
                 if (timing) cudaEventRecord(ev[0], st);
-                k_drain_begin<<<1, 32, 0, st>>>(ctx->ctl, cur);
+                k_drain_begin<<<1, 32, 0, st>>>(ctx->ctl, cur, lastPar);
                 if (ctx->S.n_images > 0) k_drain<true><<<gridTrace, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES, st>>>(ctx->ctl, poolI, recCur, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
                 else if (lean == 1) k_drain<false, RTX_FV_LUCY><<<ctx->drain_grid_lucy, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_LUCY), st>>>(ctx->ctl, poolI, recCur, cur, ctx->S, ctx->C, pp, ctx->trace_spill);
                 else if (lean == 2) k_drain<false, RTX_FV_SKY><<<ctx->drain_grid_sky, RTX_TRACE_THREADS, RTX_TRACE_SMEM_BYTES_OF(RTX_FV_SKY), st>>>(ctx->ctl, poolI, recCur, cur, ctx->S, ctx->C, pp, ctx->trace_spill);

@@ -47,8 +47,11 @@ struct DevCamera {  // post-Initialize state (rt/camera.go:41-56)
 struct Ctl {  // device-resident control block of the wavefront loop
     unsigned long long cursor, total;  // next path id / paths of this pass
     unsigned long long gen_base;
-    int n_active, n_cont, n_gen, n_next;
-    int n_shadow[2];   // by iteration parity: k_connect of iteration i may still run while iteration i + 1 is generated, extended and shaded
+    int n_active, n_cont, n_gen, pad0;
+    // The two counters k_shade appends through, in ONE word per iteration parity: low half = survivors written to the other record
+    // buffer, high half = shadow requests of this iteration (by parity: k_connect of iteration i may still run while iteration i + 1 is
+    // generated, extended and shaded). One 64-bit atomic per warp draws both tickets (RTX_PACKED_TICKETS).
+    unsigned long long tk[2];
     int n_mat[Q_COUNT];
     int done, pad;
     int cur_extend, cur_connect[2];  // job cursors of the persistent trace kernels (k_connect: by iteration parity)
@@ -117,10 +120,27 @@ __device__ __forceinline__ int warp_append(int* counter, bool pred) {
     return base + __popc(mask & ((1u << lane) - 1));
 }
 
+__host__ __device__ inline int ctl_survivors(const Ctl* c, int par) { return (int)(c->tk[par] & 0xffffffffull); }
+__host__ __device__ inline int ctl_shadow(const Ctl* c, int par) { return (int)(c->tk[par] >> 32); }
+#ifndef RTX_PACKED_TICKETS
+#define RTX_PACKED_TICKETS 1
+#endif
+// Warp leader: reserve n_surv survivor records and n_sh shadow requests of parity par; returns the two bases.
+__device__ __forceinline__ void ctl_draw_tickets(Ctl* ctl, int par, int n_surv, int n_sh, int& base_surv, int& base_sh) {
+#if RTX_PACKED_TICKETS
+    const unsigned long long old = atomicAdd(&ctl->tk[par], (unsigned long long)(unsigned)n_surv | ((unsigned long long)(unsigned)n_sh << 32));
+    base_surv = (int)(old & 0xffffffffull); base_sh = (int)(old >> 32);
+#else
+    unsigned* w = reinterpret_cast<unsigned*>(&ctl->tk[par]);   // little-endian halves
+    base_surv = n_surv ? (int)atomicAdd(w, (unsigned)n_surv) : 0;
+    base_sh = n_sh ? (int)atomicAdd(w + 1, (unsigned)n_sh) : 0;
+#endif
+}
+
 // ---- K0: iteration bookkeeping ---------------------------------------------------------------------------------
 __global__ void k_iter_begin(Ctl* ctl, int capacity, int par) {
     if (threadIdx.x != 0) return;
-    int n_cont = ctl->n_next;   // survivors: records [0, n_cont) of the buffer k_shade just wrote
+    int n_cont = ctl_survivors(ctl, par ^ 1);   // survivors: records [0, n_cont) of the buffer k_shade of the previous iteration just wrote
     unsigned long long remaining = ctl->total - ctl->cursor;
     int n_gen = (int)min((unsigned long long)(capacity - n_cont), remaining);
     ctl->gen_base = ctl->cursor;
@@ -128,7 +148,7 @@ __global__ void k_iter_begin(Ctl* ctl, int capacity, int par) {
     ctl->n_cont = n_cont;
     ctl->n_gen = n_gen;
     ctl->n_active = n_cont + n_gen;
-    ctl->n_next = 0; ctl->n_shadow[par] = 0;
+    ctl->tk[par] = 0;   // this iteration's survivor and shadow counters (the previous iteration's word is still read by its k_connect)
     ctl->cur_extend = 0; ctl->cur_connect[par] = 0;
     for (int i = 0; i < Q_COUNT; i++) ctl->n_mat[i] = 0;
     ctl->done = (n_cont + n_gen == 0);
@@ -619,7 +639,7 @@ __device__ __forceinline__ void shade_element(const DevScene& S, const DevCamera
 }
 
 // Warp-collective: appends the survivor's next record to the other record buffer and the shadow requests to this iteration's half.
-__device__ __forceinline__ void shade_commit(Ctl* ctl, const Pool& pool, const int cur, const ShadeVars& V) {
+__device__ __forceinline__ void shade_commit(Ctl* ctl, const Pool& pool, const int cur, const ShadeVars& V, unsigned long long* quad = nullptr, int quad_iter = 0) {
     const bool cont = V.cont, has_env = V.has_env, has_area = V.has_area;
     const D3 P = V.P, nd = V.nd, env_dir = V.env_dir, area_dir = V.area_dir;
     const double tm = V.tm, pixbits = V.pixbits, area_tmax = V.area_tmax;
@@ -633,12 +653,28 @@ __device__ __forceinline__ void shade_commit(Ctl* ctl, const Pool& pool, const i
     const unsigned mc = __ballot_sync(am, cont), me = __ballot_sync(am, has_env), ma = __ballot_sync(am, has_area);
     const int lane = threadIdx.x & 31, leader = __ffs(am) - 1;
     int bc = 0, bs = 0;
-    if (lane == leader) {
-        if (mc) bc = atomicAdd(&ctl->n_next, __popc(mc));
-        if (me | ma) bs = atomicAdd(&ctl->n_shadow[cur], __popc(me) + __popc(ma));
+    if (quad) {
+        // FOUR warps (threads 128 g .. 128 g + 127 of a 256-thread block, every one of them here in every iteration) draw one ticket pair:
+        // the counters of a pass are single words, and k_shade's rate was the rate of same-address atomics in L2 (one per warp: 41 % of
+        // its stall samples; packed into one word: -12 % time; one per four warps: see DESIGN.md section 8). Named barrier 1 + g, double-
+        // buffered shared words, so two barriers per iteration are enough.
+        const int w = threadIdx.x >> 5, g = w >> 2;
+        unsigned long long* cnt = quad + 16 * (quad_iter & 1);   // [0..7] per-warp packed counts, [8..9] per-group bases
+        if (lane == 0) cnt[w] = (unsigned long long)(unsigned)__popc(mc) | ((unsigned long long)(unsigned)(__popc(me) + __popc(ma)) << 32);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        if ((w & 3) == 0 && lane == 0) {
+            const unsigned long long tot = cnt[w] + cnt[w + 1] + cnt[w + 2] + cnt[w + 3];
+            cnt[8 + g] = tot ? atomicAdd(&ctl->tk[cur], tot) : 0ull;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        unsigned long long base = cnt[8 + g];
+        for (int k = 4 * g; k < w; k++) base += cnt[k];
+        bc = (int)(base & 0xffffffffull); bs = (int)(base >> 32);
+    } else {
+        if (lane == leader && (mc | me | ma)) ctl_draw_tickets(ctl, cur, __popc(mc), __popc(me) + __popc(ma), bc, bs);
+        bc = __shfl_sync(am, bc, leader);
+        bs = __shfl_sync(am, bs, leader);
     }
-    bc = __shfl_sync(am, bc, leader);
-    bs = __shfl_sync(am, bs, leader);
     const unsigned below = (1u << lane) - 1u;
     if (cont) {
         char* out = pool.records(cur ^ 1) + (size_t)(bc + __popc(mc & below)) * RTX_REC_BYTES;
@@ -670,6 +706,12 @@ __device__ __forceinline__ void shade_commit(Ctl* ctl, const Pool& pool, const i
 #ifndef RTX_SHADE_BLOCKS_LEAN
 #define RTX_SHADE_BLOCKS_LEAN RTX_SHADE_BLOCKS
 #endif
+#ifndef RTX_SHADE_PIPELINE
+#define RTX_SHADE_PIPELINE 1
+#endif
+#ifndef RTX_SHADE_QUAD_TICKETS
+#define RTX_SHADE_QUAD_TICKETS 1
+#endif
 template <int QT, unsigned FEAT = RTX_F_ALL>
 __global__ void __launch_bounds__(256, FEAT != RTX_F_ALL ? RTX_SHADE_BLOCKS_LEAN : QT < 0 ? RTX_SHADE_BLOCKS : (QT == Q_LAMBERTIAN ? RTX_SHADE_BLOCKS : RTX_SHADE_BLOCKS_Q)) k_shade(Ctl* ctl, Pool pool, int cur, DevScene S, DevCamera C, PassParams pp) {
   const int n_items = QT < 0 ? ctl->n_active : ctl->n_mat[QT < 0 ? 0 : QT];
@@ -700,6 +742,45 @@ __global__ void __launch_bounds__(256, FEAT != RTX_F_ALL ? RTX_SHADE_BLOCKS_LEAN
       // shading queue comes out of the hit record. The material-sorted order costs this HBM-bound kernel its bandwidth (gathers through the
       // queues: 44 % of the copy peak over a pass) and costs the trace kernel an atomic round trip per retire round; what it buys — warps of
       // one material — matters little to a kernel that issues 18 % of the time.
+#if RTX_SHADE_PIPELINE
+      // Software pipeline: the records of this thread's NEXT element are requested before this element's commit, so that the round trip of
+      // the commit's ticket atomics (41 % of the kernel's stall samples) and the latency of those loads (22 %) overlap instead of adding up.
+      D4 ro4, rd4, hn, hp, huv;
+      float4 th4;
+      auto request = [&](int k) {
+          const char* rec = pool.records(cur) + (size_t)k * RTX_REC_BYTES;
+          const char* hrec = pool.hit + (size_t)k * pool.hit_bytes;
+          ro4 = ld256d(rec); rd4 = ld256d(rec + 32); hn = ld256d(hrec + 32); th4 = ldrec4(rec + 64); hp = ld256d(hrec);
+          if (S.n_images > 0) huv = ld256d(hrec + 64);
+      };
+      huv.x = huv.y = huv.z = huv.w = 0.0;
+      if (i < n_items) request(i);
+#if RTX_SHADE_QUAD_TICKETS
+      __shared__ unsigned long long quad_words[32];
+      const int n_quad = (n_items + 127) & ~127;   // the four warps of a ticket group make the same number of trips
+      for (int it = 0; i < n_quad; i += stride, it++) {
+#else
+      for (; i < n_rounded; i += stride) {
+#endif
+          ShadeVars V;
+          V.reset();
+          if (i < n_items) {
+              V.tm = ro4.w; V.pixbits = rd4.w;
+              V.th = th4;
+              const long long bits = __double_as_longlong(hn.w);
+              const int type = (int)((bits >> 28) & 7);
+              const D3 P = type != Q_MISS ? d3(hp.x, hp.y, hp.z) : d3(0, 0, 0);
+              const double hu = (S.n_images > 0 && type != Q_MISS) ? huv.x : 0.0, hv = (S.n_images > 0 && type != Q_MISS) ? huv.y : 0.0;
+              shade_element<FEAT>(S, C, pp, pool, type, d3(rd4.x, rd4.y, rd4.z), P, d3(hn.x, hn.y, hn.z), hu, hv, (int)(bits & 0x0fffffff), (bits >> 31) & 1, V);
+          }
+          if (i + stride < n_items) request(i + stride);
+#if RTX_SHADE_QUAD_TICKETS
+          shade_commit(ctl, pool, cur, V, quad_words, it);
+#else
+          shade_commit(ctl, pool, cur, V);
+#endif
+      }
+#else
       for (; i < n_rounded; i += stride) {
           ShadeVars V;
           V.reset();
@@ -722,6 +803,7 @@ __global__ void __launch_bounds__(256, FEAT != RTX_F_ALL ? RTX_SHADE_BLOCKS_LEAN
           }
           shade_commit(ctl, pool, cur, V);
       }
+#endif
       return;
   }
   int type_next = -1;
@@ -774,12 +856,20 @@ __global__ void __launch_bounds__(256, FEAT != RTX_F_ALL ? RTX_SHADE_BLOCKS_LEAN
 // shades it (same shade_element, same Philox counters: the paths are the ones the separate kernels produce) and appends the survivor. The hit
 // record (64 B written, 64 B read), the queue slot and the second read of the path record disappear — for these scenes both separate kernels
 // are HBM-bound (profiles/r01_k_shade_hdri.md) — at the price of shading without material-sorted warps.
+#ifndef RTX_BOUNCE_QUAD_TICKETS
+#define RTX_BOUNCE_QUAD_TICKETS 1
+#endif
 template <bool UV, unsigned FEAT = RTX_F_ALL>
 struct BouncePolicyT {
     static constexpr bool ANY_HIT = false, CONTINUES = false;
+    // one ticket atomic per four warps (shade_commit; blocks are 256 threads) — for the SKY vocabulary only: hdri-test 64 spp 73.3 -> 67.2 ms (its
+    // launch of 16.7 M rays drew 520 K tickets from one word in a millisecond, the L2's rate for one address); where the rays of a warp differ
+    // in length the barriers cost more than the atomics did (cornell-glossy 14.1 -> 14.5 ms, earth 1.8 -> 1.9 ms)
+    static constexpr bool QUAD_TICKETS = RTX_BOUNCE_QUAD_TICKETS != 0 && FEAT == RTX_FV_SKY;
     Ctl* ctl; Pool pool; int cur; const DevScene* S; const DevCamera* C; PassParams pp;
     int n_cont; unsigned long long gen_base;   // jobs >= n_cont are fresh camera paths: generated here, never written as records
     mutable double pixbits_; mutable float4 th_;   // identity and throughput | flags of the job this thread is working on (load -> retire)
+    unsigned long long* quad = nullptr; mutable int trip = 0;   // shared words of the ticket groups, loop trips so far (their double-buffer index)
     __device__ __forceinline__ double tmin() const { return 0.001; }  // rt/camera.go:451
     __device__ __forceinline__ void prefetch(int job) const {
         if (job >= n_cont) return;   // a fresh camera path: generated, not loaded
@@ -825,7 +915,8 @@ struct BouncePolicyT {
             }
             shade_element<FEAT>(*S, *C, pp, pool, type, d3(r.dx, r.dy, r.dz), hi.P, hi.N, UV ? hi.u : 0.0, UV ? hi.v : 0.0, hi.mat, hi.front, V);
         }
-        shade_commit(ctl, pool, cur, V);
+        if (QUAD_TICKETS) shade_commit(ctl, pool, cur, V, quad, trip++);
+        else shade_commit(ctl, pool, cur, V);
     }
 };
 
@@ -838,7 +929,8 @@ struct BouncePolicyT {
 #endif
 template <bool COUNT, bool UV = false, unsigned FEAT = RTX_F_ALL>
 __global__ void __launch_bounds__(256, (FEAT & RTX_F_COMPLEX) ? RTX_BOUNCE_BLOCKS : RTX_BOUNCE_BLOCKS_LEAN) k_bounce_flat(Ctl* ctl, Pool pool, int cur, const __grid_constant__ DevScene S, const __grid_constant__ DevCamera C, PassParams pp) {
-    BouncePolicyT<UV, FEAT> P{ctl, pool, cur, &S, &C, pp, ctl->n_cont, ctl->gen_base, 0.0, make_float4(0.f, 0.f, 0.f, 0.f)};
+    __shared__ unsigned long long quad_words[32];
+    BouncePolicyT<UV, FEAT> P{ctl, pool, cur, &S, &C, pp, ctl->n_cont, ctl->gen_base, 0.0, make_float4(0.f, 0.f, 0.f, 0.f), quad_words, 0};
     TraceCounters tc = {0, 0, 0, 0, 0};
     const int n = ctl->n_active;
     trace_flat<BouncePolicyT<UV, FEAT>, COUNT, FEAT>(S, P, n, tc);
@@ -966,7 +1058,7 @@ struct DrainPolicyT {
         int bs = 0;
         const int bmin = __reduce_min_sync(am, valid ? V.bounce0 : 0x7fffffff), bmax = __reduce_max_sync(am, valid ? V.bounce0 : -1);
         if (lane == leader) {
-            if (me | ma) bs = atomicAdd(&ctl->n_shadow[par], __popc(me) + __popc(ma));
+            if (me | ma) { int unused; ctl_draw_tickets(ctl, par, 0, __popc(me) + __popc(ma), unused, bs); }
             if (mv) {
                 atomicAdd(&ctl->ext_rays, (unsigned long long)__popc(mv));
                 if (bmin < ctl->drain_bounce_min) atomicMin(&ctl->drain_bounce_min, bmin);
@@ -1008,18 +1100,20 @@ __global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_DRAIN_BLOCKS_OF(FEAT)) 
                                                                               const __grid_constant__ DevCamera C, const __grid_constant__ PassParams pp, int* spill) {
     DrainPolicyT<UV, FEAT> P{ctl, &pool, cur, par, &S, &C, &pp};
     TraceCounters tc = {0, 0, 0, 0, 0};
-    trace_persistent<DrainPolicyT<UV, FEAT>, false, RTX_TRACE_SLOTS_OF(FEAT), FEAT>(S, P, &ctl->cur_extend, ctl->n_next, tc, spill, rtx_smem);
+    trace_persistent<DrainPolicyT<UV, FEAT>, false, RTX_TRACE_SLOTS_OF(FEAT), FEAT>(S, P, &ctl->cur_extend, ctl->n_active, tc, spill, rtx_smem);
 }
 // before the drain: job cursor and shadow half; after it (and its k_connect): the books of the pass
-__global__ void k_drain_begin(Ctl* ctl, int par) {
+__global__ void k_drain_begin(Ctl* ctl, int par, int last_par) {   // last_par: parity of the last per-bounce iteration (its survivors are the drain's jobs)
     if (threadIdx.x != 0) return;
-    ctl->cur_extend = 0; ctl->n_shadow[par] = 0; ctl->cur_connect[par] = 0;
+    ctl->n_active = ctl_survivors(ctl, last_par);
+    ctl->tk[0] = 0; ctl->tk[1] = 0;
+    ctl->cur_extend = 0; ctl->cur_connect[par] = 0;
     ctl->drain_bounce_min = 0x7fffffff; ctl->drain_bounce_max = -1;
     if (ctl->t_tail_begin == 0) ctl->t_tail_begin = rtx_globaltimer();
 }
 __global__ void k_drain_end(Ctl* ctl) {
     if (threadIdx.x != 0) return;
-    ctl->n_next = 0; ctl->n_active = 0; ctl->done = 1;
+    ctl->tk[0] = 0; ctl->tk[1] = 0; ctl->n_active = 0; ctl->done = 1;
     // the bounce rounds the launch covered count as the wavefront iterations they replaced
     const int rounds = ctl->drain_bounce_max >= ctl->drain_bounce_min ? ctl->drain_bounce_max - ctl->drain_bounce_min + 1 : 1;
     ctl->iterations += rounds; ctl->tail_iterations += rounds;
@@ -1070,7 +1164,7 @@ template <bool COUNT, unsigned FEAT = RTX_F_ALL>
 __global__ void __launch_bounds__(RTX_TRACE_THREADS, RTX_TRACE_BLOCKS_OF(FEAT)) k_connect(Ctl* ctl, Pool pool, int par, const __grid_constant__ DevScene S, PassParams pp, int* spill) {
     ConnectPolicy P{pool, pp.seed_lo, pp.seed_hi};
     TraceCounters tc = {0, 0, 0, 0, 0};
-    const int n = ctl->n_shadow[par];
+    const int n = ctl_shadow(ctl, par);
     trace_persistent<ConnectPolicy, COUNT, RTX_TRACE_SLOTS_OF(FEAT), FEAT>(S, P, &ctl->cur_connect[par], n, tc, spill, rtx_smem);
     if (COUNT) flush_counters(ctl, tc);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->shadow_rays, (unsigned long long)n);
@@ -1080,7 +1174,7 @@ template <unsigned FEAT = RTX_F_ALL>
 __global__ void __launch_bounds__(256) k_connect_simple(Ctl* ctl, Pool pool, int par, const __grid_constant__ DevScene S, PassParams pp) {
     ConnectPolicy P{pool, pp.seed_lo, pp.seed_hi};
     TraceCounters tc = {0, 0, 0, 0, 0};
-    const int n = ctl->n_shadow[par];
+    const int n = ctl_shadow(ctl, par);
     trace_simple<ConnectPolicy, false, FEAT>(S, P, n, tc);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->shadow_rays, (unsigned long long)n);
 }
@@ -1089,7 +1183,7 @@ template <bool COUNT, unsigned FEAT = RTX_F_ALL>
 __global__ void __launch_bounds__(256) k_connect_flat(Ctl* ctl, Pool pool, int par, const __grid_constant__ DevScene S, PassParams pp) {
     ConnectPolicy P{pool, pp.seed_lo, pp.seed_hi};
     TraceCounters tc = {0, 0, 0, 0, 0};
-    const int n = ctl->n_shadow[par];
+    const int n = ctl_shadow(ctl, par);
     trace_flat<ConnectPolicy, COUNT, FEAT>(S, P, n, tc);
     if (COUNT) flush_counters(ctl, tc);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->shadow_rays, (unsigned long long)n);

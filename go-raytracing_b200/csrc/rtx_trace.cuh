@@ -325,11 +325,15 @@ bool entry_other(const DevScene* Sp, unsigned char* smem, int s, int ei, double 
 // reference's HittableList.Hit loop itself — one thread per ray, every entry in turn, no pool, no stack, no divergence
 // between lanes beyond the tests' own early-outs. Results are identical to the hierarchy's (closest hits do not depend on
 // the order of the tests; exact ties are resolved by rank as everywhere).
+// a policy whose retire is collective over groups of FOUR warps (shade_commit's quad tickets) says so with QUAD_TICKETS = true
+template <class P, class = void> struct policy_quad_tickets { static constexpr bool value = false; };
+template <class P> struct policy_quad_tickets<P, decltype((void)P::QUAD_TICKETS)> { static constexpr bool value = P::QUAD_TICKETS; };
 template <class Policy, bool COUNT, unsigned FEAT = RTX_F_ALL>
 __device__ __forceinline__ void trace_flat(const DevScene& S, Policy& P, int njobs, TraceCounters& tc) {
     TraceCounters* const tcp = COUNT ? &tc : nullptr;
     const double tmin = P.tmin();
-    const int nrounded = (njobs + 31) & ~31;   // whole warps reach the warp-collective retire
+    // whole warps (or whole groups of four warps) reach the collective retire
+    const int nrounded = policy_quad_tickets<Policy>::value ? (njobs + 127) & ~127 : (njobs + 31) & ~31;
     for (int job = blockIdx.x * blockDim.x + threadIdx.x; job < nrounded; job += gridDim.x * blockDim.x) {
         const bool valid = job < njobs;
         RayD r;
