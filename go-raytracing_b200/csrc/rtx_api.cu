@@ -105,7 +105,7 @@ struct rtx_ctx {
     int count_stats = 0, time_kernels = 1, blas_leaf = 4;
     float4* per_sample = nullptr; size_t per_sample_cap = 0;   // moments mode: per-sample radiance sums of the running pass (grow-only)
     int flat_max_entries = 16, scene_flat = 0, scene_has_mesh = 0;   // worlds of <= flat_max_entries entries without a mesh are traced by the flat kernels (trace_flat)
-    int pixel_major = 1;  // path order of k_generate: all samples of a pixel consecutively (1) or sample-major (0)
+    int pixel_major = 1;  // path order of k_generate: tiles of 32 neighbouring pixels, all their samples consecutively (1, generate_path); all samples of one pixel consecutively (2); sample-major (0)
     int tri_pretest = RTX_TRI_PRETEST;      // mesh worlds: float32 pre-test records for the TRI phase (takes effect at the next rtx_scene_upload)
     int fuse_drain = RTX_FUSE_DRAIN_DEFAULT;   // hierarchy worlds: the last iterations of a pass run as ONE barrier-free persistent launch (k_drain) once at most this many rays are left (0 = off)
     int shade_direct = RTX_SHADE_DIRECT_DEFAULT;   // hierarchy worlds: k_shade in stream order instead of through material-sorted queues
@@ -432,7 +432,7 @@ static int32_t set_option_single(rtx_ctx* ctx, const char* key, int64_t value) {
     } else if (k == "count_stats") ctx->count_stats = (int)value;  // bit 0: extend kernel, bit 1: connect kernel
     else if (k == "time_kernels") ctx->time_kernels = value != 0;
     else if (k == "l2_persist") { ctx->l2_persist = value != 0; ctx->window_set = false; }  // L2 persisting window over the scene geometry (default off)
-    else if (k == "pixel_major") ctx->pixel_major = value != 0;
+    else if (k == "pixel_major") ctx->pixel_major = value < 0 ? 0 : value > 2 ? 2 : (int)value;   // 0 sample-major, 1 tiles of 32 pixels (default), 2 pixel-major
     else if (k == "fuse_flat") ctx->fuse_flat = value != 0;
     else if (k == "shade_split") ctx->shade_split = value != 0;
     else if (k == "fuse_tree") ctx->fuse_tree = value != 0;

@@ -201,7 +201,22 @@ __device__ __forceinline__ RayD generate_path(const DevCamera& C, const PassPara
     // path order: pixel-major (all samples of a pixel are consecutive paths) keeps the pixels in flight few, so the radiance
     // atomics stay in L2 and neighbouring lanes start with nearly the same ray; sample-major is the other order
     uint32_t sample, pixel;
-    if (pp.pixel_major) { pixel = (uint32_t)(pid / (unsigned)pp.spp); sample = pp.sample_base + (uint32_t)(pid % (unsigned)pp.spp); }
+    if (pp.pixel_major == 1) {
+        // TILE order (default): the 32 lanes of a warp are 32 neighbouring pixels at the same sample index, consecutive warps walk the samples
+        // of that tile. The pixels in flight stay as few as in pixel-major order, but a warp's radiance atomics go to 32 different words (one
+        // 512-byte run of the accumulation buffer) instead of 32 times to the same one, which the L2 serialises.
+        const unsigned long long per_tile = 32ull * (unsigned)pp.spp, full = npix / 32u;
+        const unsigned long long tile = pid / per_tile;
+        if (tile < full) {
+            const unsigned within = (unsigned)(pid - tile * per_tile);
+            pixel = (uint32_t)tile * 32u + (within & 31u); sample = pp.sample_base + (within >> 5);
+        } else {   // the last npix % 32 pixels
+            const unsigned rest = npix - (unsigned)full * 32u;
+            const unsigned long long q = pid - full * per_tile;
+            pixel = (uint32_t)full * 32u + (uint32_t)(q % rest); sample = pp.sample_base + (uint32_t)(q / rest);
+        }
+    }
+    else if (pp.pixel_major) { pixel = (uint32_t)(pid / (unsigned)pp.spp); sample = pp.sample_base + (uint32_t)(pid % (unsigned)pp.spp); }
     else { sample = pp.sample_base + (uint32_t)(pid / npix); pixel = (uint32_t)(pid % npix); }
     int px = pixel % C.width, py = pixel / C.width;
     uint4 r0 = philox4x32(pixel, sample, 0, STREAM_CAMERA, pp.seed_lo, pp.seed_hi);

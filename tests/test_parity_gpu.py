@@ -819,6 +819,14 @@ def test_full_size_lucy_properties(grt, ctx):
     finally:
         c2.close()
     assert np.all(n3 == 6) and np.allclose(full, other, rtol=5e-5, atol=2e-5)
+    # the default path order walks tiles of 32 neighbouring pixels (810 000 pixels: 25 312 tiles and 16 left over); strict pixel-major is option 2
+    ctx.set_option("pixel_major", 2)
+    try:
+        ctx.clear(); ctx.render_pass(6, 50, seed=77)
+        strict, _, n4 = ctx.resolve_accum()
+    finally:
+        ctx.set_option("pixel_major", 1)
+    assert np.all(n4 == 6) and np.allclose(full, strict, rtol=5e-5, atol=2e-5)
 
 
 def test_resolve_matches_reference_pack(grt, orc, ctx):
