@@ -315,7 +315,9 @@ int32_t rtx_get_stats(rtx_ctx* ctx, rtx_stats* out);
  * wavefront iteration, default 1; the pass is complete on the context's stream when rtx_render_pass returns either way), "count_stats" (per-ray traversal counters: bit 0 extension rays, bit 1 shadow
  * rays), "time_kernels" (CUDA-event time per kernel kind, default 1), "lean" (kernel variants compiled per scene vocabulary, default 1; 0 = all-features kernels), "fuse_tree" (hierarchy worlds shade inside the persistent trace
  * kernel, default 0), "pretest_bare" (bare primitives beside a mesh are tested at pool entry instead of through the TLAS, default 0;
- * takes effect at the next rtx_scene_upload), "tlas_flat_max", "shade_direct", "tri_pretest", "simple_below", "fuse_drain" (DESIGN.md sections 4 and 6), "drop_caches".
+ * takes effect at the next rtx_scene_upload), "tlas_flat_max", "shade_direct", "tri_pretest", "simple_below", "fuse_drain" (DESIGN.md sections 4 and 6), "drop_caches",
+ * "pixel_major" (order of the camera paths of a pass: 1 = tiles of 32 neighbouring pixels, all their samples consecutively - the default;
+ * 2 = all samples of one pixel consecutively; 0 = sample-major. The image does not depend on it beyond float32 summation order).
  * Returns RTX_ERR_INVALID for unknown keys. */
 int32_t rtx_set_option(rtx_ctx* ctx, const char* key, int64_t value);
 
