@@ -264,3 +264,28 @@ def test_obj_parse_of_the_benchmark_mesh(grt):
     v8, t8, s8 = grt.parse_obj(path, threads=0)
     assert len(t1) >= 270000 and np.array_equal(v1, v8) and np.array_equal(t1, t8)
     print(f"lucy stand-in: {len(v1)} vertices, {len(t1)} triangles; parse {s1 * 1e3:.0f} ms on 1 thread, {s8 * 1e3:.0f} ms on all")
+
+
+def test_tile_path_order_visits_every_sample_once():
+    """generate_path (csrc/rtx_kernels.cuh), pixel_major = 1: path p of a pass of `spp` samples over `npix` pixels is pixel
+    32 (p / 32 spp) + p % 32 at sample (p / 32) % spp, the last npix % 32 pixels handled as one narrower tile. Restated here to pin the
+    claim the kernel's comment makes: a bijection onto (pixel, sample), a warp of 32 consecutive paths = 32 neighbouring pixels at one
+    sample. (The device code itself is exercised by test_full_size_lucy_properties: per-pixel sample counts on a frame of 810 000 pixels.)"""
+    def order(p, npix, spp):
+        per_tile, full = 32 * spp, npix // 32
+        tile = p // per_tile
+        if tile < full:
+            within = p - tile * per_tile
+            return tile * 32 + (within & 31), within >> 5
+        rest = npix - full * 32
+        q = p - full * per_tile
+        return full * 32 + q % rest, q // rest
+    for npix, spp in ((64, 3), (90000, 2), (810000 % 4096 + 4096, 5), (31, 7), (33, 1), (1200 * 3, 37)):
+        seen = np.zeros((npix, spp), dtype=np.int32)
+        for p in range(npix * spp):
+            px, s = order(p, npix, spp)
+            seen[px, s] += 1
+        assert (seen == 1).all(), (npix, spp)
+        if npix >= 64:
+            first = [order(p, npix, spp) for p in range(32)]
+            assert [px for px, _ in first] == list(range(32)) and {s for _, s in first} == {0}
