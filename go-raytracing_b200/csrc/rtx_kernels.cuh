@@ -662,8 +662,9 @@ __device__ __forceinline__ void shade_commit(Ctl* ctl, const Pool& pool, const i
     const int bounce0 = V.bounce0;
     const float3 env_c = V.env_c, area_c = V.area_c;
     // Survivors go to the next free records of the other buffer, shadow requests to this iteration's half, in the order the warps arrive.
-    // Both tickets are drawn by one lane BACK TO BACK (one atomic per counter per warp; the two round trips to L2 overlap) before any
-    // lane uses either: with three dependent warp_append calls this HBM-bound kernel spent its time waiting on atomic returns.
+    // Both tickets come from ONE 64-bit atomic (ctl_draw_tickets) drawn by one lane per warp — or, in quad mode, per four warps — before
+    // any lane uses either: with three dependent warp_append calls this HBM-bound kernel spent its time waiting on atomic returns, and
+    // with one atomic per counter and warp it ran at the L2's rate for same-address atomics.
     const unsigned am = __activemask();
     const unsigned mc = __ballot_sync(am, cont), me = __ballot_sync(am, has_env), ma = __ballot_sync(am, has_area);
     const int lane = threadIdx.x & 31, leader = __ffs(am) - 1;
