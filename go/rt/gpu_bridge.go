@@ -46,7 +46,7 @@ func (g *gpuContext) lastError() error {
 }
 
 func check(g *gpuContext, rc C.int32_t, what string) error {
-	if rc == C.RTX_OK {
+	if int32(rc) == int32(C.RTX_OK) { // (an enumerator: convert instead of relying on how cgo types it)
 		return nil
 	}
 	var msg string
